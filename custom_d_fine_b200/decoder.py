@@ -1,0 +1,466 @@
+"""DFINETransformer decoder graph (query selection, CDN, FDR decoder loop).
+
+Behaviour follows /root/reference/src/d_fine/arch/dfine_decoder.py (MSDeformableAttention
+49-178, TransformerDecoderLayer 181-255, Gate 258-271, Integral 274-295, LQE 298-313,
+TransformerDecoder 373-524, DFINETransformer 527-1108) and arch/utils.py
+(weighting_function 145-188, distance2bbox 119-142, CDN 357-467).
+Differences that are deliberate and value-preserving:
+  * memory / value stay token-major ``[B, L, heads*head_dim]`` — the reference's per-level
+    NCHW copies for grid_sample (utils.py:225) do not exist; the fused MSDA kernel gathers
+    128-byte head rows straight from ``memory``.
+  * sampling_offsets and attention_weights share one GEMM (concatenated weights).
+  * anchors / valid_mask / attention mask / dn indices are built on the device in closed
+    form (no per-step host build + H2D, no ``nonzero`` sync).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.init as init
+
+from .blocks import MLP, ConvUnit, mha
+from .kernels import K
+
+
+def inverse_sigmoid(x, eps=1e-5):
+    x = x.clip(min=0.0, max=1.0)
+    return torch.log(x.clip(min=eps) / (1 - x).clip(min=eps))
+
+
+def bias_init_with_prob(p=0.01):
+    return float(-math.log((1 - p) / p))
+
+
+def weighting_function(reg_max, up, reg_scale):
+    """Non-uniform FDR bin positions W(n), [reg_max+1] (arch/utils.py:145-188)."""
+    ub1 = abs(up[0]) * abs(reg_scale)
+    ub2 = ub1 * 2
+    step = (ub1 + 1) ** (2 / (reg_max - 2))
+    left = [-(step ** i) + 1 for i in range(reg_max // 2 - 1, 0, -1)]
+    right = [step ** i - 1 for i in range(1, reg_max // 2)]
+    return torch.cat([-ub2] + left + [torch.zeros_like(up[0][None])] + right + [ub2], 0)
+
+
+class DeformAttnParams(nn.Module):
+    """Parameter container for MS-deformable cross attention (keys: sampling_offsets,
+    attention_weights, num_points_scale)."""
+
+    def __init__(self, d, heads, levels, points):
+        super().__init__()
+        pts = list(points) if isinstance(points, (list, tuple)) else [points] * levels
+        assert len(pts) == levels
+        self.num_heads, self.num_levels, self.num_points_list = heads, levels, pts
+        self.head_dim = d // heads
+        self.offset_scale = 0.5
+        self.register_buffer("num_points_scale",
+                             torch.tensor([1.0 / n for n in pts for _ in range(n)], dtype=torch.float32))
+        tot = heads * sum(pts)
+        self.sampling_offsets = nn.Linear(d, tot * 2)
+        self.attention_weights = nn.Linear(d, tot)
+        # init (dfine_decoder.py:98-117): zero weights, per-head direction grid scaled by point idx
+        init.constant_(self.sampling_offsets.weight, 0)
+        th = torch.arange(heads, dtype=torch.float32) * (2.0 * math.pi / heads)
+        g = torch.stack([th.cos(), th.sin()], -1)
+        g = g / g.abs().max(-1, keepdim=True).values
+        g = g.reshape(heads, 1, 2).tile([1, sum(pts), 1])
+        g = g * torch.cat([torch.arange(1, n + 1) for n in pts]).reshape(1, -1, 1)
+        self.sampling_offsets.bias.data[...] = g.flatten()
+        init.constant_(self.attention_weights.weight, 0)
+        init.constant_(self.attention_weights.bias, 0)
+
+    def forward(self, query, ref, memory, spatial_shapes):
+        """query [B,Q,D]; ref [B,Q,4] cxcywh in [0,1]; memory [B,L,D] token-major."""
+        n_off = self.sampling_offsets.out_features
+        w = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
+        b = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
+        proj = K.linear(query, w, b)
+        return K.msda(memory, spatial_shapes, self.num_points_list, self.num_heads,
+                      proj[..., :n_off], proj[..., n_off:], ref, self.num_points_scale,
+                      self.offset_scale)
+
+
+class GateParams(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.gate = nn.Linear(2 * d, 2 * d)
+        init.constant_(self.gate.bias, bias_init_with_prob(0.5))
+        init.constant_(self.gate.weight, 0)
+        self.norm = nn.LayerNorm(d)
+
+    def forward(self, x1, x2):
+        g = K.linear(K.cat([x1, x2]), self.gate.weight, self.gate.bias)
+        return K.layernorm(K.gate_mix(g, x1, x2), self.norm.weight, self.norm.bias, self.norm.eps)
+
+
+class DecoderLayer(nn.Module):
+    def __init__(self, d, heads, ffn, levels, points):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(d, heads, dropout=0.0, batch_first=True)
+        self.norm1 = nn.LayerNorm(d)
+        self.cross_attn = DeformAttnParams(d, heads, levels, points)
+        self.gateway = GateParams(d)
+        self.linear1 = nn.Linear(d, ffn)
+        self.linear2 = nn.Linear(ffn, d)
+        self.norm3 = nn.LayerNorm(d)
+        init.xavier_uniform_(self.linear1.weight)
+        init.xavier_uniform_(self.linear2.weight)
+
+    def forward(self, tgt, ref, memory, spatial_shapes, attn_mask, qpos):
+        a = mha(self.self_attn, tgt + qpos, tgt, attn_mask)
+        tgt = K.layernorm(tgt + a, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        c = self.cross_attn(tgt + qpos, ref, memory, spatial_shapes)
+        tgt = self.gateway(tgt, c)
+        f = K.linear(tgt, self.linear1.weight, self.linear1.bias, act="relu")
+        f = K.linear(f, self.linear2.weight, self.linear2.bias)
+        return K.layernorm((tgt + f).clamp(min=-65504, max=65504),
+                           self.norm3.weight, self.norm3.bias, self.norm3.eps)
+
+
+class LQEParams(nn.Module):
+    def __init__(self, k, hidden, n_layers, reg_max):
+        super().__init__()
+        self.k, self.reg_max = k, reg_max
+        self.reg_conf = MLP(4 * (k + 1), hidden, 1, n_layers)
+        init.constant_(self.reg_conf.layers[-1].bias, 0)
+        init.constant_(self.reg_conf.layers[-1].weight, 0)
+
+    def forward(self, scores, corners):
+        return scores + self.reg_conf(K.lqe_stat(corners, self.k, self.reg_max))
+
+
+class DecoderStack(nn.Module):
+    """FDR refinement loop (dfine_decoder.py:429-524); ``layer_scale`` is 1 in every shipped
+    config so the wide-layer branch (468-476) is not built."""
+
+    def __init__(self, d, heads, ffn, levels, points, num_layers, reg_max, reg_scale, up, eval_idx):
+        super().__init__()
+        self.num_layers, self.reg_max = num_layers, reg_max
+        self.eval_idx = eval_idx if eval_idx >= 0 else num_layers + eval_idx
+        self.up, self.reg_scale = up, reg_scale  # aliases of the owner's parameters (same keys as reference)
+        self.layers = nn.ModuleList(DecoderLayer(d, heads, ffn, levels, points) for _ in range(num_layers))
+        self.lqe_layers = nn.ModuleList(LQEParams(4, 64, 2, reg_max) for _ in range(num_layers))
+
+    def forward(self, tgt, ref_unact, memory, spatial_shapes, bbox_head, score_head, qpos_head,
+                pre_bbox_head, attn_mask=None, return_queries=False):
+        project = weighting_function(self.reg_max, self.up, self.reg_scale)
+        out, out_detach, corners_prev = tgt, None, None
+        ref = torch.sigmoid(ref_unact)
+        boxes, logits, corners_all, refs, queries = [], [], [], [], []
+        for i, layer in enumerate(self.layers):
+            qpos = qpos_head(ref).clamp(min=-10, max=10)
+            out = layer(out, ref, memory, spatial_shapes, attn_mask, qpos)
+            if return_queries:
+                queries.append(out)
+            if i == 0:
+                pre_boxes = torch.sigmoid(pre_bbox_head(out) + inverse_sigmoid(ref))
+                pre_scores = K.linear(out, score_head[0].weight, score_head[0].bias)
+                ref_initial = pre_boxes.detach()
+            corners = bbox_head[i](out if out_detach is None else out + out_detach)
+            if corners_prev is not None:
+                corners = corners + corners_prev
+            box = K.fdr_decode(corners, ref_initial, project, self.reg_scale)
+            if self.training or i == self.eval_idx:
+                s = K.linear(out, score_head[i].weight, score_head[i].bias)
+                logits.append(self.lqe_layers[i](s, corners))
+                boxes.append(box)
+                corners_all.append(corners)
+                refs.append(ref_initial)
+                if not self.training:
+                    break
+            corners_prev, ref, out_detach = corners, box.detach(), out.detach()
+        hs = torch.stack(queries) if return_queries else None
+        return (torch.stack(boxes), torch.stack(logits), torch.stack(corners_all), torch.stack(refs),
+                pre_boxes, pre_scores, hs)
+
+
+def make_denoising_group(targets, num_classes, num_queries, class_embed, num_denoising=100,
+                         label_noise_ratio=0.5, box_noise_scale=1.0):
+    """Contrastive denoising queries (arch/utils.py:357-467).
+
+    The four RNG draws (rand_like int32->float, randint_like int32, randint_like float,
+    rand_like float) are issued with the same shapes/dtypes/order as the reference so that
+    both consume the torch generator identically; everything else is closed-form.
+    """
+    if num_denoising <= 0:
+        return None, None, None, None
+    num_gts = [len(t["labels"]) for t in targets]
+    device = targets[0]["labels"].device
+    max_gt = max(num_gts)
+    if max_gt == 0:
+        return None, None, None, {"dn_positive_idx": None, "dn_num_group": 0, "dn_num_split": [0, num_queries]}
+    groups = max(num_denoising // max_gt, 1)
+    bs = len(num_gts)
+    cls = torch.full([bs, max_gt], num_classes, dtype=torch.int32, device=device)
+    box = torch.zeros([bs, max_gt, 4], device=device)
+    valid = torch.zeros([bs, max_gt], dtype=torch.bool, device=device)
+    for i, n in enumerate(num_gts):
+        if n > 0:
+            cls[i, :n] = targets[i]["labels"]
+            box[i, :n] = targets[i]["boxes"]
+            valid[i, :n] = True
+    cls = cls.tile([1, 2 * groups])
+    box = box.tile([1, 2 * groups, 1])
+    valid = valid.tile([1, 2 * groups])
+    n_dn = int(max_gt * 2 * groups)
+    pos_in_group = torch.arange(n_dn, device=device) % (2 * max_gt)
+    neg = (pos_in_group >= max_gt).to(box.dtype).reshape(1, n_dn, 1)  # second half of each group
+    g_idx = torch.arange(groups, device=device)[:, None] * (2 * max_gt)
+    dn_positive_idx = tuple((g_idx + torch.arange(n, device=device)[None]).flatten() for n in num_gts)
+
+    if label_noise_ratio > 0:
+        flip = torch.rand_like(cls, dtype=torch.float) < (label_noise_ratio * 0.5)
+        new_label = torch.randint_like(flip, 0, num_classes, dtype=cls.dtype)
+        cls = torch.where(flip & valid, new_label, cls)
+    if box_noise_scale > 0:
+        half = box[..., 2:].clamp(min=0.0) * 0.5
+        xyxy = torch.cat([box[..., :2] - half, box[..., :2] + half], -1)
+        diff = torch.tile(box[..., 2:] * 0.5, [1, 1, 2]) * box_noise_scale
+        sign = torch.randint_like(box, 0, 2) * 2.0 - 1.0
+        part = torch.rand_like(box)
+        part = (part + 1.0) * neg + part * (1 - neg)
+        xyxy = torch.clip(xyxy + sign * part * diff, min=0.0, max=1.0)
+        box = torch.cat([(xyxy[..., :2] + xyxy[..., 2:]) / 2, xyxy[..., 2:] - xyxy[..., :2]], -1)
+        box = torch.where(box < 0, -box, box)
+        box_unact = inverse_sigmoid(box)
+    content = torch.nn.functional.embedding(cls, class_embed.weight, padding_idx=class_embed.padding_idx)
+
+    total = n_dn + num_queries
+    grp = torch.arange(total, device=device) // (2 * max_gt)
+    is_dn = torch.arange(total, device=device) < n_dn
+    # True = blocked: matching queries never see dn queries; a dn query only sees its own group
+    # (and all matching queries).
+    mask = is_dn[None, :] & (~is_dn[:, None] | (grp[:, None] != grp[None, :]))
+    meta = {"dn_positive_idx": dn_positive_idx, "dn_num_group": groups, "dn_num_split": [n_dn, num_queries]}
+    return content, box_unact, mask, meta
+
+
+class DFINETransformer(nn.Module):
+    def __init__(self, num_classes=80, hidden_dim=256, num_queries=300, feat_channels=(512, 1024, 2048),
+                 feat_strides=(8, 16, 32), num_levels=3, num_points=4, nhead=8, num_layers=6,
+                 dim_feedforward=1024, dropout=0.0, activation="relu", num_denoising=100,
+                 label_noise_ratio=0.5, box_noise_scale=1.0, learn_query_content=False,
+                 eval_spatial_size=None, eval_idx=-1, eps=1e-2, aux_loss=True,
+                 cross_attn_method="default", query_select_method="default", reg_max=32, reg_scale=4.0,
+                 layer_scale=1, enable_mask_head=False, mask_dim=256):
+        super().__init__()
+        assert dropout == 0.0 and activation == "relu" and layer_scale == 1
+        assert cross_attn_method == "default" and query_select_method == "default"
+        assert not learn_query_content
+        feat_strides = list(feat_strides)
+        assert len(feat_channels) <= num_levels and len(feat_strides) == len(feat_channels)
+        for _ in range(num_levels - len(feat_strides)):
+            feat_strides.append(feat_strides[-1] * 2)
+        self.hidden_dim, self.nhead, self.feat_strides = hidden_dim, nhead, feat_strides
+        self.num_levels, self.num_classes, self.num_queries = num_levels, num_classes, num_queries
+        self.eps, self.num_layers, self.eval_spatial_size = eps, num_layers, eval_spatial_size
+        self.aux_loss, self.reg_max, self.mask_dim = aux_loss, reg_max, mask_dim
+        self.enable_mask_head = enable_mask_head
+        self.query_select_method = query_select_method
+        self._anchor_cache = {}
+
+        self.input_proj = nn.ModuleList()
+        for c in feat_channels:
+            self.input_proj.append(nn.Identity() if c == hidden_dim else
+                                   ConvUnit(c, hidden_dim, 1, norm_name="norm"))
+        c = feat_channels[-1]
+        for _ in range(num_levels - len(feat_channels)):
+            if c == hidden_dim:
+                self.input_proj.append(nn.Identity())
+            else:
+                self.input_proj.append(ConvUnit(c, hidden_dim, 3, 2, norm_name="norm"))
+                c = hidden_dim
+
+        self.up = nn.Parameter(torch.tensor([0.5]), requires_grad=False)
+        # NB: the size tables pass a Python int, so this is an int64 Parameter exactly like the
+        # reference's (dfine_decoder.py:592).
+        self.reg_scale = nn.Parameter(torch.tensor([reg_scale]), requires_grad=False)
+        self.decoder = DecoderStack(hidden_dim, nhead, dim_feedforward, num_levels, num_points, num_layers,
+                                    reg_max, self.reg_scale, self.up, eval_idx)
+        self.num_denoising, self.label_noise_ratio = num_denoising, label_noise_ratio
+        self.box_noise_scale = box_noise_scale
+        if num_denoising > 0:
+            self.denoising_class_embed = nn.Embedding(num_classes + 1, hidden_dim, padding_idx=num_classes)
+            init.normal_(self.denoising_class_embed.weight[:-1])
+        if enable_mask_head:
+            from .mask_head import MaskDecoder
+            self.mask_decoder = MaskDecoder(list(feat_channels), mask_dim)
+            self.mask_head = MLP(hidden_dim, hidden_dim, mask_dim, 3)
+        self.query_pos_head = MLP(4, 2 * hidden_dim, hidden_dim, 2)
+        self.enc_output = nn.Sequential()
+        self.enc_output.add_module("proj", nn.Linear(hidden_dim, hidden_dim))
+        self.enc_output.add_module("norm", nn.LayerNorm(hidden_dim))
+        self.enc_score_head = nn.Linear(hidden_dim, num_classes)
+        self.enc_bbox_head = MLP(hidden_dim, hidden_dim, 4, 3)
+        self.eval_idx = eval_idx if eval_idx >= 0 else num_layers + eval_idx
+        self.dec_score_head = nn.ModuleList(nn.Linear(hidden_dim, num_classes) for _ in range(num_layers))
+        self.pre_bbox_head = MLP(hidden_dim, hidden_dim, 4, 3)
+        self.dec_bbox_head = nn.ModuleList(
+            MLP(hidden_dim, hidden_dim, 4 * (reg_max + 1), 3) for _ in range(num_layers))
+        if eval_spatial_size:
+            a, v = self._anchors_for(None, "cpu")
+            self.register_buffer("anchors", a)
+            self.register_buffer("valid_mask", v)
+        self._init_heads(feat_channels)
+
+    def _init_heads(self, feat_channels):
+        prior = bias_init_with_prob(0.01)
+        init.constant_(self.enc_score_head.bias, prior)
+        for head in (self.enc_bbox_head, self.pre_bbox_head, *self.dec_bbox_head):
+            init.constant_(head.layers[-1].weight, 0)
+            init.constant_(head.layers[-1].bias, 0)
+        for cls in self.dec_score_head:
+            init.constant_(cls.bias, prior)
+        init.xavier_uniform_(self.enc_output[0].weight)
+        init.xavier_uniform_(self.query_pos_head.layers[0].weight)
+        init.xavier_uniform_(self.query_pos_head.layers[1].weight)
+        for m, c in zip(self.input_proj, feat_channels):
+            if c != self.hidden_dim:
+                init.xavier_uniform_(m.conv.weight)
+
+    # ---- anchors -------------------------------------------------------------------------
+    def _anchors_for(self, spatial_shapes, device, grid_size=0.05):
+        """logit-space anchors [1,L,4] + validity [1,L,1] (dfine_decoder.py:803-826)."""
+        if spatial_shapes is None:
+            eh, ew = self.eval_spatial_size
+            spatial_shapes = [[int(eh / s), int(ew / s)] for s in self.feat_strides]
+        per_level = []
+        for lvl, (h, w) in enumerate(spatial_shapes):
+            gy, gx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+            xy = (torch.stack([gx, gy], -1).unsqueeze(0) + 0.5) / torch.tensor([w, h], dtype=torch.float32)
+            wh = torch.ones_like(xy) * grid_size * (2.0 ** lvl)
+            per_level.append(torch.cat([xy, wh], -1).reshape(-1, h * w, 4))
+        a = torch.cat(per_level, 1).to(device)
+        valid = ((a > self.eps) * (a < 1 - self.eps)).all(-1, keepdim=True)
+        a = torch.log(a / (1 - a))
+        return torch.where(valid, a, torch.inf), valid
+
+    def _anchors(self, spatial_shapes, device):
+        if not self.training and self.eval_spatial_size is not None:
+            return self.anchors, self.valid_mask
+        # train mode: the reference regenerates on the host + H2D each step (814-815); values only
+        # depend on the shapes, so cache per (shapes, device).
+        key = (tuple(map(tuple, spatial_shapes)), str(device))
+        if key not in self._anchor_cache:
+            self._anchor_cache[key] = self._anchors_for(spatial_shapes, device)
+        return self._anchor_cache[key]
+
+    # ---- stages ----------------------------------------------------------------------------
+    def _memory(self, feats):
+        proj = [p(f) if isinstance(p, ConvUnit) else f for p, f in zip(self.input_proj, feats)]
+        for i in range(len(proj), self.num_levels):
+            src = feats[-1] if i == len(feats) else proj[-1]
+            p = self.input_proj[i]
+            proj.append(p(src) if isinstance(p, ConvUnit) else src)
+        shapes = [[f.shape[1], f.shape[2]] for f in proj]
+        tokens = [f.reshape(f.shape[0], -1, f.shape[3]) for f in proj]   # NHWC -> [B, HW, C] is a view
+        return K.cat(tokens, dim=1), shapes
+
+    def _query_selection(self, memory, shapes, dn_content, dn_box_unact):
+        anchors, valid = self._anchors(shapes, memory.device)
+        mem = valid.to(memory.dtype) * memory
+        om = K.linear(mem, self.enc_output.proj.weight, self.enc_output.proj.bias)
+        om = K.layernorm(om, self.enc_output.norm.weight, self.enc_output.norm.bias, self.enc_output.norm.eps)
+        enc_logits = K.linear(om, self.enc_score_head.weight, self.enc_score_head.bias)
+        _, top = torch.topk(enc_logits.max(-1).values, self.num_queries, dim=-1)
+        bidx = torch.arange(memory.shape[0], device=memory.device)[:, None]
+        top_anchor = anchors[0][top] if anchors.shape[0] == 1 else anchors[bidx, top]
+        top_mem = om[bidx, top]
+        box_unact = self.enc_bbox_head(top_mem) + top_anchor
+        enc_boxes, enc_logits_l = [], []
+        if self.training:
+            enc_boxes.append(torch.sigmoid(box_unact))
+            enc_logits_l.append(enc_logits[bidx, top])
+        content = top_mem.detach()
+        box_unact = box_unact.detach()
+        if dn_box_unact is not None:
+            box_unact = torch.cat([dn_box_unact, box_unact], 1)
+            content = torch.cat([dn_content, content], 1)
+        return content, box_unact, enc_boxes, enc_logits_l
+
+    def _want_masks(self, targets):
+        if not self.enable_mask_head:
+            return False
+        if targets is None:
+            return True
+        return any(t.get("masks") is not None and hasattr(t["masks"], "numel") and t["masks"].numel() > 0
+                   for t in targets)
+
+    def _mask_logits(self, h, mask_feat):
+        e = self.mask_head(h) * (self.mask_dim ** -0.5)
+        return K.mask_dot(e, mask_feat)   # [B,Q,C] x [B,Hm,Wm,C] -> [B,Q,Hm,Wm]
+
+    def forward(self, feats, targets=None):
+        want_masks = self._want_masks(targets)
+        memory, shapes = self._memory(feats)
+        if self.training and self.num_denoising > 0:
+            dn_content, dn_box, attn_mask, dn_meta = make_denoising_group(
+                targets, self.num_classes, self.num_queries, self.denoising_class_embed,
+                self.num_denoising, self.label_noise_ratio, 1.0)
+        else:
+            dn_content = dn_box = attn_mask = dn_meta = None
+        content, ref_unact, enc_boxes, enc_logits = self._query_selection(memory, shapes, dn_content, dn_box)
+        boxes, logits, corners, refs, pre_boxes, pre_logits, hs = self.decoder(
+            content, ref_unact, memory, shapes, self.dec_bbox_head, self.dec_score_head,
+            self.query_pos_head, self.pre_bbox_head, attn_mask=attn_mask, return_queries=want_masks)
+
+        split_dn = self.training and dn_meta is not None
+        if split_dn:
+            n_dn = dn_meta["dn_num_split"][0]
+            dn_pre_logits, pre_logits = pre_logits[:, :n_dn], pre_logits[:, n_dn:]
+            dn_pre_boxes, pre_boxes = pre_boxes[:, :n_dn], pre_boxes[:, n_dn:]
+            dn_boxes, boxes = boxes[:, :, :n_dn], boxes[:, :, n_dn:]
+            dn_logits, logits = logits[:, :, :n_dn], logits[:, :, n_dn:]
+            dn_corners, corners = corners[:, :, :n_dn], corners[:, :, n_dn:]
+            dn_refs, refs = refs[:, :, :n_dn], refs[:, :, n_dn:]
+            if want_masks and hs is not None:
+                dn_hs, hs = hs[:, :, :n_dn], hs[:, :, n_dn:]
+
+        if want_masks:
+            mask_feat = self.mask_decoder(feats)
+            pred_masks = self._mask_logits(hs[-1], mask_feat)
+            aux_masks = [self._mask_logits(h, mask_feat) for h in hs[:-1]]
+            dn_pred_masks = dn_aux_masks = None
+            if split_dn:
+                dn_pred_masks = self._mask_logits(dn_hs[-1], mask_feat)
+                dn_aux_masks = [self._mask_logits(h, mask_feat) for h in dn_hs[:-1]]
+
+        if not self.training:
+            out = {"pred_logits": logits[-1], "pred_boxes": boxes[-1]}
+            if want_masks:
+                out["pred_masks"] = torch.sigmoid(pred_masks)
+            return out
+
+        out = {"pred_logits": logits[-1], "pred_boxes": boxes[-1], "pred_corners": corners[-1],
+               "ref_points": refs[-1], "up": self.up, "reg_scale": self.reg_scale}
+        if want_masks:
+            out["pred_masks"] = pred_masks
+        if self.aux_loss:
+            out["aux_outputs"] = _layer_dicts(logits[:-1], boxes[:-1], corners[:-1], refs[:-1],
+                                              corners[-1], logits[-1], aux_masks if want_masks else None)
+            out["enc_aux_outputs"] = [{"pred_logits": a, "pred_boxes": b} for a, b in zip(enc_logits, enc_boxes)]
+            out["pre_outputs"] = {"pred_logits": pre_logits, "pred_boxes": pre_boxes}
+            out["enc_meta"] = {"class_agnostic": False}
+            if dn_meta is not None:
+                # with masks the reference zips against the L-1 aux masks, which drops the last dn
+                # layer from dn_outputs (dfine_decoder.py:1094-1096) — reproduced by _layer_dicts.
+                out["dn_outputs"] = _layer_dicts(dn_logits, dn_boxes, dn_corners, dn_refs, dn_corners[-1],
+                                                 dn_logits[-1], dn_aux_masks if want_masks else None)
+                if want_masks and dn_pred_masks is not None:
+                    out["dn_pred_masks"] = dn_pred_masks
+                out["dn_pre_outputs"] = {"pred_logits": dn_pre_logits, "pred_boxes": dn_pre_boxes}
+                out["dn_meta"] = dn_meta
+        return out
+
+
+def _layer_dicts(logits, boxes, corners, refs, teacher_corners, teacher_logits, masks=None):
+    n = len(logits) if masks is None else min(len(logits), len(masks))
+    res = []
+    for i in range(n):
+        d = {"pred_logits": logits[i], "pred_boxes": boxes[i], "pred_corners": corners[i],
+             "ref_points": refs[i], "teacher_corners": teacher_corners, "teacher_logits": teacher_logits}
+        if masks is not None:
+            d["pred_masks"] = masks[i]
+        res.append(d)
+    return res
