@@ -66,12 +66,12 @@ class ConvUnit(nn.Module):
         return getattr(self, self._norm_name)
 
     def forward(self, x, pre_add=None, post_add=None):
-        y = K.conv2d(x, self.conv.weight, self.stride, self.pad, self.groups)
         bn = self._bn()
         frozen = isinstance(bn, FrozenBN)
         lab = getattr(self, "lab", None)
-        return K.bn_act(
-            y, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+        return K.conv_bn_act(
+            x, self.conv.weight, self.stride, self.pad, self.groups,
+            bn.weight, bn.bias, bn.running_mean, bn.running_var,
             None if frozen else bn.num_batches_tracked,
             training=self.training and not frozen, momentum=0.1, eps=bn.eps, act=self.act,
             lab_scale=None if lab is None else lab.scale,
@@ -101,7 +101,7 @@ def mha(container: nn.MultiheadAttention, qk_in, v_in, mask=None):
     hybrid_encoder.py:277, dfine_decoder.py:239) are not computed."""
     d = container.embed_dim
     w, b = container.in_proj_weight, container.in_proj_bias
-    qk = K.linear(qk_in, w[: 2 * d], b[: 2 * d])
+    qk = K.linear(qk_in, w[: 2 * d], b[: 2 * d])          # packed [.., q | k]
     v = K.linear(v_in, w[2 * d:], b[2 * d:])
-    o = K.attention(qk[..., :d], qk[..., d:], v, container.num_heads, mask)
+    o = K.attention(qk, v, container.num_heads, mask)
     return K.linear(o, container.out_proj.weight, container.out_proj.bias)

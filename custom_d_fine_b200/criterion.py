@@ -13,7 +13,6 @@ B200-first differences (values unchanged):
 """
 from __future__ import annotations
 
-import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -185,27 +184,24 @@ class DFINECriterion(nn.Module):
     # ---- index bookkeeping -----------------------------------------------------------------------
     @staticmethod
     def go_indices(indices, indices_aux_list):
-        """Per image: union of the matched (query, target) pairs of all layers; when a query is matched
-        to several targets keep the most frequent pair (ties: lexicographically first), rows ordered by
-        first appearance in the count-sorted list (dfine_criterion.py:570-591)."""
+        """Per image: union of the matched (query, target) pairs of all layers; a query matched to several
+        targets keeps its most frequent pair (dfine_criterion.py:570-591).  The matcher's indices live on
+        the host (as in the reference, matcher.py:244-247), and the tie order among equally frequent pairs
+        is whatever ``torch.argsort(counts, descending=True)`` (unstable) yields on CPU — the very same
+        calls are used here so the union is identical by construction."""
         res = []
         for b in range(len(indices)):
-            q = np.concatenate([np.asarray(indices[b][0])] + [np.asarray(a[b][0]) for a in indices_aux_list])
-            t = np.concatenate([np.asarray(indices[b][1])] + [np.asarray(a[b][1]) for a in indices_aux_list])
-            pairs = np.stack([q, t], 1)
-            if pairs.shape[0] == 0:
-                # reference: torch.tensor([]) -> float -> .long(); shapes [0]
-                res.append((torch.zeros(0, dtype=torch.int64), torch.zeros(0, dtype=torch.int64)))
-                continue
-            uniq, counts = np.unique(pairs, axis=0, return_counts=True)
-            order = np.argsort(-counts, kind="stable")
-            seen, rows, cols = set(), [], []
-            for r, c in uniq[order]:
-                if int(r) not in seen:
-                    seen.add(int(r))
-                    rows.append(int(r))
-                    cols.append(int(c))
-            res.append((torch.tensor(rows, dtype=torch.int64), torch.tensor(cols, dtype=torch.int64)))
+            q = torch.cat([indices[b][0]] + [a[b][0] for a in indices_aux_list])
+            t = torch.cat([indices[b][1]] + [a[b][1] for a in indices_aux_list])
+            ind = torch.cat([q[:, None], t[:, None]], 1)
+            unique, counts = torch.unique(ind, return_counts=True, dim=0)
+            order = torch.argsort(counts, descending=True)
+            seen = {}
+            for r, c in unique[order].tolist():
+                if r not in seen:
+                    seen[r] = c
+            res.append((torch.tensor(list(seen.keys()), dtype=torch.int64),
+                        torch.tensor(list(seen.values()), dtype=torch.int64)))
         return res
 
     @staticmethod

@@ -1,0 +1,73 @@
+// Shared helpers for libdfine_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cmath>
+
+#define DFINE_API extern "C" __attribute__((visibility("default")))
+
+void dfine_set_error(const char* fmt, ...);
+
+// argument check: negative return codes are caller errors (see include/dfine_sm100.h)
+#define DFINE_REQUIRE(cond, ...)                     \
+    do {                                             \
+        if (!(cond)) {                               \
+            dfine_set_error(__VA_ARGS__);            \
+            return -1;                               \
+        }                                            \
+    } while (0)
+
+#define DFINE_LAUNCH_CHECK(name)                                                         \
+    do {                                                                                 \
+        cudaError_t e__ = cudaGetLastError();                                            \
+        if (e__ != cudaSuccess) {                                                        \
+            dfine_set_error("%s: %s", name, cudaGetErrorString(e__));                    \
+            return (int)e__;                                                             \
+        }                                                                                \
+    } while (0)
+
+static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_GELU = 3 };
+
+__device__ __forceinline__ float act_fwd(float z, int act) {
+    switch (act) {
+        case ACT_RELU: return z > 0.f ? z : 0.f;
+        case ACT_SILU: return z / (1.f + expf(-z));
+        case ACT_GELU: return 0.5f * z * (1.f + erff(z * 0.70710678118654752f));
+        default: return z;
+    }
+}
+// d act(z) / dz
+__device__ __forceinline__ float act_bwd(float z, int act) {
+    switch (act) {
+        case ACT_RELU: return z > 0.f ? 1.f : 0.f;
+        case ACT_SILU: {
+            float s = 1.f / (1.f + expf(-z));
+            return s * (1.f + z * (1.f - s));
+        }
+        case ACT_GELU: {
+            float cdf = 0.5f * (1.f + erff(z * 0.70710678118654752f));
+            float pdf = 0.39894228040143268f * expf(-0.5f * z * z);
+            return cdf + z * pdf;
+        }
+        default: return 1.f;
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

@@ -1,0 +1,577 @@
+// tcgen05 / TMEM / TMA implicit-GEMM kernels for sm_100a (kind::tf32, fp32 storage, fp32 accumulate).
+//
+// They carry the dense convolutions of HGNetv2 / HybridEncoder (1x1 and 3x3 stride-1, reference
+// hgnetv2.py:35-80, hybrid_encoder.py:22-45) and every nn.Linear of AIFI / decoder / heads:
+//
+//   tc_fwd   : Y[pixel, n] = epi( sum_{tap, c} X[pixel + tap, c] * Wr[n, tap, c] )
+//              A tile  = TH x TW output-pixel patch (<=128 pixels) x 32 channels, fetched by ONE 4-D TMA
+//                        box per (tap, channel block) from the NHWC activation — the box origin is
+//                        shifted by the tap and TMA's out-of-bounds zero fill implements the padding,
+//                        so there is no im2col buffer and no halo logic;
+//              B tile  = BN weight rows x 32 of the re-laid weight [Cout, taps*Cin] (2-D TMA);
+//              both K-major with the 128-byte swizzle, consumed by tcgen05.mma.cta_group::1.kind::tf32
+//              (UMMA M=128, N=BN, K=8), fp32 accumulator in TMEM (BN columns);
+//              epilogue warps: tcgen05.ld -> registers -> shared transpose -> 128-byte row stores with
+//              bias / activation, plus optional per-channel sum / sum-of-squares for train-mode
+//              BatchNorm (removes the separate statistics pass over the conv output).
+//              The data-gradient of these convs is the same kernel run on dY with flipped/transposed
+//              weights.
+//   tc_wgrad : dWr[co, tap, ci] += sum_{pixel} dY[pixel, co] * X[pixel + tap, ci]
+//              both operands MN-major (the reduction runs over pixels, channels are contiguous):
+//              32-pixel x 32-channel TMA boxes, UMMA descriptors with a_major = b_major = MN;
+//              split over pixel ranges, accumulated into dWr with red.global.add.f32.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = barrier init + TMEM alloc + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp % 4).  3-stage smem ring so two CTAs fit per SM and
+// one CTA's epilogue overlaps the other's main loop.  Every mbarrier wait is bounded and traps instead
+// of hanging the device.
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 22)) __trap();  // a lost arrival must abort the launch, not hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, 128-byte swizzle (layout type 2), descriptor version 1 (sm_100).
+// K-major : rows of 128 B (32 fp32 along K), 8-row atoms; SBO = 1024 B between 8-row groups.
+// MN-major: rows of 128 B (32 fp32 along M/N), 8 k-rows per atom; SBO = 1024 B between k groups,
+//           LBO = byte distance between consecutive 32-element M/N chunks.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, M=128, N=n; major bits 15/16 (0 = K-major, 1 = MN-major)
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn, int b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+constexpr int TC_THREADS = 192;
+constexpr int BM = 128, BK = 32;
+constexpr int STAGES = 3;
+constexpr int EPI_LD = 33;
+
+struct FwdParams {
+    int taps_h, taps_w, pad;  // filter taps and symmetric padding (1x1: 1,1,0   3x3: 3,3,1)
+    int Cin;                  // channels per tap
+    int TW, TH;               // output patch per CTA (TW*TH <= 128)
+    int tiles_w, tiles_h;     // patches per image
+    int OH, OW, N;            // output geometry, N = Cout
+    long ldy;                 // output pixel stride (elements)
+    int act;
+};
+
+template <int BN>
+struct FwdSmem {
+    alignas(1024) float a[STAGES][BM * BK];
+    alignas(1024) float b[STAGES][BN * BK];
+    uint64_t full[STAGES], empty[STAGES], acc_full;   // (the epilogue's transpose buffers alias a[0])
+    uint32_t tmem_base;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS) tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                            const __grid_constant__ CUtensorMap map_w,
+                                                            float* __restrict__ y, const float* __restrict__ bias,
+                                                            double* __restrict__ stats, FwdParams p) {
+    extern __shared__ uint8_t raw[];
+    FwdSmem<BN>& sm = *reinterpret_cast<FwdSmem<BN>*>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    // tile coordinates
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+    const int img = blockIdx.x / tiles_per_img, t = blockIdx.x % tiles_per_img;
+    const int h0 = (t / p.tiles_w) * p.TH, w0 = (t % p.tiles_w) * p.TW;
+    const int n0 = blockIdx.y * BN;
+    const int cblocks = (p.Cin + BK - 1) / BK;
+    const int num_k = p.taps_h * p.taps_w * cblocks;
+
+    if (warp == 0 && lane == 0) { prefetch_tmap(&map_x); prefetch_tmap(&map_w); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+            mbar_init(&sm.acc_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(&sm.tmem_base, BN);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                mbar_wait(&sm.empty[s], ph ^ 1);
+                const int tap = kb / cblocks, c0 = (kb % cblocks) * BK;
+                const int kh = tap / p.taps_w, kw = tap % p.taps_w;
+                // the x box is TW*TH (<=128) rows of 128 B; smem rows beyond that keep stale data that only
+                // feeds accumulator rows the epilogue never stores.  expect_tx counts the box bytes:
+                mbar_expect_tx(&sm.full[s], (uint32_t)((p.TW * p.TH + BN) * BK * sizeof(float)));
+                tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 + kw - p.pad, h0 + kh - p.pad, img);
+                tma_load_2d(sm.b[s], &map_w, &sm.full[s], tap * p.Cin + c0, n0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                mbar_wait(&sm.full[s], ph);
+                tc_fence_after();
+                const uint64_t da = make_desc(smem_u32(sm.a[s]), 16, 1024);
+                const uint64_t db = make_desc(smem_u32(sm.b[s]), 16, 1024);
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k)  // UMMA_K = 8 tf32 = 32 bytes -> +2 in 16-byte units
+                    umma_tf32(tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                umma_commit(&sm.empty[s]);
+            }
+            umma_commit(&sm.acc_full);
+        }
+        __syncwarp();
+    } else {
+        const int q = warp % 4;  // TMEM lane quarter
+        // all MMAs (hence all TMA loads) have completed once acc_full fires: stage 0 is free to reuse
+        float* buf = sm.a[0] + q * 32 * EPI_LD;
+        // rows handled by this lane in the transposed store phase: r = 4*i + lane/8, i = 0..7
+        long row_off[8];
+        bool row_ok[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = 32 * q + 4 * i + lane / 8;
+            const int th = r / p.TW, tw = r % p.TW;
+            const int oh = h0 + th, ow = w0 + tw;
+            row_ok[i] = th < p.TH && oh < p.OH && ow < p.OW;
+            row_off[i] = (((long)img * p.OH + oh) * p.OW + ow) * p.ldy;
+        }
+        mbar_wait(&sm.acc_full, 0);
+        tc_fence_after();
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (n0 + c0 >= p.N) break;
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) buf[lane * EPI_LD + c] = __uint_as_float(v[c]);
+            __syncwarp();
+            const int col = n0 + c0 + 4 * (lane % 8);
+            const bool col_ok = col < p.N;  // N % 4 == 0 is required by the host wrapper
+            float4 bv = make_float4(0, 0, 0, 0);
+            if (bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+            float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = 4 * i + lane / 8;
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = buf[r * EPI_LD + 4 * (lane % 8) + j];
+                if (row_ok[i] && col_ok) {
+                    if (stats) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { s1[j] += o[j]; s2[j] += o[j] * o[j]; }
+                    }
+                    o[0] = act_fwd(o[0] + bv.x, p.act); o[1] = act_fwd(o[1] + bv.y, p.act);
+                    o[2] = act_fwd(o[2] + bv.z, p.act); o[3] = act_fwd(o[3] + bv.w, p.act);
+                    *reinterpret_cast<float4*>(y + row_off[i] + col) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            if (stats) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8); s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
+                    s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+                }
+                if (lane < 8 && col_ok) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        atomicAdd(stats + col + j, (double)s1[j]);
+                        atomicAdd(stats + p.N + col + j, (double)s2[j]);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, BN);
+}
+
+// ------------------------------------------------------------------------------------------- wgrad
+struct WgradParams {
+    int taps_h, taps_w, pad;
+    int Cin, Cout;
+    int OH, OW, B;
+    int wchunks;          // ceil(OW / 32)
+    long steps_total;     // B*OH*wchunks reduction steps of 32 pixels
+    long steps_per_split;
+    int cin_tiles;        // ceil(Cin / BN)
+};
+
+template <int BN>
+struct WgradSmem {
+    alignas(1024) float a[STAGES][BM * BK];  // 4 chunks of [32 pixels][32 cout]
+    alignas(1024) float b[STAGES][BN * BK];  // BN/32 chunks of [32 pixels][32 cin]
+    uint64_t full[STAGES], empty[STAGES], acc_full;
+    uint32_t tmem_base;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS) tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy,
+                                                              const __grid_constant__ CUtensorMap map_x,
+                                                              float* __restrict__ dwr, WgradParams p) {
+    extern __shared__ uint8_t raw[];
+    WgradSmem<BN>& sm = *reinterpret_cast<WgradSmem<BN>*>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int co0 = blockIdx.x * BM;
+    const int tap = blockIdx.y / p.cin_tiles, ci0 = (blockIdx.y % p.cin_tiles) * BN;
+    const int kh = tap / p.taps_w, kw = tap % p.taps_w;
+    const long s_begin = (long)blockIdx.z * p.steps_per_split;
+    const long s_end = s_begin + p.steps_per_split < p.steps_total ? s_begin + p.steps_per_split : p.steps_total;
+    const int num_k = (int)(s_end - s_begin);
+
+    if (warp == 0 && lane == 0) { prefetch_tmap(&map_dy); prefetch_tmap(&map_x); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+            mbar_init(&sm.acc_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(&sm.tmem_base, BN);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                mbar_wait(&sm.empty[s], ph ^ 1);
+                long step = s_begin + kb;
+                const int wc = (int)(step % p.wchunks); step /= p.wchunks;
+                const int oh = (int)(step % p.OH);
+                const int b = (int)(step / p.OH);
+                mbar_expect_tx(&sm.full[s], (uint32_t)((BM + BN) * BK * sizeof(float)));
+#pragma unroll
+                for (int c = 0; c < BM / 32; ++c)
+                    tma_load_4d(sm.a[s] + c * 32 * BK, &map_dy, &sm.full[s], co0 + 32 * c, wc * 32, oh, b);
+#pragma unroll
+                for (int c = 0; c < BN / 32; ++c)
+                    tma_load_4d(sm.b[s] + c * 32 * BK, &map_x, &sm.full[s], ci0 + 32 * c, wc * 32 + kw - p.pad,
+                                oh + kh - p.pad, b);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                mbar_wait(&sm.full[s], ph);
+                tc_fence_after();
+                // chunk (32 channels) stride = 32 pixels * 128 B = 4096 B (LBO); 8-pixel k-group = 1024 B (SBO)
+                const uint64_t da = make_desc(smem_u32(sm.a[s]), 32 * BK * 4, 1024);
+                const uint64_t db = make_desc(smem_u32(sm.b[s]), 32 * BK * 4, 1024);
+#pragma unroll
+                for (int k = 0; k < 32 / 8; ++k)  // 8 pixels per UMMA = one 1024-byte atom -> +64 in 16-byte units
+                    umma_tf32(tmem, da + 64 * k, db + 64 * k, idesc, (kb | k) != 0);
+                umma_commit(&sm.empty[s]);
+            }
+            umma_commit(&sm.acc_full);
+        }
+        __syncwarp();
+    } else if (num_k > 0) {
+        const int q = warp % 4;
+        mbar_wait(&sm.acc_full, 0);
+        tc_fence_after();
+        const int co = co0 + 32 * q + lane;
+        const long ldw = (long)p.taps_h * p.taps_w * p.Cin;
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (ci0 + c0 >= p.Cin) break;
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
+            if (co < p.Cout) {
+                float* dst = dwr + (long)co * ldw + (long)tap * p.Cin + ci0 + c0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (ci0 + c0 + c < p.Cin) atomicAdd(dst + c, __uint_as_float(v[c]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, BN);
+}
+
+// ------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+// 4-D fp32 tensor map (C, W, H, B) over an NHWC activation with pixel stride ld (elements),
+// 128-byte swizzle, zero OOB fill.
+int make_map4(CUtensorMap* m, const float* base, long C, long W, long H, long B, long ld, int box_c, int box_w,
+              int box_h, const char* who) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { dfine_set_error("%s: cuTensorMapEncodeTiled unavailable", who); return -2; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)ld * 4 * W, (cuuint64_t)ld * 4 * W * H};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, (void*)base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        dfine_set_error("%s: cuTensorMapEncodeTiled(4d) failed (%d) C=%ld W=%ld H=%ld B=%ld ld=%ld box=%d,%d,%d", who,
+                        (int)r, C, W, H, B, ld, box_c, box_w, box_h);
+        return -2;
+    }
+    return 0;
+}
+int make_map2(CUtensorMap* m, const float* base, long inner, long rows, long ld, int box_inner, int box_rows,
+              const char* who) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { dfine_set_error("%s: cuTensorMapEncodeTiled unavailable", who); return -2; }
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void*)base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        dfine_set_error("%s: cuTensorMapEncodeTiled(2d) failed (%d) inner=%ld rows=%ld ld=%ld", who, (int)r, inner, rows,
+                        ld);
+        return -2;
+    }
+    return 0;
+}
+
+void pick_patch(int OH, int OW, int* TW, int* TH) {
+    // widest patch row <= 128 that wastes the fewest rows; prefer full-width rows for narrow maps
+    if (OH == 1) { *TW = 128; *TH = 1; return; }
+    int best_tw = 1, best_th = 1;
+    double best = -1.0;
+    for (int tw = 1; tw <= 128 && tw <= 256; ++tw) {
+        if (tw > OW && tw != OW) break;
+        int th = 128 / tw;
+        if (th > 256) th = 256;
+        if (th < 1) continue;
+        const long tiles = (long)((OW + tw - 1) / tw) * ((OH + th - 1) / th);
+        const double eff = (double)OH * OW / ((double)tiles * 128.0);
+        if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > best_tw)) { best = eff; best_tw = tw; best_th = th; }
+    }
+    *TW = best_tw;
+    *TH = best_th;
+}
+
+template <int BN>
+int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, float* y, const float* bias, double* stats,
+               const FwdParams& p, int B, cudaStream_t st) {
+    static bool configured = false;
+    const int smem = (int)sizeof(FwdSmem<BN>) + 1024;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { dfine_set_error("tc_fwd: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    dim3 grid(B * p.tiles_w * p.tiles_h, ceil_div(p.N, BN));
+    tc_fwd_kernel<BN><<<grid, TC_THREADS, smem, st>>>(mx, mw, y, bias, stats, p);
+    return 0;
+}
+
+template <int BN>
+int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, float* dwr, WgradParams p, cudaStream_t st) {
+    static bool configured = false;
+    const int smem = (int)sizeof(WgradSmem<BN>) + 1024;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { dfine_set_error("tc_wgrad: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    p.cin_tiles = ceil_div(p.Cin, BN);
+    const int gx = ceil_div(p.Cout, BM), gy = p.taps_h * p.taps_w * p.cin_tiles;
+    long splits = (148L * 2 + (long)gx * gy - 1) / ((long)gx * gy);
+    if (splits < 1) splits = 1;
+    long sps = (p.steps_total + splits - 1) / splits;
+    if (sps < 8) sps = 8;
+    p.steps_per_split = sps;
+    dim3 grid(gx, gy, ceil_div(p.steps_total, sps));
+    tc_wgrad_kernel<BN><<<grid, TC_THREADS, smem, st>>>(mdy, mx, dwr, p);
+    return 0;
+}
+
+}  // namespace
+
+// 1 if the tensor-core path accepts this conv/linear geometry (the host graph uses the CUDA-core
+// kernels of conv_simt.cu otherwise).
+DFINE_API int dfine_conv_tc_supported(int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l, int pad_b,
+                                      int pad_r, long ldx, long ldy) {
+    if (stride != 1) return 0;
+    if (!((KH == 1 && KW == 1 && pad_t == 0 && pad_l == 0 && pad_b == 0 && pad_r == 0) ||
+          (KH == 3 && KW == 3 && pad_t == 1 && pad_l == 1 && pad_b == 1 && pad_r == 1)))
+        return 0;
+    if (Cin % 4 || Cout % 4 || ldx % 4 || ldy % 4) return 0;
+    if (Cin < 16 || Cout < 16) return 0;
+    return 1;
+}
+
+// y[b,oh,ow,:Cout] (pixel stride ldy) = act(conv(x[b,h,w,:Cin] (pixel stride ldx), wr[Cout, KH*KW*Cin]) + bias);
+// stride 1, "same" padding for 3x3.  stats (optional, double [2*Cout], zeroed by the caller) receives
+// per-channel sum / sum of squares of the raw conv output (valid only with bias == null, act == 0).
+// nn.Linear on [rows, K]: B=1, H=1, W=rows.
+DFINE_API int dfine_conv_fwd_tc(const float* x, const float* wr, const float* bias, float* y, double* stats, int B,
+                                int H, int W, int Cin, int Cout, int KH, int KW, long ldx, long ldy, int act,
+                                void* stream) {
+    DFINE_REQUIRE(dfine_conv_tc_supported(Cin, Cout, KH, KW, 1, KH / 2, KW / 2, KH / 2, KW / 2, ldx, ldy),
+                  "conv_fwd_tc: unsupported geometry Cin=%d Cout=%d k=%dx%d ldx=%ld ldy=%ld", Cin, Cout, KH, KW, ldx, ldy);
+    DFINE_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)wr % 16) == 0 && ((uintptr_t)y % 16) == 0 &&
+                      (!bias || ((uintptr_t)bias % 16) == 0),
+                  "conv_fwd_tc: pointers must be 16-byte aligned");
+    if ((long)B * H * W == 0) return 0;
+    FwdParams p;
+    p.taps_h = KH; p.taps_w = KW; p.pad = KH / 2; p.Cin = Cin;
+    p.OH = H; p.OW = W; p.N = Cout; p.ldy = ldy; p.act = act;
+    pick_patch(H, W, &p.TW, &p.TH);
+    p.tiles_w = ceil_div(W, p.TW);
+    p.tiles_h = ceil_div(H, p.TH);
+    CUtensorMap mx, mw;
+    int rc = make_map4(&mx, x, Cin, W, H, B, ldx, BK, p.TW, p.TH, "conv_fwd_tc(x)");
+    if (rc) return rc;
+    const long K = (long)KH * KW * Cin;
+    const int bn = Cout <= 64 ? 64 : 128;
+    rc = make_map2(&mw, wr, K, Cout, K, BK, bn, "conv_fwd_tc(w)");
+    if (rc) return rc;
+    rc = bn == 64 ? launch_fwd<64>(mx, mw, y, bias, stats, p, B, (cudaStream_t)stream)
+                  : launch_fwd<128>(mx, mw, y, bias, stats, p, B, (cudaStream_t)stream);
+    if (rc) return rc;
+    DFINE_LAUNCH_CHECK("conv_fwd_tc");
+    return 0;
+}
+
+// dwr[Cout, KH*KW*Cin] += sum over pixels dy[b,oh,ow,co] * x[b,oh+kh-p,ow+kw-p,ci]; zeroed by the caller.
+DFINE_API int dfine_conv_wgrad_tc(const float* dy, const float* x, float* dwr, int B, int H, int W, int Cin, int Cout,
+                                  int KH, int KW, long ldx, long ldy, void* stream) {
+    DFINE_REQUIRE(dfine_conv_tc_supported(Cin, Cout, KH, KW, 1, KH / 2, KW / 2, KH / 2, KW / 2, ldx, ldy),
+                  "conv_wgrad_tc: unsupported geometry Cin=%d Cout=%d k=%dx%d", Cin, Cout, KH, KW);
+    DFINE_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)dy % 16) == 0, "conv_wgrad_tc: alignment");
+    if ((long)B * H * W == 0) return 0;
+    WgradParams p;
+    p.taps_h = KH; p.taps_w = KW; p.pad = KH / 2; p.Cin = Cin; p.Cout = Cout; p.OH = H; p.OW = W; p.B = B;
+    p.wchunks = ceil_div(W, 32);
+    p.steps_total = (long)B * H * p.wchunks;
+    CUtensorMap mdy, mx;
+    int rc = make_map4(&mdy, dy, Cout, W, H, B, ldy, 32, 32, 1, "conv_wgrad_tc(dy)");
+    if (rc) return rc;
+    rc = make_map4(&mx, x, Cin, W, H, B, ldx, 32, 32, 1, "conv_wgrad_tc(x)");
+    if (rc) return rc;
+    rc = Cin <= 64 ? launch_wgrad<64>(mdy, mx, dwr, p, (cudaStream_t)stream)
+                   : launch_wgrad<128>(mdy, mx, dwr, p, (cudaStream_t)stream);
+    if (rc) return rc;
+    DFINE_LAUNCH_CHECK("conv_wgrad_tc");
+    return 0;
+}

@@ -1,0 +1,290 @@
+// Depthwise convolutions and the small spatial ops of the backbone / encoder, NHWC fp32.
+//
+//  * depthwise k x k (k = 3 stride 2 "downsample", k = 5 stride 1 LightConv, k = 3 stride 2 SCDown):
+//    hgnetv2.py:83-112,295-304, hybrid_encoder.py:96-103.  Pure HBM-bound stencils: one thread per
+//    (pixel, 4 channels), 16-byte accesses along C, neighbouring taps served by L1/L2.
+//  * stem max-pool (F.pad(0,1,0,1) + MaxPool2d(2, stride 1, ceil_mode) hgnetv2.py:154-162).
+//  * nearest x2 upsample of the FPN top-down path (hybrid_encoder.py:472).
+#include "common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& w) {
+    a.x += x.x * w.x; a.y += x.y * w.y; a.z += x.z * w.z; a.w += x.w * w.w;
+}
+
+// weights here are [k*k, C] (tap-major) — the host re-lays the [C,1,k,k] parameter once per step.
+__global__ void __launch_bounds__(NT) dwconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        float* __restrict__ y, int B, int H, int W, int C, int OH,
+                                                        int OW, int k, int stride, int pad) {
+    const int VC = C / 4;
+    const long total = (long)B * OH * OW * VC;
+    for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+        const int cv = (int)(i % VC);
+        long p = i / VC;
+        const int ow = (int)(p % OW); p /= OW;
+        const int oh = (int)(p % OH);
+        const int b = (int)(p / OH);
+        float4 acc = make_float4(0, 0, 0, 0);
+        for (int kh = 0; kh < k; ++kh) {
+            const int ih = oh * stride + kh - pad;
+            if (ih < 0 || ih >= H) continue;
+            for (int kw = 0; kw < k; ++kw) {
+                const int iw = ow * stride + kw - pad;
+                if (iw < 0 || iw >= W) continue;
+                fma4(acc, ld4(x + (((long)b * H + ih) * W + iw) * C + cv * 4), ld4(w + (long)(kh * k + kw) * C + cv * 4));
+            }
+        }
+        st4(y + i * 4, acc);
+    }
+}
+
+__global__ void __launch_bounds__(NT) dwconv_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                             float* __restrict__ dx, int B, int H, int W, int C,
+                                                             int OH, int OW, int k, int stride, int pad) {
+    const int VC = C / 4;
+    const long total = (long)B * H * W * VC;
+    for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+        const int cv = (int)(i % VC);
+        long p = i / VC;
+        const int iw = (int)(p % W); p /= W;
+        const int ih = (int)(p % H);
+        const int b = (int)(p / H);
+        float4 acc = make_float4(0, 0, 0, 0);
+        for (int kh = 0; kh < k; ++kh) {
+            const int th = ih + pad - kh;
+            if (th < 0 || th % stride) continue;
+            const int oh = th / stride;
+            if (oh >= OH) continue;
+            for (int kw = 0; kw < k; ++kw) {
+                const int tw = iw + pad - kw;
+                if (tw < 0 || tw % stride) continue;
+                const int ow = tw / stride;
+                if (ow >= OW) continue;
+                fma4(acc, ld4(dy + (((long)b * OH + oh) * OW + ow) * C + cv * 4),
+                     ld4(w + (long)(kh * k + kw) * C + cv * 4));
+            }
+        }
+        st4(dx + i * 4, acc);
+    }
+}
+
+// dw[tap, c] += sum_pixels dy * x_shifted.  CTA = slab of output pixels; lanes tile [pixels, C/4];
+// per-thread register accumulators for all taps (K*K float4), merged through shared atomics.
+template <int K>
+__global__ void __launch_bounds__(NT) dwconv_bwd_weight_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                               float* __restrict__ dw, int B, int H, int W, int C,
+                                                               int OH, int OW, int stride, int pad, long pix_per_cta) {
+    extern __shared__ float shw[];  // [K*K*C]
+    for (int i = threadIdx.x; i < K * K * C; i += NT) shw[i] = 0.f;
+    __syncthreads();
+    const int VC = C / 4;
+    const int LPR = VC < NT ? VC : NT, RPP = NT / LPR;
+    const int lane_r = threadIdx.x / LPR, lane_c = threadIdx.x % LPR;
+    const long P = (long)B * OH * OW;
+    const long p0 = (long)blockIdx.x * pix_per_cta, p1 = p0 + pix_per_cta < P ? p0 + pix_per_cta : P;
+    if (lane_r < RPP) {
+        for (int cv = lane_c; cv < VC; cv += LPR) {
+            float4 acc[K * K];
+#pragma unroll
+            for (int t = 0; t < K * K; ++t) acc[t] = make_float4(0, 0, 0, 0);
+            for (long p = p0 + lane_r; p < p1; p += RPP) {
+                const int ow = (int)(p % OW);
+                const long q = p / OW;
+                const int oh = (int)(q % OH), b = (int)(q / OH);
+                const float4 g = ld4(dy + p * C + cv * 4);
+#pragma unroll
+                for (int kh = 0; kh < K; ++kh) {
+                    const int ih = oh * stride + kh - pad;
+                    if (ih < 0 || ih >= H) continue;
+#pragma unroll
+                    for (int kw = 0; kw < K; ++kw) {
+                        const int iw = ow * stride + kw - pad;
+                        if (iw < 0 || iw >= W) continue;
+                        fma4(acc[kh * K + kw], g, ld4(x + (((long)b * H + ih) * W + iw) * C + cv * 4));
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < K * K; ++t) {
+                float* s = shw + (long)t * C + cv * 4;
+                atomicAdd(s + 0, acc[t].x); atomicAdd(s + 1, acc[t].y); atomicAdd(s + 2, acc[t].z); atomicAdd(s + 3, acc[t].w);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * K * C; i += NT) atomicAdd(&dw[i], shw[i]);
+}
+
+// out[h,w] = max over the 2x2 window of the right/bottom zero-padded map; first max wins on ties.
+__device__ __forceinline__ float padded(const float* __restrict__ x, int b, int h, int w, int c, int H, int W, int C) {
+    return (h < H && w < W) ? __ldg(x + (((long)b * H + h) * W + w) * C + c) : 0.f;
+}
+__device__ __forceinline__ int window_argmax(const float* __restrict__ x, int b, int h, int w, int c, int H, int W,
+                                             int C, float* mx) {
+    float best = padded(x, b, h, w, c, H, W, C);
+    int arg = 0;
+    float v = padded(x, b, h, w + 1, c, H, W, C);
+    if (v > best || isnan(v)) { best = v; arg = 1; }
+    v = padded(x, b, h + 1, w, c, H, W, C);
+    if (v > best || isnan(v)) { best = v; arg = 2; }
+    v = padded(x, b, h + 1, w + 1, c, H, W, C);
+    if (v > best || isnan(v)) { best = v; arg = 3; }
+    *mx = best;
+    return arg;
+}
+__global__ void __launch_bounds__(NT) maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
+                                                         int H, int W, int C) {
+    const long total = (long)B * H * W * C;
+    for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+        const int c = (int)(i % C);
+        long p = i / C;
+        const int w = (int)(p % W); p /= W;
+        const int h = (int)(p % H);
+        const int b = (int)(p / H);
+        float mx;
+        window_argmax(x, b, h, w, c, H, W, C, &mx);
+        y[i] = mx;
+    }
+}
+// gather form of the backward: input (h,w) receives dy of each of its <=4 windows whose argmax it is.
+__global__ void __launch_bounds__(NT) maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                         float* __restrict__ dx, int B, int H, int W, int C) {
+    const long total = (long)B * H * W * C;
+    for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+        const int c = (int)(i % C);
+        long p = i / C;
+        const int w = (int)(p % W); p /= W;
+        const int h = (int)(p % H);
+        const int b = (int)(p / H);
+        float acc = 0.f, mx;
+        // window origin (h-dh, w-dw) sees this element at slot dh*2+dw
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+            for (int dw = 0; dw < 2; ++dw) {
+                const int oh = h - dh, ow = w - dw;
+                if (oh < 0 || ow < 0) continue;
+                if (window_argmax(x, b, oh, ow, c, H, W, C, &mx) == dh * 2 + dw)
+                    acc += __ldg(dy + (((long)b * H + oh) * W + ow) * C + c);
+            }
+        dx[i] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(NT) upsample2x_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
+                                                            int H, int W, int VC) {
+    const long total = (long)B * (2 * H) * (2 * W) * VC;
+    for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+        const int cv = (int)(i % VC);
+        long p = i / VC;
+        const int ow = (int)(p % (2 * W)); p /= (2 * W);
+        const int oh = (int)(p % (2 * H));
+        const int b = (int)(p / (2 * H));
+        st4(y + i * 4, ld4(x + ((((long)b * H + oh / 2) * W + ow / 2) * VC + cv) * 4));
+    }
+}
+__global__ void __launch_bounds__(NT) upsample2x_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx,
+                                                            int B, int H, int W, int VC) {
+    const long total = (long)B * H * W * VC;
+    for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+        const int cv = (int)(i % VC);
+        long p = i / VC;
+        const int w = (int)(p % W); p /= W;
+        const int h = (int)(p % H);
+        const int b = (int)(p / H);
+        const float* base = dy + ((((long)b * 2 * H + 2 * h) * 2 * W + 2 * w) * VC + cv) * 4;
+        const long rs = (long)2 * W * VC * 4;
+        const float4 a = ld4(base), bb = ld4(base + VC * 4), c = ld4(base + rs), d = ld4(base + rs + VC * 4);
+        st4(dx + i * 4, make_float4(a.x + bb.x + c.x + d.x, a.y + bb.y + c.y + d.y, a.z + bb.z + c.z + d.z,
+                                    a.w + bb.w + c.w + d.w));
+    }
+}
+
+inline int ew_grid(long n) {
+    long g = (n + NT - 1) / NT;
+    const long cap = 148L * 16;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+// x [B,H,W,C], w [k*k,C] tap-major, y [B,OH,OW,C]; symmetric padding `pad`.
+DFINE_API int dfine_dwconv_fwd(const float* x, const float* w, float* y, int B, int H, int W, int C, int k,
+                               int stride, int pad, void* stream) {
+    DFINE_REQUIRE(C % 4 == 0, "dwconv_fwd: C=%d must be a multiple of 4", C);
+    const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
+    const long total = (long)B * OH * OW * (C / 4);
+    if (total == 0) return 0;
+    dwconv_fwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x, w, y, B, H, W, C, OH, OW, k, stride, pad);
+    DFINE_LAUNCH_CHECK("dwconv_fwd");
+    return 0;
+}
+
+DFINE_API int dfine_dwconv_bwd_data(const float* dy, const float* w, float* dx, int B, int H, int W, int C, int k,
+                                    int stride, int pad, void* stream) {
+    DFINE_REQUIRE(C % 4 == 0, "dwconv_bwd_data: C=%d", C);
+    const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
+    const long total = (long)B * H * W * (C / 4);
+    if (total == 0) return 0;
+    dwconv_bwd_data_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(dy, w, dx, B, H, W, C, OH, OW, k, stride,
+                                                                           pad);
+    DFINE_LAUNCH_CHECK("dwconv_bwd_data");
+    return 0;
+}
+
+// dw [k*k,C] tap-major, zero-initialised by the caller.
+DFINE_API int dfine_dwconv_bwd_weight(const float* dy, const float* x, float* dw, int B, int H, int W, int C, int k,
+                                      int stride, int pad, void* stream) {
+    DFINE_REQUIRE(C % 4 == 0 && (k == 3 || k == 5), "dwconv_bwd_weight: C=%d k=%d", C, k);
+    DFINE_REQUIRE((long)k * k * C * 4 <= 48 * 1024, "dwconv_bwd_weight: k*k*C too large for shared memory");
+    const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
+    const long P = (long)B * OH * OW;
+    if (P == 0) return 0;
+    long ppc = (P + 148L * 4 - 1) / (148L * 4);
+    if (ppc < 64) ppc = 64;
+    const size_t smem = (size_t)k * k * C * sizeof(float);
+    if (k == 3)
+        dwconv_bwd_weight_kernel<3><<<ceil_div(P, ppc), NT, smem, (cudaStream_t)stream>>>(dy, x, dw, B, H, W, C, OH, OW,
+                                                                                         stride, pad, ppc);
+    else
+        dwconv_bwd_weight_kernel<5><<<ceil_div(P, ppc), NT, smem, (cudaStream_t)stream>>>(dy, x, dw, B, H, W, C, OH, OW,
+                                                                                         stride, pad, ppc);
+    DFINE_LAUNCH_CHECK("dwconv_bwd_weight");
+    return 0;
+}
+
+DFINE_API int dfine_maxpool2x2_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+    const long total = (long)B * H * W * C;
+    if (total == 0) return 0;
+    maxpool_fwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C);
+    DFINE_LAUNCH_CHECK("maxpool_fwd");
+    return 0;
+}
+DFINE_API int dfine_maxpool2x2_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C,
+                                   void* stream) {
+    const long total = (long)B * H * W * C;
+    if (total == 0) return 0;
+    maxpool_bwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x, dy, dx, B, H, W, C);
+    DFINE_LAUNCH_CHECK("maxpool_bwd");
+    return 0;
+}
+DFINE_API int dfine_upsample2x_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+    DFINE_REQUIRE(C % 4 == 0, "upsample2x: C=%d", C);
+    const long total = (long)B * 4 * H * W * (C / 4);
+    if (total == 0) return 0;
+    upsample2x_fwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C / 4);
+    DFINE_LAUNCH_CHECK("upsample2x_fwd");
+    return 0;
+}
+DFINE_API int dfine_upsample2x_bwd(const float* dy, float* dx, int B, int H, int W, int C, void* stream) {
+    DFINE_REQUIRE(C % 4 == 0, "upsample2x: C=%d", C);
+    const long total = (long)B * H * W * (C / 4);
+    if (total == 0) return 0;
+    upsample2x_bwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(dy, dx, B, H, W, C / 4);
+    DFINE_LAUNCH_CHECK("upsample2x_bwd");
+    return 0;
+}

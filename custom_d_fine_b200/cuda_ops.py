@@ -1,0 +1,620 @@
+"""The product's only compute provider: the kernel table backed by ``csrc/libdfine_sm100.so``.
+
+Every method of :class:`CudaOps` is an entry of the kernel table ``K`` used by the host graph.
+Tensors, streams and autograd bookkeeping are PyTorch's; all arithmetic of the ops listed in
+SURVEY §8a runs in the hand-written sm_100a kernels reached through the C ABI declared in
+``include/dfine_sm100.h`` (ctypes — no torch types cross the boundary).  There is no CPU path:
+a missing library, a non-CUDA tensor or a non-zero return code raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int, c_long, c_void_p
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libdfine_sm100.so"
+_lib = None
+
+ACT = {None: 0, "relu": 1, "silu": 2, "gelu": 3}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise RuntimeError(
+                f"{_LIB_PATH} is missing — build it with `python -m custom_d_fine_b200.build` "
+                "(there is no fallback compute path)")
+        L = ctypes.CDLL(str(_LIB_PATH))
+        for name, (ret, args) in abi_prototypes().items():
+            fn = getattr(L, name)          # AttributeError = header/library mismatch: fail loudly
+            fn.restype, fn.argtypes = ret, args
+        _lib = L
+    return _lib
+
+
+_HEADER = Path(__file__).resolve().parent.parent / "include" / "dfine_sm100.h"
+
+
+def abi_prototypes(header: Path = _HEADER):
+    """Parse ``include/dfine_sm100.h`` -> {name: (restype, [argtypes])} for ctypes."""
+    import re
+
+    def ctype(decl):
+        decl = decl.strip()
+        if "*" in decl:
+            return c_void_p
+        return {"int": c_int, "long": c_long, "float": c_float, "double": ctypes.c_double}[decl.rsplit(" ", 1)[0]]
+
+    text = re.sub(r"/\*.*?\*/", "", header.read_text(), flags=re.S)
+    text = "\n".join(l for l in text.splitlines() if not l.lstrip().startswith("#"))
+    protos = {}
+    for m in re.finditer(r"(const char\*|int|long)\s+(dfine_\w+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, args = m.groups()
+        restype = {"const char*": ctypes.c_char_p, "int": c_int, "long": c_long}[ret]
+        arglist = [] if args.strip() == "void" else [ctype(a) for a in args.split(",")]
+        protos[name] = (restype, arglist)
+    return protos
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"libdfine_sm100 {what} failed (rc={rc}): {lib().dfine_last_error().decode()}")
+
+
+def _p(t):
+    return c_void_p(0) if t is None else c_void_p(t.data_ptr())
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("custom_d_fine_b200 ops need CUDA tensors (no CPU path)")
+
+
+def _rows(x):
+    """View ``x`` [..., C] as rows with one uniform row stride; returns (tensor, n_rows, ld)."""
+    C = x.shape[-1]
+    if x.stride(-1) != 1 and C > 1:
+        x = x.contiguous()
+    n = x.numel() // C if C else 0
+    if x.dim() == 1:
+        return x, 1, C
+    ld = x.stride(-2)
+    exp = ld
+    ok = ld >= C
+    for d in range(x.dim() - 2, -1, -1):
+        if x.shape[d] != 1 and x.stride(d) != exp:
+            ok = False
+            break
+        exp *= x.shape[d]
+    if not ok or (x.data_ptr() % 16) or (ld % 4):
+        x = x.contiguous()
+        ld = C
+    return x, n, ld
+
+
+_USE_TC = os.environ.get("DFINE_GEMM", "tc") != "simt"   # developer switch for kernel bring-up only
+
+
+def _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy):
+    if not _USE_TC:
+        return False
+    t, l, b, r = pad
+    return bool(lib().dfine_conv_tc_supported(Cin, Cout, k, k, stride, t, l, b, r, c_long(ldx), c_long(ldy)))
+
+
+# ------------------------------------------------------------------------------------------------
+# raw launchers (no autograd)
+# ------------------------------------------------------------------------------------------------
+def _conv_fwd(x, ldx, wr, bias, y, ldy, geom, act, stats=None):
+    """geom = (B,H,W,Cin,OH,OW,Cout,k,stride,pad4)."""
+    B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
+    if _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy):
+        _check(lib().dfine_conv_fwd_tc(_p(x), _p(wr), _p(bias), _p(y), _p(stats), B, H, W, Cin, Cout, k, k,
+                                       c_long(ldx), c_long(ldy), act, _stream()), "conv_fwd_tc")
+        return True
+    _check(lib().dfine_conv_fwd_simt(_p(x), _p(wr), _p(bias), _p(y), B, H, W, Cin, OH, OW, Cout, k, k, stride,
+                                     pad[0], pad[1], c_long(ldx), c_long(ldy), act, _stream()), "conv_fwd_simt")
+    return False
+
+
+def _conv_dgrad(dy, ldy, weight, dx, ldx, geom, wcache):
+    B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
+    if _tc_ok(Cout, Cin, k, stride, pad, ldy, ldx):
+        # data gradient of a stride-1 "same" conv = the same conv on dy with flipped, transposed taps
+        wd = wcache("wd", lambda: weight.flip(2, 3).permute(1, 2, 3, 0).contiguous())
+        _check(lib().dfine_conv_fwd_tc(_p(dy), _p(wd), None, _p(dx), None, B, OH, OW, Cout, Cin, k, k, c_long(ldy),
+                                       c_long(ldx), 0, _stream()), "conv_dgrad_tc")
+        return
+    wr = wcache("wr", lambda: weight.permute(0, 2, 3, 1).contiguous())
+    _check(lib().dfine_conv_dgrad_simt(_p(dy), _p(wr), _p(dx), B, H, W, Cin, OH, OW, Cout, k, k, stride, pad[0],
+                                       pad[1], c_long(ldx), c_long(ldy), _stream()), "conv_dgrad_simt")
+
+
+def _conv_wgrad(dy, ldy, x, ldx, geom):
+    B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
+    dwr = torch.zeros((Cout, k, k, Cin), device=dy.device, dtype=torch.float32)
+    if _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy):
+        _check(lib().dfine_conv_wgrad_tc(_p(dy), _p(x), _p(dwr), B, H, W, Cin, Cout, k, k, c_long(ldx), c_long(ldy),
+                                         _stream()), "conv_wgrad_tc")
+    else:
+        _check(lib().dfine_conv_wgrad_simt(_p(dy), _p(x), _p(dwr), B, H, W, Cin, OH, OW, Cout, k, k, stride, pad[0],
+                                           pad[1], c_long(ldx), c_long(ldy), _stream()), "conv_wgrad_simt")
+    return dwr
+
+
+class _WCache:
+    """Re-laid weight copies, keyed by parameter identity + version (optimizer steps bump it)."""
+
+    def __init__(self):
+        self.d = {}
+
+    def get(self, w, kind, make):
+        key = (id(w), kind)
+        ent = self.d.get(key)
+        ver = w._version
+        if ent is not None and ent[0] == ver and ent[1].device == w.device:
+            return ent[1]
+        with torch.no_grad():
+            val = make()
+        self.d[key] = (ver, val)
+        return val
+
+
+_wcache = _WCache()
+
+
+# ------------------------------------------------------------------------------------------------
+# conv + BatchNorm + act (+LAB, +adds)
+# ------------------------------------------------------------------------------------------------
+class _ConvBnAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bn_w, bn_b, lab_s, lab_b, pre_add, post_add, running_mean, running_var, cfg):
+        stride, pad, groups, training, momentum, eps, act, frozen = cfg
+        _req_cuda(x, weight)
+        if x.stride(-1) != 1 or x.dim() != 4:
+            x = x.contiguous()
+        B, H, W, Cin = x.shape
+        ok = x.stride(2) >= Cin and x.stride(1) == W * x.stride(2) and x.stride(0) == H * W * x.stride(2) \
+            and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0
+        if not ok:
+            x = x.contiguous()
+        ldx = x.stride(2)
+        Cout, _, k, _ = weight.shape
+        pt, pl, pb, pr = pad
+        OH = (H + pt + pb - k) // stride + 1
+        OW = (W + pl + pr - k) // stride + 1
+        geom = (B, H, W, Cin, OH, OW, Cout, k, stride, pad)
+        dev = x.device
+        conv_out = torch.empty((B, OH, OW, Cout), device=dev, dtype=torch.float32)
+        M = B * OH * OW
+        need_stats = training
+        stats = torch.zeros(2 * Cout, device=dev, dtype=torch.float64) if need_stats else None
+        depthwise = groups > 1
+        if depthwise:
+            assert groups == Cin == Cout and pt == pl == pb == pr, "only depthwise grouped convs are on the path"
+            if ldx != Cin:
+                x = x.contiguous()
+                ldx = Cin
+            wt = _wcache.get(weight, "dw", lambda: weight.reshape(Cout, k * k).t().contiguous())
+            _check(lib().dfine_dwconv_fwd(_p(x), _p(wt), _p(conv_out), B, H, W, Cin, k, stride, pt, _stream()),
+                   "dwconv_fwd")
+            fused_stats = False
+        else:
+            wr = _wcache.get(weight, "wr", lambda: weight.permute(0, 2, 3, 1).contiguous())
+            fused_stats = _conv_fwd(x, ldx, wr, None, conv_out, Cout, geom, 0, stats)
+        if need_stats and not fused_stats:
+            _check(lib().dfine_bn_stats(_p(conv_out), _p(stats), c_long(M), Cout, _stream()), "bn_stats")
+        scale = torch.empty(Cout, device=dev, dtype=torch.float32)
+        shift = torch.empty(Cout, device=dev, dtype=torch.float32)
+        mean = invstd = None
+        if training:
+            mean = torch.empty(Cout, device=dev, dtype=torch.float32)
+            invstd = torch.empty(Cout, device=dev, dtype=torch.float32)
+            _check(lib().dfine_bn_finalize(_p(stats), _p(bn_w), _p(bn_b), _p(running_mean), _p(running_var), _p(mean),
+                                           _p(invstd), _p(scale), _p(shift), c_long(M), Cout, c_float(momentum),
+                                           c_float(eps), _stream()), "bn_finalize")
+        else:
+            _check(lib().dfine_bn_fold(_p(bn_w), _p(bn_b), _p(running_mean), _p(running_var), _p(scale), _p(shift),
+                                       Cout, c_float(eps), _stream()), "bn_fold")
+        if pre_add is not None:
+            pre_add = pre_add.contiguous()
+        if post_add is not None:
+            post_add = post_add.contiguous()
+        y = torch.empty_like(conv_out)
+        _check(lib().dfine_bn_apply(_p(conv_out), _p(scale), _p(shift), _p(pre_add), _p(post_add), _p(lab_s),
+                                    _p(lab_b), _p(y), c_long(M), Cout, ACT[act], _stream()), "bn_apply")
+        ctx.save_for_backward(x, weight, conv_out, scale, shift, mean, invstd, pre_add, lab_s, lab_b, bn_w)
+        ctx.geom, ctx.ldx, ctx.cfg = geom, ldx, cfg
+        ctx.has_post = post_add is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, conv_out, scale, shift, mean, invstd, pre_add, lab_s, lab_b, bn_w = ctx.saved_tensors
+        stride, pad, groups, training, momentum, eps, act, frozen = ctx.cfg
+        B, H, W, Cin, OH, OW, Cout, k, _, _ = ctx.geom
+        dy = dy.contiguous()
+        M = B * OH * OW
+        dev = dy.device
+        bn_train = training and mean is not None
+        need_red = bn_train or lab_s is not None
+        red = torch.zeros(2 * Cout + 2, device=dev, dtype=torch.float64) if need_red else None
+        if need_red:
+            # (eval-mode BN with LAB still needs the LAB scalar gradients; mean/invstd unused then)
+            m_ = mean if mean is not None else shift
+            i_ = invstd if invstd is not None else scale
+            _check(lib().dfine_bn_bwd_reduce(_p(dy), _p(conv_out), _p(scale), _p(shift), _p(m_), _p(i_), _p(pre_add),
+                                             _p(lab_s), _p(red), c_long(M), Cout, ACT[act], _stream()),
+                   "bn_bwd_reduce")
+        dconv = torch.empty_like(conv_out)
+        dpre = torch.empty_like(conv_out) if (pre_add is not None and ctx.needs_input_grad[6]) else None
+        _check(lib().dfine_bn_bwd_apply(_p(dy), _p(conv_out), _p(scale), _p(shift), _p(mean), _p(invstd), _p(pre_add),
+                                        _p(lab_s), _p(red), _p(dconv), _p(dpre), c_long(M), Cout, ACT[act],
+                                        1 if bn_train else 0, _stream()), "bn_bwd_apply")
+        g_bn_w = g_bn_b = g_lab_s = g_lab_b = None
+        if red is not None:
+            redf = red.float()
+            if bn_train and bn_w is not None and ctx.needs_input_grad[2]:
+                g_bn_w, g_bn_b = redf[Cout:2 * Cout], redf[:Cout]
+            elif not bn_train and bn_w is not None and ctx.needs_input_grad[2]:
+                raise RuntimeError("eval-mode BatchNorm affine gradients are not on the training path")
+            if lab_s is not None:
+                g_lab_s, g_lab_b = redf[2 * Cout:2 * Cout + 1], redf[2 * Cout + 1:2 * Cout + 2]
+        g_x = g_w = None
+        ldx = ctx.ldx
+        if groups > 1:
+            wt = _wcache.get(weight, "dw", lambda: weight.reshape(Cout, k * k).t().contiguous())
+            if ctx.needs_input_grad[0]:
+                g_x = torch.empty((B, H, W, Cin), device=dev, dtype=torch.float32)
+                _check(lib().dfine_dwconv_bwd_data(_p(dconv), _p(wt), _p(g_x), B, H, W, Cin, k, stride, pad[0],
+                                                   _stream()), "dwconv_bwd_data")
+            if ctx.needs_input_grad[1]:
+                dwt = torch.zeros((k * k, Cout), device=dev, dtype=torch.float32)
+                _check(lib().dfine_dwconv_bwd_weight(_p(dconv), _p(x), _p(dwt), B, H, W, Cin, k, stride, pad[0],
+                                                     _stream()), "dwconv_bwd_weight")
+                g_w = dwt.t().reshape(Cout, 1, k, k)
+        else:
+            if ctx.needs_input_grad[0]:
+                g_x = torch.empty((B, H, W, Cin), device=dev, dtype=torch.float32)
+                _conv_dgrad(dconv, Cout, weight, g_x, Cin, ctx.geom, lambda kind, mk: _wcache.get(weight, kind, mk))
+            if ctx.needs_input_grad[1]:
+                g_w = _conv_wgrad(dconv, Cout, x, ldx, ctx.geom).permute(0, 3, 1, 2)
+        g_post = dy if ctx.has_post else None
+        return g_x, g_w, g_bn_w, g_bn_b, g_lab_s, g_lab_b, dpre, g_post, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# linear (+bias, +act)
+# ------------------------------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        _req_cuda(x, w)
+        N, Kd = w.shape
+        x2, M, ldx = _rows(x)
+        if not w.is_contiguous():
+            w = w.contiguous()
+        out = torch.empty(x.shape[:-1] + (N,), device=x.device, dtype=torch.float32)
+        geom = (1, 1, M, Kd, 1, M, N, 1, 1, (0, 0, 0, 0))
+        fused_act = act if act in (None, "relu") else None
+        _conv_fwd(x2, ldx, w, b, out, N, geom, ACT[fused_act])
+        saved_z = None
+        if act is not None and fused_act is None:
+            saved_z = out
+            out = torch.empty_like(saved_z)
+            _check(lib().dfine_act_fwd(_p(saved_z), _p(out), c_long(out.numel()), ACT[act], _stream()), "act_fwd")
+        ctx.save_for_backward(x2, w, saved_z if saved_z is not None else (out if act == "relu" else None))
+        ctx.meta = (M, ldx, geom, act, b is not None, x.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, z = ctx.saved_tensors
+        M, ldx, geom, act, has_bias, xshape = ctx.meta
+        N, Kd = w.shape
+        dy = dy.contiguous()
+        if act is not None:
+            dz = torch.empty_like(dy)
+            _check(lib().dfine_act_bwd(_p(dy), _p(z), _p(dz), c_long(dy.numel()), ACT[act], _stream()), "act_bwd")
+            dy = dz
+        g_x = g_w = g_b = None
+        if ctx.needs_input_grad[0]:
+            g_x = torch.empty(xshape, device=dy.device, dtype=torch.float32)
+            if _tc_ok(N, Kd, 1, 1, (0, 0, 0, 0), N, Kd):
+                wt = w.t().contiguous()
+                _check(lib().dfine_conv_fwd_tc(_p(dy), _p(wt), None, _p(g_x), None, 1, 1, M, N, Kd, 1, 1, c_long(N),
+                                               c_long(Kd), 0, _stream()), "linear_dgrad_tc")
+            else:
+                _check(lib().dfine_conv_dgrad_simt(_p(dy), _p(w), _p(g_x), 1, 1, M, Kd, 1, M, N, 1, 1, 1, 0, 0,
+                                                   c_long(Kd), c_long(N), _stream()), "linear_dgrad_simt")
+        if ctx.needs_input_grad[1]:
+            g_w = _conv_wgrad(dy, N, x2, ldx, geom).reshape(N, Kd)
+        if has_bias and ctx.needs_input_grad[2]:
+            g_b = torch.zeros(N, device=dy.device, dtype=torch.float32)
+            _check(lib().dfine_colsum(_p(dy), _p(g_b), c_long(M), N, c_long(N), _stream()), "colsum")
+        return g_x, g_w, g_b, None
+
+
+# ------------------------------------------------------------------------------------------------
+# layernorm (+ fused residual)
+# ------------------------------------------------------------------------------------------------
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, res, w, b, eps):
+        _req_cuda(x, w)
+        x = x.contiguous()
+        res = res.contiguous() if res is not None else None
+        D = x.shape[-1]
+        rows = x.numel() // D
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+        _check(lib().dfine_layernorm_fwd(_p(x), _p(res), _p(w), _p(b), _p(y), _p(mean), _p(rstd), c_long(rows), D,
+                                         c_float(eps), _stream()), "layernorm_fwd")
+        ctx.save_for_backward(x, res, w, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, res, w, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        D = x.shape[-1]
+        rows = x.numel() // D
+        dx = torch.empty_like(x)
+        dwb = torch.zeros(2, D, device=x.device, dtype=torch.float32)
+        _check(lib().dfine_layernorm_bwd(_p(dy), _p(x), _p(res), _p(w), _p(mean), _p(rstd), _p(dx), _p(dwb[0]),
+                                         _p(dwb[1]), c_long(rows), D, _stream()), "layernorm_bwd")
+        return dx, (dx if res is not None else None), dwb[0], dwb[1], None
+
+
+# ------------------------------------------------------------------------------------------------
+# attention core
+# ------------------------------------------------------------------------------------------------
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qk, v, heads, mask):
+        _req_cuda(qk, v)
+        qk, v = qk.contiguous(), v.contiguous()
+        B, S, D = v.shape
+        hd = D // heads
+        o = torch.empty_like(v)
+        lse = torch.empty((B, heads, S), device=v.device, dtype=torch.float32)
+        m8 = None
+        if mask is not None:
+            m8 = mask.to(torch.uint8).contiguous()
+        scale = hd ** -0.5
+        q, k = qk, qk[..., D:]
+        _check(lib().dfine_attn_fwd(_p(q), c_long(2 * D), c_void_p(qk.data_ptr() + 4 * D), c_long(2 * D), _p(v),
+                                    c_long(D), _p(m8), _p(o), c_long(D), _p(lse), B, S, heads, hd, c_float(scale),
+                                    _stream()), "attn_fwd")
+        ctx.save_for_backward(qk, v, o, lse, m8)
+        ctx.meta = (B, S, D, heads, hd, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qk, v, o, lse, m8 = ctx.saved_tensors
+        B, S, D, heads, hd, scale = ctx.meta
+        do = do.contiguous()
+        dqk = torch.empty_like(qk)
+        dv = torch.empty_like(v)
+        dsum = torch.empty_like(lse)
+        _check(lib().dfine_attn_bwd(_p(qk), c_long(2 * D), c_void_p(qk.data_ptr() + 4 * D), c_long(2 * D), _p(v),
+                                    c_long(D), _p(m8), _p(o), c_long(D), _p(do), c_long(D), _p(lse), _p(dsum),
+                                    _p(dqk), c_long(2 * D), c_void_p(dqk.data_ptr() + 4 * D), c_long(2 * D), _p(dv),
+                                    c_long(D), B, S, heads, hd, c_float(scale), _stream()), "attn_bwd")
+        return dqk, dv, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-scale deformable attention
+# ------------------------------------------------------------------------------------------------
+class _Msda(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, memory, proj, ref, pscale, shapes, points, heads, n_off, offset_scale):
+        _req_cuda(memory, proj, ref)
+        memory, proj = memory.contiguous(), proj.contiguous()
+        ref = ref.detach().contiguous().float()
+        B, L, D = memory.shape
+        Q = proj.shape[1]
+        hd = D // heads
+        hw = (c_int * (2 * len(shapes)))(*[int(v) for s in shapes for v in s])
+        pts = (c_int * len(points))(*[int(p) for p in points])
+        ld = proj.shape[-1]
+        out = torch.empty((B, Q, D), device=memory.device, dtype=torch.float32)
+        _check(lib().dfine_msda_fwd(_p(memory), _p(proj), c_long(ld), c_void_p(proj.data_ptr() + 4 * n_off),
+                                    c_long(ld), _p(ref), _p(pscale), _p(out), B, Q, L, heads, hd, len(shapes), hw,
+                                    pts, c_float(offset_scale), _stream()), "msda_fwd")
+        ctx.save_for_backward(memory, proj, ref, pscale)
+        ctx.meta = (B, Q, L, D, heads, hd, [tuple(s) for s in shapes], list(points), n_off, offset_scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        memory, proj, ref, pscale = ctx.saved_tensors
+        B, Q, L, D, heads, hd, shapes, points, n_off, offset_scale = ctx.meta
+        gout = gout.contiguous()
+        hw = (c_int * (2 * len(shapes)))(*[int(v) for s in shapes for v in s])
+        pts = (c_int * len(points))(*[int(p) for p in points])
+        ld = proj.shape[-1]
+        gmem = torch.zeros_like(memory)
+        gproj = torch.empty_like(proj)
+        _check(lib().dfine_msda_bwd(_p(memory), _p(proj), c_long(ld), c_void_p(proj.data_ptr() + 4 * n_off),
+                                    c_long(ld), _p(ref), _p(pscale), _p(gout), _p(gmem), _p(gproj), c_long(ld),
+                                    c_void_p(gproj.data_ptr() + 4 * n_off), c_long(ld), B, Q, L, heads, hd,
+                                    len(shapes), hw, pts, c_float(offset_scale), _stream()), "msda_bwd")
+        return gmem, gproj, None, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# small spatial ops
+# ------------------------------------------------------------------------------------------------
+class _MaxPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _req_cuda(x)
+        x = x.contiguous()
+        B, H, W, C = x.shape
+        y = torch.empty_like(x)
+        _check(lib().dfine_maxpool2x2_fwd(_p(x), _p(y), B, H, W, C, _stream()), "maxpool_fwd")
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        B, H, W, C = x.shape
+        dx = torch.empty_like(x)
+        _check(lib().dfine_maxpool2x2_bwd(_p(x), _p(dy.contiguous()), _p(dx), B, H, W, C, _stream()), "maxpool_bwd")
+        return dx
+
+
+class _Upsample2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _req_cuda(x)
+        x = x.contiguous()
+        B, H, W, C = x.shape
+        y = torch.empty((B, 2 * H, 2 * W, C), device=x.device, dtype=torch.float32)
+        _check(lib().dfine_upsample2x_fwd(_p(x), _p(y), B, H, W, C, _stream()), "upsample_fwd")
+        ctx.shape = (B, H, W, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, H, W, C = ctx.shape
+        dx = torch.empty((B, H, W, C), device=dy.device, dtype=torch.float32)
+        _check(lib().dfine_upsample2x_bwd(_p(dy.contiguous()), _p(dx), B, H, W, C, _stream()), "upsample_bwd")
+        return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# the kernel table
+# ------------------------------------------------------------------------------------------------
+class CudaOps:
+    name = "libdfine_sm100"
+
+    def __init__(self):
+        lib()
+        if not torch.cuda.is_available():
+            raise RuntimeError("custom_d_fine_b200 needs a CUDA device (sm_100a); there is no CPU compute path")
+        _check(lib().dfine_check_device(), "device check")
+
+    # ---- conv / norm ----
+    def conv_bn_act(self, x, w, stride, pad, groups, bn_w, bn_b, running_mean, running_var, num_batches_tracked,
+                    training, momentum=0.1, eps=1e-5, act=None, lab_scale=None, lab_bias=None, pre_add=None,
+                    post_add=None):
+        frozen = num_batches_tracked is None
+        if training and num_batches_tracked is not None:
+            num_batches_tracked.add_(1)
+        cfg = (stride, tuple(pad), groups, bool(training), float(momentum), float(eps), act, frozen)
+        return _ConvBnAct.apply(x, w, bn_w, bn_b, lab_scale, lab_bias, pre_add, post_add, running_mean, running_var,
+                                cfg)
+
+    def maxpool2x2_s1_padbr(self, x):
+        return _MaxPool.apply(x)
+
+    def upsample_nearest2x(self, x):
+        return _Upsample2x.apply(x)
+
+    def cat(self, xs, dim=-1):
+        return torch.cat(list(xs), dim)
+
+    # ---- dense ----
+    def linear(self, x, w, b=None, act=None):
+        return _Linear.apply(x, w, b, act)
+
+    def layernorm(self, x, w, b, eps=1e-5, residual=None):
+        return _LayerNorm.apply(x, residual, w, b, eps)
+
+    def attention(self, qk, v, heads, mask=None):
+        return _Attention.apply(qk, v, heads, mask)
+
+    def msda(self, memory, spatial_shapes, points, heads, proj, n_off, ref, pscale, offset_scale=0.5):
+        return _Msda.apply(memory, proj, ref, pscale, spatial_shapes, points, heads, n_off, offset_scale)
+
+    # ---- decoder head glue (elementwise; composed from device tensor ops for now) ----
+    def gate_mix(self, g, x1, x2):
+        g1, g2 = torch.sigmoid(g).chunk(2, dim=-1)
+        return g1 * x1 + g2 * x2
+
+    def fdr_decode(self, corners, ref, project, reg_scale):
+        shape = corners.shape
+        nb = project.shape[0]
+        p = torch.softmax(corners.reshape(-1, nb), dim=1)
+        d = (p @ project.to(p.dtype)).reshape(list(shape[:-1]) + [4])
+        rs = abs(reg_scale)
+        sw, sh = ref[..., 2] / rs, ref[..., 3] / rs
+        x1 = ref[..., 0] - (0.5 * rs + d[..., 0]) * sw
+        y1 = ref[..., 1] - (0.5 * rs + d[..., 1]) * sh
+        x2 = ref[..., 0] + (0.5 * rs + d[..., 2]) * sw
+        y2 = ref[..., 1] + (0.5 * rs + d[..., 3]) * sh
+        return torch.stack([(x1 + x2) / 2, (y1 + y2) / 2, x2 - x1, y2 - y1], -1)
+
+    def lqe_stat(self, corners, k, reg_max):
+        B, L, _ = corners.shape
+        prob = torch.softmax(corners.reshape(B, L, 4, reg_max + 1), dim=-1)
+        top, _ = prob.topk(k, dim=-1)
+        return torch.cat([top, top.mean(dim=-1, keepdim=True)], -1).reshape(B, L, -1)
+
+    def mask_dot(self, embed, feat_nhwc):
+        raise NotImplementedError("segmentation head is a SURVEY §8(f) 'next' row")
+
+    # ---- matcher ----
+    @torch.no_grad()
+    def match_device(self, logits, boxes, labels, tboxes, toff_dev, sumT, Tmax, alpha, gamma, w_class, w_bbox,
+                     w_giou, want_cost=False):
+        """logits [NL,B,Q,C], boxes [NL,B,Q,4] contiguous; returns device int64 [NL,sumT] x2 (+ cost)."""
+        NL, B, Q, C = logits.shape
+        dev = logits.device
+        out_q = torch.zeros((NL, sumT), device=dev, dtype=torch.int64)
+        out_t = torch.zeros((NL, sumT), device=dev, dtype=torch.int64)
+        cost = torch.zeros((NL, Q * sumT), device=dev, dtype=torch.float32) if want_cost else None
+        ws_bytes = lib().dfine_matcher_workspace_bytes(NL, B, Q, Tmax)
+        ws = torch.empty(ws_bytes // 4, device=dev, dtype=torch.float32) if ws_bytes else None
+        _check(lib().dfine_matcher(_p(logits), _p(boxes), _p(labels), _p(tboxes), _p(toff_dev), _p(out_q), _p(out_t),
+                                   _p(cost), _p(ws), NL, B, Q, C, sumT, Tmax, c_float(alpha), c_float(gamma),
+                                   c_float(w_class), c_float(w_bbox), c_float(w_giou), _stream()), "matcher")
+        return out_q, out_t, cost
+
+    @torch.no_grad()
+    def match(self, logits_list, boxes_list, targets, alpha=0.25, gamma=2.0, w_class=2.0, w_bbox=5.0, w_giou=2.0):
+        logits = torch.stack([l.detach().float() for l in logits_list]).contiguous()
+        boxes = torch.stack([b.detach().float() for b in boxes_list]).contiguous()
+        _req_cuda(logits, boxes)
+        NL, B, Q, C = logits.shape
+        sizes = [int(t["labels"].shape[0]) for t in targets]
+        sumT, Tmax = sum(sizes), max(sizes) if sizes else 0
+        empty = (torch.zeros(0, dtype=torch.int64), torch.zeros(0, dtype=torch.int64))
+        if sumT == 0:
+            return [[empty for _ in range(B)] for _ in range(NL)]
+        dev = logits.device
+        labels = torch.cat([t["labels"] for t in targets]).to(dev, torch.int64).contiguous()
+        tboxes = torch.cat([t["boxes"] for t in targets]).to(dev, torch.float32).contiguous()
+        offs = [0]
+        for s in sizes:
+            offs.append(offs[-1] + s)
+        toff = torch.tensor(offs, dtype=torch.int32).to(dev, non_blocking=True)
+        out_q, out_t, _ = self.match_device(logits, boxes, labels, tboxes, toff, sumT, Tmax, alpha, gamma, w_class,
+                                            w_bbox, w_giou)
+        both = torch.stack([out_q, out_t]).cpu()        # the step's single matcher D2H
+        res = []
+        for l in range(NL):
+            per = []
+            for b in range(B):
+                n = min(Q, sizes[b])
+                if n == 0:
+                    per.append(empty)
+                else:
+                    per.append((both[0, l, offs[b]:offs[b] + n].clone(), both[1, l, offs[b]:offs[b] + n].clone()))
+            res.append(per)
+        return res

@@ -76,9 +76,9 @@ class DeformAttnParams(nn.Module):
         w = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
         b = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
         proj = K.linear(query, w, b)
-        return K.msda(memory, spatial_shapes, self.num_points_list, self.num_heads,
-                      proj[..., :n_off], proj[..., n_off:], ref, self.num_points_scale,
-                      self.offset_scale)
+        # proj packs [sampling offsets | attention logits] per query
+        return K.msda(memory, spatial_shapes, self.num_points_list, self.num_heads, proj, n_off, ref,
+                      self.num_points_scale, self.offset_scale)
 
 
 class GateParams(nn.Module):
@@ -109,7 +109,7 @@ class DecoderLayer(nn.Module):
 
     def forward(self, tgt, ref, memory, spatial_shapes, attn_mask, qpos):
         a = mha(self.self_attn, tgt + qpos, tgt, attn_mask)
-        tgt = K.layernorm(tgt + a, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        tgt = K.layernorm(a, self.norm1.weight, self.norm1.bias, self.norm1.eps, residual=tgt)
         c = self.cross_attn(tgt + qpos, ref, memory, spatial_shapes)
         tgt = self.gateway(tgt, c)
         f = K.linear(tgt, self.linear1.weight, self.linear1.bias, act="relu")

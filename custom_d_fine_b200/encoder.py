@@ -85,10 +85,10 @@ class AIFILayer(nn.Module):
 
     def forward(self, src, pos):
         a = mha(self.self_attn, src + pos, src)
-        src = K.layernorm(src + a, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        src = K.layernorm(a, self.norm1.weight, self.norm1.bias, self.norm1.eps, residual=src)
         f = K.linear(src, self.linear1.weight, self.linear1.bias, act="gelu")
         f = K.linear(f, self.linear2.weight, self.linear2.bias)
-        return K.layernorm(src + f, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        return K.layernorm(f, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=src)
 
 
 class AIFIStack(nn.Module):

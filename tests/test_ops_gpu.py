@@ -1,0 +1,216 @@
+"""GPU parity tests: every kernel-table op of the CUDA path against the CPU oracle (oracle/torch_ops.py)
+on the same seeded inputs, called through the C ABI (ctypes) exactly as the model calls them.
+
+Tolerances: fp32 CUDA-core kernels 2e-5 relative to the tensor's max magnitude; tcgen05 kind::tf32
+kernels 2e-3 (10-bit mantissa operands, fp32 accumulation) — the same operand precision cuDNN uses
+for the reference's convolutions on GPU (torch.backends.cudnn.allow_tf32 defaults to True).
+"""
+import math
+
+import pytest
+import torch
+
+from tests.util import check_close, run_both
+
+pytestmark = pytest.mark.gpu
+
+F32 = 3e-5
+TF32 = 3e-3
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _conv_case(cuda_ops, oracle_ops, B, H, W, Cin, Cout, k, stride, pad, groups, act, lab, pre, post, training, tol,
+               seed=0, slice_in=0):
+    g = _g(seed)
+    xfull = torch.randn(B, H, W, Cin + slice_in, generator=g)
+    w = torch.randn(Cout, Cin // groups, k, k, generator=g) * (1.0 / math.sqrt(k * k * Cin / groups))
+    bn_w = torch.rand(Cout, generator=g) + 0.5
+    bn_b = torch.randn(Cout, generator=g) * 0.1
+    rm = torch.randn(Cout, generator=g) * 0.1
+    rv = torch.rand(Cout, generator=g) + 0.5
+    ls = torch.tensor([1.3]) if lab else None
+    lb = torch.tensor([-0.2]) if lab else None
+    pt, pl, pb, pr = pad
+    OH = (H + pt + pb - k) // stride + 1
+    OW = (W + pl + pr - k) // stride + 1
+    pre_t = torch.randn(B, OH, OW, Cout, generator=g) if pre else None
+    post_t = torch.randn(B, OH, OW, Cout, generator=g) if post else None
+    ins = [xfull.requires_grad_(), w.requires_grad_(), bn_w.requires_grad_(), bn_b.requires_grad_()]
+    if lab:
+        ins += [ls.requires_grad_(), lb.requires_grad_()]
+    if pre:
+        ins.append(pre_t.requires_grad_())
+    if post:
+        ins.append(post_t.requires_grad_())
+    state = {}
+
+    def fn(K, x, w, bw, bb, *rest):
+        rest = list(rest)
+        l_s = rest.pop(0) if lab else None
+        l_b = rest.pop(0) if lab else None
+        p1 = rest.pop(0) if pre else None
+        p2 = rest.pop(0) if post else None
+        dev = x.device
+        r_m, r_v = rm.clone().to(dev), rv.clone().to(dev)
+        nbt = torch.zeros((), dtype=torch.int64, device=dev)
+        xin = x[..., slice_in:] if slice_in else x
+        y = K.conv_bn_act(xin, w, stride, pad, groups, bw, bb, r_m, r_v, nbt, training=training, momentum=0.1,
+                          eps=1e-5, act=act, lab_scale=l_s, lab_bias=l_b, pre_add=p1, post_add=p2)
+        state[str(dev.type)] = (r_m.cpu(), r_v.cpu(), int(nbt))
+        return y
+
+    errs = run_both(fn, cuda_ops, oracle_ops, ins, tol, tol * 3, seed)
+    if training:
+        check_close("running_mean", state["cuda"][0], state["cpu"][0], tol)
+        check_close("running_var", state["cuda"][1], state["cpu"][1], tol)
+        assert state["cuda"][2] == state["cpu"][2] == 1
+    return errs
+
+
+CONV_CASES = [
+    # name, B,H,W,Cin,Cout,k,stride,pad,groups,act,lab,pre,post,training,tol
+    ("stem1_3x3s2", 2, 64, 64, 3, 24, 3, 2, (1, 1, 1, 1), 1, "relu", True, False, False, True, F32),
+    ("stem2a_2x2_padbr", 2, 32, 32, 24, 12, 2, 1, (0, 0, 1, 1), 1, "relu", True, False, False, True, F32),
+    ("stem3_3x3s2", 2, 32, 32, 48, 24, 3, 2, (1, 1, 1, 1), 1, "relu", True, False, False, True, F32),
+    ("dw3x3s2", 2, 40, 40, 96, 96, 3, 2, (1, 1, 1, 1), 96, None, False, False, False, True, F32),
+    ("dw5x5", 2, 20, 20, 128, 128, 5, 1, (2, 2, 2, 2), 128, "relu", True, False, False, True, F32),
+    ("pw1x1_tc", 2, 40, 40, 160, 48, 1, 1, (0, 0, 0, 0), 1, "relu", True, False, False, True, TF32),
+    ("pw1x1_tc_big", 2, 20, 20, 896, 384, 1, 1, (0, 0, 0, 0), 1, "relu", True, False, True, True, TF32),
+    ("c3x3_tc_32", 2, 40, 40, 32, 32, 3, 1, (1, 1, 1, 1), 1, "relu", True, False, False, True, TF32),
+    ("c3x3_tc_128", 2, 20, 20, 128, 128, 3, 1, (1, 1, 1, 1), 1, "silu", False, False, False, True, TF32),
+    ("c3x3_tc_128_odd", 1, 23, 37, 128, 128, 3, 1, (1, 1, 1, 1), 1, "silu", False, False, False, True, TF32),
+    ("repvgg_pre_add", 2, 20, 20, 128, 128, 1, 1, (0, 0, 0, 0), 1, "silu", False, True, False, True, TF32),
+    ("proj_eval", 2, 20, 20, 384, 256, 1, 1, (0, 0, 0, 0), 1, None, False, False, False, False, TF32),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_bn_act(cuda_ops, oracle_ops, case):
+    _conv_case(cuda_ops, oracle_ops, *case[1:])
+
+
+def test_conv_channel_slice_input(cuda_ops, oracle_ops):
+    # RepNCSPELAN4 feeds the second half of cv1's output to cv2 (hybrid_encoder.py:203-206): strided view
+    _conv_case(cuda_ops, oracle_ops, 2, 20, 20, 128, 64, 1, 1, (0, 0, 0, 0), 1, "silu", False, False, False, True,
+               TF32, slice_in=128)
+
+
+LINEAR_CASES = [
+    ("ffn_relu", (3, 50, 256), 1024, "relu", TF32),
+    ("ffn_gelu", (3, 50, 256), 1024, "gelu", TF32),
+    ("score_head", (2, 37, 256), 80, None, TF32),
+    ("bbox_head_4", (2, 37, 256), 4, None, F32),
+    ("corners_132", (2, 37, 256), 132, None, TF32),
+    ("lqe_out_1", (2, 37, 64), 1, None, F32),
+    ("lqe_in_20", (2, 37, 20), 64, "relu", TF32),
+    ("qpos_4", (2, 37, 4), 512, "relu", F32),
+    ("big", (1, 8400, 256), 256, None, TF32),
+]
+
+
+@pytest.mark.parametrize("case", LINEAR_CASES, ids=[c[0] for c in LINEAR_CASES])
+def test_linear(cuda_ops, oracle_ops, case):
+    _, xs, n, act, tol = case
+    g = _g(1)
+    x = torch.randn(*xs, generator=g).requires_grad_()
+    w = (torch.randn(n, xs[-1], generator=g) / math.sqrt(xs[-1])).requires_grad_()
+    b = torch.randn(n, generator=g).requires_grad_()
+    run_both(lambda K, x, w, b: K.linear(x, w, b, act=act), cuda_ops, oracle_ops, [x, w, b], tol, tol * 3)
+
+
+def test_layernorm_residual(cuda_ops, oracle_ops):
+    g = _g(2)
+    x = torch.randn(4, 77, 256, generator=g).requires_grad_()
+    r = torch.randn(4, 77, 256, generator=g).requires_grad_()
+    w = (torch.rand(256, generator=g) + 0.5).requires_grad_()
+    b = torch.randn(256, generator=g).requires_grad_()
+    run_both(lambda K, x, r, w, b: K.layernorm(x, w, b, 1e-5, residual=r), cuda_ops, oracle_ops, [x, r, w, b], F32,
+             1e-4)
+    run_both(lambda K, x, w, b: K.layernorm(x, w, b, 1e-5), cuda_ops, oracle_ops, [x, w, b], F32, 1e-4)
+
+
+@pytest.mark.parametrize("S,D,heads,masked", [(400, 256, 8, False), (500, 256, 8, True), (130, 128, 8, True),
+                                               (67, 384, 8, False)])
+def test_attention(cuda_ops, oracle_ops, S, D, heads, masked):
+    g = _g(3)
+    qk = torch.randn(2, S, 2 * D, generator=g).requires_grad_()
+    v = torch.randn(2, S, D, generator=g).requires_grad_()
+    mask = None
+    if masked:  # CDN-style block mask: first n_dn rows/cols are denoising groups
+        n_dn, grp = (S // 5) * 2, 10
+        idx = torch.arange(S)
+        is_dn = idx < n_dn
+        gid = idx // grp
+        mask = is_dn[None, :] & (~is_dn[:, None] | (gid[:, None] != gid[None, :]))
+
+    def fn(K, qk, v):
+        return K.attention(qk, v, heads, None if mask is None else mask.to(qk.device))
+
+    run_both(fn, cuda_ops, oracle_ops, [qk, v], 5e-5, 2e-4)
+
+
+@pytest.mark.parametrize("D,shapes,points", [(256, [(80, 80), (40, 40), (20, 20)], [3, 6, 3]),
+                                              (128, [(40, 40), (20, 20)], [6, 6]),
+                                              (256, [(13, 17), (7, 9), (4, 5)], [3, 6, 3])])
+def test_msda(cuda_ops, oracle_ops, D, shapes, points):
+    g = _g(4)
+    heads, B, Q = 8, 2, 150
+    L, P = sum(h * w for h, w in shapes), sum(points)
+    mem = torch.randn(B, L, D, generator=g).requires_grad_()
+    proj = torch.randn(B, Q, heads * P * 3, generator=g)
+    proj[..., : heads * P * 2] *= 3.0          # offsets large enough to hit the borders
+    proj.requires_grad_()
+    ref = torch.rand(B, Q, 4, generator=g)
+    ref[..., 2:] = ref[..., 2:] * 0.4 + 0.02
+    ref[0, 0] = torch.tensor([0.0, 1.0, 0.5, 0.5])   # corner query: samples fall outside the map
+    pscale = torch.tensor([1.0 / n for n in points for _ in range(n)])
+
+    def fn(K, mem, proj):
+        dev = mem.device
+        return K.msda(mem, shapes, points, heads, proj, heads * P * 2, ref.to(dev), pscale.to(dev), 0.5)
+
+    run_both(fn, cuda_ops, oracle_ops, [mem, proj], F32, 2e-4)
+
+
+def test_maxpool_upsample(cuda_ops, oracle_ops):
+    g = _g(5)
+    x = torch.randn(2, 17, 19, 24, generator=g)
+    x[0, :, :, 0] = -1.0   # all-negative plane: the zero padding wins at the border
+    x = x.requires_grad_()
+    run_both(lambda K, x: K.maxpool2x2_s1_padbr(x), cuda_ops, oracle_ops, [x], 0.0, 0.0)
+    y = torch.randn(2, 10, 10, 256, generator=g).requires_grad_()
+    run_both(lambda K, y: K.upsample_nearest2x(y), cuda_ops, oracle_ops, [y], 0.0, 1e-6)
+
+
+def test_tc_matches_simt(cuda_ops):
+    """tcgen05 kernels against the CUDA-core kernels of the same library on identical device data."""
+    import ctypes
+    from custom_d_fine_b200 import cuda_ops as co
+    L = co.lib()
+    g = _g(6)
+    for (B, H, W, Cin, Cout, k) in [(2, 40, 40, 128, 128, 3), (1, 1, 4000, 256, 512, 1), (2, 80, 80, 64, 64, 3),
+                                    (3, 20, 20, 1280, 384, 1), (1, 1, 999, 20, 64, 1)]:
+        x = torch.randn(B, H, W, Cin, generator=g).cuda()
+        wr = (torch.randn(Cout, k, k, Cin, generator=g) / math.sqrt(k * k * Cin)).cuda()
+        dy = torch.randn(B, H, W, Cout, generator=g).cuda()
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        p = k // 2
+        y_tc, y_si = torch.zeros(B, H, W, Cout).cuda(), torch.zeros(B, H, W, Cout).cuda()
+        stats = torch.zeros(2 * Cout, dtype=torch.float64).cuda()
+        co._check(L.dfine_conv_fwd_tc(co._p(x), co._p(wr), None, co._p(y_tc), co._p(stats), B, H, W, Cin, Cout, k, k,
+                                      Cin, Cout, 0, st), "tc")
+        co._check(L.dfine_conv_fwd_simt(co._p(x), co._p(wr), None, co._p(y_si), B, H, W, Cin, H, W, Cout, k, k, 1, p,
+                                        p, Cin, Cout, 0, st), "simt")
+        check_close(f"fwd {B,H,W,Cin,Cout,k}", y_tc, y_si, TF32)
+        M = B * H * W
+        check_close("fused stats sum", stats[:Cout].float(), y_si.reshape(M, Cout).sum(0), TF32 * 5)
+        check_close("fused stats sumsq", stats[Cout:].float(), (y_si.reshape(M, Cout) ** 2).sum(0), TF32)
+        dw_tc, dw_si = torch.zeros(Cout, k, k, Cin).cuda(), torch.zeros(Cout, k, k, Cin).cuda()
+        co._check(L.dfine_conv_wgrad_tc(co._p(dy), co._p(x), co._p(dw_tc), B, H, W, Cin, Cout, k, k, Cin, Cout, st),
+                  "wgrad_tc")
+        co._check(L.dfine_conv_wgrad_simt(co._p(dy), co._p(x), co._p(dw_si), B, H, W, Cin, H, W, Cout, k, k, 1, p, p,
+                                          Cin, Cout, st), "wgrad_simt")
+        check_close(f"wgrad {B,H,W,Cin,Cout,k}", dw_tc, dw_si, TF32)
