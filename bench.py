@@ -1,0 +1,317 @@
+"""Benchmark of the D-FINE train-step hot path (BASELINE.json: images/s at 640x640, D-FINE-m, batch 16 per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = model forward (with CDN), criterion (on-device Hungarian matcher), backward, gradient clip,
+AdamW, EMA — the body of the reference's hot loop (train.py:550-586, 512-535) — on one synthetic batch
+(torch.rand images, 10 boxes per image, 80 classes).  Prints ONE JSON line on rank 0.
+
+  value        images/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e          images/s through the public step API with HOST inputs: pinned-memory H2D of images and
+               targets every step and a D2H read of the loss inside the timed region
+  roofline     MSDeformableAttention kernel (the larger of fwd / bwd): algorithmic bytes / measured
+               launch duration (CUDA events around the launches inside the timed region) vs measured HBM peak
+  cpu_baseline the oracle port (this repo's host graph driven by oracle/torch_ops.py — the reference's
+               arithmetic restated on torch CPU ops) on the box's host cores, bounded sample (N=1, rank 0)
+
+--impl reference times that same CPU port with all host threads (the reference is pure Python with
+unshipped dependencies and no installable package) on a bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+MODEL, HW, NUM_CLASSES, T_PER_IMG = "m", 640, 80, 10
+CPU_SAMPLE_BATCH = 2
+
+
+def synthetic(batch, seed, device="cpu", pin=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(batch, 3, HW, HW, generator=g)
+    labels = torch.randint(0, NUM_CLASSES, (batch, T_PER_IMG), generator=g)
+    cxcy = torch.rand(batch, T_PER_IMG, 2, generator=g) * 0.6 + 0.2
+    wh = torch.rand(batch, T_PER_IMG, 2, generator=g) * 0.25 + 0.05
+    boxes = torch.cat([cxcy, wh], -1)
+    if pin:
+        x, labels, boxes = x.pin_memory(), labels.pin_memory(), boxes.pin_memory()
+    return x, labels, boxes
+
+
+def to_targets(labels, boxes):
+    return [{"labels": labels[i], "boxes": boxes[i]} for i in range(labels.shape[0])]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [c.strip() for c in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_step(device, world, local_rank):
+    from custom_d_fine_b200 import dist as dist_utils
+    from custom_d_fine_b200.model import build_loss, build_model, build_optimizer
+    from custom_d_fine_b200.train import ModelEMA, TrainStep
+    torch.manual_seed(0)
+    model = build_model(MODEL, NUM_CLASSES, False, device, img_size=(HW, HW))
+    # non-zero heads so every loss term (incl. DDF, zero at fresh init) does real work
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() >= 2 and float(p.abs().max()) == 0.0:
+                p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(p.device))
+    model.train()
+    ema = ModelEMA(model, 0.9998)
+    net = dist_utils.wrap_ddp(model, local_rank) if world > 1 else model
+    loss_fn = build_loss(MODEL, NUM_CLASSES, 0.0, False)
+    opt = build_optimizer(model, lr=1.5e-4, backbone_lr=2e-5, betas=(0.9, 0.999), weight_decay=1.25e-4, base_lr=1.5e-4)
+    return TrainStep(net, loss_fn, opt, scheduler=None, ema=ema, clip_max_norm=0.1)
+
+
+def run_ours(args):
+    from custom_d_fine_b200 import cuda_ops
+    from custom_d_fine_b200 import dist as dist_utils
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist_utils.init_distributed_mode()
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    B = args.batch
+    step = build_step(device, world, local_rank)
+    hx, hl, hb = synthetic(B, 1234 + rank, pin=True)
+    dx, dl, db = hx.to(device), hl.to(device), hb.to(device)
+    dtargets = to_targets(dl, db)
+
+    def sync_all():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        sync_all()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        sync_all()
+        ms = torch.tensor([s.elapsed_time(e)], device=device)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident():
+        step(dx, dtargets)
+
+    def step_e2e():
+        x = hx.to(device, non_blocking=True)
+        l = hl.to(device, non_blocking=True)
+        b = hb.to(device, non_blocking=True)
+        loss, _ = step(x, to_targets(l, b))
+        return float(loss.item())          # D2H read of the step's result
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    cuda_ops.counters.watch = ("msda_fwd", "msda_bwd")
+    cuda_ops.counters.timed = {}
+    l0 = cuda_ops.counters.launches
+    ms_total = timed(step_resident, args.steps)
+    launches = cuda_ops.counters.launches - l0
+    cuda_ops.counters.watch = ()
+    kern = {}
+    for name, recs in cuda_ops.counters.timed.items():
+        durs = [s.elapsed_time(e) for s, e, _ in recs]
+        kern[name] = (sum(durs) / len(durs), recs[0][2], len(durs))
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    roof = None
+    if kern:
+        name = max(kern, key=lambda k: kern[k][0])
+        ms, nbytes, n = kern[name]
+        ach = nbytes / (ms * 1e-3) / 1e9
+        roof = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(ach / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": round(ms, 4), "launches_timed": n, "algorithmic_bytes_per_launch": nbytes,
+                "others": {k: {"avg_launch_ms": round(v[0], 4), "GB/s": round(v[1] / (v[0] * 1e-3) / 1e9, 1)}
+                           for k, v in kern.items() if k != name}}
+    cpu = cpu_baseline(steps=2, warmup=1) if world == 1 and not args.no_cpu_baseline else None
+    imgs = B * world * args.steps
+    line = {
+        "metric": "images/sec (640x640) D-FINE-m train step", "value": round(imgs / (ms_total * 1e-3), 2),
+        "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "tf32 tensor-core operands / fp32 storage+accumulate", "data": "synthetic",
+        "config": {"workload": f"D-FINE-{MODEL} detect train step (fwd + criterion + bwd + clip + AdamW + EMA), "
+                               f"batch {B}/GPU, {HW}x{HW}, {T_PER_IMG} boxes/img, COCO-80 classes, Lq=500",
+                   "global_batch": B * world, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (activations + grads > 10 GB) exceeds the 126 MB L2"},
+        "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 2), "unit": "images/s", "ms_per_step": round(ms_e2e / args.steps, 3),
+                "h2d_bytes_per_step": int(hx.numel() * 4 + hl.numel() * 8 + hb.numel() * 4), "d2h_bytes_per_step": 4},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def cpu_step_fn(batch):
+    """The CPU port: this repo's host graph with the oracle provider (reference arithmetic on torch CPU ops)."""
+    from custom_d_fine_b200 import kernels
+    from custom_d_fine_b200.model import build_loss, build_model
+    from oracle.torch_ops import OracleOps
+    torch.manual_seed(0)
+    model = build_model(MODEL, NUM_CLASSES, False, "cpu", img_size=(HW, HW))
+    model.train()
+    loss_fn = build_loss(MODEL, NUM_CLASSES, 0.0, False)
+    x, l, b = synthetic(batch, 1234)
+    targets = to_targets(l, b)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
+    ops = OracleOps()
+
+    def step():
+        with kernels.use(ops):
+            out = model(x, targets=targets)
+            loss = sum(loss_fn(out, targets).values())
+            loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
+        opt.step()
+        opt.zero_grad()
+        return float(loss.detach())
+
+    return step
+
+
+def cpu_baseline(steps, warmup):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_fn(CPU_SAMPLE_BATCH)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": round(CPU_SAMPLE_BATCH * steps / dt, 3), "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} train steps of batch {CPU_SAMPLE_BATCH} (D-FINE-{MODEL}, {HW}x{HW}) after {warmup} warm-up, "
+                      f"torch CPU ops, {cores} threads"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_fn(CPU_SAMPLE_BATCH)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = round(CPU_SAMPLE_BATCH * args.steps / dt, 3)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    sample = (f"each step = one train step on a bounded sample of {CPU_SAMPLE_BATCH} images of the workload "
+              f"(D-FINE-{MODEL}, {HW}x{HW}, fwd+criterion+bwd+clip+AdamW), torch CPU ops, {cores} threads, rank 0 only")
+    print(json.dumps({
+        "impl": "reference", "metric": "images/sec (640x640) D-FINE-m train step", "value": v, "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": f"D-FINE-{MODEL} detect train step, {HW}x{HW}, {T_PER_IMG} boxes/img, COCO-80 classes "
+                               f"(CPU arm: {CPU_SAMPLE_BATCH} images per step)", "parallelism": "cpu"},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU (BASELINE config: 16)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -60,9 +60,38 @@ def abi_prototypes(header: Path = _HEADER):
     return protos
 
 
+class _Counters:
+    """Launch accounting for bench.py: every C-ABI call that enqueues kernels bumps ``launches``;
+    ``timed`` (kernel-family name -> list of (start, end, algorithmic_bytes)) is filled only while
+    ``watch`` names that family (CUDA events on the launching stream)."""
+    launches = 0
+    watch = ()
+    timed = {}
+
+
+counters = _Counters()
+
+
 def _check(rc, what):
     if rc != 0:
         raise RuntimeError(f"libdfine_sm100 {what} failed (rc={rc}): {lib().dfine_last_error().decode()}")
+    counters.launches += 1
+
+
+class _timed:
+    def __init__(self, name, nbytes):
+        self.on = name in counters.watch
+        self.name, self.nbytes = name, nbytes
+
+    def __enter__(self):
+        if self.on:
+            self.s, self.e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.s.record()
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.e.record()
+            counters.timed.setdefault(self.name, []).append((self.s, self.e, self.nbytes))
 
 
 def _p(t):
@@ -101,7 +130,17 @@ def _rows(x):
     return x, n, ld
 
 
-_USE_TC = os.environ.get("DFINE_GEMM", "tc") != "simt"   # developer switch for kernel bring-up only
+# Dense conv / linear shapes the tcgen05 kernels accept run on tensor cores (kind::tf32 operands, fp32
+# accumulate — the precision class of the reference's cuDNN convolutions on GPU); "simt" routes them to
+# the fp32 CUDA-core kernels of the same library instead (strict-fp32 parity runs and kernel bring-up).
+_USE_TC = os.environ.get("DFINE_GEMM", "tc") != "simt"
+
+
+def set_gemm_mode(mode: str) -> None:
+    global _USE_TC
+    if mode not in ("tc", "simt"):
+        raise ValueError(mode)
+    _USE_TC = mode == "tc"
 
 
 def _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy):
@@ -431,7 +470,10 @@ class _Msda(torch.autograd.Function):
         pts = (c_int * len(points))(*[int(p) for p in points])
         ld = proj.shape[-1]
         out = torch.empty((B, Q, D), device=memory.device, dtype=torch.float32)
-        _check(lib().dfine_msda_fwd(_p(memory), _p(proj), c_long(ld), c_void_p(proj.data_ptr() + 4 * n_off),
+        # algorithmic bytes: value + offsets + logits + ref read, out written
+        nbytes = 4 * (memory.numel() + proj.numel() + ref.numel() + out.numel())
+        with _timed("msda_fwd", nbytes):
+          _check(lib().dfine_msda_fwd(_p(memory), _p(proj), c_long(ld), c_void_p(proj.data_ptr() + 4 * n_off),
                                     c_long(ld), _p(ref), _p(pscale), _p(out), B, Q, L, heads, hd, len(shapes), hw,
                                     pts, c_float(offset_scale), _stream()), "msda_fwd")
         ctx.save_for_backward(memory, proj, ref, pscale)
@@ -448,7 +490,10 @@ class _Msda(torch.autograd.Function):
         ld = proj.shape[-1]
         gmem = torch.zeros_like(memory)
         gproj = torch.empty_like(proj)
-        _check(lib().dfine_msda_bwd(_p(memory), _p(proj), c_long(ld), c_void_p(proj.data_ptr() + 4 * n_off),
+        # value/offsets/logits/ref/gout read, gvalue read-modify-write (2x), goff/glogit written
+        nbytes = 4 * (memory.numel() + proj.numel() + ref.numel() + gout.numel() + 2 * gmem.numel() + gproj.numel())
+        with _timed("msda_bwd", nbytes):
+          _check(lib().dfine_msda_bwd(_p(memory), _p(proj), c_long(ld), c_void_p(proj.data_ptr() + 4 * n_off),
                                     c_long(ld), _p(ref), _p(pscale), _p(gout), _p(gmem), _p(gproj), c_long(ld),
                                     c_void_p(gproj.data_ptr() + 4 * n_off), c_long(ld), B, Q, L, heads, hd,
                                     len(shapes), hw, pts, c_float(offset_scale), _stream()), "msda_bwd")

@@ -1,0 +1,83 @@
+"""GPU parity of the on-device Hungarian matcher (cost blocks + LSAP, one launch for all layers) against
+the CPU oracle: bit-exact assignment indices, cost blocks within fp32 rounding."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.lsap import lsap
+from tests.util import check_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(NL, B, Q, C, sizes, seed, dup=False):
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(NL, B, Q, C, generator=g) * 2.0
+    cxcy = torch.rand(NL, B, Q, 2, generator=g)
+    wh = torch.rand(NL, B, Q, 2, generator=g) * 0.4 + 0.01
+    boxes = torch.cat([cxcy, wh], -1)
+    if dup:  # groups of identical predictions -> exactly tied costs
+        logits = logits[:, :, : Q // 4].repeat(1, 1, 4, 1)
+        boxes = boxes[:, :, : Q // 4].repeat(1, 1, 4, 1)
+    targets = []
+    for t in sizes:
+        targets.append({"labels": torch.randint(0, C, (t,), generator=g),
+                        "boxes": torch.cat([torch.rand(t, 2, generator=g) * 0.6 + 0.2,
+                                            torch.rand(t, 2, generator=g) * 0.25 + 0.05], 1)})
+    return logits, boxes, targets
+
+
+@pytest.mark.parametrize("name,NL,B,Q,C,sizes,dup", [
+    ("train_like", 6, 4, 300, 80, [10, 10, 10, 10], False),
+    ("ragged_empty", 3, 5, 300, 80, [10, 0, 37, 3, 1], False),
+    ("ties", 2, 3, 300, 80, [12, 7, 25], True),
+    ("more_targets_than_queries", 2, 2, 5, 20, [12, 5], False),
+    ("crowded", 1, 2, 300, 80, [180, 120], False),
+])
+def test_matcher_vs_oracle(cuda_ops, oracle_ops, name, NL, B, Q, C, sizes, dup):
+    logits, boxes, targets = _problem(NL, B, Q, C, sizes, seed=len(name), dup=dup)
+    dev_targets = [{k: v.cuda() for k, v in t.items()} for t in targets]
+    got = cuda_ops.match([l.cuda() for l in logits], [b.cuda() for b in boxes], dev_targets)
+    # (1) LSAP bit-exactness: solve the DEVICE-computed cost blocks with the CPU oracle
+    offs = np.cumsum([0] + sizes)
+    labels = torch.cat([t["labels"] for t in targets]).cuda()
+    tboxes = torch.cat([t["boxes"] for t in targets]).cuda()
+    toff = torch.tensor(offs, dtype=torch.int32).cuda()
+    oq, ot, cost = cuda_ops.match_device(logits.cuda().contiguous(), boxes.cuda().contiguous(), labels, tboxes, toff,
+                                         int(offs[-1]), max(sizes), 0.25, 2.0, 2.0, 5.0, 2.0, want_cost=True)
+    cost = cost.cpu()
+    for l in range(NL):
+        for b, t in enumerate(sizes):
+            qi, ti = got[l][b]
+            assert qi.dtype == torch.int64 and ti.dtype == torch.int64 and not qi.is_cuda
+            if t == 0:
+                assert qi.numel() == 0
+                continue
+            blk = cost[l, Q * offs[b]: Q * offs[b] + Q * t].reshape(Q, t)
+            r, c = lsap(blk.double().numpy())
+            assert qi.tolist() == r.tolist() and ti.tolist() == c.tolist(), (name, l, b)
+            # (2) cost arithmetic vs the oracle's torch restatement of matcher.py:135-172
+            ref = oracle_ops.match_cost(logits[l, b], boxes[l, b], targets[b]["labels"], targets[b]["boxes"])
+            check_close("cost block", blk, torch.nan_to_num(ref, nan=1.0), 2e-6)
+    # (3) end to end vs the oracle matcher (same indices unless two costs differ by < 1 ulp)
+    if not dup:
+        ref = oracle_ops.match(list(logits), list(boxes), targets)
+        for l in range(NL):
+            for b in range(B):
+                assert got[l][b][0].tolist() == ref[l][b][0].tolist(), (name, l, b)
+                assert got[l][b][1].tolist() == ref[l][b][1].tolist(), (name, l, b)
+
+
+def test_matcher_scipy_agreement(cuda_ops):
+    scipy_opt = pytest.importorskip("scipy.optimize")
+    logits, boxes, targets = _problem(2, 3, 300, 80, [10, 22, 5], seed=11)
+    dev_targets = [{k: v.cuda() for k, v in t.items()} for t in targets]
+    got = cuda_ops.match([l.cuda() for l in logits], [b.cuda() for b in boxes], dev_targets)
+    from oracle.torch_ops import OracleOps
+    K = OracleOps()
+    for l in range(2):
+        for b in range(3):
+            c = torch.nan_to_num(K.match_cost(logits[l, b], boxes[l, b], targets[b]["labels"], targets[b]["boxes"]),
+                                 nan=1.0)
+            r, cc = scipy_opt.linear_sum_assignment(c.numpy())
+            assert got[l][b][0].tolist() == r.tolist() and got[l][b][1].tolist() == cc.tolist()
