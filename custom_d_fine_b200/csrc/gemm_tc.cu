@@ -18,7 +18,8 @@
 //              weights.
 //   tc_wgrad : dWr[co, tap, ci] += sum_{pixel} dY[pixel, co] * X[pixel + tap, ci]
 //              both operands MN-major (the reduction runs over pixels, channels are contiguous):
-//              32-pixel x 32-channel TMA boxes, UMMA descriptors with a_major = b_major = MN;
+//              32-pixel x 32-channel TMA boxes (SWIZZLE_128B_ATOM_32B), UMMA descriptors with a_major =
+//              b_major = MN and the 128B_BASE32B layout (the only one defined for MN-major tf32);
 //              split over pixel ranges, accumulated into dWr with red.global.add.f32.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = barrier init + TMEM alloc + MMA issuer,
@@ -117,13 +118,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // K-major : rows of 128 B (32 fp32 along K), 8-row atoms; SBO = 1024 B between 8-row groups.
 // MN-major: rows of 128 B (32 fp32 along M/N), 8 k-rows per atom; SBO = 1024 B between k groups,
 //           LBO = byte distance between consecutive 32-element M/N chunks.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B — the only layout the
+// hardware accepts for MN-major 32-bit (tf32) operands: 128-byte rows, 32-byte swizzle granularity,
+// 4 k-rows per atom (TMA side: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = 2) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout_type << 61;
     return d;
 }
 // instruction descriptor: D=f32, A=B=tf32, M=128, N=n; major bits 15/16 (0 = K-major, 1 = MN-major)
@@ -360,11 +365,11 @@ __global__ void __launch_bounds__(TC_THREADS) tc_wgrad_kernel(const __grid_const
                 const int s = kb % STAGES, ph = (kb / STAGES) & 1;
                 mbar_wait(&sm.full[s], ph);
                 tc_fence_after();
-                // chunk (32 channels) stride = 32 pixels * 128 B = 4096 B (LBO); 8-pixel k-group = 1024 B (SBO)
-                const uint64_t da = make_desc(smem_u32(sm.a[s]), 32 * BK * 4, 1024);
-                const uint64_t db = make_desc(smem_u32(sm.b[s]), 32 * BK * 4, 1024);
+                // chunk (32 channels) stride = 32 pixels * 128 B = 4096 B (LBO); 4-pixel k-atom = 512 B (SBO)
+                const uint64_t da = make_desc(smem_u32(sm.a[s]), 32 * BK * 4, 512, 1);
+                const uint64_t db = make_desc(smem_u32(sm.b[s]), 32 * BK * 4, 512, 1);
 #pragma unroll
-                for (int k = 0; k < 32 / 8; ++k)  // 8 pixels per UMMA = one 1024-byte atom -> +64 in 16-byte units
+                for (int k = 0; k < 32 / 8; ++k)  // 8 pixels (two k-atoms) per UMMA -> +1024 B = +64 in 16-byte units
                     umma_tf32(tmem, da + 64 * k, db + 64 * k, idesc, (kb | k) != 0);
                 umma_commit(&sm.empty[s]);
             }
@@ -415,7 +420,7 @@ EncodeTiledFn get_encode() {
 // 4-D fp32 tensor map (C, W, H, B) over an NHWC activation with pixel stride ld (elements),
 // 128-byte swizzle, zero OOB fill.
 int make_map4(CUtensorMap* m, const float* base, long C, long W, long H, long B, long ld, int box_c, int box_w,
-              int box_h, const char* who) {
+              int box_h, const char* who, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { dfine_set_error("%s: cuTensorMapEncodeTiled unavailable", who); return -2; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -423,7 +428,7 @@ int make_map4(CUtensorMap* m, const float* base, long C, long W, long H, long B,
     cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, (void*)base, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         dfine_set_error("%s: cuTensorMapEncodeTiled(4d) failed (%d) C=%ld W=%ld H=%ld B=%ld ld=%ld box=%d,%d,%d", who,
@@ -565,9 +570,9 @@ DFINE_API int dfine_conv_wgrad_tc(const float* dy, const float* x, float* dwr, i
     p.wchunks = ceil_div(W, 32);
     p.steps_total = (long)B * H * p.wchunks;
     CUtensorMap mdy, mx;
-    int rc = make_map4(&mdy, dy, Cout, W, H, B, ldy, 32, 32, 1, "conv_wgrad_tc(dy)");
+    int rc = make_map4(&mdy, dy, Cout, W, H, B, ldy, 32, 32, 1, "conv_wgrad_tc(dy)", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    rc = make_map4(&mx, x, Cin, W, H, B, ldx, 32, 32, 1, "conv_wgrad_tc(x)");
+    rc = make_map4(&mx, x, Cin, W, H, B, ldx, 32, 32, 1, "conv_wgrad_tc(x)", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
     rc = Cin <= 64 ? launch_wgrad<64>(mdy, mx, dwr, p, (cudaStream_t)stream)
                    : launch_wgrad<128>(mdy, mx, dwr, p, (cudaStream_t)stream);

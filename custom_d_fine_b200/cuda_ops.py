@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import weakref
 from ctypes import c_float, c_int, c_long, c_void_p
 from pathlib import Path
 
@@ -200,11 +201,11 @@ class _WCache:
         key = (id(w), kind)
         ent = self.d.get(key)
         ver = w._version
-        if ent is not None and ent[0] == ver and ent[1].device == w.device:
+        if ent is not None and ent[0] == ver and ent[2]() is w:      # id() can be recycled: check identity
             return ent[1]
         with torch.no_grad():
             val = make()
-        self.d[key] = (ver, val)
+        self.d[key] = (ver, val, weakref.ref(w))
         return val
 
 

@@ -32,7 +32,7 @@ def seeded_fill(module, seed=0):
         elif k.endswith("weight"):       # norm scales
             new = torch.rand(v.shape, generator=g) + 0.5
         elif "sampling_offsets.bias" in k:
-            new = v + torch.randn(v.shape, generator=g) * 0.1
+            new = v.cpu() + torch.randn(v.shape, generator=g) * 0.1
         else:
             new = torch.randn(v.shape, generator=g) * 0.1
         v.copy_(new)

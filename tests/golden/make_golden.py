@@ -103,6 +103,7 @@ def lsap_cases():
 if __name__ == "__main__":
     torch.set_num_threads(8)
     torch.save(model_case("n", 2, 320, 0), HERE / "model_n_320.pt")
+    torch.save(model_case("s", 2, 320, 1), HERE / "model_s_320.pt")
     torch.save(msda_case(3), HERE / "msda_ref.pt")
     torch.save(lsap_cases(), HERE / "lsap_scipy.pt")
     for f in HERE.glob("*.pt"):

@@ -38,7 +38,8 @@ def _conv_case(cuda_ops, oracle_ops, B, H, W, Cin, Cout, k, stride, pad, groups,
     OW = (W + pl + pr - k) // stride + 1
     pre_t = torch.randn(B, OH, OW, Cout, generator=g) if pre else None
     post_t = torch.randn(B, OH, OW, Cout, generator=g) if post else None
-    ins = [xfull.requires_grad_(), w.requires_grad_(), bn_w.requires_grad_(), bn_b.requires_grad_()]
+    # eval-mode BatchNorm (frozen backbones of l/x, inference) has no affine gradient on the path
+    ins = [xfull.requires_grad_(), w.requires_grad_(), bn_w.requires_grad_(training), bn_b.requires_grad_(training)]
     if lab:
         ins += [ls.requires_grad_(), lb.requires_grad_()]
     if pre:
@@ -62,7 +63,11 @@ def _conv_case(cuda_ops, oracle_ops, B, H, W, Cin, Cout, k, stride, pad, groups,
         state[str(dev.type)] = (r_m.cpu(), r_v.cpu(), int(nbt))
         return y
 
-    errs = run_both(fn, cuda_ops, oracle_ops, ins, tol, tol * 3, seed)
+    # tf32 forward differences flip a few ReLU masks (pre-activations within ~1e-3 of zero); each flip moves
+    # the affected gradient entries by O(1), so tf32+ReLU gradients are compared in the L2 norm
+    kink = tol == TF32 and act == "relu"
+    errs = run_both(fn, cuda_ops, oracle_ops, ins, tol, 8e-2 if kink else tol * 3, seed,
+                    grad_metric="l2" if kink else "max")
     if training:
         check_close("running_mean", state["cuda"][0], state["cpu"][0], tol)
         check_close("running_var", state["cuda"][1], state["cpu"][1], tol)
@@ -118,7 +123,9 @@ def test_linear(cuda_ops, oracle_ops, case):
     x = torch.randn(*xs, generator=g).requires_grad_()
     w = (torch.randn(n, xs[-1], generator=g) / math.sqrt(xs[-1])).requires_grad_()
     b = torch.randn(n, generator=g).requires_grad_()
-    run_both(lambda K, x, w, b: K.linear(x, w, b, act=act), cuda_ops, oracle_ops, [x, w, b], tol, tol * 3)
+    kink = tol == TF32 and act == "relu"
+    run_both(lambda K, x, w, b: K.linear(x, w, b, act=act), cuda_ops, oracle_ops, [x, w, b], tol,
+             8e-2 if kink else tol * 3, grad_metric="l2" if kink else "max")
 
 
 def test_layernorm_residual(cuda_ops, oracle_ops):
@@ -180,7 +187,7 @@ def test_maxpool_upsample(cuda_ops, oracle_ops):
     x = torch.randn(2, 17, 19, 24, generator=g)
     x[0, :, :, 0] = -1.0   # all-negative plane: the zero padding wins at the border
     x = x.requires_grad_()
-    run_both(lambda K, x: K.maxpool2x2_s1_padbr(x), cuda_ops, oracle_ops, [x], 0.0, 0.0)
+    run_both(lambda K, x: K.maxpool2x2_s1_padbr(x), cuda_ops, oracle_ops, [x], 0.0, 1e-6)
     y = torch.randn(2, 10, 10, 256, generator=g).requires_grad_()
     run_both(lambda K, y: K.upsample_nearest2x(y), cuda_ops, oracle_ops, [y], 0.0, 1e-6)
 
@@ -214,3 +221,11 @@ def test_tc_matches_simt(cuda_ops):
         co._check(L.dfine_conv_wgrad_simt(co._p(dy), co._p(x), co._p(dw_si), B, H, W, Cin, H, W, Cout, k, k, 1, p, p,
                                           Cin, Cout, st), "wgrad_simt")
         check_close(f"wgrad {B,H,W,Cin,Cout,k}", dw_tc, dw_si, TF32)
+        # data gradient: tcgen05 forward kernel on dy with flipped / transposed taps vs the CUDA-core dgrad
+        wd = wr.permute(0, 3, 1, 2).flip(2, 3).permute(1, 2, 3, 0).contiguous()     # [Cin, k, k, Cout]
+        dx_tc, dx_si = torch.zeros(B, H, W, Cin).cuda(), torch.zeros(B, H, W, Cin).cuda()
+        co._check(L.dfine_conv_fwd_tc(co._p(dy), co._p(wd), None, co._p(dx_tc), None, B, H, W, Cout, Cin, k, k, Cout,
+                                      Cin, 0, st), "dgrad_tc")
+        co._check(L.dfine_conv_dgrad_simt(co._p(dy), co._p(wr), co._p(dx_si), B, H, W, Cin, H, W, Cout, k, k, 1, p, p,
+                                          Cin, Cout, st), "dgrad_simt")
+        check_close(f"dgrad {B,H,W,Cin,Cout,k}", dx_tc, dx_si, TF32)

@@ -15,7 +15,14 @@ def check_close(name, got, want, tol):
     return e
 
 
-def run_both(fn, cuda_ops, oracle_ops, inputs, tol_fwd, tol_bwd, seed=0, grad_inputs=None):
+def check_l2(name, got, want, tol):
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
+    e = ((got - want).norm() / want.norm().clamp_min(1e-12)).item()
+    assert e <= tol, f"{name}: |diff|_2/|ref|_2 = {e:.3e} > {tol:.1e}"
+    return e
+
+
+def run_both(fn, cuda_ops, oracle_ops, inputs, tol_fwd, tol_bwd, seed=0, grad_metric="max"):
     """``fn(K, *tensors)`` -> tensor.  Runs on CPU with the oracle and on cuda:0 with the CUDA table,
     compares the output and the gradients of every floating-point input that requires grad."""
     cpu_in = [t.detach().clone().requires_grad_(t.requires_grad) if isinstance(t, torch.Tensor) else t for t in inputs]
@@ -32,7 +39,8 @@ def run_both(fn, cuda_ops, oracle_ops, inputs, tol_fwd, tol_bwd, seed=0, grad_in
         for i, (a, b) in enumerate(zip(gpu_in, cpu_in)):
             if isinstance(b, torch.Tensor) and b.requires_grad:
                 assert a.grad is not None, f"input {i}: no gradient from the CUDA path"
-                errs[f"grad{i}"] = check_close(f"grad of input {i}", a.grad, b.grad, tol_bwd)
+                chk = check_close if grad_metric == "max" else check_l2
+                errs[f"grad{i}"] = chk(f"grad of input {i}", a.grad, b.grad, tol_bwd)
     return errs
 
 
