@@ -13,6 +13,7 @@ B200-first differences (values unchanged):
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -72,16 +73,93 @@ def fdr_bin_targets(ref, gt_xyxy, reg_max, reg_scale, up, eps=0.1):
     return idx.clamp(min=0, max=reg_max - eps).detach(), w_r.detach(), w_l.detach()
 
 
-class _Flat:
-    """Matched pairs of one index set flattened across the batch (device tensors)."""
+class IndexPlan:
+    """Host-built, fixed-shape index table of one step.
 
-    def __init__(self, indices, targets, device):
-        b = torch.cat([torch.full_like(s, i) for i, (s, _) in enumerate(indices)])
-        q = torch.cat([s for s, _ in indices])
-        self.b, self.q = b.to(device, non_blocking=True), q.to(device, non_blocking=True)
-        self.tbox = torch.cat([t["boxes"][j.to(t["boxes"].device)] for t, (_, j) in zip(targets, indices)], 0)
-        self.tlabel = torch.cat([t["labels"][j.to(t["labels"].device)] for t, (_, j) in zip(targets, indices)])
-        self.n = int(q.numel())
+    Every index set the criterion needs — one Hungarian set per matched layer, the cross-layer "GO" union
+    (dfine_criterion.py:570-591) and the denoising set (809-831) — is laid out in ONE int64 table
+    ``[4, N]`` (rows: image b, query q, global target t, valid) so that a step needs a single small H2D
+    copy, and every set has a size that depends only on the targets' sizes (the GO union is padded to its
+    worst case with valid = 0).  Static shapes are what lets the loss + backward segment of the step be
+    replayed as a CUDA graph (custom_d_fine_b200/train.py)."""
+
+    def __init__(self, sizes, num_queries, n_sets, dn_positive_idx=None, dn_groups=0):
+        self.sizes = [int(s) for s in sizes]
+        self.Q = int(num_queries)
+        self.n_sets = n_sets
+        self.offs = np.cumsum([0] + self.sizes)
+        self.per_img = [min(self.Q, s) for s in self.sizes]
+        self.n_layer = int(sum(self.per_img))
+        self.go_cap = self.n_layer * n_sets
+        self.dn_groups = dn_groups
+        self.n_dn = int(sum(self.sizes)) * dn_groups if dn_positive_idx is not None else 0
+        self.total = self.n_layer * n_sets + self.go_cap + self.n_dn
+        self.table = torch.zeros((4, max(self.total, 1)), dtype=torch.int64)
+        self.counts = torch.zeros(2, dtype=torch.float32)
+        if torch.cuda.is_available():
+            self.table, self.counts = self.table.pin_memory(), self.counts.pin_memory()
+        self._dn_static = None
+        if self.n_dn:
+            # the denoising set depends on the targets' sizes only (dfine_criterion.py:809-831)
+            b = np.concatenate([np.full(s * dn_groups, i) for i, s in enumerate(self.sizes)]) if self.n_dn else []
+            q = np.concatenate([np.asarray(p.cpu() if hasattr(p, "cpu") else p).reshape(-1)[: s * dn_groups]
+                                for p, s in zip(dn_positive_idx, self.sizes) if s > 0] or [np.zeros(0)])
+            t = np.concatenate([np.tile(np.arange(s), dn_groups) + self.offs[i] for i, s in enumerate(self.sizes)])
+            self._dn_static = np.stack([b, q, t, np.ones_like(b)]).astype(np.int64)
+
+    def set_slice(self, k):
+        """Column range of matched set k (k < n_sets), 'go' or 'dn'."""
+        if k == "go":
+            o = self.n_layer * self.n_sets
+            return o, o + self.go_cap
+        if k == "dn":
+            o = self.n_layer * self.n_sets + self.go_cap
+            return o, o + self.n_dn
+        return k * self.n_layer, (k + 1) * self.n_layer
+
+    def fill(self, out_q, out_t):
+        """out_q / out_t: host int64 [n_sets, sumT] as written by the matcher kernel (pairs of image b start at
+        offs[b], min(Q, T_b) of them, sorted by query).  Returns the per-set per-image index lists too."""
+        tab = self.table.numpy()
+        tab[:] = 0
+        per_set = []
+        col = 0
+        for k in range(self.n_sets):
+            imgs = []
+            for b, n in enumerate(self.per_img):
+                o = self.offs[b]
+                q, t = out_q[k, o:o + n], out_t[k, o:o + n]
+                tab[0, col:col + n], tab[1, col:col + n] = b, q
+                tab[2, col:col + n], tab[3, col:col + n] = t + o, 1
+                col += n
+                imgs.append((torch.from_numpy(np.ascontiguousarray(q)), torch.from_numpy(np.ascontiguousarray(t))))
+            per_set.append(imgs)
+        return per_set
+
+    def fill_go(self, go):
+        tab = self.table.numpy()
+        o, e = self.set_slice("go")
+        tab[1, o:e] = self.Q          # padded entries scatter into the dummy query column
+        col = o
+        for b, (q, t) in enumerate(go):
+            n = int(q.numel())
+            tab[0, col:col + n], tab[1, col:col + n] = b, q.numpy()
+            tab[2, col:col + n], tab[3, col:col + n] = t.numpy() + self.offs[b], 1
+            col += n
+        if self._dn_static is not None:
+            o, e = self.set_slice("dn")
+            tab[:, o:e] = self._dn_static
+        return col - self.set_slice("go")[0]
+
+
+class _Set:
+    """One index set on the device (views into the plan table)."""
+
+    def __init__(self, tab, lo, hi, Q, padded):
+        self.b, self.qs, self.t = tab[0, lo:hi], tab[1, lo:hi], tab[2, lo:hi]
+        self.q = self.qs.clamp(max=Q - 1) if padded else self.qs      # gather index (always in range)
+        self.v = tab[3, lo:hi].to(torch.float32) if padded else None  # None = every entry valid
+        self.n = hi - lo
 
 
 class DFINECriterion(nn.Module):
@@ -99,39 +177,43 @@ class DFINECriterion(nn.Module):
         self.fgl_targets = self.fgl_targets_dn = None
         self.num_pos = self.num_neg = None
 
-    # ---- individual losses ---------------------------------------------------------------------
-    def loss_labels_vfl(self, out, flat, num_boxes):
+    # ---- individual losses (S: _Set, tg: (labels_cat, boxes_cat)) -------------------------------
+    def loss_labels_vfl(self, out, S, tg, num_boxes):
+        assert S.v is None, "per-layer / denoising sets are never padded"
         logits = out["pred_logits"]
         B, Q, C = logits.shape
-        ious, _ = paired_iou_union(cxcywh_to_xyxy(out["pred_boxes"][flat.b, flat.q]), cxcywh_to_xyxy(flat.tbox))
+        tbox, tlabel = tg[1][S.t], tg[0][S.t]
+        ious, _ = paired_iou_union(cxcywh_to_xyxy(out["pred_boxes"][S.b, S.q]), cxcywh_to_xyxy(tbox))
         ious = ious.detach()
         onehot = torch.zeros(B, Q, C + 1, dtype=torch.int64, device=logits.device)
         cls = torch.full((B, Q), self.num_classes, dtype=torch.int64, device=logits.device)
-        cls[flat.b, flat.q] = flat.tlabel
+        cls[S.b, S.q] = tlabel
         onehot.scatter_(-1, cls.unsqueeze(-1), 1)
         target = onehot[..., :-1]
         score_o = torch.zeros((B, Q), dtype=logits.dtype, device=logits.device)
-        score_o[flat.b, flat.q] = ious.to(logits.dtype)
+        score_o[S.b, S.q] = ious.to(logits.dtype)
         target_score = score_o.unsqueeze(-1) * target
         p = torch.sigmoid(logits).detach()
         weight = self.alpha * p.pow(self.gamma) * (1 - target) + target_score
         loss = F.binary_cross_entropy_with_logits(logits, target_score, weight=weight, reduction="none")
         return {"loss_vfl": loss.mean(1).sum() * Q / num_boxes}
 
-    def loss_boxes(self, out, flat, num_boxes):
-        src = out["pred_boxes"][flat.b, flat.q]
-        l1 = F.l1_loss(src, flat.tbox, reduction="none").sum() / num_boxes
-        giou = (1 - paired_giou(cxcywh_to_xyxy(src), cxcywh_to_xyxy(flat.tbox))).sum() / num_boxes
-        return {"loss_bbox": l1, "loss_giou": giou}
+    def loss_boxes(self, out, S, tg, num_boxes):
+        src, tbox = out["pred_boxes"][S.b, S.q], tg[1][S.t]
+        l1 = F.l1_loss(src, tbox, reduction="none").sum(-1)
+        gi = 1 - paired_giou(cxcywh_to_xyxy(src), cxcywh_to_xyxy(tbox))
+        if S.v is not None:
+            l1, gi = l1 * S.v, gi * S.v
+        return {"loss_bbox": l1.sum() / num_boxes, "loss_giou": gi.sum() / num_boxes}
 
-    def loss_local(self, out, flat, num_boxes, T=5):
+    def loss_local(self, out, S, tg, num_boxes, T=5):
         if "pred_corners" not in out:
             return {}
         nb = self.reg_max + 1
         is_dn = "is_dn" in out
-        pc = out["pred_corners"][flat.b, flat.q].reshape(-1, nb)
-        ref = out["ref_points"][flat.b, flat.q].detach()
-        gt_xyxy = cxcywh_to_xyxy(flat.tbox)
+        pc = out["pred_corners"][S.b, S.q].reshape(-1, nb)
+        ref = out["ref_points"][S.b, S.q].detach()
+        gt_xyxy = cxcywh_to_xyxy(tg[1][S.t])
         with torch.no_grad():
             cached = self.fgl_targets_dn if is_dn else self.fgl_targets
             if cached is None:
@@ -141,8 +223,13 @@ class DFINECriterion(nn.Module):
                 else:
                     self.fgl_targets = cached
         t_idx, w_r, w_l = cached
-        ious, _ = paired_iou_union(cxcywh_to_xyxy(out["pred_boxes"][flat.b, flat.q]), gt_xyxy)
-        w_t = ious.unsqueeze(-1).repeat(1, 4).reshape(-1).detach()
+        ious, _ = paired_iou_union(cxcywh_to_xyxy(out["pred_boxes"][S.b, S.q]), gt_xyxy)
+        ious = ious.detach()
+        if S.v is not None:
+            ious_w = ious * S.v
+        else:
+            ious_w = ious
+        w_t = ious_w.unsqueeze(-1).repeat(1, 4).reshape(-1)
         left = t_idx.long()
         fgl = (F.cross_entropy(pc, left, reduction="none") * w_l
                + F.cross_entropy(pc, left + 1, reduction="none") * w_r) * w_t.float()
@@ -155,11 +242,14 @@ class DFINECriterion(nn.Module):
                 losses["loss_ddf"] = pred_all.sum() * 0          # last dn layer is its own teacher
                 return losses
             identical = (pred_all == teacher).all()              # torch.equal without the host sync (197)
-            w_loc = out["teacher_logits"].sigmoid().max(dim=-1)[0].detach().clone()
-            B, Q = w_loc.shape
-            matched = torch.zeros((B, Q), dtype=torch.bool, device=w_loc.device)
-            matched[flat.b, flat.q] = True
-            w_loc[flat.b, flat.q] = ious.detach().to(w_loc.dtype)
+            w_max = out["teacher_logits"].sigmoid().max(dim=-1)[0].detach()
+            B, Q = w_max.shape
+            # one dummy query column absorbs the padded (invalid) entries of the GO set
+            matched = torch.zeros((B, Q + 1), dtype=torch.bool, device=w_max.device)
+            matched[S.b, S.qs] = torch.ones(S.n, dtype=torch.bool, device=w_max.device)   # (device-side: capturable)
+            w_loc = torch.cat([w_max, w_max.new_zeros(B, 1)], 1)
+            w_loc[S.b, S.qs] = ious.to(w_loc.dtype)
+            matched, w_loc = matched[:, :Q], w_loc[:, :Q]
             m4 = matched.unsqueeze(-1).repeat(1, 1, 4).reshape(-1)
             w4 = w_loc.unsqueeze(-1).repeat(1, 1, 4).reshape(-1)
             kl = F.kl_div(F.log_softmax(pred_all / T, dim=1), F.softmax(teacher.detach() / T, dim=1),
@@ -176,7 +266,7 @@ class DFINECriterion(nn.Module):
             losses["loss_ddf"] = torch.where(identical, pred_all.sum() * 0, ddf)
         return losses
 
-    def loss_masks(self, out, flat, num_boxes):
+    def loss_masks(self, out, S, tg, num_boxes):
         if "pred_masks" not in out:
             return {}
         raise NotImplementedError("mask losses (dfine_criterion.py:239-556) are a SURVEY §8(f) 'next' row")
@@ -220,65 +310,100 @@ class DFINECriterion(nn.Module):
                 out.append((z, z))
         return out
 
-    # ---- orchestration ---------------------------------------------------------------------------
-    def _terms(self, out, targets, flats, num, suffix, losses, only=None):
+    # ---- the three stages of a step (custom_d_fine_b200/train.py replays 1 and 3 as CUDA graphs) --------
+    @staticmethod
+    def _matched_layers(outputs):
+        main = {k: v for k, v in outputs.items() if "aux" not in k}
+        aux, pre, enc = outputs["aux_outputs"], outputs["pre_outputs"], outputs["enc_aux_outputs"]
+        return main, aux, pre, enc
+
+    def match(self, outputs, targets):
+        """Stage 1 (device): all L+2 Hungarian problems of the step in one launch (dfine_criterion.py:619-632).
+        Returns whatever ``plan`` needs: device index tensors (CUDA path) or host index lists (oracle)."""
+        assert "aux_outputs" in outputs, ""
+        main, aux, pre, enc = self._matched_layers(outputs)
+        layers = [main] + list(aux) + [pre] + list(enc)
+        labels = torch.cat([t["labels"] for t in targets]) if targets else None
+        boxes = torch.cat([t["boxes"] for t in targets]) if targets else None
+        return self.matcher.match_layers_raw(layers, targets), (labels, boxes)
+
+    def plan(self, outputs, targets, raw, plan=None):
+        """Stage 2 (host): matcher indices -> GO union -> normalisers -> one pinned index table."""
+        main, aux, pre, enc = self._matched_layers(outputs)
+        n_sets = 1 + len(aux) + 1 + len(enc)
+        Q = outputs["pred_logits"].shape[1]
+        sizes = [int(t["labels"].shape[0]) for t in targets]
+        meta = outputs.get("dn_meta") if "dn_outputs" in outputs else None
+        if plan is None:
+            plan = IndexPlan(sizes, Q, n_sets, meta["dn_positive_idx"] if meta else None,
+                             meta["dn_num_group"] if meta else 0)
+        out_q, out_t = self.matcher.raw_to_host(raw, plan)
+        per_set = plan.fill(out_q, out_t)
+        go = self.go_indices(per_set[0], per_set[1:])
+        n_go = plan.fill_go(go)
+        counts = torch.tensor([float(n_go), float(sum(sizes))], dtype=torch.float32)
+        if dist_utils.is_dist_available_and_initialized():
+            dev = outputs["pred_logits"].device
+            c = counts.to(dev)
+            torch.distributed.all_reduce(c)   # one 2-float all-reduce instead of two (639-651)
+            counts = c.cpu()
+        plan.counts.copy_(torch.clamp(counts / dist_utils.get_world_size(), min=1))
+        return plan
+
+    def compute(self, outputs, tg, table, counts, plan):
+        """Stage 3 (device): every loss term from the fixed-shape index table (dfine_criterion.py:655-777)."""
+        self._clear_cache()
+        main, aux, pre, enc = self._matched_layers(outputs)
+        Q = plan.Q
+        nb_go, nb = counts[0], counts[1]
+        sets = [_Set(table, *plan.set_slice(k), Q, False) for k in range(plan.n_sets)]
+        s_go = _Set(table, *plan.set_slice("go"), Q, True)
+        num = {"vfl": nb, "boxes": nb_go, "local": nb_go, "masks": nb}
+
+        def sets_for(s):
+            return {"vfl": s, "boxes": s_go, "local": s_go, "masks": s}
+
+        losses = {}
+        self._terms(main, tg, sets_for(sets[0]), num, "", losses)
+        for i, a in enumerate(aux):
+            a["up"], a["reg_scale"] = outputs["up"], outputs["reg_scale"]
+            self._terms(a, tg, sets_for(sets[1 + i]), num, f"_aux_{i}", losses)
+        self._terms(pre, tg, sets_for(sets[1 + len(aux)]), num, "_pre", losses)
+        assert "enc_meta" in outputs and not outputs["enc_meta"]["class_agnostic"]
+        for i, a in enumerate(enc):
+            f = sets_for(sets[2 + len(aux) + i])
+            f["local"] = f["vfl"]      # reference passes the per-layer indices to every non-"boxes" loss (712)
+            self._terms(a, tg, f, {**num, "local": nb}, f"_enc_{i}", losses)
+
+        if "dn_outputs" in outputs:
+            meta = outputs["dn_meta"]
+            s_dn = _Set(table, *plan.set_slice("dn"), Q, False)
+            dn_num = nb * meta["dn_num_group"]
+            dsets = {k: s_dn for k in ("vfl", "boxes", "local", "masks")}
+            nums = {k: dn_num for k in ("vfl", "boxes", "local", "masks")}
+            for i, a in enumerate(outputs["dn_outputs"]):
+                a["is_dn"] = True
+                a["up"], a["reg_scale"] = outputs["up"], outputs["reg_scale"]
+                self._terms(a, tg, dsets, nums, f"_dn_{i}", losses)
+            if "dn_pre_outputs" in outputs:
+                self._terms(outputs["dn_pre_outputs"], tg, dsets, nums, "_dn_pre", losses)
+        return {k: torch.nan_to_num(v, nan=0.0) for k, v in losses.items()}
+
+    def _terms(self, out, tg, sets, num, suffix, losses):
         fn = {"vfl": self.loss_labels_vfl, "boxes": self.loss_boxes, "local": self.loss_local,
               "masks": self.loss_masks}
         for name in self.losses:
             assert name in fn, f"do you really want to compute {name} loss?"
-            d = fn[name](out, flats[name], num[name])
+            d = fn[name](out, sets[name], tg, num[name])
             for k, v in d.items():
                 if k in self.weight_dict:
                     losses[k + suffix] = v * self.weight_dict[k]
 
     def forward(self, outputs, targets, **kwargs):
-        assert "aux_outputs" in outputs, ""
-        device = outputs["pred_logits"].device
-        main = {k: v for k, v in outputs.items() if "aux" not in k}
-        aux, pre, enc = outputs["aux_outputs"], outputs["pre_outputs"], outputs["enc_aux_outputs"]
-        matched = self.matcher.match_layers([main] + list(aux) + [pre] + list(enc), targets)
-        self._clear_cache()
-        idx_main, idx_aux = matched[0], matched[1:1 + len(aux) + 1]
-        idx_enc = matched[1 + len(aux) + 1:]
-        idx_go = self.go_indices(idx_main, list(idx_aux) + list(idx_enc))
-
-        n_go = float(sum(len(x[0]) for x in idx_go))
-        n_box = float(sum(len(t["labels"]) for t in targets))
-        counts = torch.tensor([n_go, n_box], dtype=torch.float, device=device)
-        if dist_utils.is_dist_available_and_initialized():
-            torch.distributed.all_reduce(counts)   # one 2-float all-reduce instead of two (639-651)
-        counts = torch.clamp(counts / dist_utils.get_world_size(), min=1)
-        nb_go, nb = counts[0], counts[1]
-
-        flat_go = _Flat(idx_go, targets, device)
-        num = {"vfl": nb, "boxes": nb_go, "local": nb_go, "masks": nb}
-
-        def flats_for(ind):
-            f = _Flat(ind, targets, device)
-            return {"vfl": f, "boxes": flat_go, "local": flat_go, "masks": f}
-
-        losses = {}
-        self._terms(main, targets, flats_for(idx_main), num, "", losses)
-        for i, a in enumerate(aux):
-            a["up"], a["reg_scale"] = outputs["up"], outputs["reg_scale"]
-            self._terms(a, targets, flats_for(idx_aux[i]), num, f"_aux_{i}", losses)
-        self._terms(pre, targets, flats_for(idx_aux[-1]), num, "_pre", losses)
-        assert "enc_meta" in outputs and not outputs["enc_meta"]["class_agnostic"]
-        for i, a in enumerate(enc):
-            f = flats_for(idx_enc[i])
-            f["local"] = f["vfl"]      # reference passes the per-layer indices to every non-"boxes" loss (712)
-            self._terms(a, targets, f, {**num, "local": nb}, f"_enc_{i}", losses)
-
-        if "dn_outputs" in outputs:
-            meta = outputs["dn_meta"]
-            f_dn = _Flat(self.get_cdn_matched_indices(meta, targets), targets, device)
-            dn_num = nb * meta["dn_num_group"]
-            flats = {k: f_dn for k in ("vfl", "boxes", "local", "masks")}
-            nums = {k: dn_num for k in ("vfl", "boxes", "local", "masks")}
-            for i, a in enumerate(outputs["dn_outputs"]):
-                a["is_dn"] = True
-                a["up"], a["reg_scale"] = outputs["up"], outputs["reg_scale"]
-                self._terms(a, targets, flats, nums, f"_dn_{i}", losses)
-            if "dn_pre_outputs" in outputs:
-                self._terms(outputs["dn_pre_outputs"], targets, flats, nums, "_dn_pre", losses)
-        return {k: torch.nan_to_num(v, nan=0.0) for k, v in losses.items()}
+        raw, tg = self.match(outputs, targets)
+        plan = self.plan(outputs, targets, raw)
+        self.last_plan = plan
+        dev = outputs["pred_logits"].device
+        table = plan.table.to(dev, non_blocking=True)
+        counts = plan.counts.to(dev, non_blocking=True)
+        return self.compute(outputs, tg, table, counts, plan)

@@ -259,10 +259,13 @@ __global__ void __launch_bounds__(NT) attn_bwd_dkv_kernel(const float* __restric
     }
 }
 
-template <int HD>
+template <int HD, int WHICH>
 int set_smem(const void* fn) {
+    static bool done = false;   // once per kernel instantiation (also keeps the call out of graph captures)
+    if (done) return 0;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<HD>));
     if (e != cudaSuccess) { dfine_set_error("attention: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    done = true;
     return 0;
 }
 
@@ -286,7 +289,7 @@ DFINE_API int dfine_attn_fwd(const float* q, long ldq, const float* k, long ldk,
     DFINE_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "attn_fwd: row strides must be multiples of 4");
     dim3 grid(ceil_div(S, ROWS), H, B);
     ATTN_DISPATCH(head_dim, {
-        int rc = set_smem<HD>((const void*)attn_fwd_kernel<HD>);
+        int rc = set_smem<HD, 0>((const void*)attn_fwd_kernel<HD>);
         if (rc) return rc;
         attn_fwd_kernel<HD><<<grid, NT, sizeof(Smem<HD>), (cudaStream_t)stream>>>(q, ldq, k, ldk, v, ldv, mask, o, ldo,
                                                                                   lse, S, H, scale);
@@ -305,9 +308,9 @@ DFINE_API int dfine_attn_bwd(const float* q, long ldq, const float* k, long ldk,
                   "attn_bwd: row strides must be multiples of 4");
     dim3 grid(ceil_div(S, ROWS), H, B);
     ATTN_DISPATCH(head_dim, {
-        int rc = set_smem<HD>((const void*)attn_bwd_dq_kernel<HD>);
+        int rc = set_smem<HD, 1>((const void*)attn_bwd_dq_kernel<HD>);
         if (rc) return rc;
-        rc = set_smem<HD>((const void*)attn_bwd_dkv_kernel<HD>);
+        rc = set_smem<HD, 2>((const void*)attn_bwd_dkv_kernel<HD>);
         if (rc) return rc;
         attn_bwd_dq_kernel<HD><<<grid, NT, sizeof(Smem<HD>), (cudaStream_t)stream>>>(
             q, ldq, k, ldk, v, ldv, mask, o, ldo, dout, ldd, lse, dsum, dq, lddq, S, H, scale);

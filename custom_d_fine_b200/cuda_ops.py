@@ -632,6 +632,40 @@ class CudaOps:
                                    c_float(w_class), c_float(w_bbox), c_float(w_giou), _stream()), "matcher")
         return out_q, out_t, cost
 
+    _toff_cache = {}
+
+    @torch.no_grad()
+    def match_raw(self, logits_list, boxes_list, targets, alpha=0.25, gamma=2.0, w_class=2.0, w_bbox=5.0,
+                  w_giou=2.0):
+        """Launch only (graph-capturable): returns device int64 (out_q, out_t) of shape [n_layers, sumT]."""
+        logits = torch.stack([l.detach().float() for l in logits_list]).contiguous()
+        boxes = torch.stack([b.detach().float() for b in boxes_list]).contiguous()
+        _req_cuda(logits, boxes)
+        dev = logits.device
+        sizes = tuple(int(t["labels"].shape[0]) for t in targets)
+        sumT, Tmax = sum(sizes), max(sizes) if sizes else 0
+        if sumT == 0:
+            z = torch.zeros((logits.shape[0], 0), device=dev, dtype=torch.int64)
+            return z, z
+        key = (sizes, dev)
+        toff = self._toff_cache.get(key)
+        if toff is None:   # depends on the targets' sizes only; built once (a pageable H2D is not capturable)
+            offs = [0]
+            for sz in sizes:
+                offs.append(offs[-1] + sz)
+            toff = torch.tensor(offs, dtype=torch.int32).to(dev)
+            self._toff_cache[key] = toff
+        labels = torch.cat([t["labels"] for t in targets]).to(dev, torch.int64).contiguous()
+        tboxes = torch.cat([t["boxes"] for t in targets]).to(dev, torch.float32).contiguous()
+        out_q, out_t, _ = self.match_device(logits, boxes, labels, tboxes, toff, sumT, Tmax, alpha, gamma, w_class,
+                                            w_bbox, w_giou)
+        return out_q, out_t
+
+    @staticmethod
+    def match_raw_to_host(raw, plan):
+        both = torch.stack(list(raw)).cpu().numpy()        # the step's single matcher D2H (+ sync)
+        return both[0], both[1]
+
     @torch.no_grad()
     def match(self, logits_list, boxes_list, targets, alpha=0.25, gamma=2.0, w_class=2.0, w_bbox=5.0, w_giou=2.0):
         logits = torch.stack([l.detach().float() for l in logits_list]).contiguous()

@@ -41,6 +41,23 @@ class HungarianMatcher(nn.Module):
                        float(self.cost_giou))
 
     @torch.no_grad()
+    def match_layers_raw(self, outputs_list, targets):
+        """Device-side half of ``match_layers``: launches the matcher and returns the provider's raw result
+        (device int64 [n_layers, sumT] x2 on the CUDA path) without touching the host."""
+        for o in outputs_list:
+            if o.get("pred_masks") is not None and (self.cost_mask > 0 or self.cost_mask_dice > 0) and any(
+                    t.get("masks") is not None and t["masks"].numel() > 0 for t in targets):
+                raise NotImplementedError("mask matching cost (matcher.py:175-237) is a SURVEY §8(f) 'next' row")
+        return K.match_raw([o["pred_logits"] for o in outputs_list], [o["pred_boxes"] for o in outputs_list],
+                           targets, self.alpha, self.gamma, float(self.cost_class), float(self.cost_bbox),
+                           float(self.cost_giou))
+
+    @staticmethod
+    def raw_to_host(raw, plan):
+        """Host int64 arrays [n_sets, sumT] (q, t) from the provider's raw result: the step's one D2H."""
+        return K.match_raw_to_host(raw, plan)
+
+    @torch.no_grad()
     def forward(self, outputs, targets, return_topk=False):
         if return_topk:
             raise NotImplementedError("get_top_k_matches has no caller in the reference (matcher.py:259-285)")

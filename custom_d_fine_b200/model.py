@@ -88,8 +88,10 @@ def param_groups(model, backbone_lr, base_lr):
 
 
 def build_optimizer(model, lr, backbone_lr, betas, weight_decay, base_lr):
+    # capturable: the step counter lives on the device so the update can be replayed inside a CUDA graph
+    on_cuda = all(p.is_cuda for p in model.parameters())
     return optim.AdamW(param_groups(model, backbone_lr, base_lr), lr=lr, betas=betas,
-                       weight_decay=weight_decay)
+                       weight_decay=weight_decay, capturable=on_cuda)
 
 
 # ---- checkpoint loading (src/d_fine/utils.py:92-181) ------------------------------------------

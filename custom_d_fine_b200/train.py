@@ -16,7 +16,8 @@ from torch.nn.parallel import DistributedDataParallel as DDP
 class ModelEMA:
     """EMA of every floating-point state entry, momentum m*(1-exp(-it/2000)) (train.py:52-73).
     The reference walks ~920 tensors with two tiny kernels each; here the entries are updated with
-    two multi-tensor launches."""
+    multi-tensor launches, and the momentum lives in a device scalar so the update can sit inside a
+    replayed CUDA graph (``set_momentum`` outside the graph, ``apply`` inside)."""
 
     def __init__(self, student, ema_momentum):
         if isinstance(student, DDP):
@@ -26,6 +27,7 @@ class ModelEMA:
             p.requires_grad_(False)
         self.ema_momentum = ema_momentum
         self._pairs = None
+        self._m = self._om = None
 
     def ema_scheduler(self, x):
         return self.ema_momentum * (1 - math.exp(-x / 2000))
@@ -38,38 +40,56 @@ class ModelEMA:
                 ema.append(p)
                 stu.append(src[name].detach())
         self._pairs = (ema, stu)
+        dev = ema[0].device
+        self._m = torch.zeros((), device=dev)
+        self._om = torch.ones((), device=dev)
 
-    @torch.no_grad()
-    def update(self, iters, student):
+    def set_momentum(self, iters, student):
         if isinstance(student, DDP):
             student = student.module
         if self._pairs is None:
             self._build_pairs(student)
         m = self.ema_scheduler(iters)
+        self._m.fill_(m)
+        self._om.fill_(1.0 - m)
+
+    @torch.no_grad()
+    def apply(self):
         ema, stu = self._pairs
-        torch._foreach_mul_(ema, m)
-        torch._foreach_add_(ema, stu, alpha=1.0 - m)
+        torch._foreach_mul_(ema, self._m)                      # p *= m
+        torch._foreach_add_(ema, torch._foreach_mul(stu, self._om))   # p += (1-m) * student
+
+    @torch.no_grad()
+    def update(self, iters, student):
+        self.set_momentum(iters, student)
+        self.apply()
 
 
 class TrainStep:
     """One optimisation step on one batch: forward, criterion, backward, clip, AdamW, scheduler,
-    zero_grad, EMA — the reference's hot loop body."""
+    zero_grad, EMA — the reference's hot loop body (train.py:550-586 + 512-535), eager launches."""
 
     def __init__(self, model, loss_fn, optimizer, scheduler=None, ema=None, clip_max_norm=0.1, accum_steps=1):
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
         self.scheduler, self.ema, self.clip_max_norm = scheduler, ema, clip_max_norm
         self.accum_steps, self.ema_iter, self.batch_idx = accum_steps, 0, 0
 
-    def optimizer_step(self, step_scheduler=True):
+    def _apply_grads(self):
+        """clip -> AdamW -> zero_grad -> EMA blend: the device part of optimizer_step (graph-capturable)."""
         if self.clip_max_norm:
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip_max_norm)
         self.optimizer.step()
-        if step_scheduler and self.scheduler is not None:
-            self.scheduler.step()
         self.optimizer.zero_grad()
         if self.ema is not None:
+            self.ema.apply()
+
+    def optimizer_step(self, step_scheduler=True):
+        if self.ema is not None:
             self.ema_iter += 1
-            self.ema.update(self.ema_iter, self.model)
+            self.ema.set_momentum(self.ema_iter, self.model)
+        self._apply_grads()
+        if step_scheduler and self.scheduler is not None:
+            self.scheduler.step()
 
     def __call__(self, inputs, targets):
         """inputs float32 [B,3,H,W] on the device; targets list of dicts (labels int64 [T], boxes [T,4])."""
@@ -81,3 +101,92 @@ class TrainStep:
         if self.batch_idx % self.accum_steps == 0:
             self.optimizer_step()
         return loss.detach(), loss_dict
+
+
+class GraphedTrainStep(TrainStep):
+    """The same step replayed as two CUDA graphs around the host-side index planning:
+
+        graph A : model forward (+CDN) + the one-launch Hungarian matcher
+        host    : D2H of the [n_layers, sumT] index table, GO union, normalisers, one pinned H2D
+        graph B : every loss term, backward, grad clip, AdamW, EMA
+
+    The reference's step is ~9 k kernel launches driven by Python; replaying it removes the host from the
+    critical path.  Graphs are keyed by (input shape, targets' sizes); the first ``eager_steps`` calls of a
+    key run eagerly (they are real training steps and double as the warm-up CUDA graphs require), then
+    the key is captured.  Constraints: single process (DDP steps stay eager), no gradient accumulation,
+    constant learning rate inside a captured key (a scheduler forces the eager path)."""
+
+    def __init__(self, *args, eager_steps=3, **kw):
+        super().__init__(*args, **kw)
+        self.eager_steps = eager_steps
+        self._seen = {}
+        self._graphs = {}
+        self._plans = {}
+
+    def _can_graph(self):
+        return (self.accum_steps == 1 and self.scheduler is None and not isinstance(self.model, DDP)
+                and next(self.model.parameters()).is_cuda)
+
+    def __call__(self, inputs, targets):
+        if not self._can_graph():
+            return super().__call__(inputs, targets)
+        key = (tuple(inputs.shape), tuple(int(t["labels"].shape[0]) for t in targets))
+        g = self._graphs.get(key)
+        if g is None:
+            n = self._seen.get(key, 0)
+            self._seen[key] = n + 1
+            if n < self.eager_steps:
+                res = super().__call__(inputs, targets)
+                self._plans[key] = self.loss_fn.last_plan      # valid index plan of this key, reused to capture
+                return res
+            g = self._capture(inputs, targets, self._plans.pop(key))
+            self._graphs[key] = g
+        return self._replay(g, inputs, targets)
+
+    def _capture(self, inputs, targets, plan):
+        from . import cuda_ops
+        g = {}
+        dev = inputs.device
+        g["x"] = inputs.clone()
+        g["targets"] = [{"labels": t["labels"].clone(), "boxes": t["boxes"].clone()} for t in targets]
+        crit = self.loss_fn
+        # capture records launches without running them, so the index table used while capturing graph B is
+        # the (same-shaped) plan of the last eager step of this key; replays refill it before graph B runs
+        g["plan"] = plan
+        n0 = cuda_ops.counters.launches
+        g["table"] = plan.table.to(dev)
+        g["counts"] = plan.counts.to(dev)
+        self.optimizer.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
+        gA = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gA):
+            out = self.model(g["x"], targets=g["targets"])
+            raw, tg = crit.match(out, g["targets"])
+        gB = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gB, pool=gA.pool()):
+            loss_dict = crit.compute(out, tg, g["table"], g["counts"], plan)
+            loss = sum(loss_dict.values())
+            loss.backward()
+            self._apply_grads()
+            g["loss"] = loss.detach()
+            g["loss_dict"] = {k: v.detach() for k, v in loss_dict.items()}
+        g.update(gA=gA, gB=gB, out=out, raw=raw, launches=cuda_ops.counters.launches - n0)
+        return g
+
+    def _replay(self, g, inputs, targets):
+        g["x"].copy_(inputs, non_blocking=True)
+        for s, t in zip(g["targets"], targets):
+            s["labels"].copy_(t["labels"], non_blocking=True)
+            s["boxes"].copy_(t["boxes"], non_blocking=True)
+        if self.ema is not None:
+            self.ema_iter += 1
+            self.ema.set_momentum(self.ema_iter, self.model)
+        g["gA"].replay()
+        plan = self.loss_fn.plan(g["out"], g["targets"], g["raw"], g["plan"])     # syncs on the matcher D2H
+        g["table"].copy_(plan.table, non_blocking=True)
+        g["counts"].copy_(plan.counts, non_blocking=True)
+        g["gB"].replay()
+        from . import cuda_ops
+        cuda_ops.counters.launches += g["launches"]      # library kernels replayed by the two graphs
+        self.batch_idx += 1
+        return g["loss"], g["loss_dict"]
