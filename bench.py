@@ -118,10 +118,10 @@ def build_step(device, world, local_rank, eager=False):
                 p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(p.device))
     model.train()
     ema = ModelEMA(model, 0.9998)
-    net = dist_utils.wrap_ddp(model, local_rank) if world > 1 else model
+    net = model      # data-parallel ranks all-reduce the optimizer's flat gradient arenas (no DDP wrapper)
     loss_fn = build_loss(MODEL, NUM_CLASSES, 0.0, False)
     opt = build_optimizer(model, lr=1.5e-4, backbone_lr=2e-5, betas=(0.9, 0.999), weight_decay=1.25e-4, base_lr=1.5e-4)
-    cls = TrainStep if (world > 1 or eager) else GraphedTrainStep
+    cls = TrainStep if eager else GraphedTrainStep
     step = cls(net, loss_fn, opt, scheduler=None, ema=ema, clip_max_norm=0.1)
     # an eager twin over the same model / optimizer: used only to bracket single kernels with CUDA events
     step.eager_twin = TrainStep(net, loss_fn, opt, scheduler=None, ema=ema, clip_max_norm=0.1)
@@ -194,7 +194,7 @@ def run_ours(args):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
-    mode = "cuda-graph replay (2 graphs/step)" if graphed and step._graphs else "eager launches"
+    mode = "cuda-graph replay (3 graphs/step)" if graphed and step._graphs else "eager launches"
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:

@@ -22,9 +22,9 @@
 //              b_major = MN and the 128B_BASE32B layout (the only one defined for MN-major tf32);
 //              split over pixel ranges, accumulated into dWr with red.global.add.f32.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = barrier init + TMEM alloc + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp % 4).  3-stage smem ring so two CTAs fit per SM and
-// one CTA's epilogue overlaps the other's main loop.  Every mbarrier wait is bounded and traps instead
+// Warp roles: warp 0 = TMA producer, warp 1 = barrier init + TMEM alloc + MMA issuer, warps 2..5 = epilogue
+// (TMEM lane quarter = warp % 4), warps 6..9 (3xTF32 mode only) = tf32 hi/lo converters.  Multi-stage smem ring;
+// where two CTAs fit per SM one CTA's epilogue overlaps the other's main loop.  Every mbarrier wait is bounded and traps instead
 // of hanging the device.
 #include "common.cuh"
 #include <cuda.h>
@@ -137,36 +137,65 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn, int b_mn) {
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-constexpr int TC_THREADS = 192;
 constexpr int BM = 128, BK = 32;
-constexpr int STAGES = 3;
 constexpr int EPI_LD = 33;
+constexpr int MAX_TAPS = 9;
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// Implicit-GEMM geometry of one launch.  The output "tile domain" is OH x OW pixels per image; output pixel
+// (oh, ow) gathers, for tap t, the input pixel (oh*in_stride + dh[t], ow*in_stride + dw[t]) (zero outside the
+// input: TMA out-of-bounds fill) against weight columns [wk[t], wk[t] + Cin), and is stored at pixel
+// (oh*osy + ooy, ow*osx + oox) of a YH x YW output tensor.  Forward convs use os = 1; the data gradient of a
+// stride-2 conv is four launches (one per output parity) with os = 2.
 struct FwdParams {
-    int taps_h, taps_w, pad;  // filter taps and symmetric padding (1x1: 1,1,0   3x3: 3,3,1)
+    int n_taps;
+    int dh[MAX_TAPS], dw[MAX_TAPS], wk[MAX_TAPS];
+    int in_stride;
     int Cin;                  // channels per tap
     int TW, TH;               // output patch per CTA (TW*TH <= 128)
     int tiles_w, tiles_h;     // patches per image
-    int OH, OW, N;            // output geometry, N = Cout
+    int OH, OW, N;            // tile domain, N = Cout
+    int YH, YW, osy, osx, ooy, oox;
     long ldy;                 // output pixel stride (elements)
     int act;
 };
 
-template <int BN>
+// X3 = 0: one kind::tf32 MMA per k-step (operands truncated to tf32 by the tensor core).
+// X3 = 1: error-compensated "3xTF32": a = a_hi + a_lo, w = w_hi + w_lo with hi = round-to-nearest tf32;
+//         D += a_hi*w_hi + a_lo*w_hi + a_hi*w_lo.  a_hi / a_lo are produced in shared memory by four converter
+//         warps between the TMA landing and the MMA issue; w_hi / w_lo arrive pre-split from global memory.
+//         Restores fp32-class accuracy (the dropped a_lo*w_lo term is 2^-22 relative) at 3x the MMA work,
+//         which the HBM-bound layers of this network hide.
+template <int BN, int X3, int STAGES>
 struct FwdSmem {
     alignas(1024) float a[STAGES][BM * BK];
     alignas(1024) float b[STAGES][BN * BK];
-    uint64_t full[STAGES], empty[STAGES], acc_full;   // (the epilogue's transpose buffers alias a[0])
+    alignas(1024) float alo[X3 ? STAGES : 1][X3 ? BM * BK : 32];
+    alignas(1024) float blo[X3 ? STAGES : 1][X3 ? BN * BK : 32];
+    uint64_t full[STAGES], empty[STAGES], conv[STAGES], acc_full;   // (the epilogue's transpose buffers alias a[0])
     uint32_t tmem_base;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS) tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x,
-                                                            const __grid_constant__ CUtensorMap map_w,
-                                                            float* __restrict__ y, const float* __restrict__ bias,
-                                                            double* __restrict__ stats, FwdParams p) {
+constexpr int fwd_threads(int x3) { return x3 ? 320 : 192; }
+
+template <int BN, int X3, int STAGES>
+__global__ void __launch_bounds__(fwd_threads(X3)) tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                                 const __grid_constant__ CUtensorMap map_w,
+                                                                 const __grid_constant__ CUtensorMap map_wlo,
+                                                                 float* __restrict__ y, const float* __restrict__ bias,
+                                                                 double* __restrict__ stats, FwdParams p) {
     extern __shared__ uint8_t raw[];
-    FwdSmem<BN>& sm = *reinterpret_cast<FwdSmem<BN>*>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    using Smem = FwdSmem<BN, X3, STAGES>;
+    Smem& sm = *reinterpret_cast<Smem*>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     // tile coordinates
     const int tiles_per_img = p.tiles_w * p.tiles_h;
@@ -174,12 +203,12 @@ __global__ void __launch_bounds__(TC_THREADS) tc_fwd_kernel(const __grid_constan
     const int h0 = (t / p.tiles_w) * p.TH, w0 = (t % p.tiles_w) * p.TW;
     const int n0 = blockIdx.y * BN;
     const int cblocks = (p.Cin + BK - 1) / BK;
-    const int num_k = p.taps_h * p.taps_w * cblocks;
+    const int num_k = p.n_taps * cblocks;
 
-    if (warp == 0 && lane == 0) { prefetch_tmap(&map_x); prefetch_tmap(&map_w); }
+    if (warp == 0 && lane == 0) { prefetch_tmap(&map_x); prefetch_tmap(&map_w); if (X3) prefetch_tmap(&map_wlo); }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+            for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); mbar_init(&sm.conv[s], 4); }
             mbar_init(&sm.acc_full, 1);
             fence_barrier_init();
         }
@@ -197,12 +226,13 @@ __global__ void __launch_bounds__(TC_THREADS) tc_fwd_kernel(const __grid_constan
                 const int s = kb % STAGES, ph = (kb / STAGES) & 1;
                 mbar_wait(&sm.empty[s], ph ^ 1);
                 const int tap = kb / cblocks, c0 = (kb % cblocks) * BK;
-                const int kh = tap / p.taps_w, kw = tap % p.taps_w;
                 // the x box is TW*TH (<=128) rows of 128 B; smem rows beyond that keep stale data that only
                 // feeds accumulator rows the epilogue never stores.  expect_tx counts the box bytes:
-                mbar_expect_tx(&sm.full[s], (uint32_t)((p.TW * p.TH + BN) * BK * sizeof(float)));
-                tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 + kw - p.pad, h0 + kh - p.pad, img);
-                tma_load_2d(sm.b[s], &map_w, &sm.full[s], tap * p.Cin + c0, n0);
+                mbar_expect_tx(&sm.full[s], (uint32_t)((p.TW * p.TH + (X3 ? 2 : 1) * BN) * BK * sizeof(float)));
+                tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 * p.in_stride + p.dw[tap], h0 * p.in_stride + p.dh[tap],
+                            img);
+                tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
+                if (X3) tma_load_2d(sm.blo[s], &map_wlo, &sm.full[s], p.wk[tap] + c0, n0);
             }
         }
         __syncwarp();
@@ -211,19 +241,30 @@ __global__ void __launch_bounds__(TC_THREADS) tc_fwd_kernel(const __grid_constan
             constexpr uint32_t idesc = make_idesc(BN, 0, 0);
             for (int kb = 0; kb < num_k; ++kb) {
                 const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-                mbar_wait(&sm.full[s], ph);
+                mbar_wait(X3 ? &sm.conv[s] : &sm.full[s], ph);
                 tc_fence_after();
                 const uint64_t da = make_desc(smem_u32(sm.a[s]), 16, 1024);
                 const uint64_t db = make_desc(smem_u32(sm.b[s]), 16, 1024);
+                if (X3) {
+                    const uint64_t dal = make_desc(smem_u32(sm.alo[s]), 16, 1024);
+                    const uint64_t dbl = make_desc(smem_u32(sm.blo[s]), 16, 1024);
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k)  // UMMA_K = 8 tf32 = 32 bytes -> +2 in 16-byte units
-                    umma_tf32(tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < BK / 8; ++k) {
+                        umma_tf32(tmem, dal + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        umma_tf32(tmem, da + 2 * k, dbl + 2 * k, idesc, 1);
+                        umma_tf32(tmem, da + 2 * k, db + 2 * k, idesc, 1);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k)  // UMMA_K = 8 tf32 = 32 bytes -> +2 in 16-byte units
+                        umma_tf32(tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                }
                 umma_commit(&sm.empty[s]);
             }
             umma_commit(&sm.acc_full);
         }
         __syncwarp();
-    } else {
+    } else if (warp < 6) {
         const int q = warp % 4;  // TMEM lane quarter
         // all MMAs (hence all TMA loads) have completed once acc_full fires: stage 0 is free to reuse
         float* buf = sm.a[0] + q * 32 * EPI_LD;
@@ -236,7 +277,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_fwd_kernel(const __grid_constan
             const int th = r / p.TW, tw = r % p.TW;
             const int oh = h0 + th, ow = w0 + tw;
             row_ok[i] = th < p.TH && oh < p.OH && ow < p.OW;
-            row_off[i] = (((long)img * p.OH + oh) * p.OW + ow) * p.ldy;
+            row_off[i] = (((long)img * p.YH + (long)oh * p.osy + p.ooy) * p.YW + (long)ow * p.osx + p.oox) * p.ldy;
         }
         mbar_wait(&sm.acc_full, 0);
         tc_fence_after();
@@ -284,6 +325,28 @@ __global__ void __launch_bounds__(TC_THREADS) tc_fwd_kernel(const __grid_constan
             }
             __syncwarp();
         }
+    } else if (X3) {
+        // converter warps 6..9: split the landed activation tile into tf32 hi (in place) and lo parts
+        const int ct = threadIdx.x - 192;  // 0..127
+        for (int kb = 0; kb < num_k; ++kb) {
+            const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+            mbar_wait(&sm.full[s], ph);
+            float4* a4 = reinterpret_cast<float4*>(sm.a[s]);
+            float4* l4 = reinterpret_cast<float4*>(sm.alo[s]);
+#pragma unroll
+            for (int i = 0; i < BM * BK / 4 / 128; ++i) {
+                const int idx = ct + i * 128;
+                const float4 v = a4[idx];
+                float4 hi, lo;
+                hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+                lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+                a4[idx] = hi;
+                l4[idx] = lo;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.conv[s]);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -291,8 +354,11 @@ __global__ void __launch_bounds__(TC_THREADS) tc_fwd_kernel(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------- wgrad
+constexpr int WG_THREADS = 192;
+constexpr int WG_STAGES = 3;
+
 struct WgradParams {
-    int taps_h, taps_w, pad;
+    int taps_h, taps_w, pad_t, pad_l, stride;
     int Cin, Cout;
     int OH, OW, B;
     int wchunks;          // ceil(OW / 32)
@@ -303,16 +369,17 @@ struct WgradParams {
 
 template <int BN>
 struct WgradSmem {
-    alignas(1024) float a[STAGES][BM * BK];  // 4 chunks of [32 pixels][32 cout]
-    alignas(1024) float b[STAGES][BN * BK];  // BN/32 chunks of [32 pixels][32 cin]
-    uint64_t full[STAGES], empty[STAGES], acc_full;
+    alignas(1024) float a[WG_STAGES][BM * BK];  // 4 chunks of [32 pixels][32 cout]
+    alignas(1024) float b[WG_STAGES][BN * BK];  // BN/32 chunks of [32 pixels][32 cin]
+    uint64_t full[WG_STAGES], empty[WG_STAGES], acc_full;
     uint32_t tmem_base;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS) tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy,
+__global__ void __launch_bounds__(WG_THREADS) tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy,
                                                               const __grid_constant__ CUtensorMap map_x,
                                                               float* __restrict__ dwr, WgradParams p) {
+    constexpr int STAGES = WG_STAGES;
     extern __shared__ uint8_t raw[];
     WgradSmem<BN>& sm = *reinterpret_cast<WgradSmem<BN>*>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -322,6 +389,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_wgrad_kernel(const __grid_const
     const long s_begin = (long)blockIdx.z * p.steps_per_split;
     const long s_end = s_begin + p.steps_per_split < p.steps_total ? s_begin + p.steps_per_split : p.steps_total;
     const int num_k = (int)(s_end - s_begin);
+    // chunks of 32 output channels that exist (the rest of the 128-row accumulator is never stored)
+    const int co_chunks = (p.Cout - co0 + 31) / 32 < BM / 32 ? (p.Cout - co0 + 31) / 32 : BM / 32;
 
     if (warp == 0 && lane == 0) { prefetch_tmap(&map_dy); prefetch_tmap(&map_x); }
     if (warp == 1) {
@@ -347,14 +416,13 @@ __global__ void __launch_bounds__(TC_THREADS) tc_wgrad_kernel(const __grid_const
                 const int wc = (int)(step % p.wchunks); step /= p.wchunks;
                 const int oh = (int)(step % p.OH);
                 const int b = (int)(step / p.OH);
-                mbar_expect_tx(&sm.full[s], (uint32_t)((BM + BN) * BK * sizeof(float)));
-#pragma unroll
-                for (int c = 0; c < BM / 32; ++c)
+                mbar_expect_tx(&sm.full[s], (uint32_t)((co_chunks * 32 + BN) * BK * sizeof(float)));
+                for (int c = 0; c < co_chunks; ++c)
                     tma_load_4d(sm.a[s] + c * 32 * BK, &map_dy, &sm.full[s], co0 + 32 * c, wc * 32, oh, b);
 #pragma unroll
                 for (int c = 0; c < BN / 32; ++c)
-                    tma_load_4d(sm.b[s] + c * 32 * BK, &map_x, &sm.full[s], ci0 + 32 * c, wc * 32 + kw - p.pad,
-                                oh + kh - p.pad, b);
+                    tma_load_4d(sm.b[s] + c * 32 * BK, &map_x, &sm.full[s], ci0 + 32 * c,
+                                wc * 32 * p.stride + kw - p.pad_l, oh * p.stride + kh - p.pad_t, b);
             }
         }
         __syncwarp();
@@ -382,15 +450,17 @@ __global__ void __launch_bounds__(TC_THREADS) tc_wgrad_kernel(const __grid_const
         tc_fence_after();
         const int co = co0 + 32 * q + lane;
         const long ldw = (long)p.taps_h * p.taps_w * p.Cin;
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            if (ci0 + c0 >= p.Cin) break;
-            uint32_t v[32];
-            tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
-            if (co < p.Cout) {
-                float* dst = dwr + (long)co * ldw + (long)tap * p.Cin + ci0 + c0;
+        if (q < co_chunks) {
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (ci0 + c0 >= p.Cin) break;
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
+                if (co < p.Cout) {
+                    float* dst = dwr + (long)co * ldw + (long)tap * p.Cin + ci0 + c0;
 #pragma unroll
-                for (int c = 0; c < 32; ++c)
-                    if (ci0 + c0 + c < p.Cin) atomicAdd(dst + c, __uint_as_float(v[c]));
+                    for (int c = 0; c < 32; ++c)
+                        if (ci0 + c0 + c < p.Cin) atomicAdd(dst + c, __uint_as_float(v[c]));
+                }
             }
         }
     }
@@ -417,22 +487,24 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 4-D fp32 tensor map (C, W, H, B) over an NHWC activation with pixel stride ld (elements),
-// 128-byte swizzle, zero OOB fill.
+// 4-D fp32 tensor map (C, W, H, B) over an NHWC activation with pixel stride ld (elements), zero OOB fill.
+// The box covers box_w x box_h pixels sampled every `estride` pixels (strided convolutions read their
+// input through the map's element strides; there is no im2col buffer).
 int make_map4(CUtensorMap* m, const float* base, long C, long W, long H, long B, long ld, int box_c, int box_w,
-              int box_h, const char* who, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+              int box_h, int estride, const char* who, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { dfine_set_error("%s: cuTensorMapEncodeTiled unavailable", who); return -2; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)ld * 4 * W, (cuuint64_t)ld * 4 * W * H};
-    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * estride), (cuuint32_t)(box_h * estride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+    if (box[1] > 256 || box[2] > 256) { dfine_set_error("%s: TMA box %u x %u exceeds 256", who, box[1], box[2]); return -1; }
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, (void*)base, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        dfine_set_error("%s: cuTensorMapEncodeTiled(4d) failed (%d) C=%ld W=%ld H=%ld B=%ld ld=%ld box=%d,%d,%d", who,
-                        (int)r, C, W, H, B, ld, box_c, box_w, box_h);
+        dfine_set_error("%s: cuTensorMapEncodeTiled(4d) failed (%d) C=%ld W=%ld H=%ld B=%ld ld=%ld box=%d,%d,%d es=%d",
+                        who, (int)r, C, W, H, B, ld, box_c, box_w, box_h, estride);
         return -2;
     }
     return 0;
@@ -456,15 +528,15 @@ int make_map2(CUtensorMap* m, const float* base, long inner, long rows, long ld,
     return 0;
 }
 
-void pick_patch(int OH, int OW, int* TW, int* TH) {
+void pick_patch(int OH, int OW, int max_span, int* TW, int* TH) {
     // widest patch row <= 128 that wastes the fewest rows; prefer full-width rows for narrow maps
-    if (OH == 1) { *TW = 128; *TH = 1; return; }
+    if (OH == 1) { *TW = 128 < max_span ? 128 : max_span; *TH = 1; return; }
     int best_tw = 1, best_th = 1;
     double best = -1.0;
-    for (int tw = 1; tw <= 128 && tw <= 256; ++tw) {
-        if (tw > OW && tw != OW) break;
+    for (int tw = 1; tw <= 128 && tw <= max_span; ++tw) {
+        if (tw > OW) break;
         int th = 128 / tw;
-        if (th > 256) th = 256;
+        if (th > max_span) th = max_span;
         if (th < 1) continue;
         const long tiles = (long)((OW + tw - 1) / tw) * ((OH + th - 1) / th);
         const double eff = (double)OH * OW / ((double)tiles * 128.0);
@@ -474,18 +546,18 @@ void pick_patch(int OH, int OW, int* TW, int* TH) {
     *TH = best_th;
 }
 
-template <int BN>
-int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, float* y, const float* bias, double* stats,
-               const FwdParams& p, int B, cudaStream_t st) {
+template <int BN, int X3, int STAGES>
+int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mwlo, float* y, const float* bias,
+               double* stats, const FwdParams& p, int B, cudaStream_t st) {
     static bool configured = false;
-    const int smem = (int)sizeof(FwdSmem<BN>) + 1024;
+    const int smem = (int)sizeof(FwdSmem<BN, X3, STAGES>) + 1024;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<BN, X3, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { dfine_set_error("tc_fwd: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
     dim3 grid(B * p.tiles_w * p.tiles_h, ceil_div(p.N, BN));
-    tc_fwd_kernel<BN><<<grid, TC_THREADS, smem, st>>>(mx, mw, y, bias, stats, p);
+    tc_fwd_kernel<BN, X3, STAGES><<<grid, fwd_threads(X3), smem, st>>>(mx, mw, mwlo, y, bias, stats, p);
     return 0;
 }
 
@@ -506,76 +578,126 @@ int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, float* dwr, Wgra
     if (sps < 8) sps = 8;
     p.steps_per_split = sps;
     dim3 grid(gx, gy, ceil_div(p.steps_total, sps));
-    tc_wgrad_kernel<BN><<<grid, TC_THREADS, smem, st>>>(mdy, mx, dwr, p);
+    tc_wgrad_kernel<BN><<<grid, WG_THREADS, smem, st>>>(mdy, mx, dwr, p);
     return 0;
 }
 
 }  // namespace
 
-// 1 if the tensor-core path accepts this conv/linear geometry (the host graph uses the CUDA-core
-// kernels of conv_simt.cu otherwise).
+// 1 if the tensor-core path accepts this conv/linear geometry: channel counts and pixel strides multiples of
+// 4 floats (16-byte TMA granularity), stride 1 or 2, at most 9 taps.  (The 3-channel image conv and 1-wide
+// heads stay on the CUDA-core kernels.)
 DFINE_API int dfine_conv_tc_supported(int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l, int pad_b,
                                       int pad_r, long ldx, long ldy) {
-    if (stride != 1) return 0;
-    if (!((KH == 1 && KW == 1 && pad_t == 0 && pad_l == 0 && pad_b == 0 && pad_r == 0) ||
-          (KH == 3 && KW == 3 && pad_t == 1 && pad_l == 1 && pad_b == 1 && pad_r == 1)))
-        return 0;
+    (void)pad_t; (void)pad_l; (void)pad_b; (void)pad_r;
+    if (stride != 1 && stride != 2) return 0;
+    if (KH * KW > MAX_TAPS || KH < 1 || KW < 1) return 0;
     if (Cin % 4 || Cout % 4 || ldx % 4 || ldy % 4) return 0;
-    if (Cin < 16 || Cout < 16) return 0;
+    if (Cin < 4 || Cout < 4) return 0;
     return 1;
 }
 
-// y[b,oh,ow,:Cout] (pixel stride ldy) = act(conv(x[b,h,w,:Cin] (pixel stride ldx), wr[Cout, KH*KW*Cin]) + bias);
-// stride 1, "same" padding for 3x3.  stats (optional, double [2*Cout], zeroed by the caller) receives
-// per-channel sum / sum of squares of the raw conv output (valid only with bias == null, act == 0).
-// nn.Linear on [rows, K]: B=1, H=1, W=rows.
-DFINE_API int dfine_conv_fwd_tc(const float* x, const float* wr, const float* bias, float* y, double* stats, int B,
-                                int H, int W, int Cin, int Cout, int KH, int KW, long ldx, long ldy, int act,
-                                void* stream) {
-    DFINE_REQUIRE(dfine_conv_tc_supported(Cin, Cout, KH, KW, 1, KH / 2, KW / 2, KH / 2, KW / 2, ldx, ldy),
-                  "conv_fwd_tc: unsupported geometry Cin=%d Cout=%d k=%dx%d ldx=%ld ldy=%ld", Cin, Cout, KH, KW, ldx, ldy);
-    DFINE_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)wr % 16) == 0 && ((uintptr_t)y % 16) == 0 &&
-                      (!bias || ((uintptr_t)bias % 16) == 0),
-                  "conv_fwd_tc: pointers must be 16-byte aligned");
-    if ((long)B * H * W == 0) return 0;
+// General tensor-core implicit GEMM (see FwdParams):
+//   y[b, oh*osy+ooy, ow*osx+oox, :Cout] = act( sum_t sum_c x[b, oh*in_stride+dh[t], ow*in_stride+dw[t], c] * w[n, wk[t]+c] + bias )
+// for (oh, ow) in [0,OH) x [0,OW).  x: [B,H,W,Cin] pixel stride ldx; w: [Cout, ldw] row-major (tap-major K);
+// y: [B,YH,YW,*] pixel stride ldy.  taps = n_taps x (dh, dw, wk) host ints.  stats (optional, double [2*Cout],
+// zeroed by the caller) receives per-channel sum / sum of squares of the raw accumulator (train-mode BatchNorm).
+// w_lo == null: plain kind::tf32.  w_lo != null: 3xTF32 — `w` must then hold tf32-rounded weights and w_lo the
+// remainders (dfine_tf32_split); activations are split inside the kernel.  nn.Linear on [rows, K]: B=1, H=1, W=rows.
+DFINE_API int dfine_conv_tc(const float* x, const float* w, const float* w_lo, const float* bias, float* y,
+                            double* stats, int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy,
+                            int YH, int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
+                            const int* taps, long ldw, int act, void* stream) {
+    DFINE_REQUIRE(n_taps >= 1 && n_taps <= MAX_TAPS, "conv_tc: %d taps unsupported", n_taps);
+    DFINE_REQUIRE(in_stride == 1 || in_stride == 2, "conv_tc: input stride %d unsupported", in_stride);
+    DFINE_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldw % 4 == 0 && Cin >= 4 && Cout >= 4,
+                  "conv_tc: unsupported geometry Cin=%d Cout=%d ldx=%ld ldy=%ld ldw=%ld", Cin, Cout, ldx, ldy, ldw);
+    DFINE_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)y % 16) == 0 &&
+                      ((uintptr_t)w_lo % 16) == 0 && (!bias || ((uintptr_t)bias % 16) == 0),
+                  "conv_tc: pointers must be 16-byte aligned");
+    if ((long)B * OH * OW == 0) return 0;
     FwdParams p;
-    p.taps_h = KH; p.taps_w = KW; p.pad = KH / 2; p.Cin = Cin;
-    p.OH = H; p.OW = W; p.N = Cout; p.ldy = ldy; p.act = act;
-    pick_patch(H, W, &p.TW, &p.TH);
-    p.tiles_w = ceil_div(W, p.TW);
-    p.tiles_h = ceil_div(H, p.TH);
-    CUtensorMap mx, mw;
-    int rc = make_map4(&mx, x, Cin, W, H, B, ldx, BK, p.TW, p.TH, "conv_fwd_tc(x)");
+    p.n_taps = n_taps;
+    for (int t = 0; t < MAX_TAPS; ++t) {
+        p.dh[t] = t < n_taps ? taps[3 * t] : 0;
+        p.dw[t] = t < n_taps ? taps[3 * t + 1] : 0;
+        p.wk[t] = t < n_taps ? taps[3 * t + 2] : 0;
+    }
+    p.in_stride = in_stride; p.Cin = Cin;
+    p.OH = OH; p.OW = OW; p.N = Cout; p.ldy = ldy; p.act = act;
+    p.YH = YH; p.YW = YW; p.osy = osy; p.osx = osx; p.ooy = ooy; p.oox = oox;
+    pick_patch(OH, OW, 256 / in_stride, &p.TW, &p.TH);
+    p.tiles_w = ceil_div(OW, p.TW);
+    p.tiles_h = ceil_div(OH, p.TH);
+    CUtensorMap mx, mw, mwlo;
+    int rc = make_map4(&mx, x, Cin, W, H, B, ldx, BK, p.TW, p.TH, in_stride, "conv_tc(x)");
     if (rc) return rc;
-    const long K = (long)KH * KW * Cin;
-    const int bn = Cout <= 64 ? 64 : 128;
-    rc = make_map2(&mw, wr, K, Cout, K, BK, bn, "conv_fwd_tc(w)");
+    const int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
+    rc = make_map2(&mw, w, ldw, Cout, ldw, BK, bn, "conv_tc(w)");
     if (rc) return rc;
-    rc = bn == 64 ? launch_fwd<64>(mx, mw, y, bias, stats, p, B, (cudaStream_t)stream)
-                  : launch_fwd<128>(mx, mw, y, bias, stats, p, B, (cudaStream_t)stream);
+    mwlo = mw;
+    if (w_lo) {
+        rc = make_map2(&mwlo, w_lo, ldw, Cout, ldw, BK, bn, "conv_tc(w_lo)");
+        if (rc) return rc;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (w_lo) {
+        rc = bn == 32 ? launch_fwd<32, 1, 2>(mx, mw, mwlo, y, bias, stats, p, B, st)
+           : bn == 64 ? launch_fwd<64, 1, 2>(mx, mw, mwlo, y, bias, stats, p, B, st)
+                      : launch_fwd<128, 1, 3>(mx, mw, mwlo, y, bias, stats, p, B, st);
+    } else {
+        rc = bn == 32 ? launch_fwd<32, 0, 4>(mx, mw, mwlo, y, bias, stats, p, B, st)
+           : bn == 64 ? launch_fwd<64, 0, 4>(mx, mw, mwlo, y, bias, stats, p, B, st)
+                      : launch_fwd<128, 0, 3>(mx, mw, mwlo, y, bias, stats, p, B, st);
+    }
     if (rc) return rc;
-    DFINE_LAUNCH_CHECK("conv_fwd_tc");
+    DFINE_LAUNCH_CHECK("conv_tc");
     return 0;
 }
 
-// dwr[Cout, KH*KW*Cin] += sum over pixels dy[b,oh,ow,co] * x[b,oh+kh-p,ow+kw-p,ci]; zeroed by the caller.
-DFINE_API int dfine_conv_wgrad_tc(const float* dy, const float* x, float* dwr, int B, int H, int W, int Cin, int Cout,
-                                  int KH, int KW, long ldx, long ldy, void* stream) {
-    DFINE_REQUIRE(dfine_conv_tc_supported(Cin, Cout, KH, KW, 1, KH / 2, KW / 2, KH / 2, KW / 2, ldx, ldy),
-                  "conv_wgrad_tc: unsupported geometry Cin=%d Cout=%d k=%dx%d", Cin, Cout, KH, KW);
+// hi = round-to-nearest tf32(w), lo = w - hi (exact): the weight half of the 3xTF32 split, run once per
+// weight version over a flat arena.
+namespace {
+__global__ void tf32_split_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, long n) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float v = w[i], h = tf32_rna(v);
+        hi[i] = h;
+        lo[i] = v - h;
+    }
+}
+}  // namespace
+DFINE_API int dfine_tf32_split(const float* w, float* hi, float* lo, long n, void* stream) {
+    if (n == 0) return 0;
+    long g = (n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    tf32_split_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w, hi, lo, n);
+    DFINE_LAUNCH_CHECK("tf32_split");
+    return 0;
+}
+
+// dwr[Cout, KH*KW*Cin] += sum over output pixels dy[b,oh,ow,co] * x[b,oh*stride+kh-pad_t,ow*stride+kw-pad_l,ci];
+// dwr zeroed (or holding a running gradient) on entry.  x: [B,H,W,Cin] stride ldx, dy: [B,OH,OW,Cout] stride ldy.
+DFINE_API int dfine_conv_wgrad_tc(const float* dy, const float* x, float* dwr, int B, int H, int W, int Cin, int OH,
+                                  int OW, int Cout, int KH, int KW, int stride, int pad_t, int pad_l, long ldx,
+                                  long ldy, void* stream) {
+    DFINE_REQUIRE(dfine_conv_tc_supported(Cin, Cout, KH, KW, stride, pad_t, pad_l, 0, 0, ldx, ldy),
+                  "conv_wgrad_tc: unsupported geometry Cin=%d Cout=%d k=%dx%d stride=%d", Cin, Cout, KH, KW, stride);
     DFINE_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)dy % 16) == 0, "conv_wgrad_tc: alignment");
-    if ((long)B * H * W == 0) return 0;
+    if ((long)B * OH * OW == 0) return 0;
     WgradParams p;
-    p.taps_h = KH; p.taps_w = KW; p.pad = KH / 2; p.Cin = Cin; p.Cout = Cout; p.OH = H; p.OW = W; p.B = B;
-    p.wchunks = ceil_div(W, 32);
-    p.steps_total = (long)B * H * p.wchunks;
+    p.taps_h = KH; p.taps_w = KW; p.pad_t = pad_t; p.pad_l = pad_l; p.stride = stride;
+    p.Cin = Cin; p.Cout = Cout; p.OH = OH; p.OW = OW; p.B = B;
+    p.wchunks = ceil_div(OW, 32);
+    p.steps_total = (long)B * OH * p.wchunks;
     CUtensorMap mdy, mx;
-    int rc = make_map4(&mdy, dy, Cout, W, H, B, ldy, 32, 32, 1, "conv_wgrad_tc(dy)", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    int rc = make_map4(&mdy, dy, Cout, OW, OH, B, ldy, 32, 32, 1, 1, "conv_wgrad_tc(dy)", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    rc = make_map4(&mx, x, Cin, W, H, B, ldx, 32, 32, 1, "conv_wgrad_tc(x)", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    rc = make_map4(&mx, x, Cin, W, H, B, ldx, 32, 32, 1, stride, "conv_wgrad_tc(x)", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    rc = Cin <= 64 ? launch_wgrad<64>(mdy, mx, dwr, p, (cudaStream_t)stream)
-                   : launch_wgrad<128>(mdy, mx, dwr, p, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = Cin <= 32 ? launch_wgrad<32>(mdy, mx, dwr, p, st)
+       : Cin <= 64 ? launch_wgrad<64>(mdy, mx, dwr, p, st)
+                   : launch_wgrad<128>(mdy, mx, dwr, p, st);
     if (rc) return rc;
     DFINE_LAUNCH_CHECK("conv_wgrad_tc");
     return 0;

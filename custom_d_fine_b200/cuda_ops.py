@@ -131,50 +131,112 @@ def _rows(x):
     return x, n, ld
 
 
-# Dense conv / linear shapes the tcgen05 kernels accept run on tensor cores (kind::tf32 operands, fp32
-# accumulate — the precision class of the reference's cuDNN convolutions on GPU); "simt" routes them to
-# the fp32 CUDA-core kernels of the same library instead (strict-fp32 parity runs and kernel bring-up).
-_USE_TC = os.environ.get("DFINE_GEMM", "tc") != "simt"
+# Dense conv / linear shapes the tcgen05 kernels accept run on tensor cores.  Modes (env DFINE_GEMM / set_gemm_mode):
+#   "tc3"  (default) forward GEMMs as error-compensated 3xTF32 (fp32-class accuracy: the parity mode of the
+#          tensor-core path), data / weight gradients as plain kind::tf32;
+#   "tc"   plain kind::tf32 everywhere (the precision class of the reference's cuDNN convolutions on GPU);
+#   "simt" fp32 CUDA-core kernels of the same library (strict-fp32 parity runs and kernel bring-up).
+_MODE = os.environ.get("DFINE_GEMM", "tc3")
 
 
 def set_gemm_mode(mode: str) -> None:
-    global _USE_TC
-    if mode not in ("tc", "simt"):
+    global _MODE
+    if mode not in ("tc", "tc3", "simt"):
         raise ValueError(mode)
-    _USE_TC = mode == "tc"
+    _MODE = mode
+
+
+def get_gemm_mode() -> str:
+    return _MODE
 
 
 def _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy):
-    if not _USE_TC:
+    if _MODE == "simt":
         return False
     t, l, b, r = pad
     return bool(lib().dfine_conv_tc_supported(Cin, Cout, k, k, stride, t, l, b, r, c_long(ldx), c_long(ldy)))
 
 
+_taps_cache = {}
+
+
+def _taps(key, make):
+    arr = _taps_cache.get(key)
+    if arr is None:
+        flat = [int(v) for t in make() for v in t]
+        arr = ((c_int * len(flat))(*flat), len(flat) // 3)
+        _taps_cache[key] = arr
+    return arr
+
+
+def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, YH, YW, os_, oo, in_stride, taps, act,
+               stats, what):
+    arr, n = taps
+    _check(lib().dfine_conv_tc(_p(x), _p(w), _p(w_lo), _p(bias), _p(y), _p(stats), B, H, W, Cin, c_long(ldx), OH, OW,
+                               Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0], oo[1], in_stride, n, arr,
+                               c_long(ldw), act, _stream()), what)
+
+
+def _split_tf32(w2d):
+    """(hi, lo) of a re-laid weight matrix for the 3xTF32 forward (hi = RN tf32, lo = w - hi)."""
+    hi, lo = torch.empty_like(w2d), torch.empty_like(w2d)
+    _check(lib().dfine_tf32_split(_p(w2d), _p(hi), _p(lo), c_long(w2d.numel()), _stream()), "tf32_split")
+    return hi, lo
+
+
 # ------------------------------------------------------------------------------------------------
 # raw launchers (no autograd)
 # ------------------------------------------------------------------------------------------------
-def _conv_fwd(x, ldx, wr, bias, y, ldy, geom, act, stats=None):
-    """geom = (B,H,W,Cin,OH,OW,Cout,k,stride,pad4)."""
+def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None):
+    """geom = (B,H,W,Cin,OH,OW,Cout,k,stride,pad4).  ``weight`` is the parameter ([Cout,Cin,k,k] conv or [N,K]
+    linear); ``wkey`` its cache getter.  Returns True if the tensor-core kernel ran (it fuses the BN statistics)."""
     B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
     if _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy):
-        _check(lib().dfine_conv_fwd_tc(_p(x), _p(wr), _p(bias), _p(y), _p(stats), B, H, W, Cin, Cout, k, k,
-                                       c_long(ldx), c_long(ldy), act, _stream()), "conv_fwd_tc")
+        K = k * k * Cin
+        wr = wkey("wr", lambda: weight.reshape(Cout, Cin, k, k).permute(0, 2, 3, 1).reshape(Cout, K).contiguous())
+        w_hi, w_lo = wr, None
+        if _MODE == "tc3":
+            w_hi, w_lo = wkey("wr3", lambda: _split_tf32(wr))
+        taps = _taps(("f", k, pad[0], pad[1], Cin),
+                     lambda: [(kh - pad[0], kw - pad[1], (kh * k + kw) * Cin) for kh in range(k) for kw in range(k)])
+        _tc_launch(x, ldx, H, W, Cin, w_hi, w_lo, K, bias, y, ldy, B, OH, OW, Cout, OH, OW, (1, 1), (0, 0), stride,
+                   taps, act, stats, "conv_fwd_tc")
         return True
+    wr = wkey("wr", lambda: weight.reshape(Cout, Cin, k, k).permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous())
     _check(lib().dfine_conv_fwd_simt(_p(x), _p(wr), _p(bias), _p(y), B, H, W, Cin, OH, OW, Cout, k, k, stride,
                                      pad[0], pad[1], c_long(ldx), c_long(ldy), act, _stream()), "conv_fwd_simt")
     return False
 
 
-def _conv_dgrad(dy, ldy, weight, dx, ldx, geom, wcache):
+def _conv_dgrad(dy, ldy, weight, wkey, dx, ldx, geom):
+    """dx[B,H,W,Cin] (pixel stride ldx) from dy[B,OH,OW,Cout]: the forward kernel run on dy with transposed taps;
+    a stride-2 conv's data gradient is one launch per output-pixel parity."""
     B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
     if _tc_ok(Cout, Cin, k, stride, pad, ldy, ldx):
-        # data gradient of a stride-1 "same" conv = the same conv on dy with flipped, transposed taps
-        wd = wcache("wd", lambda: weight.flip(2, 3).permute(1, 2, 3, 0).contiguous())
-        _check(lib().dfine_conv_fwd_tc(_p(dy), _p(wd), None, _p(dx), None, B, OH, OW, Cout, Cin, k, k, c_long(ldy),
-                                       c_long(ldx), 0, _stream()), "conv_dgrad_tc")
+        K = k * k * Cout
+        wd = wkey("wd", lambda: weight.reshape(Cout, Cin, k, k).permute(1, 2, 3, 0).reshape(Cin, K).contiguous())
+        if stride == 1:
+            taps = _taps(("d1", k, pad[0], pad[1], Cout),
+                         lambda: [(pad[0] - kh, pad[1] - kw, (kh * k + kw) * Cout) for kh in range(k) for kw in range(k)])
+            _tc_launch(dy, ldy, OH, OW, Cout, wd, None, K, None, dx, ldx, B, H, W, Cin, H, W, (1, 1), (0, 0), 1, taps,
+                       0, None, "conv_dgrad_tc")
+            return
+        for ph in range(2):
+            for pw in range(2):
+                hp, wp = (H - ph + 1) // 2, (W - pw + 1) // 2
+                if hp <= 0 or wp <= 0:
+                    continue
+                tl = [((ph + pad[0] - kh) // 2, (pw + pad[1] - kw) // 2, (kh * k + kw) * Cout)
+                      for kh in range(k) for kw in range(k)
+                      if (ph + pad[0] - kh) % 2 == 0 and (pw + pad[1] - kw) % 2 == 0]
+                if not tl:
+                    dx[:, ph::2, pw::2].zero_()
+                    continue
+                taps = _taps(("d2", k, pad[0], pad[1], Cout, ph, pw), lambda: tl)
+                _tc_launch(dy, ldy, OH, OW, Cout, wd, None, K, None, dx, ldx, B, hp, wp, Cin, H, W, (2, 2), (ph, pw), 1,
+                           taps, 0, None, "conv_dgrad_tc_s2")
         return
-    wr = wcache("wr", lambda: weight.permute(0, 2, 3, 1).contiguous())
+    wr = wkey("wr", lambda: weight.reshape(Cout, Cin, k, k).permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous())
     _check(lib().dfine_conv_dgrad_simt(_p(dy), _p(wr), _p(dx), B, H, W, Cin, OH, OW, Cout, k, k, stride, pad[0],
                                        pad[1], c_long(ldx), c_long(ldy), _stream()), "conv_dgrad_simt")
 
@@ -183,8 +245,8 @@ def _conv_wgrad(dy, ldy, x, ldx, geom):
     B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
     dwr = torch.zeros((Cout, k, k, Cin), device=dy.device, dtype=torch.float32)
     if _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy):
-        _check(lib().dfine_conv_wgrad_tc(_p(dy), _p(x), _p(dwr), B, H, W, Cin, Cout, k, k, c_long(ldx), c_long(ldy),
-                                         _stream()), "conv_wgrad_tc")
+        _check(lib().dfine_conv_wgrad_tc(_p(dy), _p(x), _p(dwr), B, H, W, Cin, OH, OW, Cout, k, k, stride, pad[0],
+                                         pad[1], c_long(ldx), c_long(ldy), _stream()), "conv_wgrad_tc")
     else:
         _check(lib().dfine_conv_wgrad_simt(_p(dy), _p(x), _p(dwr), B, H, W, Cin, OH, OW, Cout, k, k, stride, pad[0],
                                            pad[1], c_long(ldx), c_long(ldy), _stream()), "conv_wgrad_simt")
@@ -192,15 +254,17 @@ def _conv_wgrad(dy, ldy, x, ldx, geom):
 
 
 class _WCache:
-    """Re-laid weight copies, keyed by parameter identity + version (optimizer steps bump it)."""
+    """Re-laid weight copies, keyed by parameter identity + version + the optimizer epoch (the flat-arena
+    optimizer updates parameters through raw pointers, which does not bump ``_version``)."""
 
     def __init__(self):
         self.d = {}
+        self.epoch = 0
 
     def get(self, w, kind, make):
         key = (id(w), kind)
         ent = self.d.get(key)
-        ver = w._version
+        ver = (w._version, self.epoch)
         if ent is not None and ent[0] == ver and ent[2]() is w:      # id() can be recycled: check identity
             return ent[1]
         with torch.no_grad():
@@ -208,8 +272,16 @@ class _WCache:
         self.d[key] = (ver, val, weakref.ref(w))
         return val
 
+    def getter(self, w):
+        return lambda kind, make: self.get(w, kind, make)
+
 
 _wcache = _WCache()
+
+
+def weights_changed():
+    """Called by the optimizer after it rewrote parameters in place."""
+    _wcache.epoch += 1
 
 
 # ------------------------------------------------------------------------------------------------
@@ -249,8 +321,7 @@ class _ConvBnAct(torch.autograd.Function):
                    "dwconv_fwd")
             fused_stats = False
         else:
-            wr = _wcache.get(weight, "wr", lambda: weight.permute(0, 2, 3, 1).contiguous())
-            fused_stats = _conv_fwd(x, ldx, wr, None, conv_out, Cout, geom, 0, stats)
+            fused_stats = _conv_fwd(x, ldx, weight, _wcache.getter(weight), None, conv_out, Cout, geom, 0, stats)
         if need_stats and not fused_stats:
             _check(lib().dfine_bn_stats(_p(conv_out), _p(stats), c_long(M), Cout, _stream()), "bn_stats")
         scale = torch.empty(Cout, device=dev, dtype=torch.float32)
@@ -325,7 +396,7 @@ class _ConvBnAct(torch.autograd.Function):
         else:
             if ctx.needs_input_grad[0]:
                 g_x = torch.empty((B, H, W, Cin), device=dev, dtype=torch.float32)
-                _conv_dgrad(dconv, Cout, weight, g_x, Cin, ctx.geom, lambda kind, mk: _wcache.get(weight, kind, mk))
+                _conv_dgrad(dconv, Cout, weight, _wcache.getter(weight), g_x, Cin, ctx.geom)
             if ctx.needs_input_grad[1]:
                 g_w = _conv_wgrad(dconv, Cout, x, ldx, ctx.geom).permute(0, 3, 1, 2)
         g_post = dy if ctx.has_post else None
@@ -341,12 +412,10 @@ class _Linear(torch.autograd.Function):
         _req_cuda(x, w)
         N, Kd = w.shape
         x2, M, ldx = _rows(x)
-        if not w.is_contiguous():
-            w = w.contiguous()
         out = torch.empty(x.shape[:-1] + (N,), device=x.device, dtype=torch.float32)
         geom = (1, 1, M, Kd, 1, M, N, 1, 1, (0, 0, 0, 0))
         fused_act = act if act in (None, "relu") else None
-        _conv_fwd(x2, ldx, w, b, out, N, geom, ACT[fused_act])
+        _conv_fwd(x2, ldx, w, _wcache.getter(w), b, out, N, geom, ACT[fused_act])
         saved_z = None
         if act is not None and fused_act is None:
             saved_z = out
@@ -369,13 +438,7 @@ class _Linear(torch.autograd.Function):
         g_x = g_w = g_b = None
         if ctx.needs_input_grad[0]:
             g_x = torch.empty(xshape, device=dy.device, dtype=torch.float32)
-            if _tc_ok(N, Kd, 1, 1, (0, 0, 0, 0), N, Kd):
-                wt = w.t().contiguous()
-                _check(lib().dfine_conv_fwd_tc(_p(dy), _p(wt), None, _p(g_x), None, 1, 1, M, N, Kd, 1, 1, c_long(N),
-                                               c_long(Kd), 0, _stream()), "linear_dgrad_tc")
-            else:
-                _check(lib().dfine_conv_dgrad_simt(_p(dy), _p(w), _p(g_x), 1, 1, M, Kd, 1, M, N, 1, 1, 1, 0, 0,
-                                                   c_long(Kd), c_long(N), _stream()), "linear_dgrad_simt")
+            _conv_dgrad(dy, N, w, _wcache.getter(w), g_x, Kd, geom)
         if ctx.needs_input_grad[1]:
             g_w = _conv_wgrad(dy, N, x2, ldx, geom).reshape(N, Kd)
         if has_bias and ctx.needs_input_grad[2]:

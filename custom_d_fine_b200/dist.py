@@ -80,6 +80,20 @@ def broadcast_scalar(value, src: int = 0):
     return t.item()
 
 
+def allreduce_mean_(t):
+    """In-place mean over ranks of a flat tensor (the gradient arenas).  NCCL averages inside the collective
+    (ReduceOp.AVG over NVLink / NVSwitch); gloo (CPU tests) sums and divides."""
+    world = get_world_size()
+    if world < 2:
+        return t
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(t, op=dist.ReduceOp.AVG)
+    else:
+        dist.all_reduce(t)
+        t.div_(world)
+    return t
+
+
 def synchronize() -> None:
     if get_world_size() > 1:
         dist.barrier()

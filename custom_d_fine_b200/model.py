@@ -88,10 +88,14 @@ def param_groups(model, backbone_lr, base_lr):
 
 
 def build_optimizer(model, lr, backbone_lr, betas, weight_decay, base_lr):
-    # capturable: the step counter lives on the device so the update can be replayed inside a CUDA graph
-    on_cuda = all(p.is_cuda for p in model.parameters())
-    return optim.AdamW(param_groups(model, backbone_lr, base_lr), lr=lr, betas=betas,
-                       weight_decay=weight_decay, capturable=on_cuda)
+    """AdamW over the reference's four groups (dfine.py:87-124).  On the GPU this is the flat-arena optimizer
+    (custom_d_fine_b200/optim.py: clip + AdamW + EMA + zero_grad fused, graph-replayable, scheduler-compatible);
+    on a CPU-resident model (host-logic tests) it is torch.optim.AdamW."""
+    groups = param_groups(model, backbone_lr, base_lr)
+    if all(p.is_cuda for p in model.parameters()):
+        from .optim import FusedAdamW
+        return FusedAdamW(groups, lr=lr, betas=betas, weight_decay=weight_decay)
+    return optim.AdamW(groups, lr=lr, betas=betas, weight_decay=weight_decay)
 
 
 # ---- checkpoint loading (src/d_fine/utils.py:92-181) ------------------------------------------

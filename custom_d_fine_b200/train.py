@@ -66,16 +66,40 @@ class ModelEMA:
 
 
 class TrainStep:
-    """One optimisation step on one batch: forward, criterion, backward, clip, AdamW, scheduler,
-    zero_grad, EMA — the reference's hot loop body (train.py:550-586 + 512-535), eager launches."""
+    """One optimisation step on one batch: forward, criterion, backward, (gradient all-reduce), clip, AdamW,
+    scheduler, zero_grad, EMA — the reference's hot loop body (train.py:550-586 + 512-535), eager launches.
+
+    With the flat-arena optimizer (optim.FusedAdamW, every CUDA run) clip + AdamW + EMA + zero_grad are three
+    fused launches per group and data-parallel ranks all-reduce the flat gradient arenas; with a stock torch
+    optimizer (CPU host-logic tests, or a DDP-wrapped model) the reference's call sequence is issued as is."""
 
     def __init__(self, model, loss_fn, optimizer, scheduler=None, ema=None, clip_max_norm=0.1, accum_steps=1):
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
         self.scheduler, self.ema, self.clip_max_norm = scheduler, ema, clip_max_norm
         self.accum_steps, self.ema_iter, self.batch_idx = accum_steps, 0, 0
+        self.fused = getattr(optimizer, "fused_step", False)
+        if self.fused:
+            optimizer.max_norm = float(clip_max_norm or 0.0)
+            if ema is not None:
+                optimizer.attach_ema(ema, model)
+            optimizer.broadcast_state(0)
+
+    def _host_prepare(self):
+        """Host half of optimizer_step (never captured): counters and the per-step scalars."""
+        m = None
+        if self.ema is not None:
+            self.ema_iter += 1
+            m = self.ema.ema_scheduler(self.ema_iter)
+        if self.fused:
+            self.optimizer.prepare(m)
+        elif self.ema is not None:
+            self.ema.set_momentum(self.ema_iter, self.model)
 
     def _apply_grads(self):
         """clip -> AdamW -> zero_grad -> EMA blend: the device part of optimizer_step (graph-capturable)."""
+        if self.fused:
+            self.optimizer.step()
+            return
         if self.clip_max_norm:
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.clip_max_norm)
         self.optimizer.step()
@@ -84,9 +108,9 @@ class TrainStep:
             self.ema.apply()
 
     def optimizer_step(self, step_scheduler=True):
-        if self.ema is not None:
-            self.ema_iter += 1
-            self.ema.set_momentum(self.ema_iter, self.model)
+        self._host_prepare()
+        if self.fused:
+            self.optimizer.allreduce_grads()
         self._apply_grads()
         if step_scheduler and self.scheduler is not None:
             self.scheduler.step()
@@ -104,17 +128,20 @@ class TrainStep:
 
 
 class GraphedTrainStep(TrainStep):
-    """The same step replayed as two CUDA graphs around the host-side index planning:
+    """The same step replayed as CUDA graphs around the two host-side pieces of a step:
 
         graph A : model forward (+CDN) + the one-launch Hungarian matcher
         host    : D2H of the [n_layers, sumT] index table, GO union, normalisers, one pinned H2D
-        graph B : every loss term, backward, grad clip, AdamW, EMA
+        graph B : every loss term + backward (gradients accumulate into the flat arenas)
+        NCCL    : all-reduce of the flat gradient arenas (data-parallel runs only; issued between the graphs)
+        graph C : gradient clip + AdamW + EMA + zero_grad (flat-arena optimizer)
 
     The reference's step is ~9 k kernel launches driven by Python; replaying it removes the host from the
     critical path.  Graphs are keyed by (input shape, targets' sizes); the first ``eager_steps`` calls of a
     key run eagerly (they are real training steps and double as the warm-up CUDA graphs require), then
-    the key is captured.  Constraints: single process (DDP steps stay eager), no gradient accumulation,
-    constant learning rate inside a captured key (a scheduler forces the eager path)."""
+    the key is captured.  Learning rate, weight decay, step count and EMA momentum are read by graph C from a
+    device table refreshed before each replay, so an LR scheduler keeps working.  Constraint: no gradient
+    accumulation (accum_steps == 1) and the flat-arena optimizer; anything else runs the eager step."""
 
     def __init__(self, *args, eager_steps=3, **kw):
         super().__init__(*args, **kw)
@@ -124,7 +151,7 @@ class GraphedTrainStep(TrainStep):
         self._plans = {}
 
     def _can_graph(self):
-        return (self.accum_steps == 1 and self.scheduler is None and not isinstance(self.model, DDP)
+        return (self.accum_steps == 1 and self.fused and not isinstance(self.model, DDP)
                 and next(self.model.parameters()).is_cuda)
 
     def __call__(self, inputs, targets):
@@ -156,7 +183,7 @@ class GraphedTrainStep(TrainStep):
         n0 = cuda_ops.counters.launches
         g["table"] = plan.table.to(dev)
         g["counts"] = plan.counts.to(dev)
-        self.optimizer.zero_grad(set_to_none=True)
+        self.optimizer.zero_grad()
         torch.cuda.synchronize()
         gA = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gA):
@@ -167,10 +194,12 @@ class GraphedTrainStep(TrainStep):
             loss_dict = crit.compute(out, tg, g["table"], g["counts"], plan)
             loss = sum(loss_dict.values())
             loss.backward()
-            self._apply_grads()
             g["loss"] = loss.detach()
             g["loss_dict"] = {k: v.detach() for k, v in loss_dict.items()}
-        g.update(gA=gA, gB=gB, out=out, raw=raw, launches=cuda_ops.counters.launches - n0)
+        gC = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gC, pool=gA.pool()):
+            self._apply_grads()
+        g.update(gA=gA, gB=gB, gC=gC, out=out, raw=raw, launches=cuda_ops.counters.launches - n0)
         return g
 
     def _replay(self, g, inputs, targets):
@@ -178,15 +207,18 @@ class GraphedTrainStep(TrainStep):
         for s, t in zip(g["targets"], targets):
             s["labels"].copy_(t["labels"], non_blocking=True)
             s["boxes"].copy_(t["boxes"], non_blocking=True)
-        if self.ema is not None:
-            self.ema_iter += 1
-            self.ema.set_momentum(self.ema_iter, self.model)
+        self._host_prepare()
         g["gA"].replay()
         plan = self.loss_fn.plan(g["out"], g["targets"], g["raw"], g["plan"])     # syncs on the matcher D2H
         g["table"].copy_(plan.table, non_blocking=True)
         g["counts"].copy_(plan.counts, non_blocking=True)
         g["gB"].replay()
+        self.optimizer.allreduce_grads()
+        g["gC"].replay()
+        if self.scheduler is not None:
+            self.scheduler.step()
         from . import cuda_ops
-        cuda_ops.counters.launches += g["launches"]      # library kernels replayed by the two graphs
+        cuda_ops.weights_changed()                       # graph C rewrote the parameters
+        cuda_ops.counters.launches += g["launches"]      # library kernels replayed by the graphs
         self.batch_idx += 1
         return g["loss"], g["loss_dict"]

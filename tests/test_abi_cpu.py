@@ -1,0 +1,54 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds/loads here (nvcc cross-compiles, no GPU needed),
+exports every symbol include/dfine_sm100.h declares, and the header matches the DFINE_API definitions in csrc/.
+No compute entry point is called."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from custom_d_fine_b200.build import build
+    return build()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from custom_d_fine_b200 import cuda_ops
+    protos = cuda_ops.abi_prototypes()
+    assert len(protos) >= 35
+    L = ctypes.CDLL(str(built_lib))
+    missing = [n for n in protos if not hasattr(L, n)]
+    assert not missing, missing
+    L.dfine_abi_version.restype = ctypes.c_int
+    assert L.dfine_abi_version() == 1
+    L.dfine_last_error.restype = ctypes.c_char_p
+    assert isinstance(L.dfine_last_error(), bytes)
+
+
+def test_header_matches_sources():
+    from custom_d_fine_b200 import cuda_ops
+    declared = set(cuda_ops.abi_prototypes())
+    defined = set()
+    for src in (ROOT / "custom_d_fine_b200" / "csrc").glob("*.cu"):
+        defined |= set(re.findall(r"DFINE_API\s+(?:const\s+char\*|int|long)\s+(dfine_\w+)\s*\(", src.read_text()))
+    assert declared == defined, (sorted(declared - defined), sorted(defined - declared))
+
+
+def test_product_path_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing in the package may import it."""
+    for py in (ROOT / "custom_d_fine_b200").rglob("*.py"):
+        text = py.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), py
+
+
+def test_ops_fail_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from custom_d_fine_b200.cuda_ops import CudaOps
+    with pytest.raises(RuntimeError):
+        CudaOps()

@@ -192,40 +192,58 @@ def test_maxpool_upsample(cuda_ops, oracle_ops):
     run_both(lambda K, y: K.upsample_nearest2x(y), cuda_ops, oracle_ops, [y], 0.0, 1e-6)
 
 
-def test_tc_matches_simt(cuda_ops):
-    """tcgen05 kernels against the CUDA-core kernels of the same library on identical device data."""
-    import ctypes
+TC_CASES = [
+    # B, H, W, Cin, Cout, k, stride, pad(t,l,b,r)
+    (2, 40, 40, 128, 128, 3, 1, (1, 1, 1, 1)),
+    (1, 1, 4000, 256, 512, 1, 1, (0, 0, 0, 0)),       # nn.Linear shape
+    (2, 80, 80, 64, 64, 3, 1, (1, 1, 1, 1)),
+    (3, 20, 20, 1280, 384, 1, 1, (0, 0, 0, 0)),
+    (1, 1, 999, 20, 64, 1, 1, (0, 0, 0, 0)),          # ragged K (LQE MLP)
+    (2, 64, 64, 48, 24, 3, 2, (1, 1, 1, 1)),          # stem3: stride 2 through the TMA element strides
+    (2, 33, 47, 48, 24, 3, 2, (1, 1, 1, 1)),          # odd sizes, stride 2
+    (2, 40, 40, 24, 12, 2, 1, (0, 0, 1, 1)),          # stem2a: 2x2, bottom/right padding, Cout 12
+    (2, 40, 40, 12, 24, 2, 1, (0, 0, 1, 1)),          # stem2b: Cin 12
+    (1, 1, 700, 4, 512, 1, 1, (0, 0, 0, 0)),          # query_pos_head layer 0: K = 4
+    (1, 1, 700, 256, 4, 1, 1, (0, 0, 0, 0)),          # bbox head: N = 4
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "x".join(str(v) for v in c[:7]))
+def test_tc_matches_simt(cuda_ops, case):
+    """tcgen05 kernels (plain tf32 and 3xTF32 forward, tf32 dgrad / wgrad) against the fp32 CUDA-core kernels of
+    the same library on identical device data, through the host launchers the autograd functions use."""
     from custom_d_fine_b200 import cuda_ops as co
-    L = co.lib()
+    B, H, W, Cin, Cout, k, stride, pad = case
     g = _g(6)
-    for (B, H, W, Cin, Cout, k) in [(2, 40, 40, 128, 128, 3), (1, 1, 4000, 256, 512, 1), (2, 80, 80, 64, 64, 3),
-                                    (3, 20, 20, 1280, 384, 1), (1, 1, 999, 20, 64, 1)]:
-        x = torch.randn(B, H, W, Cin, generator=g).cuda()
-        wr = (torch.randn(Cout, k, k, Cin, generator=g) / math.sqrt(k * k * Cin)).cuda()
-        dy = torch.randn(B, H, W, Cout, generator=g).cuda()
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        p = k // 2
-        y_tc, y_si = torch.zeros(B, H, W, Cout).cuda(), torch.zeros(B, H, W, Cout).cuda()
-        stats = torch.zeros(2 * Cout, dtype=torch.float64).cuda()
-        co._check(L.dfine_conv_fwd_tc(co._p(x), co._p(wr), None, co._p(y_tc), co._p(stats), B, H, W, Cin, Cout, k, k,
-                                      Cin, Cout, 0, st), "tc")
-        co._check(L.dfine_conv_fwd_simt(co._p(x), co._p(wr), None, co._p(y_si), B, H, W, Cin, H, W, Cout, k, k, 1, p,
-                                        p, Cin, Cout, 0, st), "simt")
-        check_close(f"fwd {B,H,W,Cin,Cout,k}", y_tc, y_si, TF32)
-        M = B * H * W
-        check_close("fused stats sum", stats[:Cout].float(), y_si.reshape(M, Cout).sum(0), TF32 * 5)
-        check_close("fused stats sumsq", stats[Cout:].float(), (y_si.reshape(M, Cout) ** 2).sum(0), TF32)
-        dw_tc, dw_si = torch.zeros(Cout, k, k, Cin).cuda(), torch.zeros(Cout, k, k, Cin).cuda()
-        co._check(L.dfine_conv_wgrad_tc(co._p(dy), co._p(x), co._p(dw_tc), B, H, W, Cin, Cout, k, k, Cin, Cout, st),
-                  "wgrad_tc")
-        co._check(L.dfine_conv_wgrad_simt(co._p(dy), co._p(x), co._p(dw_si), B, H, W, Cin, H, W, Cout, k, k, 1, p, p,
-                                          Cin, Cout, st), "wgrad_simt")
-        check_close(f"wgrad {B,H,W,Cin,Cout,k}", dw_tc, dw_si, TF32)
-        # data gradient: tcgen05 forward kernel on dy with flipped / transposed taps vs the CUDA-core dgrad
-        wd = wr.permute(0, 3, 1, 2).flip(2, 3).permute(1, 2, 3, 0).contiguous()     # [Cin, k, k, Cout]
-        dx_tc, dx_si = torch.zeros(B, H, W, Cin).cuda(), torch.zeros(B, H, W, Cin).cuda()
-        co._check(L.dfine_conv_fwd_tc(co._p(dy), co._p(wd), None, co._p(dx_tc), None, B, H, W, Cout, Cin, k, k, Cout,
-                                      Cin, 0, st), "dgrad_tc")
-        co._check(L.dfine_conv_dgrad_simt(co._p(dy), co._p(wr), co._p(dx_si), B, H, W, Cin, H, W, Cout, k, k, 1, p, p,
-                                          Cin, Cout, st), "dgrad_simt")
-        check_close(f"dgrad {B,H,W,Cin,Cout,k}", dx_tc, dx_si, TF32)
+    OH = (H + pad[0] + pad[2] - k) // stride + 1
+    OW = (W + pad[1] + pad[3] - k) // stride + 1
+    geom = (B, H, W, Cin, OH, OW, Cout, k, stride, pad)
+    x = torch.randn(B, H, W, Cin, generator=g).cuda()
+    weight = (torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(k * k * Cin)).cuda()
+    dy = torch.randn(B, OH, OW, Cout, generator=g).cuda()
+    M = B * OH * OW
+    res = {}
+    prev = co.get_gemm_mode()
+    try:
+        for mode in ("simt", "tc", "tc3"):
+            co.set_gemm_mode(mode)
+            cache = co._WCache()
+            y = torch.zeros(B, OH, OW, Cout).cuda()
+            stats = torch.zeros(2 * Cout, dtype=torch.float64).cuda()
+            used_tc = co._conv_fwd(x, Cin, weight, cache.getter(weight), None, y, Cout, geom, 0, stats)
+            assert used_tc == (mode != "simt"), "the tensor-core path must take every TC_CASES geometry"
+            dx = torch.full((B, H, W, Cin), float("nan")).cuda()
+            co._conv_dgrad(dy, Cout, weight, cache.getter(weight), dx, Cin, geom)
+            dw = co._conv_wgrad(dy, Cout, x, Cin, geom)
+            torch.cuda.synchronize()
+            res[mode] = (y, stats, dx, dw)
+    finally:
+        co.set_gemm_mode(prev)
+    y0, _, dx0, dw0 = res["simt"]
+    for mode, tol in (("tc", TF32), ("tc3", 2e-5)):
+        y, stats, dx, dw = res[mode]
+        check_close(f"{mode} fwd {case}", y, y0, tol)
+        check_close(f"{mode} fused stats sum", stats[:Cout].float(), y0.reshape(M, Cout).sum(0), max(tol, 1e-4) * 5)
+        check_close(f"{mode} fused stats sumsq", stats[Cout:].float(), (y0.reshape(M, Cout) ** 2).sum(0), max(tol, 1e-4))
+        check_close(f"{mode} dgrad {case}", dx, dx0, TF32)
+        check_close(f"{mode} wgrad {case}", dw, dw0, TF32)

@@ -1,0 +1,66 @@
+"""Flat-arena fused optimizer (csrc/optim.cu: clip + AdamW + EMA + zero_grad) against the reference's call
+sequence on torch CPU ops: clip_grad_norm_(0.1) -> torch.optim.AdamW.step -> zero_grad -> ModelEMA.update
+(/root/reference/src/dl/train.py:512-535, 62-73).  Floating-point kernel: tolerance 2e-6 of each tensor's max."""
+import copy
+import math
+
+import pytest
+import torch
+import torch.nn as nn
+
+from tests.util import check_close
+
+pytestmark = pytest.mark.gpu
+
+
+class _Toy(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.backbone = nn.Sequential(nn.Conv2d(3, 7, 3), nn.BatchNorm2d(7))
+        self.encoder = nn.Linear(13, 5)
+        self.decoder = nn.Linear(5, 3)
+        self.head = nn.Parameter(torch.randn(33))
+
+
+def _groups(model):
+    from custom_d_fine_b200.model import param_groups
+    return param_groups(model, 2e-5, 1.5e-4)
+
+
+def test_fused_adamw_ema_matches_torch(cuda_ops):
+    from custom_d_fine_b200.optim import FusedAdamW
+    from custom_d_fine_b200.train import ModelEMA
+    torch.manual_seed(0)
+    ref = _Toy()
+    dev = copy.deepcopy(ref).cuda()
+    ema_ref, ema_dev = ModelEMA(ref, 0.9998), ModelEMA(dev, 0.9998)
+    opt_ref = torch.optim.AdamW(_groups(ref), lr=1.5e-4, betas=(0.9, 0.999), weight_decay=1.25e-4)
+    opt_dev = FusedAdamW(_groups(dev), lr=1.5e-4, betas=(0.9, 0.999), weight_decay=1.25e-4, max_norm=0.1)
+    opt_dev.attach_ema(ema_dev, dev)
+    g = torch.Generator().manual_seed(1)
+    for it in range(1, 6):
+        for gi, grp in enumerate(opt_ref.param_groups):          # a scheduler changing lr between steps
+            grp["lr"] = opt_dev.param_groups[gi]["lr"] = grp["initial_lr"] * (1 + 0.1 * it)
+        scale = 10.0 if it % 2 else 1e-3                         # clipped and un-clipped steps
+        for (n, p), (_, q) in zip(ref.named_parameters(), dev.named_parameters()):
+            gr = torch.randn(p.shape, generator=g) * scale
+            p.grad = gr.clone()
+            q.grad.copy_(gr)                                     # gradients live in the flat arena
+        ref.backbone[1].running_mean.add_(0.01 * it)             # a floating-point buffer the EMA must track
+        dev.backbone[1].running_mean.add_(0.01 * it)
+        total = torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.1)
+        opt_ref.step()
+        opt_ref.zero_grad()
+        ema_ref.update(it, ref)
+        opt_dev.prepare(ema_ref.ema_scheduler(it))
+        opt_dev.step()
+        torch.cuda.synchronize()
+        check_close("grad norm", opt_dev.grad_norm().float().cpu(), total.reshape(1), 1e-5)
+        for (n, p), (_, q) in zip(ref.named_parameters(), dev.named_parameters()):
+            check_close(f"param {n} step {it}", q, p, 2e-6)
+            assert float(q.grad.abs().max()) == 0.0, "step() must leave zeroed gradients"
+        es, ed = ema_ref.model.state_dict(), ema_dev.model.state_dict()
+        for k in es:
+            if es[k].dtype.is_floating_point:
+                check_close(f"ema {k} step {it}", ed[k], es[k], 2e-6)
+    assert math.isfinite(float(opt_dev.grad_norm()))
