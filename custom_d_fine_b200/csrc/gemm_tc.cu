@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(fwd_threads(X3)) tc_fwd_kernel(const __grid_co
     if (warp == 0 && lane == 0) { prefetch_tmap(&map_x); prefetch_tmap(&map_w); if (X3) prefetch_tmap(&map_wlo); }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); mbar_init(&sm.conv[s], 4); }
+            for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); mbar_init(&sm.conv[s], 128); }
             mbar_init(&sm.acc_full, 1);
             fence_barrier_init();
         }
@@ -326,26 +326,31 @@ __global__ void __launch_bounds__(fwd_threads(X3)) tc_fwd_kernel(const __grid_co
             __syncwarp();
         }
     } else if (X3) {
-        // converter warps 6..9: split the landed activation tile into tf32 hi (in place) and lo parts
+        // converter warps 6..9: split the landed activation tile into tf32 hi (in place) and lo parts.
+        // Explicit ld.shared / st.shared (not generic accesses through the shared window) so that
+        // fence.proxy.async.shared::cta orders exactly these writes before the tensor core's async-proxy reads;
+        // every converter thread fences its own writes and arrives itself (barrier count 128).
         const int ct = threadIdx.x - 192;  // 0..127
         for (int kb = 0; kb < num_k; ++kb) {
             const int s = kb % STAGES, ph = (kb / STAGES) & 1;
             mbar_wait(&sm.full[s], ph);
-            float4* a4 = reinterpret_cast<float4*>(sm.a[s]);
-            float4* l4 = reinterpret_cast<float4*>(sm.alo[s]);
+            const uint32_t a_base = smem_u32(sm.a[s]), l_base = smem_u32(sm.alo[s]);
 #pragma unroll
             for (int i = 0; i < BM * BK / 4 / 128; ++i) {
-                const int idx = ct + i * 128;
-                const float4 v = a4[idx];
+                const uint32_t off = (uint32_t)(ct + i * 128) * 16u;
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a_base + off) : "memory");
                 float4 hi, lo;
                 hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
                 lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
-                a4[idx] = hi;
-                l4[idx] = lo;
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + off), "f"(hi.x), "f"(hi.y),
+                             "f"(hi.z), "f"(hi.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(l_base + off), "f"(lo.x), "f"(lo.y),
+                             "f"(lo.z), "f"(lo.w) : "memory");
             }
             fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.conv[s]);
+            mbar_arrive(&sm.conv[s]);
         }
     }
     tc_fence_before();

@@ -174,10 +174,18 @@ __global__ void __launch_bounds__(NT) bn_bwd_apply_kernel(
     const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ scale,
     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ pre_add, const float* __restrict__ lab, const double* __restrict__ red,
-    float* __restrict__ dx, float* __restrict__ dpre, long n4, int VC, long M, int act, int training) {
+    float* __restrict__ dx, float* __restrict__ dpre, long n4, int VC, long M, int act, int training,
+    float* __restrict__ g_w, float* __restrict__ g_b, float* __restrict__ g_lab_s, float* __restrict__ g_lab_b) {
     const float ls = lab ? __ldg(lab) : 1.f;
     const int C = VC * 4;
     const double invM = 1.0 / (double)M;
+    if (blockIdx.x == 0) {
+        // parameter gradients straight into the (flat-arena) .grad tensors: d(bn.weight) = sum dz*xhat,
+        // d(bn.bias) = sum dz, LAB scalars; `red` is complete (written by the previous launch)
+        if (g_w)
+            for (int c = threadIdx.x; c < C; c += NT) { g_w[c] += (float)red[C + c]; g_b[c] += (float)red[c]; }
+        if (g_lab_s && threadIdx.x == 0) { g_lab_s[0] += (float)red[2 * C]; g_lab_b[0] += (float)red[2 * C + 1]; }
+    }
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long)gridDim.x * NT) {
         const int c = (int)(i % VC) * 4;
         const float4 g = ld4(dy + i * 4), v = ld4(x + i * 4), sc = ld4(scale + c), sf = ld4(shift + c);
@@ -391,12 +399,15 @@ DFINE_API int dfine_bn_bwd_reduce(const float* dy, const float* x, const float* 
 DFINE_API int dfine_bn_bwd_apply(const float* dy, const float* x, const float* scale, const float* shift,
                                  const float* mean, const float* invstd, const float* pre_add, const float* lab,
                                  const double* red, float* dx, float* dpre, long M, int C, int act, int training,
-                                 void* stream) {
+                                 float* g_w, float* g_b, float* g_lab_s, float* g_lab_b, void* stream) {
     DFINE_REQUIRE(C % 4 == 0, "bn_bwd_apply: C=%d", C);
+    DFINE_REQUIRE((g_w == nullptr) == (g_b == nullptr) && (g_lab_s == nullptr) == (g_lab_b == nullptr),
+                  "bn_bwd_apply: gradient outputs come in pairs");
     const long n4 = M * C / 4;
     if (n4 == 0) return 0;
     bn_bwd_apply_kernel<<<ew_grid(n4), NT, 0, (cudaStream_t)stream>>>(dy, x, scale, shift, mean, invstd, pre_add, lab,
-                                                                     red, dx, dpre, n4, C / 4, M, act, training);
+                                                                     red, dx, dpre, n4, C / 4, M, act, training, g_w,
+                                                                     g_b, g_lab_s, g_lab_b);
     DFINE_LAUNCH_CHECK("bn_bwd_apply");
     return 0;
 }

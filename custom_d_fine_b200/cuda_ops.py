@@ -241,9 +241,25 @@ def _conv_dgrad(dy, ldy, weight, wkey, dx, ldx, geom):
                                        pad[1], c_long(ldx), c_long(ldy), _stream()), "conv_dgrad_simt")
 
 
-def _conv_wgrad(dy, ldy, x, ldx, geom):
+def _grad_dst(p, kind):
+    """The parameter's pre-zeroed ``.grad`` viewed in the layout a kernel accumulates into, or None.
+    With the flat-arena optimizer (optim.FusedAdamW) gradients live in an arena zeroed by the optimizer step, so
+    backward kernels add straight into it (no temporary, no AccumulateGrad add kernel); a parameter without such
+    a gradient buffer (plain torch optimizer) takes the returned-gradient path."""
+    if p is None or not p.is_leaf or not p.requires_grad:
+        return None
+    g = p.grad
+    if g is None or not g.is_cuda or g.dtype != torch.float32:
+        return None
+    if kind == "conv":          # [Co,Ci,kh,kw] stored channels-last -> [Co,kh,kw,Ci] contiguous
+        v = g.permute(0, 2, 3, 1)
+        return v if v.is_contiguous() else None
+    return g if g.is_contiguous() else None
+
+
+def _conv_wgrad(dy, ldy, x, ldx, geom, dst=None):
     B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
-    dwr = torch.zeros((Cout, k, k, Cin), device=dy.device, dtype=torch.float32)
+    dwr = dst if dst is not None else torch.zeros((Cout, k, k, Cin), device=dy.device, dtype=torch.float32)
     if _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy):
         _check(lib().dfine_conv_wgrad_tc(_p(dy), _p(x), _p(dwr), B, H, W, Cin, OH, OW, Cout, k, k, stride, pad[0],
                                          pad[1], c_long(ldx), c_long(ldy), _stream()), "conv_wgrad_tc")
@@ -346,6 +362,7 @@ class _ConvBnAct(torch.autograd.Function):
         ctx.save_for_backward(x, weight, conv_out, scale, shift, mean, invstd, pre_add, lab_s, lab_b, bn_w)
         ctx.geom, ctx.ldx, ctx.cfg = geom, ldx, cfg
         ctx.has_post = post_add is not None
+        ctx.bn_b_ref = bn_b
         return y
 
     @staticmethod
@@ -368,17 +385,32 @@ class _ConvBnAct(torch.autograd.Function):
                    "bn_bwd_reduce")
         dconv = torch.empty_like(conv_out)
         dpre = torch.empty_like(conv_out) if (pre_add is not None and ctx.needs_input_grad[6]) else None
+        # parameter gradients of BN / LAB: accumulated by the apply kernel straight into the .grad arenas
+        bn_direct = lab_direct = None
+        if bn_train and bn_w is not None and ctx.needs_input_grad[2]:
+            gw_, gb_ = _grad_dst(bn_w, "flat"), _grad_dst(ctx.bn_b_ref, "flat")
+            if gw_ is not None and gb_ is not None:
+                bn_direct = (gw_, gb_)
+        if lab_s is not None:
+            gs_, gl_ = _grad_dst(lab_s, "flat"), _grad_dst(lab_b, "flat")
+            if gs_ is not None and gl_ is not None:
+                lab_direct = (gs_, gl_)
         _check(lib().dfine_bn_bwd_apply(_p(dy), _p(conv_out), _p(scale), _p(shift), _p(mean), _p(invstd), _p(pre_add),
                                         _p(lab_s), _p(red), _p(dconv), _p(dpre), c_long(M), Cout, ACT[act],
-                                        1 if bn_train else 0, _stream()), "bn_bwd_apply")
+                                        1 if bn_train else 0, _p(bn_direct[0]) if bn_direct else None,
+                                        _p(bn_direct[1]) if bn_direct else None,
+                                        _p(lab_direct[0]) if lab_direct else None,
+                                        _p(lab_direct[1]) if lab_direct else None, _stream()), "bn_bwd_apply")
         g_bn_w = g_bn_b = g_lab_s = g_lab_b = None
         if red is not None:
-            redf = red.float()
-            if bn_train and bn_w is not None and ctx.needs_input_grad[2]:
+            redf = None
+            if bn_train and bn_w is not None and ctx.needs_input_grad[2] and bn_direct is None:
+                redf = red.float()
                 g_bn_w, g_bn_b = redf[Cout:2 * Cout], redf[:Cout]
             elif not bn_train and bn_w is not None and ctx.needs_input_grad[2]:
                 raise RuntimeError("eval-mode BatchNorm affine gradients are not on the training path")
-            if lab_s is not None:
+            if lab_s is not None and lab_direct is None:
+                redf = red.float() if redf is None else redf
                 g_lab_s, g_lab_b = redf[2 * Cout:2 * Cout + 1], redf[2 * Cout + 1:2 * Cout + 2]
         g_x = g_w = None
         ldx = ctx.ldx
@@ -398,7 +430,11 @@ class _ConvBnAct(torch.autograd.Function):
                 g_x = torch.empty((B, H, W, Cin), device=dev, dtype=torch.float32)
                 _conv_dgrad(dconv, Cout, weight, _wcache.getter(weight), g_x, Cin, ctx.geom)
             if ctx.needs_input_grad[1]:
-                g_w = _conv_wgrad(dconv, Cout, x, ldx, ctx.geom).permute(0, 3, 1, 2)
+                dst = _grad_dst(weight, "conv")
+                if dst is not None:
+                    _conv_wgrad(dconv, Cout, x, ldx, ctx.geom, dst)      # accumulated in place; autograd gets None
+                else:
+                    g_w = _conv_wgrad(dconv, Cout, x, ldx, ctx.geom).permute(0, 3, 1, 2)
         g_post = dy if ctx.has_post else None
         return g_x, g_w, g_bn_w, g_bn_b, g_lab_s, g_lab_b, dpre, g_post, None, None, None
 
@@ -423,6 +459,7 @@ class _Linear(torch.autograd.Function):
             _check(lib().dfine_act_fwd(_p(saved_z), _p(out), c_long(out.numel()), ACT[act], _stream()), "act_fwd")
         ctx.save_for_backward(x2, w, saved_z if saved_z is not None else (out if act == "relu" else None))
         ctx.meta = (M, ldx, geom, act, b is not None, x.shape)
+        ctx.bias_ref = b
         return out
 
     @staticmethod
@@ -440,10 +477,17 @@ class _Linear(torch.autograd.Function):
             g_x = torch.empty(xshape, device=dy.device, dtype=torch.float32)
             _conv_dgrad(dy, N, w, _wcache.getter(w), g_x, Kd, geom)
         if ctx.needs_input_grad[1]:
-            g_w = _conv_wgrad(dy, N, x2, ldx, geom).reshape(N, Kd)
+            dst = _grad_dst(w, "flat")
+            if dst is not None:
+                _conv_wgrad(dy, N, x2, ldx, geom, dst.view(N, 1, 1, Kd))
+            else:
+                g_w = _conv_wgrad(dy, N, x2, ldx, geom).reshape(N, Kd)
         if has_bias and ctx.needs_input_grad[2]:
-            g_b = torch.zeros(N, device=dy.device, dtype=torch.float32)
-            _check(lib().dfine_colsum(_p(dy), _p(g_b), c_long(M), N, c_long(N), _stream()), "colsum")
+            b_ = ctx.bias_ref
+            dst = _grad_dst(b_, "flat") if b_ is not None else None
+            if dst is None:
+                g_b = dst = torch.zeros(N, device=dy.device, dtype=torch.float32)
+            _check(lib().dfine_colsum(_p(dy), _p(dst), c_long(M), N, c_long(N), _stream()), "colsum")
         return g_x, g_w, g_b, None
 
 
@@ -464,6 +508,7 @@ class _LayerNorm(torch.autograd.Function):
         _check(lib().dfine_layernorm_fwd(_p(x), _p(res), _p(w), _p(b), _p(y), _p(mean), _p(rstd), c_long(rows), D,
                                          c_float(eps), _stream()), "layernorm_fwd")
         ctx.save_for_backward(x, res, w, mean, rstd)
+        ctx.b_ref = b
         return y
 
     @staticmethod
@@ -473,10 +518,14 @@ class _LayerNorm(torch.autograd.Function):
         D = x.shape[-1]
         rows = x.numel() // D
         dx = torch.empty_like(x)
-        dwb = torch.zeros(2, D, device=x.device, dtype=torch.float32)
-        _check(lib().dfine_layernorm_bwd(_p(dy), _p(x), _p(res), _p(w), _p(mean), _p(rstd), _p(dx), _p(dwb[0]),
-                                         _p(dwb[1]), c_long(rows), D, _stream()), "layernorm_bwd")
-        return dx, (dx if res is not None else None), dwb[0], dwb[1], None
+        gw_, gb_ = _grad_dst(w, "flat"), _grad_dst(ctx.b_ref, "flat")
+        direct = gw_ is not None and gb_ is not None
+        if not direct:
+            dwb = torch.zeros(2, D, device=x.device, dtype=torch.float32)
+            gw_, gb_ = dwb[0], dwb[1]
+        _check(lib().dfine_layernorm_bwd(_p(dy), _p(x), _p(res), _p(w), _p(mean), _p(rstd), _p(dx), _p(gw_),
+                                         _p(gb_), c_long(rows), D, _stream()), "layernorm_bwd")
+        return dx, (dx if res is not None else None), None if direct else gw_, None if direct else gb_, None
 
 
 # ------------------------------------------------------------------------------------------------

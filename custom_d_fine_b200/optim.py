@@ -28,6 +28,17 @@ def _pad4(n):
     return (n + 3) // 4 * 4
 
 
+def _arena_view(arena, off, t):
+    """View of ``arena`` with ``t``'s shape.  Dense conv weights [Co,Ci,kh,kw] are stored channels-last
+    ([Co,kh,kw,Ci] in memory): that is the K-major layout the implicit-GEMM kernels read, so neither the forward
+    weight operand nor the weight gradient ever needs a re-layout copy."""
+    n = t.numel()
+    if t.dim() == 4 and t.shape[1] > 1 and t.shape[2] * t.shape[3] > 1:
+        co, ci, kh, kw = t.shape
+        return arena[off:off + n].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+    return arena[off:off + n].view(t.shape)
+
+
 def flatten_into_arena(tensors, device=None):
     """Re-home ``tensors`` (fp32) into one contiguous arena; each tensor's ``.data`` becomes a view whose offset
     is a multiple of 4 floats (16-byte aligned: TMA / float4 access).  Returns (arena, offsets)."""
@@ -38,7 +49,7 @@ def flatten_into_arena(tensors, device=None):
     device = device or (tensors[0].device if tensors else "cpu")
     arena = torch.zeros(max(total, 4), dtype=torch.float32, device=device)
     for t, o in zip(tensors, offs):
-        view = arena[o:o + t.numel()].view(t.shape)
+        view = _arena_view(arena, o, t)
         view.copy_(t.detach())
         t.data = view
     return arena, offs
@@ -69,7 +80,7 @@ class FusedAdamW(torch.optim.Optimizer):
             pflat, offs = flatten_into_arena(ps)
             gflat = torch.zeros_like(pflat)
             for p, o in zip(ps, offs):
-                p.grad = gflat[o:o + p.numel()].view(p.shape)
+                p.grad = _arena_view(gflat, o, p)          # same layout as the parameter: kernels accumulate in place
             self._arenas.append(dict(params=ps, offs=offs, p=pflat, g=gflat, m=torch.zeros_like(pflat),
                                      v=torch.zeros_like(pflat), ema=None))
         self._dev = dev

@@ -149,6 +149,9 @@ class GraphedTrainStep(TrainStep):
         self._seen = {}
         self._graphs = {}
         self._plans = {}
+        # Warm-up steps and captures share ONE side stream: autograd's AccumulateGrad nodes remember the stream
+        # they were created on, and a node created on the legacy default stream cannot be used under capture.
+        self._side = torch.cuda.Stream() if next(self.model.parameters()).is_cuda else None
 
     def _can_graph(self):
         return (self.accum_steps == 1 and self.fused and not isinstance(self.model, DDP)
@@ -162,12 +165,18 @@ class GraphedTrainStep(TrainStep):
         if g is None:
             n = self._seen.get(key, 0)
             self._seen[key] = n + 1
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                if n < self.eager_steps:
+                    res = super().__call__(inputs, targets)
+                    self._plans[key] = self.loss_fn.last_plan  # valid index plan of this key, reused to capture
+                else:
+                    g = self._capture(inputs, targets, self._plans.pop(key))
+                    self._graphs[key] = g
+            cur.wait_stream(self._side)
             if n < self.eager_steps:
-                res = super().__call__(inputs, targets)
-                self._plans[key] = self.loss_fn.last_plan      # valid index plan of this key, reused to capture
                 return res
-            g = self._capture(inputs, targets, self._plans.pop(key))
-            self._graphs[key] = g
         return self._replay(g, inputs, targets)
 
     def _capture(self, inputs, targets, plan):
@@ -186,18 +195,18 @@ class GraphedTrainStep(TrainStep):
         self.optimizer.zero_grad()
         torch.cuda.synchronize()
         gA = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gA):
+        with torch.cuda.graph(gA, stream=self._side):
             out = self.model(g["x"], targets=g["targets"])
             raw, tg = crit.match(out, g["targets"])
         gB = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gB, pool=gA.pool()):
+        with torch.cuda.graph(gB, pool=gA.pool(), stream=self._side):
             loss_dict = crit.compute(out, tg, g["table"], g["counts"], plan)
             loss = sum(loss_dict.values())
             loss.backward()
             g["loss"] = loss.detach()
             g["loss_dict"] = {k: v.detach() for k, v in loss_dict.items()}
         gC = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gC, pool=gA.pool()):
+        with torch.cuda.graph(gC, pool=gA.pool(), stream=self._side):
             self._apply_grads()
         g.update(gA=gA, gB=gB, gC=gC, out=out, raw=raw, launches=cuda_ops.counters.launches - n0)
         return g
