@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <cstdlib>
 
 namespace {
 
@@ -167,6 +168,7 @@ struct FwdParams {
     int YH, YW, osy, osx, ooy, oox;
     long ldy;                 // output pixel stride (elements)
     int act;
+    int dbg;                  // bring-up switch for the 3xTF32 converter (0 = normal)
 };
 
 // X3 = 0: one kind::tf32 MMA per k-step (operands truncated to tf32 by the tensor core).
@@ -344,6 +346,8 @@ __global__ void __launch_bounds__(fwd_threads(X3)) tc_fwd_kernel(const __grid_co
                 float4 hi, lo;
                 hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
                 lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+                if (p.dbg == 1) { lo = v; hi = make_float4(0.f, 0.f, 0.f, 0.f); }       // everything through alo
+                if (p.dbg == 3) { lo = make_float4(0.f, 0.f, 0.f, 0.f); hi = make_float4(0.f, 0.f, 0.f, 0.f); }
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + off), "f"(hi.x), "f"(hi.y),
                              "f"(hi.z), "f"(hi.w) : "memory");
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(l_base + off), "f"(lo.x), "f"(lo.y),
@@ -356,6 +360,216 @@ __global__ void __launch_bounds__(fwd_threads(X3)) tc_fwd_kernel(const __grid_co
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, BN);
+}
+
+// ------------------------------------------------------------------------------------------- persistent forward
+// Same math as tc_fwd_kernel, restructured the Blackwell way: ONE CTA per SM loops over output tiles
+// (tile = blockIdx.x + i*gridDim.x, N tiles of the same pixel patch adjacent so the A patch is fetched from
+// HBM once and re-served by L2), the smem ring runs continuously across tile boundaries, and the fp32
+// accumulator is DOUBLE-BUFFERED in TMEM (2*BN columns): the MMA warp starts tile i+1 while the four
+// epilogue warps drain tile i.  Removes the per-tile prologue (barrier init, TMEM alloc) that dominates the
+// small-K layers (stem / stage-1 maps with 10^4 tiles) and exposes no epilogue latency.
+template <int BN, int X3, int STAGES>
+struct PersistSmem {
+    alignas(1024) float a[STAGES][BM * BK];
+    alignas(1024) float b[STAGES][BN * BK];
+    alignas(1024) float alo[X3 ? STAGES : 1][X3 ? BM * BK : 32];
+    alignas(1024) float blo[X3 ? STAGES : 1][X3 ? BN * BK : 32];
+    float epi[4][32 * EPI_LD];
+    uint64_t full[STAGES], empty[STAGES], conv[STAGES], tfull[2], tempty[2];
+    uint32_t tmem_base;
+};
+
+struct TileSched {
+    int n_tiles, total;   // N tiles per pixel patch, total tiles
+};
+
+template <int BN, int X3, int STAGES>
+__global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __grid_constant__ CUtensorMap map_x,
+                                                                    const __grid_constant__ CUtensorMap map_w,
+                                                                    const __grid_constant__ CUtensorMap map_wlo,
+                                                                    float* __restrict__ y, const float* __restrict__ bias,
+                                                                    double* __restrict__ stats, FwdParams p, TileSched ts) {
+    extern __shared__ uint8_t raw[];
+    using Smem = PersistSmem<BN, X3, STAGES>;
+    Smem& sm = *reinterpret_cast<Smem*>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+    const int cblocks = (p.Cin + BK - 1) / BK;
+    const int num_k = p.n_taps * cblocks;
+    constexpr uint32_t TMEM_COLS = 2 * BN;
+
+    if (warp == 0 && lane == 0) { prefetch_tmap(&map_x); prefetch_tmap(&map_w); if (X3) prefetch_tmap(&map_wlo); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); mbar_init(&sm.conv[s], 128); }
+            for (int a = 0; a < 2; ++a) { mbar_init(&sm.tfull[a], 1); mbar_init(&sm.tempty[a], 4); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(&sm.tmem_base, TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
+                const int mt = t / ts.n_tiles, n0 = (t % ts.n_tiles) * BN;
+                const int img = mt / tiles_per_img, tt = mt % tiles_per_img;
+                const int h0 = (tt / p.tiles_w) * p.TH, w0 = (tt % p.tiles_w) * p.TW;
+                for (int kb = 0; kb < num_k; ++kb, ++g) {
+                    const int s = g % STAGES, ph = (g / STAGES) & 1;
+                    mbar_wait(&sm.empty[s], ph ^ 1);
+                    const int tap = kb / cblocks, c0 = (kb % cblocks) * BK;
+                    mbar_expect_tx(&sm.full[s], (uint32_t)((p.TW * p.TH + (X3 ? 2 : 1) * BN) * BK * sizeof(float)));
+                    tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 * p.in_stride + p.dw[tap],
+                                h0 * p.in_stride + p.dh[tap], img);
+                    tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
+                    if (X3) tma_load_2d(sm.blo[s], &map_wlo, &sm.full[s], p.wk[tap] + c0, n0);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+            uint32_t g = 0, i = 0;
+            for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
+                const uint32_t acc = i & 1, aph = (i >> 1) & 1;
+                mbar_wait(&sm.tempty[acc], aph ^ 1);          // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d = tmem + acc * BN;
+                for (int kb = 0; kb < num_k; ++kb, ++g) {
+                    const int s = g % STAGES, ph = (g / STAGES) & 1;
+                    mbar_wait(X3 ? &sm.conv[s] : &sm.full[s], ph);
+                    tc_fence_after();
+                    const uint64_t da = make_desc(smem_u32(sm.a[s]), 16, 1024);
+                    const uint64_t db = make_desc(smem_u32(sm.b[s]), 16, 1024);
+                    if (X3) {
+                        const uint64_t dal = make_desc(smem_u32(sm.alo[s]), 16, 1024);
+                        const uint64_t dbl = make_desc(smem_u32(sm.blo[s]), 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k) {
+                            umma_tf32(d, dal + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            umma_tf32(d, da + 2 * k, dbl + 2 * k, idesc, 1);
+                            umma_tf32(d, da + 2 * k, db + 2 * k, idesc, 1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k) umma_tf32(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&sm.empty[s]);
+                }
+                umma_commit(&sm.tfull[acc]);
+            }
+        }
+        __syncwarp();
+    } else if (warp < 6) {
+        const int q = warp % 4;  // TMEM lane quarter
+        float* buf = sm.epi[q];
+        uint32_t i = 0;
+        for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
+            const uint32_t acc = i & 1, aph = (i >> 1) & 1;
+            const int mt = t / ts.n_tiles, n0 = (t % ts.n_tiles) * BN;
+            const int img = mt / tiles_per_img, tt = mt % tiles_per_img;
+            const int h0 = (tt / p.tiles_w) * p.TH, w0 = (tt % p.tiles_w) * p.TW;
+            long row_off[8];
+            bool row_ok[8];
+#pragma unroll
+            for (int r8 = 0; r8 < 8; ++r8) {
+                const int r = 32 * q + 4 * r8 + lane / 8;
+                const int th = r / p.TW, tw = r % p.TW;
+                const int oh = h0 + th, ow = w0 + tw;
+                row_ok[r8] = th < p.TH && oh < p.OH && ow < p.OW;
+                row_off[r8] = (((long)img * p.YH + (long)oh * p.osy + p.ooy) * p.YW + (long)ow * p.osx + p.oox) * p.ldy;
+            }
+            mbar_wait(&sm.tfull[acc], aph);
+            tc_fence_after();
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (n0 + c0 >= p.N) break;
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + acc * BN + (uint32_t)c0, v);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) buf[lane * EPI_LD + c] = __uint_as_float(v[c]);
+                __syncwarp();
+                const int col = n0 + c0 + 4 * (lane % 8);
+                const bool col_ok = col < p.N;  // N % 4 == 0 is required by the host wrapper
+                float4 bv = make_float4(0, 0, 0, 0);
+                if (bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+                float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int r8 = 0; r8 < 8; ++r8) {
+                    const int r = 4 * r8 + lane / 8;
+                    float o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o[j] = buf[r * EPI_LD + 4 * (lane % 8) + j];
+                    if (row_ok[r8] && col_ok) {
+                        if (stats) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { s1[j] += o[j]; s2[j] += o[j] * o[j]; }
+                        }
+                        o[0] = act_fwd(o[0] + bv.x, p.act); o[1] = act_fwd(o[1] + bv.y, p.act);
+                        o[2] = act_fwd(o[2] + bv.z, p.act); o[3] = act_fwd(o[3] + bv.w, p.act);
+                        *reinterpret_cast<float4*>(y + row_off[r8] + col) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+                if (stats) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8); s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
+                        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+                    }
+                    if (lane < 8 && col_ok) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            atomicAdd(stats + col + j, (double)s1[j]);
+                            atomicAdd(stats + p.N + col + j, (double)s2[j]);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            // every tcgen05.ld of this warp has completed (tmem_ld32 waits): hand the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.tempty[acc]);
+        }
+    } else if (X3) {
+        const int ct = threadIdx.x - 192;  // 0..127
+        uint32_t g = 0;
+        for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
+            for (int kb = 0; kb < num_k; ++kb, ++g) {
+                const int s = g % STAGES, ph = (g / STAGES) & 1;
+                mbar_wait(&sm.full[s], ph);
+                const uint32_t a_base = smem_u32(sm.a[s]), l_base = smem_u32(sm.alo[s]);
+#pragma unroll
+                for (int i = 0; i < BM * BK / 4 / 128; ++i) {
+                    const uint32_t off = (uint32_t)(ct + i * 128) * 16u;
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a_base + off) : "memory");
+                    float4 hi, lo;
+                    hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+                    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+                    if (p.dbg == 1) { lo = v; hi = make_float4(0.f, 0.f, 0.f, 0.f); }       // everything through alo
+                    if (p.dbg == 3) { lo = make_float4(0.f, 0.f, 0.f, 0.f); hi = make_float4(0.f, 0.f, 0.f, 0.f); }
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + off), "f"(hi.x), "f"(hi.y),
+                                 "f"(hi.z), "f"(hi.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(l_base + off), "f"(lo.x), "f"(lo.y),
+                                 "f"(lo.z), "f"(lo.w) : "memory");
+                }
+                fence_proxy_async();
+                mbar_arrive(&sm.conv[s]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------- wgrad
@@ -566,6 +780,34 @@ int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& 
     return 0;
 }
 
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BN, int X3, int STAGES>
+int launch_persist(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mwlo, float* y, const float* bias,
+                   double* stats, const FwdParams& p, int B, cudaStream_t st) {
+    static bool configured = false;
+    const int smem = (int)sizeof(PersistSmem<BN, X3, STAGES>) + 1024;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_fwd_persist<BN, X3, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { dfine_set_error("tc_fwd_persist: smem attribute (%d B): %s", smem, cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    TileSched ts;
+    ts.n_tiles = ceil_div(p.N, BN);
+    ts.total = B * p.tiles_w * p.tiles_h * ts.n_tiles;
+    const int grid = ts.total < sm_count() ? ts.total : sm_count();
+    tc_fwd_persist<BN, X3, STAGES><<<grid, fwd_threads(X3), smem, st>>>(mx, mw, mwlo, y, bias, stats, p, ts);
+    return 0;
+}
+
 template <int BN>
 int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, float* dwr, WgradParams p, cudaStream_t st) {
     static bool configured = false;
@@ -628,6 +870,8 @@ DFINE_API int dfine_conv_tc(const float* x, const float* w, const float* w_lo, c
         p.dw[t] = t < n_taps ? taps[3 * t + 1] : 0;
         p.wk[t] = t < n_taps ? taps[3 * t + 2] : 0;
     }
+    static const int dbg = [] { const char* e = getenv("DFINE_TC_DBG"); return e ? atoi(e) : 0; }();
+    p.dbg = dbg;
     p.in_stride = in_stride; p.Cin = Cin;
     p.OH = OH; p.OW = OW; p.N = Cout; p.ldy = ldy; p.act = act;
     p.YH = YH; p.YW = YW; p.osy = osy; p.osx = osx; p.ooy = ooy; p.oox = oox;
@@ -637,7 +881,10 @@ DFINE_API int dfine_conv_tc(const float* x, const float* w, const float* w_lo, c
     CUtensorMap mx, mw, mwlo;
     int rc = make_map4(&mx, x, Cin, W, H, B, ldx, BK, p.TW, p.TH, in_stride, "conv_tc(x)");
     if (rc) return rc;
-    const int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
+    static const bool persist_bn = [] { const char* e = getenv("DFINE_TC_PERSIST"); return !(e && e[0] == '0'); }();
+    // N tile: one tile covers Cout when it can (the A patch is then read exactly once); 256-wide tiles only on
+    // the persistent plain-tf32 kernel (its smem ring has room for 48 KB stages)
+    const int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : ((Cout <= 128 || w_lo || !persist_bn) ? 128 : 256));
     rc = make_map2(&mw, w, ldw, Cout, ldw, BK, bn, "conv_tc(w)");
     if (rc) return rc;
     mwlo = mw;
@@ -646,7 +893,19 @@ DFINE_API int dfine_conv_tc(const float* x, const float* w, const float* w_lo, c
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (w_lo) {
+    static const bool persist = [] { const char* e = getenv("DFINE_TC_PERSIST"); return !(e && e[0] == '0'); }();
+    if (persist) {
+        if (w_lo) {
+            rc = bn == 32 ? launch_persist<32, 1, 4>(mx, mw, mwlo, y, bias, stats, p, B, st)
+               : bn == 64 ? launch_persist<64, 1, 4>(mx, mw, mwlo, y, bias, stats, p, B, st)
+                          : launch_persist<128, 1, 3>(mx, mw, mwlo, y, bias, stats, p, B, st);
+        } else {
+            rc = bn == 32  ? launch_persist<32, 0, 8>(mx, mw, mwlo, y, bias, stats, p, B, st)
+               : bn == 64  ? launch_persist<64, 0, 8>(mx, mw, mwlo, y, bias, stats, p, B, st)
+               : bn == 128 ? launch_persist<128, 0, 6>(mx, mw, mwlo, y, bias, stats, p, B, st)
+                           : launch_persist<256, 0, 4>(mx, mw, mwlo, y, bias, stats, p, B, st);
+        }
+    } else if (w_lo) {
         rc = bn == 32 ? launch_fwd<32, 1, 2>(mx, mw, mwlo, y, bias, stats, p, B, st)
            : bn == 64 ? launch_fwd<64, 1, 2>(mx, mw, mwlo, y, bias, stats, p, B, st)
                       : launch_fwd<128, 1, 3>(mx, mw, mwlo, y, bias, stats, p, B, st);

@@ -93,7 +93,7 @@ def test_train_step_matches_reference_fixture(cuda_ops, mode, tol):
         err = (g - g_ref).double().norm() / g_ref.double().norm()
         # plain tf32 ("tc") through the whole backward chain of the ill-conditioned seeded network: the stem
         # gradients sit behind ~60 tf32 layers and ReLU kinks; the parity modes keep the tight bars
-        lim = (0.5 if mode == "tc" else 0.1) if k.startswith("backbone") else 0.05
+        lim = 0.5 if mode == "tc" else (0.1 if k.startswith("backbone") else 0.05)
         assert err < lim, (mode, k, float(err))
     check_close("running_mean", model.state_dict()["backbone.stem.stem1.bn.running_mean"].cpu(),
                 fix["running_mean_stem1"], 1e-4)
