@@ -39,6 +39,23 @@ def paired_iou_union(a, b):
     return inter / union, union
 
 
+def _iou_nd(a, b):
+    """paired_iou_union for [..., 4] xyxy tensors (broadcasting)."""
+    area_a = (a[..., 2] - a[..., 0]) * (a[..., 3] - a[..., 1])
+    area_b = (b[..., 2] - b[..., 0]) * (b[..., 3] - b[..., 1])
+    wh = (torch.min(a[..., 2:], b[..., 2:]) - torch.max(a[..., :2], b[..., :2])).clamp(min=0)
+    inter = wh[..., 0] * wh[..., 1]
+    union = area_a + area_b - inter
+    return inter / union, union
+
+
+def _giou_nd(a, b):
+    iou, union = _iou_nd(a, b)
+    wh = (torch.max(a[..., 2:], b[..., 2:]) - torch.min(a[..., :2], b[..., :2])).clamp(min=0)
+    area = wh[..., 0] * wh[..., 1]
+    return iou - (area - union) / area
+
+
 def paired_giou(a, b):
     iou, union = paired_iou_union(a, b)
     wh = (torch.max(a[:, 2:], b[:, 2:]) - torch.min(a[:, :2], b[:, :2])).clamp(min=0)
@@ -171,6 +188,7 @@ class DFINECriterion(nn.Module):
             raise NotImplementedError("boxes_weight_format is None in every shipped config")
         self.boxes_weight_format, self.share_matched_indices = boxes_weight_format, share_matched_indices
         self.alpha, self.gamma, self.reg_max, self.label_smoothing = alpha, gamma, reg_max, label_smoothing
+        self.batched = True           # evaluate each loss family once over all heads (False: head by head)
         self._clear_cache()
 
     def _clear_cache(self):
@@ -350,9 +368,146 @@ class DFINECriterion(nn.Module):
         plan.counts.copy_(torch.clamp(counts / dist_utils.get_world_size(), min=1))
         return plan
 
+    # ---- layer-batched evaluation ---------------------------------------------------------------------------
+    # The reference walks the heads one by one (48 loss terms for D-FINE-m, each 5-30 tiny kernels,
+    # dfine_criterion.py:655-773).  All heads of a group have the same shapes, so each loss family is
+    # evaluated ONCE over a leading "set" axis: group A = main + aux layers + pre + encoder head (300 queries),
+    # group DN = denoising layers + dn_pre.  Values are those of the per-head functions above
+    # (tests/test_oracle_cpu.py compares both paths with the reference's loss dict).
+    def _vfl_sets(self, logits, boxes, sb, sq, st, tg, num_boxes):
+        """logits [S,B,Q,C], boxes [S,B,Q,4]; sb/sq/st int64 [S,n] (or [1,n] shared) -> [S]."""
+        S, B, Q, C = logits.shape
+        n = sb.shape[-1]
+        ks = torch.arange(S, device=logits.device)[:, None].expand(S, n)
+        sb, sq, st = sb.expand(S, n), sq.expand(S, n), st.expand(S, n)
+        tbox, tlabel = tg[1][st], tg[0][st]
+        ious, _ = _iou_nd(cxcywh_to_xyxy(boxes[ks, sb, sq]), cxcywh_to_xyxy(tbox))
+        ious = ious.detach()
+        cls = torch.full((S, B, Q), self.num_classes, dtype=torch.int64, device=logits.device)
+        cls[ks, sb, sq] = tlabel
+        target = F.one_hot(cls, C + 1)[..., :-1]
+        score_o = torch.zeros((S, B, Q), dtype=logits.dtype, device=logits.device)
+        score_o[ks, sb, sq] = ious.to(logits.dtype)
+        target_score = score_o.unsqueeze(-1) * target
+        p = torch.sigmoid(logits).detach()
+        weight = self.alpha * p.pow(self.gamma) * (1 - target) + target_score
+        loss = F.binary_cross_entropy_with_logits(logits, target_score, weight=weight, reduction="none")
+        return loss.mean(2).sum((1, 2)) * Q / num_boxes
+
+    @staticmethod
+    def _box_sets(boxes, G, tg, num_boxes):
+        """boxes [S,B,Q,4]; G: shared index set -> (l1 [S], giou [S])."""
+        src, tbox = boxes[:, G.b, G.q], tg[1][G.t]
+        l1 = (src - tbox).abs().sum(-1)
+        gi = 1 - _giou_nd(cxcywh_to_xyxy(src), cxcywh_to_xyxy(tbox))
+        if G.v is not None:
+            l1, gi = l1 * G.v, gi * G.v
+        return l1.sum(1) / num_boxes, gi.sum(1) / num_boxes
+
+    def _local_sets(self, corners, boxes, refs0, teacher_logits, G, tg, num_boxes, up, reg_scale, is_dn, T=5):
+        """corners [L,B,Q,4*nb] ordered by decoder layer (teacher = last), boxes [L,B,Q,4] -> (fgl [L], ddf [L-1])."""
+        nb = self.reg_max + 1
+        L, B, Q, _ = corners.shape
+        gt_xyxy = cxcywh_to_xyxy(tg[1][G.t])
+        with torch.no_grad():
+            t_idx, w_r, w_l = fdr_bin_targets(refs0[G.b, G.q].detach(), gt_xyxy, self.reg_max, reg_scale, up)
+        ious, _ = _iou_nd(cxcywh_to_xyxy(boxes[:, G.b, G.q]), gt_xyxy)          # [L, n]
+        ious = ious.detach()
+        ious_w = ious * G.v if G.v is not None else ious
+        w_t = ious_w.unsqueeze(-1).expand(L, G.n, 4).reshape(L, -1)
+        lsm = F.log_softmax(corners[:, G.b, G.q].reshape(L, -1, nb), dim=-1)
+        left = t_idx.long()[None, :, None].expand(L, -1, 1)
+        ce_l = -lsm.gather(-1, left).squeeze(-1)
+        ce_r = -lsm.gather(-1, left + 1).squeeze(-1)
+        fgl = ((ce_l * w_l + ce_r * w_r) * w_t.float()).sum(1) / num_boxes
+        if L < 2:
+            return fgl, fgl.new_zeros(0)
+        pred_all = corners[:-1].reshape(L - 1, -1, nb)
+        teacher = corners[-1].reshape(-1, nb)
+        identical = (pred_all == teacher).all(-1).all(-1)             # torch.equal per layer, no host sync (197)
+        w_max = teacher_logits.sigmoid().max(dim=-1)[0].detach()      # [B,Q]
+        matched = torch.zeros((B, Q + 1), dtype=torch.bool, device=w_max.device)
+        matched[G.b, G.qs] = torch.ones(G.n, dtype=torch.bool, device=w_max.device)
+        w_loc = torch.cat([w_max, w_max.new_zeros(B, 1)], 1)[None].repeat(L - 1, 1, 1)
+        ks = torch.arange(L - 1, device=w_max.device)[:, None].expand(L - 1, G.n)
+        w_loc[ks, G.b.expand(L - 1, -1), G.qs.expand(L - 1, -1)] = ious[:-1].to(w_loc.dtype)
+        matched, w_loc = matched[:, :Q], w_loc[:, :, :Q]
+        m4 = matched.unsqueeze(-1).expand(B, Q, 4).reshape(-1)
+        w4 = w_loc.unsqueeze(-1).expand(L - 1, B, Q, 4).reshape(L - 1, -1)
+        kl = F.kl_div(F.log_softmax(pred_all / T, dim=-1), F.softmax(teacher.detach() / T, dim=-1)[None],
+                      reduction="none").sum(-1)
+        per = w4 * (T ** 2) * kl
+        n_pos, n_neg = m4.sum(), (~m4).sum()
+        if not is_dn:
+            scale = 8 / B
+            self.num_pos, self.num_neg = (n_pos * scale) ** 0.5, (n_neg * scale) ** 0.5
+        zero = per.new_zeros(())
+        l_pos = torch.where(n_pos > 0, (per * m4).sum(1) / n_pos.clamp(min=1), zero)
+        l_neg = torch.where(n_neg > 0, (per * (~m4)).sum(1) / n_neg.clamp(min=1), zero)
+        ddf = (l_pos * self.num_pos + l_neg * self.num_neg) / (self.num_pos + self.num_neg)
+        return fgl, torch.where(identical, torch.zeros_like(ddf), ddf)
+
+    def _compute_batched(self, outputs, tg, table, counts, plan):
+        st_ = outputs["_stacked"]
+        logits, boxes, corners, refs = st_["logits"], st_["boxes"], st_["corners"], st_["refs"]
+        L = logits.shape[0]
+        pre, enc = outputs["pre_outputs"], outputs["enc_aux_outputs"]
+        assert len(enc) == 1 and plan.n_sets == L + 2
+        Q, n = plan.Q, plan.n_layer
+        nb_go, nb = counts[0], counts[1]
+        W = self.weight_dict
+        up, reg_scale = outputs["up"], outputs["reg_scale"]
+        # plan order of the matched sets: main (= last layer), aux_0..aux_{L-2}, pre, enc
+        order = torch.cat([logits[L - 1:], logits[:L - 1], pre["pred_logits"][None], enc[0]["pred_logits"][None]])
+        order_b = torch.cat([boxes[L - 1:], boxes[:L - 1], pre["pred_boxes"][None], enc[0]["pred_boxes"][None]])
+        S = L + 2
+        idx = table[:, :S * n].reshape(4, S, n)
+        vfl = self._vfl_sets(order, order_b, idx[0], idx[1], idx[2], tg, nb)
+        s_go = _Set(table, *plan.set_slice("go"), Q, True)
+        l1, gi = self._box_sets(order_b, s_go, tg, nb_go)
+        fgl, ddf = self._local_sets(corners, boxes, refs[L - 1], logits[L - 1], s_go, tg, nb_go, up, reg_scale, False)
+        vfl, l1, gi, fgl, ddf = (torch.nan_to_num(v, nan=0.0) for v in (vfl, l1, gi, fgl, ddf))
+        losses = {}
+
+        def put(suffix, k, lay=None, with_ddf=False):
+            losses["loss_vfl" + suffix] = vfl_[k] * W["loss_vfl"]
+            losses["loss_bbox" + suffix] = l1_[k] * W["loss_bbox"]
+            losses["loss_giou" + suffix] = gi_[k] * W["loss_giou"]
+            if lay is not None:
+                losses["loss_fgl" + suffix] = fgl_[lay] * W["loss_fgl"]
+                if with_ddf:
+                    losses["loss_ddf" + suffix] = ddf_[lay] * W["loss_ddf"] if lay < ddf_.shape[0] else ddf_.sum() * 0
+
+        vfl_, l1_, gi_, fgl_, ddf_ = vfl, l1, gi, fgl, ddf
+        put("", 0, L - 1)
+        for i in range(L - 1):
+            put(f"_aux_{i}", 1 + i, i, True)
+        put("_pre", L)
+        put("_enc_0", L + 1)
+        if "dn_outputs" in outputs:
+            meta = outputs["dn_meta"]
+            dl, db_, dc, dr = st_["dn_logits"], st_["dn_boxes"], st_["dn_corners"], st_["dn_refs"]
+            dpre = outputs["dn_pre_outputs"]
+            s_dn = _Set(table, *plan.set_slice("dn"), Q, False)
+            dn_num = nb * meta["dn_num_group"]
+            dlog = torch.cat([dl, dpre["pred_logits"][None]])
+            dbox = torch.cat([db_, dpre["pred_boxes"][None]])
+            vfl_ = self._vfl_sets(dlog, dbox, s_dn.b[None], s_dn.q[None], s_dn.t[None], tg, dn_num)
+            l1_, gi_ = self._box_sets(dbox, s_dn, tg, dn_num)
+            fgl_, ddf_ = self._local_sets(dc, db_, dr[0], dl[L - 1], s_dn, tg, dn_num, up, reg_scale, True)
+            vfl_, l1_, gi_, fgl_, ddf_ = (torch.nan_to_num(v, nan=0.0) for v in (vfl_, l1_, gi_, fgl_, ddf_))
+            n_dn_layers = len(outputs["dn_outputs"])
+            for i in range(n_dn_layers):
+                put(f"_dn_{i}", i, i, True)
+            put("_dn_pre", L)
+        return losses
+
     def compute(self, outputs, tg, table, counts, plan):
         """Stage 3 (device): every loss term from the fixed-shape index table (dfine_criterion.py:655-777)."""
         self._clear_cache()
+        if (self.batched and "_stacked" in outputs and list(self.losses) == ["vfl", "boxes", "local"]
+                and "pred_masks" not in outputs and len(outputs["enc_aux_outputs"]) == 1):
+            return self._compute_batched(outputs, tg, table, counts, plan)
         main, aux, pre, enc = self._matched_layers(outputs)
         Q = plan.Q
         nb_go, nb = counts[0], counts[1]

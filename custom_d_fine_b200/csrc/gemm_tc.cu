@@ -706,11 +706,24 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
+// Element type of the tensor maps.  FLOAT32 is a plain copy (the tensor core then truncates the low 13
+// mantissa bits); TFLOAT32 makes the TMA unit round to nearest tf32 while copying, which measured ~16 B/clk per
+// SM (one 128-byte row per ~8.5 cycles) on B200 and throttled every GEMM of the network (profiles/README.md).
+// DFINE_TMA_TF32=1 restores the rounding maps for A/B measurements.
+CUtensorMapDataType map_dtype() {
+    static const CUtensorMapDataType t = [] {
+        const char* e = getenv("DFINE_TMA_TF32");
+        return (e && e[0] == '1') ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    }();
+    return t;
+}
+
 // 4-D fp32 tensor map (C, W, H, B) over an NHWC activation with pixel stride ld (elements), zero OOB fill.
 // The box covers box_w x box_h pixels sampled every `estride` pixels (strided convolutions read their
 // input through the map's element strides; there is no im2col buffer).
 int make_map4(CUtensorMap* m, const float* base, long C, long W, long H, long B, long ld, int box_c, int box_w,
-              int box_h, int estride, const char* who, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+              int box_h, int estride, const char* who, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B,
+              CUtensorMapDataType dtype = map_dtype()) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { dfine_set_error("%s: cuTensorMapEncodeTiled unavailable", who); return -2; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -718,7 +731,7 @@ int make_map4(CUtensorMap* m, const float* base, long C, long W, long H, long B,
     cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * estride), (cuuint32_t)(box_h * estride), 1};
     cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
     if (box[1] > 256 || box[2] > 256) { dfine_set_error("%s: TMA box %u x %u exceeds 256", who, box[1], box[2]); return -1; }
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, (void*)base, dims, strides, box, es,
+    CUresult r = enc(m, dtype, 4, (void*)base, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -736,7 +749,7 @@ int make_map2(CUtensorMap* m, const float* base, long inner, long rows, long ld,
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
     cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void*)base, dims, strides, box, es,
+    CUresult r = enc(m, map_dtype(), 2, (void*)base, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -879,7 +892,10 @@ DFINE_API int dfine_conv_tc(const float* x, const float* w, const float* w_lo, c
     p.tiles_w = ceil_div(OW, p.TW);
     p.tiles_h = ceil_div(OH, p.TH);
     CUtensorMap mx, mw, mwlo;
-    int rc = make_map4(&mx, x, Cin, W, H, B, ldx, BK, p.TW, p.TH, in_stride, "conv_tc(x)");
+    // TFLOAT32 maps make the TMA unit round fp32 -> tf32 (nearest) while it copies: right for the plain path,
+    // but the 3xTF32 converter needs the untouched fp32 activations to form a_lo = a - tf32(a)
+    int rc = make_map4(&mx, x, Cin, W, H, B, ldx, BK, p.TW, p.TH, in_stride, "conv_tc(x)", CU_TENSOR_MAP_SWIZZLE_128B,
+                       w_lo ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : map_dtype());
     if (rc) return rc;
     static const bool persist_bn = [] { const char* e = getenv("DFINE_TC_PERSIST"); return !(e && e[0] == '0'); }();
     // N tile: one tile covers Cout when it can (the A patch is then read exactly once); 256-wide tiles only on

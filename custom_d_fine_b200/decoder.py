@@ -436,6 +436,10 @@ class DFINETransformer(nn.Module):
                "ref_points": refs[-1], "up": self.up, "reg_scale": self.reg_scale}
         if want_masks:
             out["pred_masks"] = pred_masks
+        # layer-stacked views of the same tensors: the criterion evaluates every loss family once over all layers
+        out["_stacked"] = {"logits": logits, "boxes": boxes, "corners": corners, "refs": refs}
+        if split_dn:
+            out["_stacked"].update(dn_logits=dn_logits, dn_boxes=dn_boxes, dn_corners=dn_corners, dn_refs=dn_refs)
         if self.aux_loss:
             out["aux_outputs"] = _layer_dicts(logits[:-1], boxes[:-1], corners[:-1], refs[:-1],
                                               corners[-1], logits[-1], aux_masks if want_masks else None)
