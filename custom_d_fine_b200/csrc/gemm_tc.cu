@@ -169,6 +169,10 @@ struct FwdParams {
     long ldy;                 // output pixel stride (elements)
     int act;
     int dbg;                  // bring-up switch for the 3xTF32 converter (0 = normal)
+    const float* x;           // input tensor geometry again, for the L2 prefetch warp
+    int B, H, W;
+    long ldx;
+    int prefetch;             // k-blocks the prefetch warp may run ahead of the TMA producer (0 = off)
 };
 
 // X3 = 0: one kind::tf32 MMA per k-step (operands truncated to tf32 by the tensor core).
@@ -187,7 +191,7 @@ struct FwdSmem {
     uint32_t tmem_base;
 };
 
-constexpr int fwd_threads(int x3) { return x3 ? 320 : 192; }
+constexpr int fwd_threads(int x3) { return x3 ? 352 : 224; }   // + one L2-prefetch warp (persistent kernel)
 
 template <int BN, int X3, int STAGES>
 __global__ void __launch_bounds__(fwd_threads(X3)) tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x,
@@ -327,7 +331,7 @@ __global__ void __launch_bounds__(fwd_threads(X3)) tc_fwd_kernel(const __grid_co
             }
             __syncwarp();
         }
-    } else if (X3) {
+    } else if (X3 && warp < 10) {
         // converter warps 6..9: split the landed activation tile into tf32 hi (in place) and lo parts.
         // Explicit ld.shared / st.shared (not generic accesses through the shared window) so that
         // fence.proxy.async.shared::cta orders exactly these writes before the tensor core's async-proxy reads;
@@ -378,6 +382,7 @@ struct PersistSmem {
     float epi[4][32 * EPI_LD];
     uint64_t full[STAGES], empty[STAGES], conv[STAGES], tfull[2], tempty[2];
     uint32_t tmem_base;
+    volatile uint32_t produced;   // k-blocks whose TMA loads have been issued (progress hint for the prefetch warp)
 };
 
 struct TileSched {
@@ -404,6 +409,7 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); mbar_init(&sm.conv[s], 128); }
             for (int a = 0; a < 2; ++a) { mbar_init(&sm.tfull[a], 1); mbar_init(&sm.tempty[a], 4); }
+            sm.produced = 0;
             fence_barrier_init();
         }
         __syncwarp();
@@ -430,8 +436,10 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                                 h0 * p.in_stride + p.dh[tap], img);
                     tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
                     if (X3) tma_load_2d(sm.blo[s], &map_wlo, &sm.full[s], p.wk[tap] + c0, n0);
+                    sm.produced = g + 1;
                 }
             }
+            sm.produced = 0x7fffffffu;
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -538,7 +546,47 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.tempty[acc]);
         }
-    } else if (X3) {
+    } else if (warp == (X3 ? 10 : 6)) {
+        // L2 prefetch warp.  TMA keeps only ~32 KB of 128-byte row requests in flight per SM (measured:
+        // ~28 GB/s per SM when the activation tile streams from HBM, profiles/README.md), which cannot cover
+        // HBM latency.  This warp walks the producer's (tile, k-block) sequence a bounded distance AHEAD of
+        // it and issues fire-and-forget prefetch.global.L2 for every 128-byte row of the coming activation
+        // boxes, so the TMA loads hit L2.  Purely a hint: no barrier, no effect on results.
+        if (p.prefetch > 0) {
+            const uint32_t my_tiles = (uint32_t)((ts.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+            const uint32_t total_k = my_tiles * (uint32_t)num_k;
+            const uint32_t dmin = STAGES, dmax = STAGES + (uint32_t)p.prefetch;
+            uint32_t gp = 0;
+            while (gp < total_k) {
+                const uint32_t done = sm.produced;
+                if (done >= total_k) break;
+                if (gp < done + dmin) gp = done + dmin;          // already being fetched by TMA: skip ahead
+                if (gp >= total_k) break;
+                if (gp > done + dmax) { __nanosleep(200); continue; }
+                const int t = (int)blockIdx.x + (int)(gp / (uint32_t)num_k) * (int)gridDim.x;
+                const int kb = (int)(gp % (uint32_t)num_k);
+                const int mt = t / ts.n_tiles;
+                const int img = mt / tiles_per_img, tt = mt % tiles_per_img;
+                const int h0 = (tt / p.tiles_w) * p.TH, w0 = (tt % p.tiles_w) * p.TW;
+                const int tap = kb / cblocks, c0 = (kb % cblocks) * BK;
+                // N tiles of one pixel patch re-read the same A boxes: prefetch for the first of them only
+                if (t % ts.n_tiles == 0 && img < p.B) {
+#pragma unroll
+                    for (int rr = 0; rr < BM / 32; ++rr) {
+                        const int r = lane + 32 * rr;
+                        const int th = r / p.TW, tw = r % p.TW;
+                        const int ih = (h0 + th) * p.in_stride + p.dh[tap], iw = (w0 + tw) * p.in_stride + p.dw[tap];
+                        if (th < p.TH && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
+                            const float* a = p.x + (((long)img * p.H + ih) * p.W + iw) * p.ldx + c0;
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                            if (((uintptr_t)a & 127) != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 31));
+                        }
+                    }
+                }
+                ++gp;
+            }
+        }
+    } else if (X3 && warp < 10) {
         const int ct = threadIdx.x - 192;  // 0..127
         uint32_t g = 0;
         for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
@@ -885,6 +933,8 @@ DFINE_API int dfine_conv_tc(const float* x, const float* w, const float* w_lo, c
     }
     static const int dbg = [] { const char* e = getenv("DFINE_TC_DBG"); return e ? atoi(e) : 0; }();
     p.dbg = dbg;
+    static const int pf = [] { const char* e = getenv("DFINE_TC_PREFETCH"); return e ? atoi(e) : 16; }();
+    p.prefetch = pf; p.x = x; p.B = B; p.H = H; p.W = W; p.ldx = ldx;
     p.in_stride = in_stride; p.Cin = Cin;
     p.OH = OH; p.OW = OW; p.N = Cout; p.ldy = ldy; p.act = act;
     p.YH = YH; p.YW = YW; p.osy = osy; p.osx = osx; p.ooy = ooy; p.oox = oox;

@@ -172,9 +172,12 @@ def _taps(key, make):
 def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, YH, YW, os_, oo, in_stride, taps, act,
                stats, what):
     arr, n = taps
-    _check(lib().dfine_conv_tc(_p(x), _p(w), _p(w_lo), _p(bias), _p(y), _p(stats), B, H, W, Cin, c_long(ldx), OH, OW,
-                               Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0], oo[1], in_stride, n, arr,
-                               c_long(ldw), act, _stream()), what)
+    # algorithmic bytes: input pixels + output pixels + weights, each touched once, fp32
+    nbytes = 4 * (B * min(H * W, OH * OW * in_stride * in_stride) * Cin + B * OH * OW * Cout + Cout * n * Cin)
+    with _timed("conv_tc", nbytes):
+        _check(lib().dfine_conv_tc(_p(x), _p(w), _p(w_lo), _p(bias), _p(y), _p(stats), B, H, W, Cin, c_long(ldx), OH,
+                                   OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0], oo[1], in_stride, n, arr,
+                                   c_long(ldw), act, _stream()), what)
 
 
 def _split_tf32(w2d):
@@ -261,8 +264,10 @@ def _conv_wgrad(dy, ldy, x, ldx, geom, dst=None):
     B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
     dwr = dst if dst is not None else torch.zeros((Cout, k, k, Cin), device=dy.device, dtype=torch.float32)
     if _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy):
-        _check(lib().dfine_conv_wgrad_tc(_p(dy), _p(x), _p(dwr), B, H, W, Cin, OH, OW, Cout, k, k, stride, pad[0],
-                                         pad[1], c_long(ldx), c_long(ldy), _stream()), "conv_wgrad_tc")
+        nbytes = 4 * (B * H * W * Cin + B * OH * OW * Cout + 2 * Cout * k * k * Cin)
+        with _timed("conv_wgrad_tc", nbytes):
+            _check(lib().dfine_conv_wgrad_tc(_p(dy), _p(x), _p(dwr), B, H, W, Cin, OH, OW, Cout, k, k, stride, pad[0],
+                                             pad[1], c_long(ldx), c_long(ldy), _stream()), "conv_wgrad_tc")
     else:
         _check(lib().dfine_conv_wgrad_simt(_p(dy), _p(x), _p(dwr), B, H, W, Cin, OH, OW, Cout, k, k, stride, pad[0],
                                            pad[1], c_long(ldx), c_long(ldy), _stream()), "conv_wgrad_simt")

@@ -1,9 +1,10 @@
 """GPU parity tests: every kernel-table op of the CUDA path against the CPU oracle (oracle/torch_ops.py)
 on the same seeded inputs, called through the C ABI (ctypes) exactly as the model calls them.
 
-Tolerances: fp32 CUDA-core kernels 2e-5 relative to the tensor's max magnitude; tcgen05 kind::tf32
-kernels 2e-3 (10-bit mantissa operands, fp32 accumulation) — the same operand precision cuDNN uses
-for the reference's convolutions on GPU (torch.backends.cudnn.allow_tf32 defaults to True).
+Tolerances: fp32 CUDA-core kernels 3e-5 relative to the tensor's max magnitude; tcgen05 kernels 3e-3: in the
+default "tc3" mode the forward GEMM is 3xTF32 (measured 3e-7..8e-6, profiles/README.md) but data / weight
+gradients use plain kind::tf32 operands (10-bit mantissa, fp32 accumulation) — the operand precision cuDNN
+uses for the reference's convolutions on GPU (torch.backends.cudnn.allow_tf32 defaults to True).
 """
 import math
 
@@ -78,8 +79,8 @@ def _conv_case(cuda_ops, oracle_ops, B, H, W, Cin, Cout, k, stride, pad, groups,
 CONV_CASES = [
     # name, B,H,W,Cin,Cout,k,stride,pad,groups,act,lab,pre,post,training,tol
     ("stem1_3x3s2", 2, 64, 64, 3, 24, 3, 2, (1, 1, 1, 1), 1, "relu", True, False, False, True, F32),
-    ("stem2a_2x2_padbr", 2, 32, 32, 24, 12, 2, 1, (0, 0, 1, 1), 1, "relu", True, False, False, True, F32),
-    ("stem3_3x3s2", 2, 32, 32, 48, 24, 3, 2, (1, 1, 1, 1), 1, "relu", True, False, False, True, F32),
+    ("stem2a_2x2_padbr", 2, 32, 32, 24, 12, 2, 1, (0, 0, 1, 1), 1, "relu", True, False, False, True, TF32),
+    ("stem3_3x3s2", 2, 32, 32, 48, 24, 3, 2, (1, 1, 1, 1), 1, "relu", True, False, False, True, TF32),
     ("dw3x3s2", 2, 40, 40, 96, 96, 3, 2, (1, 1, 1, 1), 96, None, False, False, False, True, F32),
     ("dw5x5", 2, 20, 20, 128, 128, 5, 1, (2, 2, 2, 2), 128, "relu", True, False, False, True, F32),
     ("pw1x1_tc", 2, 40, 40, 160, 48, 1, 1, (0, 0, 0, 0), 1, "relu", True, False, False, True, TF32),
@@ -107,11 +108,11 @@ LINEAR_CASES = [
     ("ffn_relu", (3, 50, 256), 1024, "relu", TF32),
     ("ffn_gelu", (3, 50, 256), 1024, "gelu", TF32),
     ("score_head", (2, 37, 256), 80, None, TF32),
-    ("bbox_head_4", (2, 37, 256), 4, None, F32),
+    ("bbox_head_4", (2, 37, 256), 4, None, TF32),
     ("corners_132", (2, 37, 256), 132, None, TF32),
     ("lqe_out_1", (2, 37, 64), 1, None, F32),
     ("lqe_in_20", (2, 37, 20), 64, "relu", TF32),
-    ("qpos_4", (2, 37, 4), 512, "relu", F32),
+    ("qpos_4", (2, 37, 4), 512, "relu", TF32),
     ("big", (1, 8400, 256), 256, None, TF32),
 ]
 
