@@ -9,6 +9,7 @@
 //   q/k/v/o rows are addressed as  base + (b*S + s)*ld + h*HD  (strided views of the packed
 //   in-projection output are consumed in place).  mask: uint8 [S,S], non-zero = blocked, or null.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -278,7 +279,20 @@ int set_smem(const void* fn) {
         default: dfine_set_error("attention: head_dim %d unsupported (16|32|48|64)", HD_); return -1; \
     }
 
+bool use_mma() {
+    static const bool on = [] { const char* e = getenv("DFINE_ATTN"); return !(e && e[0] == 's'); }();   // "simt" = CUDA cores
+    return on;
+}
+
 }  // namespace
+
+// tensor-core (mma.sync, 3xTF32) kernels of attention_mma.cu
+int attn_mma_fwd(const float* q, long ldq, const float* k, long ldk, const float* v, long ldv, const unsigned char* mask,
+                 float* o, long ldo, float* lse, int B, int S, int H, int head_dim, float scale, cudaStream_t st);
+int attn_mma_bwd(const float* q, long ldq, const float* k, long ldk, const float* v, long ldv, const unsigned char* mask,
+                 const float* o, long ldo, const float* dout, long ldd, const float* lse, float* dsum, float* dq, long lddq,
+                 float* dk, long lddk, float* dv, long lddv, int B, int S, int H, int head_dim, float scale,
+                 cudaStream_t st);
 
 // o [B,S,*] (row stride ldo), lse [B,H,S].  scale = 1/sqrt(head_dim).  All row strides in elements,
 // multiples of 4; base pointers 16-byte aligned.
@@ -286,7 +300,14 @@ DFINE_API int dfine_attn_fwd(const float* q, long ldq, const float* k, long ldk,
                              const unsigned char* mask, float* o, long ldo, float* lse, int B, int S, int H,
                              int head_dim, float scale, void* stream) {
     if (B * S * H == 0) return 0;
-    DFINE_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "attn_fwd: row strides must be multiples of 4");
+    DFINE_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 2 == 0,
+                  "attn_fwd: row strides must be multiples of 4");
+    if (use_mma() && (head_dim == 16 || head_dim == 32 || head_dim == 48 || head_dim == 64)) {
+        int rc = attn_mma_fwd(q, ldq, k, ldk, v, ldv, mask, o, ldo, lse, B, S, H, head_dim, scale, (cudaStream_t)stream);
+        if (rc) return rc;
+        DFINE_LAUNCH_CHECK("attn_fwd(mma)");
+        return 0;
+    }
     dim3 grid(ceil_div(S, ROWS), H, B);
     ATTN_DISPATCH(head_dim, {
         int rc = set_smem<HD, 0>((const void*)attn_fwd_kernel<HD>);
@@ -306,6 +327,14 @@ DFINE_API int dfine_attn_bwd(const float* q, long ldq, const float* k, long ldk,
     if (B * S * H == 0) return 0;
     DFINE_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldd % 4 == 0,
                   "attn_bwd: row strides must be multiples of 4");
+    if (use_mma() && (head_dim == 16 || head_dim == 32 || head_dim == 48 || head_dim == 64) && lddq % 2 == 0 &&
+        lddk % 2 == 0 && lddv % 2 == 0) {
+        int rc = attn_mma_bwd(q, ldq, k, ldk, v, ldv, mask, o, ldo, dout, ldd, lse, dsum, dq, lddq, dk, lddk, dv, lddv, B, S,
+                              H, head_dim, scale, (cudaStream_t)stream);
+        if (rc) return rc;
+        DFINE_LAUNCH_CHECK("attn_bwd(mma)");
+        return 0;
+    }
     dim3 grid(ceil_div(S, ROWS), H, B);
     ATTN_DISPATCH(head_dim, {
         int rc = set_smem<HD, 1>((const void*)attn_bwd_dq_kernel<HD>);

@@ -380,6 +380,7 @@ struct PersistSmem {
     alignas(1024) float alo[X3 ? STAGES : 1][X3 ? BM * BK : 32];
     alignas(1024) float blo[X3 ? STAGES : 1][X3 ? BN * BK : 32];
     float epi[4][32 * EPI_LD];
+    double stat[2 * BN];          // per-CTA BatchNorm partial sums (sum, sum of squares), flushed once at the end
     uint64_t full[STAGES], empty[STAGES], conv[STAGES], tfull[2], tempty[2];
     uint32_t tmem_base;
     volatile uint32_t produced;   // k-blocks whose TMA loads have been issued (progress hint for the prefetch warp)
@@ -404,6 +405,8 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
     const int num_k = p.n_taps * cblocks;
     constexpr uint32_t TMEM_COLS = 2 * BN;
 
+    if (stats)
+        for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) sm.stat[i] = 0.0;
     if (warp == 0 && lane == 0) { prefetch_tmap(&map_x); prefetch_tmap(&map_w); if (X3) prefetch_tmap(&map_wlo); }
     if (warp == 1) {
         if (lane == 0) {
@@ -531,11 +534,23 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                         s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8); s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
                         s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
                     }
+                    // per-CTA accumulation in shared memory: with one global fp64 atomic per (tile, warp, channel)
+                    // the 10^4-tile stem layers serialised on a few dozen L2 addresses (profiles/README.md)
+                    // (possible when one N tile covers Cout, i.e. every tile of the CTA maps to the same channels;
+                    // wide-Cout layers have few tiles per channel and keep the direct global atomics)
                     if (lane < 8 && col_ok) {
+                        if (ts.n_tiles == 1) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            atomicAdd(stats + col + j, (double)s1[j]);
-                            atomicAdd(stats + p.N + col + j, (double)s2[j]);
+                            for (int j = 0; j < 4; ++j) {
+                                atomicAdd(&sm.stat[c0 + 4 * lane + j], (double)s1[j]);
+                                atomicAdd(&sm.stat[BN + c0 + 4 * lane + j], (double)s2[j]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                atomicAdd(stats + col + j, (double)s1[j]);
+                                atomicAdd(stats + p.N + col + j, (double)s2[j]);
+                            }
                         }
                     }
                 }
@@ -618,6 +633,13 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+    if (stats && ts.n_tiles == 1) {
+        for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
+            const int c = i % BN, which = i / BN;
+            const double v = sm.stat[i];
+            if (c < p.N && v != 0.0) atomicAdd(stats + (long)which * p.N + c, v);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------- wgrad
