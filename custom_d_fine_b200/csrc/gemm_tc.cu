@@ -434,11 +434,22 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                     const int s = g % STAGES, ph = (g / STAGES) & 1;
                     mbar_wait(&sm.empty[s], ph ^ 1);
                     const int tap = kb / cblocks, c0 = (kb % cblocks) * BK;
+                    if (p.dbg == 11) {            // bring-up: no loads (the MMAs run on whatever smem holds)
+                        mbar_arrive(&sm.full[s]);
+                    } else if (p.dbg == 12) {     // bring-up: weights only
+                        mbar_expect_tx(&sm.full[s], (uint32_t)(BN * BK * sizeof(float)));
+                        tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
+                    } else if (p.dbg == 13) {     // bring-up: activations only
+                        mbar_expect_tx(&sm.full[s], (uint32_t)(p.TW * p.TH * BK * sizeof(float)));
+                        tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 * p.in_stride + p.dw[tap],
+                                    h0 * p.in_stride + p.dh[tap], img);
+                    } else {
                     mbar_expect_tx(&sm.full[s], (uint32_t)((p.TW * p.TH + (X3 ? 2 : 1) * BN) * BK * sizeof(float)));
                     tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 * p.in_stride + p.dw[tap],
                                 h0 * p.in_stride + p.dh[tap], img);
                     tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
                     if (X3) tma_load_2d(sm.blo[s], &map_wlo, &sm.full[s], p.wk[tap] + c0, n0);
+                    }
                     sm.produced = g + 1;
                 }
             }
@@ -469,7 +480,7 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                             umma_tf32(d, da + 2 * k, dbl + 2 * k, idesc, 1);
                             umma_tf32(d, da + 2 * k, db + 2 * k, idesc, 1);
                         }
-                    } else {
+                    } else if (p.dbg != 10) {     // dbg 10 = bring-up: loads only, no MMAs
 #pragma unroll
                         for (int k = 0; k < BK / 8; ++k) umma_tf32(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                     }

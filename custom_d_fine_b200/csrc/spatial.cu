@@ -72,40 +72,141 @@ __global__ void __launch_bounds__(NT) dwconv_bwd_data_kernel(const float* __rest
     }
 }
 
+// ---- register-blocked variants: one thread = PX consecutive output pixels along W x 4 channels -------------
+// A K x K depthwise stencil issues K*K activation + K*K weight loads per output in the simple kernels above
+// (LSU-bound: 36 us for the 13 MB 5x5 layers).  Blocking PX = 4 outputs per thread loads each input row
+// segment once ((PX-1)*S + K float4) and every weight once per thread: 16 instead of 50 loads per output.
+constexpr int PX = 4;
+
+template <int K, int S>
+__global__ void __launch_bounds__(NT) dwconv_fwd_blocked(const float* __restrict__ x, const float* __restrict__ w,
+                                                         float* __restrict__ y, int B, int H, int W, int C, int OH,
+                                                         int OW, int pad) {
+    constexpr int SPAN = (PX - 1) * S + K;
+    const int VC = C / 4, WB = (OW + PX - 1) / PX;
+    const long total = (long)B * OH * WB * VC;
+    for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+        const int cv = (int)(i % VC);
+        long p = i / VC;
+        const int ow0 = (int)(p % WB) * PX; p /= WB;
+        const int oh = (int)(p % OH);
+        const int b = (int)(p / OH);
+        float4 acc[PX];
+#pragma unroll
+        for (int q = 0; q < PX; ++q) acc[q] = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int kh = 0; kh < K; ++kh) {
+            const int ih = oh * S + kh - pad;
+            if (ih < 0 || ih >= H) continue;
+            const float* row = x + ((long)b * H + ih) * W * C + cv * 4;
+            float4 xin[SPAN];
+#pragma unroll
+            for (int s = 0; s < SPAN; ++s) {
+                const int iw = ow0 * S + s - pad;
+                xin[s] = (iw >= 0 && iw < W) ? ld4(row + (long)iw * C) : make_float4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int kw = 0; kw < K; ++kw) {
+                const float4 wv = ld4(w + (long)(kh * K + kw) * C + cv * 4);
+#pragma unroll
+                for (int q = 0; q < PX; ++q) fma4(acc[q], xin[q * S + kw], wv);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < PX; ++q)
+            if (ow0 + q < OW) st4(y + ((((long)b * OH + oh) * OW + ow0 + q) * VC + cv) * 4, acc[q]);
+    }
+}
+
+// stride-1 data gradient: dx[ih, iw] = sum_{kh,kw} dy[ih + pad - kh, iw + pad - kw] * w[kh, kw]
+template <int K>
+__global__ void __launch_bounds__(NT) dwconv_bwd_data_blocked(const float* __restrict__ dy, const float* __restrict__ w,
+                                                              float* __restrict__ dx, int B, int H, int W, int C,
+                                                              int OH, int OW, int pad) {
+    constexpr int SPAN = PX - 1 + K;
+    const int VC = C / 4, WB = (W + PX - 1) / PX;
+    const long total = (long)B * H * WB * VC;
+    for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+        const int cv = (int)(i % VC);
+        long p = i / VC;
+        const int iw0 = (int)(p % WB) * PX; p /= WB;
+        const int ih = (int)(p % H);
+        const int b = (int)(p / H);
+        float4 acc[PX];
+#pragma unroll
+        for (int q = 0; q < PX; ++q) acc[q] = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int kh = 0; kh < K; ++kh) {
+            const int oh = ih + pad - kh;
+            if (oh < 0 || oh >= OH) continue;
+            const float* row = dy + ((long)b * OH + oh) * OW * C + cv * 4;
+            float4 g[SPAN];   // g[s] = dy[oh, iw0 + pad - (K-1) + s]
+#pragma unroll
+            for (int s = 0; s < SPAN; ++s) {
+                const int ow = iw0 + pad - (K - 1) + s;
+                g[s] = (ow >= 0 && ow < OW) ? ld4(row + (long)ow * C) : make_float4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int kw = 0; kw < K; ++kw) {
+                const float4 wv = ld4(w + (long)(kh * K + kw) * C + cv * 4);
+#pragma unroll
+                for (int q = 0; q < PX; ++q) fma4(acc[q], g[q + (K - 1 - kw)], wv);   // ow = iw0 + q + pad - kw
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < PX; ++q)
+            if (iw0 + q < W) st4(dx + ((((long)b * H + ih) * W + iw0 + q) * VC + cv) * 4, acc[q]);
+    }
+}
+
 // dw[tap, c] += sum_pixels dy * x_shifted.  CTA = slab of output pixels; lanes tile [pixels, C/4];
 // per-thread register accumulators for all taps (K*K float4), merged through shared atomics.
-template <int K>
+template <int K, int S>
 __global__ void __launch_bounds__(NT) dwconv_bwd_weight_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                float* __restrict__ dw, int B, int H, int W, int C,
-                                                               int OH, int OW, int stride, int pad, long pix_per_cta) {
+                                                               int OH, int OW, int pad, long pix_per_cta) {
+    constexpr int stride = S;
     extern __shared__ float shw[];  // [K*K*C]
     for (int i = threadIdx.x; i < K * K * C; i += NT) shw[i] = 0.f;
     __syncthreads();
     const int VC = C / 4;
     const int LPR = VC < NT ? VC : NT, RPP = NT / LPR;
     const int lane_r = threadIdx.x / LPR, lane_c = threadIdx.x % LPR;
-    const long P = (long)B * OH * OW;
+    const long P = (long)B * OH * ((OW + PX - 1) / PX);      // pixel blocks
     const long p0 = (long)blockIdx.x * pix_per_cta, p1 = p0 + pix_per_cta < P ? p0 + pix_per_cta : P;
     if (lane_r < RPP) {
         for (int cv = lane_c; cv < VC; cv += LPR) {
             float4 acc[K * K];
 #pragma unroll
             for (int t = 0; t < K * K; ++t) acc[t] = make_float4(0, 0, 0, 0);
+            // pixel blocks of PX outputs along W: dy loaded once per block, each input row segment once per kh
+            constexpr int SPANW = (PX - 1) * S + K;
+            const int WB = (OW + PX - 1) / PX;
             for (long p = p0 + lane_r; p < p1; p += RPP) {
-                const int ow = (int)(p % OW);
-                const long q = p / OW;
+                const int ow0 = (int)(p % WB) * PX;
+                const long q = p / WB;
                 const int oh = (int)(q % OH), b = (int)(q / OH);
-                const float4 g = ld4(dy + p * C + cv * 4);
+                float4 g[PX];
+#pragma unroll
+                for (int j = 0; j < PX; ++j)
+                    g[j] = (ow0 + j < OW) ? ld4(dy + ((((long)b * OH + oh) * OW + ow0 + j) * C) + cv * 4)
+                                          : make_float4(0, 0, 0, 0);
 #pragma unroll
                 for (int kh = 0; kh < K; ++kh) {
                     const int ih = oh * stride + kh - pad;
                     if (ih < 0 || ih >= H) continue;
+                    const float* row = x + ((long)b * H + ih) * W * C + cv * 4;
+                    float4 xin[SPANW];
 #pragma unroll
-                    for (int kw = 0; kw < K; ++kw) {
-                        const int iw = ow * stride + kw - pad;
-                        if (iw < 0 || iw >= W) continue;
-                        fma4(acc[kh * K + kw], g, ld4(x + (((long)b * H + ih) * W + iw) * C + cv * 4));
+                    for (int sI = 0; sI < SPANW; ++sI) {
+                        const int iw = ow0 * stride + sI - pad;
+                        xin[sI] = (iw >= 0 && iw < W) ? ld4(row + (long)iw * C) : make_float4(0, 0, 0, 0);
                     }
+#pragma unroll
+                    for (int kw = 0; kw < K; ++kw)
+#pragma unroll
+                        for (int j = 0; j < PX; ++j)
+                            fma4(acc[kh * K + kw], g[j], xin[S * j + kw]);
                 }
             }
 #pragma unroll
@@ -219,7 +320,16 @@ DFINE_API int dfine_dwconv_fwd(const float* x, const float* w, float* y, int B, 
     const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
     const long total = (long)B * OH * OW * (C / 4);
     if (total == 0) return 0;
-    dwconv_fwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x, w, y, B, H, W, C, OH, OW, k, stride, pad);
+    const long blocked = (long)B * OH * ((OW + PX - 1) / PX) * (C / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (k == 5 && stride == 1)
+        dwconv_fwd_blocked<5, 1><<<ew_grid(blocked), NT, 0, st>>>(x, w, y, B, H, W, C, OH, OW, pad);
+    else if (k == 3 && stride == 2)
+        dwconv_fwd_blocked<3, 2><<<ew_grid(blocked), NT, 0, st>>>(x, w, y, B, H, W, C, OH, OW, pad);
+    else if (k == 3 && stride == 1)
+        dwconv_fwd_blocked<3, 1><<<ew_grid(blocked), NT, 0, st>>>(x, w, y, B, H, W, C, OH, OW, pad);
+    else
+        dwconv_fwd_kernel<<<ew_grid(total), NT, 0, st>>>(x, w, y, B, H, W, C, OH, OW, k, stride, pad);
     DFINE_LAUNCH_CHECK("dwconv_fwd");
     return 0;
 }
@@ -230,8 +340,14 @@ DFINE_API int dfine_dwconv_bwd_data(const float* dy, const float* w, float* dx, 
     const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
     const long total = (long)B * H * W * (C / 4);
     if (total == 0) return 0;
-    dwconv_bwd_data_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(dy, w, dx, B, H, W, C, OH, OW, k, stride,
-                                                                           pad);
+    const long blocked = (long)B * H * ((W + PX - 1) / PX) * (C / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (k == 5 && stride == 1)
+        dwconv_bwd_data_blocked<5><<<ew_grid(blocked), NT, 0, st>>>(dy, w, dx, B, H, W, C, OH, OW, pad);
+    else if (k == 3 && stride == 1)
+        dwconv_bwd_data_blocked<3><<<ew_grid(blocked), NT, 0, st>>>(dy, w, dx, B, H, W, C, OH, OW, pad);
+    else
+        dwconv_bwd_data_kernel<<<ew_grid(total), NT, 0, st>>>(dy, w, dx, B, H, W, C, OH, OW, k, stride, pad);
     DFINE_LAUNCH_CHECK("dwconv_bwd_data");
     return 0;
 }
@@ -242,17 +358,22 @@ DFINE_API int dfine_dwconv_bwd_weight(const float* dy, const float* x, float* dw
     DFINE_REQUIRE(C % 4 == 0 && (k == 3 || k == 5), "dwconv_bwd_weight: C=%d k=%d", C, k);
     DFINE_REQUIRE((long)k * k * C * 4 <= 48 * 1024, "dwconv_bwd_weight: k*k*C too large for shared memory");
     const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
-    const long P = (long)B * OH * OW;
+    DFINE_REQUIRE(stride == 1 || stride == 2, "dwconv_bwd_weight: stride %d", stride);
+    const long P = (long)B * OH * ((OW + PX - 1) / PX);      // blocks of PX output pixels along W
     if (P == 0) return 0;
     long ppc = (P + 148L * 4 - 1) / (148L * 4);
-    if (ppc < 64) ppc = 64;
+    if (ppc < 16) ppc = 16;
     const size_t smem = (size_t)k * k * C * sizeof(float);
-    if (k == 3)
-        dwconv_bwd_weight_kernel<3><<<ceil_div(P, ppc), NT, smem, (cudaStream_t)stream>>>(dy, x, dw, B, H, W, C, OH, OW,
-                                                                                         stride, pad, ppc);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = ceil_div(P, ppc);
+    if (k == 3 && stride == 1)
+        dwconv_bwd_weight_kernel<3, 1><<<grid, NT, smem, st>>>(dy, x, dw, B, H, W, C, OH, OW, pad, ppc);
+    else if (k == 3)
+        dwconv_bwd_weight_kernel<3, 2><<<grid, NT, smem, st>>>(dy, x, dw, B, H, W, C, OH, OW, pad, ppc);
+    else if (stride == 1)
+        dwconv_bwd_weight_kernel<5, 1><<<grid, NT, smem, st>>>(dy, x, dw, B, H, W, C, OH, OW, pad, ppc);
     else
-        dwconv_bwd_weight_kernel<5><<<ceil_div(P, ppc), NT, smem, (cudaStream_t)stream>>>(dy, x, dw, B, H, W, C, OH, OW,
-                                                                                         stride, pad, ppc);
+        dwconv_bwd_weight_kernel<5, 2><<<grid, NT, smem, st>>>(dy, x, dw, B, H, W, C, OH, OW, pad, ppc);
     DFINE_LAUNCH_CHECK("dwconv_bwd_weight");
     return 0;
 }
