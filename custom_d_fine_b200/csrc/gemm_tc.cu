@@ -373,14 +373,29 @@ __global__ void __launch_bounds__(fwd_threads(X3)) tc_fwd_kernel(const __grid_co
 // accumulator is DOUBLE-BUFFERED in TMEM (2*BN columns): the MMA warp starts tile i+1 while the four
 // epilogue warps drain tile i.  Removes the per-tile prologue (barrier init, TMEM alloc) that dominates the
 // small-K layers (stem / stage-1 maps with 10^4 tiles) and exposes no epilogue latency.
+constexpr int EPL = 36;   // epilogue transpose pitch (floats): 16-byte aligned rows, conflict-free float4 phases
+template <int BN> struct StatT { typedef double type; };
+template <> struct StatT<256> { typedef float type; };
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 template <int BN, int X3, int STAGES>
 struct PersistSmem {
     alignas(1024) float a[STAGES][BM * BK];
     alignas(1024) float b[STAGES][BN * BK];
-    alignas(1024) float alo[X3 ? STAGES : 1][X3 ? BM * BK : 32];
-    alignas(1024) float blo[X3 ? STAGES : 1][X3 ? BN * BK : 32];
-    float epi[4][32 * EPI_LD];
-    double stat[2 * BN];          // per-CTA BatchNorm partial sums (sum, sum of squares), flushed once at the end
+    alignas(X3 ? 1024 : 16) float alo[X3 ? STAGES : 1][X3 ? BM * BK : 4];
+    alignas(X3 ? 1024 : 16) float blo[X3 ? STAGES : 1][X3 ? BN * BK : 4];
+    alignas(16) float epi[4][32 * EPL];
+    // warp-private BatchNorm partial sums (sum | sum of squares per channel of the N tile), plain adds, merged
+    // and flushed to global memory once per CTA.  (fp32 slots on the 256-wide tile, where smem is exhausted
+    // and a CTA sees at most ~6 tiles; double elsewhere.)
+    typename StatT<BN>::type statw[4][2 * BN];
     uint64_t full[STAGES], empty[STAGES], conv[STAGES], tfull[2], tempty[2];
     uint32_t tmem_base;
     volatile uint32_t produced;   // k-blocks whose TMA loads have been issued (progress hint for the prefetch warp)
@@ -406,7 +421,7 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
     constexpr uint32_t TMEM_COLS = 2 * BN;
 
     if (stats)
-        for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) sm.stat[i] = 0.0;
+        for (int i = threadIdx.x; i < 4 * 2 * BN; i += blockDim.x) (&sm.statw[0][0])[i] = 0;
     if (warp == 0 && lane == 0) { prefetch_tmap(&map_x); prefetch_tmap(&map_w); if (X3) prefetch_tmap(&map_wlo); }
     if (warp == 1) {
         if (lane == 0) {
@@ -491,8 +506,13 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
         }
         __syncwarp();
     } else if (warp < 6) {
+        // Epilogue: TMEM -> registers (one accumulator row per lane) -> shared transpose (float4, pitch 36) ->
+        // 128-byte row stores.  Shared accesses are explicit st/ld.shared.v4 (8 + 8 per 32-column chunk).
         const int q = warp % 4;  // TMEM lane quarter
-        float* buf = sm.epi[q];
+        const uint32_t wbase = smem_u32(sm.epi[q]);
+        const bool plain = (bias == nullptr) && p.act == 0;
+        const bool local_stats = stats != nullptr && ts.n_tiles == 1;
+        typename StatT<BN>::type* sw = sm.statw[q];
         uint32_t i = 0;
         for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
             const uint32_t acc = i & 1, aph = (i >> 1) & 1;
@@ -516,7 +536,9 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                 uint32_t v[32];
                 tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + acc * BN + (uint32_t)c0, v);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) buf[lane * EPI_LD + c] = __uint_as_float(v[c]);
+                for (int c4 = 0; c4 < 8; ++c4)
+                    sts128(wbase + (uint32_t)(lane * EPL + 4 * c4) * 4u, __uint_as_float(v[4 * c4]),
+                           __uint_as_float(v[4 * c4 + 1]), __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
                 __syncwarp();
                 const int col = n0 + c0 + 4 * (lane % 8);
                 const bool col_ok = col < p.N;  // N % 4 == 0 is required by the host wrapper
@@ -526,17 +548,17 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
 #pragma unroll
                 for (int r8 = 0; r8 < 8; ++r8) {
                     const int r = 4 * r8 + lane / 8;
-                    float o[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) o[j] = buf[r * EPI_LD + 4 * (lane % 8) + j];
+                    float4 o = lds128(wbase + (uint32_t)(r * EPL + 4 * (lane % 8)) * 4u);
                     if (row_ok[r8] && col_ok) {
                         if (stats) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) { s1[j] += o[j]; s2[j] += o[j] * o[j]; }
+                            s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
+                            s2[0] += o.x * o.x; s2[1] += o.y * o.y; s2[2] += o.z * o.z; s2[3] += o.w * o.w;
                         }
-                        o[0] = act_fwd(o[0] + bv.x, p.act); o[1] = act_fwd(o[1] + bv.y, p.act);
-                        o[2] = act_fwd(o[2] + bv.z, p.act); o[3] = act_fwd(o[3] + bv.w, p.act);
-                        *reinterpret_cast<float4*>(y + row_off[r8] + col) = make_float4(o[0], o[1], o[2], o[3]);
+                        if (!plain) {
+                            o.x = act_fwd(o.x + bv.x, p.act); o.y = act_fwd(o.y + bv.y, p.act);
+                            o.z = act_fwd(o.z + bv.z, p.act); o.w = act_fwd(o.w + bv.w, p.act);
+                        }
+                        *reinterpret_cast<float4*>(y + row_off[r8] + col) = o;
                     }
                 }
                 if (stats) {
@@ -545,20 +567,16 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                         s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8); s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
                         s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
                     }
-                    // per-CTA accumulation in shared memory: with one global fp64 atomic per (tile, warp, channel)
-                    // the 10^4-tile stem layers serialised on a few dozen L2 addresses (profiles/README.md)
-                    // (possible when one N tile covers Cout, i.e. every tile of the CTA maps to the same channels;
-                    // wide-Cout layers have few tiles per channel and keep the direct global atomics)
                     if (lane < 8 && col_ok) {
-                        if (ts.n_tiles == 1) {
+                        if (local_stats) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                atomicAdd(&sm.stat[c0 + 4 * lane + j], (double)s1[j]);
-                                atomicAdd(&sm.stat[BN + c0 + 4 * lane + j], (double)s2[j]);
+                            for (int j = 0; j < 4; ++j) {      // warp-private slots: plain read-modify-write
+                                sw[c0 + 4 * lane + j] += s1[j];
+                                sw[BN + c0 + 4 * lane + j] += s2[j];
                             }
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
+                            for (int j = 0; j < 4; ++j) {      // wide-Cout layers: few tiles per channel
                                 atomicAdd(stats + col + j, (double)s1[j]);
                                 atomicAdd(stats + p.N + col + j, (double)s2[j]);
                             }
@@ -647,7 +665,7 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
     if (stats && ts.n_tiles == 1) {
         for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
             const int c = i % BN, which = i / BN;
-            const double v = sm.stat[i];
+            const double v = (double)sm.statw[0][i] + (double)sm.statw[1][i] + (double)sm.statw[2][i] + (double)sm.statw[3][i];
             if (c < p.N && v != 0.0) atomicAdd(stats + (long)which * p.N + c, v);
         }
     }
