@@ -31,16 +31,19 @@ __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<floa
 // ---------------------------------------------------------------------------------------------
 // BatchNorm statistics: stats[0:C] += sum(x), stats[C:2C] += sum(x^2)      (double accumulators)
 // ---------------------------------------------------------------------------------------------
+// Partial sums are merged without atomics: thread (row lane, channel group) owns the slot part[row lane][channel]
+// of a shared fp32 table, the CTA then sums the <= 256/LPR row lanes in double and issues ONE global fp64 atomic
+// per channel.  (Shared-memory fp64 atomicAdd is a CAS loop on sm_100: with 256 threads hitting 2*C addresses it
+// cost more than the HBM pass itself.)
 __global__ void __launch_bounds__(NT) bn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats,
                                                       long M, int C, long rows_per_cta) {
-    extern __shared__ double sh[];  // [2*C]
-    for (int i = threadIdx.x; i < 2 * C; i += NT) sh[i] = 0.0;
-    __syncthreads();
+    extern __shared__ float part[];  // [RPP][2*C]
     const RowMap m = make_rowmap(C);
     const long r0 = (long)blockIdx.x * rows_per_cta;
     const long r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
     const int lane_r = threadIdx.x / m.LPR, lane_c = threadIdx.x % m.LPR;
     if (lane_r < m.RPP) {
+        float* mine = part + (size_t)lane_r * 2 * C;
         for (int cv = lane_c; cv < m.VC; cv += m.LPR) {
             float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
             for (long r = r0 + lane_r; r < r1; r += m.RPP) {
@@ -48,15 +51,16 @@ __global__ void __launch_bounds__(NT) bn_stats_kernel(const float* __restrict__ 
                 s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
                 q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
             }
-            const int c = cv * 4;
-            atomicAdd(&sh[c + 0], (double)s.x); atomicAdd(&sh[c + 1], (double)s.y);
-            atomicAdd(&sh[c + 2], (double)s.z); atomicAdd(&sh[c + 3], (double)s.w);
-            atomicAdd(&sh[C + c + 0], (double)q.x); atomicAdd(&sh[C + c + 1], (double)q.y);
-            atomicAdd(&sh[C + c + 2], (double)q.z); atomicAdd(&sh[C + c + 3], (double)q.w);
+            st4(mine + cv * 4, s);
+            st4(mine + C + cv * 4, q);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += NT) atomicAdd(&stats[i], sh[i]);
+    for (int i = threadIdx.x; i < 2 * C; i += NT) {
+        double a = 0.0;
+        for (int r = 0; r < m.RPP; ++r) a += (double)part[(size_t)r * 2 * C + i];
+        atomicAdd(&stats[i], a);
+    }
 }
 
 // mean / invstd / folded scale+shift / running-stat update (momentum, unbiased var) — C threads.
@@ -123,16 +127,16 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(
     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ pre_add, const float* __restrict__ lab, double* __restrict__ red, long M, int C,
     long rows_per_cta, int act) {
-    extern __shared__ double sh[];  // [2*C + 2]
-    for (int i = threadIdx.x; i < 2 * C + 2; i += NT) sh[i] = 0.0;
-    __syncthreads();
+    extern __shared__ float part[];  // [RPP][2*C] partial sums + [NT/32][2] LAB partials (see bn_stats_kernel)
     const float ls = lab ? __ldg(lab) : 1.f;
     const RowMap m = make_rowmap(C);
+    float* labp = part + (size_t)m.RPP * 2 * C;
     const long r0 = (long)blockIdx.x * rows_per_cta;
     const long r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
     const int lane_r = threadIdx.x / m.LPR, lane_c = threadIdx.x % m.LPR;
     float lab_gs = 0.f, lab_gb = 0.f;
     if (lane_r < m.RPP) {
+        float* mine = part + (size_t)lane_r * 2 * C;
         for (int cv = lane_c; cv < m.VC; cv += m.LPR) {
             const int c = cv * 4;
             const float4 sc = ld4(scale + c), sf = ld4(shift + c), mu = ld4(mean + c), is = ld4(invstd + c);
@@ -153,19 +157,26 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(
                 q.x += dz.x * (v.x - mu.x) * is.x; q.y += dz.y * (v.y - mu.y) * is.y;
                 q.z += dz.z * (v.z - mu.z) * is.z; q.w += dz.w * (v.w - mu.w) * is.w;
             }
-            atomicAdd(&sh[c + 0], (double)s.x); atomicAdd(&sh[c + 1], (double)s.y);
-            atomicAdd(&sh[c + 2], (double)s.z); atomicAdd(&sh[c + 3], (double)s.w);
-            atomicAdd(&sh[C + c + 0], (double)q.x); atomicAdd(&sh[C + c + 1], (double)q.y);
-            atomicAdd(&sh[C + c + 2], (double)q.z); atomicAdd(&sh[C + c + 3], (double)q.w);
+            st4(mine + c, s);
+            st4(mine + C + c, q);
         }
     }
     if (lab) {
         lab_gs = warp_sum(lab_gs);
         lab_gb = warp_sum(lab_gb);
-        if ((threadIdx.x & 31) == 0) { atomicAdd(&sh[2 * C], (double)lab_gs); atomicAdd(&sh[2 * C + 1], (double)lab_gb); }
+        if ((threadIdx.x & 31) == 0) { labp[2 * (threadIdx.x / 32)] = lab_gs; labp[2 * (threadIdx.x / 32) + 1] = lab_gb; }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C + (lab ? 2 : 0); i += NT) atomicAdd(&red[i], sh[i]);
+    for (int i = threadIdx.x; i < 2 * C; i += NT) {
+        double a = 0.0;
+        for (int r = 0; r < m.RPP; ++r) a += (double)part[(size_t)r * 2 * C + i];
+        atomicAdd(&red[i], a);
+    }
+    if (lab && threadIdx.x < 2) {
+        double a = 0.0;
+        for (int w = 0; w < NT / 32; ++w) a += (double)labp[2 * w + threadIdx.x];
+        atomicAdd(&red[2 * C + threadIdx.x], a);
+    }
 }
 
 // Backward pass 2.  training: dx = scale*(dz - sum_dz/M - xhat*sum_dzx/M) ; else dx = scale*dz.
@@ -179,6 +190,11 @@ __global__ void __launch_bounds__(NT) bn_bwd_apply_kernel(
     const float ls = lab ? __ldg(lab) : 1.f;
     const int C = VC * 4;
     const double invM = 1.0 / (double)M;
+    extern __shared__ float mean_terms[];   // [2*C]: sum(dz)/M and sum(dz*xhat)/M as floats (one fp64 multiply per channel)
+    if (training) {
+        for (int c = threadIdx.x; c < 2 * C; c += NT) mean_terms[c] = (float)(red[c] * invM);
+        __syncthreads();
+    }
     if (blockIdx.x == 0) {
         // parameter gradients straight into the (flat-arena) .grad tensors: d(bn.weight) = sum dz*xhat,
         // d(bn.bias) = sum dz, LAB scalars; `red` is complete (written by the previous launch)
@@ -200,7 +216,7 @@ __global__ void __launch_bounds__(NT) bn_bwd_apply_kernel(
             const float mm[4] = {mu.x, mu.y, mu.z, mu.w}, ii[4] = {is.x, is.y, is.z, is.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float m1 = (float)(red[c + k] * invM), m2 = (float)(red[C + c + k] * invM);
+                const float m1 = mean_terms[c + k], m2 = mean_terms[C + c + k];
                 o[k] = ss[k] * (dz[k] - m1 - (vv[k] - mm[k]) * ii[k] * m2);
             }
         } else {
@@ -347,7 +363,8 @@ DFINE_API int dfine_bn_stats(const float* x, double* stats, long M, int C, void*
     DFINE_REQUIRE(C % 4 == 0 && C > 0 && C <= 3064, "bn_stats: C=%d must be a multiple of 4 (<=4096)", C);
     if (M == 0) return 0;
     const long rpc = pick_rows_per_cta(M, C);
-    bn_stats_kernel<<<ceil_div(M, rpc), NT, 2 * C * sizeof(double), (cudaStream_t)stream>>>(x, stats, M, C, rpc);
+    const RowMap rm = make_rowmap(C);
+    bn_stats_kernel<<<ceil_div(M, rpc), NT, (size_t)rm.RPP * 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, stats, M, C, rpc);
     DFINE_LAUNCH_CHECK("bn_stats");
     return 0;
 }
@@ -390,7 +407,9 @@ DFINE_API int dfine_bn_bwd_reduce(const float* dy, const float* x, const float* 
     DFINE_REQUIRE(C % 4 == 0 && C > 0 && C <= 3064, "bn_bwd_reduce: C=%d", C);
     if (M == 0) return 0;
     const long rpc = pick_rows_per_cta(M, C);
-    bn_bwd_reduce_kernel<<<ceil_div(M, rpc), NT, (2 * C + 2) * sizeof(double), (cudaStream_t)stream>>>(
+    const RowMap rm = make_rowmap(C);
+    const size_t smem = ((size_t)rm.RPP * 2 * C + 2 * (NT / 32)) * sizeof(float);
+    bn_bwd_reduce_kernel<<<ceil_div(M, rpc), NT, smem, (cudaStream_t)stream>>>(
         dy, x, scale, shift, mean, invstd, pre_add, lab, red, M, C, rpc, act);
     DFINE_LAUNCH_CHECK("bn_bwd_reduce");
     return 0;
@@ -405,7 +424,7 @@ DFINE_API int dfine_bn_bwd_apply(const float* dy, const float* x, const float* s
                   "bn_bwd_apply: gradient outputs come in pairs");
     const long n4 = M * C / 4;
     if (n4 == 0) return 0;
-    bn_bwd_apply_kernel<<<ew_grid(n4), NT, 0, (cudaStream_t)stream>>>(dy, x, scale, shift, mean, invstd, pre_add, lab,
+    bn_bwd_apply_kernel<<<ew_grid(n4), NT, 2 * C * sizeof(float), (cudaStream_t)stream>>>(dy, x, scale, shift, mean, invstd, pre_add, lab,
                                                                      red, dx, dpre, n4, C / 4, M, act, training, g_w,
                                                                      g_b, g_lab_s, g_lab_b);
     DFINE_LAUNCH_CHECK("bn_bwd_apply");
