@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(
     const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ scale,
     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ pre_add, const float* __restrict__ lab, double* __restrict__ red, long M, int C,
-    long rows_per_cta, int act) {
+    long rows_per_cta, int act, long ld_dy) {
     extern __shared__ float part[];  // [RPP][2*C] partial sums + [NT/32][2] LAB partials (see bn_stats_kernel)
     const float ls = lab ? __ldg(lab) : 1.f;
     const RowMap m = make_rowmap(C);
@@ -141,9 +141,8 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(
             const int c = cv * 4;
             const float4 sc = ld4(scale + c), sf = ld4(shift + c), mu = ld4(mean + c), is = ld4(invstd + c);
             float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
-            for (long r = r0 + lane_r; r < r1; r += m.RPP) {
-                const long o = r * C + c;
-                const float4 g = ld4(dy + o), v = ld4(x + o);
+            // rows are walked four at a time so that eight independent 16-byte loads are in flight per thread
+            auto body = [&](const float4 g, const float4 v, const long o) {
                 float4 z = make_float4(v.x * sc.x + sf.x, v.y * sc.y + sf.y, v.z * sc.z + sf.z, v.w * sc.w + sf.w);
                 if (pre_add) { const float4 a = ld4(pre_add + o); z.x += a.x; z.y += a.y; z.z += a.z; z.w += a.w; }
                 if (lab) {
@@ -156,7 +155,19 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(
                 s.x += dz.x; s.y += dz.y; s.z += dz.z; s.w += dz.w;
                 q.x += dz.x * (v.x - mu.x) * is.x; q.y += dz.y * (v.y - mu.y) * is.y;
                 q.z += dz.z * (v.z - mu.z) * is.z; q.w += dz.w * (v.w - mu.w) * is.w;
+            };
+            long r = r0 + lane_r;
+            for (; r + 3L * m.RPP < r1; r += 4L * m.RPP) {
+                float4 g[4], v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    g[u] = ld4(dy + (r + (long)u * m.RPP) * ld_dy + c);
+                    v[u] = ld4(x + (r + (long)u * m.RPP) * C + c);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) body(g[u], v[u], (r + (long)u * m.RPP) * C + c);
             }
+            for (; r < r1; r += m.RPP) body(ld4(dy + r * ld_dy + c), ld4(x + r * C + c), r * C + c);
             st4(mine + c, s);
             st4(mine + C + c, q);
         }
@@ -186,7 +197,8 @@ __global__ void __launch_bounds__(NT) bn_bwd_apply_kernel(
     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ pre_add, const float* __restrict__ lab, const double* __restrict__ red,
     float* __restrict__ dx, float* __restrict__ dpre, long n4, int VC, long M, int act, int training,
-    float* __restrict__ g_w, float* __restrict__ g_b, float* __restrict__ g_lab_s, float* __restrict__ g_lab_b) {
+    float* __restrict__ g_w, float* __restrict__ g_b, float* __restrict__ g_lab_s, float* __restrict__ g_lab_b,
+    long ld_dy) {
     const float ls = lab ? __ldg(lab) : 1.f;
     const int C = VC * 4;
     const double invM = 1.0 / (double)M;
@@ -204,7 +216,7 @@ __global__ void __launch_bounds__(NT) bn_bwd_apply_kernel(
     }
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long)gridDim.x * NT) {
         const int c = (int)(i % VC) * 4;
-        const float4 g = ld4(dy + i * 4), v = ld4(x + i * 4), sc = ld4(scale + c), sf = ld4(shift + c);
+        const float4 g = ld4(dy + (i / VC) * ld_dy + c), v = ld4(x + i * 4), sc = ld4(scale + c), sf = ld4(shift + c);
         float z[4] = {v.x * sc.x + sf.x, v.y * sc.y + sf.y, v.z * sc.z + sf.z, v.w * sc.w + sf.w};
         if (pre_add) { const float4 a = ld4(pre_add + i * 4); z[0] += a.x; z[1] += a.y; z[2] += a.z; z[3] += a.w; }
         const float gg[4] = {g.x, g.y, g.z, g.w}, vv[4] = {v.x, v.y, v.z, v.w}, ss[4] = {sc.x, sc.y, sc.z, sc.w};
@@ -403,14 +415,15 @@ DFINE_API int dfine_bn_apply(const float* x, const float* scale, const float* sh
 // red: double [2*C+2], zero-initialised by the caller.
 DFINE_API int dfine_bn_bwd_reduce(const float* dy, const float* x, const float* scale, const float* shift,
                                   const float* mean, const float* invstd, const float* pre_add, const float* lab,
-                                  double* red, long M, int C, int act, void* stream) {
+                                  double* red, long M, int C, int act, long ld_dy, void* stream) {
     DFINE_REQUIRE(C % 4 == 0 && C > 0 && C <= 3064, "bn_bwd_reduce: C=%d", C);
+    DFINE_REQUIRE(ld_dy >= C && ld_dy % 4 == 0 && ((uintptr_t)dy % 16) == 0, "bn_bwd_reduce: dy row stride %ld", ld_dy);
     if (M == 0) return 0;
     const long rpc = pick_rows_per_cta(M, C);
     const RowMap rm = make_rowmap(C);
     const size_t smem = ((size_t)rm.RPP * 2 * C + 2 * (NT / 32)) * sizeof(float);
     bn_bwd_reduce_kernel<<<ceil_div(M, rpc), NT, smem, (cudaStream_t)stream>>>(
-        dy, x, scale, shift, mean, invstd, pre_add, lab, red, M, C, rpc, act);
+        dy, x, scale, shift, mean, invstd, pre_add, lab, red, M, C, rpc, act, ld_dy);
     DFINE_LAUNCH_CHECK("bn_bwd_reduce");
     return 0;
 }
@@ -418,15 +431,16 @@ DFINE_API int dfine_bn_bwd_reduce(const float* dy, const float* x, const float* 
 DFINE_API int dfine_bn_bwd_apply(const float* dy, const float* x, const float* scale, const float* shift,
                                  const float* mean, const float* invstd, const float* pre_add, const float* lab,
                                  const double* red, float* dx, float* dpre, long M, int C, int act, int training,
-                                 float* g_w, float* g_b, float* g_lab_s, float* g_lab_b, void* stream) {
+                                 float* g_w, float* g_b, float* g_lab_s, float* g_lab_b, long ld_dy, void* stream) {
     DFINE_REQUIRE(C % 4 == 0, "bn_bwd_apply: C=%d", C);
+    DFINE_REQUIRE(ld_dy >= C && ld_dy % 4 == 0 && ((uintptr_t)dy % 16) == 0, "bn_bwd_apply: dy row stride %ld", ld_dy);
     DFINE_REQUIRE((g_w == nullptr) == (g_b == nullptr) && (g_lab_s == nullptr) == (g_lab_b == nullptr),
                   "bn_bwd_apply: gradient outputs come in pairs");
     const long n4 = M * C / 4;
     if (n4 == 0) return 0;
     bn_bwd_apply_kernel<<<ew_grid(n4), NT, 2 * C * sizeof(float), (cudaStream_t)stream>>>(dy, x, scale, shift, mean, invstd, pre_add, lab,
                                                                      red, dx, dpre, n4, C / 4, M, act, training, g_w,
-                                                                     g_b, g_lab_s, g_lab_b);
+                                                                     g_b, g_lab_s, g_lab_b, ld_dy);
     DFINE_LAUNCH_CHECK("bn_bwd_apply");
     return 0;
 }

@@ -99,6 +99,36 @@ def _p(t):
     return c_void_p(0) if t is None else c_void_p(t.data_ptr())
 
 
+class _ZeroPool:
+    """Pre-zeroed fp64 scratch for the per-layer BatchNorm statistics / backward reductions.  The reference's
+    equivalent is implicit in ATen; here ~270 tiny `torch.zeros` launches per step become ONE memset: the train
+    step calls ``begin_step`` (also under CUDA-graph capture, where the memset is captured once), ops take
+    slices with ``take``; without an active step (unit tests calling ops directly) ``take`` allocates."""
+
+    def __init__(self):
+        self.buf, self.off, self.active = None, 0, False
+
+    def begin_step(self, device, n_doubles=1 << 19):
+        if self.buf is None or self.buf.device != device or self.buf.numel() < n_doubles:
+            self.buf = torch.empty(n_doubles, dtype=torch.float64, device=device)
+        self.buf.zero_()
+        self.off, self.active = 0, True
+
+    def end_step(self):
+        self.active = False
+
+    def take(self, n, device):
+        n_al = (n + 1) // 2 * 2          # keep 16-byte alignment
+        if not self.active or self.buf is None or self.buf.device != device or self.off + n_al > self.buf.numel():
+            return torch.zeros(n, dtype=torch.float64, device=device)
+        out = self.buf[self.off:self.off + n]
+        self.off += n_al
+        return out
+
+
+zero_pool = _ZeroPool()
+
+
 def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -330,7 +360,7 @@ class _ConvBnAct(torch.autograd.Function):
         conv_out = torch.empty((B, OH, OW, Cout), device=dev, dtype=torch.float32)
         M = B * OH * OW
         need_stats = training
-        stats = torch.zeros(2 * Cout, device=dev, dtype=torch.float64) if need_stats else None
+        stats = zero_pool.take(2 * Cout, dev) if need_stats else None
         depthwise = groups > 1
         if depthwise:
             assert groups == Cin == Cout and pt == pl == pb == pr, "only depthwise grouped convs are on the path"
@@ -375,18 +405,23 @@ class _ConvBnAct(torch.autograd.Function):
         x, weight, conv_out, scale, shift, mean, invstd, pre_add, lab_s, lab_b, bn_w = ctx.saved_tensors
         stride, pad, groups, training, momentum, eps, act, frozen = ctx.cfg
         B, H, W, Cin, OH, OW, Cout, k, _, _ = ctx.geom
-        dy = dy.contiguous()
+        # dy is often a channel slice of a concatenation's gradient: consumed in place through its row stride
+        ld_dy = dy.stride(2) if dy.dim() == 4 else 0
+        if not (dy.dim() == 4 and dy.stride(3) == 1 and ld_dy >= Cout and ld_dy % 4 == 0 and dy.stride(1) == OW * ld_dy
+                and dy.stride(0) == OH * OW * ld_dy and dy.data_ptr() % 16 == 0):
+            dy = dy.contiguous()
+            ld_dy = Cout
         M = B * OH * OW
         dev = dy.device
         bn_train = training and mean is not None
         need_red = bn_train or lab_s is not None
-        red = torch.zeros(2 * Cout + 2, device=dev, dtype=torch.float64) if need_red else None
+        red = zero_pool.take(2 * Cout + 2, dev) if need_red else None
         if need_red:
             # (eval-mode BN with LAB still needs the LAB scalar gradients; mean/invstd unused then)
             m_ = mean if mean is not None else shift
             i_ = invstd if invstd is not None else scale
             _check(lib().dfine_bn_bwd_reduce(_p(dy), _p(conv_out), _p(scale), _p(shift), _p(m_), _p(i_), _p(pre_add),
-                                             _p(lab_s), _p(red), c_long(M), Cout, ACT[act], _stream()),
+                                             _p(lab_s), _p(red), c_long(M), Cout, ACT[act], c_long(ld_dy), _stream()),
                    "bn_bwd_reduce")
         dconv = torch.empty_like(conv_out)
         dpre = torch.empty_like(conv_out) if (pre_add is not None and ctx.needs_input_grad[6]) else None
@@ -405,7 +440,8 @@ class _ConvBnAct(torch.autograd.Function):
                                         1 if bn_train else 0, _p(bn_direct[0]) if bn_direct else None,
                                         _p(bn_direct[1]) if bn_direct else None,
                                         _p(lab_direct[0]) if lab_direct else None,
-                                        _p(lab_direct[1]) if lab_direct else None, _stream()), "bn_bwd_apply")
+                                        _p(lab_direct[1]) if lab_direct else None, c_long(ld_dy), _stream()),
+               "bn_bwd_apply")
         g_bn_w = g_bn_b = g_lab_s = g_lab_b = None
         if red is not None:
             redf = None
@@ -440,7 +476,7 @@ class _ConvBnAct(torch.autograd.Function):
                     _conv_wgrad(dconv, Cout, x, ldx, ctx.geom, dst)      # accumulated in place; autograd gets None
                 else:
                     g_w = _conv_wgrad(dconv, Cout, x, ldx, ctx.geom).permute(0, 3, 1, 2)
-        g_post = dy if ctx.has_post else None
+        g_post = (dy if dy.is_contiguous() else dy.contiguous()) if ctx.has_post else None
         return g_x, g_w, g_bn_w, g_bn_b, g_lab_s, g_lab_b, dpre, g_post, None, None, None
 
 

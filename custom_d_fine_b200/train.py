@@ -13,6 +13,18 @@ import torch
 from torch.nn.parallel import DistributedDataParallel as DDP
 
 
+def _begin_step(inputs):
+    """One memset for every per-layer fp64 reduction buffer of the step (cuda_ops.zero_pool)."""
+    if inputs.is_cuda:
+        from . import cuda_ops
+        cuda_ops.zero_pool.begin_step(inputs.device)
+
+
+def _end_step():
+    from . import cuda_ops
+    cuda_ops.zero_pool.end_step()
+
+
 class ModelEMA:
     """EMA of every floating-point state entry, momentum m*(1-exp(-it/2000)) (train.py:52-73).
     The reference walks ~920 tensors with two tiny kernels each; here the entries are updated with
@@ -117,10 +129,12 @@ class TrainStep:
 
     def __call__(self, inputs, targets):
         """inputs float32 [B,3,H,W] on the device; targets list of dicts (labels int64 [T], boxes [T,4])."""
+        _begin_step(inputs)
         output = self.model(inputs, targets=targets)
         loss_dict = self.loss_fn(output, targets)
         loss = sum(loss_dict.values()) / self.accum_steps
         loss.backward()
+        _end_step()
         self.batch_idx += 1
         if self.batch_idx % self.accum_steps == 0:
             self.optimizer_step()
@@ -196,6 +210,7 @@ class GraphedTrainStep(TrainStep):
         torch.cuda.synchronize()
         gA = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gA, stream=self._side):
+            _begin_step(g["x"])
             out = self.model(g["x"], targets=g["targets"])
             raw, tg = crit.match(out, g["targets"])
         gB = torch.cuda.CUDAGraph()
@@ -203,6 +218,7 @@ class GraphedTrainStep(TrainStep):
             loss_dict = crit.compute(out, tg, g["table"], g["counts"], plan)
             loss = sum(loss_dict.values())
             loss.backward()
+            _end_step()
             g["loss"] = loss.detach()
             g["loss_dict"] = {k: v.detach() for k, v in loss_dict.items()}
         gC = torch.cuda.CUDAGraph()
