@@ -276,6 +276,69 @@ __global__ void __launch_bounds__(NT) maxpool_bwd_kernel(const float* __restrict
     }
 }
 
+// ---- float4 variants of the stem max-pool (C % 4 == 0): one thread = one pixel x 4 channels ----------------
+__device__ __forceinline__ float4 padded4(const float* __restrict__ x, int b, int h, int w, int cv, int H, int W, int VC) {
+    return (h < H && w < W) ? ld4(x + ((((long)b * H + h) * W + w) * VC + cv) * 4) : make_float4(0, 0, 0, 0);
+}
+// argmax slot (0..3, first max wins, NaN propagates) of each of the 4 channels, packed in one int
+__device__ __forceinline__ int window_argmax4(const float* __restrict__ x, int b, int h, int w, int cv, int H, int W,
+                                              int VC, float4* mx) {
+    const float4 v[4] = {padded4(x, b, h, w, cv, H, W, VC), padded4(x, b, h, w + 1, cv, H, W, VC),
+                         padded4(x, b, h + 1, w, cv, H, W, VC), padded4(x, b, h + 1, w + 1, cv, H, W, VC)};
+    float best[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
+    int arg[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int s = 1; s < 4; ++s) {
+        const float e[4] = {v[s].x, v[s].y, v[s].z, v[s].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (e[c] > best[c] || isnan(e[c])) { best[c] = e[c]; arg[c] = s; }
+    }
+    *mx = make_float4(best[0], best[1], best[2], best[3]);
+    return arg[0] | (arg[1] << 2) | (arg[2] << 4) | (arg[3] << 6);
+}
+__global__ void __launch_bounds__(NT) maxpool_fwd4_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
+                                                          int H, int W, int VC) {
+    const long total = (long)B * H * W * VC;
+    for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+        const int cv = (int)(i % VC);
+        long p = i / VC;
+        const int w = (int)(p % W); p /= W;
+        const int h = (int)(p % H);
+        const int b = (int)(p / H);
+        float4 mx;
+        window_argmax4(x, b, h, w, cv, H, W, VC, &mx);
+        st4(y + i * 4, mx);
+    }
+}
+__global__ void __launch_bounds__(NT) maxpool_bwd4_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                          float* __restrict__ dx, int B, int H, int W, int VC) {
+    const long total = (long)B * H * W * VC;
+    for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+        const int cv = (int)(i % VC);
+        long p = i / VC;
+        const int w = (int)(p % W); p /= W;
+        const int h = (int)(p % H);
+        const int b = (int)(p / H);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float4 mx;
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+            for (int dw = 0; dw < 2; ++dw) {
+                const int oh = h - dh, ow = w - dw;
+                if (oh < 0 || ow < 0) continue;
+                const int arg = window_argmax4(x, b, oh, ow, cv, H, W, VC, &mx);
+                const float4 g = ld4(dy + ((((long)b * H + oh) * W + ow) * VC + cv) * 4);
+                const float ge[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (((arg >> (2 * c)) & 3) == dh * 2 + dw) acc[c] += ge[c];
+            }
+        st4(dx + i * 4, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    }
+}
+
 __global__ void __launch_bounds__(NT) upsample2x_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
                                                             int H, int W, int VC) {
     const long total = (long)B * (2 * H) * (2 * W) * VC;
@@ -381,7 +444,10 @@ DFINE_API int dfine_dwconv_bwd_weight(const float* dy, const float* x, float* dw
 DFINE_API int dfine_maxpool2x2_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream) {
     const long total = (long)B * H * W * C;
     if (total == 0) return 0;
-    maxpool_fwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C);
+    if (C % 4 == 0)
+        maxpool_fwd4_kernel<<<ew_grid(total / 4), NT, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C / 4);
+    else
+        maxpool_fwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C);
     DFINE_LAUNCH_CHECK("maxpool_fwd");
     return 0;
 }
@@ -389,7 +455,10 @@ DFINE_API int dfine_maxpool2x2_bwd(const float* x, const float* dy, float* dx, i
                                    void* stream) {
     const long total = (long)B * H * W * C;
     if (total == 0) return 0;
-    maxpool_bwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x, dy, dx, B, H, W, C);
+    if (C % 4 == 0)
+        maxpool_bwd4_kernel<<<ew_grid(total / 4), NT, 0, (cudaStream_t)stream>>>(x, dy, dx, B, H, W, C / 4);
+    else
+        maxpool_bwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x, dy, dx, B, H, W, C);
     DFINE_LAUNCH_CHECK("maxpool_bwd");
     return 0;
 }
