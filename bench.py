@@ -220,8 +220,13 @@ def run_ours(args):
                     "algorithmic_bytes_per_launch": int(nbytes)}
         name = max(kern, key=lambda k: kern[k][3])        # the family with the largest share of the step
         e = entry(name)
+        # DRAM traffic per launch of that family from the committed ncu pass (tools/gpu_trip_final.sh ncu_traffic)
+        traffic, tr_file = None, ROOT / "profiles" / "r1_traffic.json"
+        if tr_file.exists():
+            tr = json.loads(tr_file.read_text()).get(name)
+            traffic = int(tr["dram_bytes_per_launch"]) if tr else None
         roof = {"kernel": name, "bound": "hbm", "achieved": e["GB/s"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": e["frac"], "traffic": None, "peak_source": peak_src, "avg_launch_ms": e["avg_launch_ms"],
+                "frac": e["frac"], "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": e["avg_launch_ms"],
                 "launches_per_step": e["launches_per_step"], "ms_per_step": e["ms_per_step"],
                 "algorithmic_bytes_per_launch": e["algorithmic_bytes_per_launch"],
                 "definition": "sum of algorithmic bytes (in + out + weights, fp32) over the family's launches / sum of "

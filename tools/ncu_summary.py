@@ -61,5 +61,33 @@ def full(src, dst):
                         for k, i in idx])
 
 
+def traffic(src, dst):
+    """Per kernel family: launches, summed duration, summed DRAM read / write bytes of one step (json)."""
+    import json
+    lines = open(src).read().splitlines()
+    start = next(i for i, l in enumerate(lines) if l.startswith('"ID"'))
+    fam = collections.defaultdict(lambda: {"launches": 0, "us": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0})
+    seen = set()
+    for row in csv.DictReader(lines[start:]):
+        name = row["Kernel Name"]
+        key = "conv_tc" if "tc_fwd_persist" in name else "conv_wgrad_tc" if "tc_wgrad" in name else \
+            "msda_fwd" if "msda_fwd" in name else "msda_bwd" if "msda_bwd" in name else None
+        if key is None:
+            continue
+        v = float(row["Metric Value"].replace(",", ""))
+        unit, metric = row["Metric Unit"], row["Metric Name"]
+        if metric == "gpu__time_duration.sum":
+            fam[key]["us"] += {"ns": v / 1e3, "us": v, "ms": v * 1e3}.get(unit, v)
+            if row["ID"] not in seen:
+                seen.add(row["ID"])
+                fam[key]["launches"] += 1
+        else:
+            b = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+            fam[key]["dram_read_bytes" if "read" in metric else "dram_write_bytes"] += b
+    for k, d in fam.items():
+        d["dram_bytes_per_launch"] = (d["dram_read_bytes"] + d["dram_write_bytes"]) / max(d["launches"], 1)
+    json.dump(fam, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
