@@ -75,6 +75,14 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -683,6 +691,7 @@ struct WgradParams {
     long steps_total;     // B*OH*wchunks reduction steps of 32 pixels
     long steps_per_split;
     int cin_tiles;        // ceil(Cin / BN)
+    int dy5, x5;          // operand fetched as ONE 5-D box per step (channel count % 32 == 0) instead of one per 32-ch chunk
 };
 
 template <int BN>
@@ -734,13 +743,24 @@ __global__ void __launch_bounds__(WG_THREADS) tc_wgrad_kernel(const __grid_const
                 const int wc = (int)(step % p.wchunks); step /= p.wchunks;
                 const int oh = (int)(step % p.OH);
                 const int b = (int)(step / p.OH);
-                mbar_expect_tx(&sm.full[s], (uint32_t)((co_chunks * 32 + BN) * BK * sizeof(float)));
-                for (int c = 0; c < co_chunks; ++c)
-                    tma_load_4d(sm.a[s] + c * 32 * BK, &map_dy, &sm.full[s], co0 + 32 * c, wc * 32, oh, b);
+                // one 5-D box {32 ch, 32 px, chunks, row, image} per operand where the channel count allows it
+                // (TMA instruction issue, not bytes, bounded the per-chunk version: 8 boxes of 4 KB per step)
+                mbar_expect_tx(&sm.full[s], (uint32_t)(((p.dy5 ? BM / 32 : co_chunks) * 32 + BN) * BK * sizeof(float)));
+                if (p.dy5) {
+                    tma_load_5d(sm.a[s], &map_dy, &sm.full[s], 0, wc * 32, co0 / 32, oh, b);
+                } else {
+                    for (int c = 0; c < co_chunks; ++c)
+                        tma_load_4d(sm.a[s] + c * 32 * BK, &map_dy, &sm.full[s], co0 + 32 * c, wc * 32, oh, b);
+                }
+                if (p.x5) {
+                    tma_load_5d(sm.b[s], &map_x, &sm.full[s], 0, wc * 32 * p.stride + kw - p.pad_l, ci0 / 32,
+                                oh * p.stride + kh - p.pad_t, b);
+                } else {
 #pragma unroll
-                for (int c = 0; c < BN / 32; ++c)
-                    tma_load_4d(sm.b[s] + c * 32 * BK, &map_x, &sm.full[s], ci0 + 32 * c,
-                                wc * 32 * p.stride + kw - p.pad_l, oh * p.stride + kh - p.pad_t, b);
+                    for (int c = 0; c < BN / 32; ++c)
+                        tma_load_4d(sm.b[s] + c * 32 * BK, &map_x, &sm.full[s], ci0 + 32 * c,
+                                    wc * 32 * p.stride + kw - p.pad_l, oh * p.stride + kh - p.pad_t, b);
+                }
             }
         }
         __syncwarp();
@@ -853,6 +873,26 @@ int make_map4(CUtensorMap* m, const float* base, long C, long W, long H, long B,
     if (r != CUDA_SUCCESS) {
         dfine_set_error("%s: cuTensorMapEncodeTiled(4d) failed (%d) C=%ld W=%ld H=%ld B=%ld ld=%ld box=%d,%d,%d es=%d",
                         who, (int)r, C, W, H, B, ld, box_c, box_w, box_h, estride);
+        return -2;
+    }
+    return 0;
+}
+// 5-D view {32 channels of a chunk, W, chunk index, H, B} of an NHWC activation whose channel count is a multiple
+// of 32: one box {32, box_w*estride, box_chunks, 1, 1} lands in shared memory as [chunk][pixel][32 ch] — the
+// MN-major operand layout of the weight-gradient kernel — with a single TMA instruction.
+int make_map5(CUtensorMap* m, const float* base, long C, long W, long H, long B, long ld, int box_w, int box_chunks,
+              int estride, const char* who) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { dfine_set_error("%s: cuTensorMapEncodeTiled unavailable", who); return -2; }
+    cuuint64_t dims[5] = {32, (cuuint64_t)W, (cuuint64_t)(C / 32), (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[4] = {(cuuint64_t)ld * 4, 128, (cuuint64_t)ld * 4 * W, (cuuint64_t)ld * 4 * W * H};
+    cuuint32_t box[5] = {32, (cuuint32_t)(box_w * estride), (cuuint32_t)box_chunks, 1, 1};
+    cuuint32_t es[5] = {1, (cuuint32_t)estride, 1, 1, 1};
+    CUresult r = enc(m, map_dtype(), 5, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        dfine_set_error("%s: cuTensorMapEncodeTiled(5d) failed (%d) C=%ld W=%ld H=%ld B=%ld ld=%ld", who, (int)r, C, W, H, B, ld);
         return -2;
     }
     return 0;
@@ -1088,10 +1128,29 @@ DFINE_API int dfine_conv_wgrad_tc(const float* dy, const float* x, float* dwr, i
     p.wchunks = ceil_div(OW, 32);
     p.steps_total = (long)B * OH * p.wchunks;
     CUtensorMap mdy, mx;
-    int rc = make_map4(&mdy, dy, Cout, OW, OH, B, ldy, 32, 32, 1, 1, "conv_wgrad_tc(dy)", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-    if (rc) return rc;
-    rc = make_map4(&mx, x, Cin, W, H, B, ldx, 32, 32, 1, stride, "conv_wgrad_tc(x)", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-    if (rc) return rc;
+    static const bool box5 = [] { const char* e = getenv("DFINE_WGRAD_BOX5"); return !(e && e[0] == '0'); }();
+    const int bn = Cin <= 32 ? 32 : (Cin <= 64 ? 64 : 128);
+    p.dy5 = box5 && Cout % 32 == 0;
+    p.x5 = box5 && Cin % 32 == 0;
+    static bool box5_ok = true;    // cleared if the driver rejects the 5-D encoding (then one box per 32-channel chunk)
+    int rc = 0;
+    if (p.dy5 && box5_ok && make_map5(&mdy, dy, Cout, OW, OH, B, ldy, 32, BM / 32, 1, "conv_wgrad_tc(dy5)") != 0) box5_ok = false;
+    if (!box5_ok) p.dy5 = 0;
+    if (!p.dy5) {
+        rc = make_map4(&mdy, dy, Cout, OW, OH, B, ldy, 32, 32, 1, 1, "conv_wgrad_tc(dy)", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc) return rc;
+    }
+    if (p.x5 && box5_ok && make_map5(&mx, x, Cin, W, H, B, ldx, 32, bn / 32, stride, "conv_wgrad_tc(x5)") != 0) box5_ok = false;
+    if (!box5_ok) p.x5 = 0;
+    if (!p.x5) {
+        rc = make_map4(&mx, x, Cin, W, H, B, ldx, 32, 32, 1, stride, "conv_wgrad_tc(x)", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc) return rc;
+    }
+    if (!box5_ok && p.dy5) {       // the x encoding failed after dy was encoded 5-D: re-encode dy per chunk
+        p.dy5 = 0;
+        rc = make_map4(&mdy, dy, Cout, OW, OH, B, ldy, 32, 32, 1, 1, "conv_wgrad_tc(dy)", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc) return rc;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     rc = Cin <= 32 ? launch_wgrad<32>(mdy, mx, dwr, p, st)
        : Cin <= 64 ? launch_wgrad<64>(mdy, mx, dwr, p, st)
