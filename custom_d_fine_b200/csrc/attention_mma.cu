@@ -42,6 +42,14 @@ __device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], con
     mma(c, ah, bh0, bh1);
 }
 
+// c += a * b with the B operand already split (tiles staged as hi / lo planes)
+__device__ __forceinline__ void mma3s(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
+                                      uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+    mma(c, al, bh0, bh1);
+    mma(c, ah, bl0, bl1);
+    mma(c, ah, bh0, bh1);
+}
+
 // rows r0 = row0 + g and r0 + 8 of a [S, ld] matrix as A fragments for every k-step (8 columns each), scaled
 template <int HD>
 __device__ __forceinline__ void load_a_frags(const float* __restrict__ base, long ld, int row0, int S, float scale, int g,
@@ -58,31 +66,40 @@ __device__ __forceinline__ void load_a_frags(const float* __restrict__ base, lon
     }
 }
 
-// stage rows [row0, row0 + BT) of a [S, ld] matrix (HD columns) into smem with row pitch LD; zero past S
+// stage rows [row0, row0 + BT) of a [S, ld] matrix (HD columns) into smem as two planes (tf32 hi | lo remainder)
+// with row pitch LD; zero past S.  Splitting once per tile (not once per warp and use) halves the instruction
+// count of the MMA loops.
 template <int HD, int LD>
-__device__ __forceinline__ void stage(float* dst, const float* __restrict__ src, long ld, int row0, int S) {
+__device__ __forceinline__ void stage(uint32_t* hi, uint32_t* lo, const float* __restrict__ src, long ld, int row0, int S) {
     for (int e = threadIdx.x; e < BT * (HD / 4); e += NT) {
         const int r = e / (HD / 4), c4 = e % (HD / 4);
         float4 v = make_float4(0, 0, 0, 0);
         if (row0 + r < S) v = __ldg(reinterpret_cast<const float4*>(src + (long)(row0 + r) * ld + c4 * 4));
-        *reinterpret_cast<float4*>(dst + r * LD + c4 * 4) = v;
+        uint4 h, l;
+        split(v.x, h.x, l.x); split(v.y, h.y, l.y); split(v.z, h.z, l.z); split(v.w, h.w, l.w);
+        *reinterpret_cast<uint4*>(hi + r * LD + c4 * 4) = h;
+        *reinterpret_cast<uint4*>(lo + r * LD + c4 * 4) = l;
     }
 }
 
 // acc[nt] (16 x 8 per n-tile, NTILES tiles) += A(regs, HD wide) * Bs^T where Bs is [rows = n][HD] in smem (pitch LD)
 template <int HD, int LD, int NTILES>
 __device__ __forceinline__ void gemm_abt(float (&acc)[NTILES][4], const uint32_t (&ah)[HD / 8][4],
-                                         const uint32_t (&al)[HD / 8][4], const float* Bs, int g, int t) {
+                                         const uint32_t (&al)[HD / 8][4], const uint32_t* Bh, const uint32_t* Bl, int g,
+                                         int t) {
 #pragma unroll
     for (int nt = 0; nt < NTILES; ++nt)
 #pragma unroll
-        for (int kk = 0; kk < HD / 8; ++kk)
-            mma3(acc[nt], ah[kk], al[kk], Bs[(8 * nt + g) * LD + 8 * kk + t], Bs[(8 * nt + g) * LD + 8 * kk + t + 4]);
+        for (int kk = 0; kk < HD / 8; ++kk) {
+            const int i0 = (8 * nt + g) * LD + 8 * kk + t;
+            mma3s(acc[nt], ah[kk], al[kk], Bh[i0], Bh[i0 + 4], Bl[i0], Bl[i0 + 4]);
+        }
 }
 
 // acc[nt] (16 x 8 per n-tile over HD columns) += P(16 x BT, smem pitch PLD) * Bs where Bs is [rows = k][HD] (pitch LD)
 template <int HD, int LD>
-__device__ __forceinline__ void gemm_pb(float (&acc)[HD / 8][4], const float* Ps, const float* Bs, int g, int t) {
+__device__ __forceinline__ void gemm_pb(float (&acc)[HD / 8][4], const float* Ps, const uint32_t* Bh, const uint32_t* Bl,
+                                        int g, int t) {
 #pragma unroll
     for (int kk = 0; kk < BT / 8; ++kk) {
         uint32_t ah[4], al[4];
@@ -91,8 +108,10 @@ __device__ __forceinline__ void gemm_pb(float (&acc)[HD / 8][4], const float* Ps
         split(Ps[g * PLD + 8 * kk + t + 4], ah[2], al[2]);
         split(Ps[(g + 8) * PLD + 8 * kk + t + 4], ah[3], al[3]);
 #pragma unroll
-        for (int nt = 0; nt < HD / 8; ++nt)
-            mma3(acc[nt], ah, al, Bs[(8 * kk + t) * LD + 8 * nt + g], Bs[(8 * kk + t + 4) * LD + 8 * nt + g]);
+        for (int nt = 0; nt < HD / 8; ++nt) {
+            const int i0 = (8 * kk + t) * LD + 8 * nt + g, i1 = (8 * kk + t + 4) * LD + 8 * nt + g;
+            mma3s(acc[nt], ah, al, Bh[i0], Bh[i1], Bl[i0], Bl[i1]);
+        }
     }
 }
 
@@ -117,8 +136,8 @@ __device__ __forceinline__ void store_c(float* Ps, const float (&c)[BT / 8][4], 
 // ------------------------------------------------------------------------------------------- forward
 template <int HD>
 struct FwdSmem {
-    float k[BT * (HD + 4)];
-    float v[BT * (HD + 8)];
+    uint32_t k[BT * (HD + 4)], kl[BT * (HD + 4)];
+    uint32_t v[BT * (HD + 8)], vl[BT * (HD + 8)];
     float p[NT / 32][16 * PLD];
 };
 
@@ -141,11 +160,11 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const float* __restrict__ q, lo
     float* Ps = sm.p[warp];
     for (int t0 = 0; t0 < S; t0 += BT) {
         __syncthreads();
-        stage<HD, HD + 4>(sm.k, kb, ldk, t0, S);
-        stage<HD, HD + 8>(sm.v, vb, ldv, t0, S);
+        stage<HD, HD + 4>(sm.k, sm.kl, kb, ldk, t0, S);
+        stage<HD, HD + 8>(sm.v, sm.vl, vb, ldv, t0, S);
         __syncthreads();
         float s[BT / 8][4] = {};
-        gemm_abt<HD, HD + 4, BT / 8>(s, qh, ql, sm.k, g, t);
+        gemm_abt<HD, HD + 4, BT / 8>(s, qh, ql, sm.k, sm.kl, g, t);
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < BT / 8; ++nt)
@@ -181,7 +200,7 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const float* __restrict__ q, lo
         __syncwarp();
         store_c(Ps, s, g, t);
         __syncwarp();
-        gemm_pb<HD, HD + 8>(oacc, Ps, sm.v, g, t);
+        gemm_pb<HD, HD + 8>(oacc, Ps, sm.v, sm.vl, g, t);
     }
     const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
     float* ob = o + (long)b * S * ldo + h * HD;
@@ -199,8 +218,8 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const float* __restrict__ q, lo
 // ------------------------------------------------------------------------------------------- dQ (+ D = rowsum(dO*O))
 template <int HD>
 struct DqSmem {
-    float k[BT * (HD + 4)];
-    float v[BT * (HD + 4)];
+    uint32_t k[BT * (HD + 4)], kl[BT * (HD + 4)];
+    uint32_t v[BT * (HD + 4)], vl[BT * (HD + 4)];
     float p[NT / 32][16 * PLD];
 };
 
@@ -245,12 +264,12 @@ __global__ void __launch_bounds__(NT) dq_kernel(const float* __restrict__ q, lon
     float* Ps = sm.p[warp];
     for (int t0 = 0; t0 < S; t0 += BT) {
         __syncthreads();
-        stage<HD, HD + 4>(sm.k, kb, ldk, t0, S);
-        stage<HD, HD + 4>(sm.v, vb, ldv, t0, S);
+        stage<HD, HD + 4>(sm.k, sm.kl, kb, ldk, t0, S);
+        stage<HD, HD + 4>(sm.v, sm.vl, vb, ldv, t0, S);
         __syncthreads();
         float s[BT / 8][4] = {}, dp[BT / 8][4] = {};
-        gemm_abt<HD, HD + 4, BT / 8>(s, qh, ql, sm.k, g, t);
-        gemm_abt<HD, HD + 4, BT / 8>(dp, dh, dl, sm.v, g, t);
+        gemm_abt<HD, HD + 4, BT / 8>(s, qh, ql, sm.k, sm.kl, g, t);
+        gemm_abt<HD, HD + 4, BT / 8>(dp, dh, dl, sm.v, sm.vl, g, t);
 #pragma unroll
         for (int nt = 0; nt < BT / 8; ++nt)
 #pragma unroll
@@ -265,7 +284,7 @@ __global__ void __launch_bounds__(NT) dq_kernel(const float* __restrict__ q, lon
         __syncwarp();
         store_c(Ps, s, g, t);
         __syncwarp();
-        gemm_pb<HD, HD + 4>(acc, Ps, sm.k, g, t);
+        gemm_pb<HD, HD + 4>(acc, Ps, sm.k, sm.kl, g, t);
     }
     float* qo = dq + (long)b * S * lddq + h * HD;
 #pragma unroll
@@ -278,8 +297,8 @@ __global__ void __launch_bounds__(NT) dq_kernel(const float* __restrict__ q, lon
 // ------------------------------------------------------------------------------------------- dK, dV
 template <int HD>
 struct DkvSmem {
-    float q[BT * (HD + 4)];
-    float d[BT * (HD + 4)];
+    uint32_t q[BT * (HD + 4)], ql[BT * (HD + 4)];
+    uint32_t d[BT * (HD + 4)], dl[BT * (HD + 4)];
     float lse[BT], dsum[BT];
     float p[NT / 32][16 * PLD];
     float ds[NT / 32][16 * PLD];
@@ -308,8 +327,8 @@ __global__ void __launch_bounds__(NT) dkv_kernel(const float* __restrict__ q, lo
     float* Ds = sm.ds[warp];
     for (int t0 = 0; t0 < S; t0 += BT) {
         __syncthreads();
-        stage<HD, HD + 4>(sm.q, qb, ldq, t0, S);
-        stage<HD, HD + 4>(sm.d, db, ldd, t0, S);
+        stage<HD, HD + 4>(sm.q, sm.ql, qb, ldq, t0, S);
+        stage<HD, HD + 4>(sm.d, sm.dl, db, ldd, t0, S);
         for (int e = threadIdx.x; e < BT; e += NT) {
             const bool ok = t0 + e < S;
             sm.lse[e] = ok ? __ldg(lse + ((long)b * H + h) * S + t0 + e) : 0.f;
@@ -317,8 +336,8 @@ __global__ void __launch_bounds__(NT) dkv_kernel(const float* __restrict__ q, lo
         }
         __syncthreads();
         float s[BT / 8][4] = {}, dp[BT / 8][4] = {};
-        gemm_abt<HD, HD + 4, BT / 8>(s, kh, kl, sm.q, g, t);     // S^T[key, query]
-        gemm_abt<HD, HD + 4, BT / 8>(dp, vh, vl, sm.d, g, t);    // dP^T[key, query] = V dO^T
+        gemm_abt<HD, HD + 4, BT / 8>(s, kh, kl, sm.q, sm.ql, g, t);     // S^T[key, query]
+        gemm_abt<HD, HD + 4, BT / 8>(dp, vh, vl, sm.d, sm.dl, g, t);    // dP^T[key, query] = V dO^T
 #pragma unroll
         for (int nt = 0; nt < BT / 8; ++nt)
 #pragma unroll
@@ -338,8 +357,8 @@ __global__ void __launch_bounds__(NT) dkv_kernel(const float* __restrict__ q, lo
         store_c(Ps, s, g, t);
         store_c(Ds, dp, g, t);
         __syncwarp();
-        gemm_pb<HD, HD + 4>(av, Ps, sm.d, g, t);   // dV += P^T dO
-        gemm_pb<HD, HD + 4>(ak, Ds, sm.q, g, t);   // dK += dS^T Q
+        gemm_pb<HD, HD + 4>(av, Ps, sm.d, sm.dl, g, t);   // dV += P^T dO
+        gemm_pb<HD, HD + 4>(ak, Ds, sm.q, sm.ql, g, t);   // dK += dS^T Q
     }
     float* ko = dk + (long)b * S * lddk + h * HD;
     float* vo = dv + (long)b * S * lddv + h * HD;
