@@ -67,6 +67,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
     asm volatile(
@@ -181,6 +188,7 @@ struct FwdParams {
     int B, H, W;
     long ldx;
     int prefetch;             // k-blocks the prefetch warp may run ahead of the TMA producer (0 = off)
+    int w_planes;             // 3xTF32: map_w is a 3-D {K, Cout, 2} map over adjacent hi / lo weight planes
 };
 
 // X3 = 0: one kind::tf32 MMA per k-step (operands truncated to tf32 by the tensor core).
@@ -396,9 +404,8 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 template <int BN, int X3, int STAGES>
 struct PersistSmem {
     alignas(1024) float a[STAGES][BM * BK];
-    alignas(1024) float b[STAGES][BN * BK];
+    alignas(1024) float b[STAGES][X3 ? 2 : 1][BN * BK];      // [stage][hi | lo plane][BN x 32]
     alignas(X3 ? 1024 : 16) float alo[X3 ? STAGES : 1][X3 ? BM * BK : 4];
-    alignas(X3 ? 1024 : 16) float blo[X3 ? STAGES : 1][X3 ? BN * BK : 4];
     alignas(16) float epi[4][32 * EPL];
     // warp-private BatchNorm partial sums (sum | sum of squares per channel of the N tile), plain adds, merged
     // and flushed to global memory once per CTA.  (fp32 slots on the 256-wide tile, where smem is exhausted
@@ -461,7 +468,7 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                         mbar_arrive(&sm.full[s]);
                     } else if (p.dbg == 12) {     // bring-up: weights only
                         mbar_expect_tx(&sm.full[s], (uint32_t)(BN * BK * sizeof(float)));
-                        tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
+                        tma_load_2d(sm.b[s][0], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
                     } else if (p.dbg == 13) {     // bring-up: activations only
                         mbar_expect_tx(&sm.full[s], (uint32_t)(p.TW * p.TH * BK * sizeof(float)));
                         tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 * p.in_stride + p.dw[tap],
@@ -470,8 +477,12 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                     mbar_expect_tx(&sm.full[s], (uint32_t)((p.TW * p.TH + (X3 ? 2 : 1) * BN) * BK * sizeof(float)));
                     tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 * p.in_stride + p.dw[tap],
                                 h0 * p.in_stride + p.dh[tap], img);
-                    tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
-                    if (X3) tma_load_2d(sm.blo[s], &map_wlo, &sm.full[s], p.wk[tap] + c0, n0);
+                    if (X3 && p.w_planes) {       // hi and lo weight planes are adjacent in memory: one 3-D box
+                        tma_load_3d(sm.b[s][0], &map_w, &sm.full[s], p.wk[tap] + c0, n0, 0);
+                    } else {
+                        tma_load_2d(sm.b[s][0], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
+                        if (X3) tma_load_2d(sm.b[s][X3 ? 1 : 0], &map_wlo, &sm.full[s], p.wk[tap] + c0, n0);
+                    }
                     }
                     sm.produced = g + 1;
                 }
@@ -493,10 +504,10 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                     mbar_wait(X3 ? &sm.conv[s] : &sm.full[s], ph);
                     tc_fence_after();
                     const uint64_t da = make_desc(smem_u32(sm.a[s]), 16, 1024);
-                    const uint64_t db = make_desc(smem_u32(sm.b[s]), 16, 1024);
+                    const uint64_t db = make_desc(smem_u32(sm.b[s][0]), 16, 1024);
                     if (X3) {
                         const uint64_t dal = make_desc(smem_u32(sm.alo[s]), 16, 1024);
-                        const uint64_t dbl = make_desc(smem_u32(sm.blo[s]), 16, 1024);
+                        const uint64_t dbl = make_desc(smem_u32(sm.b[s][X3 ? 1 : 0]), 16, 1024);
 #pragma unroll
                         for (int k = 0; k < BK / 8; ++k) {
                             umma_tf32(d, dal + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
@@ -1062,9 +1073,24 @@ DFINE_API int dfine_conv_tc(const float* x, const float* w, const float* w_lo, c
     rc = make_map2(&mw, w, ldw, Cout, ldw, BK, bn, "conv_tc(w)");
     if (rc) return rc;
     mwlo = mw;
+    p.w_planes = 0;
     if (w_lo) {
         rc = make_map2(&mwlo, w_lo, ldw, Cout, ldw, BK, bn, "conv_tc(w_lo)");
         if (rc) return rc;
+        if (persist_bn && w_lo == w + (long)Cout * ldw) {      // dfine_tf32_split planes: fetch both with one box
+            EncodeTiledFn enc = get_encode();
+            cuuint64_t dims[3] = {(cuuint64_t)ldw, (cuuint64_t)Cout, 2};
+            cuuint64_t strides[2] = {(cuuint64_t)ldw * 4, (cuuint64_t)ldw * 4 * Cout};
+            cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)bn, 2};
+            cuuint32_t es[3] = {1, 1, 1};
+            CUtensorMap m3;
+            if (enc && enc(&m3, map_dtype(), 3, (void*)w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+                mw = m3;
+                p.w_planes = 1;
+            }
+        }
     }
     cudaStream_t st = (cudaStream_t)stream;
     static const bool persist = [] { const char* e = getenv("DFINE_TC_PERSIST"); return !(e && e[0] == '0'); }();

@@ -212,7 +212,8 @@ def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, Y
 
 def _split_tf32(w2d):
     """(hi, lo) of a re-laid weight matrix for the 3xTF32 forward (hi = RN tf32, lo = w - hi)."""
-    hi, lo = torch.empty_like(w2d), torch.empty_like(w2d)
+    planes = torch.empty((2,) + tuple(w2d.shape), device=w2d.device, dtype=torch.float32)   # adjacent: one TMA box
+    hi, lo = planes[0], planes[1]
     _check(lib().dfine_tf32_split(_p(w2d), _p(hi), _p(lo), c_long(w2d.numel()), _stream()), "tf32_split")
     return hi, lo
 
