@@ -25,6 +25,52 @@ def _end_step():
     cuda_ops.zero_pool.end_step()
 
 
+class DevicePrefetcher:
+    """Wraps a loader of host batches ``(images, targets, extra)`` (the reference's collate format,
+    dataset.py:651-656) and yields device batches whose pinned host->device copies were issued on a side stream
+    while the previous step was computing — what the reference gets from ``pin_memory`` + ``non_blocking`` copies
+    (train.py:558-565, dataset.py:570-580) only if the copy does not serialise with the step.  One batch ahead."""
+
+    def __init__(self, loader, device):
+        self.loader, self.device = loader, torch.device(device)
+        self.stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _stage(self, batch):
+        x, targets, extra = batch
+        if self.stream is None:
+            return x.to(self.device), [{k: v.to(self.device) for k, v in t.items() if torch.is_tensor(v)} for t in targets], extra, None
+        with torch.cuda.stream(self.stream):
+            x = x.to(self.device, non_blocking=True)
+            targets = [{k: v.to(self.device, non_blocking=True) for k, v in t.items() if torch.is_tensor(v)}
+                       for t in targets]
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return x, targets, extra, ev
+
+    def __iter__(self):
+        it = iter(self.loader)
+        try:
+            nxt = self._stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            x, targets, extra, ev = nxt
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
+                x.record_stream(torch.cuda.current_stream(self.device))
+                for t in targets:
+                    for v in t.values():
+                        v.record_stream(torch.cuda.current_stream(self.device))
+            try:
+                nxt = self._stage(next(it))      # next batch's copies overlap this batch's step
+            except StopIteration:
+                nxt = None
+            yield x, targets, extra
+
+
 class ModelEMA:
     """EMA of every floating-point state entry, momentum m*(1-exp(-it/2000)) (train.py:52-73).
     The reference walks ~920 tensors with two tiny kernels each; here the entries are updated with

@@ -24,7 +24,7 @@ from torch.optim.lr_scheduler import OneCycleLR
 
 from custom_d_fine_b200 import dist as dist_utils
 from custom_d_fine_b200.model import build_loss, build_model, build_optimizer
-from custom_d_fine_b200.train import GraphedTrainStep, ModelEMA, TrainStep  # noqa: F401
+from custom_d_fine_b200.train import DevicePrefetcher, GraphedTrainStep, ModelEMA, TrainStep  # noqa: F401
 
 DEFAULTS = {
     "model_name": "m", "task": "detect", "exp": "b200",
@@ -166,10 +166,8 @@ class Trainer:
         for epoch in range(1, self.epochs + 1):
             self.model.train()
             t0, n_img, losses = time.perf_counter(), 0, []
-            for inputs, targets, _ in self.train_loader:
-                inputs = inputs.to(self.device, non_blocking=True)
-                targets = [{k: v.to(self.device, non_blocking=True) for k, v in t.items() if torch.is_tensor(v)}
-                           for t in targets]
+            # host->device copies of batch k+1 run on a side stream while batch k trains (train.py:558-565)
+            for inputs, targets, _ in DevicePrefetcher(self.train_loader, self.device):
                 loss, _ = self.step(inputs, targets)
                 losses.append(loss)
                 n_img += inputs.shape[0]
