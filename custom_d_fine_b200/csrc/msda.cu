@@ -33,6 +33,11 @@ struct PointSlot {  // one sampling point of one (b,q,h), shared-memory resident
     float dscale_x, dscale_y;  // d(pixel)/d(offset) for the backward chain rule
 };
 
+struct FwdSlot {  // forward only: the four bilinear corners resolved once per point instead of once per lane
+    int tok[4];   // token index of each corner (0 where the corner is outside the map: weight 0, load still legal)
+    float w[4];   // softmax weight x bilinear weight (0 outside)
+};
+
 template <int TPG>
 __device__ __forceinline__ float group_max(float v) {
 #pragma unroll
@@ -47,12 +52,32 @@ __device__ __forceinline__ float group_sum(float v) {
 }
 
 // Phase 1 shared by fwd and bwd.  `lane` = lane inside the group.
-template <int TPG>
+__device__ __forceinline__ void put_slot(PointSlot* slots, int p, const PointSlot& s) { slots[p] = s; }
+__device__ __forceinline__ void put_slot(FwdSlot* slots, int p, const PointSlot& s) {
+    const float xf = floorf(s.x), yf = floorf(s.y);
+    const int x0 = (int)xf, y0 = (int)yf;
+    const float fx = s.x - xf, fy = s.y - yf;
+    const bool vx0 = x0 >= 0 && x0 < s.W, vx1 = x0 + 1 >= 0 && x0 + 1 < s.W;
+    const bool vy0 = y0 >= 0 && y0 < s.H, vy1 = y0 + 1 >= 0 && y0 + 1 < s.H;
+    const int t00 = s.start + y0 * s.W + x0;
+    FwdSlot f;
+    f.tok[0] = (vx0 && vy0) ? t00 : 0;
+    f.tok[1] = (vx1 && vy0) ? t00 + 1 : 0;
+    f.tok[2] = (vx0 && vy1) ? t00 + s.W : 0;
+    f.tok[3] = (vx1 && vy1) ? t00 + s.W + 1 : 0;
+    f.w[0] = (vx0 && vy0) ? s.w * (1.f - fx) * (1.f - fy) : 0.f;
+    f.w[1] = (vx1 && vy0) ? s.w * fx * (1.f - fy) : 0.f;
+    f.w[2] = (vx0 && vy1) ? s.w * (1.f - fx) * fy : 0.f;
+    f.w[3] = (vx1 && vy1) ? s.w * fx * fy : 0.f;
+    slots[p] = f;
+}
+
+template <int TPG, typename SlotT>
 __device__ __forceinline__ void msda_prepare(const MsdaGeom& g, const float* __restrict__ off_row,
                                              const float* __restrict__ logit_row,
                                              const float* __restrict__ ref4,
                                              const float* __restrict__ pscale, float offset_scale,
-                                             int lane, PointSlot* slots) {
+                                             int lane, SlotT* slots) {
     constexpr int NS = MAX_POINTS / TPG;
     float lg[NS];
     float m = -INFINITY;
@@ -95,7 +120,7 @@ __device__ __forceinline__ void msda_prepare(const MsdaGeom& g, const float* __r
             ps_out.H = g.H[l];
             ps_out.dscale_x = sx * (float)g.W[l];
             ps_out.dscale_y = sy * (float)g.H[l];
-            slots[p] = ps_out;
+            put_slot(slots, p, ps_out);
         }
     }
 }
@@ -108,7 +133,7 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(
     int L, float offset_scale) {
     constexpr int D = TPG * 4;
     constexpr int GROUPS = 256 / TPG;
-    __shared__ PointSlot slots[GROUPS][MAX_POINTS];
+    __shared__ __align__(16) FwdSlot slots[GROUPS][MAX_POINTS];
     const int grp = threadIdx.x / TPG, lane = threadIdx.x % TPG;
     const long gid = (long)blockIdx.x * GROUPS + grp;  // (b*Q+q)*heads + h
     const long total = (long)B * Q * heads;
@@ -117,33 +142,26 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(
     const int h = live ? (int)(gid % heads) : 0;
     const int b = (int)(bq / Q);
     // dead groups (tail CTA) run phase 1 on row 0 so that the full-mask shuffles stay convergent
-    msda_prepare<TPG>(g, offsets + bq * off_ld + (long)h * g.P * 2, logits + bq * logit_ld + (long)h * g.P,
+    msda_prepare<TPG, FwdSlot>(g, offsets + bq * off_ld + (long)h * g.P * 2, logits + bq * logit_ld + (long)h * g.P,
                       ref + bq * 4, pscale, offset_scale, lane, slots[grp]);
     __syncwarp();
     if (!live) return;
     const float* vbase = value + ((long)b * L * heads + h) * D + lane * 4;
     const long tok_stride = (long)heads * D;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+    // 2 x LDS.128 + 4 x LDG.128 + 16 FMA per point; two points (8 gathers) in flight per iteration
+#pragma unroll 2
     for (int p = 0; p < g.P; ++p) {
-        const PointSlot s = slots[grp][p];
-        const float xf = floorf(s.x), yf = floorf(s.y);
-        const int x0 = (int)xf, y0 = (int)yf;
-        const float fx = s.x - xf, fy = s.y - yf;
-        const bool vx0 = x0 >= 0 && x0 < s.W, vx1 = x0 + 1 >= 0 && x0 + 1 < s.W;
-        const bool vy0 = y0 >= 0 && y0 < s.H, vy1 = y0 + 1 >= 0 && y0 + 1 < s.H;
-        const float* base = vbase + (long)(s.start + y0 * s.W + x0) * tok_stride;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 v00 = (vx0 && vy0) ? __ldg(reinterpret_cast<const float4*>(base)) : z;
-        const float4 v01 = (vx1 && vy0) ? __ldg(reinterpret_cast<const float4*>(base + tok_stride)) : z;
-        const float4 v10 = (vx0 && vy1) ? __ldg(reinterpret_cast<const float4*>(base + (long)s.W * tok_stride)) : z;
-        const float4 v11 = (vx1 && vy1) ? __ldg(reinterpret_cast<const float4*>(base + (long)(s.W + 1) * tok_stride)) : z;
-        const float w00 = s.w * (1.f - fx) * (1.f - fy), w01 = s.w * fx * (1.f - fy);
-        const float w10 = s.w * (1.f - fx) * fy, w11 = s.w * fx * fy;
-        acc.x += w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x;
-        acc.y += w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y;
-        acc.z += w00 * v00.z + w01 * v01.z + w10 * v10.z + w11 * v11.z;
-        acc.w += w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w;
+        const int4 tk = *reinterpret_cast<const int4*>(slots[grp][p].tok);
+        const float4 w = *reinterpret_cast<const float4*>(slots[grp][p].w);
+        const float4 v00 = __ldg(reinterpret_cast<const float4*>(vbase + (long)tk.x * tok_stride));
+        const float4 v01 = __ldg(reinterpret_cast<const float4*>(vbase + (long)tk.y * tok_stride));
+        const float4 v10 = __ldg(reinterpret_cast<const float4*>(vbase + (long)tk.z * tok_stride));
+        const float4 v11 = __ldg(reinterpret_cast<const float4*>(vbase + (long)tk.w * tok_stride));
+        acc.x += w.x * v00.x + w.y * v01.x + w.z * v10.x + w.w * v11.x;
+        acc.y += w.x * v00.y + w.y * v01.y + w.z * v10.y + w.w * v11.y;
+        acc.z += w.x * v00.z + w.y * v01.z + w.z * v10.z + w.w * v11.z;
+        acc.w += w.x * v00.w + w.y * v01.w + w.z * v10.w + w.w * v11.w;
     }
     *reinterpret_cast<float4*>(out + gid * D + lane * 4) = acc;
 }
@@ -175,7 +193,7 @@ __global__ void __launch_bounds__(256) msda_bwd_kernel(
     const int h = live ? (int)(gid % heads) : 0;
     const int b = (int)(bq / Q);
     // dead groups (tail CTA) run phase 1 on row 0 so that the full-mask shuffles stay convergent
-    msda_prepare<TPG>(g, offsets + bq * off_ld + (long)h * g.P * 2, logits + bq * logit_ld + (long)h * g.P,
+    msda_prepare<TPG, PointSlot>(g, offsets + bq * off_ld + (long)h * g.P * 2, logits + bq * logit_ld + (long)h * g.P,
                       ref + bq * 4, pscale, offset_scale, lane, slots[grp]);
     __syncwarp();
     // NB: no early return before the shuffles below — dead groups run with zero gradients.

@@ -157,7 +157,9 @@ def test_attention(cuda_ops, oracle_ops, S, D, heads, masked):
     def fn(K, qk, v):
         return K.attention(qk, v, heads, None if mask is None else mask.to(qk.device))
 
-    run_both(fn, cuda_ops, oracle_ops, [qk, v], 5e-5, 2e-4)
+    # forward: 3xTF32 logits and P*V (fp32-class).  backward: logits recomputed in 3xTF32, the four gradient
+    # products (dP, dQ, dK, dV) are single round-to-nearest tf32 MMAs like every other gradient GEMM of the library
+    run_both(fn, cuda_ops, oracle_ops, [qk, v], 5e-5, TF32)
 
 
 @pytest.mark.parametrize("D,shapes,points", [(256, [(80, 80), (40, 40), (20, 20)], [3, 6, 3]),
