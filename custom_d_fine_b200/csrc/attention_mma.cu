@@ -294,15 +294,18 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const float* __restrict__ q, lo
                 mx0 = quad_max(mx0);
                 mx1 = quad_max(mx1);
                 const float n0 = fmaxf(mrun[mi][0], mx0), n1 = fmaxf(mrun[mi][1], mx1);
-                const float c0 = (n0 == -INFINITY) ? 1.f : expf(mrun[mi][0] - n0);
-                const float c1 = (n1 == -INFINITY) ? 1.f : expf(mrun[mi][1] - n1);
+                // __expf = ex2.approx(x * log2 e): 2 ulp, one MUFU op instead of expf's ~20 instructions (the softmax,
+                // not the MMAs, was the larger half of this kernel's instruction stream).  A row that has seen only
+                // masked keys has n = -inf: subtract 0 instead, every exponent is then exp(-inf) = 0.
+                const float z0 = (n0 == -INFINITY) ? 0.f : n0, z1 = (n1 == -INFINITY) ? 0.f : n1;
+                const float c0 = __expf(mrun[mi][0] - z0), c1 = __expf(mrun[mi][1] - z1);
                 float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll
                 for (int nt = 0; nt < HT / 8; ++nt)
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        s[mi][nt][j] = (s[mi][nt][j] == -INFINITY) ? 0.f : expf(s[mi][nt][j] - n0);
-                        s[mi][nt][2 + j] = (s[mi][nt][2 + j] == -INFINITY) ? 0.f : expf(s[mi][nt][2 + j] - n1);
+                        s[mi][nt][j] = __expf(s[mi][nt][j] - z0);
+                        s[mi][nt][2 + j] = __expf(s[mi][nt][2 + j] - z1);
                         ps0 += s[mi][nt][j];
                         ps1 += s[mi][nt][2 + j];
                     }
@@ -430,10 +433,10 @@ __global__ void __launch_bounds__(NT) dq_kernel(const float* __restrict__ q, lon
                         if (r1 < S) mask2(mask, r1, key, S, even, b0, b1);
                     }
                     const bool k0 = key < S, k1 = key + 1 < S;
-                    s[mi][nt][0] = (k0 && r0 < S && !a0) ? expf(s[mi][nt][0] - Lr[mi][0]) * (dp[mi][nt][0] - Dr[mi][0]) : 0.f;
-                    s[mi][nt][1] = (k1 && r0 < S && !a1) ? expf(s[mi][nt][1] - Lr[mi][0]) * (dp[mi][nt][1] - Dr[mi][0]) : 0.f;
-                    s[mi][nt][2] = (k0 && r1 < S && !b0) ? expf(s[mi][nt][2] - Lr[mi][1]) * (dp[mi][nt][2] - Dr[mi][1]) : 0.f;
-                    s[mi][nt][3] = (k1 && r1 < S && !b1) ? expf(s[mi][nt][3] - Lr[mi][1]) * (dp[mi][nt][3] - Dr[mi][1]) : 0.f;
+                    s[mi][nt][0] = (k0 && r0 < S && !a0) ? __expf(s[mi][nt][0] - Lr[mi][0]) * (dp[mi][nt][0] - Dr[mi][0]) : 0.f;
+                    s[mi][nt][1] = (k1 && r0 < S && !a1) ? __expf(s[mi][nt][1] - Lr[mi][0]) * (dp[mi][nt][1] - Dr[mi][0]) : 0.f;
+                    s[mi][nt][2] = (k0 && r1 < S && !b0) ? __expf(s[mi][nt][2] - Lr[mi][1]) * (dp[mi][nt][2] - Dr[mi][1]) : 0.f;
+                    s[mi][nt][3] = (k1 && r1 < S && !b1) ? __expf(s[mi][nt][3] - Lr[mi][1]) * (dp[mi][nt][3] - Dr[mi][1]) : 0.f;
                 }
             }
             gemm_pb1<HD, HD + 4, MI>(acc, s, sm.kh2, kb, g, t);
@@ -520,8 +523,8 @@ __global__ void __launch_bounds__(NT) dkv_kernel(const float* __restrict__ q, lo
                         const bool ok0 = in && r0 < S && !(mask && __ldg(mask + (long)qi * S + r0));
                         const bool ok1 = in && r1 < S && !(mask && __ldg(mask + (long)qi * S + r1));
                         const float Lq = sm.lse[qi_l], Dq = sm.dsum[qi_l];
-                        const float p0 = ok0 ? expf(s[mi][nt][j] - Lq) : 0.f;
-                        const float p1 = ok1 ? expf(s[mi][nt][2 + j] - Lq) : 0.f;
+                        const float p0 = ok0 ? __expf(s[mi][nt][j] - Lq) : 0.f;
+                        const float p1 = ok1 ? __expf(s[mi][nt][2 + j] - Lq) : 0.f;
                         s[mi][nt][j] = p0;
                         s[mi][nt][2 + j] = p1;
                         dp[mi][nt][j] = p0 * (dp[mi][nt][j] - Dq);

@@ -28,6 +28,7 @@
 // of hanging the device.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <mutex>
 #include <cstdlib>
 
@@ -112,6 +113,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -151,6 +161,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn, int b_mn) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// the same for kind::f16 with bf16 operands (a_format = b_format = 1), K-major, D = f32
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// {hi, lo} bf16 pair of an fp32 value: hi = RN bf16(x), lo = RN bf16(x - hi); x = hi + lo up to 2^-17 relative
+__device__ __forceinline__ void bf16_split(float x, uint32_t& hi, uint32_t& lo) {
+    const uint32_t h = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x));
+    const float r = x - __uint_as_float(h << 16);
+    hi = h;
+    lo = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(r));
 }
 
 constexpr int BM = 128, BK = 32;
@@ -401,11 +423,21 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     return v;
 }
 
+// X3 = 2: error-compensated "3xBF16": a = a_hi + a_lo, w = w_hi + w_lo with bf16 parts (16 mantissa bits per
+//         operand, products exact in the fp32 accumulator; dropped a_lo*w_lo and representation terms 2^-17 relative).
+//         Same three MMAs per k-step as 3xTF32 but kind::f16 runs at twice the tf32 rate and both bf16 planes of
+//         an operand take the bytes of ONE fp32 plane: half the tensor time and 2/3 of the L2->SM bytes of X3 = 1.
+//         The fp32 activation tile lands by TMA (128-byte swizzle) and four converter warps write its bf16 hi / lo
+//         planes (64-byte rows, 64-byte swizzle); weights arrive pre-split as bf16 planes.
 template <int BN, int X3, int STAGES>
 struct PersistSmem {
-    alignas(1024) float a[STAGES][BM * BK];
-    alignas(1024) float b[STAGES][X3 ? 2 : 1][BN * BK];      // [stage][hi | lo plane][BN x 32]
-    alignas(X3 ? 1024 : 16) float alo[X3 ? STAGES : 1][X3 ? BM * BK : 4];
+    static constexpr int B_PLANE = X3 == 2 ? BN * BK * 2 : BN * BK * 4;        // bytes of one weight plane
+    static constexpr int B_BYTES = (X3 ? 2 : 1) * B_PLANE;                       // [hi | lo]
+    static constexpr int A2_PLANE = X3 == 2 ? BM * BK * 2 : BM * BK * 4;
+    static constexpr int A2_BYTES = X3 == 1 ? A2_PLANE : (X3 == 2 ? 2 * A2_PLANE : 16);   // tf32 lo | bf16 hi + lo
+    alignas(1024) float a[STAGES][BM * BK];                                      // TMA landing buffer (fp32)
+    alignas(1024) uint8_t b[STAGES][B_BYTES];
+    alignas(X3 ? 1024 : 16) uint8_t a2[X3 ? STAGES : 1][A2_BYTES];
     alignas(16) float epi[4][32 * EPL];
     // warp-private BatchNorm partial sums (sum | sum of squares per channel of the N tile), plain adds, merged
     // and flushed to global memory once per CTA.  (fp32 slots on the 256-wide tile, where smem is exhausted
@@ -468,20 +500,20 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                         mbar_arrive(&sm.full[s]);
                     } else if (p.dbg == 12) {     // bring-up: weights only
                         mbar_expect_tx(&sm.full[s], (uint32_t)(BN * BK * sizeof(float)));
-                        tma_load_2d(sm.b[s][0], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
+                        tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
                     } else if (p.dbg == 13) {     // bring-up: activations only
                         mbar_expect_tx(&sm.full[s], (uint32_t)(p.TW * p.TH * BK * sizeof(float)));
                         tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 * p.in_stride + p.dw[tap],
                                     h0 * p.in_stride + p.dh[tap], img);
                     } else {
-                    mbar_expect_tx(&sm.full[s], (uint32_t)((p.TW * p.TH + (X3 ? 2 : 1) * BN) * BK * sizeof(float)));
+                    mbar_expect_tx(&sm.full[s], (uint32_t)(p.TW * p.TH * BK * sizeof(float)) + (uint32_t)Smem::B_BYTES);
                     tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 * p.in_stride + p.dw[tap],
                                 h0 * p.in_stride + p.dh[tap], img);
-                    if (X3 && p.w_planes) {       // hi and lo weight planes are adjacent in memory: one 3-D box
-                        tma_load_3d(sm.b[s][0], &map_w, &sm.full[s], p.wk[tap] + c0, n0, 0);
+                    if (X3 == 2 || (X3 && p.w_planes)) {   // hi and lo weight planes are adjacent in memory: one 3-D box
+                        tma_load_3d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0, n0, 0);
                     } else {
-                        tma_load_2d(sm.b[s][0], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
-                        if (X3) tma_load_2d(sm.b[s][X3 ? 1 : 0], &map_wlo, &sm.full[s], p.wk[tap] + c0, n0);
+                        tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
+                        if (X3) tma_load_2d(sm.b[s] + Smem::B_PLANE, &map_wlo, &sm.full[s], p.wk[tap] + c0, n0);
                     }
                     }
                     sm.produced = g + 1;
@@ -504,10 +536,24 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                     mbar_wait(X3 ? &sm.conv[s] : &sm.full[s], ph);
                     tc_fence_after();
                     const uint64_t da = make_desc(smem_u32(sm.a[s]), 16, 1024);
-                    const uint64_t db = make_desc(smem_u32(sm.b[s][0]), 16, 1024);
-                    if (X3) {
-                        const uint64_t dal = make_desc(smem_u32(sm.alo[s]), 16, 1024);
-                        const uint64_t dbl = make_desc(smem_u32(sm.b[s][X3 ? 1 : 0]), 16, 1024);
+                    const uint64_t db = make_desc(smem_u32(sm.b[s]), 16, 1024);
+                    if constexpr (X3 == 2) {
+                        // bf16 planes: 64-byte rows (32 channels), 64-byte swizzle (layout 4), 8-row atoms of 512 B;
+                        // UMMA_K = 16 bf16 = 32 bytes -> +2 in 16-byte units per k-step
+                        constexpr uint32_t idesc16 = make_idesc_bf16(BN);
+                        const uint64_t ah = make_desc(smem_u32(sm.a2[s]), 16, 512, 4);
+                        const uint64_t al = make_desc(smem_u32(sm.a2[s] + Smem::A2_PLANE), 16, 512, 4);
+                        const uint64_t bh = make_desc(smem_u32(sm.b[s]), 16, 512, 4);
+                        const uint64_t bl = make_desc(smem_u32(sm.b[s] + Smem::B_PLANE), 16, 512, 4);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            umma_bf16(d, al + 2 * k, bh + 2 * k, idesc16, (kb | k) != 0);
+                            umma_bf16(d, ah + 2 * k, bl + 2 * k, idesc16, 1);
+                            umma_bf16(d, ah + 2 * k, bh + 2 * k, idesc16, 1);
+                        }
+                    } else if constexpr (X3 == 1) {
+                        const uint64_t dal = make_desc(smem_u32(sm.a2[s]), 16, 1024);
+                        const uint64_t dbl = make_desc(smem_u32(sm.b[s] + Smem::B_PLANE), 16, 1024);
 #pragma unroll
                         for (int k = 0; k < BK / 8; ++k) {
                             umma_tf32(d, dal + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
@@ -656,22 +702,47 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
             for (int kb = 0; kb < num_k; ++kb, ++g) {
                 const int s = g % STAGES, ph = (g / STAGES) & 1;
                 mbar_wait(&sm.full[s], ph);
-                const uint32_t a_base = smem_u32(sm.a[s]), l_base = smem_u32(sm.alo[s]);
+                const uint32_t a_base = smem_u32(sm.a[s]), l_base = smem_u32(sm.a2[s]);
+                if constexpr (X3 == 2) {
+                    // fp32 tile: 128-byte rows, 16-byte chunk j of row r at physical chunk j ^ (r & 7).  bf16 planes:
+                    // 64-byte rows, 16-byte chunk c (channels 8c..8c+7) at physical chunk c ^ ((r >> 1) & 3).  The two
+                    // fp32 chunks of one bf16 chunk are the physical PAIR k = c ^ ((r & 7) >> 1) — the very index
+                    // of the destination chunk — in swapped order on odd rows.  So item idx = 4 r + k reads 32
+                    // contiguous bytes at idx * 32 and writes 16 contiguous bytes at idx * 16 of each plane.
 #pragma unroll
-                for (int i = 0; i < BM * BK / 4 / 128; ++i) {
-                    const uint32_t off = (uint32_t)(ct + i * 128) * 16u;
-                    float4 v;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a_base + off) : "memory");
-                    float4 hi, lo;
-                    hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
-                    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
-                    if (p.dbg == 1) { lo = v; hi = make_float4(0.f, 0.f, 0.f, 0.f); }       // everything through alo
-                    if (p.dbg == 3) { lo = make_float4(0.f, 0.f, 0.f, 0.f); hi = make_float4(0.f, 0.f, 0.f, 0.f); }
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + off), "f"(hi.x), "f"(hi.y),
-                                 "f"(hi.z), "f"(hi.w) : "memory");
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(l_base + off), "f"(lo.x), "f"(lo.y),
-                                 "f"(lo.z), "f"(lo.w) : "memory");
+                    for (int i = 0; i < BM * 4 / 128; ++i) {
+                        const uint32_t idx = (uint32_t)(ct + i * 128);
+                        float4 v0 = lds128(a_base + idx * 32u), v1 = lds128(a_base + idx * 32u + 16u);
+                        if ((idx >> 2) & 1) { const float4 tmp = v0; v0 = v1; v1 = tmp; }
+                        uint32_t h[8], l[8];
+                        bf16_split(v0.x, h[0], l[0]); bf16_split(v0.y, h[1], l[1]);
+                        bf16_split(v0.z, h[2], l[2]); bf16_split(v0.w, h[3], l[3]);
+                        bf16_split(v1.x, h[4], l[4]); bf16_split(v1.y, h[5], l[5]);
+                        bf16_split(v1.z, h[6], l[6]); bf16_split(v1.w, h[7], l[7]);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(l_base + idx * 16u),
+                                     "r"(h[0] | (h[1] << 16)), "r"(h[2] | (h[3] << 16)), "r"(h[4] | (h[5] << 16)),
+                                     "r"(h[6] | (h[7] << 16)) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(l_base + (uint32_t)Smem::A2_PLANE + idx * 16u),
+                                     "r"(l[0] | (l[1] << 16)), "r"(l[2] | (l[3] << 16)), "r"(l[4] | (l[5] << 16)),
+                                     "r"(l[6] | (l[7] << 16)) : "memory");
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < BM * BK / 4 / 128; ++i) {
+                        const uint32_t off = (uint32_t)(ct + i * 128) * 16u;
+                        float4 v;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a_base + off) : "memory");
+                        float4 hi, lo;
+                        hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+                        lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+                        if (p.dbg == 1) { lo = v; hi = make_float4(0.f, 0.f, 0.f, 0.f); }       // everything through alo
+                        if (p.dbg == 3) { lo = make_float4(0.f, 0.f, 0.f, 0.f); hi = make_float4(0.f, 0.f, 0.f, 0.f); }
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + off), "f"(hi.x), "f"(hi.y),
+                                     "f"(hi.z), "f"(hi.w) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(l_base + off), "f"(lo.x), "f"(lo.y),
+                                     "f"(lo.z), "f"(lo.w) : "memory");
+                    }
                 }
                 fence_proxy_async();
                 mbar_arrive(&sm.conv[s]);
@@ -1031,16 +1102,19 @@ DFINE_API int dfine_conv_tc_supported(int Cin, int Cout, int KH, int KW, int str
 // zeroed by the caller) receives per-channel sum / sum of squares of the raw accumulator (train-mode BatchNorm).
 // w_lo == null: plain kind::tf32.  w_lo != null: 3xTF32 — `w` must then hold tf32-rounded weights and w_lo the
 // remainders (dfine_tf32_split); activations are split inside the kernel.  nn.Linear on [rows, K]: B=1, H=1, W=rows.
-DFINE_API int dfine_conv_tc(const float* x, const float* w, const float* w_lo, const float* bias, float* y,
-                            double* stats, int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy,
-                            int YH, int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
-                            const int* taps, long ldw, int act, void* stream) {
+namespace {
+int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* w_bf16, const float* bias, float* y,
+                 double* stats, int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy,
+                 int YH, int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
+                 const int* taps, long ldw, int act, void* stream) {
     DFINE_REQUIRE(n_taps >= 1 && n_taps <= MAX_TAPS, "conv_tc: %d taps unsupported", n_taps);
     DFINE_REQUIRE(in_stride == 1 || in_stride == 2, "conv_tc: input stride %d unsupported", in_stride);
-    DFINE_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldw % 4 == 0 && Cin >= 4 && Cout >= 4,
+    DFINE_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldw % (w_bf16 ? 8 : 4) == 0 &&
+                      Cin >= 4 && Cout >= 4,
                   "conv_tc: unsupported geometry Cin=%d Cout=%d ldx=%ld ldy=%ld ldw=%ld", Cin, Cout, ldx, ldy, ldw);
     DFINE_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)y % 16) == 0 &&
-                      ((uintptr_t)w_lo % 16) == 0 && (!bias || ((uintptr_t)bias % 16) == 0),
+                      ((uintptr_t)w_lo % 16) == 0 && ((uintptr_t)w_bf16 % 16) == 0 &&
+                      (!bias || ((uintptr_t)bias % 16) == 0),
                   "conv_tc: pointers must be 16-byte aligned");
     if ((long)B * OH * OW == 0) return 0;
     FwdParams p;
@@ -1064,8 +1138,34 @@ DFINE_API int dfine_conv_tc(const float* x, const float* w, const float* w_lo, c
     // TFLOAT32 maps make the TMA unit round fp32 -> tf32 (nearest) while it copies: right for the plain path,
     // but the 3xTF32 converter needs the untouched fp32 activations to form a_lo = a - tf32(a)
     int rc = make_map4(&mx, x, Cin, W, H, B, ldx, BK, p.TW, p.TH, in_stride, "conv_tc(x)", CU_TENSOR_MAP_SWIZZLE_128B,
-                       w_lo ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : map_dtype());
+                       (w_lo || w_bf16) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : map_dtype());
     if (rc) return rc;
+    if (w_bf16) {
+        // 3xBF16: weights are two adjacent bf16 planes [2][Cout][ldw] (dfine_bf16_split); one 3-D box
+        // {32 k, bn rows, 2 planes} with the 64-byte swizzle lands as [plane][row][64 B]
+        const int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
+        EncodeTiledFn enc = get_encode();
+        if (!enc) { dfine_set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return -2; }
+        cuuint64_t dims[3] = {(cuuint64_t)ldw, (cuuint64_t)Cout, 2};
+        cuuint64_t strides[2] = {(cuuint64_t)ldw * 2, (cuuint64_t)ldw * 2 * Cout};
+        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)bn, 2};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_bf16), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            dfine_set_error("conv_tc: cuTensorMapEncodeTiled(bf16 planes) failed (%d) ldw=%ld Cout=%d", (int)r, ldw, Cout);
+            return -2;
+        }
+        p.w_planes = 1;
+        cudaStream_t st = (cudaStream_t)stream;
+        rc = bn == 32 ? launch_persist<32, 2, 4>(mx, mw, mw, y, bias, stats, p, B, st)
+           : bn == 64 ? launch_persist<64, 2, 4>(mx, mw, mw, y, bias, stats, p, B, st)
+                      : launch_persist<128, 2, 4>(mx, mw, mw, y, bias, stats, p, B, st);
+        if (rc) return rc;
+        DFINE_LAUNCH_CHECK("conv_tc(bf16x3)");
+        return 0;
+    }
     static const bool persist_bn = [] { const char* e = getenv("DFINE_TC_PERSIST"); return !(e && e[0] == '0'); }();
     // N tile: one tile covers Cout when it can (the A patch is then read exactly once); 256-wide tiles only on
     // the persistent plain-tf32 kernel (its smem ring has room for 48 KB stages)
@@ -1116,6 +1216,57 @@ DFINE_API int dfine_conv_tc(const float* x, const float* w, const float* w_lo, c
     }
     if (rc) return rc;
     DFINE_LAUNCH_CHECK("conv_tc");
+    return 0;
+}
+}  // namespace
+
+DFINE_API int dfine_conv_tc(const float* x, const float* w, const float* w_lo, const float* bias, float* y,
+                            double* stats, int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy,
+                            int YH, int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
+                            const int* taps, long ldw, int act, void* stream) {
+    return conv_tc_impl(x, w, w_lo, nullptr, bias, y, stats, B, H, W, Cin, ldx, OH, OW, Cout, ldy, YH, YW, osy, osx, ooy,
+                        oox, in_stride, n_taps, taps, ldw, act, stream);
+}
+
+// The same contract with error-compensated 3xBF16 operands (see PersistSmem): `w_planes` = the two bf16 planes
+// [2][Cout][ldw] written by dfine_bf16_split (each tap's channels padded to a multiple of 8, so ldw % 8 == 0 and
+// the taps' weight offsets wk[] are multiples of 8); activations are split in the kernel.
+DFINE_API int dfine_conv_tc_bf16x3(const float* x, const void* w_planes, const float* bias, float* y, double* stats,
+                                   int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy, int YH,
+                                   int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
+                                   const int* taps, long ldw, int act, void* stream) {
+    DFINE_REQUIRE(w_planes != nullptr, "conv_tc_bf16x3: null weight planes");
+    return conv_tc_impl(x, nullptr, nullptr, w_planes, bias, y, stats, B, H, W, Cin, ldx, OH, OW, Cout, ldy, YH, YW, osy,
+                        osx, ooy, oox, in_stride, n_taps, taps, ldw, act, stream);
+}
+
+// The weight half of the 3xBF16 split.  w: [rows][taps * Cin] fp32 (row stride ldw); planes: [2][rows][taps * Cin_p]
+// bf16 with every tap's channel run padded to Cin_p = Cin rounded up to 8 (a TMA box must start on a 16-byte
+// boundary: tap * Cin_p * 2 bytes); planes[0] = RN bf16(w), planes[1] = RN bf16(w - planes[0]), pads zero.
+namespace {
+__global__ void bf16_split_kernel(const float* __restrict__ w, long ldw, unsigned short* __restrict__ planes,
+                                  long rows, int taps, int Cin, int Cin_p) {
+    const long ldp = (long)taps * Cin_p, n = rows * ldp;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / ldp;
+        const int k = (int)(i % ldp), tap = k / Cin_p, c = k % Cin_p;
+        uint32_t hi = 0, lo = 0;
+        if (c < Cin) bf16_split(w[r * ldw + (long)tap * Cin + c], hi, lo);
+        planes[i] = (unsigned short)hi;
+        planes[n + i] = (unsigned short)lo;
+    }
+}
+}  // namespace
+DFINE_API int dfine_bf16_split(const float* w, long ldw, void* planes, long rows, int taps, int Cin, int Cin_p,
+                               void* stream) {
+    DFINE_REQUIRE(Cin_p >= Cin && Cin_p % 8 == 0 && taps >= 1 && ((uintptr_t)planes % 16) == 0,
+                  "bf16_split: Cin=%d Cin_p=%d taps=%d", Cin, Cin_p, taps);
+    const long n = rows * taps * Cin_p;
+    if (n == 0) return 0;
+    long g = (n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    bf16_split_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w, ldw, (unsigned short*)planes, rows, taps, Cin, Cin_p);
+    DFINE_LAUNCH_CHECK("bf16_split");
     return 0;
 }
 

@@ -129,6 +129,21 @@ class _ZeroPool:
 zero_pool = _ZeroPool()
 
 
+_scalar_cache = {}
+
+
+def _as_dev_scalar(v, device):
+    """A [1] fp32 device tensor for a kernel that reads the scalar from memory (tensors pass through; python
+    numbers are uploaded once per value and cached — a pageable H2D copy is not graph-capturable)."""
+    if isinstance(v, torch.Tensor):
+        return v
+    key = (float(v), str(device))
+    t = _scalar_cache.get(key)
+    if t is None:
+        t = _scalar_cache[key] = torch.full((1,), float(v), device=device, dtype=torch.float32)
+    return t
+
+
 def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -164,6 +179,8 @@ def _rows(x):
 # Dense conv / linear shapes the tcgen05 kernels accept run on tensor cores.  Modes (env DFINE_GEMM / set_gemm_mode):
 #   "tc3"  (default) forward GEMMs as error-compensated 3xTF32 (fp32-class accuracy: the parity mode of the
 #          tensor-core path), data / weight gradients as plain kind::tf32;
+#   "bf3"  forward GEMMs as error-compensated 3xBF16 (two bf16 parts per operand = 16 mantissa bits, three
+#          kind::f16 MMAs at twice the tf32 rate; ~1e-5 relative), gradients as in "tc3";
 #   "tc"   plain kind::tf32 everywhere (the precision class of the reference's cuDNN convolutions on GPU);
 #   "simt" fp32 CUDA-core kernels of the same library (strict-fp32 parity runs and kernel bring-up).
 _MODE = os.environ.get("DFINE_GEMM", "tc3")
@@ -171,7 +188,7 @@ _MODE = os.environ.get("DFINE_GEMM", "tc3")
 
 def set_gemm_mode(mode: str) -> None:
     global _MODE
-    if mode not in ("tc", "tc3", "simt"):
+    if mode not in ("tc", "tc3", "bf3", "simt"):
         raise ValueError(mode)
     _MODE = mode
 
@@ -200,14 +217,20 @@ def _taps(key, make):
 
 
 def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, YH, YW, os_, oo, in_stride, taps, act,
-               stats, what):
+               stats, what, bf16_planes=None):
     arr, n = taps
     # algorithmic bytes: input pixels + output pixels + weights, each touched once, fp32
     nbytes = 4 * (B * min(H * W, OH * OW * in_stride * in_stride) * Cin + B * OH * OW * Cout + Cout * n * Cin)
     with _timed("conv_tc", nbytes):
-        _check(lib().dfine_conv_tc(_p(x), _p(w), _p(w_lo), _p(bias), _p(y), _p(stats), B, H, W, Cin, c_long(ldx), OH,
-                                   OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0], oo[1], in_stride, n, arr,
-                                   c_long(ldw), act, _stream()), what)
+        if bf16_planes is not None:
+            _check(lib().dfine_conv_tc_bf16x3(_p(x), _p(bf16_planes), _p(bias), _p(y), _p(stats), B, H, W, Cin,
+                                              c_long(ldx), OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0],
+                                              oo[1], in_stride, n, arr, c_long(bf16_planes.shape[-1]), act, _stream()),
+                   what)
+        else:
+            _check(lib().dfine_conv_tc(_p(x), _p(w), _p(w_lo), _p(bias), _p(y), _p(stats), B, H, W, Cin, c_long(ldx),
+                                       OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0], oo[1], in_stride, n,
+                                       arr, c_long(ldw), act, _stream()), what)
 
 
 def _split_tf32(w2d):
@@ -216,6 +239,17 @@ def _split_tf32(w2d):
     hi, lo = planes[0], planes[1]
     _check(lib().dfine_tf32_split(_p(w2d), _p(hi), _p(lo), c_long(w2d.numel()), _stream()), "tf32_split")
     return hi, lo
+
+
+def _split_bf16(w2d, taps, Cin):
+    """bf16 (hi, lo) planes [2, rows, taps * Cin_p] of a re-laid weight matrix [rows, taps * Cin] for the 3xBF16
+    forward; Cin_p = Cin rounded up to 8 elements (every tap starts on a 16-byte boundary for TMA; pads are zero)."""
+    rows = w2d.shape[0]
+    cin_p = (Cin + 7) // 8 * 8
+    planes = torch.empty((2, rows, taps * cin_p), device=w2d.device, dtype=torch.bfloat16)
+    _check(lib().dfine_bf16_split(_p(w2d), c_long(w2d.shape[1]), _p(planes), c_long(rows), taps, Cin, cin_p, _stream()),
+           "bf16_split")
+    return planes
 
 
 # ------------------------------------------------------------------------------------------------
@@ -228,15 +262,23 @@ def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None):
     if _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy):
         K = k * k * Cin
         wr = wkey("wr", lambda: weight.reshape(Cout, Cin, k, k).permute(0, 2, 3, 1).reshape(Cout, K).contiguous())
-        w_hi, w_lo = wr, None
+        w_hi, w_lo, planes = wr, None, None
         if _MODE == "tc3":
             w_hi, w_lo = wkey("wr3", lambda: _split_tf32(wr))
-        taps = _taps(("f", k, pad[0], pad[1], Cin),
-                     lambda: [(kh - pad[0], kw - pad[1], (kh * k + kw) * Cin) for kh in range(k) for kw in range(k)])
+        elif _MODE == "bf3":
+            planes = wkey("wrb", lambda: _split_bf16(wr, k * k, Cin))
+        cs = Cin if planes is None else (Cin + 7) // 8 * 8        # channel run of one tap in the weight matrix
+        taps = _taps(("f", k, pad[0], pad[1], cs),
+                     lambda: [(kh - pad[0], kw - pad[1], (kh * k + kw) * cs) for kh in range(k) for kw in range(k)])
         _tc_launch(x, ldx, H, W, Cin, w_hi, w_lo, K, bias, y, ldy, B, OH, OW, Cout, OH, OW, (1, 1), (0, 0), stride,
-                   taps, act, stats, "conv_fwd_tc")
+                   taps, act, stats, "conv_fwd_tc", planes)
         return True
     wr = wkey("wr", lambda: weight.reshape(Cout, Cin, k, k).permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous())
+    if bias is None and act == 0 and _MODE != "simt" and \
+            lib().dfine_stem_conv_supported(Cin, Cout, k, k, stride, pad[0], pad[1], pad[2], pad[3], c_long(ldy)):
+        _check(lib().dfine_stem_conv_fwd(_p(x), c_long(ldx), _p(wr), _p(y), c_long(ldy), B, H, W, Cout, _stream()),
+               "stem_conv_fwd")
+        return False
     _check(lib().dfine_conv_fwd_simt(_p(x), _p(wr), _p(bias), _p(y), B, H, W, Cin, OH, OW, Cout, k, k, stride,
                                      pad[0], pad[1], c_long(ldx), c_long(ldy), act, _stream()), "conv_fwd_simt")
     return False
@@ -299,6 +341,10 @@ def _conv_wgrad(dy, ldy, x, ldx, geom, dst=None):
         with _timed("conv_wgrad_tc", nbytes):
             _check(lib().dfine_conv_wgrad_tc(_p(dy), _p(x), _p(dwr), B, H, W, Cin, OH, OW, Cout, k, k, stride, pad[0],
                                              pad[1], c_long(ldx), c_long(ldy), _stream()), "conv_wgrad_tc")
+    elif _MODE != "simt" and lib().dfine_stem_conv_supported(Cin, Cout, k, k, stride, pad[0], pad[1], pad[2], pad[3],
+                                                              c_long(ldy)):
+        _check(lib().dfine_stem_conv_wgrad(_p(dy), c_long(ldy), _p(x), c_long(ldx), _p(dwr), B, H, W, Cout, _stream()),
+               "stem_conv_wgrad")
     else:
         _check(lib().dfine_conv_wgrad_simt(_p(dy), _p(x), _p(dwr), B, H, W, Cin, OH, OW, Cout, k, k, stride, pad[0],
                                            pad[1], c_long(ldx), c_long(ldy), _stream()), "conv_wgrad_simt")
@@ -656,6 +702,40 @@ class _Msda(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+# FDR head: Integral + distance2bbox + LQE statistics in one pass over pred_corners
+# ------------------------------------------------------------------------------------------------
+class _FdrHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, corners, ref, project, reg_scale, k, want_box, want_stat):
+        _req_cuda(corners, ref, project, reg_scale)
+        corners = corners.contiguous()
+        NB = project.shape[0]
+        rows = corners.numel() // (4 * NB)
+        ref = ref.detach().contiguous().float()
+        project = project.detach().contiguous().float()
+        rs = reg_scale.detach().reshape(-1).float().contiguous()      # device scalar: no host read, graph-capturable
+        lead = tuple(corners.shape[:-1])
+        box = torch.empty(lead + (4,), device=corners.device, dtype=torch.float32) if want_box else None
+        stat = torch.empty(lead + (4 * (k + 1),), device=corners.device, dtype=torch.float32) if want_stat else None
+        _check(lib().dfine_fdr_head_fwd(_p(corners), _p(ref), _p(project), _p(rs), _p(box), _p(stat), c_long(rows), NB,
+                                        k, _stream()), "fdr_head_fwd")
+        ctx.save_for_backward(corners, ref, project, rs)
+        ctx.meta = (rows, NB, k)
+        return box, stat
+
+    @staticmethod
+    def backward(ctx, dbox, dstat):
+        corners, ref, project, rs = ctx.saved_tensors
+        rows, NB, k = ctx.meta
+        dbox = dbox.contiguous() if dbox is not None else None
+        dstat = dstat.contiguous() if dstat is not None else None
+        dcorners = torch.empty_like(corners)
+        _check(lib().dfine_fdr_head_bwd(_p(corners), _p(ref), _p(project), _p(rs), _p(dbox), _p(dstat), _p(dcorners),
+                                        c_long(rows), NB, k, _stream()), "fdr_head_bwd")
+        return dcorners, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
 # small spatial ops
 # ------------------------------------------------------------------------------------------------
 class _MaxPool(torch.autograd.Function):
@@ -748,23 +828,16 @@ class CudaOps:
         return g1 * x1 + g2 * x2
 
     def fdr_decode(self, corners, ref, project, reg_scale):
-        shape = corners.shape
-        nb = project.shape[0]
-        p = torch.softmax(corners.reshape(-1, nb), dim=1)
-        d = (p @ project.to(p.dtype)).reshape(list(shape[:-1]) + [4])
-        rs = abs(reg_scale)
-        sw, sh = ref[..., 2] / rs, ref[..., 3] / rs
-        x1 = ref[..., 0] - (0.5 * rs + d[..., 0]) * sw
-        y1 = ref[..., 1] - (0.5 * rs + d[..., 1]) * sh
-        x2 = ref[..., 0] + (0.5 * rs + d[..., 2]) * sw
-        y2 = ref[..., 1] + (0.5 * rs + d[..., 3]) * sh
-        return torch.stack([(x1 + x2) / 2, (y1 + y2) / 2, x2 - x1, y2 - y1], -1)
+        return _FdrHead.apply(corners, ref, project, _as_dev_scalar(reg_scale, corners.device), 0, True, False)[0]
 
     def lqe_stat(self, corners, k, reg_max):
-        B, L, _ = corners.shape
-        prob = torch.softmax(corners.reshape(B, L, 4, reg_max + 1), dim=-1)
-        top, _ = prob.topk(k, dim=-1)
-        return torch.cat([top, top.mean(dim=-1, keepdim=True)], -1).reshape(B, L, -1)
+        one = _as_dev_scalar(1.0, corners.device)
+        dummy = torch.zeros(reg_max + 1, device=corners.device, dtype=torch.float32)
+        return _FdrHead.apply(corners, corners.new_zeros(corners.shape[:-1] + (4,)), dummy, one, k, False, True)[1]
+
+    def fdr_head(self, corners, ref, project, reg_scale, k):
+        """(boxes, LQE statistics) of one decoder layer from one pass over pred_corners."""
+        return _FdrHead.apply(corners, ref, project, _as_dev_scalar(reg_scale, corners.device), k, True, True)
 
     def mask_dot(self, embed, feat_nhwc):
         raise NotImplementedError("segmentation head is a SURVEY §8(f) 'next' row")

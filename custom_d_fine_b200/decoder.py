@@ -126,8 +126,10 @@ class LQEParams(nn.Module):
         init.constant_(self.reg_conf.layers[-1].bias, 0)
         init.constant_(self.reg_conf.layers[-1].weight, 0)
 
-    def forward(self, scores, corners):
-        return scores + self.reg_conf(K.lqe_stat(corners, self.k, self.reg_max))
+    def forward(self, scores, corners, stat=None):
+        if stat is None:
+            stat = K.lqe_stat(corners, self.k, self.reg_max)
+        return scores + self.reg_conf(stat)
 
 
 class DecoderStack(nn.Module):
@@ -160,10 +162,14 @@ class DecoderStack(nn.Module):
             corners = bbox_head[i](out if out_detach is None else out + out_detach)
             if corners_prev is not None:
                 corners = corners + corners_prev
-            box = K.fdr_decode(corners, ref_initial, project, self.reg_scale)
-            if self.training or i == self.eval_idx:
+            need_scores = self.training or i == self.eval_idx
+            if need_scores:      # boxes and LQE statistics from one pass over the corner logits
+                box, stat = K.fdr_head(corners, ref_initial, project, self.reg_scale, self.lqe_layers[i].k)
+            else:
+                box = K.fdr_decode(corners, ref_initial, project, self.reg_scale)
+            if need_scores:
                 s = K.linear(out, score_head[i].weight, score_head[i].bias)
-                logits.append(self.lqe_layers[i](s, corners))
+                logits.append(self.lqe_layers[i](s, corners, stat))
                 boxes.append(box)
                 corners_all.append(corners)
                 refs.append(ref_initial)
@@ -366,12 +372,14 @@ class DFINETransformer(nn.Module):
         _, top = torch.topk(enc_logits.max(-1).values, self.num_queries, dim=-1)
         bidx = torch.arange(memory.shape[0], device=memory.device)[:, None]
         top_anchor = anchors[0][top] if anchors.shape[0] == 1 else anchors[bidx, top]
-        top_mem = om[bidx, top]
+        # torch.gather, not om[bidx, top]: same values, but the backward is a scatter_add (the indices of one image
+        # are distinct) instead of index_put(accumulate)'s sort-based kernel (0.66 ms per step at batch 16)
+        top_mem = om.gather(1, top[..., None].expand(-1, -1, om.shape[-1]))
         box_unact = self.enc_bbox_head(top_mem) + top_anchor
         enc_boxes, enc_logits_l = [], []
         if self.training:
             enc_boxes.append(torch.sigmoid(box_unact))
-            enc_logits_l.append(enc_logits[bidx, top])
+            enc_logits_l.append(enc_logits.gather(1, top[..., None].expand(-1, -1, enc_logits.shape[-1])))
         content = top_mem.detach()
         box_unact = box_unact.detach()
         if dn_box_unact is not None:

@@ -7,6 +7,9 @@ Tolerances (BASELINE.json north_star: 1e-3 relative on logits / boxes).
           one-to-one with the reference's, 1e-3 relative (x3 slack) on every loss term.
   "tc3"   the product default — tcgen05 forward GEMMs as error-compensated 3xTF32, tf32 gradients: the same
           1e-3 bars on the forward quantities.
+  "bf3"   forward GEMMs as error-compensated 3xBF16 (16 mantissa bits per operand, measured 4e-6 .. 6e-6 per GEMM
+          against 2e-7 .. 8e-6 for 3xTF32): the seeded network amplifies that to 2.3e-3 on logits / boxes, so this
+          optional faster mode is held to 4e-3 and is NOT the default (tc3 is).
   "tc"    plain kind::tf32 (the precision class of the reference's own GPU convolutions, cuDNN allow_tf32):
           on this deliberately ill-conditioned seeded network the top-300 query selection is discontinuous, so
           10-bit operands change the selected set; only the loss terms (6 %) and gradients are compared.
@@ -69,7 +72,7 @@ class _host_rng:
         torch.rand_like, torch.randint_like = self.r, self.ri
 
 
-@pytest.mark.parametrize("mode,tol", [("simt", 1e-3), ("tc3", 1e-3), ("tc", 2e-2)])
+@pytest.mark.parametrize("mode,tol", [("simt", 1e-3), ("tc3", 1e-3), ("bf3", 4e-3), ("tc", 2e-2)])
 def test_train_step_matches_reference_fixture(cuda_ops, mode, tol):
     fix, model, out, losses = _run(mode)
     assert list(losses.keys()) == list(fix["losses"].keys())

@@ -185,6 +185,29 @@ def test_msda(cuda_ops, oracle_ops, D, shapes, points):
     run_both(fn, cuda_ops, oracle_ops, [mem, proj], F32, 2e-4)
 
 
+@pytest.mark.parametrize("which", ["both", "decode", "stat"])
+def test_fdr_head(cuda_ops, oracle_ops, which):
+    """Integral + distance2bbox + LQE statistics kernel (fdr.cu) against the reference's op chain
+    (dfine_decoder.py:291-313, arch/utils.py:119-188) on the same corner logits, forward and d(pred_corners)."""
+    from custom_d_fine_b200.decoder import weighting_function
+    g = _g(11)
+    corners = (torch.randn(2, 37, 4 * 33, generator=g) * 2.0).requires_grad_()
+    ref = torch.rand(2, 37, 4, generator=g) * 0.5 + 0.2
+    reg_scale = torch.tensor([4.0])
+    project = weighting_function(32, torch.tensor([0.5]), reg_scale)
+
+    def fn(K, c):
+        dev = c.device
+        if which == "decode":
+            return K.fdr_decode(c, ref.to(dev), project.to(dev), reg_scale.to(dev))
+        if which == "stat":
+            return K.lqe_stat(c, 4, 32)
+        box, stat = K.fdr_head(c, ref.to(dev), project.to(dev), reg_scale.to(dev), 4)
+        return torch.cat([box, stat], -1)
+
+    run_both(fn, cuda_ops, oracle_ops, [corners], F32, F32)
+
+
 def test_maxpool_upsample(cuda_ops, oracle_ops):
     g = _g(5)
     x = torch.randn(2, 17, 19, 24, generator=g)
@@ -228,7 +251,7 @@ def test_tc_matches_simt(cuda_ops, case):
     res = {}
     prev = co.get_gemm_mode()
     try:
-        for mode in ("simt", "tc", "tc3"):
+        for mode in ("simt", "tc", "tc3", "bf3"):
             co.set_gemm_mode(mode)
             cache = co._WCache()
             y = torch.zeros(B, OH, OW, Cout).cuda()
@@ -243,7 +266,7 @@ def test_tc_matches_simt(cuda_ops, case):
     finally:
         co.set_gemm_mode(prev)
     y0, _, dx0, dw0 = res["simt"]
-    for mode, tol in (("tc", TF32), ("tc3", 2e-5)):
+    for mode, tol in (("tc", TF32), ("tc3", 2e-5), ("bf3", 5e-5)):   # bf3: 16 mantissa bits per operand
         y, stats, dx, dw = res[mode]
         check_close(f"{mode} fwd {case}", y, y0, tol)
         check_close(f"{mode} fused stats sum", stats[:Cout].float(), y0.reshape(M, Cout).sum(0), max(tol, 1e-4) * 5)
