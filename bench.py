@@ -204,12 +204,34 @@ def run_ours(args):
     # are summed per family: the conv kernel runs ~300 launches of 49 shapes per step)
     cuda_ops.counters.watch = ("conv_tc", "conv_wgrad_tc", "msda_fwd", "msda_bwd")
     cuda_ops.counters.timed = {}
+    cuda_ops.wgrad_stream.disabled = True      # one stream: a kernel's event pair must not time a concurrent kernel too
     timed(lambda: step.eager_twin(dx, dtargets), args.steps)
+    cuda_ops.wgrad_stream.disabled = False
     cuda_ops.counters.watch = ()
-    kern = {}
+    kern, split = {}, {}
+    pk0 = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    # tf32 tensor peak = half the measured dense bf16 rate (kind::tf32 issues at half the kind::f16 rate);
+    # ridge point of a launch, in FLOP per algorithmic fp32 byte
+    tf32_peak = float(pk0.get("bf16_tflops_sustained", 1394.5)) / 2.0
+    ridge = tf32_peak * 1e12 / (float(pk0.get("hbm_gbs", 6650.0)) * 1e9)
     for name, recs in cuda_ops.counters.timed.items():
-        durs = [s.elapsed_time(e) for s, e, _ in recs]
+        durs = [r[0].elapsed_time(r[1]) for r in recs]
         kern[name] = (sum(durs) / len(durs), sum(r[2] for r in recs) / len(recs), len(durs), sum(durs) / args.steps)
+        if name in ("conv_tc", "conv_wgrad_tc"):
+            # per-launch classification against the ridge: which roofline bounds the launch
+            l_hbm = [(d, r[2]) for d, r in zip(durs, recs) if r[3] / max(r[2], 1) < ridge]
+            l_tc = [(d, r[3]) for d, r in zip(durs, recs) if r[3] / max(r[2], 1) >= ridge]
+            split[name] = {
+                "ridge_flop_per_byte": round(ridge, 1),
+                "hbm_bound": {"launches_per_step": len(l_hbm) // args.steps, "ms_per_step": round(sum(d for d, _ in l_hbm) / args.steps, 3),
+                              "GB/s": round(sum(b for _, b in l_hbm) / max(sum(d for d, _ in l_hbm), 1e-9) / 1e6, 1)} if l_hbm else None,
+                "tensor_bound": {"launches_per_step": len(l_tc) // args.steps, "ms_per_step": round(sum(d for d, _ in l_tc) / args.steps, 3),
+                                 "TFLOP/s": round(sum(f for _, f in l_tc) / max(sum(d for d, _ in l_tc), 1e-9) / 1e9, 1),
+                                 "tf32_peak_TFLOP/s": tf32_peak} if l_tc else None}
+            if split[name]["hbm_bound"]:
+                split[name]["hbm_bound"]["frac"] = round(split[name]["hbm_bound"]["GB/s"] / float(pk0.get("hbm_gbs", 6650.0)), 4)
+            if split[name]["tensor_bound"]:
+                split[name]["tensor_bound"]["frac"] = round(split[name]["tensor_bound"]["TFLOP/s"] / tf32_peak, 4)
     run_e2e(2)
     ms_e2e = timed(lambda: run_e2e(args.steps), 1)
     mode = "cuda-graph replay (3 graphs/step)" if graphed and step._graphs else "eager launches"
@@ -247,7 +269,8 @@ def run_ours(args):
                 "definition": "sum of algorithmic bytes (in + out + weights, fp32) over the family's launches / sum of "
                               "their CUDA-event durations",
                 "timed_in": "an eager pass of the same K steps (CUDA events on the launching stream)",
-                "others": {k: entry(k) for k in kern if k != name}}
+                "by_bound": split.get(name),
+                "others": {k: dict(entry(k), **({"by_bound": split[k]} if k in split else {})) for k in kern if k != name}}
     cpu = cpu_baseline(steps=2, warmup=1) if world == 1 and not args.no_cpu_baseline else None
     imgs = B * world * args.steps
     line = {
@@ -263,6 +286,8 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(hx.numel() * 4 + hl.numel() * 8 + hb.numel() * 4), "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
     }
+    if graphed and step.host_gap_ms() is not None:
+        line["config"]["host_gap_ms"] = round(step.host_gap_ms(), 3)   # device idle between graphs A and B (index planning)
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -40,7 +40,10 @@ class LightConv(nn.Module):
         self.conv1 = ConvUnit(cin, cout, 1, act=None, lab=lab, frozen_norm=frozen)
         self.conv2 = ConvUnit(cout, cout, k, groups=cout, act="relu", lab=lab, frozen_norm=frozen)
 
-    def forward(self, x):
+    def forward(self, x, tap=False):
+        if tap:
+            y, x_alias = self.conv1(x, tap=True)
+            return self.conv2(y), x_alias
         return self.conv2(self.conv1(x))
 
 
@@ -62,11 +65,14 @@ class HGBlock(nn.Module):
         )
 
     def forward(self, x):
-        feats = [x]
+        # every layer input is also a member of the concat: the concat reads the layer's `tap` alias of its input so
+        # that the concat's gradient slice is added inside that layer's data-gradient kernel (hgnetv2.py:265-275)
+        feats = []
         y = x
         for layer in self.layers:
-            y = layer(y)
-            feats.append(y)
+            y, y_in = layer(y, tap=True)
+            feats.append(y_in)
+        feats.append(y)
         y = self.aggregation[0](K.cat(feats))
         return self.aggregation[1](y, post_add=x if self.residual else None)
 

@@ -65,7 +65,7 @@ class ConvUnit(nn.Module):
     def _bn(self):
         return getattr(self, self._norm_name)
 
-    def forward(self, x, pre_add=None, post_add=None):
+    def forward(self, x, pre_add=None, post_add=None, tap=False):
         bn = self._bn()
         frozen = isinstance(bn, FrozenBN)
         lab = getattr(self, "lab", None)
@@ -76,7 +76,7 @@ class ConvUnit(nn.Module):
             training=self.training and not frozen, momentum=0.1, eps=bn.eps, act=self.act,
             lab_scale=None if lab is None else lab.scale,
             lab_bias=None if lab is None else lab.bias,
-            pre_add=pre_add, post_add=post_add)
+            pre_add=pre_add, post_add=post_add, tap=tap)
 
 
 class MLP(nn.Module):

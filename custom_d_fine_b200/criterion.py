@@ -116,6 +116,7 @@ class IndexPlan:
         if torch.cuda.is_available():
             self.table, self.counts = self.table.pin_memory(), self.counts.pin_memory()
         self._dn_static = None
+        self._cols = None
         if self.n_dn:
             # the denoising set depends on the targets' sizes only (dfine_criterion.py:809-831)
             b = np.concatenate([np.full(s * dn_groups, i) for i, s in enumerate(self.sizes)]) if self.n_dn else []
@@ -134,11 +135,22 @@ class IndexPlan:
             return o, o + self.n_dn
         return k * self.n_layer, (k + 1) * self.n_layer
 
-    def fill(self, out_q, out_t):
+    def fill(self, out_q, out_t, want_lists=True):
         """out_q / out_t: host int64 [n_sets, sumT] as written by the matcher kernel (pairs of image b start at
         offs[b], min(Q, T_b) of them, sorted by query).  Returns the per-set per-image index lists too."""
         tab = self.table.numpy()
         tab[:] = 0
+        if not want_lists and self.per_img == self.sizes:
+            # every image keeps all its targets (T_b <= Q): the matched sets are the matcher's arrays as they are
+            n, S = self.n_layer, self.n_sets
+            if self._cols is None:
+                b_of = np.repeat(np.arange(len(self.sizes)), self.sizes)
+                self._cols = (np.tile(b_of, S), np.tile(np.repeat(self.offs[:-1], self.sizes), S))
+            tab[0, :S * n] = self._cols[0]
+            tab[1, :S * n] = np.asarray(out_q[:, :n]).reshape(-1)
+            tab[2, :S * n] = np.asarray(out_t[:, :n]).reshape(-1) + self._cols[1]
+            tab[3, :S * n] = 1
+            return None
         per_set = []
         col = 0
         for k in range(self.n_sets):
@@ -159,9 +171,10 @@ class IndexPlan:
         tab[1, o:e] = self.Q          # padded entries scatter into the dummy query column
         col = o
         for b, (q, t) in enumerate(go):
-            n = int(q.numel())
-            tab[0, col:col + n], tab[1, col:col + n] = b, q.numpy()
-            tab[2, col:col + n], tab[3, col:col + n] = t.numpy() + self.offs[b], 1
+            q, t = np.asarray(q), np.asarray(t)       # torch (reference-style lists) or numpy (go_indices_host)
+            n = int(q.shape[0])
+            tab[0, col:col + n], tab[1, col:col + n] = b, q
+            tab[2, col:col + n], tab[3, col:col + n] = t + self.offs[b], 1
             col += n
         if self._dn_static is not None:
             o, e = self.set_slice("dn")
@@ -301,15 +314,44 @@ class DFINECriterion(nn.Module):
         for b in range(len(indices)):
             q = torch.cat([indices[b][0]] + [a[b][0] for a in indices_aux_list])
             t = torch.cat([indices[b][1]] + [a[b][1] for a in indices_aux_list])
-            ind = torch.cat([q[:, None], t[:, None]], 1)
-            unique, counts = torch.unique(ind, return_counts=True, dim=0)
-            order = torch.argsort(counts, descending=True)
-            seen = {}
-            for r, c in unique[order].tolist():
-                if r not in seen:
-                    seen[r] = c
-            res.append((torch.tensor(list(seen.keys()), dtype=torch.int64),
-                        torch.tensor(list(seen.values()), dtype=torch.int64)))
+            res.append(DFINECriterion._go_union(q, t))
+        return res
+
+    _GO_M = 1 << 20       # > any target index: (q, t) <-> q * M + t keeps the lexicographic row order
+
+    @staticmethod
+    def _go_union(q, t):
+        """One image.  The reference's ``torch.unique(pairs, dim=0)`` (215 us per image on the host, with the device
+        idle between the two CUDA graphs of a step) is evaluated on the scalar key q*M + t: same sorted order, same
+        counts, hence the same input to the very same unstable ``torch.argsort`` call and the same union."""
+        M = DFINECriterion._GO_M
+        uniq, counts = torch.unique(q * M + t, return_counts=True)
+        order = torch.argsort(counts, descending=True)
+        uq = torch.div(uniq, M, rounding_mode="floor")[order].tolist()
+        ut = (uniq % M)[order].tolist()
+        seen = {}
+        for r, c in zip(uq, ut):
+            if r not in seen:
+                seen[r] = c
+        return (torch.tensor(list(seen.keys()), dtype=torch.int64), torch.tensor(list(seen.values()), dtype=torch.int64))
+
+    @staticmethod
+    def go_indices_host(out_q, out_t, plan):
+        """``go_indices`` straight from the matcher kernel's host arrays [n_sets, sumT] (set-major concatenation per
+        image = the order of the reference's torch.cat over layers)."""
+        M = DFINECriterion._GO_M
+        key = np.asarray(out_q) * M + np.asarray(out_t)
+        res = []
+        for b, n in enumerate(plan.per_img):
+            o = int(plan.offs[b])
+            uniq, counts = np.unique(key[:, o:o + n].reshape(-1), return_counts=True)   # = torch.unique: sorted, counted
+            # the tie order among equally frequent pairs is whatever torch's unstable CPU argsort yields on this
+            # very counts vector (dfine_criterion.py:584) — so that call is kept
+            order = torch.argsort(torch.from_numpy(counts.astype(np.int64, copy=False)), descending=True).numpy()
+            ku = uniq[order]
+            _, first = np.unique(ku // M, return_index=True)      # first occurrence of every query, in list order
+            sel = ku[np.sort(first)]
+            res.append((sel // M, sel % M))
         return res
 
     @staticmethod
@@ -356,8 +398,8 @@ class DFINECriterion(nn.Module):
             plan = IndexPlan(sizes, Q, n_sets, meta["dn_positive_idx"] if meta else None,
                              meta["dn_num_group"] if meta else 0)
         out_q, out_t = self.matcher.raw_to_host(raw, plan)
-        per_set = plan.fill(out_q, out_t)
-        go = self.go_indices(per_set[0], per_set[1:])
+        plan.fill(out_q, out_t, want_lists=False)
+        go = self.go_indices_host(out_q, out_t, plan)
         n_go = plan.fill_go(go)
         counts = torch.tensor([float(n_go), float(sum(sizes))], dtype=torch.float32)
         if dist_utils.is_dist_available_and_initialized():
@@ -395,9 +437,17 @@ class DFINECriterion(nn.Module):
         return loss.mean(2).sum((1, 2)) * Q / num_boxes
 
     @staticmethod
+    def _rows(x, b, q):
+        """x[:, b, q] for x [S,B,Q,D] and index vectors b, q [n] -> [S,n,D], as an index_select on the flattened
+        (B*Q) axis: same values, but the backward is index_add (atomics) instead of index_put(accumulate)'s
+        sort-based kernel (0.65 ms per step on the [L,B,Q,132] corner logits)."""
+        S, B, Q, D = x.shape
+        return x.reshape(S, B * Q, D).index_select(1, b * Q + q)
+
+    @staticmethod
     def _box_sets(boxes, G, tg, num_boxes):
         """boxes [S,B,Q,4]; G: shared index set -> (l1 [S], giou [S])."""
-        src, tbox = boxes[:, G.b, G.q], tg[1][G.t]
+        src, tbox = DFINECriterion._rows(boxes, G.b, G.q), tg[1][G.t]
         l1 = (src - tbox).abs().sum(-1)
         gi = 1 - _giou_nd(cxcywh_to_xyxy(src), cxcywh_to_xyxy(tbox))
         if G.v is not None:
@@ -415,7 +465,7 @@ class DFINECriterion(nn.Module):
         ious = ious.detach()
         ious_w = ious * G.v if G.v is not None else ious
         w_t = ious_w.unsqueeze(-1).expand(L, G.n, 4).reshape(L, -1)
-        lsm = F.log_softmax(corners[:, G.b, G.q].reshape(L, -1, nb), dim=-1)
+        lsm = F.log_softmax(self._rows(corners, G.b, G.q).reshape(L, -1, nb), dim=-1)
         left = t_idx.long()[None, :, None].expand(L, -1, 1)
         ce_l = -lsm.gather(-1, left).squeeze(-1)
         ce_r = -lsm.gather(-1, left + 1).squeeze(-1)

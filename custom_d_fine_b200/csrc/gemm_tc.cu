@@ -175,6 +175,13 @@ __device__ __forceinline__ void bf16_split(float x, uint32_t& hi, uint32_t& lo) 
     lo = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(r));
 }
 
+// two fp32 -> one packed bf16x2 word (element a in the low half: lower address)
+__device__ __forceinline__ uint32_t bf16x2_rn(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+
 constexpr int BM = 128, BK = 32;
 constexpr int EPI_LD = 33;
 constexpr int MAX_TAPS = 9;
@@ -211,6 +218,9 @@ struct FwdParams {
     long ldx;
     int prefetch;             // k-blocks the prefetch warp may run ahead of the TMA producer (0 = off)
     int w_planes;             // 3xTF32: map_w is a 3-D {K, Cout, 2} map over adjacent hi / lo weight planes
+    int wk2[MAX_TAPS];        // hybrid mode: first weight column of tap t in the tap-padded bf16 planes
+    const float* res;         // optional tensor added to the output in the epilogue (same pixel geometry as y,
+    long ldres;               // pixel stride ldres): fuses the gradient-accumulation add of a multi-consumer tensor
 };
 
 // X3 = 0: one kind::tf32 MMA per k-step (operands truncated to tf32 by the tensor core).
@@ -229,7 +239,10 @@ struct FwdSmem {
     uint32_t tmem_base;
 };
 
-constexpr int fwd_threads(int x3) { return x3 ? 352 : 224; }   // + one L2-prefetch warp (persistent kernel)
+// warps: 0 TMA, 1 MMA, 2..5 epilogue, then the converter warps (4 for 3xTF32, 8 for the bf16-plane modes whose
+// converter would otherwise bound the k-block time), then one L2-prefetch warp (persistent kernel)
+constexpr int conv_warps(int x3) { return x3 == 0 ? 0 : (x3 == 1 ? 4 : 8); }
+constexpr int fwd_threads(int x3) { return 32 * (6 + conv_warps(x3) + 1); }
 
 template <int BN, int X3, int STAGES>
 __global__ void __launch_bounds__(fwd_threads(X3)) tc_fwd_kernel(const __grid_constant__ CUtensorMap map_x,
@@ -431,10 +444,15 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 //         planes (64-byte rows, 64-byte swizzle); weights arrive pre-split as bf16 planes.
 template <int BN, int X3, int STAGES>
 struct PersistSmem {
-    static constexpr int B_PLANE = X3 == 2 ? BN * BK * 2 : BN * BK * 4;        // bytes of one weight plane
-    static constexpr int B_BYTES = (X3 ? 2 : 1) * B_PLANE;                       // [hi | lo]
-    static constexpr int A2_PLANE = X3 == 2 ? BM * BK * 2 : BM * BK * 4;
-    static constexpr int A2_BYTES = X3 == 1 ? A2_PLANE : (X3 == 2 ? 2 * A2_PLANE : 16);   // tf32 lo | bf16 hi + lo
+    // X3 = 3 ("hybrid"): a_hi*w_hi as kind::tf32 (operands RN tf32), the two cross terms a_lo*w_hi + a_hi*w_lo as
+    //         kind::f16 on bf16 copies (a 2^-9 relative error on a 2^-12 relative term): 3xTF32-class accuracy for
+    //         8 instead of 12 tf32-MMA times per k-block.  b = [w_hi fp32 | bf16(w) | bf16(w_lo)],
+    //         a = tf32 hi in place, a2 = [bf16(a_lo) | bf16(a)].
+    static constexpr int B_PLANE = X3 == 2 ? BN * BK * 2 : BN * BK * 4;        // bytes of the first weight plane
+    static constexpr int B16_PLANE = BN * BK * 2;
+    static constexpr int B_BYTES = X3 == 3 ? B_PLANE + 2 * B16_PLANE : (X3 ? 2 : 1) * B_PLANE;   // [hi | lo]
+    static constexpr int A2_PLANE = X3 >= 2 ? BM * BK * 2 : BM * BK * 4;
+    static constexpr int A2_BYTES = X3 == 1 ? A2_PLANE : (X3 >= 2 ? 2 * A2_PLANE : 16);   // tf32 lo | two bf16 planes
     alignas(1024) float a[STAGES][BM * BK];                                      // TMA landing buffer (fp32)
     alignas(1024) uint8_t b[STAGES][B_BYTES];
     alignas(X3 ? 1024 : 16) uint8_t a2[X3 ? STAGES : 1][A2_BYTES];
@@ -472,7 +490,7 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
     if (warp == 0 && lane == 0) { prefetch_tmap(&map_x); prefetch_tmap(&map_w); if (X3) prefetch_tmap(&map_wlo); }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); mbar_init(&sm.conv[s], 128); }
+            for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); mbar_init(&sm.conv[s], 32 * conv_warps(X3)); }
             for (int a = 0; a < 2; ++a) { mbar_init(&sm.tfull[a], 1); mbar_init(&sm.tempty[a], 4); }
             sm.produced = 0;
             fence_barrier_init();
@@ -509,7 +527,10 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                     mbar_expect_tx(&sm.full[s], (uint32_t)(p.TW * p.TH * BK * sizeof(float)) + (uint32_t)Smem::B_BYTES);
                     tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 * p.in_stride + p.dw[tap],
                                 h0 * p.in_stride + p.dh[tap], img);
-                    if (X3 == 2 || (X3 && p.w_planes)) {   // hi and lo weight planes are adjacent in memory: one 3-D box
+                    if (X3 == 3) {       // tf32 hi plane (fp32 map) + the two bf16 planes (one 3-D box, tap-padded K)
+                        tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
+                        tma_load_3d(sm.b[s] + Smem::B_PLANE, &map_wlo, &sm.full[s], p.wk2[tap] + c0, n0, 0);
+                    } else if (X3 == 2 || (X3 && p.w_planes)) {   // hi and lo weight planes are adjacent in memory: one 3-D box
                         tma_load_3d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0, n0, 0);
                     } else {
                         tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
@@ -551,6 +572,19 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                             umma_bf16(d, ah + 2 * k, bl + 2 * k, idesc16, 1);
                             umma_bf16(d, ah + 2 * k, bh + 2 * k, idesc16, 1);
                         }
+                    } else if constexpr (X3 == 3) {
+                        constexpr uint32_t idesc16 = make_idesc_bf16(BN);
+                        const uint64_t al = make_desc(smem_u32(sm.a2[s]), 16, 512, 4);                        // bf16(a_lo)
+                        const uint64_t ab = make_desc(smem_u32(sm.a2[s] + Smem::A2_PLANE), 16, 512, 4);     // bf16(a)
+                        const uint64_t wb = make_desc(smem_u32(sm.b[s] + Smem::B_PLANE), 16, 512, 4);       // bf16(w)
+                        const uint64_t wl = make_desc(smem_u32(sm.b[s] + Smem::B_PLANE + Smem::B16_PLANE), 16, 512, 4);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            umma_bf16(d, al + 2 * k, wb + 2 * k, idesc16, (kb | k) != 0);
+                            umma_bf16(d, ab + 2 * k, wl + 2 * k, idesc16, 1);
+                        }
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k) umma_tf32(d, da + 2 * k, db + 2 * k, idesc, 1);
                     } else if constexpr (X3 == 1) {
                         const uint64_t dal = make_desc(smem_u32(sm.a2[s]), 16, 1024);
                         const uint64_t dbl = make_desc(smem_u32(sm.b[s] + Smem::B_PLANE), 16, 1024);
@@ -584,7 +618,7 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
             const int mt = t / ts.n_tiles, n0 = (t % ts.n_tiles) * BN;
             const int img = mt / tiles_per_img, tt = mt % tiles_per_img;
             const int h0 = (tt / p.tiles_w) * p.TH, w0 = (tt % p.tiles_w) * p.TW;
-            long row_off[8];
+            long row_off[8];       // output pixel index of the row (multiplied by the pixel stride at the access)
             bool row_ok[8];
 #pragma unroll
             for (int r8 = 0; r8 < 8; ++r8) {
@@ -592,12 +626,27 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                 const int th = r / p.TW, tw = r % p.TW;
                 const int oh = h0 + th, ow = w0 + tw;
                 row_ok[r8] = th < p.TH && oh < p.OH && ow < p.OW;
-                row_off[r8] = (((long)img * p.YH + (long)oh * p.osy + p.ooy) * p.YW + (long)ow * p.osx + p.oox) * p.ldy;
+                row_off[r8] = ((long)img * p.YH + (long)oh * p.osy + p.ooy) * p.YW + (long)ow * p.osx + p.oox;
             }
+            // Residual tile (data-gradient launches only, X3 = 0): software-pipelined one 32-column chunk ahead, the
+            // first chunk requested BEFORE waiting for the accumulator so that its HBM latency hides behind the
+            // tile's MMAs (issued inside the chunk loop the dependent loads made the epilogue the bottleneck).
+            float4 rcur[8], rnxt[8];
+            auto load_res = [&](int c0, float4 (&dst)[8]) {
+                const int col = n0 + c0 + 4 * (lane % 8);
+#pragma unroll
+                for (int r8 = 0; r8 < 8; ++r8)
+                    dst[r8] = (row_ok[r8] && col < p.N)
+                                  ? __ldg(reinterpret_cast<const float4*>(p.res + row_off[r8] * p.ldres + col))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            const bool has_res = X3 == 0 && p.res != nullptr;
+            if (X3 == 0 && has_res) load_res(0, rcur);
             mbar_wait(&sm.tfull[acc], aph);
             tc_fence_after();
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 if (n0 + c0 >= p.N) break;
+                if (X3 == 0 && has_res && c0 + 32 < BN && n0 + c0 + 32 < p.N) load_res(c0 + 32, rnxt);
                 uint32_t v[32];
                 tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + acc * BN + (uint32_t)c0, v);
 #pragma unroll
@@ -623,8 +672,13 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                             o.x = act_fwd(o.x + bv.x, p.act); o.y = act_fwd(o.y + bv.y, p.act);
                             o.z = act_fwd(o.z + bv.z, p.act); o.w = act_fwd(o.w + bv.w, p.act);
                         }
-                        *reinterpret_cast<float4*>(y + row_off[r8] + col) = o;
+                        if (X3 == 0 && has_res) { o.x += rcur[r8].x; o.y += rcur[r8].y; o.z += rcur[r8].z; o.w += rcur[r8].w; }
+                        *reinterpret_cast<float4*>(y + row_off[r8] * p.ldy + col) = o;
                     }
+                }
+                if (X3 == 0 && has_res) {
+#pragma unroll
+                    for (int r8 = 0; r8 < 8; ++r8) rcur[r8] = rnxt[r8];
                 }
                 if (stats) {
 #pragma unroll
@@ -655,7 +709,7 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.tempty[acc]);
         }
-    } else if (warp == (X3 ? 10 : 6)) {
+    } else if (warp == 6 + conv_warps(X3)) {
         // L2 prefetch warp.  TMA keeps only ~32 KB of 128-byte row requests in flight per SM (measured:
         // ~28 GB/s per SM when the activation tile streams from HBM, profiles/README.md), which cannot cover
         // HBM latency.  This warp walks the producer's (tile, k-block) sequence a bounded distance AHEAD of
@@ -695,36 +749,64 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                 ++gp;
             }
         }
-    } else if (X3 && warp < 10) {
-        const int ct = threadIdx.x - 192;  // 0..127
+    } else if (X3 && warp < 6 + conv_warps(X3)) {
+        constexpr int CT = 32 * conv_warps(X3);   // converter threads
+        const int ct = threadIdx.x - 192;  // 0..CT-1
         uint32_t g = 0;
         for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
             for (int kb = 0; kb < num_k; ++kb, ++g) {
                 const int s = g % STAGES, ph = (g / STAGES) & 1;
                 mbar_wait(&sm.full[s], ph);
                 const uint32_t a_base = smem_u32(sm.a[s]), l_base = smem_u32(sm.a2[s]);
-                if constexpr (X3 == 2) {
+                if constexpr (X3 >= 2) {
                     // fp32 tile: 128-byte rows, 16-byte chunk j of row r at physical chunk j ^ (r & 7).  bf16 planes:
                     // 64-byte rows, 16-byte chunk c (channels 8c..8c+7) at physical chunk c ^ ((r >> 1) & 3).  The two
                     // fp32 chunks of one bf16 chunk are the physical PAIR k = c ^ ((r & 7) >> 1) — the very index
                     // of the destination chunk — in swapped order on odd rows.  So item idx = 4 r + k reads 32
                     // contiguous bytes at idx * 32 and writes 16 contiguous bytes at idx * 16 of each plane.
+                    constexpr int ITEMS = BM * 4 / CT;
+                    float4 v0[ITEMS], v1[ITEMS];
 #pragma unroll
-                    for (int i = 0; i < BM * 4 / 128; ++i) {
-                        const uint32_t idx = (uint32_t)(ct + i * 128);
-                        float4 v0 = lds128(a_base + idx * 32u), v1 = lds128(a_base + idx * 32u + 16u);
-                        if ((idx >> 2) & 1) { const float4 tmp = v0; v0 = v1; v1 = tmp; }
-                        uint32_t h[8], l[8];
-                        bf16_split(v0.x, h[0], l[0]); bf16_split(v0.y, h[1], l[1]);
-                        bf16_split(v0.z, h[2], l[2]); bf16_split(v0.w, h[3], l[3]);
-                        bf16_split(v1.x, h[4], l[4]); bf16_split(v1.y, h[5], l[5]);
-                        bf16_split(v1.z, h[6], l[6]); bf16_split(v1.w, h[7], l[7]);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(l_base + idx * 16u),
-                                     "r"(h[0] | (h[1] << 16)), "r"(h[2] | (h[3] << 16)), "r"(h[4] | (h[5] << 16)),
-                                     "r"(h[6] | (h[7] << 16)) : "memory");
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(l_base + (uint32_t)Smem::A2_PLANE + idx * 16u),
-                                     "r"(l[0] | (l[1] << 16)), "r"(l[2] | (l[3] << 16)), "r"(l[4] | (l[5] << 16)),
-                                     "r"(l[6] | (l[7] << 16)) : "memory");
+                    for (int i = 0; i < ITEMS; ++i) {      // all loads first: one shared-memory round trip per k-block
+                        const uint32_t idx = (uint32_t)(ct + i * CT);
+                        v0[i] = lds128(a_base + idx * 32u);
+                        v1[i] = lds128(a_base + idx * 32u + 16u);
+                    }
+#pragma unroll
+                    for (int i = 0; i < ITEMS; ++i) {
+                        const uint32_t idx = (uint32_t)(ct + i * CT);
+                        float4 x0 = v0[i], x1 = v1[i], r0, r1;       // plane 1 source (a) and plane 0 source (residual)
+                        if constexpr (X3 == 3) {
+                            float4 h0, h1;                           // tf32 hi, written back in place (same order)
+                            h0.x = tf32_rna(x0.x); h0.y = tf32_rna(x0.y); h0.z = tf32_rna(x0.z); h0.w = tf32_rna(x0.w);
+                            h1.x = tf32_rna(x1.x); h1.y = tf32_rna(x1.y); h1.z = tf32_rna(x1.z); h1.w = tf32_rna(x1.w);
+                            sts128(a_base + idx * 32u, h0.x, h0.y, h0.z, h0.w);
+                            sts128(a_base + idx * 32u + 16u, h1.x, h1.y, h1.z, h1.w);
+                            r0 = make_float4(x0.x - h0.x, x0.y - h0.y, x0.z - h0.z, x0.w - h0.w);
+                            r1 = make_float4(x1.x - h1.x, x1.y - h1.y, x1.z - h1.z, x1.w - h1.w);
+                        }
+                        if ((idx >> 2) & 1) {                        // odd row: the pair is stored high chunk first
+                            float4 tmp = x0; x0 = x1; x1 = tmp;
+                            if constexpr (X3 == 3) { tmp = r0; r0 = r1; r1 = tmp; }
+                        }
+                        const uint32_t b0 = bf16x2_rn(x0.x, x0.y), b1 = bf16x2_rn(x0.z, x0.w);
+                        const uint32_t b2 = bf16x2_rn(x1.x, x1.y), b3 = bf16x2_rn(x1.z, x1.w);
+                        uint32_t l0, l1, l2, l3;
+                        if constexpr (X3 == 2) {                     // residual against the bf16 value itself
+                            l0 = bf16x2_rn(x0.x - __uint_as_float(b0 << 16), x0.y - __uint_as_float(b0 & 0xffff0000u));
+                            l1 = bf16x2_rn(x0.z - __uint_as_float(b1 << 16), x0.w - __uint_as_float(b1 & 0xffff0000u));
+                            l2 = bf16x2_rn(x1.x - __uint_as_float(b2 << 16), x1.y - __uint_as_float(b2 & 0xffff0000u));
+                            l3 = bf16x2_rn(x1.z - __uint_as_float(b3 << 16), x1.w - __uint_as_float(b3 & 0xffff0000u));
+                        } else {                                     // residual against the tf32 hi part
+                            l0 = bf16x2_rn(r0.x, r0.y); l1 = bf16x2_rn(r0.z, r0.w);
+                            l2 = bf16x2_rn(r1.x, r1.y); l3 = bf16x2_rn(r1.z, r1.w);
+                        }
+                        // plane order: X3 = 2 -> [hi | lo]; X3 = 3 -> [bf16(a_lo) | bf16(a)]
+                        const uint32_t pa = l_base + idx * 16u, pb = l_base + (uint32_t)Smem::A2_PLANE + idx * 16u;
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(X3 == 2 ? pa : pb), "r"(b0), "r"(b1),
+                                     "r"(b2), "r"(b3) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(X3 == 2 ? pb : pa), "r"(l0), "r"(l1),
+                                     "r"(l2), "r"(l3) : "memory");
                     }
                 } else {
 #pragma unroll
@@ -1106,10 +1188,11 @@ namespace {
 int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* w_bf16, const float* bias, float* y,
                  double* stats, int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy,
                  int YH, int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
-                 const int* taps, long ldw, int act, void* stream) {
+                 const int* taps, long ldw, int act, void* stream, long ldw16 = 0, const float* res = nullptr,
+                 long ldres = 0) {
     DFINE_REQUIRE(n_taps >= 1 && n_taps <= MAX_TAPS, "conv_tc: %d taps unsupported", n_taps);
     DFINE_REQUIRE(in_stride == 1 || in_stride == 2, "conv_tc: input stride %d unsupported", in_stride);
-    DFINE_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldw % (w_bf16 ? 8 : 4) == 0 &&
+    DFINE_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldw % ((w_bf16 && !w) ? 8 : 4) == 0 &&
                       Cin >= 4 && Cout >= 4,
                   "conv_tc: unsupported geometry Cin=%d Cout=%d ldx=%ld ldy=%ld ldw=%ld", Cin, Cout, ldx, ldy, ldw);
     DFINE_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)y % 16) == 0 &&
@@ -1128,6 +1211,8 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
     p.dbg = dbg;
     static const int pf = [] { const char* e = getenv("DFINE_TC_PREFETCH"); return e ? atoi(e) : 16; }();
     p.prefetch = pf; p.x = x; p.B = B; p.H = H; p.W = W; p.ldx = ldx;
+    DFINE_REQUIRE(!res || (ldres % 4 == 0 && ldres >= Cout && ((uintptr_t)res % 16) == 0), "conv_tc: residual stride %ld", ldres);
+    p.res = res; p.ldres = ldres;
     p.in_stride = in_stride; p.Cin = Cin;
     p.OH = OH; p.OW = OW; p.N = Cout; p.ldy = ldy; p.act = act;
     p.YH = YH; p.YW = YW; p.osy = osy; p.osx = osx; p.ooy = ooy; p.oox = oox;
@@ -1141,13 +1226,26 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
                        (w_lo || w_bf16) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : map_dtype());
     if (rc) return rc;
     if (w_bf16) {
-        // 3xBF16: weights are two adjacent bf16 planes [2][Cout][ldw] (dfine_bf16_split); one 3-D box
+        // 3xBF16 / hybrid: two adjacent bf16 weight planes [2][Cout][ld16] (dfine_bf16_split); one 3-D box
         // {32 k, bn rows, 2 planes} with the 64-byte swizzle lands as [plane][row][64 B]
+        const bool hybrid = w != nullptr;
+        const long ld16 = hybrid ? ldw16 : ldw;
         const int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
         EncodeTiledFn enc = get_encode();
         if (!enc) { dfine_set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return -2; }
-        cuuint64_t dims[3] = {(cuuint64_t)ldw, (cuuint64_t)Cout, 2};
-        cuuint64_t strides[2] = {(cuuint64_t)ldw * 2, (cuuint64_t)ldw * 2 * Cout};
+        if (hybrid) {
+            // tf32 hi plane through a plain fp32 map; the taps' columns in the tap-padded bf16 planes
+            DFINE_REQUIRE(ld16 % 8 == 0 && ld16 % n_taps == 0, "conv_tc(hybrid): ldw16=%ld taps=%d", ld16, n_taps);
+            const int cin_p = (int)(ld16 / n_taps);
+            for (int t = 0; t < MAX_TAPS; ++t) {
+                DFINE_REQUIRE(p.wk[t] % Cin == 0, "conv_tc(hybrid): tap column %d is not a multiple of Cin=%d", p.wk[t], Cin);
+                p.wk2[t] = p.wk[t] / Cin * cin_p;
+            }
+            rc = make_map2(&mwlo, w, ldw, Cout, ldw, BK, bn, "conv_tc(w_hi)");     // placeholder var; swapped below
+            if (rc) return rc;
+        }
+        cuuint64_t dims[3] = {(cuuint64_t)ld16, (cuuint64_t)Cout, 2};
+        cuuint64_t strides[2] = {(cuuint64_t)ld16 * 2, (cuuint64_t)ld16 * 2 * Cout};
         cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)bn, 2};
         cuuint32_t es[3] = {1, 1, 1};
         CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_bf16), dims, strides, box, es,
@@ -1159,11 +1257,17 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
         }
         p.w_planes = 1;
         cudaStream_t st = (cudaStream_t)stream;
-        rc = bn == 32 ? launch_persist<32, 2, 4>(mx, mw, mw, y, bias, stats, p, B, st)
-           : bn == 64 ? launch_persist<64, 2, 4>(mx, mw, mw, y, bias, stats, p, B, st)
-                      : launch_persist<128, 2, 4>(mx, mw, mw, y, bias, stats, p, B, st);
+        if (hybrid) {     // map_w = fp32 hi plane (encoded into mwlo above), map_wlo = the bf16 planes (in mw)
+            rc = bn == 32 ? launch_persist<32, 3, 4>(mx, mwlo, mw, y, bias, stats, p, B, st)
+               : bn == 64 ? launch_persist<64, 3, 4>(mx, mwlo, mw, y, bias, stats, p, B, st)
+                          : launch_persist<128, 3, 3>(mx, mwlo, mw, y, bias, stats, p, B, st);
+        } else {
+            rc = bn == 32 ? launch_persist<32, 2, 4>(mx, mw, mw, y, bias, stats, p, B, st)
+               : bn == 64 ? launch_persist<64, 2, 4>(mx, mw, mw, y, bias, stats, p, B, st)
+                          : launch_persist<128, 2, 4>(mx, mw, mw, y, bias, stats, p, B, st);
+        }
         if (rc) return rc;
-        DFINE_LAUNCH_CHECK("conv_tc(bf16x3)");
+        DFINE_LAUNCH_CHECK("conv_tc(bf16 planes)");
         return 0;
     }
     static const bool persist_bn = [] { const char* e = getenv("DFINE_TC_PERSIST"); return !(e && e[0] == '0'); }();
@@ -1177,10 +1281,13 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
     if (w_lo) {
         rc = make_map2(&mwlo, w_lo, ldw, Cout, ldw, BK, bn, "conv_tc(w_lo)");
         if (rc) return rc;
-        if (persist_bn && w_lo == w + (long)Cout * ldw) {      // dfine_tf32_split planes: fetch both with one box
+        const long plane_dist = (long)(w_lo - w);              // floats between the hi and the lo plane
+        if (persist_bn && plane_dist > 0 && plane_dist % 4 == 0 && plane_dist * 4 < (1L << 40)) {
+            // the planes sit at a fixed distance (adjacent per weight, or the optimizer's hi / lo arenas): both are
+            // fetched by ONE 3-D box whose outer dimension steps from the hi to the lo plane
             EncodeTiledFn enc = get_encode();
             cuuint64_t dims[3] = {(cuuint64_t)ldw, (cuuint64_t)Cout, 2};
-            cuuint64_t strides[2] = {(cuuint64_t)ldw * 4, (cuuint64_t)ldw * 4 * Cout};
+            cuuint64_t strides[2] = {(cuuint64_t)ldw * 4, (cuuint64_t)plane_dist * 4};
             cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)bn, 2};
             cuuint32_t es[3] = {1, 1, 1};
             CUtensorMap m3;
@@ -1194,6 +1301,7 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
     }
     cudaStream_t st = (cudaStream_t)stream;
     static const bool persist = [] { const char* e = getenv("DFINE_TC_PERSIST"); return !(e && e[0] == '0'); }();
+    DFINE_REQUIRE((persist && !w_lo && !w_bf16) || !res, "conv_tc: the fused residual add needs the persistent plain-tf32 kernel");
     if (persist) {
         if (w_lo) {
             rc = bn == 32 ? launch_persist<32, 1, 4>(mx, mw, mwlo, y, bias, stats, p, B, st)
@@ -1220,12 +1328,14 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
 }
 }  // namespace
 
+// `res` (optional, pixel stride ldres, same pixel geometry as y): y = act(conv + bias) + res — the data-gradient
+// launches use it to fold the gradient-accumulation add of a tensor with two consumers into the epilogue.
 DFINE_API int dfine_conv_tc(const float* x, const float* w, const float* w_lo, const float* bias, float* y,
                             double* stats, int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy,
                             int YH, int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
-                            const int* taps, long ldw, int act, void* stream) {
+                            const int* taps, long ldw, int act, const float* res, long ldres, void* stream) {
     return conv_tc_impl(x, w, w_lo, nullptr, bias, y, stats, B, H, W, Cin, ldx, OH, OW, Cout, ldy, YH, YW, osy, osx, ooy,
-                        oox, in_stride, n_taps, taps, ldw, act, stream);
+                        oox, in_stride, n_taps, taps, ldw, act, stream, 0, res, ldres);
 }
 
 // The same contract with error-compensated 3xBF16 operands (see PersistSmem): `w_planes` = the two bf16 planes
@@ -1240,32 +1350,51 @@ DFINE_API int dfine_conv_tc_bf16x3(const float* x, const void* w_planes, const f
                         osx, ooy, oox, in_stride, n_taps, taps, ldw, act, stream);
 }
 
+// Hybrid operands (see PersistSmem, X3 = 3): a_hi*w_hi on kind::tf32, the cross terms on bf16 copies.  `w_hi` = the
+// tf32-rounded fp32 weight matrix [Cout][ldw] (dfine_tf32_split's hi plane), `w_planes16` = bf16 planes
+// [2][Cout][ldw16] = [bf16(w) | bf16(w - tf32(w))] written by dfine_bf16_split(mode 1), every tap's channel run
+// padded to a multiple of 8 (ldw16 = n_taps * Cin_p).  Taps must address whole channel runs (wk[t] % Cin == 0).
+DFINE_API int dfine_conv_tc_hybrid(const float* x, const float* w_hi, const void* w_planes16, const float* bias, float* y,
+                                   double* stats, int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout,
+                                   long ldy, int YH, int YW, int osy, int osx, int ooy, int oox, int in_stride,
+                                   int n_taps, const int* taps, long ldw, long ldw16, int act, void* stream) {
+    DFINE_REQUIRE(w_hi != nullptr && w_planes16 != nullptr, "conv_tc_hybrid: null weights");
+    return conv_tc_impl(x, w_hi, nullptr, w_planes16, bias, y, stats, B, H, W, Cin, ldx, OH, OW, Cout, ldy, YH, YW, osy,
+                        osx, ooy, oox, in_stride, n_taps, taps, ldw, act, stream, ldw16);
+}
+
 // The weight half of the 3xBF16 split.  w: [rows][taps * Cin] fp32 (row stride ldw); planes: [2][rows][taps * Cin_p]
 // bf16 with every tap's channel run padded to Cin_p = Cin rounded up to 8 (a TMA box must start on a 16-byte
 // boundary: tap * Cin_p * 2 bytes); planes[0] = RN bf16(w), planes[1] = RN bf16(w - planes[0]), pads zero.
 namespace {
 __global__ void bf16_split_kernel(const float* __restrict__ w, long ldw, unsigned short* __restrict__ planes,
-                                  long rows, int taps, int Cin, int Cin_p) {
+                                  long rows, int taps, int Cin, int Cin_p, int mode) {
     const long ldp = (long)taps * Cin_p, n = rows * ldp;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         const long r = i / ldp;
         const int k = (int)(i % ldp), tap = k / Cin_p, c = k % Cin_p;
         uint32_t hi = 0, lo = 0;
-        if (c < Cin) bf16_split(w[r * ldw + (long)tap * Cin + c], hi, lo);
+        if (c < Cin) {
+            const float v = w[r * ldw + (long)tap * Cin + c];
+            bf16_split(v, hi, lo);
+            if (mode == 1) lo = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v - tf32_rna(v)));
+        }
         planes[i] = (unsigned short)hi;
         planes[n + i] = (unsigned short)lo;
     }
 }
 }  // namespace
+// mode 0: planes[1] = RN bf16(w - planes[0]) (3xBF16); mode 1: planes[1] = RN bf16(w - RN tf32(w)) (hybrid).
 DFINE_API int dfine_bf16_split(const float* w, long ldw, void* planes, long rows, int taps, int Cin, int Cin_p,
-                               void* stream) {
+                               int mode, void* stream) {
     DFINE_REQUIRE(Cin_p >= Cin && Cin_p % 8 == 0 && taps >= 1 && ((uintptr_t)planes % 16) == 0,
                   "bf16_split: Cin=%d Cin_p=%d taps=%d", Cin, Cin_p, taps);
     const long n = rows * taps * Cin_p;
     if (n == 0) return 0;
     long g = (n + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
-    bf16_split_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w, ldw, (unsigned short*)planes, rows, taps, Cin, Cin_p);
+    bf16_split_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w, ldw, (unsigned short*)planes, rows, taps, Cin, Cin_p,
+                                                               mode);
     DFINE_LAUNCH_CHECK("bf16_split");
     return 0;
 }

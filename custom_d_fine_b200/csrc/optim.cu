@@ -32,13 +32,20 @@ __global__ void __launch_bounds__(NT) sumsq_kernel(const float4* __restrict__ g,
     }
 }
 
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
 // hyper (device, 4 floats): lr, weight_decay, step (1-based, already incremented), ema momentum
 __global__ void __launch_bounds__(NT) adamw_ema_kernel(float4* __restrict__ p, float4* __restrict__ g,
                                                        float4* __restrict__ m, float4* __restrict__ v,
                                                        float4* __restrict__ ema, long n4,
                                                        const float* __restrict__ hyper,
                                                        const double* __restrict__ gnorm_sq, float max_norm,
-                                                       float beta1, float beta2, float eps, int zero_grad) {
+                                                       float beta1, float beta2, float eps, int zero_grad,
+                                                       float4* __restrict__ hi, float4* __restrict__ lo) {
     const float lr = __ldg(hyper + 0), wd = __ldg(hyper + 1), step = __ldg(hyper + 2), em = __ldg(hyper + 3);
     // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
     float coef = 1.f;
@@ -68,6 +75,12 @@ __global__ void __launch_bounds__(NT) adamw_ema_kernel(float4* __restrict__ p, f
         }
         p[i] = pv; m[i] = mv; v[i] = vv;
         if (zero_grad) g[i] = zero;
+        if (hi != nullptr) {     // 3xTF32 operand planes of the new weights (hi = RN tf32, lo = exact remainder)
+            float4 h;
+            h.x = tf32_rn(pv.x); h.y = tf32_rn(pv.y); h.z = tf32_rn(pv.z); h.w = tf32_rn(pv.w);
+            hi[i] = h;
+            lo[i] = make_float4(pv.x - h.x, pv.y - h.y, pv.z - h.z, pv.w - h.w);
+        }
         if (ema != nullptr) {
             float4 ev = ema[i];
             ev.x = em * ev.x + (1.f - em) * pv.x; ev.y = em * ev.y + (1.f - em) * pv.y;
@@ -111,18 +124,21 @@ DFINE_API int dfine_sumsq(const float* g, long n, double* out, void* stream) {
 //   hyper     device float[4] = {lr, weight_decay, step, ema_momentum}
 //   gnorm_sq  device double, squared global gradient norm (null: no clipping)
 //   ema       null: no EMA blend
+//   hi, lo    null, or arenas receiving the 3xTF32 split of the updated parameters (same element order): the
+//             forward GEMMs of the next step read their weight planes from there, no per-layer split launches
 DFINE_API int dfine_adamw_ema(float* p, float* g, float* m, float* v, float* ema, long n, const float* hyper,
                               const double* gnorm_sq, float max_norm, float beta1, float beta2, float eps,
-                              int zero_grad, void* stream) {
+                              int zero_grad, float* hi, float* lo, void* stream) {
     DFINE_REQUIRE(n % 4 == 0, "adamw_ema: arena length must be a multiple of 4");
     DFINE_REQUIRE(((uintptr_t)p % 16) == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)m % 16) == 0 &&
-                      ((uintptr_t)v % 16) == 0 && ((uintptr_t)ema % 16) == 0,
+                      ((uintptr_t)v % 16) == 0 && ((uintptr_t)ema % 16) == 0 && ((uintptr_t)hi % 16) == 0 &&
+                      ((uintptr_t)lo % 16) == 0 && ((hi == nullptr) == (lo == nullptr)),
                   "adamw_ema: arenas must be 16-byte aligned");
     if (n == 0) return 0;
     adamw_ema_kernel<<<grid_for(n / 4), NT, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g), reinterpret_cast<float4*>(m),
         reinterpret_cast<float4*>(v), reinterpret_cast<float4*>(ema), n / 4, hyper, gnorm_sq, max_norm, beta1, beta2,
-        eps, zero_grad);
+        eps, zero_grad, reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo));
     DFINE_LAUNCH_CHECK("adamw_ema");
     return 0;
 }

@@ -80,9 +80,9 @@ def _check(rc, what):
 
 
 class _timed:
-    def __init__(self, name, nbytes):
+    def __init__(self, name, nbytes, flops=0):
         self.on = name in counters.watch
-        self.name, self.nbytes = name, nbytes
+        self.name, self.nbytes, self.flops = name, nbytes, flops
 
     def __enter__(self):
         if self.on:
@@ -92,7 +92,7 @@ class _timed:
     def __exit__(self, *exc):
         if self.on:
             self.e.record()
-            counters.timed.setdefault(self.name, []).append((self.s, self.e, self.nbytes))
+            counters.timed.setdefault(self.name, []).append((self.s, self.e, self.nbytes, self.flops))
 
 
 def _p(t):
@@ -144,6 +144,53 @@ def _as_dev_scalar(v, device):
     return t
 
 
+class _WgradStream:
+    """Weight gradients on a second stream.  Nothing in the backward pass consumes a weight gradient (the kernels
+    accumulate straight into the optimizer's flat arenas), so each conv / linear weight-gradient launch is forked
+    off the backward stream right after its operands exist and the chain of data gradients continues without
+    waiting for it; the step joins the stream once, after backward (train._end_step).  Under CUDA-graph capture the
+    fork / join become graph edges.  Operand tensors are kept alive until the join: the caching allocator must not
+    hand their memory to a later main-stream allocation while the side stream still reads it.
+    Active only between train._begin_step and train._end_step (DFINE_WGRAD_STREAM=0 disables it)."""
+
+    def __init__(self):
+        self.stream, self.on, self.used, self.keep = None, False, False, []
+        self.disabled = False      # bench.py serialises the step while it brackets single kernels with events
+
+    def begin(self, device):
+        if self.disabled or os.environ.get("DFINE_WGRAD_STREAM", "1") == "0":
+            return
+        if self.stream is None or self.stream.device != device:
+            self.stream = torch.cuda.Stream(device)
+        self.on = True
+
+    def run(self, fn, *keep):
+        if not self.on:
+            fn()
+            return
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            fn()
+        self.keep.extend(keep)
+        self.used = True
+
+    def sync_main(self):
+        """The main stream waits for everything queued here so far (end of the forward pass: the re-laid weights
+        prepared for the backward; also required before a CUDA-graph capture that contains a fork ends)."""
+        if self.used:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.keep.clear()
+        self.used = False
+
+    def join(self):
+        self.sync_main()
+        self.on = False
+
+
+wgrad_stream = _WgradStream()
+
+
 def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -179,16 +226,19 @@ def _rows(x):
 # Dense conv / linear shapes the tcgen05 kernels accept run on tensor cores.  Modes (env DFINE_GEMM / set_gemm_mode):
 #   "tc3"  (default) forward GEMMs as error-compensated 3xTF32 (fp32-class accuracy: the parity mode of the
 #          tensor-core path), data / weight gradients as plain kind::tf32;
+#   "tch"  forward GEMMs as a hybrid split: a_hi*w_hi on kind::tf32, the cross terms a_lo*w_hi + a_hi*w_lo on bf16
+#          copies through kind::f16 (3xTF32-class accuracy for 2/3 of its tensor time), gradients as in "tc3";
 #   "bf3"  forward GEMMs as error-compensated 3xBF16 (two bf16 parts per operand = 16 mantissa bits, three
 #          kind::f16 MMAs at twice the tf32 rate; ~1e-5 relative), gradients as in "tc3";
 #   "tc"   plain kind::tf32 everywhere (the precision class of the reference's cuDNN convolutions on GPU);
 #   "simt" fp32 CUDA-core kernels of the same library (strict-fp32 parity runs and kernel bring-up).
 _MODE = os.environ.get("DFINE_GEMM", "tc3")
+_TAP = os.environ.get("DFINE_TAP", "1") != "0"      # A/B switch: gradient-routing aliases (fused accumulation adds)
 
 
 def set_gemm_mode(mode: str) -> None:
     global _MODE
-    if mode not in ("tc", "tc3", "bf3", "simt"):
+    if mode not in ("tc", "tc3", "tch", "bf3", "simt"):
         raise ValueError(mode)
     _MODE = mode
 
@@ -217,12 +267,17 @@ def _taps(key, make):
 
 
 def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, YH, YW, os_, oo, in_stride, taps, act,
-               stats, what, bf16_planes=None):
+               stats, what, bf16_planes=None, res=None, ldres=0):
     arr, n = taps
     # algorithmic bytes: input pixels + output pixels + weights, each touched once, fp32
     nbytes = 4 * (B * min(H * W, OH * OW * in_stride * in_stride) * Cin + B * OH * OW * Cout + Cout * n * Cin)
-    with _timed("conv_tc", nbytes):
-        if bf16_planes is not None:
+    with _timed("conv_tc", nbytes, 2 * B * OH * OW * Cout * n * Cin):
+        if bf16_planes is not None and w is not None:      # hybrid: tf32 hi plane + bf16 cross-term planes
+            _check(lib().dfine_conv_tc_hybrid(_p(x), _p(w), _p(bf16_planes), _p(bias), _p(y), _p(stats), B, H, W, Cin,
+                                              c_long(ldx), OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0],
+                                              oo[1], in_stride, n, arr, c_long(ldw), c_long(bf16_planes.shape[-1]),
+                                              act, _stream()), what)
+        elif bf16_planes is not None:
             _check(lib().dfine_conv_tc_bf16x3(_p(x), _p(bf16_planes), _p(bias), _p(y), _p(stats), B, H, W, Cin,
                                               c_long(ldx), OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0],
                                               oo[1], in_stride, n, arr, c_long(bf16_planes.shape[-1]), act, _stream()),
@@ -230,7 +285,7 @@ def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, Y
         else:
             _check(lib().dfine_conv_tc(_p(x), _p(w), _p(w_lo), _p(bias), _p(y), _p(stats), B, H, W, Cin, c_long(ldx),
                                        OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0], oo[1], in_stride, n,
-                                       arr, c_long(ldw), act, _stream()), what)
+                                       arr, c_long(ldw), act, _p(res), c_long(ldres), _stream()), what)
 
 
 def _split_tf32(w2d):
@@ -241,14 +296,14 @@ def _split_tf32(w2d):
     return hi, lo
 
 
-def _split_bf16(w2d, taps, Cin):
+def _split_bf16(w2d, taps, Cin, mode=0):
     """bf16 (hi, lo) planes [2, rows, taps * Cin_p] of a re-laid weight matrix [rows, taps * Cin] for the 3xBF16
     forward; Cin_p = Cin rounded up to 8 elements (every tap starts on a 16-byte boundary for TMA; pads are zero)."""
     rows = w2d.shape[0]
     cin_p = (Cin + 7) // 8 * 8
     planes = torch.empty((2, rows, taps * cin_p), device=w2d.device, dtype=torch.bfloat16)
-    _check(lib().dfine_bf16_split(_p(w2d), c_long(w2d.shape[1]), _p(planes), c_long(rows), taps, Cin, cin_p, _stream()),
-           "bf16_split")
+    _check(lib().dfine_bf16_split(_p(w2d), c_long(w2d.shape[1]), _p(planes), c_long(rows), taps, Cin, cin_p, mode,
+                                  _stream()), "bf16_split")
     return planes
 
 
@@ -264,10 +319,15 @@ def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None):
         wr = wkey("wr", lambda: weight.reshape(Cout, Cin, k, k).permute(0, 2, 3, 1).reshape(Cout, K).contiguous())
         w_hi, w_lo, planes = wr, None, None
         if _MODE == "tc3":
-            w_hi, w_lo = wkey("wr3", lambda: _split_tf32(wr))
+            pl = _planes_of(weight)
+            w_hi, w_lo = pl if pl is not None else wkey("wr3", lambda: _split_tf32(wr))
         elif _MODE == "bf3":
             planes = wkey("wrb", lambda: _split_bf16(wr, k * k, Cin))
-        cs = Cin if planes is None else (Cin + 7) // 8 * 8        # channel run of one tap in the weight matrix
+            w_hi = None
+        elif _MODE == "tch":
+            w_hi, _ = wkey("wr3", lambda: _split_tf32(wr))
+            planes = wkey("wrh", lambda: _split_bf16(wr, k * k, Cin, mode=1))
+        cs = (Cin + 7) // 8 * 8 if _MODE == "bf3" else Cin        # channel run of one tap in the weight matrix
         taps = _taps(("f", k, pad[0], pad[1], cs),
                      lambda: [(kh - pad[0], kw - pad[1], (kh * k + kw) * cs) for kh in range(k) for kw in range(k)])
         _tc_launch(x, ldx, H, W, Cin, w_hi, w_lo, K, bias, y, ldy, B, OH, OW, Cout, OH, OW, (1, 1), (0, 0), stride,
@@ -284,10 +344,33 @@ def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None):
     return False
 
 
-def _conv_dgrad(dy, ldy, weight, wkey, dx, ldx, geom):
-    """dx[B,H,W,Cin] (pixel stride ldx) from dy[B,OH,OW,Cout]: the forward kernel run on dy with transposed taps;
-    a stride-2 conv's data gradient is one launch per output-pixel parity."""
+def _prefetch_dgrad_weight(weight, geom, ldx, ldy):
+    """Forward-time, on the weight-gradient stream: the [Cin, taps*Cout] weight copy the data gradient of this layer
+    will read.  It depends on the weights only, so it overlaps the forward pass instead of sitting in the backward
+    chain (one small strided copy per layer and step: the parameters change every step)."""
+    if not wgrad_stream.on or not torch.is_grad_enabled():
+        return
     B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
+    if not _tc_ok(Cout, Cin, k, stride, pad, ldy, ldx):
+        return
+    K = k * k * Cout
+    wkey = _wcache.getter(weight)
+    wgrad_stream.run(lambda: wkey("wd", lambda: weight.reshape(Cout, Cin, k, k).permute(1, 2, 3, 0).reshape(Cin, K).contiguous()))
+
+
+def _conv_dgrad(dy, ldy, weight, wkey, dx, ldx, geom, res=None):
+    """dx[B,H,W,Cin] (pixel stride ldx) from dy[B,OH,OW,Cout]: the forward kernel run on dy with transposed taps;
+    a stride-2 conv's data gradient is one launch per output-pixel parity.  ``res`` ([B,H,W,Cin], possibly a
+    channel slice with a larger pixel stride): added to dx — in the kernel epilogue on the stride-1 tensor-core path."""
+    B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
+    if res is not None:
+        ok = (res.dim() == 4 and res.stride(3) == 1 and res.stride(2) % 4 == 0 and res.stride(2) >= Cin
+              and res.stride(1) == W * res.stride(2) and res.stride(0) == H * W * res.stride(2)
+              and res.data_ptr() % 16 == 0)
+        if not (ok and stride == 1 and _tc_ok(Cout, Cin, k, stride, pad, ldy, ldx)):
+            _conv_dgrad(dy, ldy, weight, wkey, dx, ldx, geom)
+            dx.add_(res)
+            return
     if _tc_ok(Cout, Cin, k, stride, pad, ldy, ldx):
         K = k * k * Cout
         wd = wkey("wd", lambda: weight.reshape(Cout, Cin, k, k).permute(1, 2, 3, 0).reshape(Cin, K).contiguous())
@@ -295,7 +378,7 @@ def _conv_dgrad(dy, ldy, weight, wkey, dx, ldx, geom):
             taps = _taps(("d1", k, pad[0], pad[1], Cout),
                          lambda: [(pad[0] - kh, pad[1] - kw, (kh * k + kw) * Cout) for kh in range(k) for kw in range(k)])
             _tc_launch(dy, ldy, OH, OW, Cout, wd, None, K, None, dx, ldx, B, H, W, Cin, H, W, (1, 1), (0, 0), 1, taps,
-                       0, None, "conv_dgrad_tc")
+                       0, None, "conv_dgrad_tc", None, res, res.stride(2) if res is not None else 0)
             return
         for ph in range(2):
             for pw in range(2):
@@ -338,7 +421,7 @@ def _conv_wgrad(dy, ldy, x, ldx, geom, dst=None):
     dwr = dst if dst is not None else torch.zeros((Cout, k, k, Cin), device=dy.device, dtype=torch.float32)
     if _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy):
         nbytes = 4 * (B * H * W * Cin + B * OH * OW * Cout + 2 * Cout * k * k * Cin)
-        with _timed("conv_wgrad_tc", nbytes):
+        with _timed("conv_wgrad_tc", nbytes, 2 * B * OH * OW * Cout * k * k * Cin):
             _check(lib().dfine_conv_wgrad_tc(_p(dy), _p(x), _p(dwr), B, H, W, Cin, OH, OW, Cout, k, k, stride, pad[0],
                                              pad[1], c_long(ldx), c_long(ldy), _stream()), "conv_wgrad_tc")
     elif _MODE != "simt" and lib().dfine_stem_conv_supported(Cin, Cout, k, k, stride, pad[0], pad[1], pad[2], pad[3],
@@ -377,6 +460,33 @@ class _WCache:
 _wcache = _WCache()
 
 
+# tf32 hi / lo planes kept by the flat-arena optimizer (optim.FusedAdamW): id(param) -> (weakref, version, hi, lo).
+# The AdamW kernel rewrites them with the parameters; a parameter modified any other way (``_version`` moved: a
+# checkpoint load, an in-place init) is re-split on its next use.
+_arena_planes = {}
+
+
+def register_weight_planes(p, hi, lo):
+    _arena_planes[id(p)] = (weakref.ref(p), p._version, hi, lo)
+
+
+def _planes_of(weight):
+    ent = _arena_planes.get(id(weight))
+    if ent is None or ent[0]() is not weight:
+        return None
+    _, ver, hi, lo = ent
+    if ver != weight._version:       # rewritten outside the optimizer kernel: refresh this weight's planes
+        src = weight.detach()
+        src = src.permute(0, 2, 3, 1) if src.dim() == 4 else src
+        with torch.no_grad():
+            flat = src.reshape(hi.shape)
+            if flat.data_ptr() != weight.data_ptr():      # not the channels-last arena view any more
+                return None
+            _check(lib().dfine_tf32_split(_p(flat), _p(hi), _p(lo), c_long(hi.numel()), _stream()), "tf32_split")
+        _arena_planes[id(weight)] = (ent[0], weight._version, hi, lo)
+    return hi, lo
+
+
 def weights_changed():
     """Called by the optimizer after it rewrote parameters in place."""
     _wcache.epoch += 1
@@ -388,8 +498,9 @@ def weights_changed():
 class _ConvBnAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bn_w, bn_b, lab_s, lab_b, pre_add, post_add, running_mean, running_var, cfg):
-        stride, pad, groups, training, momentum, eps, act, frozen = cfg
+        stride, pad, groups, training, momentum, eps, act, frozen, tap = cfg
         _req_cuda(x, weight)
+        x_in = x
         if x.stride(-1) != 1 or x.dim() != 4:
             x = x.contiguous()
         B, H, W, Cin = x.shape
@@ -420,6 +531,8 @@ class _ConvBnAct(torch.autograd.Function):
             fused_stats = False
         else:
             fused_stats = _conv_fwd(x, ldx, weight, _wcache.getter(weight), None, conv_out, Cout, geom, 0, stats)
+            if ctx.needs_input_grad[0]:
+                _prefetch_dgrad_weight(weight, geom, ldx, Cout)
         if need_stats and not fused_stats:
             _check(lib().dfine_bn_stats(_p(conv_out), _p(stats), c_long(M), Cout, _stream()), "bn_stats")
         scale = torch.empty(Cout, device=dev, dtype=torch.float32)
@@ -445,12 +558,17 @@ class _ConvBnAct(torch.autograd.Function):
         ctx.geom, ctx.ldx, ctx.cfg = geom, ldx, cfg
         ctx.has_post = post_add is not None
         ctx.bn_b_ref = bn_b
+        if tap:
+            # second output = the input itself: a consumer that reads x besides this conv (the channel concat of an
+            # HG block) takes this alias instead, so its gradient arrives HERE (dtap) and is added to the data
+            # gradient in the dgrad kernel's epilogue — no separate gradient-accumulation kernel
+            return y, x_in
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dtap=None):
         x, weight, conv_out, scale, shift, mean, invstd, pre_add, lab_s, lab_b, bn_w = ctx.saved_tensors
-        stride, pad, groups, training, momentum, eps, act, frozen = ctx.cfg
+        stride, pad, groups, training, momentum, eps, act, frozen, tap = ctx.cfg
         B, H, W, Cin, OH, OW, Cout, k, _, _ = ctx.geom
         # dy is often a channel slice of a concatenation's gradient: consumed in place through its row stride
         ld_dy = dy.stride(2) if dy.dim() == 4 else 0
@@ -508,21 +626,24 @@ class _ConvBnAct(torch.autograd.Function):
                 g_x = torch.empty((B, H, W, Cin), device=dev, dtype=torch.float32)
                 _check(lib().dfine_dwconv_bwd_data(_p(dconv), _p(wt), _p(g_x), B, H, W, Cin, k, stride, pad[0],
                                                    _stream()), "dwconv_bwd_data")
+                if dtap is not None:
+                    g_x.add_(dtap)
             if ctx.needs_input_grad[1]:
                 dwt = torch.zeros((k * k, Cout), device=dev, dtype=torch.float32)
                 _check(lib().dfine_dwconv_bwd_weight(_p(dconv), _p(x), _p(dwt), B, H, W, Cin, k, stride, pad[0],
                                                      _stream()), "dwconv_bwd_weight")
                 g_w = dwt.t().reshape(Cout, 1, k, k)
         else:
-            if ctx.needs_input_grad[0]:
-                g_x = torch.empty((B, H, W, Cin), device=dev, dtype=torch.float32)
-                _conv_dgrad(dconv, Cout, weight, _wcache.getter(weight), g_x, Cin, ctx.geom)
-            if ctx.needs_input_grad[1]:
+            if ctx.needs_input_grad[1]:       # forked first: it then overlaps this layer's data gradient too
                 dst = _grad_dst(weight, "conv")
-                if dst is not None:
-                    _conv_wgrad(dconv, Cout, x, ldx, ctx.geom, dst)      # accumulated in place; autograd gets None
+                if dst is not None:      # accumulated in place on the weight-gradient stream; autograd gets None
+                    geom_ = ctx.geom
+                    wgrad_stream.run(lambda: _conv_wgrad(dconv, Cout, x, ldx, geom_, dst), dconv, x)
                 else:
                     g_w = _conv_wgrad(dconv, Cout, x, ldx, ctx.geom).permute(0, 3, 1, 2)
+            if ctx.needs_input_grad[0]:
+                g_x = torch.empty((B, H, W, Cin), device=dev, dtype=torch.float32)
+                _conv_dgrad(dconv, Cout, weight, _wcache.getter(weight), g_x, Cin, ctx.geom, dtap)
         g_post = (dy if dy.is_contiguous() else dy.contiguous()) if ctx.has_post else None
         return g_x, g_w, g_bn_w, g_bn_b, g_lab_s, g_lab_b, dpre, g_post, None, None, None
 
@@ -540,6 +661,8 @@ class _Linear(torch.autograd.Function):
         geom = (1, 1, M, Kd, 1, M, N, 1, 1, (0, 0, 0, 0))
         fused_act = act if act in (None, "relu") else None
         _conv_fwd(x2, ldx, w, _wcache.getter(w), b, out, N, geom, ACT[fused_act])
+        if ctx.needs_input_grad[0]:
+            _prefetch_dgrad_weight(w, geom, ldx, N)
         saved_z = None
         if act is not None and fused_act is None:
             saved_z = out
@@ -561,13 +684,11 @@ class _Linear(torch.autograd.Function):
             _check(lib().dfine_act_bwd(_p(dy), _p(z), _p(dz), c_long(dy.numel()), ACT[act], _stream()), "act_bwd")
             dy = dz
         g_x = g_w = g_b = None
-        if ctx.needs_input_grad[0]:
-            g_x = torch.empty(xshape, device=dy.device, dtype=torch.float32)
-            _conv_dgrad(dy, N, w, _wcache.getter(w), g_x, Kd, geom)
         if ctx.needs_input_grad[1]:
             dst = _grad_dst(w, "flat")
             if dst is not None:
-                _conv_wgrad(dy, N, x2, ldx, geom, dst.view(N, 1, 1, Kd))
+                dst4 = dst.view(N, 1, 1, Kd)
+                wgrad_stream.run(lambda: _conv_wgrad(dy, N, x2, ldx, geom, dst4), dy, x2)
             else:
                 g_w = _conv_wgrad(dy, N, x2, ldx, geom).reshape(N, Kd)
         if has_bias and ctx.needs_input_grad[2]:
@@ -575,7 +696,14 @@ class _Linear(torch.autograd.Function):
             dst = _grad_dst(b_, "flat") if b_ is not None else None
             if dst is None:
                 g_b = dst = torch.zeros(N, device=dy.device, dtype=torch.float32)
-            _check(lib().dfine_colsum(_p(dy), _p(dst), c_long(M), N, c_long(N), _stream()), "colsum")
+                _check(lib().dfine_colsum(_p(dy), _p(dst), c_long(M), N, c_long(N), _stream()), "colsum")
+            else:
+                dstb = dst
+                wgrad_stream.run(lambda: _check(lib().dfine_colsum(_p(dy), _p(dstb), c_long(M), N, c_long(N), _stream()),
+                                                "colsum"), dy)
+        if ctx.needs_input_grad[0]:
+            g_x = torch.empty(xshape, device=dy.device, dtype=torch.float32)
+            _conv_dgrad(dy, N, w, _wcache.getter(w), g_x, Kd, geom)
         return g_x, g_w, g_b, None
 
 
@@ -738,6 +866,25 @@ class _FdrHead(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # small spatial ops
 # ------------------------------------------------------------------------------------------------
+class _SplitLast(torch.autograd.Function):
+    """x -> (x[..., :c], x[..., c:]) as views.  Autograd's own slicing would answer each half with a zero-filled
+    full-size gradient and add the two (fill + copy twice, then an add); here the backward is one concatenation."""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        ctx.c, ctx.n = c, x.shape[-1]
+        return x[..., :c], x[..., c:]
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        ref = ga if ga is not None else gb
+        if ga is None:
+            ga = ref.new_zeros(ref.shape[:-1] + (ctx.c,))
+        if gb is None:
+            gb = ref.new_zeros(ref.shape[:-1] + (ctx.n - ctx.c,))
+        return torch.cat([ga, gb], -1), None
+
+
 class _MaxPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
@@ -792,13 +939,17 @@ class CudaOps:
     # ---- conv / norm ----
     def conv_bn_act(self, x, w, stride, pad, groups, bn_w, bn_b, running_mean, running_var, num_batches_tracked,
                     training, momentum=0.1, eps=1e-5, act=None, lab_scale=None, lab_bias=None, pre_add=None,
-                    post_add=None):
+                    post_add=None, tap=False):
         frozen = num_batches_tracked is None
         if training and num_batches_tracked is not None:
             num_batches_tracked.add_(1)
-        cfg = (stride, tuple(pad), groups, bool(training), float(momentum), float(eps), act, frozen)
-        return _ConvBnAct.apply(x, w, bn_w, bn_b, lab_scale, lab_bias, pre_add, post_add, running_mean, running_var,
-                                cfg)
+        # tap: also return the input as a second output (see _ConvBnAct.forward); plain pass-through without autograd
+        tap_ag = bool(tap) and _TAP and torch.is_grad_enabled() and x.requires_grad
+        cfg = (stride, tuple(pad), groups, bool(training), float(momentum), float(eps), act, frozen, tap_ag)
+        out = _ConvBnAct.apply(x, w, bn_w, bn_b, lab_scale, lab_bias, pre_add, post_add, running_mean, running_var, cfg)
+        if tap and not tap_ag:
+            return out, x
+        return out
 
     def maxpool2x2_s1_padbr(self, x):
         return _MaxPool.apply(x)
@@ -808,6 +959,9 @@ class CudaOps:
 
     def cat(self, xs, dim=-1):
         return torch.cat(list(xs), dim)
+
+    def split_last(self, x, c):
+        return _SplitLast.apply(x, c)
 
     # ---- dense ----
     def linear(self, x, w, b=None, act=None):

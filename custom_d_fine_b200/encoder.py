@@ -27,7 +27,10 @@ class RepVGG(nn.Module):
         self.conv2 = _cn(cin, cout, 1, act=act)  # act runs after the branch sum (pre_add)
 
     def forward(self, x):
-        return self.conv2(x, pre_add=self.conv1(x))
+        # x feeds both branches: the 1x1 branch reads the 3x3 conv's `tap` alias of x, so its data gradient is added
+        # inside the 3x3 conv's data-gradient kernel instead of by a separate accumulation kernel
+        a, xa = self.conv1(x, tap=True)
+        return self.conv2(xa, pre_add=a)
 
 
 class CSP(nn.Module):
@@ -38,11 +41,13 @@ class CSP(nn.Module):
         self.bottlenecks = nn.Sequential(*[RepVGG(cout, cout, act) for _ in range(n)])
         # expansion == 1.0 everywhere => hidden == out => the reference's conv3 is Identity
 
-    def forward(self, x):
-        a = self.conv1(x)
+    def forward(self, x, tap=False):
+        a, xa = self.conv1(x, tap=True)
         for blk in self.bottlenecks:
             a = blk(a)
-        return self.conv2(x, post_add=a)
+        if tap:      # hand the alias chain on: a further reader of x (the ELAN concat) routes its gradient through here
+            return self.conv2(xa, post_add=a, tap=True)
+        return self.conv2(xa, post_add=a)
 
 
 class ELANBlock(nn.Module):
@@ -58,10 +63,12 @@ class ELANBlock(nn.Module):
 
     def forward(self, x):
         y = self.cv1(x)
-        y2 = y[..., self.c:]
-        y3 = self.cv2[1](self.cv2[0](y2))
-        y4 = self.cv3[1](self.cv3[0](y3))
-        return self.cv4(K.cat([y, y3, y4]))
+        y1, y2 = K.split_last(y, self.c)           # views; one concatenation kernel in the backward
+        t, y2 = self.cv2[0](y2, tap=True)          # the concat below reads the tap aliases of y2 / y3
+        y3 = self.cv2[1](t)
+        t, y3a = self.cv3[0](y3, tap=True)
+        y4 = self.cv3[1](t)
+        return self.cv4(K.cat([y1, y2, y3a, y4]))
 
 
 class SCDown(nn.Module):

@@ -81,8 +81,12 @@ class FusedAdamW(torch.optim.Optimizer):
             gflat = torch.zeros_like(pflat)
             for p, o in zip(ps, offs):
                 p.grad = _arena_view(gflat, o, p)          # same layout as the parameter: kernels accumulate in place
-            self._arenas.append(dict(params=ps, offs=offs, p=pflat, g=gflat, m=torch.zeros_like(pflat),
-                                     v=torch.zeros_like(pflat), ema=None))
+            a = dict(params=ps, offs=offs, p=pflat, g=gflat, m=torch.zeros_like(pflat), v=torch.zeros_like(pflat),
+                     ema=None, planes=None)
+            if any(p.dim() >= 2 for p in ps):
+                # 3xTF32 weight planes (hi | lo) in the arena's element order, rewritten by the AdamW kernel itself
+                a["planes"] = torch.empty((2, pflat.numel()), dtype=torch.float32, device=pflat.device)
+            self._arenas.append(a)
         self._dev = dev
         n = len(self.param_groups)
         self._hyper = torch.zeros((n, 4), dtype=torch.float32, device=dev)
@@ -90,6 +94,23 @@ class FusedAdamW(torch.optim.Optimizer):
         self._gnorm = torch.zeros(1, dtype=torch.float64, device=dev)
         self._buf_src = self._buf_ema = None
         self._mom = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._register_planes()
+
+    def _register_planes(self):
+        """Split every arena once and tell the kernel table where each dense weight's tf32 hi / lo planes live."""
+        from . import cuda_ops
+        for a in self._arenas:
+            if a is None or a["planes"] is None:
+                continue
+            hi, lo = a["planes"][0], a["planes"][1]
+            cuda_ops._check(cuda_ops.lib().dfine_tf32_split(cuda_ops._p(a["p"]), cuda_ops._p(hi), cuda_ops._p(lo),
+                                                            ctypes.c_long(a["p"].numel()), cuda_ops._stream()),
+                            "tf32_split")
+            for p, o in zip(a["params"], a["offs"]):
+                if p.dim() >= 2:
+                    n = p.numel()
+                    rows = p.shape[0]
+                    cuda_ops.register_weight_planes(p, hi[o:o + n].view(rows, n // rows), lo[o:o + n].view(rows, n // rows))
 
     # ---- wiring -------------------------------------------------------------------------------
     def attach_ema(self, ema, student):
@@ -181,7 +202,9 @@ class FusedAdamW(torch.optim.Optimizer):
             _check(L.dfine_adamw_ema(_p(a["p"]), _p(a["g"]), _p(a["m"]), _p(a["v"]), _p(a["ema"]),
                                      ctypes.c_long(a["p"].numel()), ctypes.c_void_p(self._hyper[i].data_ptr()),
                                      _p(self._gnorm) if use_clip else None, ctypes.c_float(self.max_norm),
-                                     ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(g["eps"]), 1, _stream()),
+                                     ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(g["eps"]), 1,
+                                     _p(a["planes"][0]) if a["planes"] is not None else None,
+                                     _p(a["planes"][1]) if a["planes"] is not None else None, _stream()),
                    "adamw_ema")
         if self._buf_src is not None:
             _check(L.dfine_ema_blend(_p(self._buf_ema), _p(self._buf_src), ctypes.c_long(self._buf_src.numel()),

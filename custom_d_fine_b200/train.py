@@ -18,11 +18,19 @@ def _begin_step(inputs):
     if inputs.is_cuda:
         from . import cuda_ops
         cuda_ops.zero_pool.begin_step(inputs.device)
+        cuda_ops.wgrad_stream.begin(inputs.device)
+
+
+def _after_forward():
+    """The weight-gradient stream prepared the backward's re-laid weights during the forward: rejoin it."""
+    from . import cuda_ops
+    cuda_ops.wgrad_stream.sync_main()
 
 
 def _end_step():
     from . import cuda_ops
     cuda_ops.zero_pool.end_step()
+    cuda_ops.wgrad_stream.join()     # the weight-gradient stream rejoins the step before the optimizer reads the arenas
 
 
 class DevicePrefetcher:
@@ -177,6 +185,7 @@ class TrainStep:
         """inputs float32 [B,3,H,W] on the device; targets list of dicts (labels int64 [T], boxes [T,4])."""
         _begin_step(inputs)
         output = self.model(inputs, targets=targets)
+        _after_forward()
         loss_dict = self.loss_fn(output, targets)
         loss = sum(loss_dict.values()) / self.accum_steps
         loss.backward()
@@ -212,6 +221,14 @@ class GraphedTrainStep(TrainStep):
         # Warm-up steps and captures share ONE side stream: autograd's AccumulateGrad nodes remember the stream
         # they were created on, and a node created on the legacy default stream cannot be used under capture.
         self._side = torch.cuda.Stream() if next(self.model.parameters()).is_cuda else None
+
+    def host_gap_ms(self):
+        """Device idle time between graph A and graph B of the last replayed step (host index planning)."""
+        ev = getattr(self, "_last_gap", None)
+        if ev is None:
+            return None
+        ev[1].synchronize()
+        return ev[0].elapsed_time(ev[1])
 
     def _can_graph(self):
         return (self.accum_steps == 1 and self.fused and not isinstance(self.model, DDP)
@@ -259,6 +276,7 @@ class GraphedTrainStep(TrainStep):
             _begin_step(g["x"])
             out = self.model(g["x"], targets=g["targets"])
             raw, tg = crit.match(out, g["targets"])
+            _after_forward()
         gB = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gB, pool=gA.pool(), stream=self._side):
             loss_dict = crit.compute(out, tg, g["table"], g["counts"], plan)
@@ -280,9 +298,13 @@ class GraphedTrainStep(TrainStep):
             s["boxes"].copy_(t["boxes"], non_blocking=True)
         self._host_prepare()
         g["gA"].replay()
+        ev = g.setdefault("gap_events", (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+        ev[0].record()
         plan = self.loss_fn.plan(g["out"], g["targets"], g["raw"], g["plan"])     # syncs on the matcher D2H
         g["table"].copy_(plan.table, non_blocking=True)
         g["counts"].copy_(plan.counts, non_blocking=True)
+        ev[1].record()                                   # ev[0] -> ev[1] = device idle time while the host plans
+        self._last_gap = ev
         g["gB"].replay()
         self.optimizer.allreduce_grads()
         g["gC"].replay()

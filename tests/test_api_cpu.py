@@ -68,3 +68,47 @@ def test_trainer_runs_the_reference_loop_on_cpu(tmp_path):
     assert tr.optimizer.param_groups[3]["lr"] != lr0, "OneCycleLR must advance once per optimizer step"
     ckpt = torch.load(tmp_path / "last.pt", weights_only=True)
     assert set(ckpt) == set(tr.model.state_dict()), "last.pt is a bare state_dict with the reference's keys"
+
+
+def test_go_union_fast_paths_equal_the_reference_formulation():
+    """The host index planning between the two CUDA graphs of a step evaluates the reference's GO union
+    (dfine_criterion.py:570-591: torch.unique(pairs, dim=0) + unstable argsort of the counts + first pair per query)
+    on scalar keys / numpy; both fast paths must reproduce the reference formulation pair for pair, in order."""
+    import numpy as np
+    import torch
+    from custom_d_fine_b200.criterion import DFINECriterion, IndexPlan
+
+    def ref_union(q, t):
+        ind = torch.cat([q[:, None], t[:, None]], 1)
+        unique, counts = torch.unique(ind, return_counts=True, dim=0)
+        order = torch.argsort(counts, descending=True)
+        seen = {}
+        for r, c in unique[order].tolist():
+            if r not in seen:
+                seen[r] = c
+        return list(seen.keys()), list(seen.values())
+
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        T, S = int(rng.integers(1, 30)), int(rng.integers(1, 8))
+        Q = int(rng.integers(T, 40))                      # few queries: many queries matched to several targets
+        oq = np.stack([np.sort(rng.choice(Q, T, replace=False)) for _ in range(S)])
+        ot = np.stack([rng.permutation(T) for _ in range(S)])
+        q, t = torch.from_numpy(oq.reshape(-1)), torch.from_numpy(ot.reshape(-1))
+        want = ref_union(q, t)
+        got = DFINECriterion._go_union(q, t)
+        assert want[0] == got[0].tolist() and want[1] == got[1].tolist()
+        plan = IndexPlan([T], Q, S, None, 0)
+        (hq, ht), = DFINECriterion.go_indices_host(oq, ot, plan)
+        assert want[0] == hq.tolist() and want[1] == ht.tolist()
+    # table filling: vectorised path == per-image path
+    B, S, T, Q = 5, 6, 7, 300
+    oq = np.stack([np.concatenate([np.sort(rng.choice(Q, T, replace=False)) for _ in range(B)]) for _ in range(S)])
+    ot = np.stack([np.concatenate([rng.permutation(T) for _ in range(B)]) for _ in range(S)])
+    p1, p2 = IndexPlan([T] * B, Q, S, None, 0), IndexPlan([T] * B, Q, S, None, 0)
+    lists = p1.fill(oq, ot)
+    p2.fill(oq, ot, want_lists=False)
+    assert torch.equal(p1.table, p2.table)
+    n1 = p1.fill_go(DFINECriterion.go_indices(lists[0], lists[1:]))
+    n2 = p2.fill_go(DFINECriterion.go_indices_host(oq, ot, p2))
+    assert n1 == n2 and torch.equal(p1.table, p2.table)

@@ -251,7 +251,7 @@ def test_tc_matches_simt(cuda_ops, case):
     res = {}
     prev = co.get_gemm_mode()
     try:
-        for mode in ("simt", "tc", "tc3", "bf3"):
+        for mode in ("simt", "tc", "tc3", "tch", "bf3"):
             co.set_gemm_mode(mode)
             cache = co._WCache()
             y = torch.zeros(B, OH, OW, Cout).cuda()
@@ -261,12 +261,17 @@ def test_tc_matches_simt(cuda_ops, case):
             dx = torch.full((B, H, W, Cin), float("nan")).cuda()
             co._conv_dgrad(dy, Cout, weight, cache.getter(weight), dx, Cin, geom)
             dw = co._conv_wgrad(dy, Cout, x, Cin, geom)
+            if mode == "tc":     # residual folded into the data-gradient epilogue (a channel slice: pixel stride Cin + 8)
+                rfull = torch.randn(B, H, W, Cin + 8, generator=g).cuda()
+                dxr = torch.full((B, H, W, Cin), float("nan")).cuda()
+                co._conv_dgrad(dy, Cout, weight, cache.getter(weight), dxr, Cin, geom, rfull[..., 4:4 + Cin])
+                check_close(f"dgrad + residual {case}", dxr, dx + rfull[..., 4:4 + Cin], 1e-6)
             torch.cuda.synchronize()
             res[mode] = (y, stats, dx, dw)
     finally:
         co.set_gemm_mode(prev)
     y0, _, dx0, dw0 = res["simt"]
-    for mode, tol in (("tc", TF32), ("tc3", 2e-5), ("bf3", 5e-5)):   # bf3: 16 mantissa bits per operand
+    for mode, tol in (("tc", TF32), ("tc3", 2e-5), ("tch", 2e-5), ("bf3", 5e-5)):   # bf3: 16 mantissa bits per operand
         y, stats, dx, dw = res[mode]
         check_close(f"{mode} fwd {case}", y, y0, tol)
         check_close(f"{mode} fused stats sum", stats[:Cout].float(), y0.reshape(M, Cout).sum(0), max(tol, 1e-4) * 5)

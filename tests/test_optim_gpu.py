@@ -64,3 +64,9 @@ def test_fused_adamw_ema_matches_torch(cuda_ops):
             if es[k].dtype.is_floating_point:
                 check_close(f"ema {k} step {it}", ed[k], es[k], 5e-6)
     assert math.isfinite(float(opt_dev.grad_norm()))
+    # the AdamW kernel also maintains the 3xTF32 weight planes: hi is tf32-representable, hi + lo is the parameter
+    for a in opt_dev._arenas:
+        if a is not None and a["planes"] is not None:
+            hi, lo = a["planes"][0], a["planes"][1]
+            assert torch.equal(hi + lo, a["p"])
+            assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
