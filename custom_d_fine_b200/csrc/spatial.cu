@@ -159,6 +159,51 @@ __global__ void __launch_bounds__(NT) dwconv_bwd_data_blocked(const float* __res
     }
 }
 
+// 3x3 / stride 2 / pad 1 data gradient (HG_Stage.downsample, SCDown): one thread = a 2x2 block of input pixels
+// (even row, even column origin) x 4 channels.  With stride 2 an input pixel receives 1, 2, 2 or 4 taps depending on
+// its row / column parity, all from the four outputs (oh, ow), (oh, ow+1), (oh+1, ow), (oh+1, ow+1), oh = ih0 / 2:
+// four dy loads feed four stores (the generic kernel walked 9 taps with modulo tests per input pixel).
+__global__ void __launch_bounds__(NT) dwconv3x3s2_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                                  float* __restrict__ dx, int B, int H, int W, int C,
+                                                                  int OH, int OW) {
+    const int VC = C / 4, HB = (H + 1) / 2, WB = (W + 1) / 2;
+    const long total = (long)B * HB * WB * VC;
+    for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
+        const int cv = (int)(i % VC);
+        long p = i / VC;
+        const int ow = (int)(p % WB); p /= WB;
+        const int oh = (int)(p % HB);
+        const int b = (int)(p / HB);
+        const int ih0 = 2 * oh, iw0 = 2 * ow;
+        const float4 z = make_float4(0, 0, 0, 0);
+        const float* base = dy + ((long)b * OH * OW) * C + cv * 4;
+        const bool r0 = oh < OH, r1 = oh + 1 < OH, c0 = ow < OW, c1 = ow + 1 < OW;
+        const float4 g00 = (r0 && c0) ? ld4(base + ((long)oh * OW + ow) * C) : z;
+        const float4 g01 = (r0 && c1) ? ld4(base + ((long)oh * OW + ow + 1) * C) : z;
+        const float4 g10 = (r1 && c0) ? ld4(base + ((long)(oh + 1) * OW + ow) * C) : z;
+        const float4 g11 = (r1 && c1) ? ld4(base + ((long)(oh + 1) * OW + ow + 1) * C) : z;
+        const float* wc = w + cv * 4;
+        float4 a;
+        // (even row, even col): ih = 2 oh + kh - 1 -> kh = 1; iw likewise kw = 1
+        a = z; fma4(a, g00, ld4(wc + (long)(1 * 3 + 1) * C));
+        st4(dx + ((((long)b * H + ih0) * W + iw0) * VC + cv) * 4, a);
+        if (iw0 + 1 < W) {   // (even, odd): kw = 0 from output ow + 1, kw = 2 from output ow
+            a = z; fma4(a, g01, ld4(wc + (long)(1 * 3 + 0) * C)); fma4(a, g00, ld4(wc + (long)(1 * 3 + 2) * C));
+            st4(dx + ((((long)b * H + ih0) * W + iw0 + 1) * VC + cv) * 4, a);
+        }
+        if (ih0 + 1 < H) {   // (odd, even): kh = 0 from output oh + 1, kh = 2 from output oh
+            a = z; fma4(a, g10, ld4(wc + (long)(0 * 3 + 1) * C)); fma4(a, g00, ld4(wc + (long)(2 * 3 + 1) * C));
+            st4(dx + ((((long)b * H + ih0 + 1) * W + iw0) * VC + cv) * 4, a);
+            if (iw0 + 1 < W) {
+                a = z;
+                fma4(a, g11, ld4(wc + (long)(0 * 3 + 0) * C)); fma4(a, g10, ld4(wc + (long)(0 * 3 + 2) * C));
+                fma4(a, g01, ld4(wc + (long)(2 * 3 + 0) * C)); fma4(a, g00, ld4(wc + (long)(2 * 3 + 2) * C));
+                st4(dx + ((((long)b * H + ih0 + 1) * W + iw0 + 1) * VC + cv) * 4, a);
+            }
+        }
+    }
+}
+
 // dw[tap, c] += sum_pixels dy * x_shifted.  CTA = slab of output pixels; lanes tile [pixels, C/4];
 // per-thread register accumulators for all taps (K*K float4), merged through shared atomics.
 template <int K, int S>
@@ -409,6 +454,9 @@ DFINE_API int dfine_dwconv_bwd_data(const float* dy, const float* w, float* dx, 
         dwconv_bwd_data_blocked<5><<<ew_grid(blocked), NT, 0, st>>>(dy, w, dx, B, H, W, C, OH, OW, pad);
     else if (k == 3 && stride == 1)
         dwconv_bwd_data_blocked<3><<<ew_grid(blocked), NT, 0, st>>>(dy, w, dx, B, H, W, C, OH, OW, pad);
+    else if (k == 3 && stride == 2 && pad == 1)
+        dwconv3x3s2_bwd_data_kernel<<<ew_grid((long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4)), NT, 0, st>>>(
+            dy, w, dx, B, H, W, C, OH, OW);
     else
         dwconv_bwd_data_kernel<<<ew_grid(total), NT, 0, st>>>(dy, w, dx, B, H, W, C, OH, OW, k, stride, pad);
     DFINE_LAUNCH_CHECK("dwconv_bwd_data");
@@ -424,7 +472,9 @@ DFINE_API int dfine_dwconv_bwd_weight(const float* dy, const float* x, float* dw
     DFINE_REQUIRE(stride == 1 || stride == 2, "dwconv_bwd_weight: stride %d", stride);
     const long P = (long)B * OH * ((OW + PX - 1) / PX);      // blocks of PX output pixels along W
     if (P == 0) return 0;
-    long ppc = (P + 148L * 4 - 1) / (148L * 4);
+    // one CTA per SM: every CTA ends with k*k*C global atomics on the same k*k*C addresses, which bounded the small
+    // 5x5 layers (400 CTAs x 3200 atomics for 13 MB of operands: 40 us) — fewer, longer CTAs
+    long ppc = (P + 148L - 1) / 148L;
     if (ppc < 16) ppc = 16;
     const size_t smem = (size_t)k * k * C * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;

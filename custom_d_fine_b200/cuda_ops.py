@@ -155,9 +155,12 @@ class _WgradStream:
 
     def __init__(self):
         self.stream, self.on, self.used, self.keep = None, False, False, []
+        self.in_step = False       # between train._begin_step and train._end_step (also when the stream itself is off)
         self.disabled = False      # bench.py serialises the step while it brackets single kernels with events
 
     def begin(self, device):
+        _msda_shared.clear()
+        self.in_step = True
         if self.disabled or os.environ.get("DFINE_WGRAD_STREAM", "1") == "0":
             return
         if self.stream is None or self.stream.device != device:
@@ -185,7 +188,7 @@ class _WgradStream:
 
     def join(self):
         self.sync_main()
-        self.on = False
+        self.on = self.in_step = False
 
 
 wgrad_stream = _WgradStream()
@@ -233,7 +236,10 @@ def _rows(x):
 #   "tc"   plain kind::tf32 everywhere (the precision class of the reference's cuDNN convolutions on GPU);
 #   "simt" fp32 CUDA-core kernels of the same library (strict-fp32 parity runs and kernel bring-up).
 _MODE = os.environ.get("DFINE_GEMM", "tc3")
-_TAP = os.environ.get("DFINE_TAP", "1") != "0"      # A/B switch: gradient-routing aliases (fused accumulation adds)
+# Gradient-routing aliases (`tap`): fold the gradient-accumulation add of a tensor with two consumers into the data-
+# gradient kernel's epilogue.  Measured on B200 (profiles/README.md): the extra epilogue read makes the persistent dgrad
+# kernels epilogue-bound and the step 0.8 ms SLOWER than the separate add kernels -> off by default, kept for A/B.
+_TAP = os.environ.get("DFINE_TAP", "0") == "1"
 
 
 def set_gemm_mode(mode: str) -> None:
@@ -786,10 +792,21 @@ class _Attention(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # multi-scale deformable attention
 # ------------------------------------------------------------------------------------------------
+# d(memory) of the decoder's deformable-attention layers.  Every layer gathers from the SAME memory tensor, so autograd
+# would receive one zero-filled [B, L, 256] gradient per layer and add them (4 fills + 3 adds of 137 MB each at batch
+# 16).  The layers scatter with red.add anyway: they share ONE buffer per memory tensor — the first backward to run
+# zero-fills it, the others accumulate, and only the last one hands it to autograd (the others return None).
+_msda_shared = {}
+
+
 class _Msda(torch.autograd.Function):
     @staticmethod
     def forward(ctx, memory, proj, ref, pscale, shapes, points, heads, n_off, offset_scale):
         _req_cuda(memory, proj, ref)
+        ctx.share_key = None
+        if memory.requires_grad and torch.is_grad_enabled() and wgrad_stream.in_step:   # inside a train step only
+            ctx.share_key = (memory.data_ptr(), memory._version, tuple(memory.shape))
+            _msda_shared.setdefault(ctx.share_key, [0, None])[0] += 1
         memory, proj = memory.contiguous(), proj.contiguous()
         ref = ref.detach().contiguous().float()
         B, L, D = memory.shape
@@ -817,7 +834,17 @@ class _Msda(torch.autograd.Function):
         hw = (c_int * (2 * len(shapes)))(*[int(v) for s in shapes for v in s])
         pts = (c_int * len(points))(*[int(p) for p in points])
         ld = proj.shape[-1]
-        gmem = torch.zeros_like(memory)
+        ent = _msda_shared.get(ctx.share_key) if ctx.share_key is not None else None
+        if ent is not None:
+            if ent[1] is None:
+                ent[1] = torch.zeros_like(memory)
+            gmem = ent[1]
+            ent[0] -= 1
+            last = ent[0] == 0
+            if last:
+                del _msda_shared[ctx.share_key]
+        else:
+            gmem, last = torch.zeros_like(memory), True
         gproj = torch.empty_like(proj)
         # value/offsets/logits/ref/gout read, gvalue read-modify-write (2x), goff/glogit written
         nbytes = 4 * (memory.numel() + proj.numel() + ref.numel() + gout.numel() + 2 * gmem.numel() + gproj.numel())
@@ -826,7 +853,7 @@ class _Msda(torch.autograd.Function):
                                     c_long(ld), _p(ref), _p(pscale), _p(gout), _p(gmem), _p(gproj), c_long(ld),
                                     c_void_p(gproj.data_ptr() + 4 * n_off), c_long(ld), B, Q, L, heads, hd,
                                     len(shapes), hw, pts, c_float(offset_scale), _stream()), "msda_bwd")
-        return gmem, gproj, None, None, None, None, None, None, None
+        return (gmem if last else None), gproj, None, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -866,25 +893,6 @@ class _FdrHead(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # small spatial ops
 # ------------------------------------------------------------------------------------------------
-class _SplitLast(torch.autograd.Function):
-    """x -> (x[..., :c], x[..., c:]) as views.  Autograd's own slicing would answer each half with a zero-filled
-    full-size gradient and add the two (fill + copy twice, then an add); here the backward is one concatenation."""
-
-    @staticmethod
-    def forward(ctx, x, c):
-        ctx.c, ctx.n = c, x.shape[-1]
-        return x[..., :c], x[..., c:]
-
-    @staticmethod
-    def backward(ctx, ga, gb):
-        ref = ga if ga is not None else gb
-        if ga is None:
-            ga = ref.new_zeros(ref.shape[:-1] + (ctx.c,))
-        if gb is None:
-            gb = ref.new_zeros(ref.shape[:-1] + (ctx.n - ctx.c,))
-        return torch.cat([ga, gb], -1), None
-
-
 class _MaxPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
@@ -959,9 +967,6 @@ class CudaOps:
 
     def cat(self, xs, dim=-1):
         return torch.cat(list(xs), dim)
-
-    def split_last(self, x, c):
-        return _SplitLast.apply(x, c)
 
     # ---- dense ----
     def linear(self, x, w, b=None, act=None):

@@ -63,12 +63,10 @@ class ELANBlock(nn.Module):
 
     def forward(self, x):
         y = self.cv1(x)
-        y1, y2 = K.split_last(y, self.c)           # views; one concatenation kernel in the backward
-        t, y2 = self.cv2[0](y2, tap=True)          # the concat below reads the tap aliases of y2 / y3
-        y3 = self.cv2[1](t)
-        t, y3a = self.cv3[0](y3, tap=True)
-        y4 = self.cv3[1](t)
-        return self.cv4(K.cat([y1, y2, y3a, y4]))
+        y2 = y[..., self.c:]
+        y3 = self.cv2[1](self.cv2[0](y2))
+        y4 = self.cv3[1](self.cv3[0](y3))
+        return self.cv4(K.cat([y, y3, y4]))
 
 
 class SCDown(nn.Module):

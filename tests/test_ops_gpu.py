@@ -82,6 +82,7 @@ CONV_CASES = [
     ("stem2a_2x2_padbr", 2, 32, 32, 24, 12, 2, 1, (0, 0, 1, 1), 1, "relu", True, False, False, True, TF32),
     ("stem3_3x3s2", 2, 32, 32, 48, 24, 3, 2, (1, 1, 1, 1), 1, "relu", True, False, False, True, TF32),
     ("dw3x3s2", 2, 40, 40, 96, 96, 3, 2, (1, 1, 1, 1), 96, None, False, False, False, True, F32),
+    ("dw3x3s2_odd", 2, 37, 41, 32, 32, 3, 2, (1, 1, 1, 1), 32, None, False, False, False, True, F32),
     ("dw5x5", 2, 20, 20, 128, 128, 5, 1, (2, 2, 2, 2), 128, "relu", True, False, False, True, F32),
     ("pw1x1_tc", 2, 40, 40, 160, 48, 1, 1, (0, 0, 0, 0), 1, "relu", True, False, False, True, TF32),
     ("pw1x1_tc_big", 2, 20, 20, 896, 384, 1, 1, (0, 0, 0, 0), 1, "relu", True, False, True, True, TF32),
