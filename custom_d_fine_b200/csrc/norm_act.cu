@@ -119,6 +119,56 @@ __global__ void __launch_bounds__(NT) bn_apply_kernel(const float* __restrict__ 
     }
 }
 
+// Train-mode finalize + apply in one launch: every CTA derives the per-channel scale / shift table from the batch
+// statistics into shared memory (C double rsqrt's per CTA, noise next to the pass over the tensor), CTA 0 also
+// publishes mean / invstd / scale / shift for the backward and updates the running statistics.  Removes one tiny
+// dependent launch per BatchNorm layer from the forward chain (133 per step for D-FINE-m).
+__global__ void __launch_bounds__(NT) bn_finalize_apply_kernel(
+    const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ weight,
+    const float* __restrict__ bias, float* __restrict__ running_mean, float* __restrict__ running_var,
+    float* __restrict__ mean_out, float* __restrict__ invstd_out, float* __restrict__ scale_out,
+    float* __restrict__ shift_out, const float* __restrict__ pre_add, const float* __restrict__ post_add,
+    const float* __restrict__ lab, const float* __restrict__ lab_b, float* __restrict__ y, long M, int C, float momentum,
+    float eps, int act) {
+    extern __shared__ float tab[];   // [C] scale | [C] shift
+    for (int c = threadIdx.x; c < C; c += NT) {
+        const double mean = stats[c] / (double)M;
+        double var = stats[C + c] / (double)M - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float w = weight ? weight[c] : 1.f, b = bias ? bias[c] : 0.f;
+        const float sc = w * invstd, sh = b - (float)mean * sc;
+        tab[c] = sc;
+        tab[C + c] = sh;
+        if (blockIdx.x == 0) {
+            mean_out[c] = (float)mean;
+            invstd_out[c] = invstd;
+            scale_out[c] = sc;
+            shift_out[c] = sh;
+            if (running_mean) {
+                const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+            }
+        }
+    }
+    __syncthreads();
+    const float ls = lab ? __ldg(lab) : 1.f, lb = lab ? __ldg(lab_b) : 0.f;
+    const int VC = C / 4;
+    const long n4 = M * VC;
+    for (long i = (long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long)gridDim.x * NT) {
+        const int c = (int)(i % VC) * 4;
+        const float4 v = ld4(x + i * 4);
+        const float4 sc = *reinterpret_cast<const float4*>(tab + c), sh = *reinterpret_cast<const float4*>(tab + C + c);
+        float4 z = make_float4(v.x * sc.x + sh.x, v.y * sc.y + sh.y, v.z * sc.z + sh.z, v.w * sc.w + sh.w);
+        if (pre_add) { const float4 a = ld4(pre_add + i * 4); z.x += a.x; z.y += a.y; z.z += a.z; z.w += a.w; }
+        float4 o = make_float4(act_fwd(z.x, act), act_fwd(z.y, act), act_fwd(z.z, act), act_fwd(z.w, act));
+        if (lab) { o.x = ls * o.x + lb; o.y = ls * o.y + lb; o.z = ls * o.z + lb; o.w = ls * o.w + lb; }
+        if (post_add) { const float4 a = ld4(post_add + i * 4); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+        st4(y + i * 4, o);
+    }
+}
+
 // Backward pass 1: per-channel sums of dz and dz*xhat (double), LAB scalar grads.
 //   dz = dy * lab_s * act'(z),  z = x*scale+shift (+pre_add),  xhat = (x-mean)*invstd
 // red[0:C] += sum dz ; red[C:2C] += sum dz*xhat ; red[2C] += sum dy*act(z) ; red[2C+1] += sum dy
@@ -292,6 +342,7 @@ __global__ void __launch_bounds__(NT) layernorm_fwd_kernel(const float* __restri
 // pre-reduced over the CTA's 8 rows x ROWS_PER_WARP in shared memory).  x here is the LN *input*
 // (x + res when the forward fused a residual; the caller passes that sum's two terms again).
 constexpr int LN_ROWS_PER_WARP = 8;
+template <int MAXV>
 __global__ void __launch_bounds__(NT) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                            const float* __restrict__ res,
                                                            const float* __restrict__ w, const float* __restrict__ mean,
@@ -302,9 +353,9 @@ __global__ void __launch_bounds__(NT) layernorm_bwd_kernel(const float* __restri
     for (int i = threadIdx.x; i < 2 * D; i += NT) shf[i] = 0.f;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x / 32, VD = D / 4;
-    float4 aw[LN_MAXV], ab[LN_MAXV];
+    float4 aw[MAXV], ab[MAXV];
 #pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k) { aw[k] = make_float4(0, 0, 0, 0); ab[k] = make_float4(0, 0, 0, 0); }
+    for (int k = 0; k < MAXV; ++k) { aw[k] = make_float4(0, 0, 0, 0); ab[k] = make_float4(0, 0, 0, 0); }
     // grid-stride over slabs of (NT/32) x LN_ROWS_PER_WARP rows: the grid is capped (a few CTAs per SM), so the
     // parameter-gradient atomics below run once per CTA, not once per 64 rows (the 134 400-row encoder LayerNorm
     // issued 1.07 M global atomics on 512 addresses: 282 us for a 100 MB pass)
@@ -314,10 +365,10 @@ __global__ void __launch_bounds__(NT) layernorm_bwd_kernel(const float* __restri
         const long row = (slab * (NT / 32) + warp) * LN_ROWS_PER_WARP + rr;
         if (row >= rows) break;
         const float mu = mean[row], rs = rstd[row];
-        float4 xh[LN_MAXV], g[LN_MAXV];
+        float4 xh[MAXV], g[MAXV];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < LN_MAXV; ++k) {
+        for (int k = 0; k < MAXV; ++k) {
             const int i = lane + k * 32;
             if (i < VD) {
                 float4 v = ld4(x + row * D + i * 4);
@@ -334,7 +385,7 @@ __global__ void __launch_bounds__(NT) layernorm_bwd_kernel(const float* __restri
         s1 = warp_sum(s1) / (float)D;
         s2 = warp_sum(s2) / (float)D;
 #pragma unroll
-        for (int k = 0; k < LN_MAXV; ++k) {
+        for (int k = 0; k < MAXV; ++k) {
             const int i = lane + k * 32;
             if (i < VD) {
                 float4 o;
@@ -345,7 +396,7 @@ __global__ void __launch_bounds__(NT) layernorm_bwd_kernel(const float* __restri
         }
     }
 #pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k) {
+    for (int k = 0; k < MAXV; ++k) {
         const int i = lane + k * 32;
         if (i < VD) {
             atomicAdd(&shf[i * 4 + 0], aw[k].x); atomicAdd(&shf[i * 4 + 1], aw[k].y);
@@ -417,6 +468,22 @@ DFINE_API int dfine_bn_apply(const float* x, const float* scale, const float* sh
 }
 
 // red: double [2*C+2], zero-initialised by the caller.
+// dfine_bn_finalize followed by dfine_bn_apply, one launch (train mode).  stats: double [2*C] sums from the conv
+// epilogue / dfine_bn_stats; mean / invstd / scale / shift [C] are written for the backward pass.
+DFINE_API int dfine_bn_finalize_apply(const float* x, const double* stats, const float* weight, const float* bias,
+                                      float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
+                                      float* shift, const float* pre_add, const float* post_add, const float* lab,
+                                      const float* lab_b, float* y, long M, int C, float momentum, float eps, int act,
+                                      void* stream) {
+    DFINE_REQUIRE(C % 4 == 0 && C > 0 && C <= 3064, "bn_finalize_apply: C=%d", C);
+    if (M == 0) return 0;
+    bn_finalize_apply_kernel<<<ew_grid(M * C / 4), NT, 2 * (size_t)C * sizeof(float), (cudaStream_t)stream>>>(
+        x, stats, weight, bias, running_mean, running_var, mean, invstd, scale, shift, pre_add, post_add, lab, lab_b, y,
+        M, C, momentum, eps, act);
+    DFINE_LAUNCH_CHECK("bn_finalize_apply");
+    return 0;
+}
+
 DFINE_API int dfine_bn_bwd_reduce(const float* dy, const float* x, const float* scale, const float* shift,
                                   const float* mean, const float* invstd, const float* pre_add, const float* lab,
                                   double* red, long M, int C, int act, long ld_dy, void* stream) {
@@ -468,8 +535,15 @@ DFINE_API int dfine_layernorm_bwd(const float* dy, const float* x, const float* 
     if (rows == 0) return 0;
     const long per_cta = (long)(NT / 32) * LN_ROWS_PER_WARP;
     const long slabs = (rows + per_cta - 1) / per_cta;
-    layernorm_bwd_kernel<<<(int)(slabs < 148L * 4 ? slabs : 148L * 4), NT, 2 * D * sizeof(float), (cudaStream_t)stream>>>(
-        dy, x, res, w, mean, rstd, dx, dw, db, rows, D);
+    // float4 per lane as a template parameter: at D = 256 the register arrays shrink 4x (170 -> ~60 registers) and
+    // four times as many rows are in flight per SM (the 134 400-row encoder LayerNorm ran at 1.6 TB/s)
+    const int grid = (int)(slabs < 148L * 8 ? slabs : 148L * 8);
+    if (D <= 256)
+        layernorm_bwd_kernel<2><<<grid, NT, 2 * D * sizeof(float), (cudaStream_t)stream>>>(dy, x, res, w, mean, rstd, dx,
+                                                                                          dw, db, rows, D);
+    else
+        layernorm_bwd_kernel<LN_MAXV><<<grid, NT, 2 * D * sizeof(float), (cudaStream_t)stream>>>(dy, x, res, w, mean, rstd,
+                                                                                                dx, dw, db, rows, D);
     DFINE_LAUNCH_CHECK("layernorm_bwd");
     return 0;
 }

@@ -544,22 +544,24 @@ class _ConvBnAct(torch.autograd.Function):
         scale = torch.empty(Cout, device=dev, dtype=torch.float32)
         shift = torch.empty(Cout, device=dev, dtype=torch.float32)
         mean = invstd = None
-        if training:
-            mean = torch.empty(Cout, device=dev, dtype=torch.float32)
-            invstd = torch.empty(Cout, device=dev, dtype=torch.float32)
-            _check(lib().dfine_bn_finalize(_p(stats), _p(bn_w), _p(bn_b), _p(running_mean), _p(running_var), _p(mean),
-                                           _p(invstd), _p(scale), _p(shift), c_long(M), Cout, c_float(momentum),
-                                           c_float(eps), _stream()), "bn_finalize")
-        else:
-            _check(lib().dfine_bn_fold(_p(bn_w), _p(bn_b), _p(running_mean), _p(running_var), _p(scale), _p(shift),
-                                       Cout, c_float(eps), _stream()), "bn_fold")
         if pre_add is not None:
             pre_add = pre_add.contiguous()
         if post_add is not None:
             post_add = post_add.contiguous()
         y = torch.empty_like(conv_out)
-        _check(lib().dfine_bn_apply(_p(conv_out), _p(scale), _p(shift), _p(pre_add), _p(post_add), _p(lab_s),
-                                    _p(lab_b), _p(y), c_long(M), Cout, ACT[act], _stream()), "bn_apply")
+        if training:      # statistics -> scale / shift -> normalise + activation in ONE launch
+            mean = torch.empty(Cout, device=dev, dtype=torch.float32)
+            invstd = torch.empty(Cout, device=dev, dtype=torch.float32)
+            _check(lib().dfine_bn_finalize_apply(_p(conv_out), _p(stats), _p(bn_w), _p(bn_b), _p(running_mean),
+                                                 _p(running_var), _p(mean), _p(invstd), _p(scale), _p(shift), _p(pre_add),
+                                                 _p(post_add), _p(lab_s), _p(lab_b), _p(y), c_long(M), Cout,
+                                                 c_float(momentum), c_float(eps), ACT[act], _stream()),
+                   "bn_finalize_apply")
+        else:
+            _check(lib().dfine_bn_fold(_p(bn_w), _p(bn_b), _p(running_mean), _p(running_var), _p(scale), _p(shift),
+                                       Cout, c_float(eps), _stream()), "bn_fold")
+            _check(lib().dfine_bn_apply(_p(conv_out), _p(scale), _p(shift), _p(pre_add), _p(post_add), _p(lab_s),
+                                        _p(lab_b), _p(y), c_long(M), Cout, ACT[act], _stream()), "bn_apply")
         ctx.save_for_backward(x, weight, conv_out, scale, shift, mean, invstd, pre_add, lab_s, lab_b, bn_w)
         ctx.geom, ctx.ldx, ctx.cfg = geom, ldx, cfg
         ctx.has_post = post_add is not None
