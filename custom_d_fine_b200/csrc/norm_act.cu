@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(NT) bn_apply_kernel(const float* __restrict__ 
                                                       const float* __restrict__ pre_add,
                                                       const float* __restrict__ post_add,
                                                       const float* __restrict__ lab, const float* __restrict__ lab_b,
-                                                      float* __restrict__ y, long n4, int VC, int act) {
+                                                      float* __restrict__ y, long n4, int VC, int act, long ldy) {
     const float ls = lab ? __ldg(lab) : 1.f, lb = lab ? __ldg(lab_b) : 0.f;
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long)gridDim.x * NT) {
         const int c = (int)(i % VC) * 4;
@@ -115,57 +115,7 @@ __global__ void __launch_bounds__(NT) bn_apply_kernel(const float* __restrict__ 
         float4 o = make_float4(act_fwd(z.x, act), act_fwd(z.y, act), act_fwd(z.z, act), act_fwd(z.w, act));
         if (lab) { o.x = ls * o.x + lb; o.y = ls * o.y + lb; o.z = ls * o.z + lb; o.w = ls * o.w + lb; }
         if (post_add) { const float4 a = ld4(post_add + i * 4); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
-        st4(y + i * 4, o);
-    }
-}
-
-// Train-mode finalize + apply in one launch: every CTA derives the per-channel scale / shift table from the batch
-// statistics into shared memory (C double rsqrt's per CTA, noise next to the pass over the tensor), CTA 0 also
-// publishes mean / invstd / scale / shift for the backward and updates the running statistics.  Removes one tiny
-// dependent launch per BatchNorm layer from the forward chain (133 per step for D-FINE-m).
-__global__ void __launch_bounds__(NT) bn_finalize_apply_kernel(
-    const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ weight,
-    const float* __restrict__ bias, float* __restrict__ running_mean, float* __restrict__ running_var,
-    float* __restrict__ mean_out, float* __restrict__ invstd_out, float* __restrict__ scale_out,
-    float* __restrict__ shift_out, const float* __restrict__ pre_add, const float* __restrict__ post_add,
-    const float* __restrict__ lab, const float* __restrict__ lab_b, float* __restrict__ y, long M, int C, float momentum,
-    float eps, int act) {
-    extern __shared__ float tab[];   // [C] scale | [C] shift
-    for (int c = threadIdx.x; c < C; c += NT) {
-        const double mean = stats[c] / (double)M;
-        double var = stats[C + c] / (double)M - mean * mean;
-        if (var < 0.0) var = 0.0;
-        const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-        const float w = weight ? weight[c] : 1.f, b = bias ? bias[c] : 0.f;
-        const float sc = w * invstd, sh = b - (float)mean * sc;
-        tab[c] = sc;
-        tab[C + c] = sh;
-        if (blockIdx.x == 0) {
-            mean_out[c] = (float)mean;
-            invstd_out[c] = invstd;
-            scale_out[c] = sc;
-            shift_out[c] = sh;
-            if (running_mean) {
-                const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
-                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-                running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
-            }
-        }
-    }
-    __syncthreads();
-    const float ls = lab ? __ldg(lab) : 1.f, lb = lab ? __ldg(lab_b) : 0.f;
-    const int VC = C / 4;
-    const long n4 = M * VC;
-    for (long i = (long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long)gridDim.x * NT) {
-        const int c = (int)(i % VC) * 4;
-        const float4 v = ld4(x + i * 4);
-        const float4 sc = *reinterpret_cast<const float4*>(tab + c), sh = *reinterpret_cast<const float4*>(tab + C + c);
-        float4 z = make_float4(v.x * sc.x + sh.x, v.y * sc.y + sh.y, v.z * sc.z + sh.z, v.w * sc.w + sh.w);
-        if (pre_add) { const float4 a = ld4(pre_add + i * 4); z.x += a.x; z.y += a.y; z.z += a.z; z.w += a.w; }
-        float4 o = make_float4(act_fwd(z.x, act), act_fwd(z.y, act), act_fwd(z.z, act), act_fwd(z.w, act));
-        if (lab) { o.x = ls * o.x + lb; o.y = ls * o.y + lb; o.z = ls * o.z + lb; o.w = ls * o.w + lb; }
-        if (post_add) { const float4 a = ld4(post_add + i * 4); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
-        st4(y + i * 4, o);
+        st4(y + (i / VC) * ldy + c, o);
     }
 }
 
@@ -248,7 +198,7 @@ __global__ void __launch_bounds__(NT) bn_bwd_apply_kernel(
     const float* __restrict__ pre_add, const float* __restrict__ lab, const double* __restrict__ red,
     float* __restrict__ dx, float* __restrict__ dpre, long n4, int VC, long M, int act, int training,
     float* __restrict__ g_w, float* __restrict__ g_b, float* __restrict__ g_lab_s, float* __restrict__ g_lab_b,
-    long ld_dy) {
+    long ld_dy, long ld_dx) {
     const float ls = lab ? __ldg(lab) : 1.f;
     const int C = VC * 4;
     const double invM = 1.0 / (double)M;
@@ -285,7 +235,7 @@ __global__ void __launch_bounds__(NT) bn_bwd_apply_kernel(
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] = ss[k] * dz[k];
         }
-        st4(dx + i * 4, make_float4(o[0], o[1], o[2], o[3]));
+        st4(dx + (i / VC) * ld_dx + c, make_float4(o[0], o[1], o[2], o[3]));
         if (dpre) st4(dpre + i * 4, make_float4(dz[0], dz[1], dz[2], dz[3]));
     }
 }
@@ -457,33 +407,18 @@ DFINE_API int dfine_bn_fold(const float* weight, const float* bias, const float*
 // lab / lab_b: device pointers to the scalar LAB scale and bias (both or neither).  pre_add/post_add optional [M,C].
 DFINE_API int dfine_bn_apply(const float* x, const float* scale, const float* shift, const float* pre_add,
                              const float* post_add, const float* lab, const float* lab_b, float* y, long M, int C,
-                             int act, void* stream) {
+                             int act, long ldy, void* stream) {
     DFINE_REQUIRE(C % 4 == 0, "bn_apply: C=%d must be a multiple of 4", C);
+    DFINE_REQUIRE(ldy >= C && ldy % 4 == 0 && ((uintptr_t)y % 16) == 0, "bn_apply: output row stride %ld", ldy);
     const long n4 = M * C / 4;
     if (n4 == 0) return 0;
     bn_apply_kernel<<<ew_grid(n4), NT, 0, (cudaStream_t)stream>>>(x, scale, shift, pre_add, post_add, lab, lab_b, y,
-                                                                 n4, C / 4, act);
+                                                                 n4, C / 4, act, ldy);
     DFINE_LAUNCH_CHECK("bn_apply");
     return 0;
 }
 
 // red: double [2*C+2], zero-initialised by the caller.
-// dfine_bn_finalize followed by dfine_bn_apply, one launch (train mode).  stats: double [2*C] sums from the conv
-// epilogue / dfine_bn_stats; mean / invstd / scale / shift [C] are written for the backward pass.
-DFINE_API int dfine_bn_finalize_apply(const float* x, const double* stats, const float* weight, const float* bias,
-                                      float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
-                                      float* shift, const float* pre_add, const float* post_add, const float* lab,
-                                      const float* lab_b, float* y, long M, int C, float momentum, float eps, int act,
-                                      void* stream) {
-    DFINE_REQUIRE(C % 4 == 0 && C > 0 && C <= 3064, "bn_finalize_apply: C=%d", C);
-    if (M == 0) return 0;
-    bn_finalize_apply_kernel<<<ew_grid(M * C / 4), NT, 2 * (size_t)C * sizeof(float), (cudaStream_t)stream>>>(
-        x, stats, weight, bias, running_mean, running_var, mean, invstd, scale, shift, pre_add, post_add, lab, lab_b, y,
-        M, C, momentum, eps, act);
-    DFINE_LAUNCH_CHECK("bn_finalize_apply");
-    return 0;
-}
-
 DFINE_API int dfine_bn_bwd_reduce(const float* dy, const float* x, const float* scale, const float* shift,
                                   const float* mean, const float* invstd, const float* pre_add, const float* lab,
                                   double* red, long M, int C, int act, long ld_dy, void* stream) {
@@ -502,8 +437,10 @@ DFINE_API int dfine_bn_bwd_reduce(const float* dy, const float* x, const float* 
 DFINE_API int dfine_bn_bwd_apply(const float* dy, const float* x, const float* scale, const float* shift,
                                  const float* mean, const float* invstd, const float* pre_add, const float* lab,
                                  const double* red, float* dx, float* dpre, long M, int C, int act, int training,
-                                 float* g_w, float* g_b, float* g_lab_s, float* g_lab_b, long ld_dy, void* stream) {
+                                 float* g_w, float* g_b, float* g_lab_s, float* g_lab_b, long ld_dy, long ld_dx,
+                                 void* stream) {
     DFINE_REQUIRE(C % 4 == 0, "bn_bwd_apply: C=%d", C);
+    DFINE_REQUIRE(ld_dx >= C && ld_dx % 4 == 0 && ((uintptr_t)dx % 16) == 0, "bn_bwd_apply: dx row stride %ld", ld_dx);
     DFINE_REQUIRE(ld_dy >= C && ld_dy % 4 == 0 && ((uintptr_t)dy % 16) == 0, "bn_bwd_apply: dy row stride %ld", ld_dy);
     DFINE_REQUIRE((g_w == nullptr) == (g_b == nullptr) && (g_lab_s == nullptr) == (g_lab_b == nullptr),
                   "bn_bwd_apply: gradient outputs come in pairs");
@@ -511,7 +448,7 @@ DFINE_API int dfine_bn_bwd_apply(const float* dy, const float* x, const float* s
     if (n4 == 0) return 0;
     bn_bwd_apply_kernel<<<ew_grid(n4), NT, 2 * C * sizeof(float), (cudaStream_t)stream>>>(dy, x, scale, shift, mean, invstd, pre_add, lab,
                                                                      red, dx, dpre, n4, C / 4, M, act, training, g_w,
-                                                                     g_b, g_lab_s, g_lab_b, ld_dy);
+                                                                     g_b, g_lab_s, g_lab_b, ld_dy, ld_dx);
     DFINE_LAUNCH_CHECK("bn_bwd_apply");
     return 0;
 }

@@ -322,14 +322,14 @@ __global__ void __launch_bounds__(NT) maxpool_bwd_kernel(const float* __restrict
 }
 
 // ---- float4 variants of the stem max-pool (C % 4 == 0): one thread = one pixel x 4 channels ----------------
-__device__ __forceinline__ float4 padded4(const float* __restrict__ x, int b, int h, int w, int cv, int H, int W, int VC) {
-    return (h < H && w < W) ? ld4(x + ((((long)b * H + h) * W + w) * VC + cv) * 4) : make_float4(0, 0, 0, 0);
+__device__ __forceinline__ float4 padded4(const float* __restrict__ x, int b, int h, int w, int cv, int H, int W, long ldx) {
+    return (h < H && w < W) ? ld4(x + (((long)b * H + h) * W + w) * ldx + cv * 4) : make_float4(0, 0, 0, 0);
 }
 // argmax slot (0..3, first max wins, NaN propagates) of each of the 4 channels, packed in one int
 __device__ __forceinline__ int window_argmax4(const float* __restrict__ x, int b, int h, int w, int cv, int H, int W,
-                                              int VC, float4* mx) {
-    const float4 v[4] = {padded4(x, b, h, w, cv, H, W, VC), padded4(x, b, h, w + 1, cv, H, W, VC),
-                         padded4(x, b, h + 1, w, cv, H, W, VC), padded4(x, b, h + 1, w + 1, cv, H, W, VC)};
+                                              long ldx, float4* mx) {
+    const float4 v[4] = {padded4(x, b, h, w, cv, H, W, ldx), padded4(x, b, h, w + 1, cv, H, W, ldx),
+                         padded4(x, b, h + 1, w, cv, H, W, ldx), padded4(x, b, h + 1, w + 1, cv, H, W, ldx)};
     float best[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
     int arg[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -343,7 +343,7 @@ __device__ __forceinline__ int window_argmax4(const float* __restrict__ x, int b
     return arg[0] | (arg[1] << 2) | (arg[2] << 4) | (arg[3] << 6);
 }
 __global__ void __launch_bounds__(NT) maxpool_fwd4_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
-                                                          int H, int W, int VC) {
+                                                          int H, int W, int VC, long ldx) {
     const long total = (long)B * H * W * VC;
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
         const int cv = (int)(i % VC);
@@ -352,12 +352,12 @@ __global__ void __launch_bounds__(NT) maxpool_fwd4_kernel(const float* __restric
         const int h = (int)(p % H);
         const int b = (int)(p / H);
         float4 mx;
-        window_argmax4(x, b, h, w, cv, H, W, VC, &mx);
+        window_argmax4(x, b, h, w, cv, H, W, ldx, &mx);
         st4(y + i * 4, mx);
     }
 }
 __global__ void __launch_bounds__(NT) maxpool_bwd4_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                          float* __restrict__ dx, int B, int H, int W, int VC) {
+                                                          float* __restrict__ dx, int B, int H, int W, int VC, long ldx) {
     const long total = (long)B * H * W * VC;
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
         const int cv = (int)(i % VC);
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(NT) maxpool_bwd4_kernel(const float* __restric
             for (int dw = 0; dw < 2; ++dw) {
                 const int oh = h - dh, ow = w - dw;
                 if (oh < 0 || ow < 0) continue;
-                const int arg = window_argmax4(x, b, oh, ow, cv, H, W, VC, &mx);
+                const int arg = window_argmax4(x, b, oh, ow, cv, H, W, ldx, &mx);
                 const float4 g = ld4(dy + ((((long)b * H + oh) * W + ow) * VC + cv) * 4);
                 const float ge[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
@@ -467,7 +467,7 @@ DFINE_API int dfine_dwconv_bwd_data(const float* dy, const float* w, float* dx, 
 DFINE_API int dfine_dwconv_bwd_weight(const float* dy, const float* x, float* dw, int B, int H, int W, int C, int k,
                                       int stride, int pad, void* stream) {
     DFINE_REQUIRE(C % 4 == 0 && (k == 3 || k == 5), "dwconv_bwd_weight: C=%d k=%d", C, k);
-    DFINE_REQUIRE((long)k * k * C * 4 <= 48 * 1024, "dwconv_bwd_weight: k*k*C too large for shared memory");
+    DFINE_REQUIRE((long)k * k * C * 4 <= 200 * 1024, "dwconv_bwd_weight: k*k*C too large for shared memory");
     const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
     DFINE_REQUIRE(stride == 1 || stride == 2, "dwconv_bwd_weight: stride %d", stride);
     const long P = (long)B * OH * ((OW + PX - 1) / PX);      // blocks of PX output pixels along W
@@ -479,34 +479,44 @@ DFINE_API int dfine_dwconv_bwd_weight(const float* dy, const float* x, float* dw
     const size_t smem = (size_t)k * k * C * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = ceil_div(P, ppc);
-    if (k == 3 && stride == 1)
-        dwconv_bwd_weight_kernel<3, 1><<<grid, NT, smem, st>>>(dy, x, dw, B, H, W, C, OH, OW, pad, ppc);
-    else if (k == 3)
-        dwconv_bwd_weight_kernel<3, 2><<<grid, NT, smem, st>>>(dy, x, dw, B, H, W, C, OH, OW, pad, ppc);
-    else if (stride == 1)
-        dwconv_bwd_weight_kernel<5, 1><<<grid, NT, smem, st>>>(dy, x, dw, B, H, W, C, OH, OW, pad, ppc);
-    else
-        dwconv_bwd_weight_kernel<5, 2><<<grid, NT, smem, st>>>(dy, x, dw, B, H, W, C, OH, OW, pad, ppc);
+    // wide 5x5 layers (D-FINE-x: 512 channels = 51 KB of per-CTA partial sums) need the opt-in shared-memory limit
+    auto launch = [&](auto kern) -> int {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { dfine_set_error("dwconv_bwd_weight: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+        }
+        kern<<<grid, NT, smem, st>>>(dy, x, dw, B, H, W, C, OH, OW, pad, ppc);
+        return 0;
+    };
+    int rc;
+    if (k == 3 && stride == 1) rc = launch(dwconv_bwd_weight_kernel<3, 1>);
+    else if (k == 3) rc = launch(dwconv_bwd_weight_kernel<3, 2>);
+    else if (stride == 1) rc = launch(dwconv_bwd_weight_kernel<5, 1>);
+    else rc = launch(dwconv_bwd_weight_kernel<5, 2>);
+    if (rc) return rc;
     DFINE_LAUNCH_CHECK("dwconv_bwd_weight");
     return 0;
 }
 
-DFINE_API int dfine_maxpool2x2_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+// x may carry a padded pixel stride ldx >= C (elements); y / dy / dx are dense [B,H,W,C].
+DFINE_API int dfine_maxpool2x2_fwd(const float* x, long ldx, float* y, int B, int H, int W, int C, void* stream) {
     const long total = (long)B * H * W * C;
     if (total == 0) return 0;
+    DFINE_REQUIRE(ldx == C || (C % 4 == 0 && ldx % 4 == 0 && ldx > C), "maxpool_fwd: pixel stride %ld", ldx);
     if (C % 4 == 0)
-        maxpool_fwd4_kernel<<<ew_grid(total / 4), NT, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C / 4);
+        maxpool_fwd4_kernel<<<ew_grid(total / 4), NT, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C / 4, ldx);
     else
         maxpool_fwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C);
     DFINE_LAUNCH_CHECK("maxpool_fwd");
     return 0;
 }
-DFINE_API int dfine_maxpool2x2_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C,
+DFINE_API int dfine_maxpool2x2_bwd(const float* x, long ldx, const float* dy, float* dx, int B, int H, int W, int C,
                                    void* stream) {
     const long total = (long)B * H * W * C;
     if (total == 0) return 0;
+    DFINE_REQUIRE(ldx == C || (C % 4 == 0 && ldx % 4 == 0 && ldx > C), "maxpool_bwd: pixel stride %ld", ldx);
     if (C % 4 == 0)
-        maxpool_bwd4_kernel<<<ew_grid(total / 4), NT, 0, (cudaStream_t)stream>>>(x, dy, dx, B, H, W, C / 4);
+        maxpool_bwd4_kernel<<<ew_grid(total / 4), NT, 0, (cudaStream_t)stream>>>(x, dy, dx, B, H, W, C / 4, ldx);
     else
         maxpool_bwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x, dy, dx, B, H, W, C);
     DFINE_LAUNCH_CHECK("maxpool_bwd");

@@ -204,6 +204,21 @@ def _req_cuda(*ts):
             raise RuntimeError("custom_d_fine_b200 ops need CUDA tensors (no CPU path)")
 
 
+def _pad_ld(C):
+    """Pixel stride for a freshly allocated NHWC activation of C channels.  Padding the 12 / 24 / 48-channel stem
+    tensors to 128-byte rows was measured (profiles/README.md): the tcgen05 kernels on them did not get faster (their
+    cost is TMA's per-row zero fill of the channels past Cin, not the row alignment) while the BatchNorm and copy
+    kernels got slower, so activations stay dense.  The kernels keep their pixel-stride parameters."""
+    return C
+
+
+def _alloc_nhwc(B, H, W, C, device):
+    ld = _pad_ld(C)
+    if ld == C:
+        return torch.empty((B, H, W, C), device=device, dtype=torch.float32), C
+    return torch.empty((B, H, W, ld), device=device, dtype=torch.float32)[..., :C], ld
+
+
 def _rows(x):
     """View ``x`` [..., C] as rows with one uniform row stride; returns (tensor, n_rows, ld)."""
     C = x.shape[-1]
@@ -548,20 +563,20 @@ class _ConvBnAct(torch.autograd.Function):
             pre_add = pre_add.contiguous()
         if post_add is not None:
             post_add = post_add.contiguous()
-        y = torch.empty_like(conv_out)
-        if training:      # statistics -> scale / shift -> normalise + activation in ONE launch
+        y, ldy_out = _alloc_nhwc(B, OH, OW, Cout, dev)
+        # (a fused finalize+apply launch was measured SLOWER: every CTA re-derives the scale / shift table in fp64 and
+        #  synchronises before its first load — 20.5 us against 12.3 + 4.8 us per layer, profiles/README.md)
+        if training:
             mean = torch.empty(Cout, device=dev, dtype=torch.float32)
             invstd = torch.empty(Cout, device=dev, dtype=torch.float32)
-            _check(lib().dfine_bn_finalize_apply(_p(conv_out), _p(stats), _p(bn_w), _p(bn_b), _p(running_mean),
-                                                 _p(running_var), _p(mean), _p(invstd), _p(scale), _p(shift), _p(pre_add),
-                                                 _p(post_add), _p(lab_s), _p(lab_b), _p(y), c_long(M), Cout,
-                                                 c_float(momentum), c_float(eps), ACT[act], _stream()),
-                   "bn_finalize_apply")
+            _check(lib().dfine_bn_finalize(_p(stats), _p(bn_w), _p(bn_b), _p(running_mean), _p(running_var), _p(mean),
+                                           _p(invstd), _p(scale), _p(shift), c_long(M), Cout, c_float(momentum),
+                                           c_float(eps), _stream()), "bn_finalize")
         else:
             _check(lib().dfine_bn_fold(_p(bn_w), _p(bn_b), _p(running_mean), _p(running_var), _p(scale), _p(shift),
                                        Cout, c_float(eps), _stream()), "bn_fold")
-            _check(lib().dfine_bn_apply(_p(conv_out), _p(scale), _p(shift), _p(pre_add), _p(post_add), _p(lab_s),
-                                        _p(lab_b), _p(y), c_long(M), Cout, ACT[act], _stream()), "bn_apply")
+        _check(lib().dfine_bn_apply(_p(conv_out), _p(scale), _p(shift), _p(pre_add), _p(post_add), _p(lab_s),
+                                    _p(lab_b), _p(y), c_long(M), Cout, ACT[act], c_long(ldy_out), _stream()), "bn_apply")
         ctx.save_for_backward(x, weight, conv_out, scale, shift, mean, invstd, pre_add, lab_s, lab_b, bn_w)
         ctx.geom, ctx.ldx, ctx.cfg = geom, ldx, cfg
         ctx.has_post = post_add is not None
@@ -596,7 +611,7 @@ class _ConvBnAct(torch.autograd.Function):
             _check(lib().dfine_bn_bwd_reduce(_p(dy), _p(conv_out), _p(scale), _p(shift), _p(m_), _p(i_), _p(pre_add),
                                              _p(lab_s), _p(red), c_long(M), Cout, ACT[act], c_long(ld_dy), _stream()),
                    "bn_bwd_reduce")
-        dconv = torch.empty_like(conv_out)
+        dconv, ld_dc = (torch.empty_like(conv_out), Cout) if groups > 1 else _alloc_nhwc(B, OH, OW, Cout, dev)
         dpre = torch.empty_like(conv_out) if (pre_add is not None and ctx.needs_input_grad[6]) else None
         # parameter gradients of BN / LAB: accumulated by the apply kernel straight into the .grad arenas
         bn_direct = lab_direct = None
@@ -613,8 +628,8 @@ class _ConvBnAct(torch.autograd.Function):
                                         1 if bn_train else 0, _p(bn_direct[0]) if bn_direct else None,
                                         _p(bn_direct[1]) if bn_direct else None,
                                         _p(lab_direct[0]) if lab_direct else None,
-                                        _p(lab_direct[1]) if lab_direct else None, c_long(ld_dy), _stream()),
-               "bn_bwd_apply")
+                                        _p(lab_direct[1]) if lab_direct else None, c_long(ld_dy), c_long(ld_dc),
+                                        _stream()), "bn_bwd_apply")
         g_bn_w = g_bn_b = g_lab_s = g_lab_b = None
         if red is not None:
             redf = None
@@ -646,12 +661,12 @@ class _ConvBnAct(torch.autograd.Function):
                 dst = _grad_dst(weight, "conv")
                 if dst is not None:      # accumulated in place on the weight-gradient stream; autograd gets None
                     geom_ = ctx.geom
-                    wgrad_stream.run(lambda: _conv_wgrad(dconv, Cout, x, ldx, geom_, dst), dconv, x)
+                    wgrad_stream.run(lambda: _conv_wgrad(dconv, ld_dc, x, ldx, geom_, dst), dconv, x)
                 else:
-                    g_w = _conv_wgrad(dconv, Cout, x, ldx, ctx.geom).permute(0, 3, 1, 2)
+                    g_w = _conv_wgrad(dconv, ld_dc, x, ldx, ctx.geom).permute(0, 3, 1, 2)
             if ctx.needs_input_grad[0]:
                 g_x = torch.empty((B, H, W, Cin), device=dev, dtype=torch.float32)
-                _conv_dgrad(dconv, Cout, weight, _wcache.getter(weight), g_x, Cin, ctx.geom, dtap)
+                _conv_dgrad(dconv, ld_dc, weight, _wcache.getter(weight), g_x, Cin, ctx.geom, dtap)
         g_post = (dy if dy.is_contiguous() else dy.contiguous()) if ctx.has_post else None
         return g_x, g_w, g_bn_w, g_bn_b, g_lab_s, g_lab_b, dpre, g_post, None, None, None
 
@@ -895,24 +910,62 @@ class _FdrHead(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # small spatial ops
 # ------------------------------------------------------------------------------------------------
+def _nhwc_ld(x):
+    """(tensor, pixel stride) of an NHWC activation that is dense or a channel-prefix view of a padded buffer."""
+    B, H, W, C = x.shape
+    ld = x.stride(2)
+    if x.stride(3) == 1 and ld >= C and ld % 4 == 0 and x.stride(1) == W * ld and x.stride(0) == H * W * ld \
+            and x.data_ptr() % 16 == 0 and (ld == C or C % 4 == 0):
+        return x, ld
+    return x.contiguous(), C
+
+
 class _MaxPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
         _req_cuda(x)
-        x = x.contiguous()
+        x, ldx = _nhwc_ld(x)
         B, H, W, C = x.shape
-        y = torch.empty_like(x)
-        _check(lib().dfine_maxpool2x2_fwd(_p(x), _p(y), B, H, W, C, _stream()), "maxpool_fwd")
+        y = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
+        _check(lib().dfine_maxpool2x2_fwd(_p(x), c_long(ldx), _p(y), B, H, W, C, _stream()), "maxpool_fwd")
         ctx.save_for_backward(x)
+        ctx.ldx = ldx
         return y
 
     @staticmethod
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
         B, H, W, C = x.shape
-        dx = torch.empty_like(x)
-        _check(lib().dfine_maxpool2x2_bwd(_p(x), _p(dy.contiguous()), _p(dx), B, H, W, C, _stream()), "maxpool_bwd")
+        dx = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
+        _check(lib().dfine_maxpool2x2_bwd(_p(x), c_long(ctx.ldx), _p(dy.contiguous()), _p(dx), B, H, W, C, _stream()),
+               "maxpool_bwd")
         return dx
+
+
+class _CatPad(torch.autograd.Function):
+    """Channel concat of NHWC tensors into a buffer with a 128-byte-aligned pixel stride (see _pad_ld); the backward
+    hands out channel-slice views of the incoming gradient, as torch.cat's does."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        B, H, W, _ = xs[0].shape
+        cs = [int(x.shape[-1]) for x in xs]
+        C = sum(cs)
+        out, _ = _alloc_nhwc(B, H, W, C, xs[0].device)
+        o = 0
+        for x, c in zip(xs, cs):
+            out[..., o:o + c].copy_(x)
+            o += c
+        ctx.cs = cs
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        outs, o = [], 0
+        for c in ctx.cs:
+            outs.append(g[..., o:o + c])
+            o += c
+        return tuple(outs)
 
 
 class _Upsample2x(torch.autograd.Function):
@@ -968,7 +1021,10 @@ class CudaOps:
         return _Upsample2x.apply(x)
 
     def cat(self, xs, dim=-1):
-        return torch.cat(list(xs), dim)
+        xs = list(xs)
+        if dim in (-1, 3) and xs[0].dim() == 4 and _pad_ld(sum(int(x.shape[-1]) for x in xs)) != sum(int(x.shape[-1]) for x in xs):
+            return _CatPad.apply(*xs)
+        return torch.cat(xs, dim)
 
     # ---- dense ----
     def linear(self, x, w, b=None, act=None):

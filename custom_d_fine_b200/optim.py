@@ -162,6 +162,11 @@ class FusedAdamW(torch.optim.Optimizer):
         if self._buf_src is not None:
             dist.broadcast(self._buf_src, src)
             dist.broadcast(self._buf_ema, src)
+        self._register_planes()      # the arenas were overwritten behind the parameters' version counters
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._register_planes()
 
     def allreduce_grads(self):
         """Average the flat gradient arenas over ranks (NCCL over NVLink; the step's only gradient collective)."""
