@@ -268,7 +268,8 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": e["algorithmic_bytes_per_launch"],
                 "definition": "sum of algorithmic bytes (in + out + weights, fp32) over the family's launches / sum of "
                               "their CUDA-event durations",
-                "timed_in": "an eager pass of the same K steps (CUDA events on the launching stream)",
+                "timed_in": "an eager pass of the same K steps, one stream, CUDA events on the launching stream; a ~40 us "
+                            "spin kernel queued before each start event keeps host launch latency out of the interval",
                 "by_bound": split.get(name),
                 "others": {k: dict(entry(k), **({"by_bound": split[k]} if k in split else {})) for k in kern if k != name}}
     cpu = cpu_baseline(steps=2, warmup=1) if world == 1 and not args.no_cpu_baseline else None

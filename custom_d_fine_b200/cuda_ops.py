@@ -79,6 +79,9 @@ def _check(rc, what):
     counters.launches += 1
 
 
+_SPIN_CYCLES = 80_000      # ~40 us at 1.97 GHz
+
+
 class _timed:
     def __init__(self, name, nbytes, flops=0):
         self.on = name in counters.watch
@@ -87,6 +90,10 @@ class _timed:
     def __enter__(self):
         if self.on:
             self.s, self.e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            # In an eager step the device is idle when a launch arrives, so an event recorded before the (ctypes) call
+            # would also time the host's 10-20 us of argument marshalling.  A short spin kernel queued first keeps the
+            # stream busy until start event, kernel and stop event are all enqueued: the pair then brackets the kernel.
+            torch.cuda._sleep(_SPIN_CYCLES)
             self.s.record()
 
     def __exit__(self, *exc):
