@@ -949,32 +949,6 @@ class _MaxPool(torch.autograd.Function):
         return dx
 
 
-class _CatPad(torch.autograd.Function):
-    """Channel concat of NHWC tensors into a buffer with a 128-byte-aligned pixel stride (see _pad_ld); the backward
-    hands out channel-slice views of the incoming gradient, as torch.cat's does."""
-
-    @staticmethod
-    def forward(ctx, *xs):
-        B, H, W, _ = xs[0].shape
-        cs = [int(x.shape[-1]) for x in xs]
-        C = sum(cs)
-        out, _ = _alloc_nhwc(B, H, W, C, xs[0].device)
-        o = 0
-        for x, c in zip(xs, cs):
-            out[..., o:o + c].copy_(x)
-            o += c
-        ctx.cs = cs
-        return out
-
-    @staticmethod
-    def backward(ctx, g):
-        outs, o = [], 0
-        for c in ctx.cs:
-            outs.append(g[..., o:o + c])
-            o += c
-        return tuple(outs)
-
-
 class _Upsample2x(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
@@ -1028,10 +1002,7 @@ class CudaOps:
         return _Upsample2x.apply(x)
 
     def cat(self, xs, dim=-1):
-        xs = list(xs)
-        if dim in (-1, 3) and xs[0].dim() == 4 and _pad_ld(sum(int(x.shape[-1]) for x in xs)) != sum(int(x.shape[-1]) for x in xs):
-            return _CatPad.apply(*xs)
-        return torch.cat(xs, dim)
+        return torch.cat(list(xs), dim)
 
     # ---- dense ----
     def linear(self, x, w, b=None, act=None):
