@@ -205,6 +205,7 @@ class DFINECriterion(nn.Module):
         self._clear_cache()
 
     def _clear_cache(self):
+        self._mask_cache = (None, None)
         self.fgl_targets = self.fgl_targets_dn = None
         self.num_pos = self.num_neg = None
 
@@ -298,9 +299,39 @@ class DFINECriterion(nn.Module):
         return losses
 
     def loss_masks(self, out, S, tg, num_boxes):
+        """Cropped BCE + cropped Dice of the matched mask logits against the GT masks resized to the prediction size
+        (dfine_criterion.py:504-556 with 239-305, 335-386, 404-450): both are evaluated inside the GT box only, the BCE sum
+        normalised by the box area, then averaged over the matched instances (NOT divided by num_boxes)."""
         if "pred_masks" not in out:
             return {}
-        raise NotImplementedError("mask losses (dfine_criterion.py:239-556) are a SURVEY §8(f) 'next' row")
+        pm = out["pred_masks"]                                   # [B, Q, Hm, Wm] logits
+        B, Q, Hm, Wm = pm.shape
+        if S.n == 0 or tg[2] is None or tg[2].numel() == 0:
+            zero = pm.sum() * 0
+            return {"loss_mask_bce": zero, "loss_mask_dice": zero}
+        assert S.v is None, "per-layer / denoising sets are never padded"
+        pred = pm.reshape(B * Q, Hm, Wm).index_select(0, S.b * Q + S.q)           # [M, Hm, Wm]
+        key = (Hm, Wm, tg[2].data_ptr())
+        if getattr(self, "_mask_cache", (None,))[0] != key:          # every GT mask resized once per step
+            g = tg[2].unsqueeze(1).float()
+            g = F.interpolate(g, size=(Hm, Wm), mode="bilinear", align_corners=False).squeeze(1).clamp_(0, 1)
+            self._mask_cache = (key, g)
+        tgt = self._mask_cache[1].index_select(0, S.t)
+        cx, cy, w, h = tg[1].index_select(0, S.t).unbind(-1)
+        x1 = ((cx - w / 2) * Wm).clamp(0, Wm - 1)[:, None, None]
+        y1 = ((cy - h / 2) * Hm).clamp(0, Hm - 1)[:, None, None]
+        x2 = ((cx + w / 2) * Wm).clamp(1, Wm)[:, None, None]
+        y2 = ((cy + h / 2) * Hm).clamp(1, Hm)[:, None, None]
+        ys = torch.arange(Hm, device=pm.device, dtype=pm.dtype)[None, :, None]
+        xs = torch.arange(Wm, device=pm.device, dtype=pm.dtype)[None, None, :]
+        inside = ((xs >= x1) & (xs < x2)).float() * ((ys >= y1) & (ys < y2)).float()     # [M, Hm, Wm]
+        bce = F.binary_cross_entropy_with_logits(pred, tgt, reduction="none") * inside
+        area = ((x2 - x1) * (y2 - y1)).reshape(-1).clamp(min=1.0)
+        loss_bce = (bce.sum(dim=(1, 2)) / area).mean()
+        p = (pred.sigmoid() * inside).flatten(1)
+        t = (tgt * inside).flatten(1)
+        dice = 1.0 - (2.0 * (p * t).sum(1) + 1e-6) / (p.sum(1) + t.sum(1) + 1e-6)
+        return {"loss_mask_bce": loss_bce, "loss_mask_dice": dice.mean()}
 
     # ---- index bookkeeping -----------------------------------------------------------------------
     @staticmethod
@@ -385,7 +416,10 @@ class DFINECriterion(nn.Module):
         layers = [main] + list(aux) + [pre] + list(enc)
         labels = torch.cat([t["labels"] for t in targets]) if targets else None
         boxes = torch.cat([t["boxes"] for t in targets]) if targets else None
-        return self.matcher.match_layers_raw(layers, targets), (labels, boxes)
+        masks = None
+        if "masks" in self.losses and targets and all(t.get("masks") is not None and t["masks"].dim() == 3 for t in targets):
+            masks = torch.cat([t["masks"] for t in targets])          # [sumT, H, W] (the batch shares one image size)
+        return self.matcher.match_layers_raw(layers, targets), (labels, boxes, masks)
 
     def plan(self, outputs, targets, raw, plan=None):
         """Stage 2 (host): matcher indices -> GO union -> normalisers -> one pinned index table."""
@@ -590,6 +624,11 @@ class DFINECriterion(nn.Module):
                 a["is_dn"] = True
                 a["up"], a["reg_scale"] = outputs["up"], outputs["reg_scale"]
                 self._terms(a, tg, dsets, nums, f"_dn_{i}", losses)
+            if "dn_pred_masks" in outputs and "masks" in self.losses:      # final denoising layer's masks (756-767)
+                d = self.loss_masks({"pred_masks": outputs["dn_pred_masks"]}, s_dn, tg, dn_num)
+                for k, v in d.items():
+                    if k in self.weight_dict:
+                        losses[k + "_dn_final"] = v * self.weight_dict[k]
             if "dn_pre_outputs" in outputs:
                 self._terms(outputs["dn_pre_outputs"], tg, dsets, nums, "_dn_pre", losses)
         return {k: torch.nan_to_num(v, nan=0.0) for k, v in losses.items()}

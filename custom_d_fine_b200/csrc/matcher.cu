@@ -46,7 +46,8 @@ __device__ __forceinline__ Key shfl_key(const Key& k, int o) {
 
 __device__ __forceinline__ float cost_entry(const float* __restrict__ lg, const float* __restrict__ bx,
                                             long label, const float* __restrict__ tb, float alpha, float gamma,
-                                            float w_class, float w_bbox, float w_giou) {
+                                            float w_class, float w_bbox, float w_giou, float extra = 0.f,
+                                            bool has_extra = false) {
     // class term (matcher.py:150-158)
     const float x = lg[label];
     const float p = 1.f / (1.f + expf(-x));
@@ -70,6 +71,7 @@ __device__ __forceinline__ float cost_entry(const float* __restrict__ lg, const 
     const float area = cw * ch;
     const float giou = iou - (area - uni) / area;
     float c = w_bbox * c_box + w_class * c_cls + w_giou * (-giou);
+    if (has_extra) c = c + extra;     // segmentation: mask cost block added before the NaN guard (matcher.py:233-242)
     // torch.nan_to_num(C, nan=1.0) (matcher.py:242)
     if (isnan(c)) c = 1.0f;
     else if (isinf(c)) c = c > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
@@ -93,6 +95,7 @@ __global__ void __launch_bounds__(32) matcher_kernel(
     long* __restrict__ out_q, long* __restrict__ out_t,  // [NL,sumT]
     float* __restrict__ cost_out,      // optional [NL, Q*sumT] (block b at Q*toff[b], [Q,T_b] row-major) or null
     float* __restrict__ workspace,     // used for the cost block when it does not fit in smem
+    const float* __restrict__ extra,   // optional additive cost, same layout as cost_out (mask cost), or null
     int NL, int B, int Q, int C, int sumT, int Tmax, int cost_in_smem, float alpha, float gamma,
     float w_class, float w_bbox, float w_giou) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -126,8 +129,9 @@ __global__ void __launch_bounds__(32) matcher_kernel(
     const float* bx = boxes + ((long)layer * B + b) * Q * 4;
     for (int e = lane; e < Q * T; e += 32) {
         const int q = e / T, t = e % T;
+        const float ex = extra ? __ldg(extra + (long)layer * Q * sumT + (long)Q * t0 + e) : 0.f;
         const float c = cost_entry(lg + (long)q * C, bx + q * 4, labels[t0 + t], tboxes + (long)(t0 + t) * 4, alpha,
-                                   gamma, w_class, w_bbox, w_giou);
+                                   gamma, w_class, w_bbox, w_giou, ex, extra != nullptr);
         if (cost_out) cost_out[(long)layer * Q * sumT + (long)Q * t0 + e] = c;
         if (transposed) w.cost[t * Cc + q] = c; else w.cost[q * Cc + t] = c;
     }
@@ -223,10 +227,11 @@ DFINE_API long dfine_matcher_workspace_bytes(int NL, int B, int Q, int Tmax) {
 // logits [NL,B,Q,C], boxes [NL,B,Q,4] (cxcywh), labels int64 [sumT], tboxes [sumT,4], toff int32 [B+1]
 // (device).  out_q/out_t int64 [NL,sumT]: for image b of layer l the min(Q,T_b) matched pairs, sorted
 // by query index, start at l*sumT + toff[b].  cost_out (optional) receives the fp32 cost blocks.
-DFINE_API int dfine_matcher(const float* logits, const float* boxes, const long* labels, const float* tboxes,
-                            const int* toff, long* out_q, long* out_t, float* cost_out, float* workspace, int NL,
-                            int B, int Q, int C, int sumT, int Tmax, float alpha, float gamma, float w_class,
-                            float w_bbox, float w_giou, void* stream) {
+namespace {
+int matcher_impl(const float* logits, const float* boxes, const long* labels, const float* tboxes, const int* toff,
+                 long* out_q, long* out_t, float* cost_out, float* workspace, const float* extra, int NL, int B, int Q,
+                 int C, int sumT, int Tmax, float alpha, float gamma, float w_class, float w_bbox, float w_giou,
+                 void* stream) {
     if (NL * B == 0 || sumT == 0) return 0;
     DFINE_REQUIRE(Tmax > 0 && Q > 0 && C > 0, "matcher: bad dims");
     const int Rmax = Tmax < Q ? Tmax : Q, Cmax = Tmax < Q ? Q : Tmax;
@@ -243,8 +248,28 @@ DFINE_API int dfine_matcher(const float* logits, const float* boxes, const long*
         configured = 1;
     }
     matcher_kernel<<<NL * B, 32, smem, (cudaStream_t)stream>>>(logits, boxes, labels, tboxes, toff, out_q, out_t,
-                                                              cost_out, workspace, NL, B, Q, C, sumT, Tmax, in_smem,
-                                                              alpha, gamma, w_class, w_bbox, w_giou);
+                                                              cost_out, workspace, extra, NL, B, Q, C, sumT, Tmax,
+                                                              in_smem, alpha, gamma, w_class, w_bbox, w_giou);
     DFINE_LAUNCH_CHECK("matcher");
     return 0;
+}
+}  // namespace
+
+DFINE_API int dfine_matcher(const float* logits, const float* boxes, const long* labels, const float* tboxes,
+                            const int* toff, long* out_q, long* out_t, float* cost_out, float* workspace, int NL,
+                            int B, int Q, int C, int sumT, int Tmax, float alpha, float gamma, float w_class,
+                            float w_bbox, float w_giou, void* stream) {
+    return matcher_impl(logits, boxes, labels, tboxes, toff, out_q, out_t, cost_out, workspace, nullptr, NL, B, Q, C,
+                        sumT, Tmax, alpha, gamma, w_class, w_bbox, w_giou, stream);
+}
+
+// The same with an additive cost `extra` [NL, Q*sumT] in cost_out's layout (image b's [Q, T_b] block row-major at
+// Q*toff[b]), added before the NaN guard: the mask term of the segmentation matcher (matcher.py:175-237).
+DFINE_API int dfine_matcher_extra(const float* logits, const float* boxes, const long* labels, const float* tboxes,
+                                  const int* toff, const float* extra, long* out_q, long* out_t, float* cost_out,
+                                  float* workspace, int NL, int B, int Q, int C, int sumT, int Tmax, float alpha,
+                                  float gamma, float w_class, float w_bbox, float w_giou, void* stream) {
+    DFINE_REQUIRE(extra != nullptr, "matcher_extra: null extra cost");
+    return matcher_impl(logits, boxes, labels, tboxes, toff, out_q, out_t, cost_out, workspace, extra, NL, B, Q, C, sumT,
+                        Tmax, alpha, gamma, w_class, w_bbox, w_giou, stream);
 }

@@ -679,6 +679,53 @@ class _ConvBnAct(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+# plain convolution (no norm): the MaskDecoder's lateral / fusion / up convs, which are followed by GroupNorm
+# ------------------------------------------------------------------------------------------------
+class _Conv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, stride, pad):
+        _req_cuda(x, weight)
+        if x.stride(-1) != 1 or x.dim() != 4:
+            x = x.contiguous()
+        B, H, W, Cin = x.shape
+        ok = x.stride(2) >= Cin and x.stride(1) == W * x.stride(2) and x.stride(0) == H * W * x.stride(2) \
+            and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0
+        if not ok:
+            x = x.contiguous()
+        ldx = x.stride(2)
+        Cout, _, k, _ = weight.shape
+        pt, pl, pb, pr = pad
+        OH = (H + pt + pb - k) // stride + 1
+        OW = (W + pl + pr - k) // stride + 1
+        geom = (B, H, W, Cin, OH, OW, Cout, k, stride, tuple(pad))
+        y = torch.empty((B, OH, OW, Cout), device=x.device, dtype=torch.float32)
+        _conv_fwd(x, ldx, weight, _wcache.getter(weight), None, y, Cout, geom, 0, None)
+        if ctx.needs_input_grad[0]:
+            _prefetch_dgrad_weight(weight, geom, ldx, Cout)
+        ctx.save_for_backward(x, weight)
+        ctx.geom, ctx.ldx = geom, ldx
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        B, H, W, Cin, OH, OW, Cout, k, stride, pad = ctx.geom
+        dy = dy.contiguous()
+        geom, ldx = ctx.geom, ctx.ldx
+        g_x = g_w = None
+        if ctx.needs_input_grad[1]:
+            dst = _grad_dst(weight, "conv")
+            if dst is not None:
+                wgrad_stream.run(lambda: _conv_wgrad(dy, Cout, x, ldx, geom, dst), dy, x)
+            else:
+                g_w = _conv_wgrad(dy, Cout, x, ldx, geom).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[0]:
+            g_x = torch.empty((B, H, W, Cin), device=dy.device, dtype=torch.float32)
+            _conv_dgrad(dy, Cout, weight, _wcache.getter(weight), g_x, Cin, geom)
+        return g_x, g_w, None, None
+
+
+# ------------------------------------------------------------------------------------------------
 # linear (+bias, +act)
 # ------------------------------------------------------------------------------------------------
 class _Linear(torch.autograd.Function):
@@ -1034,13 +1081,36 @@ class CudaOps:
         """(boxes, LQE statistics) of one decoder layer from one pass over pred_corners."""
         return _FdrHead.apply(corners, ref, project, _as_dev_scalar(reg_scale, corners.device), k, True, True)
 
+    # ---- segmentation head (SURVEY §8 row a25; built at the end of round 1, NOT yet run on a GPU) ----
+    # The three convolutions go through the library's conv kernels; GroupNorm, the bilinear resizes and the
+    # [B,Q,C] x [B,HW,C] mask product are composed from torch device ops for now (their own kernels are next).
+    def conv2d(self, x, w, stride=1, pad=(0, 0, 0, 0), groups=1):
+        if groups != 1:
+            raise NotImplementedError("plain grouped convolutions are not on any path")
+        return _Conv.apply(x, w, int(stride), tuple(int(v) for v in pad))
+
+    def group_norm(self, x, groups, w, b, eps=1e-5, act=None):
+        _req_cuda(x)
+        y = torch.nn.functional.group_norm(x.permute(0, 3, 1, 2), groups, w, b, eps).permute(0, 2, 3, 1)
+        if act == "relu":
+            y = torch.relu(y)
+        elif act is not None:
+            raise NotImplementedError(act)
+        return y.contiguous()
+
+    def resize_bilinear(self, x, size):
+        _req_cuda(x)
+        return torch.nn.functional.interpolate(x.permute(0, 3, 1, 2), size=tuple(size), mode="bilinear",
+                                               align_corners=False).permute(0, 2, 3, 1).contiguous()
+
     def mask_dot(self, embed, feat_nhwc):
-        raise NotImplementedError("segmentation head is a SURVEY §8(f) 'next' row")
+        _req_cuda(embed, feat_nhwc)
+        return torch.einsum("bqc,bhwc->bqhw", embed, feat_nhwc)
 
     # ---- matcher ----
     @torch.no_grad()
     def match_device(self, logits, boxes, labels, tboxes, toff_dev, sumT, Tmax, alpha, gamma, w_class, w_bbox,
-                     w_giou, want_cost=False):
+                     w_giou, want_cost=False, extra_cost=None):
         """logits [NL,B,Q,C], boxes [NL,B,Q,4] contiguous; returns device int64 [NL,sumT] x2 (+ cost)."""
         NL, B, Q, C = logits.shape
         dev = logits.device
@@ -1049,6 +1119,14 @@ class CudaOps:
         cost = torch.zeros((NL, Q * sumT), device=dev, dtype=torch.float32) if want_cost else None
         ws_bytes = lib().dfine_matcher_workspace_bytes(NL, B, Q, Tmax)
         ws = torch.empty(ws_bytes // 4, device=dev, dtype=torch.float32) if ws_bytes else None
+        if extra_cost is not None:      # segmentation: mask cost blocks [NL, Q*sumT] (matcher.HungarianMatcher.mask_cost)
+            extra_cost = extra_cost.detach().float().contiguous()
+            assert tuple(extra_cost.shape) == (NL, Q * sumT), (tuple(extra_cost.shape), NL, Q, sumT)
+            _check(lib().dfine_matcher_extra(_p(logits), _p(boxes), _p(labels), _p(tboxes), _p(toff_dev), _p(extra_cost),
+                                             _p(out_q), _p(out_t), _p(cost), _p(ws), NL, B, Q, C, sumT, Tmax,
+                                             c_float(alpha), c_float(gamma), c_float(w_class), c_float(w_bbox),
+                                             c_float(w_giou), _stream()), "matcher")
+            return out_q, out_t, cost
         _check(lib().dfine_matcher(_p(logits), _p(boxes), _p(labels), _p(tboxes), _p(toff_dev), _p(out_q), _p(out_t),
                                    _p(cost), _p(ws), NL, B, Q, C, sumT, Tmax, c_float(alpha), c_float(gamma),
                                    c_float(w_class), c_float(w_bbox), c_float(w_giou), _stream()), "matcher")
@@ -1058,7 +1136,7 @@ class CudaOps:
 
     @torch.no_grad()
     def match_raw(self, logits_list, boxes_list, targets, alpha=0.25, gamma=2.0, w_class=2.0, w_bbox=5.0,
-                  w_giou=2.0):
+                  w_giou=2.0, extra_cost=None):
         """Launch only (graph-capturable): returns device int64 (out_q, out_t) of shape [n_layers, sumT]."""
         logits = torch.stack([l.detach().float() for l in logits_list]).contiguous()
         boxes = torch.stack([b.detach().float() for b in boxes_list]).contiguous()
@@ -1080,7 +1158,7 @@ class CudaOps:
         labels = torch.cat([t["labels"] for t in targets]).to(dev, torch.int64).contiguous()
         tboxes = torch.cat([t["boxes"] for t in targets]).to(dev, torch.float32).contiguous()
         out_q, out_t, _ = self.match_device(logits, boxes, labels, tboxes, toff, sumT, Tmax, alpha, gamma, w_class,
-                                            w_bbox, w_giou)
+                                            w_bbox, w_giou, extra_cost=extra_cost)
         return out_q, out_t
 
     @staticmethod
@@ -1089,7 +1167,8 @@ class CudaOps:
         return both[0], both[1]
 
     @torch.no_grad()
-    def match(self, logits_list, boxes_list, targets, alpha=0.25, gamma=2.0, w_class=2.0, w_bbox=5.0, w_giou=2.0):
+    def match(self, logits_list, boxes_list, targets, alpha=0.25, gamma=2.0, w_class=2.0, w_bbox=5.0, w_giou=2.0,
+              extra_cost=None):
         logits = torch.stack([l.detach().float() for l in logits_list]).contiguous()
         boxes = torch.stack([b.detach().float() for b in boxes_list]).contiguous()
         _req_cuda(logits, boxes)
@@ -1107,7 +1186,7 @@ class CudaOps:
             offs.append(offs[-1] + s)
         toff = torch.tensor(offs, dtype=torch.int32).to(dev, non_blocking=True)
         out_q, out_t, _ = self.match_device(logits, boxes, labels, tboxes, toff, sumT, Tmax, alpha, gamma, w_class,
-                                            w_bbox, w_giou)
+                                            w_bbox, w_giou, extra_cost=extra_cost)
         both = torch.stack([out_q, out_t]).cpu()        # the step's single matcher D2H
         res = []
         for l in range(NL):

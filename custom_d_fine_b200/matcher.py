@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from .kernels import K
 
@@ -29,28 +30,78 @@ class HungarianMatcher(nn.Module):
             raise NotImplementedError("softmax class cost is not on any shipped config's path")
 
     @torch.no_grad()
+    def mask_cost(self, outputs_list, targets):
+        """Segmentation term of the matching cost (matcher.py:19-71, 175-237): per layer that predicts masks and per
+        image, cost_mask_dice * (1 - pairwise Dice(sigmoid(pred), gt)) + cost_mask * pixel-wise sigmoid focal cost, GT
+        masks bilinearly resized to the prediction size.  Returns None (no layer / no masks) or [n_layers, Q*sumT] in
+        the matcher's cost layout (image b's [Q, T_b] block row-major at Q*offset_b; zero rows for layers without
+        masks).  Device tensor ops: two [Q, HW] x [HW, T_b] GEMMs per (layer, image)."""
+        if not (self.cost_mask > 0 or self.cost_mask_dice > 0):
+            return None
+        if not any(o.get("pred_masks") is not None for o in outputs_list):
+            return None
+        if not any(t.get("masks") is not None and t["masks"].numel() > 0 for t in targets):
+            return None
+        sizes = [len(t["boxes"]) for t in targets]
+        Q = outputs_list[0]["pred_logits"].shape[1]
+        dev = outputs_list[0]["pred_logits"].device
+        extra = torch.zeros((len(outputs_list), Q * sum(sizes)), device=dev, dtype=torch.float32)
+        resized = {}
+        for li, o in enumerate(outputs_list):
+            pm = o.get("pred_masks")
+            if pm is None:
+                continue
+            if pm.shape[1] != Q:                    # denoising queries in front of the matching queries (matcher.py:192-198)
+                pm = pm[:, pm.shape[1] - Q:]
+            Hm, Wm = pm.shape[-2:]
+            off = 0
+            for b, t in enumerate(targets):
+                n = sizes[b]
+                m = t.get("masks")
+                if n == 0 or m is None or m.numel() == 0:
+                    off += n
+                    continue
+                key = (b, Hm, Wm)
+                if key not in resized:
+                    g = m.float().to(dev)
+                    if g.shape[-2:] != (Hm, Wm):
+                        g = F.interpolate(g.unsqueeze(1), size=(Hm, Wm), mode="bilinear", align_corners=False).squeeze(1)
+                    resized[key] = g.flatten(1)                                      # [T_b, HW]
+                gt = resized[key]
+                logit = pm[b].flatten(1).float()                                     # [Q, HW]
+                prob = logit.sigmoid()
+                cost = torch.zeros((Q, n), device=dev, dtype=torch.float32)
+                if self.cost_mask_dice > 0:
+                    num = 2 * (prob @ gt.t())
+                    den = prob.sum(1, keepdim=True) + gt.sum(1)
+                    cost = cost + self.cost_mask_dice * (1 - (num + 1e-6) / (den + 1e-6))
+                if self.cost_mask > 0:
+                    neg = (1 - self.alpha) * (prob ** self.gamma) * (-(1 - prob + 1e-8).log())
+                    pos = self.alpha * ((1 - prob) ** self.gamma) * (-(prob + 1e-8).log())
+                    cost = cost + self.cost_mask * ((pos @ gt.t() + neg @ (1 - gt).t()) / logit.shape[1])
+                extra[li, Q * off:Q * (off + n)] = cost.reshape(-1)
+                off += n
+        return extra
+
+    @torch.no_grad()
     def match_layers(self, outputs_list, targets):
         """Match several prediction sets (decoder layers) against the same targets at once.
         Returns, per layer, a list over images of (query_idx ascending, target_idx) int64 CPU tensors."""
-        for o in outputs_list:
-            if o.get("pred_masks") is not None and (self.cost_mask > 0 or self.cost_mask_dice > 0) and any(
-                    t.get("masks") is not None and t["masks"].numel() > 0 for t in targets):
-                raise NotImplementedError("mask matching cost (matcher.py:175-237) is a SURVEY §8(f) 'next' row")
+        extra = self.mask_cost(outputs_list, targets)
+        kw = {} if extra is None else {"extra_cost": extra}
         return K.match([o["pred_logits"] for o in outputs_list], [o["pred_boxes"] for o in outputs_list],
                        targets, self.alpha, self.gamma, float(self.cost_class), float(self.cost_bbox),
-                       float(self.cost_giou))
+                       float(self.cost_giou), **kw)
 
     @torch.no_grad()
     def match_layers_raw(self, outputs_list, targets):
         """Device-side half of ``match_layers``: launches the matcher and returns the provider's raw result
         (device int64 [n_layers, sumT] x2 on the CUDA path) without touching the host."""
-        for o in outputs_list:
-            if o.get("pred_masks") is not None and (self.cost_mask > 0 or self.cost_mask_dice > 0) and any(
-                    t.get("masks") is not None and t["masks"].numel() > 0 for t in targets):
-                raise NotImplementedError("mask matching cost (matcher.py:175-237) is a SURVEY §8(f) 'next' row")
+        extra = self.mask_cost(outputs_list, targets)
+        kw = {} if extra is None else {"extra_cost": extra}
         return K.match_raw([o["pred_logits"] for o in outputs_list], [o["pred_boxes"] for o in outputs_list],
                            targets, self.alpha, self.gamma, float(self.cost_class), float(self.cost_bbox),
-                           float(self.cost_giou))
+                           float(self.cost_giou), **kw)
 
     @staticmethod
     def raw_to_host(raw, plan):

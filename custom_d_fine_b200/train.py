@@ -235,8 +235,8 @@ class GraphedTrainStep(TrainStep):
                 and next(self.model.parameters()).is_cuda)
 
     def __call__(self, inputs, targets):
-        if not self._can_graph():
-            return super().__call__(inputs, targets)
+        if not self._can_graph() or any(t.get("masks") is not None for t in targets):
+            return super().__call__(inputs, targets)        # (segmentation batches run the eager step for now)
         key = (tuple(inputs.shape), tuple(int(t["labels"].shape[0]) for t in targets))
         g = self._graphs.get(key)
         if g is None:

@@ -51,3 +51,15 @@ def synthetic_batch(B, H, W, seed=1234, T=(10, 7, 0, 3), num_classes=80):
         targets.append({"labels": torch.randint(0, num_classes, (t,), generator=g),
                         "boxes": torch.cat([cxcy, wh], 1)})
     return x, targets
+
+
+def rect_masks(boxes, H, W):
+    """uint8 [T, H, W] filled GT rectangles of normalised cxcywh boxes (segment config targets)."""
+    T = boxes.shape[0]
+    m = torch.zeros(T, H, W, dtype=torch.uint8)
+    for i in range(T):
+        cx, cy, w, h = boxes[i].tolist()
+        x0, x1 = int(round((cx - w / 2) * W)), int(round((cx + w / 2) * W))
+        y0, y1 = int(round((cy - h / 2) * H)), int(round((cy + h / 2) * H))
+        m[i, max(y0, 0):max(min(y1, H), 0), max(x0, 0):max(min(x1, W), 0)] = 1
+    return m

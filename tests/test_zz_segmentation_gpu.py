@@ -1,0 +1,74 @@
+"""Segmentation rows through the CUDA table, against the CPU oracle.
+
+The host graph, the oracle ops and their parity with the REAL reference are pinned on CPU
+(tests/test_oracle_cpu.py::test_seg_*).  The CUDA side — the plain-conv autograd binding over the library's conv kernels,
+the matcher kernel's additive mask-cost input, GroupNorm / bilinear resize / mask product as torch device ops — was
+written after the round's GPU budget was spent: these tests have NOT run on hardware yet, hence the non-strict xfail
+marks (an XPASS is the expected outcome; the file sorts last so that it cannot hide another test behind `-x`).
+"""
+import pytest
+import torch
+
+from custom_d_fine_b200 import kernels
+from custom_d_fine_b200.model import build_loss, build_model
+from tests.golden.common import rect_masks, seeded_fill, synthetic_batch
+from tests.util import check_rows_up_to_order
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="segmentation CUDA path not yet verified on a GPU (end of round 1)")]
+
+
+def test_matcher_extra_cost_matches_oracle(cuda_ops, oracle_ops):
+    g = torch.Generator().manual_seed(5)
+    NL, B, Q, C, sizes = 3, 2, 60, 80, [7, 4]
+    logits = [torch.randn(B, Q, C, generator=g) for _ in range(NL)]
+    boxes = [torch.rand(B, Q, 4, generator=g) * 0.5 + 0.2 for _ in range(NL)]
+    targets = [{"labels": torch.randint(0, C, (n,), generator=g), "boxes": torch.rand(n, 4, generator=g) * 0.4 + 0.2}
+               for n in sizes]
+    extra = torch.rand(NL, Q * sum(sizes), generator=g) * 3.0
+    want = oracle_ops.match(logits, boxes, targets, extra_cost=extra)
+    got = cuda_ops.match([t.cuda() for t in logits], [t.cuda() for t in boxes],
+                         [{k: v.cuda() for k, v in t.items()} for t in targets], extra_cost=extra.cuda())
+    for l in range(NL):
+        for b in range(B):
+            assert got[l][b][0].tolist() == want[l][b][0].tolist() and got[l][b][1].tolist() == want[l][b][1].tolist()
+
+
+def test_segmentation_step_matches_cpu_oracle(cuda_ops, oracle_ops):
+    hw, seed = 320, 2
+    x, targets = synthetic_batch(2, hw, hw, seed=1234 + seed)
+    for t in targets:
+        t["masks"] = rect_masks(t["boxes"], hw, hw)
+    runs = {}
+    for dev in ("cpu", "cuda"):
+        torch.manual_seed(0)
+        model = build_model("s", 80, True, dev, img_size=(hw, hw))
+        seeded_fill(model, seed)
+        model.train()
+        xs = x.to(dev)
+        tg = [{k: v.to(dev) for k, v in t.items()} for t in targets]
+        crit = build_loss("s", 80, 0.0, True)
+        torch.manual_seed(7)
+        from tests.test_model_gpu import _host_rng
+        with _host_rng():
+            if dev == "cpu":
+                with kernels.use(oracle_ops):
+                    out = model(xs, targets=tg)
+                    losses = crit(out, tg)
+                    sum(losses.values()).backward()
+            else:
+                out = model(xs, targets=tg)
+                losses = crit(out, tg)
+                sum(losses.values()).backward()
+                torch.cuda.synchronize()
+        runs[dev] = (model, out, losses)
+    (m0, o0, l0), (m1, o1, l1) = runs["cpu"], runs["cuda"]
+    assert list(l0.keys()) == list(l1.keys())
+    for k in l0:
+        a, b = float(l1[k]), float(l0[k])
+        assert abs(a - b) <= 3e-3 * max(abs(b), 1e-2), (k, a, b)
+    both = torch.cat([o1["pred_logits"], o1["pred_boxes"]], -1)
+    both_ref = torch.cat([o0["pred_logits"], o0["pred_boxes"]], -1)
+    check_rows_up_to_order("seg: pred_logits|pred_boxes", both, both_ref, 1e-3, 1.0)
+    d = (o1["dn_pred_masks"].cpu() - o0["dn_pred_masks"]).abs().max() / o0["dn_pred_masks"].abs().max()
+    assert float(d) <= 1e-3, float(d)
