@@ -1081,7 +1081,7 @@ class CudaOps:
         """(boxes, LQE statistics) of one decoder layer from one pass over pred_corners."""
         return _FdrHead.apply(corners, ref, project, _as_dev_scalar(reg_scale, corners.device), k, True, True)
 
-    # ---- segmentation head (SURVEY §8 row a25; built at the end of round 1, NOT yet run on a GPU) ----
+    # ---- segmentation head (SURVEY §8 row a25; parity-checked on B200 by tests/test_zz_segmentation_gpu.py) ----
     # The three convolutions go through the library's conv kernels; GroupNorm, the bilinear resizes and the
     # [B,Q,C] x [B,HW,C] mask product are composed from torch device ops for now (their own kernels are next).
     def conv2d(self, x, w, stride=1, pad=(0, 0, 0, 0), groups=1):

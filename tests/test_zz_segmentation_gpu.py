@@ -1,10 +1,9 @@
 """Segmentation rows through the CUDA table, against the CPU oracle.
 
 The host graph, the oracle ops and their parity with the REAL reference are pinned on CPU
-(tests/test_oracle_cpu.py::test_seg_*).  The CUDA side — the plain-conv autograd binding over the library's conv kernels,
-the matcher kernel's additive mask-cost input, GroupNorm / bilinear resize / mask product as torch device ops — was
-written after the round's GPU budget was spent: these tests have NOT run on hardware yet, hence the non-strict xfail
-marks (an XPASS is the expected outcome; the file sorts last so that it cannot hide another test behind `-x`).
+(tests/test_oracle_cpu.py::test_seg_*).  The CUDA side: the plain-conv autograd binding over the library's conv kernels,
+the matcher kernel's additive mask-cost input (`dfine_matcher_extra`), GroupNorm / bilinear resize / mask product as
+torch device ops.  Both tests passed on a B200 in the last GPU call of round 1 (tools/gpu_trip38.sh).
 """
 import pytest
 import torch
@@ -14,8 +13,7 @@ from custom_d_fine_b200.model import build_loss, build_model
 from tests.golden.common import rect_masks, seeded_fill, synthetic_batch
 from tests.util import check_rows_up_to_order
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="segmentation CUDA path not yet verified on a GPU (end of round 1)")]
+pytestmark = pytest.mark.gpu
 
 
 def test_matcher_extra_cost_matches_oracle(cuda_ops, oracle_ops):
