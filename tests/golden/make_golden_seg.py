@@ -52,7 +52,17 @@ def seg_case(size, B, hw, seed):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if "--l" in sys.argv:       # BASELINE config 3 family (D-FINE-l segment): losses + indices only (small fixture)
+        fix = seg_case("l", 2, 320, 5)
+        small = {k: fix[k] for k in ("size", "B", "hw", "seed", "losses", "indices", "pred_masks_absmax", "mask_keys")}
+        small["grad_norms"] = {k: v for k, v in fix["grad_norms"].items() if "mask" in k}
+        torch.save(small, HERE / "model_l_seg_320.pt")
+        print(len(small["losses"]), (HERE / "model_l_seg_320.pt").stat().st_size)
+        sys.exit(0)
     fix = seg_case("s", 2, 320, 2)
+    fix["grads"].pop("decoder.mask_decoder.up_conv.weight", None)       # 2.4 MB; its norm is kept
+    fix["pred_masks_q0_20"] = fix["pred_masks_q0_20"][:, :10].clone()
+    fix["dn_pred_masks_q0_8"] = fix["dn_pred_masks_q0_8"][:, :4].clone()
     torch.save(fix, HERE / "model_s_seg_320.pt")
     print({k: v for k, v in fix["losses"].items() if "mask" in k})
     print(len(fix["losses"]), fix["mask_keys"][:6], (HERE / "model_s_seg_320.pt").stat().st_size)
