@@ -52,6 +52,22 @@ def seg_case(size, B, hw, seed):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if "--x" in sys.argv:       # BASELINE config 4 family (D-FINE-x detect): losses + indices only
+        torch.manual_seed(0)
+        model = build_model("x", 80, False, "cpu", img_size=(320, 320))
+        seeded_fill(model, 11)
+        model.train()
+        x, targets = synthetic_batch(2, 320, 320, seed=1234 + 11)
+        torch.manual_seed(7)
+        out = model(x, targets=targets)
+        crit = build_loss("x", 80, 0.0, False)
+        losses = crit(out, targets)
+        with torch.no_grad():
+            idx = crit.matcher({k: v for k, v in out.items() if "aux" not in k}, targets)["indices"]
+        torch.save({"size": "x", "B": 2, "hw": 320, "seed": 11, "losses": {k: float(v) for k, v in losses.items()},
+                    "indices": [(i.clone(), j.clone()) for i, j in idx]}, HERE / "model_x_320.pt")
+        print(len(losses), (HERE / "model_x_320.pt").stat().st_size)
+        sys.exit(0)
     if "--l" in sys.argv:       # BASELINE config 3 family (D-FINE-l segment): losses + indices only (small fixture)
         fix = seg_case("l", 2, 320, 5)
         small = {k: fix[k] for k in ("size", "B", "hw", "seed", "losses", "indices", "pred_masks_absmax", "mask_keys")}
