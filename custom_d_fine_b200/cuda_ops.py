@@ -93,7 +93,8 @@ class _timed:
             # In an eager step the device is idle when a launch arrives, so an event recorded before the (ctypes) call
             # would also time the host's 10-20 us of argument marshalling.  A short spin kernel queued first keeps the
             # stream busy until start event, kernel and stop event are all enqueued: the pair then brackets the kernel.
-            torch.cuda._sleep(_SPIN_CYCLES)
+            if hasattr(torch.cuda, "_sleep"):
+                torch.cuda._sleep(_SPIN_CYCLES)
             self.s.record()
 
     def __exit__(self, *exc):
