@@ -23,9 +23,10 @@ from .kernels import K
 
 
 def cxcywh_to_xyxy(b):
-    cx, cy, w, h = b.unbind(-1)
-    w, h = w.clamp(min=0.0), h.clamp(min=0.0)
-    return torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], -1)
+    # (cx - 0.5 w, cy - 0.5 h, cx + 0.5 w, cy + 0.5 h) with w, h clamped at 0 — the reference's arithmetic on column
+    # PAIRS: 5 device ops instead of 13 per call (12 calls per step), bit-identical values
+    half = 0.5 * b[..., 2:].clamp(min=0.0)
+    return torch.cat([b[..., :2] - half, b[..., :2] + half], -1)
 
 
 def paired_iou_union(a, b):
@@ -41,8 +42,8 @@ def paired_iou_union(a, b):
 
 def _iou_nd(a, b):
     """paired_iou_union for [..., 4] xyxy tensors (broadcasting)."""
-    area_a = (a[..., 2] - a[..., 0]) * (a[..., 3] - a[..., 1])
-    area_b = (b[..., 2] - b[..., 0]) * (b[..., 3] - b[..., 1])
+    sa, sb = a[..., 2:] - a[..., :2], b[..., 2:] - b[..., :2]
+    area_a, area_b = sa[..., 0] * sa[..., 1], sb[..., 0] * sb[..., 1]
     wh = (torch.min(a[..., 2:], b[..., 2:]) - torch.max(a[..., :2], b[..., :2])).clamp(min=0)
     inter = wh[..., 0] * wh[..., 1]
     union = area_a + area_b - inter
@@ -69,10 +70,10 @@ def fdr_bin_targets(ref, gt_xyxy, reg_max, reg_scale, up, eps=0.1):
     from .decoder import weighting_function
 
     rs = abs(reg_scale)
-    sw, sh = ref[:, 2] / rs + 1e-16, ref[:, 3] / rs + 1e-16
-    d = torch.stack([(ref[:, 0] - gt_xyxy[:, 0]) / sw - 0.5 * rs, (ref[:, 1] - gt_xyxy[:, 1]) / sh - 0.5 * rs,
-                     (gt_xyxy[:, 2] - ref[:, 0]) / sw - 0.5 * rs, (gt_xyxy[:, 3] - ref[:, 1]) / sh - 0.5 * rs],
-                    -1).reshape(-1)
+    swh = ref[:, 2:] / rs + 1e-16                                   # (sw, sh)
+    # ((rx - x1)/sw, (ry - y1)/sh, (x2 - rx)/sw, (y2 - ry)/sh) - 0.5 rs on column pairs (same arithmetic, 7 ops for 34)
+    d = (torch.cat([ref[:, :2] - gt_xyxy[:, :2], gt_xyxy[:, 2:] - ref[:, :2]], -1) / torch.cat([swh, swh], -1)
+         - 0.5 * rs).reshape(-1)
     wn = weighting_function(reg_max, up, reg_scale)
     left = ((wn[None] - d[:, None]) <= 0).sum(1) - 1
     idx = left.float()

@@ -34,7 +34,28 @@ def bias_init_with_prob(p=0.01):
 
 
 def weighting_function(reg_max, up, reg_scale):
-    """Non-uniform FDR bin positions W(n), [reg_max+1] (arch/utils.py:145-188)."""
+    """Non-uniform FDR bin positions W(n), [reg_max+1] (arch/utils.py:145-188).
+
+    The reference rebuilds W(n) with ~90 one-element tensor ops every time it is needed (once per decoder forward, once
+    per FGL target set: ~270 tiny launches per train step).  `up` / `reg_scale` are non-trainable parameters, so the
+    result is memoised ON the `up` tensor (it dies with the model), keyed by the partner tensor's identity and both
+    version counters: the very same op sequence runs once per parameter version (bit-identical values), later calls —
+    and CUDA-graph captures — reuse the tensor."""
+    if up.requires_grad or reg_scale.requires_grad:
+        return _weighting_function(reg_max, up, reg_scale)
+    ent = getattr(up, "_dfine_wn", None)
+    key = (reg_max, up._version, reg_scale._version, up.data_ptr(), reg_scale.data_ptr(), up.device)
+    if ent is not None and ent[0] is reg_scale and ent[1] == key:
+        return ent[2]
+    wn = _weighting_function(reg_max, up, reg_scale).detach()
+    try:        # (writes that bypass the version counter — `p.data.fill_()` — are invisible here, as they are to autograd)
+        up._dfine_wn = (reg_scale, key, wn)
+    except AttributeError:      # a tensor type that refuses attributes: just recompute next time
+        pass
+    return wn
+
+
+def _weighting_function(reg_max, up, reg_scale):
     ub1 = abs(up[0]) * abs(reg_scale)
     ub2 = ub1 * 2
     step = (ub1 + 1) ** (2 / (reg_max - 2))
