@@ -91,6 +91,33 @@ def fdr_bin_targets(ref, gt_xyxy, reg_max, reg_scale, up, eps=0.1):
     return idx.clamp(min=0, max=reg_max - eps).detach(), w_r.detach(), w_l.detach()
 
 
+class _Scalars(torch.autograd.Function):
+    """vec [S] -> S zero-dim tensors (the entries of the loss dict).  Autograd's own `vec[k]` answers every entry's
+    gradient with a zero-filled [S] tensor, a copy and an accumulation (3 tiny kernels per loss term, 48 terms); here
+    the backward is ONE stack of the incoming scalars."""
+
+    @staticmethod
+    def forward(ctx, vec):
+        ctx.n, ctx.like = vec.shape[0], vec
+        return tuple(vec.unbind(0))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        z = None
+        out = []
+        for g in grads:
+            if g is None:
+                if z is None:
+                    z = ctx.like.new_zeros(())
+                g = z
+            out.append(g)
+        return torch.stack(out)
+
+
+def _scalars(vec):
+    return _Scalars.apply(vec) if vec.shape[0] else ()
+
+
 class IndexPlan:
     """Host-built, fixed-shape index table of one step.
 
@@ -554,16 +581,21 @@ class DFINECriterion(nn.Module):
         vfl, l1, gi, fgl, ddf = (torch.nan_to_num(v, nan=0.0) for v in (vfl, l1, gi, fgl, ddf))
         losses = {}
 
-        def put(suffix, k, lay=None, with_ddf=False):
-            losses["loss_vfl" + suffix] = vfl_[k] * W["loss_vfl"]
-            losses["loss_bbox" + suffix] = l1_[k] * W["loss_bbox"]
-            losses["loss_giou" + suffix] = gi_[k] * W["loss_giou"]
-            if lay is not None:
-                losses["loss_fgl" + suffix] = fgl_[lay] * W["loss_fgl"]
-                if with_ddf:
-                    losses["loss_ddf" + suffix] = ddf_[lay] * W["loss_ddf"] if lay < ddf_.shape[0] else ddf_.sum() * 0
+        def weighted(vfl_, l1_, gi_, fgl_, ddf_):
+            # one multiply per loss family (not per term) and one gradient stack per family (see _Scalars)
+            return (_scalars(vfl_ * W["loss_vfl"]), _scalars(l1_ * W["loss_bbox"]), _scalars(gi_ * W["loss_giou"]),
+                    _scalars(fgl_ * W["loss_fgl"]), _scalars(ddf_ * W["loss_ddf"]), ddf_)
 
-        vfl_, l1_, gi_, fgl_, ddf_ = vfl, l1, gi, fgl, ddf
+        def put(suffix, k, lay=None, with_ddf=False):
+            losses["loss_vfl" + suffix] = fam[0][k]
+            losses["loss_bbox" + suffix] = fam[1][k]
+            losses["loss_giou" + suffix] = fam[2][k]
+            if lay is not None:
+                losses["loss_fgl" + suffix] = fam[3][lay]
+                if with_ddf:
+                    losses["loss_ddf" + suffix] = fam[4][lay] if lay < len(fam[4]) else fam[5].sum() * 0
+
+        fam = weighted(vfl, l1, gi, fgl, ddf)
         put("", 0, L - 1)
         for i in range(L - 1):
             put(f"_aux_{i}", 1 + i, i, True)
@@ -580,7 +612,7 @@ class DFINECriterion(nn.Module):
             vfl_ = self._vfl_sets(dlog, dbox, s_dn.b[None], s_dn.q[None], s_dn.t[None], tg, dn_num)
             l1_, gi_ = self._box_sets(dbox, s_dn, tg, dn_num)
             fgl_, ddf_ = self._local_sets(dc, db_, dr[0], dl[L - 1], s_dn, tg, dn_num, up, reg_scale, True)
-            vfl_, l1_, gi_, fgl_, ddf_ = (torch.nan_to_num(v, nan=0.0) for v in (vfl_, l1_, gi_, fgl_, ddf_))
+            fam = weighted(*(torch.nan_to_num(v, nan=0.0) for v in (vfl_, l1_, gi_, fgl_, ddf_)))
             n_dn_layers = len(outputs["dn_outputs"])
             for i in range(n_dn_layers):
                 put(f"_dn_{i}", i, i, True)
