@@ -36,8 +36,21 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-MODEL, HW, NUM_CLASSES, T_PER_IMG = "m", 640, 80, 10
-CPU_SAMPLE_BATCH = 2
+NUM_CLASSES, T_PER_IMG = 80, 10
+# BASELINE.json configs that fit one GPU (the per-GPU half of the data-parallel ones): name -> (size, img, batch/GPU, masks)
+WORKLOADS = {
+    "m640": ("m", 640, 16, False, 4),       # configs[1] / [2]: the headline
+    "lseg640": ("l", 640, 8, True, 2),      # configs[3]: D-FINE-l + mask head
+    "x1280": ("x", 1280, 4, False, 1),      # configs[4]: per-GPU share of the 8-GPU run
+}   # last entry: images per step of the bounded CPU-arm sample
+MODEL, HW, SEG = "m", 640, False
+CPU_SAMPLE_BATCH = 4
+
+
+def select_workload(name, batch=None):
+    global MODEL, HW, SEG, CPU_SAMPLE_BATCH
+    MODEL, HW, b, SEG, CPU_SAMPLE_BATCH = WORKLOADS[name]
+    return batch or b
 
 
 def synthetic(batch, seed, device="cpu", pin=False):
@@ -52,8 +65,24 @@ def synthetic(batch, seed, device="cpu", pin=False):
     return x, labels, boxes
 
 
-def to_targets(labels, boxes):
-    return [{"labels": labels[i], "boxes": boxes[i]} for i in range(labels.shape[0])]
+def rect_masks(boxes, hw):
+    """uint8 [B, T, hw, hw] filled GT rectangles (the segment config's targets)."""
+    B, T, _ = boxes.shape
+    ys = torch.arange(hw).view(1, 1, hw, 1)
+    xs = torch.arange(hw).view(1, 1, 1, hw)
+    x0 = ((boxes[..., 0] - boxes[..., 2] / 2) * hw).round().view(B, T, 1, 1)
+    x1 = ((boxes[..., 0] + boxes[..., 2] / 2) * hw).round().view(B, T, 1, 1)
+    y0 = ((boxes[..., 1] - boxes[..., 3] / 2) * hw).round().view(B, T, 1, 1)
+    y1 = ((boxes[..., 1] + boxes[..., 3] / 2) * hw).round().view(B, T, 1, 1)
+    return ((xs >= x0) & (xs < x1) & (ys >= y0) & (ys < y1)).to(torch.uint8)
+
+
+def to_targets(labels, boxes, masks=None):
+    out = [{"labels": labels[i], "boxes": boxes[i]} for i in range(labels.shape[0])]
+    if masks is not None:
+        for i, t in enumerate(out):
+            t["masks"] = masks[i]
+    return out
 
 
 class ClockSampler:
@@ -110,7 +139,7 @@ def build_step(device, world, local_rank, eager=False):
     from custom_d_fine_b200.model import build_loss, build_model, build_optimizer
     from custom_d_fine_b200.train import GraphedTrainStep, ModelEMA, TrainStep
     torch.manual_seed(0)
-    model = build_model(MODEL, NUM_CLASSES, False, device, img_size=(HW, HW))
+    model = build_model(MODEL, NUM_CLASSES, SEG, device, img_size=(HW, HW))
     # non-zero heads so every loss term (incl. DDF, zero at fresh init) does real work
     g = torch.Generator().manual_seed(1)
     with torch.no_grad():
@@ -120,7 +149,7 @@ def build_step(device, world, local_rank, eager=False):
     model.train()
     ema = ModelEMA(model, 0.9998)
     net = model      # data-parallel ranks all-reduce the optimizer's flat gradient arenas (no DDP wrapper)
-    loss_fn = build_loss(MODEL, NUM_CLASSES, 0.0, False)
+    loss_fn = build_loss(MODEL, NUM_CLASSES, 0.0, SEG)
     opt = build_optimizer(model, lr=1.5e-4, backbone_lr=2e-5, betas=(0.9, 0.999), weight_decay=1.25e-4, base_lr=1.5e-4)
     cls = TrainStep if eager else GraphedTrainStep
     step = cls(net, loss_fn, opt, scheduler=None, ema=ema, clip_max_norm=0.1)
@@ -142,8 +171,9 @@ def run_ours(args):
     B = args.batch
     step = build_step(device, world, local_rank)
     hx, hl, hb = synthetic(B, 1234 + rank, pin=True)
+    hm = rect_masks(hb, HW).pin_memory() if SEG else None
     dx, dl, db = hx.to(device), hl.to(device), hb.to(device)
-    dtargets = to_targets(dl, db)
+    dtargets = to_targets(dl, db, hm.to(device) if SEG else None)
 
     def sync_all():
         if world > 1:
@@ -179,7 +209,7 @@ def run_ours(args):
 
         def __iter__(self):
             for _ in range(self.n):
-                yield hx, to_targets(hl, hb), None
+                yield hx, to_targets(hl, hb, hm), None
 
     def run_e2e(n):
         from custom_d_fine_b200.train import DevicePrefetcher
@@ -213,6 +243,14 @@ def run_ours(args):
     # tf32 tensor peak = half the measured dense bf16 rate (kind::tf32 issues at half the kind::f16 rate);
     # ridge point of a launch, in FLOP per algorithmic fp32 byte
     tf32_peak = float(pk0.get("bf16_tflops_sustained", 1394.5)) / 2.0
+    tf32_measured = False
+    tfile = ROOT / "profiles" / "r2_tf32_peak.json"
+    if tfile.exists():       # cuBLAS tf32 8192^3 measured on this pool's B200 (tools/measure_tf32_peak.py)
+        try:
+            tf32_peak = float(json.loads(tfile.read_text())["tf32_tflops_sustained"])
+            tf32_measured = True
+        except (KeyError, ValueError):
+            pass
     ridge = tf32_peak * 1e12 / (float(pk0.get("hbm_gbs", 6650.0)) * 1e9)
     for name, recs in cuda_ops.counters.timed.items():
         durs = [r[0].elapsed_time(r[1]) for r in recs]
@@ -258,8 +296,10 @@ def run_ours(args):
         name = max(kern, key=lambda k: kern[k][3])        # the family with the largest share of the step
         e = entry(name)
         # DRAM traffic per launch of that family from the committed ncu pass (tools/gpu_trip_final.sh ncu_traffic)
-        traffic, tr_file = None, ROOT / "profiles" / "r1_traffic.json"
-        if tr_file.exists():
+        traffic, tr_file = None, ROOT / "profiles" / "r2_traffic.json"
+        if not tr_file.exists():
+            tr_file = ROOT / "profiles" / "r1_traffic.json"
+        if tr_file.exists() and args.config == "m640":
             tr = json.loads(tr_file.read_text()).get(name)
             traffic = int(tr["dram_bytes_per_launch"]) if tr else None
         roof = {"kernel": name, "bound": "hbm", "achieved": e["GB/s"], "peak": hbm_peak, "unit": "GB/s",
@@ -273,18 +313,22 @@ def run_ours(args):
                 "by_bound": split.get(name),
                 "others": {k: dict(entry(k), **({"by_bound": split[k]} if k in split else {})) for k in kern if k != name}}
     cpu = cpu_baseline(steps=2, warmup=1) if world == 1 and not args.no_cpu_baseline else None
+    tf32_src = "measured cuBLAS tf32 8192^3 (profiles/r2_tf32_peak.json)" if tf32_measured else "assumed = measured bf16 sustained / 2"
+    if roof is not None:
+        roof["tf32_peak_source"] = tf32_src
     imgs = B * world * args.steps
     line = {
-        "metric": "images/sec (640x640) D-FINE-m train step", "value": round(imgs / (ms_total * 1e-3), 2),
+        "metric": metric_name(), "value": round(imgs / (ms_total * 1e-3), 2),
         "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
         "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "tf32 tensor-core operands / fp32 storage+accumulate", "data": "synthetic",
-        "config": {"workload": f"D-FINE-{MODEL} detect train step (fwd + criterion + bwd + clip + AdamW + EMA), "
-                               f"batch {B}/GPU, {HW}x{HW}, {T_PER_IMG} boxes/img, COCO-80 classes, Lq=500",
+        "config": {"workload": workload_text(B), "name": args.config, "weights": "seeded default init with randomised zero-"
+                   "initialised heads (the COCO checkpoint of SURVEY 8d is used by the parity tests; perf-neutral)",
                    "global_batch": B * world, "parallelism": f"dp{world}", "launch_mode": mode, "gemm_mode": cuda_ops.get_gemm_mode(),
                    "l2": "per-step working set (activations + grads > 10 GB) exceeds the 126 MB L2"},
         "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 2), "unit": "images/s", "ms_per_step": round(ms_e2e / args.steps, 3),
-                "h2d_bytes_per_step": int(hx.numel() * 4 + hl.numel() * 8 + hb.numel() * 4), "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": int(hx.numel() * 4 + hl.numel() * 8 + hb.numel() * 4 + (hm.numel() if SEG else 0)),
+                "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
     }
     if graphed and step.host_gap_ms() is not None:
@@ -294,17 +338,79 @@ def run_ours(args):
         torch.distributed.destroy_process_group()
 
 
-def cpu_step_fn(batch):
-    """The CPU port: this repo's host graph with the oracle provider (reference arithmetic on torch CPU ops)."""
+def metric_name():
+    return f"images/sec ({HW}x{HW}) D-FINE-{MODEL}{'-seg' if SEG else ''} train step"
+
+
+def workload_text(B):
+    return (f"D-FINE-{MODEL} {'segment' if SEG else 'detect'} train step (fwd + criterion + bwd + clip + AdamW + EMA), "
+            f"batch {B}/GPU, {HW}x{HW}, {T_PER_IMG} boxes/img{' + filled-rectangle masks' if SEG else ''}, COCO-80 classes, Lq=500")
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+REF_DIR = ROOT / "baseline" / "_ref"
+
+
+def _reference_available():
+    return (REF_DIR / "MANIFEST.json").exists() and (REF_DIR / "src" / "d_fine" / "dfine.py").exists()
+
+
+def reference_step_fn(batch):
+    """The UNMODIFIED reference (`baseline/_ref/src/d_fine`, copied byte for byte by tools/install_reference.py; see its
+    MANIFEST.json) on CPU: its own build_model / build_loss / build_optimizer and the body of its hot loop
+    (train.py:571-581 forward, criterion, backward; 512-535 clip_grad_norm_ + AdamW.step + zero_grad) in fp32
+    (`amp_enabled=False`).  The reference's ModelEMA lives in src/dl/train.py, which cannot be imported here (hydra,
+    albumentations, torchmetrics are absent): the EMA update is left out of the CPU arm, in the reference's favour."""
+    # the reference's package is called `src`, like this repo's drop-in shims: make its tree the only `src` visible
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+        del sys.modules[k]
+    keep = [q for q in sys.path if q not in ("", str(ROOT), str(ROOT) + "/")]
+    sys.path[:] = [str(REF_DIR)] + keep
+    try:
+        import logging
+        logging.disable(logging.WARNING)
+        try:
+            from loguru import logger
+            logger.remove()
+        except Exception:  # noqa: BLE001
+            pass
+        from src.d_fine.dfine import build_loss, build_model, build_optimizer
+    finally:
+        sys.path[:] = [str(ROOT)] + [q for q in sys.path if q != str(REF_DIR)]
+    torch.manual_seed(0)
+    model = build_model(MODEL, NUM_CLASSES, SEG, "cpu", img_size=(HW, HW))
+    model.train()
+    loss_fn = build_loss(MODEL, NUM_CLASSES, 0.0, SEG)
+    opt = build_optimizer(model, lr=1.5e-4, backbone_lr=2e-5, betas=(0.9, 0.999), weight_decay=1.25e-4, base_lr=1.5e-4)
+    x, l, b = synthetic(batch, 1234)
+    targets = to_targets(l, b, rect_masks(b, HW) if SEG else None)
+    for t in targets:
+        t["orig_size"] = torch.tensor([HW, HW])
+
+    def step():
+        out = model(x, targets=targets)
+        loss = sum(loss_fn(out, targets).values())
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
+        opt.step()
+        opt.zero_grad()
+        return float(loss.detach())
+
+    return step
+
+
+def port_step_fn(batch):
+    """Fallback when baseline/_ref is absent: this repo's host graph with the oracle provider (the reference's
+    arithmetic restated on torch CPU ops)."""
     from custom_d_fine_b200 import kernels
     from custom_d_fine_b200.model import build_loss, build_model
     from oracle.torch_ops import OracleOps
     torch.manual_seed(0)
-    model = build_model(MODEL, NUM_CLASSES, False, "cpu", img_size=(HW, HW))
+    model = build_model(MODEL, NUM_CLASSES, SEG, "cpu", img_size=(HW, HW))
     model.train()
-    loss_fn = build_loss(MODEL, NUM_CLASSES, 0.0, False)
+    loss_fn = build_loss(MODEL, NUM_CLASSES, 0.0, SEG)
     x, l, b = synthetic(batch, 1234)
-    targets = to_targets(l, b)
+    targets = to_targets(l, b, rect_masks(b, HW) if SEG else None)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
     ops = OracleOps()
 
@@ -321,45 +427,44 @@ def cpu_step_fn(batch):
     return step
 
 
-def cpu_baseline(steps, warmup):
+def cpu_arm(steps, warmup, batch):
+    """(images/s, cores, kind, sample text) of the CPU arm: the unmodified reference when baseline/_ref travelled."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = cpu_step_fn(CPU_SAMPLE_BATCH)
+    kind = "reference" if _reference_available() else "port"
+    step = (reference_step_fn if kind == "reference" else port_step_fn)(batch)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return {"value": round(CPU_SAMPLE_BATCH * steps / dt, 3), "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} train steps of batch {CPU_SAMPLE_BATCH} (D-FINE-{MODEL}, {HW}x{HW}) after {warmup} warm-up, "
-                      f"torch CPU ops, {cores} threads"}
+    what = ("the unmodified reference src/d_fine (baseline/_ref, fp32, no EMA)" if kind == "reference"
+            else "the oracle port (this repo's host graph over oracle/torch_ops.py)")
+    sample = (f"{steps} train steps of batch {batch} (bounded sample of the workload: D-FINE-{MODEL}{'-seg' if SEG else ''}, "
+              f"{HW}x{HW}, fwd + criterion + bwd + clip + AdamW) after {warmup} warm-up, {what}, torch CPU, {cores} threads")
+    return batch * steps / dt, dt / steps, cores, kind, sample
+
+
+def cpu_baseline(steps, warmup):
+    v, _, cores, kind, sample = cpu_arm(steps, warmup, CPU_SAMPLE_BATCH)
+    return {"value": round(v, 3), "unit": "images/s", "cores": cores, "kind": kind, "sample": sample}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    step = cpu_step_fn(CPU_SAMPLE_BATCH)
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    v = round(CPU_SAMPLE_BATCH * args.steps / dt, 3)
+    v, s_per_step, cores, kind, sample = cpu_arm(args.steps, args.warmup, CPU_SAMPLE_BATCH)
+    v = round(v, 3)
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    sample = (f"each step = one train step on a bounded sample of {CPU_SAMPLE_BATCH} images of the workload "
-              f"(D-FINE-{MODEL}, {HW}x{HW}, fwd+criterion+bwd+clip+AdamW), torch CPU ops, {cores} threads, rank 0 only")
     print(json.dumps({
-        "impl": "reference", "metric": "images/sec (640x640) D-FINE-m train step", "value": v, "unit": "images/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1),
+        "impl": "reference", "metric": metric_name(), "value": v, "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(s_per_step * 1e3, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": f"D-FINE-{MODEL} detect train step, {HW}x{HW}, {T_PER_IMG} boxes/img, COCO-80 classes "
-                               f"(CPU arm: {CPU_SAMPLE_BATCH} images per step)", "parallelism": "cpu"},
-        "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_text(args.batch) + f" (CPU arm: each step = {CPU_SAMPLE_BATCH} images of it)",
+                   "name": args.config, "parallelism": "cpu", "rank0_only": True},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -370,9 +475,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="images per GPU (BASELINE config: 16)")
+    ap.add_argument("--config", default="m640", choices=sorted(WORKLOADS),
+                    help="BASELINE.json workload: m640 (headline, configs 1/2), lseg640 (config 3), x1280 (config 4)")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.batch = select_workload(args.config, args.batch)
     if args.impl == "reference":
         run_reference(args)
     else:
