@@ -27,6 +27,23 @@ void dfine_set_error(const char* fmt, ...);
         }                                                                                \
     } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (call site, device): a process that later switches to
+// another GPU must set the attribute there too.  `kernel` may be a parenthesised template-id.
+#define DFINE_SET_SMEM_ONCE(kernel, bytes, what)                                                                   \
+    do {                                                                                                           \
+        static unsigned long long done__ = 0ull;                                                                   \
+        int dev__ = 0;                                                                                             \
+        cudaGetDevice(&dev__);                                                                                     \
+        if (!((done__ >> (dev__ & 63)) & 1ull)) {                                                                  \
+            cudaError_t e__ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+            if (e__ != cudaSuccess) {                                                                              \
+                dfine_set_error("%s: smem attribute (%d B): %s", what, (int)(bytes), cudaGetErrorString(e__));     \
+                return (int)e__;                                                                                   \
+            }                                                                                                      \
+            done__ |= 1ull << (dev__ & 63);                                                                        \
+        }                                                                                                          \
+    } while (0)
+
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_GELU = 3 };

@@ -1101,13 +1101,8 @@ void pick_patch(int OH, int OW, int max_span, int* TW, int* TH) {
 template <int BN, int X3, int STAGES>
 int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mwlo, float* y, const float* bias,
                double* stats, const FwdParams& p, int B, cudaStream_t st) {
-    static bool configured = false;
     const int smem = (int)sizeof(FwdSmem<BN, X3, STAGES>) + 1024;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<BN, X3, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) { dfine_set_error("tc_fwd: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-        configured = true;
-    }
+    DFINE_SET_SMEM_ONCE((tc_fwd_kernel<BN, X3, STAGES>), smem, "tc_fwd");
     dim3 grid(B * p.tiles_w * p.tiles_h, ceil_div(p.N, BN));
     tc_fwd_kernel<BN, X3, STAGES><<<grid, fwd_threads(X3), smem, st>>>(mx, mw, mwlo, y, bias, stats, p);
     return 0;
@@ -1126,13 +1121,8 @@ int sm_count() {
 template <int BN, int X3, int STAGES>
 int launch_persist(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mwlo, float* y, const float* bias,
                    double* stats, const FwdParams& p, int B, cudaStream_t st) {
-    static bool configured = false;
     const int smem = (int)sizeof(PersistSmem<BN, X3, STAGES>) + 1024;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_fwd_persist<BN, X3, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) { dfine_set_error("tc_fwd_persist: smem attribute (%d B): %s", smem, cudaGetErrorString(e)); return (int)e; }
-        configured = true;
-    }
+    DFINE_SET_SMEM_ONCE((tc_fwd_persist<BN, X3, STAGES>), smem, "tc_fwd_persist");
     TileSched ts;
     ts.n_tiles = ceil_div(p.N, BN);
     ts.total = B * p.tiles_w * p.tiles_h * ts.n_tiles;
@@ -1143,13 +1133,8 @@ int launch_persist(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorM
 
 template <int BN>
 int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, float* dwr, WgradParams p, cudaStream_t st) {
-    static bool configured = false;
     const int smem = (int)sizeof(WgradSmem<BN>) + 1024;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) { dfine_set_error("tc_wgrad: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-        configured = true;
-    }
+    DFINE_SET_SMEM_ONCE((tc_wgrad_kernel<BN>), smem, "tc_wgrad");
     p.cin_tiles = ceil_div(p.Cin, BN);
     const int gx = ceil_div(p.Cout, BM), gy = p.taps_h * p.taps_w * p.cin_tiles;
     long splits = (148L * 2 + (long)gx * gy - 1) / ((long)gx * gy);

@@ -44,6 +44,11 @@ __device__ __forceinline__ Key shfl_key(const Key& k, int o) {
     return r;
 }
 
+// A label outside [0, C) would be an out-of-bounds read of the logits row (the reference raises an index error there,
+// matcher.py:150); labels are validated on the host where they are host tensors (train.DevicePrefetcher) and clamped
+// here so that a bad device-resident label can never read outside the tensor.
+__device__ __forceinline__ long clamp_label(long l, int C) { return l < 0 ? 0 : (l >= C ? C - 1 : l); }
+
 __device__ __forceinline__ float cost_entry(const float* __restrict__ lg, const float* __restrict__ bx,
                                             long label, const float* __restrict__ tb, float alpha, float gamma,
                                             float w_class, float w_bbox, float w_giou, float extra = 0.f,
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(32) matcher_kernel(
     for (int e = lane; e < Q * T; e += 32) {
         const int q = e / T, t = e % T;
         const float ex = extra ? __ldg(extra + (long)layer * Q * sumT + (long)Q * t0 + e) : 0.f;
-        const float c = cost_entry(lg + (long)q * C, bx + q * 4, labels[t0 + t], tboxes + (long)(t0 + t) * 4, alpha,
+        const float c = cost_entry(lg + (long)q * C, bx + q * 4, clamp_label(labels[t0 + t], C), tboxes + (long)(t0 + t) * 4, alpha,
                                    gamma, w_class, w_bbox, w_giou, ex, extra != nullptr);
         if (cost_out) cost_out[(long)layer * Q * sumT + (long)Q * t0 + e] = c;
         if (transposed) w.cost[t * Cc + q] = c; else w.cost[q * Cc + t] = c;
@@ -241,12 +246,7 @@ int matcher_impl(const float* logits, const float* boxes, const long* labels, co
     DFINE_REQUIRE(fixed <= 200 * 1024, "matcher: problem too large (Q=%d, Tmax=%d)", Q, Tmax);
     DFINE_REQUIRE(in_smem || workspace != nullptr, "matcher: workspace required for Q=%d Tmax=%d", Q, Tmax);
     const long smem = fixed + (in_smem ? cost : 0);
-    static int configured = 0;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(matcher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        if (e != cudaSuccess) { dfine_set_error("matcher: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-        configured = 1;
-    }
+    DFINE_SET_SMEM_ONCE(matcher_kernel, 220 * 1024, "matcher");
     matcher_kernel<<<NL * B, 32, smem, (cudaStream_t)stream>>>(logits, boxes, labels, tboxes, toff, out_q, out_t,
                                                               cost_out, workspace, extra, NL, B, Q, C, sumT, Tmax,
                                                               in_smem, alpha, gamma, w_class, w_bbox, w_giou);

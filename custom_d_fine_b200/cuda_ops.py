@@ -429,12 +429,26 @@ def _conv_dgrad(dy, ldy, weight, wkey, dx, ldx, geom, res=None):
                                        pad[1], c_long(ldx), c_long(ldy), _stream()), "conv_dgrad_simt")
 
 
+# Parameters whose ``.grad`` is a view of a flat-arena optimizer's gradient arena (optim.FusedAdamW registers them):
+# id(param) -> weakref.  ONLY these take the direct-accumulation path below.  Any other parameter — a stock torch
+# optimizer, a DDP wrap with gradient_as_bucket_view (whose reducer must see the AccumulateGrad hook fire),
+# torch.autograd.grad, user hooks on weights — gets its gradient returned to autograd as usual.
+_direct_grads = {}
+
+
+def register_direct_grad(p):
+    _direct_grads[id(p)] = weakref.ref(p)
+
+
 def _grad_dst(p, kind):
     """The parameter's pre-zeroed ``.grad`` viewed in the layout a kernel accumulates into, or None.
     With the flat-arena optimizer (optim.FusedAdamW) gradients live in an arena zeroed by the optimizer step, so
-    backward kernels add straight into it (no temporary, no AccumulateGrad add kernel); a parameter without such
-    a gradient buffer (plain torch optimizer) takes the returned-gradient path."""
+    backward kernels add straight into it (no temporary, no AccumulateGrad add kernel); a parameter that is not
+    registered by such an optimizer takes the returned-gradient path."""
     if p is None or not p.is_leaf or not p.requires_grad:
+        return None
+    ent = _direct_grads.get(id(p))
+    if ent is None or ent() is not p:
         return None
     g = p.grad
     if g is None or not g.is_cuda or g.dtype != torch.float32:
@@ -1035,6 +1049,9 @@ class CudaOps:
         frozen = num_batches_tracked is None
         if training and num_batches_tracked is not None:
             num_batches_tracked.add_(1)
+        if groups == 1 and (x.shape[-1] % 4 or w.shape[0] % 4):
+            return self._conv_bn_act_padded(x, w, stride, pad, bn_w, bn_b, running_mean, running_var, training,
+                                            momentum, eps, act, lab_scale, lab_bias, pre_add, post_add, frozen, tap)
         # tap: also return the input as a second output (see _ConvBnAct.forward); plain pass-through without autograd
         tap_ag = bool(tap) and _TAP and torch.is_grad_enabled() and x.requires_grad
         cfg = (stride, tuple(pad), groups, bool(training), float(momentum), float(eps), act, frozen, tap_ag)
@@ -1042,6 +1059,33 @@ class CudaOps:
         if tap and not tap_ag:
             return out, x
         return out
+
+    def _conv_bn_act_padded(self, x, w, stride, pad, bn_w, bn_b, running_mean, running_var, training, momentum, eps,
+                            act, lab_scale, lab_bias, pre_add, post_add, frozen, tap):
+        """Channel counts that are not multiples of 4 (D-FINE-n: the 21-channel CSP layers of expansion 0.34 and their
+        298-channel concat, hybrid_encoder.py:181-239): the kernels' 16-byte channel granularity is met by padding the
+        channel STRIDE, not by changing the math — input channels, weight rows / columns and the BatchNorm vectors are
+        zero-extended to the next multiple of 4 (gamma = beta = 0 on the pad channels, so they stay exactly zero
+        through BatchNorm, the activation and every gradient), the same kernels run on the padded tensors and the
+        result is the channel-prefix view.  Parameters keep their reference shapes (state-dict identical); the pad /
+        slice are autograd ops, so parameter gradients arrive through the ordinary accumulation path."""
+        F = torch.nn.functional
+        Cin, Cout = x.shape[-1], w.shape[0]
+        ci, co = (-Cin) % 4, (-Cout) % 4
+        xp = F.pad(x, (0, ci)) if ci else x
+        wp = F.pad(w, (0, 0, 0, 0, 0, ci, 0, co)) if (ci or co) else w
+        vec = (lambda t, v=0.0: F.pad(t, (0, co), value=v)) if co else (lambda t, v=0.0: t)
+        rm, rv = vec(running_mean), vec(running_var, 1.0)
+        padc = (lambda t: None if t is None else (F.pad(t, (0, co)) if co else t))
+        cfg = (stride, tuple(pad), 1, bool(training), float(momentum), float(eps), act, frozen, False)
+        out = _ConvBnAct.apply(xp, wp, vec(bn_w), vec(bn_b), lab_scale, lab_bias, padc(pre_add), padc(post_add), rm, rv,
+                               cfg)
+        if training and co:
+            with torch.no_grad():
+                running_mean.copy_(rm[:Cout])
+                running_var.copy_(rv[:Cout])
+        y = out[..., :Cout] if co else out
+        return (y, x) if tap else y
 
     def maxpool2x2_s1_padbr(self, x):
         return _MaxPool.apply(x)
@@ -1155,6 +1199,8 @@ class CudaOps:
             for sz in sizes:
                 offs.append(offs[-1] + sz)
             toff = torch.tensor(offs, dtype=torch.int32).to(dev)
+            if len(self._toff_cache) >= 256:          # bounded: per-image target counts rarely repeat with a real loader
+                self._toff_cache.pop(next(iter(self._toff_cache)))
             self._toff_cache[key] = toff
         labels = torch.cat([t["labels"] for t in targets]).to(dev, torch.int64).contiguous()
         tboxes = torch.cat([t["boxes"] for t in targets]).to(dev, torch.float32).contiguous()

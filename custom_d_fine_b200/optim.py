@@ -11,6 +11,10 @@ floating-point buffers — HBM-bound passes of 36 B/parameter instead of ~2 k ti
 (lr, weight decay, step count, EMA momentum) are read from a small device table refreshed by one pinned H2D
 copy, so the launches replay unchanged from a CUDA graph while a scheduler keeps mutating ``param_groups``.
 
+Known divergence from torch.optim.AdamW: the kernel updates every arena element, so a parameter that received no
+gradient in a step (the mask head on a batch without masks) still sees weight decay and its decaying momentum, where
+torch skips parameters whose ``.grad`` is None.  No BASELINE config has such a step.
+
 Data-parallel runs all-reduce the flat gradient arenas (one NCCL call per group over NVLink) in
 ``allreduce_grads`` — the only collective on the gradient path.
 """
@@ -79,8 +83,10 @@ class FusedAdamW(torch.optim.Optimizer):
                 raise RuntimeError("FusedAdamW needs CUDA parameters (there is no CPU compute path)")
             pflat, offs = flatten_into_arena(ps)
             gflat = torch.zeros_like(pflat)
+            from . import cuda_ops
             for p, o in zip(ps, offs):
                 p.grad = _arena_view(gflat, o, p)          # same layout as the parameter: kernels accumulate in place
+                cuda_ops.register_direct_grad(p)           # backward kernels may add straight into this view
             a = dict(params=ps, offs=offs, p=pflat, g=gflat, m=torch.zeros_like(pflat), v=torch.zeros_like(pflat),
                      ema=None, planes=None)
             if any(p.dim() >= 2 for p in ps):
@@ -164,8 +170,45 @@ class FusedAdamW(torch.optim.Optimizer):
             dist.broadcast(self._buf_ema, src)
         self._register_planes()      # the arenas were overwritten behind the parameters' version counters
 
+    # ---- checkpoint format: torch.optim.AdamW's (per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq``) ------------
+    def state_dict(self):
+        """The Adam moments live in flat arenas; they are exposed here per parameter in torch.optim.AdamW's own
+        layout (logical parameter shapes, cloned), so a checkpoint written by this optimizer resumes in either this
+        class or a stock ``torch.optim.AdamW`` over the same groups (the reference's optimizer, dfine.py:87-124)."""
+        self.state.clear()
+        for a in self._arenas:
+            if a is None:
+                continue
+            for p, o in zip(a["params"], a["offs"]):
+                self.state[p] = {"step": torch.tensor(float(self._t)),
+                                 "exp_avg": _arena_view(a["m"], o, p).detach().clone(),
+                                 "exp_avg_sq": _arena_view(a["v"], o, p).detach().clone()}
+        sd = super().state_dict()
+        self.state.clear()
+        sd["fused"] = {"t": self._t, "ema_momentum": self._ema_m}
+        return sd
+
     def load_state_dict(self, state_dict):
-        super().load_state_dict(state_dict)
+        state_dict = dict(state_dict)
+        fused = state_dict.pop("fused", None)
+        super().load_state_dict(state_dict)            # param_groups (lr, betas, ...) + per-parameter state tensors
+        t = None
+        with torch.no_grad():
+            for a in self._arenas:
+                if a is None:
+                    continue
+                for p, o in zip(a["params"], a["offs"]):
+                    st = self.state.get(p)
+                    if not st:
+                        continue
+                    _arena_view(a["m"], o, p).copy_(st["exp_avg"])
+                    _arena_view(a["v"], o, p).copy_(st["exp_avg_sq"])
+                    t = int(st["step"]) if t is None else t
+        self.state.clear()
+        if fused is not None:
+            self._t, self._ema_m = int(fused["t"]), float(fused["ema_momentum"])
+        elif t is not None:
+            self._t = t
         self._register_planes()
 
     def allreduce_grads(self):

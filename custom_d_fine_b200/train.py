@@ -212,11 +212,17 @@ class GraphedTrainStep(TrainStep):
     device table refreshed before each replay, so an LR scheduler keeps working.  Constraint: no gradient
     accumulation (accum_steps == 1) and the flat-arena optimizer; anything else runs the eager step."""
 
-    def __init__(self, *args, eager_steps=3, **kw):
+    def __init__(self, *args, eager_steps=3, max_graphs=8, max_keys=1024, **kw):
         super().__init__(*args, **kw)
+        from collections import OrderedDict
         self.eager_steps = eager_steps
-        self._seen = {}
-        self._graphs = {}
+        # Every per-key cache is bounded.  With a real loader the per-image target counts rarely repeat: such keys run
+        # the eager step (a correct, slower path), are remembered in an LRU of `max_keys` counters, and only a key seen
+        # more than `eager_steps` times is captured; at most `max_graphs` captured keys (each owns a private memory pool
+        # for its forward + backward) are kept, least recently replayed evicted first.
+        self.max_graphs, self.max_keys = max_graphs, max_keys
+        self._seen = OrderedDict()
+        self._graphs = OrderedDict()
         self._plans = {}
         # Warm-up steps and captures share ONE side stream: autograd's AccumulateGrad nodes remember the stream
         # they were created on, and a node created on the legacy default stream cannot be used under capture.
@@ -239,20 +245,31 @@ class GraphedTrainStep(TrainStep):
             return super().__call__(inputs, targets)        # (segmentation batches run the eager step for now)
         key = (tuple(inputs.shape), tuple(int(t["labels"].shape[0]) for t in targets))
         g = self._graphs.get(key)
-        if g is None:
-            n = self._seen.get(key, 0)
-            self._seen[key] = n + 1
+        if g is not None:
+            self._graphs.move_to_end(key)
+        else:
+            n = self._seen.pop(key, 0)
+            self._seen[key] = n + 1                        # (re-inserted at the recent end)
+            while len(self._seen) > self.max_keys:
+                old, _ = self._seen.popitem(last=False)
+                self._plans.pop(old, None)
             cur = torch.cuda.current_stream()
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
-                if n < self.eager_steps:
+                if n < self.eager_steps or key not in self._plans:     # (a plan evicted with its counter: one more eager step)
                     res = super().__call__(inputs, targets)
-                    self._plans[key] = self.loss_fn.last_plan  # valid index plan of this key, reused to capture
+                    if n >= self.eager_steps - 1:          # the index plan of the LAST eager step is reused to capture
+                        self._plans[key] = self.loss_fn.last_plan
+                    eager = True
                 else:
                     g = self._capture(inputs, targets, self._plans.pop(key))
                     self._graphs[key] = g
+                    self._seen.pop(key, None)
+                    while len(self._graphs) > self.max_graphs:      # drop the least recently replayed key and its pool
+                        self._graphs.popitem(last=False)
+                    eager = False
             cur.wait_stream(self._side)
-            if n < self.eager_steps:
+            if eager:
                 return res
         return self._replay(g, inputs, targets)
 
@@ -314,4 +331,7 @@ class GraphedTrainStep(TrainStep):
         cuda_ops.weights_changed()                       # graph C rewrote the parameters
         cuda_ops.counters.launches += g["launches"]      # library kernels replayed by the graphs
         self.batch_idx += 1
-        return g["loss"], g["loss_dict"]
+        # the graph's output buffers are overwritten by every replay: hand out copies (one stacked clone), so that a
+        # caller may keep the losses of several steps (src/dl/train.Trainer averages them per epoch)
+        vals = torch.stack([g["loss"]] + list(g["loss_dict"].values())).clone()
+        return vals[0], dict(zip(g["loss_dict"].keys(), vals[1:].unbind(0)))

@@ -1,0 +1,121 @@
+"""BASELINE.json's configurations at their stated sizes, and D-FINE-n, through the CUDA library against the CPU oracle
+driving the same host graph on the same seeded weights and batch (one train step: forward, criterion with the on-device
+Hungarian matcher, backward):
+
+  config 1   D-FINE-n (21-channel CSP layers, head_dim 16, two feature levels) — 320x320, batch 2
+  config 4   D-FINE-l + mask head, 640x640, batch 8 (87 loss terms, mask cost in the matcher, mask losses)
+  config 5   D-FINE-x, 1280x1280, batch 4 per GPU (AIFI over 1600 tokens x head_dim 48, MSDA over 33 600 tokens)
+
+Bars (north star: 1e-3 relative on logits / boxes, bit-exact Hungarian indices given equal costs): relative L2 error of
+pred_logits and of pred_boxes after pairing the query rows through the top-k order, every loss term relative to
+max(|ref|, 1e-2); the worst single entry is reported and only guarded (it is a property of the network: top-300
+selection and deformable sampling amplify a 1e-6 GEMM rounding a thousandfold).
+"""
+import pytest
+import torch
+
+from custom_d_fine_b200 import cuda_ops as co
+from custom_d_fine_b200 import kernels
+from custom_d_fine_b200.model import build_loss, build_model
+from tests.golden.common import rect_masks, seeded_fill, synthetic_batch
+from tests.test_model_gpu import _check_param_grads, _host_rng
+
+pytestmark = pytest.mark.gpu
+
+
+def step_both(oracle_ops, size, hw, B, seg, mode, seed=11, T=(10, 7, 0, 3)):
+    x, targets = synthetic_batch(B, hw, hw, seed=1234 + seed, T=T)
+    if seg:
+        for t in targets:
+            t["masks"] = rect_masks(t["boxes"], hw, hw)
+    runs = {}
+    prev = co.get_gemm_mode()
+    co.set_gemm_mode(mode)
+    try:
+        for dev in ("cpu", "cuda"):
+            torch.manual_seed(0)
+            model = build_model(size, 80, seg, dev, img_size=(hw, hw))
+            seeded_fill(model, seed)
+            model.train()
+            xs = x.to(dev)
+            tg = [{k: v.to(dev) for k, v in t.items()} for t in targets]
+            crit = build_loss(size, 80, 0.0, seg)
+            torch.manual_seed(7)
+            with _host_rng():
+                if dev == "cpu":
+                    with kernels.use(oracle_ops):
+                        out = model(xs, targets=tg)
+                        losses = crit(out, tg)
+                        sum(losses.values()).backward()
+                else:
+                    out = model(xs, targets=tg)
+                    losses = crit(out, tg)
+                    sum(losses.values()).backward()
+                    torch.cuda.synchronize()
+            runs[dev] = (model, out, losses)
+    finally:
+        co.set_gemm_mode(prev)
+    return runs["cpu"], runs["cuda"]
+
+
+def compare(tag, cpu, cuda, l2_bar, loss_bar, entry_bar, grad_scale=2.0):
+    (m0, o0, l0), (m1, o1, l1) = cpu, cuda
+    assert list(l0.keys()) == list(l1.keys())
+    worst_loss = ("", 0.0)
+    for k in l0:
+        a, b = float(l1[k]), float(l0[k])
+        e = abs(a - b) / max(abs(b), 1e-2)
+        if e > worst_loss[1]:
+            worst_loss = (k, e)
+    C = o0["pred_logits"].shape[-1]
+    both = torch.cat([o1["pred_logits"], o1["pred_boxes"]], -1).detach().double().cpu()
+    both_ref = torch.cat([o0["pred_logits"], o0["pred_boxes"]], -1).detach().double()
+    scale = both_ref.abs().max()
+    l2 = {"pred_logits": 0.0, "pred_boxes": 0.0}
+    worst_entry, unpaired, pairing = 0.0, 0, []
+    for b in range(both.shape[0]):
+        dist = torch.cdist(both[b], both_ref[b], p=float("inf"))
+        vals, idx = dist.min(1)
+        pairing.append(idx)
+        unpaired += both.shape[1] - len(set(idx.tolist()))
+        worst_entry = max(worst_entry, float(vals.max() / scale))
+        ref = both_ref[b][idx]
+        for name, sl in (("pred_logits", slice(0, C)), ("pred_boxes", slice(C, C + 4))):
+            l2[name] = max(l2[name], float((both[b][:, sl] - ref[:, sl]).norm() / ref[:, sl].norm()))
+    print(f"\n[{tag}] rel-L2 logits {l2['pred_logits']:.2e} boxes {l2['pred_boxes']:.2e}; worst entry {worst_entry:.2e}; "
+          f"worst loss term {worst_loss[0]} {worst_loss[1]:.2e}; unpaired rows {unpaired}; {len(l0)} loss terms")
+    assert unpaired == 0, f"{tag}: {unpaired} query rows do not pair up one-to-one"
+    assert l2["pred_logits"] <= l2_bar and l2["pred_boxes"] <= l2_bar, (tag, l2)
+    assert worst_loss[1] <= loss_bar, (tag, worst_loss)
+    assert worst_entry <= entry_bar, (tag, worst_entry)
+    if grad_scale:
+        _check_param_grads(tag, m1, m0, lambda k: (0.1 if k.startswith("backbone") else 0.05) * grad_scale)
+    return pairing
+
+
+@pytest.mark.parametrize("mode,l2_bar,entry_bar", [("simt", 1e-3, 1e-3), ("tc3", 1e-3, 5e-3)])
+def test_n_matches_cpu_oracle(cuda_ops, oracle_ops, mode, l2_bar, entry_bar):
+    """D-FINE-n (BASELINE config 1's family) ON THE GPU: its 21 / 298-channel layers run through the same kernels on
+    zero-extended channel strides (cuda_ops._conv_bn_act_padded); head_dim 16 attention and deformable attention."""
+    cpu, cuda = step_both(oracle_ops, "n", 320, 2, False, mode)
+    compare(f"n/{mode}", cpu, cuda, l2_bar, 3e-3, entry_bar, grad_scale=1.0 if mode == "simt" else 2.0)
+
+
+def test_x_1280_batch4_matches_cpu_oracle(cuda_ops, oracle_ops):
+    """BASELINE config 5 (per-GPU share): D-FINE-x, 1280x1280, batch 4, default tensor-core mode."""
+    cpu, cuda = step_both(oracle_ops, "x", 1280, 4, False, "tc3", T=(10, 7, 3, 10))
+    compare("x@1280/tc3", cpu, cuda, 2e-3, 6e-3, 2e-2, grad_scale=4.0)
+
+
+def test_lseg_640_batch8_matches_cpu_oracle(cuda_ops, oracle_ops):
+    """BASELINE config 4: D-FINE-l with the mask head, 640x640, batch 8, default tensor-core mode (mask matching cost,
+    mask BCE / Dice terms, MaskDecoder, [B,Q,160,160] mask logits per layer)."""
+    cpu, cuda = step_both(oracle_ops, "l", 640, 8, True, "tc3", T=(10, 7, 3, 10))
+    (m0, o0, l0), (m1, o1, l1) = cpu, cuda
+    assert len(l0) == 87, len(l0)
+    pairing = compare("l-seg@640/tc3", cpu, cuda, 2e-3, 6e-3, 2e-2, grad_scale=4.0)
+    got = torch.stack([o1["pred_masks"][b].detach().cpu() for b in range(len(pairing))])
+    ref = torch.stack([o0["pred_masks"][b].detach()[pairing[b]] for b in range(len(pairing))])
+    d = (got - ref).norm() / ref.norm()
+    print(f"[l-seg@640/tc3] pred_masks rel-L2 {float(d):.2e}")
+    assert float(d) <= 2e-3, float(d)
