@@ -16,7 +16,7 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libdfine_sm100.so"
 SOURCES = ["lib.cu", "msda.cu", "matcher.cu", "norm_act.cu", "spatial.cu", "conv_simt.cu", "attention.cu", "attention_mma.cu",
-           "gemm_tc.cu", "fdr.cu", "stem.cu", "optim.cu"]
+           "gemm_tc.cu", "fdr.cu", "stem.cu", "optim.cu", "loss.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
 PER_FILE = {"matcher.cu": ["-fmad=false"]}
@@ -38,7 +38,7 @@ def _stale(target: Path, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = _nvcc()
-    headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h"))
+    headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list((CSRC.parents[1] / "include").glob("dfine_loss_desc.h"))
     srcs = [s for s in SOURCES if (CSRC / s).exists()]
     objs, jobs = [], []
     for s in srcs:

@@ -13,6 +13,8 @@ B200-first differences (values unchanged):
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -559,15 +561,16 @@ class DFINECriterion(nn.Module):
         ddf = (l_pos * self.num_pos + l_neg * self.num_neg) / (self.num_pos + self.num_neg)
         return fgl, torch.where(identical, torch.zeros_like(ddf), ddf)
 
-    def _compute_batched(self, outputs, tg, table, counts, plan):
+    def _families_torch(self, outputs, tg, table, counts, plan):
+        """The five loss families of both query groups with torch device ops (the oracle's restatement; also the
+        DFINE_LOSS=torch A/B path on the GPU).  Returns (A, DN): tuples (vfl, l1, giou, fgl, ddf); group A vectors in plan
+        order (main, aux_0.., pre, enc), group DN in layer order (+ dn_pre)."""
         st_ = outputs["_stacked"]
         logits, boxes, corners, refs = st_["logits"], st_["boxes"], st_["corners"], st_["refs"]
         L = logits.shape[0]
         pre, enc = outputs["pre_outputs"], outputs["enc_aux_outputs"]
-        assert len(enc) == 1 and plan.n_sets == L + 2
         Q, n = plan.Q, plan.n_layer
         nb_go, nb = counts[0], counts[1]
-        W = self.weight_dict
         up, reg_scale = outputs["up"], outputs["reg_scale"]
         # plan order of the matched sets: main (= last layer), aux_0..aux_{L-2}, pre, enc
         order = torch.cat([logits[L - 1:], logits[:L - 1], pre["pred_logits"][None], enc[0]["pred_logits"][None]])
@@ -578,29 +581,8 @@ class DFINECriterion(nn.Module):
         s_go = _Set(table, *plan.set_slice("go"), Q, True)
         l1, gi = self._box_sets(order_b, s_go, tg, nb_go)
         fgl, ddf = self._local_sets(corners, boxes, refs[L - 1], logits[L - 1], s_go, tg, nb_go, up, reg_scale, False)
-        vfl, l1, gi, fgl, ddf = (torch.nan_to_num(v, nan=0.0) for v in (vfl, l1, gi, fgl, ddf))
-        losses = {}
-
-        def weighted(vfl_, l1_, gi_, fgl_, ddf_):
-            # one multiply per loss family (not per term) and one gradient stack per family (see _Scalars)
-            return (_scalars(vfl_ * W["loss_vfl"]), _scalars(l1_ * W["loss_bbox"]), _scalars(gi_ * W["loss_giou"]),
-                    _scalars(fgl_ * W["loss_fgl"]), _scalars(ddf_ * W["loss_ddf"]), ddf_)
-
-        def put(suffix, k, lay=None, with_ddf=False):
-            losses["loss_vfl" + suffix] = fam[0][k]
-            losses["loss_bbox" + suffix] = fam[1][k]
-            losses["loss_giou" + suffix] = fam[2][k]
-            if lay is not None:
-                losses["loss_fgl" + suffix] = fam[3][lay]
-                if with_ddf:
-                    losses["loss_ddf" + suffix] = fam[4][lay] if lay < len(fam[4]) else fam[5].sum() * 0
-
-        fam = weighted(vfl, l1, gi, fgl, ddf)
-        put("", 0, L - 1)
-        for i in range(L - 1):
-            put(f"_aux_{i}", 1 + i, i, True)
-        put("_pre", L)
-        put("_enc_0", L + 1)
+        A = tuple(torch.nan_to_num(v, nan=0.0) for v in (vfl, l1, gi, fgl, ddf))
+        DN = None
         if "dn_outputs" in outputs:
             meta = outputs["dn_meta"]
             dl, db_, dc, dr = st_["dn_logits"], st_["dn_boxes"], st_["dn_corners"], st_["dn_refs"]
@@ -612,19 +594,97 @@ class DFINECriterion(nn.Module):
             vfl_ = self._vfl_sets(dlog, dbox, s_dn.b[None], s_dn.q[None], s_dn.t[None], tg, dn_num)
             l1_, gi_ = self._box_sets(dbox, s_dn, tg, dn_num)
             fgl_, ddf_ = self._local_sets(dc, db_, dr[0], dl[L - 1], s_dn, tg, dn_num, up, reg_scale, True)
-            fam = weighted(*(torch.nan_to_num(v, nan=0.0) for v in (vfl_, l1_, gi_, fgl_, ddf_)))
-            n_dn_layers = len(outputs["dn_outputs"])
-            for i in range(n_dn_layers):
-                put(f"_dn_{i}", i, i, True)
+            DN = tuple(torch.nan_to_num(v, nan=0.0) for v in (vfl_, l1_, gi_, fgl_, ddf_))
+        return A, DN
+
+    _perm_cache = {}
+
+    def _families_kernel(self, outputs, tg, table, counts, plan):
+        """The same five families from the criterion kernels (csrc/loss.cu): ONE autograd node over the unsplit decoder
+        stacks, ~6 launches forward and 6 backward instead of ~500 + ~1000 eager device ops."""
+        full = outputs["_stacked"]["full"]
+        L = full["logits"].shape[0]
+        enc = outputs["enc_aux_outputs"][0]
+        has_dn = "dn_outputs" in outputs
+        groups = outputs["dn_meta"]["dn_num_group"] if has_dn else 0
+        meta = dict(n_dn=full["n_dn"] if has_dn else 0, n_layer=plan.n_layer, go_cap=plan.go_cap,
+                    n_dn_entries=plan.n_dn if has_dn else 0, dn_groups=groups, alpha=self.alpha, gamma=self.gamma, T=5.0)
+        from .decoder import weighting_function
+        project = weighting_function(self.reg_max, outputs["up"], outputs["reg_scale"])
+        vfl, l1, gi, fgl, ddf = K.criterion_sets(full, enc["pred_logits"], enc["pred_boxes"], table, counts, tg[0], tg[1],
+                                                 project, outputs["reg_scale"], meta)
+        dev = vfl.device
+        key = (L, str(dev))
+        perm = self._perm_cache.get(key)
+        if perm is None:       # head order (layers, pre, enc) -> plan order (main = last layer, aux_0.., pre, enc)
+            perm = self._perm_cache[key] = torch.tensor([L - 1] + list(range(L - 1)) + [L, L + 1], device=dev)
+        A = (vfl[0].index_select(0, perm), l1[0].index_select(0, perm), gi[0].index_select(0, perm), fgl[0], ddf[0, :L - 1])
+        DN = (vfl[1, :L + 1], l1[1, :L + 1], gi[1, :L + 1], fgl[1], ddf[1, :L - 1]) if has_dn else None
+        return A, DN
+
+    def _compute_batched(self, outputs, tg, table, counts, plan, use_kernel=False):
+        st_ = outputs["_stacked"]
+        L = st_["logits"].shape[0]
+        enc = outputs["enc_aux_outputs"]
+        assert len(enc) == 1 and plan.n_sets == L + 2
+        A, DN = (self._families_kernel if use_kernel else self._families_torch)(outputs, tg, table, counts, plan)
+        W = self.weight_dict
+        Q = plan.Q
+        with_masks = "masks" in self.losses and "pred_masks" in outputs
+        losses = {}
+
+        def weighted(vfl_, l1_, gi_, fgl_, ddf_):
+            # one multiply per loss family (not per term) and one gradient stack per family (see _Scalars)
+            return (_scalars(vfl_ * W["loss_vfl"]), _scalars(l1_ * W["loss_bbox"]), _scalars(gi_ * W["loss_giou"]),
+                    _scalars(fgl_ * W["loss_fgl"]), _scalars(ddf_ * W["loss_ddf"]), ddf_)
+
+        def put(suffix, k, lay=None, with_ddf=False, mask_out=None, mask_set=None, mask_num=None):
+            losses["loss_vfl" + suffix] = fam[0][k]
+            losses["loss_bbox" + suffix] = fam[1][k]
+            losses["loss_giou" + suffix] = fam[2][k]
+            if lay is not None:
+                losses["loss_fgl" + suffix] = fam[3][lay]
+                if with_ddf:
+                    losses["loss_ddf" + suffix] = fam[4][lay] if lay < len(fam[4]) else fam[5].sum() * 0
+            if with_masks and mask_out is not None and "pred_masks" in mask_out:
+                for kk, v in self.loss_masks(mask_out, mask_set, tg, mask_num).items():
+                    if kk in W:
+                        losses[kk + suffix] = torch.nan_to_num(v * W[kk], nan=0.0)
+
+        nb = counts[1]
+        sets = [_Set(table, *plan.set_slice(k), Q, False) for k in range(plan.n_sets)] if with_masks else [None] * plan.n_sets
+        aux = outputs["aux_outputs"]
+        fam = weighted(*A)
+        put("", 0, L - 1, mask_out=outputs, mask_set=sets[0], mask_num=nb)
+        for i in range(L - 1):
+            put(f"_aux_{i}", 1 + i, i, True, mask_out=aux[i] if i < len(aux) else None, mask_set=sets[1 + i], mask_num=nb)
+        put("_pre", L)
+        put("_enc_0", L + 1)
+        if DN is not None:
+            meta = outputs["dn_meta"]
+            fam = weighted(*DN)
+            s_dn = _Set(table, *plan.set_slice("dn"), Q, False) if with_masks else None
+            dn_num = nb * meta["dn_num_group"]
+            dn_out = outputs["dn_outputs"]
+            for i in range(len(dn_out)):
+                put(f"_dn_{i}", i, i, True, mask_out=dn_out[i], mask_set=s_dn, mask_num=dn_num)
+            if with_masks and "dn_pred_masks" in outputs:      # final denoising layer's masks (dfine_criterion.py:756-767)
+                for kk, v in self.loss_masks({"pred_masks": outputs["dn_pred_masks"]}, s_dn, tg, dn_num).items():
+                    if kk in W:
+                        losses[kk + "_dn_final"] = torch.nan_to_num(v * W[kk], nan=0.0)
             put("_dn_pre", L)
         return losses
 
     def compute(self, outputs, tg, table, counts, plan):
         """Stage 3 (device): every loss term from the fixed-shape index table (dfine_criterion.py:655-777)."""
         self._clear_cache()
-        if (self.batched and "_stacked" in outputs and list(self.losses) == ["vfl", "boxes", "local"]
-                and "pred_masks" not in outputs and len(outputs["enc_aux_outputs"]) == 1):
-            return self._compute_batched(outputs, tg, table, counts, plan)
+        if (self.batched and "_stacked" in outputs and list(self.losses)[:3] == ["vfl", "boxes", "local"]
+                and set(self.losses) <= {"vfl", "boxes", "local", "masks"} and len(outputs["enc_aux_outputs"]) == 1):
+            # the criterion kernels when the provider has them (the CUDA table; DFINE_LOSS=torch keeps the device-op path
+            # for A/B runs), else the torch restatement (the CPU oracle)
+            use_kernel = (table.is_cuda and os.environ.get("DFINE_LOSS", "kernel") != "torch"
+                          and "full" in outputs["_stacked"] and hasattr(K, "criterion_sets"))
+            return self._compute_batched(outputs, tg, table, counts, plan, use_kernel)
         main, aux, pre, enc = self._matched_layers(outputs)
         Q = plan.Q
         nb_go, nb = counts[0], counts[1]

@@ -977,6 +977,64 @@ class _FdrHead(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+# criterion: every loss head of the step (VFL, L1 + GIoU, FGL + DDF) in one autograd node over the stacked tensors
+# ------------------------------------------------------------------------------------------------
+class _Criterion(torch.autograd.Function):
+    """Inputs: the UNSPLIT decoder stacks logits [L,B,n_dn+Q,C], boxes [L,B,n_dn+Q,4], corners [L,B,n_dn+Q,4*NB], the
+    pre head's [B,n_dn+Q,*] and the encoder head's [B,Q,*] tensors, plus the criterion's plan table / normalisers.
+    Outputs: the unweighted loss scalars as five small tensors (loss_desc.split_out).  Backward writes one gradient per
+    input tensor (logits / corners completely, boxes on matched rows of a zero fill)."""
+
+    @staticmethod
+    def forward(ctx, logits, boxes, corners, pre_logits, pre_boxes, enc_logits, enc_boxes, ref0, table, counts, labels,
+                tboxes, project, reg_scale, meta):
+        from . import loss_desc as ld
+        _req_cuda(logits, boxes, corners, table)
+        t = dict(logits=logits.contiguous(), boxes=boxes.contiguous(), corners=corners.contiguous(),
+                 ref0=ref0.detach().contiguous().float(), pre_logits=pre_logits.contiguous(),
+                 pre_boxes=pre_boxes.contiguous(), enc_logits=enc_logits.contiguous(), enc_boxes=enc_boxes.contiguous(),
+                 table=table.contiguous(), labels=labels.contiguous(), tboxes=tboxes.contiguous().float(),
+                 counts=counts.contiguous().float(), project=project.detach().contiguous().float(),
+                 reg_scale=reg_scale.detach().reshape(-1).float().contiguous())
+        assert t["table"].dtype == torch.int64 and t["labels"].dtype == torch.int64
+        d = ld.build(t, meta)
+        L = d.L
+        dev = logits.device
+        ws = torch.empty(int(lib().dfine_loss_workspace_bytes(L, d.B, d.Q, d.n_dn)), dtype=torch.uint8, device=dev)
+        out = torch.empty(ld.out_count(L), dtype=torch.float32, device=dev)
+        ref = ctypes.byref(d)
+        st = _stream()
+        _check(lib().dfine_loss_prepare(ref, _p(ws), st), "loss_prepare")
+        _check(lib().dfine_loss_vfl_fwd(ref, _p(ws), st), "loss_vfl_fwd")
+        _check(lib().dfine_loss_box_fwd(ref, _p(ws), st), "loss_box_fwd")
+        _check(lib().dfine_loss_fgl_ddf_fwd(ref, _p(ws), st), "loss_fgl_ddf_fwd")
+        _check(lib().dfine_loss_finalize(ref, _p(ws), _p(out), st), "loss_finalize")
+        ctx.t, ctx.meta, ctx.ws, ctx.out = t, dict(meta), ws, out
+        return tuple(v.clone() for v in ld.split_out(out, L))
+
+    @staticmethod
+    def backward(ctx, g_vfl, g_l1, g_gi, g_fgl, g_ddf):
+        from . import loss_desc as ld
+        t, ws, out = ctx.t, ctx.ws, ctx.out
+        d = ld.build(t, ctx.meta)
+        L, H = d.L, d.L + 2
+        dev = out.device
+        parts = []
+        for g, n in ((g_vfl, 2 * H), (g_l1, 2 * H), (g_gi, 2 * H), (g_fgl, 2 * L), (g_ddf, 2 * L)):
+            parts.append(torch.zeros(n, device=dev) if g is None else g.reshape(-1).float())
+        gout = torch.cat(parts).contiguous()
+        dlogits, dpre_l, denc_l = torch.empty_like(t["logits"]), torch.empty_like(t["pre_logits"]), torch.empty_like(t["enc_logits"])
+        dboxes, dpre_b, denc_b = torch.zeros_like(t["boxes"]), torch.zeros_like(t["pre_boxes"]), torch.zeros_like(t["enc_boxes"])
+        dcorners = torch.empty_like(t["corners"])
+        ref = ctypes.byref(d)
+        st = _stream()
+        _check(lib().dfine_loss_vfl_bwd(ref, _p(ws), _p(gout), _p(dlogits), _p(dpre_l), _p(denc_l), st), "loss_vfl_bwd")
+        _check(lib().dfine_loss_box_bwd(ref, _p(ws), _p(gout), _p(dboxes), _p(dpre_b), _p(denc_b), st), "loss_box_bwd")
+        _check(lib().dfine_loss_fgl_ddf_bwd(ref, _p(ws), _p(out), _p(gout), _p(dcorners), st), "loss_fgl_ddf_bwd")
+        return (dlogits, dboxes, dcorners, dpre_l, dpre_b, denc_l, denc_b) + (None,) * 8
+
+
+# ------------------------------------------------------------------------------------------------
 # small spatial ops
 # ------------------------------------------------------------------------------------------------
 def _nhwc_ld(x):
@@ -1151,6 +1209,14 @@ class CudaOps:
     def mask_dot(self, embed, feat_nhwc):
         _req_cuda(embed, feat_nhwc)
         return torch.einsum("bqc,bhwc->bqhw", embed, feat_nhwc)
+
+    # ---- criterion ----
+    def criterion_sets(self, full, enc_logits, enc_boxes, table, counts, labels, tboxes, project, reg_scale, meta):
+        """All VFL / L1 / GIoU / FGL / DDF terms of a step from the unsplit decoder stacks (loss.cu); returns
+        (vfl [2,L+2], l1, giou, fgl [2,L], ddf [2,L]) — group 0 = matching queries, 1 = denoising; heads = layers, pre, enc."""
+        return _Criterion.apply(full["logits"], full["boxes"], full["corners"], full["pre_logits"], full["pre_boxes"],
+                                enc_logits, enc_boxes, full["refs"][0], table, counts, labels, tboxes, project, reg_scale,
+                                meta)
 
     # ---- matcher ----
     @torch.no_grad()

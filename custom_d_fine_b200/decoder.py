@@ -434,8 +434,13 @@ class DFINETransformer(nn.Module):
             content, ref_unact, memory, shapes, self.dec_bbox_head, self.dec_score_head,
             self.query_pos_head, self.pre_bbox_head, attn_mask=attn_mask, return_queries=want_masks)
 
+        # the unsplit stacks ([L,B,n_dn+Q,*]): the criterion kernels read both query groups from them in place and write
+        # ONE gradient tensor per stack (no slicing / concatenation in autograd)
+        full = dict(logits=logits, boxes=boxes, corners=corners, refs=refs, pre_logits=pre_logits, pre_boxes=pre_boxes,
+                    n_dn=0)
         split_dn = self.training and dn_meta is not None
         if split_dn:
+            full["n_dn"] = dn_meta["dn_num_split"][0]
             n_dn = dn_meta["dn_num_split"][0]
             dn_pre_logits, pre_logits = pre_logits[:, :n_dn], pre_logits[:, n_dn:]
             dn_pre_boxes, pre_boxes = pre_boxes[:, :n_dn], pre_boxes[:, n_dn:]
@@ -466,7 +471,7 @@ class DFINETransformer(nn.Module):
         if want_masks:
             out["pred_masks"] = pred_masks
         # layer-stacked views of the same tensors: the criterion evaluates every loss family once over all layers
-        out["_stacked"] = {"logits": logits, "boxes": boxes, "corners": corners, "refs": refs}
+        out["_stacked"] = {"logits": logits, "boxes": boxes, "corners": corners, "refs": refs, "full": full}
         if split_dn:
             out["_stacked"].update(dn_logits=dn_logits, dn_boxes=dn_boxes, dn_corners=dn_corners, dn_refs=dn_refs)
         if self.aux_loss:

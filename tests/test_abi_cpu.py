@@ -52,3 +52,13 @@ def test_ops_fail_loudly_without_a_gpu():
     from custom_d_fine_b200.cuda_ops import CudaOps
     with pytest.raises(RuntimeError):
         CudaOps()
+
+
+def test_loss_descriptor_layout_matches_the_library(built_lib):
+    """The ctypes mirror of include/dfine_loss_desc.h has the size the compiled library uses (no compute call)."""
+    from custom_d_fine_b200 import loss_desc
+    L = ctypes.CDLL(str(built_lib))
+    L.dfine_loss_desc_size.restype = ctypes.c_int
+    assert L.dfine_loss_desc_size() == ctypes.sizeof(loss_desc.LossDesc)
+    L.dfine_loss_out_count.restype = ctypes.c_int
+    assert L.dfine_loss_out_count(4) == loss_desc.out_count(4)

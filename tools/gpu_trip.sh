@@ -15,7 +15,7 @@ run() { name=$1; shift; echo "== $name: $*" ; ( time timeout ${STEP_TIMEOUT:-900
 for step in "$@"; do
   IFS=: read -r kind a b c <<< "$step"
   case $kind in
-    tests)    if [ -n "$a" ]; then run tests_${b:-sel} python -m pytest tests -x -q -m gpu -s -k "$a"; else run tests python -m pytest tests -x -q -m gpu; fi ;;
+    tests)    if [ -n "$a" ]; then run tests_${b:-sel} python -m pytest tests -q -m gpu -s -k "$a"; else run tests python -m pytest tests -q -m gpu; fi ;;
     smoke)    run smoke python __graft_entry__.py smoke ;;
     bench)    run bench_${a:-m640}${b:+_$b} env ${b:+DFINE_GEMM=$b} python bench.py --config ${a:-m640} --steps 10 --warmup 3 ${c:+--no-cpu-baseline} ;;
     ref)      run bench_ref python bench.py --impl reference --steps 2 --warmup 1 ;;
