@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <mutex>
 #include <cstdlib>
 
@@ -167,6 +168,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn, int b_mn) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
+// kind::f16 with fp16 operands (a_format = b_format = 0), K-major, D = f32
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
 // {hi, lo} bf16 pair of an fp32 value: hi = RN bf16(x), lo = RN bf16(x - hi); x = hi + lo up to 2^-17 relative
 __device__ __forceinline__ void bf16_split(float x, uint32_t& hi, uint32_t& lo) {
     const uint32_t h = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x));
@@ -181,6 +186,15 @@ __device__ __forceinline__ uint32_t bf16x2_rn(float a, float b) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
 }
+
+// two fp32 -> one packed f16x2 word (element a in the low half), and the two halves back as fp32
+__device__ __forceinline__ uint32_t f16x2_rn(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ float f16_lo(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xffffu))); }
+__device__ __forceinline__ float f16_hi(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
 
 constexpr int BM = 128, BK = 32;
 constexpr int EPI_LD = 33;
@@ -219,6 +233,8 @@ struct FwdParams {
     int prefetch;             // k-blocks the prefetch warp may run ahead of the TMA producer (0 = off)
     int w_planes;             // 3xTF32: map_w is a 3-D {K, Cout, 2} map over adjacent hi / lo weight planes
     int wk2[MAX_TAPS];        // hybrid mode: first weight column of tap t in the tap-padded bf16 planes
+    int half16;               // 16-bit plane modes (X3 = 2): 0 = bf16 planes (3xBF16), 1 = fp16 planes (3xFP16)
+    float out_scale;          // accumulator scale applied first in the epilogue (3xFP16 weights are stored x 2^8)
     const float* res;         // optional tensor added to the output in the epilogue (same pixel geometry as y,
     long ldres;               // pixel stride ldres): fuses the gradient-accumulation add of a multi-consumer tensor
 };
@@ -561,7 +577,7 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                     if constexpr (X3 == 2) {
                         // bf16 planes: 64-byte rows (32 channels), 64-byte swizzle (layout 4), 8-row atoms of 512 B;
                         // UMMA_K = 16 bf16 = 32 bytes -> +2 in 16-byte units per k-step
-                        constexpr uint32_t idesc16 = make_idesc_bf16(BN);
+                        const uint32_t idesc16 = p.half16 ? make_idesc_f16(BN) : make_idesc_bf16(BN);
                         const uint64_t ah = make_desc(smem_u32(sm.a2[s]), 16, 512, 4);
                         const uint64_t al = make_desc(smem_u32(sm.a2[s] + Smem::A2_PLANE), 16, 512, 4);
                         const uint64_t bh = make_desc(smem_u32(sm.b[s]), 16, 512, 4);
@@ -663,6 +679,7 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                 for (int r8 = 0; r8 < 8; ++r8) {
                     const int r = 4 * r8 + lane / 8;
                     float4 o = lds128(wbase + (uint32_t)(r * EPL + 4 * (lane % 8)) * 4u);
+                    if (X3 == 2) { o.x *= p.out_scale; o.y *= p.out_scale; o.z *= p.out_scale; o.w *= p.out_scale; }
                     if (row_ok[r8] && col_ok) {
                         if (stats) {
                             s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
@@ -789,10 +806,20 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                             float4 tmp = x0; x0 = x1; x1 = tmp;
                             if constexpr (X3 == 3) { tmp = r0; r0 = r1; r1 = tmp; }
                         }
-                        const uint32_t b0 = bf16x2_rn(x0.x, x0.y), b1 = bf16x2_rn(x0.z, x0.w);
-                        const uint32_t b2 = bf16x2_rn(x1.x, x1.y), b3 = bf16x2_rn(x1.z, x1.w);
-                        uint32_t l0, l1, l2, l3;
-                        if constexpr (X3 == 2) {                     // residual against the bf16 value itself
+                        uint32_t b0, b1, b2, b3, l0, l1, l2, l3;
+                        if (X3 == 2 && p.half16) {                   // fp16 planes: hi = RN f16(x), lo = RN f16(x - hi)
+                            b0 = f16x2_rn(x0.x, x0.y); b1 = f16x2_rn(x0.z, x0.w);
+                            b2 = f16x2_rn(x1.x, x1.y); b3 = f16x2_rn(x1.z, x1.w);
+                            l0 = f16x2_rn(x0.x - f16_lo(b0), x0.y - f16_hi(b0));
+                            l1 = f16x2_rn(x0.z - f16_lo(b1), x0.w - f16_hi(b1));
+                            l2 = f16x2_rn(x1.x - f16_lo(b2), x1.y - f16_hi(b2));
+                            l3 = f16x2_rn(x1.z - f16_lo(b3), x1.w - f16_hi(b3));
+                        } else {
+                            b0 = bf16x2_rn(x0.x, x0.y); b1 = bf16x2_rn(x0.z, x0.w);
+                            b2 = bf16x2_rn(x1.x, x1.y); b3 = bf16x2_rn(x1.z, x1.w);
+                        }
+                        if (X3 == 2 && p.half16) {
+                        } else if constexpr (X3 == 2) {              // residual against the bf16 value itself
                             l0 = bf16x2_rn(x0.x - __uint_as_float(b0 << 16), x0.y - __uint_as_float(b0 & 0xffff0000u));
                             l1 = bf16x2_rn(x0.z - __uint_as_float(b1 << 16), x0.w - __uint_as_float(b1 & 0xffff0000u));
                             l2 = bf16x2_rn(x1.x - __uint_as_float(b2 << 16), x1.y - __uint_as_float(b2 & 0xffff0000u));
@@ -1174,7 +1201,7 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
                  double* stats, int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy,
                  int YH, int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
                  const int* taps, long ldw, int act, void* stream, long ldw16 = 0, const float* res = nullptr,
-                 long ldres = 0) {
+                 long ldres = 0, int half16 = 0, float out_scale = 1.f) {
     DFINE_REQUIRE(n_taps >= 1 && n_taps <= MAX_TAPS, "conv_tc: %d taps unsupported", n_taps);
     DFINE_REQUIRE(in_stride == 1 || in_stride == 2, "conv_tc: input stride %d unsupported", in_stride);
     DFINE_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldw % ((w_bf16 && !w) ? 8 : 4) == 0 &&
@@ -1198,6 +1225,7 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
     p.prefetch = pf; p.x = x; p.B = B; p.H = H; p.W = W; p.ldx = ldx;
     DFINE_REQUIRE(!res || (ldres % 4 == 0 && ldres >= Cout && ((uintptr_t)res % 16) == 0), "conv_tc: residual stride %ld", ldres);
     p.res = res; p.ldres = ldres;
+    p.half16 = half16; p.out_scale = out_scale;
     p.in_stride = in_stride; p.Cin = Cin;
     p.OH = OH; p.OW = OW; p.N = Cout; p.ldy = ldy; p.act = act;
     p.YH = YH; p.YW = YW; p.osy = osy; p.osx = osx; p.ooy = ooy; p.oox = oox;
@@ -1215,7 +1243,9 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
         // {32 k, bn rows, 2 planes} with the 64-byte swizzle lands as [plane][row][64 B]
         const bool hybrid = w != nullptr;
         const long ld16 = hybrid ? ldw16 : ldw;
-        const int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
+        // 256-wide tiles (the A patch is then read and converted once for Cout = 256) on the two-plane 16-bit modes
+        static const bool wide16 = [] { const char* e = getenv("DFINE_TC_WIDE16"); return !(e && e[0] == '0'); }();
+        const int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : ((Cout <= 128 || hybrid || !wide16) ? 128 : 256));
         EncodeTiledFn enc = get_encode();
         if (!enc) { dfine_set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return -2; }
         if (hybrid) {
@@ -1233,7 +1263,8 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
         cuuint64_t strides[2] = {(cuuint64_t)ld16 * 2, (cuuint64_t)ld16 * 2 * Cout};
         cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)bn, 2};
         cuuint32_t es[3] = {1, 1, 1};
-        CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_bf16), dims, strides, box, es,
+        CUresult r = enc(&mw, half16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                         const_cast<void*>(w_bf16), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -1247,9 +1278,10 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
                : bn == 64 ? launch_persist<64, 3, 4>(mx, mwlo, mw, y, bias, stats, p, B, st)
                           : launch_persist<128, 3, 3>(mx, mwlo, mw, y, bias, stats, p, B, st);
         } else {
-            rc = bn == 32 ? launch_persist<32, 2, 4>(mx, mw, mw, y, bias, stats, p, B, st)
-               : bn == 64 ? launch_persist<64, 2, 4>(mx, mw, mw, y, bias, stats, p, B, st)
-                          : launch_persist<128, 2, 4>(mx, mw, mw, y, bias, stats, p, B, st);
+            rc = bn == 32  ? launch_persist<32, 2, 4>(mx, mw, mw, y, bias, stats, p, B, st)
+               : bn == 64  ? launch_persist<64, 2, 4>(mx, mw, mw, y, bias, stats, p, B, st)
+               : bn == 128 ? launch_persist<128, 2, 4>(mx, mw, mw, y, bias, stats, p, B, st)
+                           : launch_persist<256, 2, 3>(mx, mw, mw, y, bias, stats, p, B, st);
         }
         if (rc) return rc;
         DFINE_LAUNCH_CHECK("conv_tc(bf16 planes)");
@@ -1335,6 +1367,22 @@ DFINE_API int dfine_conv_tc_bf16x3(const float* x, const void* w_planes, const f
                         osx, ooy, oox, in_stride, n_taps, taps, ldw, act, stream);
 }
 
+// Error-compensated 3xFP16: the 3xBF16 contract with fp16 planes — 11 significand bits per part (the very precision of
+// tf32), so a = a_hi + a_lo carries 22 bits like the 3xTF32 split while the three MMAs run on kind::f16 at twice the
+// tf32 rate and both planes of an operand take the bytes of one fp32 plane.  fp16's narrow exponent is handled by
+// scale: `w_planes` = dfine_f16_split(w * w_scale) with w_scale a power of two that lifts the small weights' lo parts
+// out of the subnormal range; `out_scale` = 1 / w_scale is applied to the accumulator first thing in the epilogue
+// (exact).  Activations are split unscaled inside the kernel (post-normalisation values are O(1); |a| must stay below
+// 65504, lo parts below 2^-14 lose relative — not absolute (2^-25) — precision).
+DFINE_API int dfine_conv_tc_f16x3(const float* x, const void* w_planes, const float* bias, float* y, double* stats,
+                                  int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy, int YH,
+                                  int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
+                                  const int* taps, long ldw, int act, float out_scale, void* stream) {
+    DFINE_REQUIRE(w_planes != nullptr, "conv_tc_f16x3: null weight planes");
+    return conv_tc_impl(x, nullptr, nullptr, w_planes, bias, y, stats, B, H, W, Cin, ldx, OH, OW, Cout, ldy, YH, YW, osy,
+                        osx, ooy, oox, in_stride, n_taps, taps, ldw, act, stream, 0, nullptr, 0, 1, out_scale);
+}
+
 // Hybrid operands (see PersistSmem, X3 = 3): a_hi*w_hi on kind::tf32, the cross terms on bf16 copies.  `w_hi` = the
 // tf32-rounded fp32 weight matrix [Cout][ldw] (dfine_tf32_split's hi plane), `w_planes16` = bf16 planes
 // [2][Cout][ldw16] = [bf16(w) | bf16(w - tf32(w))] written by dfine_bf16_split(mode 1), every tap's channel run
@@ -1369,6 +1417,40 @@ __global__ void bf16_split_kernel(const float* __restrict__ w, long ldw, unsigne
     }
 }
 }  // namespace
+namespace {
+__global__ void f16_split_kernel(const float* __restrict__ w, long ldw, unsigned short* __restrict__ planes, long rows,
+                                 int taps, int Cin, int Cin_p, float scale) {
+    const long ldp = (long)taps * Cin_p, n = rows * ldp;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / ldp;
+        const int k = (int)(i % ldp), tap = k / Cin_p, c = k % Cin_p;
+        unsigned short hi = 0, lo = 0;
+        if (c < Cin) {
+            const float v = w[r * ldw + (long)tap * Cin + c] * scale;
+            const __half h = __float2half_rn(v);
+            hi = __half_as_ushort(h);
+            lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+        }
+        planes[i] = hi;
+        planes[n + i] = lo;
+    }
+}
+}  // namespace
+// The weight half of the 3xFP16 split: planes [2][rows][taps * Cin_p] fp16 of w * scale (scale a power of two),
+// planes[0] = RN f16(w * scale), planes[1] = RN f16(w * scale - planes[0]); tap runs padded to Cin_p like dfine_bf16_split.
+DFINE_API int dfine_f16_split(const float* w, long ldw, void* planes, long rows, int taps, int Cin, int Cin_p,
+                              float scale, void* stream) {
+    DFINE_REQUIRE(Cin_p >= Cin && Cin_p % 8 == 0 && taps >= 1 && ((uintptr_t)planes % 16) == 0 && scale > 0.f,
+                  "f16_split: Cin=%d Cin_p=%d taps=%d scale=%g", Cin, Cin_p, taps, (double)scale);
+    const long n = rows * taps * Cin_p;
+    if (n == 0) return 0;
+    long g = (n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    f16_split_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w, ldw, (unsigned short*)planes, rows, taps, Cin, Cin_p, scale);
+    DFINE_LAUNCH_CHECK("f16_split");
+    return 0;
+}
+
 // mode 0: planes[1] = RN bf16(w - planes[0]) (3xBF16); mode 1: planes[1] = RN bf16(w - RN tf32(w)) (hybrid).
 DFINE_API int dfine_bf16_split(const float* w, long ldw, void* planes, long rows, int taps, int Cin, int Cin_p,
                                int mode, void* stream) {

@@ -256,6 +256,8 @@ def _rows(x):
 #          copies through kind::f16 (3xTF32-class accuracy for 2/3 of its tensor time), gradients as in "tc3";
 #   "bf3"  forward GEMMs as error-compensated 3xBF16 (two bf16 parts per operand = 16 mantissa bits, three
 #          kind::f16 MMAs at twice the tf32 rate; ~1e-5 relative), gradients as in "tc3";
+#   "hf3"  forward GEMMs as error-compensated 3xFP16 (two fp16 parts per operand = 22 significand bits like 3xTF32, three
+#          kind::f16 MMAs at twice the tf32 rate, weights pre-scaled by 2^8), gradients as in "tc3";
 #   "tc"   plain kind::tf32 everywhere (the precision class of the reference's cuDNN convolutions on GPU);
 #   "simt" fp32 CUDA-core kernels of the same library (strict-fp32 parity runs and kernel bring-up).
 _MODE = os.environ.get("DFINE_GEMM", "tc3")
@@ -267,7 +269,7 @@ _TAP = os.environ.get("DFINE_TAP", "0") == "1"
 
 def set_gemm_mode(mode: str) -> None:
     global _MODE
-    if mode not in ("tc", "tc3", "tch", "bf3", "simt"):
+    if mode not in ("tc", "tc3", "tch", "bf3", "hf3", "simt"):
         raise ValueError(mode)
     _MODE = mode
 
@@ -306,6 +308,11 @@ def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, Y
                                               c_long(ldx), OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0],
                                               oo[1], in_stride, n, arr, c_long(ldw), c_long(bf16_planes.shape[-1]),
                                               act, _stream()), what)
+        elif bf16_planes is not None and bf16_planes.dtype == torch.float16:
+            _check(lib().dfine_conv_tc_f16x3(_p(x), _p(bf16_planes), _p(bias), _p(y), _p(stats), B, H, W, Cin,
+                                             c_long(ldx), OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0],
+                                             oo[1], in_stride, n, arr, c_long(bf16_planes.shape[-1]), act,
+                                             c_float(1.0 / _F16_WSCALE), _stream()), what)
         elif bf16_planes is not None:
             _check(lib().dfine_conv_tc_bf16x3(_p(x), _p(bf16_planes), _p(bias), _p(y), _p(stats), B, H, W, Cin,
                                               c_long(ldx), OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0],
@@ -323,6 +330,19 @@ def _split_tf32(w2d):
     hi, lo = planes[0], planes[1]
     _check(lib().dfine_tf32_split(_p(w2d), _p(hi), _p(lo), c_long(w2d.numel()), _stream()), "tf32_split")
     return hi, lo
+
+
+_F16_WSCALE = 256.0      # power of two applied to the weights of the 3xFP16 mode (see dfine_conv_tc_f16x3)
+
+
+def _split_f16(w2d, taps, Cin):
+    """fp16 (hi, lo) planes [2, rows, taps * Cin_p] of w * 2^8 for the 3xFP16 forward (tap runs padded to 8 channels)."""
+    rows = w2d.shape[0]
+    cin_p = (Cin + 7) // 8 * 8
+    planes = torch.empty((2, rows, taps * cin_p), device=w2d.device, dtype=torch.float16)
+    _check(lib().dfine_f16_split(_p(w2d), c_long(w2d.shape[1]), _p(planes), c_long(rows), taps, Cin, cin_p,
+                                 c_float(_F16_WSCALE), _stream()), "f16_split")
+    return planes
 
 
 def _split_bf16(w2d, taps, Cin, mode=0):
@@ -353,10 +373,13 @@ def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None):
         elif _MODE == "bf3":
             planes = wkey("wrb", lambda: _split_bf16(wr, k * k, Cin))
             w_hi = None
+        elif _MODE == "hf3":
+            planes = wkey("wrf", lambda: _split_f16(wr, k * k, Cin))
+            w_hi = None
         elif _MODE == "tch":
             w_hi, _ = wkey("wr3", lambda: _split_tf32(wr))
             planes = wkey("wrh", lambda: _split_bf16(wr, k * k, Cin, mode=1))
-        cs = (Cin + 7) // 8 * 8 if _MODE == "bf3" else Cin        # channel run of one tap in the weight matrix
+        cs = (Cin + 7) // 8 * 8 if _MODE in ("bf3", "hf3") else Cin        # channel run of one tap in the weight matrix
         taps = _taps(("f", k, pad[0], pad[1], cs),
                      lambda: [(kh - pad[0], kw - pad[1], (kh * k + kw) * cs) for kh in range(k) for kw in range(k)])
         _tc_launch(x, ldx, H, W, Cin, w_hi, w_lo, K, bias, y, ldy, B, OH, OW, Cout, OH, OW, (1, 1), (0, 0), stride,
@@ -1107,7 +1130,8 @@ class CudaOps:
         frozen = num_batches_tracked is None
         if training and num_batches_tracked is not None:
             num_batches_tracked.add_(1)
-        if groups == 1 and (x.shape[-1] % 4 or w.shape[0] % 4):
+        # (the 3-channel image convolution has its own direct kernels, csrc/stem.cu)
+        if groups == 1 and ((x.shape[-1] % 4 and x.shape[-1] != 3) or w.shape[0] % 4):
             return self._conv_bn_act_padded(x, w, stride, pad, bn_w, bn_b, running_mean, running_var, training,
                                             momentum, eps, act, lab_scale, lab_bias, pre_add, post_add, frozen, tap)
         # tap: also return the input as a second output (see _ConvBnAct.forward); plain pass-through without autograd

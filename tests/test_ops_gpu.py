@@ -252,7 +252,7 @@ def test_tc_matches_simt(cuda_ops, case):
     res = {}
     prev = co.get_gemm_mode()
     try:
-        for mode in ("simt", "tc", "tc3", "tch", "bf3"):
+        for mode in ("simt", "tc", "tc3", "tch", "bf3", "hf3"):
             co.set_gemm_mode(mode)
             cache = co._WCache()
             y = torch.zeros(B, OH, OW, Cout).cuda()
@@ -272,7 +272,7 @@ def test_tc_matches_simt(cuda_ops, case):
     finally:
         co.set_gemm_mode(prev)
     y0, _, dx0, dw0 = res["simt"]
-    for mode, tol in (("tc", TF32), ("tc3", 2e-5), ("tch", 2e-5), ("bf3", 5e-5)):   # bf3: 16 mantissa bits per operand
+    for mode, tol in (("tc", TF32), ("tc3", 2e-5), ("tch", 2e-5), ("bf3", 5e-5), ("hf3", 2e-5)):   # bf3: 16 mantissa bits per operand
         y, stats, dx, dw = res[mode]
         check_close(f"{mode} fwd {case}", y, y0, tol)
         check_close(f"{mode} fused stats sum", stats[:Cout].float(), y0.reshape(M, Cout).sum(0), max(tol, 1e-4) * 5)

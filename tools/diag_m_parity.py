@@ -42,7 +42,7 @@ def run(dev, mode=None):
 
 o0, l0 = run("cpu")
 co.CudaOps()
-for mode in ("simt", "tc3", "tch", "bf3", "tc"):
+for mode in ("simt", "tc3", "hf3", "tch", "bf3", "tc"):
     o1, l1 = run("cuda", mode)
     line = [mode]
     for key in ("pred_logits", "pred_boxes"):

@@ -49,6 +49,7 @@ for (M, K, N) in [(512, 4, 512), (512, 32, 128), (1024, 256, 128), (2048, 1152, 
           f"tc3 x-low-bits only {err(run('tc3', x, wr), x, wr):.2e} | "
           f"tc3 w-low-bits only {err(run('tc3', xr, w), xr, w):.2e} | "
           f"tc3 general {err(run('tc3', x, w), x, w):.2e} | "
-          f"bf3 general {err(run('bf3', x, w), x, w):.2e} | tch general {err(run('tch', x, w), x, w):.2e} | "
+          f"bf3 general {err(run('bf3', x, w), x, w):.2e} | hf3 general {err(run('hf3', x, w), x, w):.2e} | "
+          f"hf3 small-x (x*1e-3) {err(run('hf3', x * 1e-3, w), x * 1e-3, w):.2e} | tc3 small-x {err(run('tc3', x * 1e-3, w), x * 1e-3, w):.2e} | tch general {err(run('tch', x, w), x, w):.2e} | "
           f"simt {err(run('simt', x, w), x, w):.2e} | tc3 out absmax {float(run('tc3', x, w).abs().max()):.3e} "
           f"ref absmax {float((x.double() @ w.double().t()).abs().max()):.3e}")
