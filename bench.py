@@ -44,6 +44,13 @@ WORKLOADS = {
     "x1280": ("x", 1280, 4, False, 1),      # configs[4]: per-GPU share of the 8-GPU run
 }   # last entry: images per step of the bounded CPU-arm sample
 MODEL, HW, SEG = "m", 640, False
+DTYPES = {
+    "hf3": "fp32 storage + fp32 accumulate; forward GEMMs on 3xFP16 split operands (22 significand bits, kind::f16 tensor cores), "
+           "gradient GEMMs on tf32 operands",
+    "tc3": "fp32 storage + fp32 accumulate; forward GEMMs on 3xTF32 split operands, gradient GEMMs on tf32 operands",
+    "tc": "fp32 storage + fp32 accumulate; tf32 tensor-core operands",
+    "simt": "fp32 (CUDA cores)",
+}
 CPU_SAMPLE_BATCH = 4
 
 
@@ -321,7 +328,7 @@ def run_ours(args):
         "metric": metric_name(), "value": round(imgs / (ms_total * 1e-3), 2),
         "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
         "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "tf32 tensor-core operands / fp32 storage+accumulate", "data": "synthetic",
+        "vs_baseline": None, "dtype": DTYPES.get(cuda_ops.get_gemm_mode(), cuda_ops.get_gemm_mode()), "data": "synthetic",
         "config": {"workload": workload_text(B), "name": args.config, "weights": "seeded default init with randomised zero-"
                    "initialised heads (the COCO checkpoint of SURVEY 8d is used by the parity tests; perf-neutral)",
                    "global_batch": B * world, "parallelism": f"dp{world}", "launch_mode": mode, "gemm_mode": cuda_ops.get_gemm_mode(),

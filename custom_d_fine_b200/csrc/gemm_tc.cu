@@ -1201,7 +1201,7 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
                  double* stats, int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy,
                  int YH, int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
                  const int* taps, long ldw, int act, void* stream, long ldw16 = 0, const float* res = nullptr,
-                 long ldres = 0, int half16 = 0, float out_scale = 1.f) {
+                 long ldres = 0, int half16 = 0, float out_scale = 1.f, long plane_stride16 = 0) {
     DFINE_REQUIRE(n_taps >= 1 && n_taps <= MAX_TAPS, "conv_tc: %d taps unsupported", n_taps);
     DFINE_REQUIRE(in_stride == 1 || in_stride == 2, "conv_tc: input stride %d unsupported", in_stride);
     DFINE_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldw % ((w_bf16 && !w) ? 8 : 4) == 0 &&
@@ -1260,7 +1260,10 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
             if (rc) return rc;
         }
         cuuint64_t dims[3] = {(cuuint64_t)ld16, (cuuint64_t)Cout, 2};
-        cuuint64_t strides[2] = {(cuuint64_t)ld16 * 2, (cuuint64_t)ld16 * 2 * Cout};
+        // (the two planes of a weight are adjacent, or sit in two arenas `plane_stride16` elements apart)
+        const cuuint64_t pstride = plane_stride16 > 0 ? (cuuint64_t)plane_stride16 * 2 : (cuuint64_t)ld16 * 2 * Cout;
+        DFINE_REQUIRE(pstride % 16 == 0, "conv_tc: 16-bit plane stride %ld must be a multiple of 8 elements", plane_stride16);
+        cuuint64_t strides[2] = {(cuuint64_t)ld16 * 2, pstride};
         cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)bn, 2};
         cuuint32_t es[3] = {1, 1, 1};
         CUresult r = enc(&mw, half16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
@@ -1372,15 +1375,16 @@ DFINE_API int dfine_conv_tc_bf16x3(const float* x, const void* w_planes, const f
 // tf32 rate and both planes of an operand take the bytes of one fp32 plane.  fp16's narrow exponent is handled by
 // scale: `w_planes` = dfine_f16_split(w * w_scale) with w_scale a power of two that lifts the small weights' lo parts
 // out of the subnormal range; `out_scale` = 1 / w_scale is applied to the accumulator first thing in the epilogue
-// (exact).  Activations are split unscaled inside the kernel (post-normalisation values are O(1); |a| must stay below
+// (exact).  `plane_stride` = elements between the hi and the lo plane (0: adjacent, [2][Cout][ldw]).  Activations are split unscaled inside the kernel (post-normalisation values are O(1); |a| must stay below
 // 65504, lo parts below 2^-14 lose relative — not absolute (2^-25) — precision).
 DFINE_API int dfine_conv_tc_f16x3(const float* x, const void* w_planes, const float* bias, float* y, double* stats,
                                   int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy, int YH,
                                   int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
-                                  const int* taps, long ldw, int act, float out_scale, void* stream) {
+                                  const int* taps, long ldw, int act, float out_scale, long plane_stride,
+                                  void* stream) {
     DFINE_REQUIRE(w_planes != nullptr, "conv_tc_f16x3: null weight planes");
     return conv_tc_impl(x, nullptr, nullptr, w_planes, bias, y, stats, B, H, W, Cin, ldx, OH, OW, Cout, ldy, YH, YW, osy,
-                        osx, ooy, oox, in_stride, n_taps, taps, ldw, act, stream, 0, nullptr, 0, 1, out_scale);
+                        osx, ooy, oox, in_stride, n_taps, taps, ldw, act, stream, 0, nullptr, 0, 1, out_scale, plane_stride);
 }
 
 // Hybrid operands (see PersistSmem, X3 = 3): a_hi*w_hi on kind::tf32, the cross terms on bf16 copies.  `w_hi` = the

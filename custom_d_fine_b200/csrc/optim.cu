@@ -10,6 +10,7 @@
 // Every scalar that changes between steps (learning rate, weight decay, step count, EMA momentum, the
 // squared gradient norm) is read from device memory, so the launches can be replayed from a CUDA graph.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -38,6 +39,30 @@ __device__ __forceinline__ float tf32_rn(float x) {
     return __uint_as_float(u);
 }
 
+// four weights x scale -> fp16 hi (RN) and lo (RN of the remainder), packed 4 halves per uint2
+__device__ __forceinline__ void split_f16x4(const float4& w, float scale, uint2& hi, uint2& lo) {
+    const float v[4] = {w.x * scale, w.y * scale, w.z * scale, w.w * scale};
+    unsigned short h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __half hh = __float2half_rn(v[j]);
+        h[j] = __half_as_ushort(hh);
+        l[j] = __half_as_ushort(__float2half_rn(v[j] - __half2float(hh)));
+    }
+    hi = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+    lo = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+}
+
+__global__ void __launch_bounds__(NT) f16_split_flat_kernel(const float4* __restrict__ w, uint2* __restrict__ hi,
+                                                            uint2* __restrict__ lo, long n4, float scale) {
+    for (long i = (long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long)gridDim.x * NT) {
+        uint2 h, l;
+        split_f16x4(__ldg(w + i), scale, h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
 // hyper (device, 4 floats): lr, weight_decay, step (1-based, already incremented), ema momentum
 __global__ void __launch_bounds__(NT) adamw_ema_kernel(float4* __restrict__ p, float4* __restrict__ g,
                                                        float4* __restrict__ m, float4* __restrict__ v,
@@ -45,7 +70,8 @@ __global__ void __launch_bounds__(NT) adamw_ema_kernel(float4* __restrict__ p, f
                                                        const float* __restrict__ hyper,
                                                        const double* __restrict__ gnorm_sq, float max_norm,
                                                        float beta1, float beta2, float eps, int zero_grad,
-                                                       float4* __restrict__ hi, float4* __restrict__ lo) {
+                                                       float4* __restrict__ hi, float4* __restrict__ lo, int plane_mode,
+                                                       float plane_scale) {
     const float lr = __ldg(hyper + 0), wd = __ldg(hyper + 1), step = __ldg(hyper + 2), em = __ldg(hyper + 3);
     // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
     float coef = 1.f;
@@ -75,7 +101,12 @@ __global__ void __launch_bounds__(NT) adamw_ema_kernel(float4* __restrict__ p, f
         }
         p[i] = pv; m[i] = mv; v[i] = vv;
         if (zero_grad) g[i] = zero;
-        if (hi != nullptr) {     // 3xTF32 operand planes of the new weights (hi = RN tf32, lo = exact remainder)
+        if (hi != nullptr && plane_mode == 1) {     // 3xFP16 operand planes of the new weights x plane_scale (fp16 arenas)
+            uint2 h16, l16;
+            split_f16x4(pv, plane_scale, h16, l16);
+            reinterpret_cast<uint2*>(hi)[i] = h16;
+            reinterpret_cast<uint2*>(lo)[i] = l16;
+        } else if (hi != nullptr) {     // 3xTF32 operand planes of the new weights (hi = RN tf32, lo = exact remainder)
             float4 h;
             h.x = tf32_rn(pv.x); h.y = tf32_rn(pv.y); h.z = tf32_rn(pv.z); h.w = tf32_rn(pv.w);
             hi[i] = h;
@@ -124,11 +155,13 @@ DFINE_API int dfine_sumsq(const float* g, long n, double* out, void* stream) {
 //   hyper     device float[4] = {lr, weight_decay, step, ema_momentum}
 //   gnorm_sq  device double, squared global gradient norm (null: no clipping)
 //   ema       null: no EMA blend
-//   hi, lo    null, or arenas receiving the 3xTF32 split of the updated parameters (same element order): the
-//             forward GEMMs of the next step read their weight planes from there, no per-layer split launches
+//   hi, lo    null, or arenas receiving the operand split of the updated parameters (same element order): the forward
+//             GEMMs of the next step read their weight planes from there, no per-layer split launches.
+//             plane_mode 0: fp32 arenas, 3xTF32 split (hi = RN tf32, lo = remainder); plane_mode 1: fp16 arenas
+//             (n halves each), 3xFP16 split of w * plane_scale
 DFINE_API int dfine_adamw_ema(float* p, float* g, float* m, float* v, float* ema, long n, const float* hyper,
                               const double* gnorm_sq, float max_norm, float beta1, float beta2, float eps,
-                              int zero_grad, float* hi, float* lo, void* stream) {
+                              int zero_grad, void* hi, void* lo, int plane_mode, float plane_scale, void* stream) {
     DFINE_REQUIRE(n % 4 == 0, "adamw_ema: arena length must be a multiple of 4");
     DFINE_REQUIRE(((uintptr_t)p % 16) == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)m % 16) == 0 &&
                       ((uintptr_t)v % 16) == 0 && ((uintptr_t)ema % 16) == 0 && ((uintptr_t)hi % 16) == 0 &&
@@ -138,8 +171,19 @@ DFINE_API int dfine_adamw_ema(float* p, float* g, float* m, float* v, float* ema
     adamw_ema_kernel<<<grid_for(n / 4), NT, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g), reinterpret_cast<float4*>(m),
         reinterpret_cast<float4*>(v), reinterpret_cast<float4*>(ema), n / 4, hyper, gnorm_sq, max_norm, beta1, beta2,
-        eps, zero_grad, reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo));
+        eps, zero_grad, reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo), plane_mode, plane_scale);
     DFINE_LAUNCH_CHECK("adamw_ema");
+    return 0;
+}
+
+// hi16 / lo16 (n halves each) = the 3xFP16 split of w * scale over a flat arena (n % 4 == 0).
+DFINE_API int dfine_f16_split_flat(const float* w, void* hi16, void* lo16, long n, float scale, void* stream) {
+    DFINE_REQUIRE(n % 4 == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)hi16 % 8) == 0 && ((uintptr_t)lo16 % 8) == 0 && scale > 0.f,
+                  "f16_split_flat: alignment / n %% 4");
+    if (n == 0) return 0;
+    f16_split_flat_kernel<<<grid_for(n / 4), NT, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(w), reinterpret_cast<uint2*>(hi16), reinterpret_cast<uint2*>(lo16), n / 4, scale);
+    DFINE_LAUNCH_CHECK("f16_split_flat");
     return 0;
 }
 

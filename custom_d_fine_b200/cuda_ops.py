@@ -202,6 +202,24 @@ class _WgradStream:
 wgrad_stream = _WgradStream()
 
 
+# BatchNorm `num_batches_tracked` buffers re-homed into one int64 arena by train.TrainStep: one add per step instead of
+# one tiny launch per BatchNorm layer (133 for D-FINE-m).  data_ptr -> True.
+_step_counters = {}
+
+
+def register_step_counters(model):
+    """Re-home every BatchNorm step counter of `model` (CUDA) into one int64 arena; returns the arena (or None)."""
+    mods = [m for m in model.modules() if isinstance(m, torch.nn.BatchNorm2d) and m.num_batches_tracked is not None
+            and m.num_batches_tracked.is_cuda]
+    if not mods:
+        return None
+    arena = torch.stack([m.num_batches_tracked.detach().reshape(()) for m in mods]).contiguous()
+    for i, m in enumerate(mods):
+        m.num_batches_tracked.data = arena[i]
+        _step_counters[arena[i].data_ptr()] = True
+    return arena
+
+
 def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -250,8 +268,9 @@ def _rows(x):
 
 
 # Dense conv / linear shapes the tcgen05 kernels accept run on tensor cores.  Modes (env DFINE_GEMM / set_gemm_mode):
-#   "tc3"  (default) forward GEMMs as error-compensated 3xTF32 (fp32-class accuracy: the parity mode of the
-#          tensor-core path), data / weight gradients as plain kind::tf32;
+#   "hf3"  (default) forward GEMMs as error-compensated 3xFP16 — see the entry below; the parity mode of the tensor-core
+#          path since round 2 (measured closer to the fp32 oracle than "tc3" on the headline network, 6.5 % faster);
+#   "tc3"  forward GEMMs as error-compensated 3xTF32 (fp32-class accuracy), data / weight gradients as plain kind::tf32;
 #   "tch"  forward GEMMs as a hybrid split: a_hi*w_hi on kind::tf32, the cross terms a_lo*w_hi + a_hi*w_lo on bf16
 #          copies through kind::f16 (3xTF32-class accuracy for 2/3 of its tensor time), gradients as in "tc3";
 #   "bf3"  forward GEMMs as error-compensated 3xBF16 (two bf16 parts per operand = 16 mantissa bits, three
@@ -260,7 +279,7 @@ def _rows(x):
 #          kind::f16 MMAs at twice the tf32 rate, weights pre-scaled by 2^8), gradients as in "tc3";
 #   "tc"   plain kind::tf32 everywhere (the precision class of the reference's cuDNN convolutions on GPU);
 #   "simt" fp32 CUDA-core kernels of the same library (strict-fp32 parity runs and kernel bring-up).
-_MODE = os.environ.get("DFINE_GEMM", "tc3")
+_MODE = os.environ.get("DFINE_GEMM", "hf3")
 # Gradient-routing aliases (`tap`): fold the gradient-accumulation add of a tensor with two consumers into the data-
 # gradient kernel's epilogue.  Measured on B200 (profiles/README.md): the extra epilogue read makes the persistent dgrad
 # kernels epilogue-bound and the step 0.8 ms SLOWER than the separate add kernels -> off by default, kept for A/B.
@@ -298,7 +317,7 @@ def _taps(key, make):
 
 
 def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, YH, YW, os_, oo, in_stride, taps, act,
-               stats, what, bf16_planes=None, res=None, ldres=0):
+               stats, what, bf16_planes=None, res=None, ldres=0, plane_stride=0):
     arr, n = taps
     # algorithmic bytes: input pixels + output pixels + weights, each touched once, fp32
     nbytes = 4 * (B * min(H * W, OH * OW * in_stride * in_stride) * Cin + B * OH * OW * Cout + Cout * n * Cin)
@@ -312,7 +331,7 @@ def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, Y
             _check(lib().dfine_conv_tc_f16x3(_p(x), _p(bf16_planes), _p(bias), _p(y), _p(stats), B, H, W, Cin,
                                              c_long(ldx), OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0],
                                              oo[1], in_stride, n, arr, c_long(bf16_planes.shape[-1]), act,
-                                             c_float(1.0 / _F16_WSCALE), _stream()), what)
+                                             c_float(1.0 / _F16_WSCALE), c_long(plane_stride), _stream()), what)
         elif bf16_planes is not None:
             _check(lib().dfine_conv_tc_bf16x3(_p(x), _p(bf16_planes), _p(bias), _p(y), _p(stats), B, H, W, Cin,
                                               c_long(ldx), OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0],
@@ -366,7 +385,7 @@ def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None):
     if _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy):
         K = k * k * Cin
         wr = wkey("wr", lambda: weight.reshape(Cout, Cin, k, k).permute(0, 2, 3, 1).reshape(Cout, K).contiguous())
-        w_hi, w_lo, planes = wr, None, None
+        w_hi, w_lo, planes, plane_stride = wr, None, None, 0
         if _MODE == "tc3":
             pl = _planes_of(weight)
             w_hi, w_lo = pl if pl is not None else wkey("wr3", lambda: _split_tf32(wr))
@@ -374,7 +393,11 @@ def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None):
             planes = wkey("wrb", lambda: _split_bf16(wr, k * k, Cin))
             w_hi = None
         elif _MODE == "hf3":
-            planes = wkey("wrf", lambda: _split_f16(wr, k * k, Cin))
+            pl = _planes_of(weight) if Cin % 8 == 0 else None
+            if pl is not None:       # fp16 planes kept current by the AdamW kernel (two arenas a fixed distance apart)
+                planes, plane_stride = pl[0], (pl[1].data_ptr() - pl[0].data_ptr()) // 2
+            else:
+                planes = wkey("wrf", lambda: _split_f16(wr, k * k, Cin))
             w_hi = None
         elif _MODE == "tch":
             w_hi, _ = wkey("wr3", lambda: _split_tf32(wr))
@@ -383,7 +406,7 @@ def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None):
         taps = _taps(("f", k, pad[0], pad[1], cs),
                      lambda: [(kh - pad[0], kw - pad[1], (kh * k + kw) * cs) for kh in range(k) for kw in range(k)])
         _tc_launch(x, ldx, H, W, Cin, w_hi, w_lo, K, bias, y, ldy, B, OH, OW, Cout, OH, OW, (1, 1), (0, 0), stride,
-                   taps, act, stats, "conv_fwd_tc", planes)
+                   taps, act, stats, "conv_fwd_tc", planes, plane_stride=plane_stride)
         return True
     wr = wkey("wr", lambda: weight.reshape(Cout, Cin, k, k).permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous())
     if bias is None and act == 0 and _MODE != "simt" and \
@@ -541,6 +564,8 @@ def _planes_of(weight):
     if ent is None or ent[0]() is not weight:
         return None
     _, ver, hi, lo = ent
+    if hi.dtype != (torch.float16 if _MODE == "hf3" else torch.float32):
+        return None                  # planes of another operand mode (the mode was switched after the optimizer was built)
     if ver != weight._version:       # rewritten outside the optimizer kernel: refresh this weight's planes
         src = weight.detach()
         src = src.permute(0, 2, 3, 1) if src.dim() == 4 else src
@@ -548,7 +573,13 @@ def _planes_of(weight):
             flat = src.reshape(hi.shape)
             if flat.data_ptr() != weight.data_ptr():      # not the channels-last arena view any more
                 return None
-            _check(lib().dfine_tf32_split(_p(flat), _p(hi), _p(lo), c_long(hi.numel()), _stream()), "tf32_split")
+            if hi.dtype == torch.float16:
+                if hi.numel() % 4:
+                    return None
+                _check(lib().dfine_f16_split_flat(_p(flat), _p(hi), _p(lo), c_long(hi.numel()), c_float(_F16_WSCALE),
+                                                  _stream()), "f16_split_flat")
+            else:
+                _check(lib().dfine_tf32_split(_p(flat), _p(hi), _p(lo), c_long(hi.numel()), _stream()), "tf32_split")
         _arena_planes[id(weight)] = (ent[0], weight._version, hi, lo)
     return hi, lo
 
@@ -1058,6 +1089,33 @@ class _Criterion(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+# decoder gate: sigmoid(g[:, :D]) * x1 + sigmoid(g[:, D:]) * x2
+# ------------------------------------------------------------------------------------------------
+class _GateMix(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, x1, x2):
+        _req_cuda(g, x1, x2)
+        g, x1, x2 = g.contiguous(), x1.contiguous(), x2.contiguous()
+        D = x1.shape[-1]
+        rows = x1.numel() // D
+        out = torch.empty_like(x1)
+        _check(lib().dfine_gate_mix_fwd(_p(g), _p(x1), _p(x2), _p(out), c_long(rows), D, _stream()), "gate_mix_fwd")
+        ctx.save_for_backward(g, x1, x2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        g, x1, x2 = ctx.saved_tensors
+        D = x1.shape[-1]
+        rows = x1.numel() // D
+        dout = dout.contiguous()
+        dg, dx1, dx2 = torch.empty_like(g), torch.empty_like(x1), torch.empty_like(x2)
+        _check(lib().dfine_gate_mix_bwd(_p(dout), _p(g), _p(x1), _p(x2), _p(dg), _p(dx1), _p(dx2), c_long(rows), D,
+                                        _stream()), "gate_mix_bwd")
+        return dg, dx1, dx2
+
+
+# ------------------------------------------------------------------------------------------------
 # small spatial ops
 # ------------------------------------------------------------------------------------------------
 def _nhwc_ld(x):
@@ -1128,8 +1186,9 @@ class CudaOps:
                     training, momentum=0.1, eps=1e-5, act=None, lab_scale=None, lab_bias=None, pre_add=None,
                     post_add=None, tap=False):
         frozen = num_batches_tracked is None
-        if training and num_batches_tracked is not None:
-            num_batches_tracked.add_(1)
+        if training and num_batches_tracked is not None and not (
+                wgrad_stream.in_step and num_batches_tracked.data_ptr() in _step_counters):
+            num_batches_tracked.add_(1)      # (inside a train step the step bumps all registered counters at once)
         # (the 3-channel image convolution has its own direct kernels, csrc/stem.cu)
         if groups == 1 and ((x.shape[-1] % 4 and x.shape[-1] != 3) or w.shape[0] % 4):
             return self._conv_bn_act_padded(x, w, stride, pad, bn_w, bn_b, running_mean, running_var, training,
@@ -1191,10 +1250,20 @@ class CudaOps:
     def msda(self, memory, spatial_shapes, points, heads, proj, n_off, ref, pscale, offset_scale=0.5):
         return _Msda.apply(memory, proj, ref, pscale, spatial_shapes, points, heads, n_off, offset_scale)
 
-    # ---- decoder head glue (elementwise; composed from device tensor ops for now) ----
+    # ---- decoder glue ----
     def gate_mix(self, g, x1, x2):
-        g1, g2 = torch.sigmoid(g).chunk(2, dim=-1)
-        return g1 * x1 + g2 * x2
+        return _GateMix.apply(g, x1, x2)
+
+    @torch.no_grad()
+    def select_topk(self, logits, k):
+        """Indices int64 [B,k] of the k tokens with the largest row maximum of logits [B,L,C], descending."""
+        _req_cuda(logits)
+        logits = logits.contiguous().float()
+        B, L, C = logits.shape
+        scores = torch.empty((B, L), device=logits.device, dtype=torch.float32)
+        idx = torch.empty((B, k), device=logits.device, dtype=torch.int64)
+        _check(lib().dfine_topk_rowmax(_p(logits), _p(scores), _p(idx), B, L, C, int(k), _stream()), "topk_rowmax")
+        return idx
 
     def fdr_decode(self, corners, ref, project, reg_scale):
         return _FdrHead.apply(corners, ref, project, _as_dev_scalar(reg_scale, corners.device), 0, True, False)[0]

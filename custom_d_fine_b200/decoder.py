@@ -390,7 +390,7 @@ class DFINETransformer(nn.Module):
         om = K.linear(mem, self.enc_output.proj.weight, self.enc_output.proj.bias)
         om = K.layernorm(om, self.enc_output.norm.weight, self.enc_output.norm.bias, self.enc_output.norm.eps)
         enc_logits = K.linear(om, self.enc_score_head.weight, self.enc_score_head.bias)
-        _, top = torch.topk(enc_logits.max(-1).values, self.num_queries, dim=-1)
+        top = K.select_topk(enc_logits.detach(), self.num_queries)
         bidx = torch.arange(memory.shape[0], device=memory.device)[:, None]
         top_anchor = anchors[0][top] if anchors.shape[0] == 1 else anchors[bidx, top]
         # torch.gather, not om[bidx, top]: same values, but the backward is a scatter_add (the indices of one image

@@ -29,7 +29,8 @@ from . import dist as dist_utils
 
 
 def _pad4(n):
-    return (n + 3) // 4 * 4
+    # 8 elements: float4 access for the fp32 arenas AND 16-byte TMA alignment of the matching fp16 operand planes
+    return (n + 7) // 8 * 8
 
 
 def _arena_view(arena, off, t):
@@ -90,8 +91,12 @@ class FusedAdamW(torch.optim.Optimizer):
             a = dict(params=ps, offs=offs, p=pflat, g=gflat, m=torch.zeros_like(pflat), v=torch.zeros_like(pflat),
                      ema=None, planes=None)
             if any(p.dim() >= 2 for p in ps):
-                # 3xTF32 weight planes (hi | lo) in the arena's element order, rewritten by the AdamW kernel itself
-                a["planes"] = torch.empty((2, pflat.numel()), dtype=torch.float32, device=pflat.device)
+                # operand planes (hi | lo) of the forward GEMMs in the arena's element order, rewritten by the AdamW
+                # kernel itself: fp16 planes of w * 2^8 for the 3xFP16 mode, fp32 tf32-split planes for 3xTF32
+                from . import cuda_ops
+                half = cuda_ops.get_gemm_mode() == "hf3"
+                a["planes"] = torch.empty((2, pflat.numel()), dtype=torch.float16 if half else torch.float32,
+                                          device=pflat.device)
             self._arenas.append(a)
         self._dev = dev
         n = len(self.param_groups)
@@ -109,13 +114,24 @@ class FusedAdamW(torch.optim.Optimizer):
             if a is None or a["planes"] is None:
                 continue
             hi, lo = a["planes"][0], a["planes"][1]
-            cuda_ops._check(cuda_ops.lib().dfine_tf32_split(cuda_ops._p(a["p"]), cuda_ops._p(hi), cuda_ops._p(lo),
-                                                            ctypes.c_long(a["p"].numel()), cuda_ops._stream()),
-                            "tf32_split")
+            half = hi.dtype == torch.float16
+            if half:
+                cuda_ops._check(cuda_ops.lib().dfine_f16_split_flat(cuda_ops._p(a["p"]), cuda_ops._p(hi), cuda_ops._p(lo),
+                                                                    ctypes.c_long(a["p"].numel()),
+                                                                    ctypes.c_float(cuda_ops._F16_WSCALE), cuda_ops._stream()),
+                                "f16_split_flat")
+            else:
+                cuda_ops._check(cuda_ops.lib().dfine_tf32_split(cuda_ops._p(a["p"]), cuda_ops._p(hi), cuda_ops._p(lo),
+                                                                ctypes.c_long(a["p"].numel()), cuda_ops._stream()),
+                                "tf32_split")
             for p, o in zip(a["params"], a["offs"]):
                 if p.dim() >= 2:
                     n = p.numel()
                     rows = p.shape[0]
+                    # (fp16 planes are read by TMA with every tap's channel run starting on a 16-byte boundary: the
+                    #  arena order qualifies when the channel count is a multiple of 8; other layers split per use)
+                    if half and (p.shape[1] % 8 != 0 or o % 8 != 0):
+                        continue
                     cuda_ops.register_weight_planes(p, hi[o:o + n].view(rows, n // rows), lo[o:o + n].view(rows, n // rows))
 
     # ---- wiring -------------------------------------------------------------------------------
@@ -234,6 +250,7 @@ class FusedAdamW(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         """Device half (graph-capturable): grad-norm, then clip + AdamW + EMA + zero_grad per group."""
+        from .cuda_ops import _F16_WSCALE as _wscale
         from .cuda_ops import _check, _p, _stream, lib, weights_changed
         L = lib()
         weights_changed()          # parameters are rewritten through raw pointers: invalidate re-laid weight copies
@@ -252,7 +269,9 @@ class FusedAdamW(torch.optim.Optimizer):
                                      _p(self._gnorm) if use_clip else None, ctypes.c_float(self.max_norm),
                                      ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(g["eps"]), 1,
                                      _p(a["planes"][0]) if a["planes"] is not None else None,
-                                     _p(a["planes"][1]) if a["planes"] is not None else None, _stream()),
+                                     _p(a["planes"][1]) if a["planes"] is not None else None,
+                                     1 if (a["planes"] is not None and a["planes"].dtype == torch.float16) else 0,
+                                     ctypes.c_float(_wscale), _stream()),
                    "adamw_ema")
         if self._buf_src is not None:
             _check(L.dfine_ema_blend(_p(self._buf_ema), _p(self._buf_src), ctypes.c_long(self._buf_src.numel()),

@@ -13,12 +13,15 @@ import torch
 from torch.nn.parallel import DistributedDataParallel as DDP
 
 
-def _begin_step(inputs):
-    """One memset for every per-layer fp64 reduction buffer of the step (cuda_ops.zero_pool)."""
+def _begin_step(inputs, counters=None):
+    """One memset for every per-layer fp64 reduction buffer of the step (cuda_ops.zero_pool), one add for every
+    BatchNorm step counter."""
     if inputs.is_cuda:
         from . import cuda_ops
         cuda_ops.zero_pool.begin_step(inputs.device)
         cuda_ops.wgrad_stream.begin(inputs.device)
+        if counters is not None:
+            counters.add_(1)
 
 
 def _after_forward():
@@ -144,6 +147,11 @@ class TrainStep:
         self.scheduler, self.ema, self.clip_max_norm = scheduler, ema, clip_max_norm
         self.accum_steps, self.ema_iter, self.batch_idx = accum_steps, 0, 0
         self.fused = getattr(optimizer, "fused_step", False)
+        self._counters = None
+        m = model.module if isinstance(model, DDP) else model
+        if next(m.parameters()).is_cuda:
+            from . import cuda_ops
+            self._counters = cuda_ops.register_step_counters(m)
         if self.fused:
             optimizer.max_norm = float(clip_max_norm or 0.0)
             if ema is not None:
@@ -183,7 +191,7 @@ class TrainStep:
 
     def __call__(self, inputs, targets):
         """inputs float32 [B,3,H,W] on the device; targets list of dicts (labels int64 [T], boxes [T,4])."""
-        _begin_step(inputs)
+        _begin_step(inputs, self._counters if self.model.training else None)
         output = self.model(inputs, targets=targets)
         _after_forward()
         loss_dict = self.loss_fn(output, targets)
@@ -290,7 +298,7 @@ class GraphedTrainStep(TrainStep):
         torch.cuda.synchronize()
         gA = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gA, stream=self._side):
-            _begin_step(g["x"])
+            _begin_step(g["x"], self._counters)
             out = self.model(g["x"], targets=g["targets"])
             raw, tg = crit.match(out, g["targets"])
             _after_forward()

@@ -109,7 +109,7 @@ def compare(tag, cpu, cuda, l2_bar, loss_bar, entry_bar, grad_scale=2.0, max_swa
     return pairing
 
 
-@pytest.mark.parametrize("mode,l2_bar,entry_bar", [("simt", 1e-3, 1e-3), ("tc3", 1e-3, 5e-3)])
+@pytest.mark.parametrize("mode,l2_bar,entry_bar", [("simt", 1e-3, 1e-3), ("hf3", 1e-3, 5e-3), ("tc3", 1e-3, 5e-3)])
 def test_n_matches_cpu_oracle(cuda_ops, oracle_ops, mode, l2_bar, entry_bar):
     """D-FINE-n (BASELINE config 1's family) ON THE GPU: its 21 / 298-channel layers run through the same kernels on
     zero-extended channel strides (cuda_ops._conv_bn_act_padded); head_dim 16 attention and deformable attention."""
@@ -118,20 +118,20 @@ def test_n_matches_cpu_oracle(cuda_ops, oracle_ops, mode, l2_bar, entry_bar):
 
 
 def test_x_1280_batch4_matches_cpu_oracle(cuda_ops, oracle_ops):
-    """BASELINE config 5 (per-GPU share): D-FINE-x, 1280x1280, batch 4, default tensor-core mode."""
-    cpu, cuda = step_both(oracle_ops, "x", 1280, 4, False, "tc3", T=(10, 7, 3, 10))
-    compare("x@1280/tc3", cpu, cuda, 2e-3, 6e-3, 2e-2, grad_scale=4.0, max_swapped=3)
+    """BASELINE config 5 (per-GPU share): D-FINE-x, 1280x1280, batch 4, default tensor-core mode (3xFP16)."""
+    cpu, cuda = step_both(oracle_ops, "x", 1280, 4, False, "hf3", T=(10, 7, 3, 10))
+    compare("x@1280/hf3", cpu, cuda, 2e-3, 6e-3, 2e-2, grad_scale=4.0, max_swapped=3)
 
 
 def test_lseg_640_batch8_matches_cpu_oracle(cuda_ops, oracle_ops):
     """BASELINE config 4: D-FINE-l with the mask head, 640x640, batch 8, default tensor-core mode (mask matching cost,
     mask BCE / Dice terms, MaskDecoder, [B,Q,160,160] mask logits per layer)."""
-    cpu, cuda = step_both(oracle_ops, "l", 640, 8, True, "tc3", T=(10, 7, 3, 10))
+    cpu, cuda = step_both(oracle_ops, "l", 640, 8, True, "hf3", T=(10, 7, 3, 10))
     (m0, o0, l0), (m1, o1, l1) = cpu, cuda
     assert len(l0) == 87, len(l0)
-    pairing = compare("l-seg@640/tc3", cpu, cuda, 2e-3, 6e-3, 2e-2, grad_scale=4.0, max_swapped=3)
+    pairing = compare("l-seg@640/hf3", cpu, cuda, 2e-3, 6e-3, 2e-2, grad_scale=4.0, max_swapped=3)
     got = torch.cat([o1["pred_masks"][b].detach().cpu()[keep] for b, (idx, keep) in enumerate(pairing)])
     ref = torch.cat([o0["pred_masks"][b].detach()[idx][keep] for b, (idx, keep) in enumerate(pairing)])
     d = (got - ref).norm() / ref.norm()
-    print(f"[l-seg@640/tc3] pred_masks rel-L2 {float(d):.2e}")
+    print(f"[l-seg@640/hf3] pred_masks rel-L2 {float(d):.2e}")
     assert float(d) <= 2e-3, float(d)

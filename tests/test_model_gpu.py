@@ -136,7 +136,7 @@ def test_train_step_matches_reference_fixture(cuda_ops, mode, tol):
                 fix["running_mean_stem1"], 1e-4)
 
 
-@pytest.mark.parametrize("size,mode,tol", [("l", "simt", 1e-3), ("l", "tc3", 3e-3), ("x", "simt", 1e-3), ("x", "tc3", 6e-3)])
+@pytest.mark.parametrize("size,mode,tol", [("l", "simt", 1e-3), ("l", "hf3", 3e-3), ("l", "tc3", 3e-3), ("x", "simt", 1e-3), ("x", "hf3", 6e-3), ("x", "tc3", 6e-3)])
 def test_other_model_sizes_match_cpu_oracle(cuda_ops, oracle_ops, size, mode, tol):
     """The other GPU families of BASELINE.json's configs (l / x: the detect part of configs 3 / 4) through the CUDA
     library against the CPU oracle driving the same host graph on the same seeded weights and batch: x exercises
@@ -189,7 +189,7 @@ def test_other_model_sizes_match_cpu_oracle(cuda_ops, oracle_ops, size, mode, to
     _check_param_grads(f"{size}/{mode}", m1, m0, lambda k: (0.1 if k.startswith("backbone") else 0.05) * scale)
 
 
-@pytest.mark.parametrize("mode,max_entry", [("simt", 3e-3), ("tc3", 1.5e-2)])
+@pytest.mark.parametrize("mode,max_entry", [("simt", 3e-3), ("hf3", 1.5e-2), ("tc3", 1.5e-2)])
 def test_m_with_pretrained_weights_matches_cpu_oracle(cuda_ops, oracle_ops, mode, max_entry):
     """BASELINE.json's headline configuration as the survey specifies it: D-FINE-m at 640x640 with
     the reference's own COCO checkpoint (`pretrained/dfine_m_coco.pth`, copied by hand to the git-ignored

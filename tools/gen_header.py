@@ -39,6 +39,8 @@ GROUPS = [
      " * unimodal_distribution_focal_loss 837-858, bbox2distance / translate_gt arch/utils.py:267-354.  One launch\n"
      " * description (dfine_loss_desc.h) for all entry points; call order: prepare, {vfl,box,fgl_ddf}_fwd, finalize;\n"
      " * backward: {vfl,box,fgl_ddf}_bwd with the same description and workspace."),
+    ("select.cu", "Query selection (row max + top-k) and the decoder gate",
+     "DFINETransformer._select_topk dfine_decoder.py:875-910; Gate.forward dfine_decoder.py:258-271."),
     ("matcher.cu", "Hungarian matcher (cost blocks + LSAP)",
      "HungarianMatcher.forward matcher.py:110-257 (scipy.optimize.linear_sum_assignment at 243)."),
     ("optim.cu", "Optimizer / EMA",
