@@ -65,7 +65,35 @@ class ConvUnit(nn.Module):
     def _bn(self):
         return getattr(self, self._norm_name)
 
+    def fused_kernel_bias(self):
+        """Conv weight / bias with the BatchNorm's running statistics folded in (hybrid_encoder.py:66-80)."""
+        bn = self._bn()
+        t = bn.weight / (bn.running_var + bn.eps).sqrt()
+        return (self.conv.weight * t.reshape(-1, 1, 1, 1)).detach(), (bn.bias - bn.running_mean * t).detach()
+
+    def convert_to_deploy(self):
+        """Inference re-parameterisation (ConvNormLayer_fuse.convert_to_deploy, hybrid_encoder.py:47-63): conv and
+        BatchNorm become ONE biased conv (`conv_bn_fused`, the reference's name); the forward pass is then a single
+        kernel launch with bias, activation and the LAB scalars in its epilogue.  Applied to every conv unit of the graph
+        (the reference folds its encoder layers only; the arithmetic is the same eval-mode affine map)."""
+        if hasattr(self, "conv_bn_fused"):
+            return
+        w, b = self.fused_kernel_bias()
+        c = self.conv
+        fused = nn.Conv2d(c.in_channels, c.out_channels, c.kernel_size, c.stride, c.padding, groups=c.groups, bias=True)
+        fused.weight.data, fused.bias.data = w.contiguous(), b.contiguous()
+        fused.requires_grad_(False)
+        lab = getattr(self, "lab", None)
+        self._lab = None if lab is None else (float(lab.scale), float(lab.bias))
+        self.conv_bn_fused = fused
+        del self.conv
+        delattr(self, self._norm_name)
+
     def forward(self, x, pre_add=None, post_add=None, tap=False):
+        if hasattr(self, "conv_bn_fused"):
+            f = self.conv_bn_fused
+            y = K.conv_bias_act(x, f.weight, f.bias, self.stride, self.pad, self.groups, self.act, self._lab, pre_add, post_add)
+            return (y, x) if tap else y
         bn = self._bn()
         frozen = isinstance(bn, FrozenBN)
         lab = getattr(self, "lab", None)

@@ -235,6 +235,8 @@ struct FwdParams {
     int wk2[MAX_TAPS];        // hybrid mode: first weight column of tap t in the tap-padded bf16 planes
     int half16;               // 16-bit plane modes (X3 = 2): 0 = bf16 planes (3xBF16), 1 = fp16 planes (3xFP16)
     float out_scale;          // accumulator scale applied first in the epilogue (3xFP16 weights are stored x 2^8)
+    int lab;                  // deploy-mode epilogue: y = lab_s * act(acc + bias) + lab_b (LearnableAffineBlock, hgnetv2.py:25-32)
+    float lab_s, lab_b;
     const float* res;         // optional tensor added to the output in the epilogue (same pixel geometry as y,
     long ldres;               // pixel stride ldres): fuses the gradient-accumulation add of a multi-consumer tensor
 };
@@ -625,7 +627,7 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
         // 128-byte row stores.  Shared accesses are explicit st/ld.shared.v4 (8 + 8 per 32-column chunk).
         const int q = warp % 4;  // TMEM lane quarter
         const uint32_t wbase = smem_u32(sm.epi[q]);
-        const bool plain = (bias == nullptr) && p.act == 0;
+        const bool plain = (bias == nullptr) && p.act == 0 && !p.lab;
         const bool local_stats = stats != nullptr && ts.n_tiles == 1;
         typename StatT<BN>::type* sw = sm.statw[q];
         uint32_t i = 0;
@@ -688,6 +690,10 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                         if (!plain) {
                             o.x = act_fwd(o.x + bv.x, p.act); o.y = act_fwd(o.y + bv.y, p.act);
                             o.z = act_fwd(o.z + bv.z, p.act); o.w = act_fwd(o.w + bv.w, p.act);
+                            if (p.lab) {
+                                o.x = fmaf(o.x, p.lab_s, p.lab_b); o.y = fmaf(o.y, p.lab_s, p.lab_b);
+                                o.z = fmaf(o.z, p.lab_s, p.lab_b); o.w = fmaf(o.w, p.lab_s, p.lab_b);
+                            }
                         }
                         if (X3 == 0 && has_res) { o.x += rcur[r8].x; o.y += rcur[r8].y; o.z += rcur[r8].z; o.w += rcur[r8].w; }
                         *reinterpret_cast<float4*>(y + row_off[r8] * p.ldy + col) = o;
@@ -1201,7 +1207,8 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
                  double* stats, int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy,
                  int YH, int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
                  const int* taps, long ldw, int act, void* stream, long ldw16 = 0, const float* res = nullptr,
-                 long ldres = 0, int half16 = 0, float out_scale = 1.f, long plane_stride16 = 0) {
+                 long ldres = 0, int half16 = 0, float out_scale = 1.f, long plane_stride16 = 0, int lab = 0,
+                 float lab_s = 1.f, float lab_b = 0.f) {
     DFINE_REQUIRE(n_taps >= 1 && n_taps <= MAX_TAPS, "conv_tc: %d taps unsupported", n_taps);
     DFINE_REQUIRE(in_stride == 1 || in_stride == 2, "conv_tc: input stride %d unsupported", in_stride);
     DFINE_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldw % ((w_bf16 && !w) ? 8 : 4) == 0 &&
@@ -1226,6 +1233,7 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
     DFINE_REQUIRE(!res || (ldres % 4 == 0 && ldres >= Cout && ((uintptr_t)res % 16) == 0), "conv_tc: residual stride %ld", ldres);
     p.res = res; p.ldres = ldres;
     p.half16 = half16; p.out_scale = out_scale;
+    p.lab = lab; p.lab_s = lab_s; p.lab_b = lab_b;
     p.in_stride = in_stride; p.Cin = Cin;
     p.OH = OH; p.OW = OW; p.N = Cout; p.ldy = ldy; p.act = act;
     p.YH = YH; p.YW = YW; p.osy = osy; p.osx = osx; p.ooy = ooy; p.oox = oox;
@@ -1375,16 +1383,17 @@ DFINE_API int dfine_conv_tc_bf16x3(const float* x, const void* w_planes, const f
 // tf32 rate and both planes of an operand take the bytes of one fp32 plane.  fp16's narrow exponent is handled by
 // scale: `w_planes` = dfine_f16_split(w * w_scale) with w_scale a power of two that lifts the small weights' lo parts
 // out of the subnormal range; `out_scale` = 1 / w_scale is applied to the accumulator first thing in the epilogue
-// (exact).  `plane_stride` = elements between the hi and the lo plane (0: adjacent, [2][Cout][ldw]).  Activations are split unscaled inside the kernel (post-normalisation values are O(1); |a| must stay below
+// (exact).  lab != 0: the deploy-mode epilogue y = lab_scale * act(acc + bias) + lab_bias.  `plane_stride` = elements between the hi and the lo plane (0: adjacent, [2][Cout][ldw]).  Activations are split unscaled inside the kernel (post-normalisation values are O(1); |a| must stay below
 // 65504, lo parts below 2^-14 lose relative — not absolute (2^-25) — precision).
 DFINE_API int dfine_conv_tc_f16x3(const float* x, const void* w_planes, const float* bias, float* y, double* stats,
                                   int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy, int YH,
                                   int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
                                   const int* taps, long ldw, int act, float out_scale, long plane_stride,
-                                  void* stream) {
+                                  int lab, float lab_scale, float lab_bias, void* stream) {
     DFINE_REQUIRE(w_planes != nullptr, "conv_tc_f16x3: null weight planes");
     return conv_tc_impl(x, nullptr, nullptr, w_planes, bias, y, stats, B, H, W, Cin, ldx, OH, OW, Cout, ldy, YH, YW, osy,
-                        osx, ooy, oox, in_stride, n_taps, taps, ldw, act, stream, 0, nullptr, 0, 1, out_scale, plane_stride);
+                        osx, ooy, oox, in_stride, n_taps, taps, ldw, act, stream, 0, nullptr, 0, 1, out_scale, plane_stride,
+                        lab, lab_scale, lab_bias);
 }
 
 // Hybrid operands (see PersistSmem, X3 = 3): a_hi*w_hi on kind::tf32, the cross terms on bf16 copies.  `w_hi` = the

@@ -140,6 +140,17 @@ zero_pool = _ZeroPool()
 _scalar_cache = {}
 
 
+_ones = {}
+
+
+def _ones_cache(n, device):
+    key = (n, str(device))
+    t = _ones.get(key)
+    if t is None:
+        t = _ones[key] = torch.ones(n, device=device, dtype=torch.float32)
+    return t
+
+
 def _as_dev_scalar(v, device):
     """A [1] fp32 device tensor for a kernel that reads the scalar from memory (tensors pass through; python
     numbers are uploaded once per value and cached — a pageable H2D copy is not graph-capturable)."""
@@ -317,7 +328,7 @@ def _taps(key, make):
 
 
 def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, YH, YW, os_, oo, in_stride, taps, act,
-               stats, what, bf16_planes=None, res=None, ldres=0, plane_stride=0):
+               stats, what, bf16_planes=None, res=None, ldres=0, plane_stride=0, lab=None):
     arr, n = taps
     # algorithmic bytes: input pixels + output pixels + weights, each touched once, fp32
     nbytes = 4 * (B * min(H * W, OH * OW * in_stride * in_stride) * Cin + B * OH * OW * Cout + Cout * n * Cin)
@@ -331,7 +342,9 @@ def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, Y
             _check(lib().dfine_conv_tc_f16x3(_p(x), _p(bf16_planes), _p(bias), _p(y), _p(stats), B, H, W, Cin,
                                              c_long(ldx), OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0],
                                              oo[1], in_stride, n, arr, c_long(bf16_planes.shape[-1]), act,
-                                             c_float(1.0 / _F16_WSCALE), c_long(plane_stride), _stream()), what)
+                                             c_float(1.0 / _F16_WSCALE), c_long(plane_stride), 0 if lab is None else 1,
+                                             c_float(1.0 if lab is None else lab[0]), c_float(0.0 if lab is None else lab[1]),
+                                             _stream()), what)
         elif bf16_planes is not None:
             _check(lib().dfine_conv_tc_bf16x3(_p(x), _p(bf16_planes), _p(bias), _p(y), _p(stats), B, H, W, Cin,
                                               c_long(ldx), OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0],
@@ -378,10 +391,11 @@ def _split_bf16(w2d, taps, Cin, mode=0):
 # ------------------------------------------------------------------------------------------------
 # raw launchers (no autograd)
 # ------------------------------------------------------------------------------------------------
-def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None):
+def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None, lab=None):
     """geom = (B,H,W,Cin,OH,OW,Cout,k,stride,pad4).  ``weight`` is the parameter ([Cout,Cin,k,k] conv or [N,K]
     linear); ``wkey`` its cache getter.  Returns True if the tensor-core kernel ran (it fuses the BN statistics)."""
     B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
+    assert lab is None or _MODE == "hf3", "the fused LAB epilogue exists on the 3xFP16 path only"
     if _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy):
         K = k * k * Cin
         wr = wkey("wr", lambda: weight.reshape(Cout, Cin, k, k).permute(0, 2, 3, 1).reshape(Cout, K).contiguous())
@@ -406,8 +420,9 @@ def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None):
         taps = _taps(("f", k, pad[0], pad[1], cs),
                      lambda: [(kh - pad[0], kw - pad[1], (kh * k + kw) * cs) for kh in range(k) for kw in range(k)])
         _tc_launch(x, ldx, H, W, Cin, w_hi, w_lo, K, bias, y, ldy, B, OH, OW, Cout, OH, OW, (1, 1), (0, 0), stride,
-                   taps, act, stats, "conv_fwd_tc", planes, plane_stride=plane_stride)
+                   taps, act, stats, "conv_fwd_tc", planes, plane_stride=plane_stride, lab=lab)
         return True
+    assert lab is None, "fused LAB epilogue needs a tensor-core geometry"
     wr = wkey("wr", lambda: weight.reshape(Cout, Cin, k, k).permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous())
     if bias is None and act == 0 and _MODE != "simt" and \
             lib().dfine_stem_conv_supported(Cin, Cout, k, k, stride, pad[0], pad[1], pad[2], pad[3], c_long(ldy)):
@@ -1228,6 +1243,58 @@ class CudaOps:
         y = out[..., :Cout] if co else out
         return (y, x) if tap else y
 
+    @torch.no_grad()
+    def conv_bias_act(self, x, w, b, stride, pad, groups, act=None, lab=None, pre_add=None, post_add=None):
+        """Deploy-mode conv unit (inference only, no autograd): conv with the BatchNorm folded into weight / bias
+        (hybrid_encoder.py:47-80, 123-137), activation, LAB scalars `lab = (scale, bias)` — ONE kernel on the tensor-core
+        path (bias + act + LAB in the epilogue); depthwise / ragged geometries and fused adds run conv + one apply pass."""
+        _req_cuda(x, w)
+        if x.stride(-1) != 1 or x.dim() != 4:
+            x = x.contiguous()
+        B, H, W, Cin = x.shape
+        ok = x.stride(2) >= Cin and x.stride(1) == W * x.stride(2) and x.stride(0) == H * W * x.stride(2) \
+            and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0
+        if not ok:
+            x = x.contiguous()
+        ldx = x.stride(2)
+        Cout, _, k, _ = w.shape
+        pt, pl, pb, pr = pad
+        OH = (H + pt + pb - k) // stride + 1
+        OW = (W + pl + pr - k) // stride + 1
+        geom = (B, H, W, Cin, OH, OW, Cout, k, stride, tuple(pad))
+        y = torch.empty((B, OH, OW, Cout), device=x.device, dtype=torch.float32)
+        fused = (groups == 1 and pre_add is None and post_add is None and _MODE == "hf3" and Cin % 4 == 0 and Cout % 4 == 0
+                 and act in (None, "relu", "silu") and _tc_ok(Cin, Cout, k, stride, pad, ldx, Cout))
+        if fused:
+            _conv_fwd(x, ldx, w, _wcache.getter(w), b, y, Cout, geom, ACT[act], None, lab)
+            return y
+        if groups > 1:
+            assert groups == Cin == Cout and pt == pl == pb == pr
+            if ldx != Cin:
+                x, ldx = x.contiguous(), Cin
+            wt = _wcache.get(w, "dw", lambda: w.reshape(Cout, k * k).t().contiguous())
+            _check(lib().dfine_dwconv_fwd(_p(x), _p(wt), _p(y), B, H, W, Cin, k, stride, pt, _stream()), "dwconv_fwd")
+        elif Cin % 4 or Cout % 4:
+            if Cin == 3:
+                _conv_fwd(x, ldx, w, _wcache.getter(w), None, y, Cout, geom, 0, None)
+            else:   # D-FINE-n's 21-channel layers: zero-extended channel strides (see _conv_bn_act_padded)
+                F = torch.nn.functional
+                ci, co = (-Cin) % 4, (-Cout) % 4
+                yp = self.conv_bias_act(F.pad(x, (0, ci)), F.pad(w, (0, 0, 0, 0, 0, ci, 0, co)), F.pad(b, (0, co)), stride,
+                                        pad, 1, act, lab, None if pre_add is None else F.pad(pre_add, (0, co)),
+                                        None if post_add is None else F.pad(post_add, (0, co)))
+                return yp[..., :Cout]
+        else:
+            _conv_fwd(x, ldx, w, _wcache.getter(w), None, y, Cout, geom, 0, None)
+        one = _ones_cache(Cout, x.device)
+        out = torch.empty_like(y)
+        ls = None if lab is None else _as_dev_scalar(lab[0], x.device)
+        lb = None if lab is None else _as_dev_scalar(lab[1], x.device)
+        _check(lib().dfine_bn_apply(_p(y), _p(one), _p(b), _p(None if pre_add is None else pre_add.contiguous()),
+                                    _p(None if post_add is None else post_add.contiguous()), _p(ls), _p(lb), _p(out),
+                                    c_long(B * OH * OW), Cout, ACT[act], c_long(Cout), _stream()), "bn_apply")
+        return out
+
     def maxpool2x2_s1_padbr(self, x):
         return _MaxPool.apply(x)
 
@@ -1302,6 +1369,48 @@ class CudaOps:
     def mask_dot(self, embed, feat_nhwc):
         _req_cuda(embed, feat_nhwc)
         return torch.einsum("bqc,bhwc->bqhw", embed, feat_nhwc)
+
+    # ---- input side / post-processing (the callers either side of the hot path) ----
+    @torch.no_grad()
+    def preprocess_u8(self, images_u8, size=None, mul=1.0 / 255.0, swap_rb=True):
+        _req_cuda(images_u8)
+        assert images_u8.dtype == torch.uint8 and images_u8.dim() == 4
+        x = images_u8.contiguous()
+        B, Hs, Ws, C = x.shape
+        H, W = (Hs, Ws) if size is None else (int(size[0]), int(size[1]))
+        out = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
+        _check(lib().dfine_preprocess_u8(_p(x), _p(out), B, Hs, Ws, H, W, C, c_float(mul), 1 if swap_rb else 0, _stream()),
+               "preprocess_u8")
+        return out
+
+    @torch.no_grad()
+    def resize_images(self, x_nhwc, size):
+        _req_cuda(x_nhwc)
+        x = x_nhwc.contiguous().float()
+        B, Hs, Ws, C = x.shape
+        H, W = int(size[0]), int(size[1])
+        out = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
+        _check(lib().dfine_resize_bilinear_f32(_p(x), _p(out), B, Hs, Ws, H, W, C, _stream()), "resize_bilinear_f32")
+        return out
+
+    @torch.no_grad()
+    def postprocess(self, logits, boxes, k, height, width, to_round=True):
+        """(labels int64 [B,k], boxes xyxy [B,k,4] in input pixels, scores [B,k], query index int64 [B,k])."""
+        _req_cuda(logits, boxes)
+        logits, boxes = logits.contiguous().float(), boxes.contiguous().float()
+        B, Q, C = logits.shape
+        dev = logits.device
+        ws = torch.empty((B, Q * C), device=dev, dtype=torch.float32)
+        idx = torch.empty((B, k), device=dev, dtype=torch.int64)
+        _check(lib().dfine_topk_rowmax(_p(logits), _p(ws), _p(idx), B, Q * C, 1, int(k), _stream()), "topk_rowmax")
+        labels = torch.empty((B, k), device=dev, dtype=torch.int64)
+        qidx = torch.empty((B, k), device=dev, dtype=torch.int64)
+        out_boxes = torch.empty((B, k, 4), device=dev, dtype=torch.float32)
+        scores = torch.empty((B, k), device=dev, dtype=torch.float32)
+        _check(lib().dfine_postprocess(_p(logits), _p(boxes), _p(idx), _p(labels), _p(out_boxes), _p(scores), _p(qidx), B, Q,
+                                       C, int(k), c_float(height), c_float(width), 1 if to_round else 0, _stream()),
+               "postprocess")
+        return labels, out_boxes, scores, qidx
 
     # ---- criterion ----
     def criterion_sets(self, full, enc_logits, enc_boxes, table, counts, labels, tboxes, project, reg_scale, meta):

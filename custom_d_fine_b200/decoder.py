@@ -165,6 +165,11 @@ class DecoderStack(nn.Module):
         self.layers = nn.ModuleList(DecoderLayer(d, heads, ffn, levels, points) for _ in range(num_layers))
         self.lqe_layers = nn.ModuleList(LQEParams(4, 64, 2, reg_max) for _ in range(num_layers))
 
+    def convert_to_deploy(self):
+        """Inference truncation (dfine_decoder.py:422-427): layers past `eval_idx` and the unused LQE heads go."""
+        self.layers = self.layers[: self.eval_idx + 1]
+        self.lqe_layers = nn.ModuleList([nn.Identity()] * self.eval_idx + [self.lqe_layers[self.eval_idx]])
+
     def forward(self, tgt, ref_unact, memory, spatial_shapes, bbox_head, score_head, qpos_head,
                 pre_bbox_head, attn_mask=None, return_queries=False):
         project = weighting_function(self.reg_max, self.up, self.reg_scale)
@@ -178,7 +183,7 @@ class DecoderStack(nn.Module):
                 queries.append(out)
             if i == 0:
                 pre_boxes = torch.sigmoid(pre_bbox_head(out) + inverse_sigmoid(ref))
-                pre_scores = K.linear(out, score_head[0].weight, score_head[0].bias)
+                pre_scores = K.linear(out, score_head[0].weight, score_head[0].bias) if self.training else None
                 ref_initial = pre_boxes.detach()
             corners = bbox_head[i](out if out_detach is None else out + out_detach)
             if corners_prev is not None:
@@ -330,6 +335,12 @@ class DFINETransformer(nn.Module):
             self.register_buffer("anchors", a)
             self.register_buffer("valid_mask", v)
         self._init_heads(feat_channels)
+
+    def convert_to_deploy(self):
+        """Inference pruning of the per-layer heads (dfine_decoder.py:698-707)."""
+        self.dec_score_head = nn.ModuleList([nn.Identity()] * self.eval_idx + [self.dec_score_head[self.eval_idx]])
+        self.dec_bbox_head = nn.ModuleList([self.dec_bbox_head[i] if i <= self.eval_idx else nn.Identity()
+                                            for i in range(len(self.dec_bbox_head))])
 
     def _init_heads(self, feat_channels):
         prior = bias_init_with_prob(0.01)

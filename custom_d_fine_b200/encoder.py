@@ -26,7 +26,26 @@ class RepVGG(nn.Module):
         self.conv1 = _cn(cin, cout, 3)
         self.conv2 = _cn(cin, cout, 1, act=act)  # act runs after the branch sum (pre_add)
 
+    def convert_to_deploy(self):
+        """RepVGG re-parameterisation (VGGBlock.convert_to_deploy, hybrid_encoder.py:123-137): both branches with their
+        BatchNorms folded become one biased 3x3 conv (the 1x1 kernel zero-padded into the centre tap)."""
+        if hasattr(self, "conv"):
+            return
+        w3, b3 = self.conv1.fused_kernel_bias()
+        w1, b1 = self.conv2.fused_kernel_bias()
+        cout, cin = w3.shape[:2]
+        conv = nn.Conv2d(cin, cout, 3, 1, padding=1)
+        conv.weight.data = (w3 + torch.nn.functional.pad(w1, (1, 1, 1, 1))).contiguous()
+        conv.bias.data = (b3 + b1).contiguous()
+        conv.requires_grad_(False)
+        self._act = self.conv2.act
+        self.conv = conv
+        del self.conv1
+        del self.conv2
+
     def forward(self, x):
+        if hasattr(self, "conv"):
+            return K.conv_bias_act(x, self.conv.weight, self.conv.bias, 1, (1, 1, 1, 1), 1, self._act)
         # x feeds both branches: the 1x1 branch reads the 3x3 conv's `tap` alias of x, so its data gradient is added
         # inside the 3x3 conv's data-gradient kernel instead of by a separate accumulation kernel
         a, xa = self.conv1(x, tap=True)

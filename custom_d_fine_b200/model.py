@@ -33,9 +33,12 @@ class DFINE(nn.Module):
         return self.decoder(self.encoder(self.backbone(x)), targets)
 
     def deploy(self):
+        """Inference form (dfine.py:43-48): eval mode + every module's `convert_to_deploy` — conv + BatchNorm folded
+        into one biased conv, RepVGG branches merged into one 3x3 conv, decoder layers / heads past `eval_idx` dropped.
+        Parents convert before their children (a RepVGG block folds its two branches itself)."""
         self.eval()
-        for m in self.modules():
-            if hasattr(m, "convert_to_deploy"):
+        for m in list(self.modules()):
+            if m is not self and hasattr(m, "convert_to_deploy"):
                 m.convert_to_deploy()
         return self
 

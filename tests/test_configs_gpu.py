@@ -23,8 +23,28 @@ from tests.test_model_gpu import _check_param_grads, _host_rng
 pytestmark = pytest.mark.gpu
 
 
-def step_both(oracle_ops, size, hw, B, seg, mode, seed=11, T=(10, 7, 0, 3)):
+def step_both(oracle_ops, size, hw, B, seg, mode, seed=11, T=(10, 7, 0, 3), pin_selection=False):
+    """pin_selection: the CUDA run selects the SAME top-300 memory tokens as the oracle run (its own selection is
+    compared separately: same set up to candidates whose scores tie with the rank-300 score within rounding).  The
+    selection is a discontinuity of the model — one candidate exchanged at rank 300 changes every other query through
+    the decoder's self-attention — so arithmetic parity of everything downstream is measured given equal selections,
+    exactly like the matcher's indices are compared given equal costs."""
+    from custom_d_fine_b200.cuda_ops import CudaOps
     x, targets = synthetic_batch(B, hw, hw, seed=1234 + seed, T=T)
+    picked = {}
+    orig_cpu, orig_cuda = type(oracle_ops).select_topk, CudaOps.select_topk
+
+    def cpu_select(self, logits, k):
+        picked["cpu"] = orig_cpu(self, logits, k)
+        picked["cpu_scores"] = logits.max(-1).values.detach()
+        return picked["cpu"]
+
+    def cuda_select(self, logits, k):
+        picked["cuda"] = orig_cuda(self, logits, k)
+        picked["cuda_scores"] = logits.max(-1).values.detach().cpu()
+        return picked["cpu"].to(logits.device) if pin_selection else picked["cuda"]
+
+    type(oracle_ops).select_topk, CudaOps.select_topk = cpu_select, cuda_select
     if seg:
         for t in targets:
             t["masks"] = rect_masks(t["boxes"], hw, hw)
@@ -55,7 +75,30 @@ def step_both(oracle_ops, size, hw, B, seg, mode, seed=11, T=(10, 7, 0, 3)):
             runs[dev] = (model, out, losses)
     finally:
         co.set_gemm_mode(prev)
+        type(oracle_ops).select_topk, CudaOps.select_topk = orig_cpu, orig_cuda
+    if pin_selection:
+        check_selection(f"{size}@{hw}/{mode}", picked)
     return runs["cpu"], runs["cuda"]
+
+
+def check_selection(tag, picked):
+    """The CUDA path's own top-k against the oracle's: equal as sets except for candidates whose score is within 1e-4
+    (relative to the score range) of the rank-k score — near-ties that any fp32 re-association may order either way."""
+    a, b = picked["cpu"], picked["cuda"].cpu()
+    sc, sg = picked["cpu_scores"], picked["cuda_scores"]
+    worst, n_swapped = 0.0, 0
+    for i in range(a.shape[0]):
+        sa, sb = set(a[i].tolist()), set(b[i].tolist())
+        thr = float(sc[i][a[i]].min())
+        rng = float(sc[i].max() - sc[i].min())
+        for t in sa ^ sb:
+            worst = max(worst, abs(float(sc[i][t]) - thr) / rng)
+        n_swapped = max(n_swapped, len(sa - sb))
+    err = float((sg - sc).abs().max() / sc.abs().max())
+    print(f"\n[{tag}] query selection: encoder scores max err {err:.2e}; candidates exchanged at the rank-k boundary (max per "
+          f"image) {n_swapped}, their distance to the rank-k score {worst:.2e} of the score range")
+    assert worst <= 1e-4, (tag, worst)
+    assert n_swapped <= 0.05 * a.shape[1], (tag, n_swapped)
 
 
 def compare(tag, cpu, cuda, l2_bar, loss_bar, entry_bar, grad_scale=2.0, max_swapped=0):
@@ -119,17 +162,17 @@ def test_n_matches_cpu_oracle(cuda_ops, oracle_ops, mode, l2_bar, entry_bar):
 
 def test_x_1280_batch4_matches_cpu_oracle(cuda_ops, oracle_ops):
     """BASELINE config 5 (per-GPU share): D-FINE-x, 1280x1280, batch 4, default tensor-core mode (3xFP16)."""
-    cpu, cuda = step_both(oracle_ops, "x", 1280, 4, False, "hf3", T=(10, 7, 3, 10))
-    compare("x@1280/hf3", cpu, cuda, 2e-3, 6e-3, 2e-2, grad_scale=4.0, max_swapped=3)
+    cpu, cuda = step_both(oracle_ops, "x", 1280, 4, False, "hf3", T=(10, 7, 3, 10), pin_selection=True)
+    compare("x@1280/hf3", cpu, cuda, 2e-3, 6e-3, 2e-2, grad_scale=4.0)
 
 
 def test_lseg_640_batch8_matches_cpu_oracle(cuda_ops, oracle_ops):
     """BASELINE config 4: D-FINE-l with the mask head, 640x640, batch 8, default tensor-core mode (mask matching cost,
     mask BCE / Dice terms, MaskDecoder, [B,Q,160,160] mask logits per layer)."""
-    cpu, cuda = step_both(oracle_ops, "l", 640, 8, True, "hf3", T=(10, 7, 3, 10))
+    cpu, cuda = step_both(oracle_ops, "l", 640, 8, True, "hf3", T=(10, 7, 3, 10), pin_selection=True)
     (m0, o0, l0), (m1, o1, l1) = cpu, cuda
     assert len(l0) == 87, len(l0)
-    pairing = compare("l-seg@640/hf3", cpu, cuda, 2e-3, 6e-3, 2e-2, grad_scale=4.0, max_swapped=3)
+    pairing = compare("l-seg@640/hf3", cpu, cuda, 2e-3, 6e-3, 2e-2, grad_scale=4.0)
     got = torch.cat([o1["pred_masks"][b].detach().cpu()[keep] for b, (idx, keep) in enumerate(pairing)])
     ref = torch.cat([o0["pred_masks"][b].detach()[idx][keep] for b, (idx, keep) in enumerate(pairing)])
     d = (got - ref).norm() / ref.norm()

@@ -64,9 +64,16 @@ def test_fused_adamw_ema_matches_torch(cuda_ops):
             if es[k].dtype.is_floating_point:
                 check_close(f"ema {k} step {it}", ed[k], es[k], 5e-6)
     assert math.isfinite(float(opt_dev.grad_norm()))
-    # the AdamW kernel also maintains the 3xTF32 weight planes: hi is tf32-representable, hi + lo is the parameter
+    # the AdamW kernel also maintains the operand planes of the forward GEMMs
+    from custom_d_fine_b200 import cuda_ops as co
     for a in opt_dev._arenas:
         if a is not None and a["planes"] is not None:
             hi, lo = a["planes"][0], a["planes"][1]
-            assert torch.equal(hi + lo, a["p"])
-            assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+            if hi.dtype == torch.float16:      # 3xFP16: fp16 parts of w * 2^8, 22 significand bits together
+                back = (hi.double() + lo.double()) / co._F16_WSCALE
+                err = (back - a["p"].double()).abs()
+                assert float((err / a["p"].double().abs().clamp_min(2.0 ** -14)).max()) <= 2.0 ** -20
+                assert torch.equal(hi, (a["p"] * co._F16_WSCALE).half())
+            else:                              # 3xTF32: hi is tf32-representable, hi + lo is the parameter
+                assert torch.equal(hi + lo, a["p"])
+                assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0

@@ -41,6 +41,9 @@ GROUPS = [
      " * backward: {vfl,box,fgl_ddf}_bwd with the same description and workspace."),
     ("select.cu", "Query selection (row max + top-k) and the decoder gate",
      "DFINETransformer._select_topk dfine_decoder.py:875-910; Gate.forward dfine_decoder.py:258-271."),
+    ("io.cu", "Input preparation (uint8 -> float, resize) and detection post-processing",
+     "Torch_model._prepare_inputs / _preds_postprocess infer/torch_model.py:153-292; DFINEPostProcessor dl/export.py:20-100;\n"
+     " * multiscale collate dl/dataset.py:675-683."),
     ("matcher.cu", "Hungarian matcher (cost blocks + LSAP)",
      "HungarianMatcher.forward matcher.py:110-257 (scipy.optimize.linear_sum_assignment at 243)."),
     ("optim.cu", "Optimizer / EMA",
