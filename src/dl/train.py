@@ -34,7 +34,7 @@ DEFAULTS = {
         "base_lr": 1.5e-4, "backbone_lr": 2e-5, "betas": [0.9, 0.999], "weight_decay": 1.25e-4,
         "use_scheduler": True, "cycler_pct_start": 0.1, "amp_enabled": False, "pretrained_model_path": None,
         "label_to_name": {i: str(i) for i in range(80)}, "path_to_save": "output/b200", "ddp": {"enabled": False},
-        "synthetic_steps_per_epoch": 50, "targets_per_image": 10, "cuda_graphs": True,
+        "synthetic_steps_per_epoch": 50, "targets_per_image": 10, "cuda_graphs": True, "resume_from": None,
     },
 }
 
@@ -161,9 +161,52 @@ class Trainer:
         m = self.ema_model.model if self.ema_model is not None else self.model
         torch.save({k: v.detach().cpu().clone() for k, v in m.state_dict().items()}, self.path_to_save / name)
 
+    # ---- resume -----------------------------------------------------------------------
+    # The reference only ever writes bare state dicts (`last.pt`, `model.pt`, train.py:476-503) and cannot resume.  Those
+    # files keep their format (Torch_model / export load them); next to them `resume.pt` holds everything a restart
+    # needs: raw model weights, the EMA weights and its step counter, the optimizer in torch.optim.AdamW's own layout
+    # (optim.FusedAdamW.state_dict), the scheduler, the epoch and the generators' states.
+    def save_checkpoint(self, epoch, name="resume.pt"):
+        if not self.is_main:
+            return
+        self.path_to_save.mkdir(parents=True, exist_ok=True)
+        cpu = lambda sd: {k: (v.detach().cpu().clone() if torch.is_tensor(v) else v) for k, v in sd.items()}  # noqa: E731
+        ck = {"format": "custom_d_fine_b200.resume.v1", "epoch": epoch, "model": cpu(self.model.state_dict()),
+              "ema": cpu(self.ema_model.model.state_dict()) if self.ema_model is not None else None,
+              "ema_iter": self.step.ema_iter, "batch_idx": self.step.batch_idx,
+              "optimizer": self.optimizer.state_dict(),
+              "scheduler": self.scheduler.state_dict() if self.scheduler is not None else None,
+              "rng": {"cpu": torch.get_rng_state(),
+                      "cuda": torch.cuda.get_rng_state(self.device) if self.device.type == "cuda" else None}}
+        tmp = self.path_to_save / (name + ".tmp")
+        torch.save(ck, tmp)
+        tmp.replace(self.path_to_save / name)         # atomic: a crash while writing never corrupts the last checkpoint
+
+    def resume(self, path):
+        """Restore a `save_checkpoint` file; returns the epoch to continue from (the saved one + 1)."""
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+        assert ck.get("format") == "custom_d_fine_b200.resume.v1", "not a resume checkpoint"
+        self.model.load_state_dict(ck["model"])
+        if self.ema_model is not None and ck["ema"] is not None:
+            self.ema_model.model.load_state_dict(ck["ema"])
+        self.optimizer.load_state_dict(ck["optimizer"])
+        if self.scheduler is not None and ck["scheduler"] is not None:
+            self.scheduler.load_state_dict(ck["scheduler"])
+        self.step.ema_iter, self.step.batch_idx = ck["ema_iter"], ck["batch_idx"]
+        torch.set_rng_state(ck["rng"]["cpu"])
+        if self.device.type == "cuda" and ck["rng"]["cuda"] is not None:
+            torch.cuda.set_rng_state(ck["rng"]["cuda"], self.device)
+        if self.device.type == "cuda":
+            from custom_d_fine_b200 import cuda_ops
+            cuda_ops.weights_changed()            # re-laid weight copies / operand planes follow the loaded parameters
+            if hasattr(self.optimizer, "_register_planes"):
+                self.optimizer._register_planes()
+        self.start_epoch = int(ck["epoch"]) + 1
+        return self.start_epoch
+
     def train(self):
         history = []
-        for epoch in range(1, self.epochs + 1):
+        for epoch in range(getattr(self, "start_epoch", 1), self.epochs + 1):
             self.model.train()
             t0, n_img, losses = time.perf_counter(), 0, []
             # host->device copies of batch k+1 run on a side stream while batch k trains (train.py:558-565)
@@ -177,6 +220,7 @@ class Trainer:
             if self.is_main:
                 print(f"epoch {epoch}: loss {mean_loss:.4f}, {history[-1]['images_per_s']:.1f} img/s")
             self.save_model("last.pt")
+            self.save_checkpoint(epoch)
         return history
 
 
@@ -189,6 +233,9 @@ def main(cfg=None):
         dist_utils.init_distributed_mode()
     try:
         trainer = Trainer(cfg)
+        resume = getattr(cfg.train, "resume_from", None)
+        if resume:
+            trainer.resume(resume)
         return trainer.train()
     finally:
         if ddp:

@@ -70,6 +70,37 @@ def test_trainer_runs_the_reference_loop_on_cpu(tmp_path):
     assert set(ckpt) == set(tr.model.state_dict()), "last.pt is a bare state_dict with the reference's keys"
 
 
+def test_resume_continues_the_same_trajectory(tmp_path):
+    """2 epochs in one run == 1 epoch + checkpoint + restart + 1 epoch: model, EMA, optimizer moments, scheduler and the
+    generators all come back from `resume.pt` (the reference cannot resume; its `last.pt` format is kept beside it)."""
+    from custom_d_fine_b200 import kernels
+    from oracle.torch_ops import OracleOps
+    from src.dl.train import SyntheticLoader, Trainer, load_cfg
+
+    def make(epochs, out):
+        torch.manual_seed(0)
+        cfg = load_cfg(None, ["model_name=n", "train.device=cpu", "train.batch_size=2", "train.img_size=[320,320]",
+                              f"train.epochs={epochs}", f"train.path_to_save={out}", "train.cuda_graphs=False"])
+        return Trainer(cfg, train_loader=SyntheticLoader(2, (320, 320), steps=2, targets_per_image=3))
+
+    with kernels.use(OracleOps()):
+        full = make(2, tmp_path / "a")
+        full.train()
+        first = make(2, tmp_path / "b")
+        first.epochs = 1
+        first.train()
+        again = make(2, tmp_path / "c")
+        assert again.resume(tmp_path / "b" / "resume.pt") == 2
+        again.train()
+    for (k, a), (_, b) in zip(full.model.state_dict().items(), again.model.state_dict().items()):
+        if a.dtype.is_floating_point:
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), k
+    for (k, a), (_, b) in zip(full.ema_model.model.state_dict().items(), again.ema_model.model.state_dict().items()):
+        if a.dtype.is_floating_point:
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), ("ema", k)
+    assert full.optimizer.param_groups[3]["lr"] == again.optimizer.param_groups[3]["lr"]
+
+
 def test_go_union_fast_paths_equal_the_reference_formulation():
     """The host index planning between the two CUDA graphs of a step evaluates the reference's GO union
     (dfine_criterion.py:570-591: torch.unique(pairs, dim=0) + unstable argsort of the counts + first pair per query)

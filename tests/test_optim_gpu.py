@@ -77,3 +77,43 @@ def test_fused_adamw_ema_matches_torch(cuda_ops):
             else:                              # 3xTF32: hi is tf32-representable, hi + lo is the parameter
                 assert torch.equal(hi + lo, a["p"])
                 assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+
+
+def test_fused_adamw_state_dict_round_trip(cuda_ops):
+    """The flat-arena optimizer's checkpoint is torch.optim.AdamW's own layout: a stock AdamW resumes from it, and a fresh
+    FusedAdamW loading it continues exactly where the first one stopped (moments, step count, bias correction)."""
+    from custom_d_fine_b200.optim import FusedAdamW
+    torch.manual_seed(0)
+    base = _Toy().cuda()
+    g = torch.Generator().manual_seed(4)
+    grads = [[torch.randn(p.shape, generator=g).cuda() for p in base.parameters()] for _ in range(4)]
+
+    def run(model, opt, steps):
+        for gs in steps:
+            for p, gr in zip(model.parameters(), gs):
+                p.grad.copy_(gr)
+            opt.prepare(None)
+            opt.step()
+
+    m1 = copy.deepcopy(base)
+    o1 = FusedAdamW(_groups(m1), lr=1e-3, betas=(0.9, 0.999), weight_decay=1e-2, max_norm=0.1)
+    run(m1, o1, grads)
+    m2 = copy.deepcopy(base)
+    o2 = FusedAdamW(_groups(m2), lr=1e-3, betas=(0.9, 0.999), weight_decay=1e-2, max_norm=0.1)
+    run(m2, o2, grads[:2])
+    sd, weights = o2.state_dict(), copy.deepcopy(m2.state_dict())
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    # a stock AdamW accepts the same dict
+    m_t = copy.deepcopy(base)
+    m_t.load_state_dict(weights)
+    o_t = torch.optim.AdamW(_groups(m_t), lr=1e-3, betas=(0.9, 0.999), weight_decay=1e-2)
+    o_t.load_state_dict({k: v for k, v in sd.items() if k != "fused"})
+    assert float(o_t.state[next(iter(m_t.parameters()))]["step"]) == 2.0
+    m3 = copy.deepcopy(base)
+    m3.load_state_dict(weights)
+    o3 = FusedAdamW(_groups(m3), lr=1e-3, betas=(0.9, 0.999), weight_decay=1e-2, max_norm=0.1)
+    o3.load_state_dict(sd)
+    run(m3, o3, grads[2:])
+    torch.cuda.synchronize()
+    for (n, p), (_, q) in zip(m1.named_parameters(), m3.named_parameters()):
+        check_close(f"resumed param {n}", q, p, 1e-6)
