@@ -451,8 +451,10 @@ class DFINECriterion(nn.Module):
             masks = torch.cat([t["masks"] for t in targets])          # [sumT, H, W] (the batch shares one image size)
         return self.matcher.match_layers_raw(layers, targets), (labels, boxes, masks)
 
-    def plan(self, outputs, targets, raw, plan=None):
-        """Stage 2 (host): matcher indices -> GO union -> normalisers -> one pinned index table."""
+    def plan(self, outputs, targets, raw, plan=None, local_counts=False):
+        """Stage 2 (host): matcher indices -> GO union -> normalisers -> one pinned index table.
+        local_counts: leave this rank's raw (n_go, n_targets) in ``plan.counts``; the caller exchanges them on the
+        device (``finish_counts``) so that the host never waits for the collective."""
         main, aux, pre, enc = self._matched_layers(outputs)
         n_sets = 1 + len(aux) + 1 + len(enc)
         Q = outputs["pred_logits"].shape[1]
@@ -466,6 +468,9 @@ class DFINECriterion(nn.Module):
         go = self.go_indices_host(out_q, out_t, plan)
         n_go = plan.fill_go(go)
         counts = torch.tensor([float(n_go), float(sum(sizes))], dtype=torch.float32)
+        if local_counts:
+            plan.counts.copy_(counts)
+            return plan
         if dist_utils.is_dist_available_and_initialized():
             dev = outputs["pred_logits"].device
             c = counts.to(dev)
@@ -473,6 +478,17 @@ class DFINECriterion(nn.Module):
             counts = c.cpu()
         plan.counts.copy_(torch.clamp(counts / dist_utils.get_world_size(), min=1))
         return plan
+
+    @staticmethod
+    def finish_counts(counts_dev):
+        """Device half of the normaliser exchange (dfine_criterion.py:635-652): ONE 2-float all-reduce (the reference
+        issues two and reads both back with .item()), mean over ranks, clamp at 1 — stream-ordered, no host sync."""
+        world = dist_utils.get_world_size()
+        if world > 1:
+            torch.distributed.all_reduce(counts_dev)
+            counts_dev.div_(world)
+        counts_dev.clamp_(min=1)
+        return counts_dev
 
     # ---- layer-batched evaluation ---------------------------------------------------------------------------
     # The reference walks the heads one by one (48 loss terms for D-FINE-m, each 5-30 tiny kernels,

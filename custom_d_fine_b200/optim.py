@@ -227,13 +227,30 @@ class FusedAdamW(torch.optim.Optimizer):
             self._t = t
         self._register_planes()
 
-    def allreduce_grads(self):
-        """Average the flat gradient arenas over ranks (NCCL over NVLink; the step's only gradient collective)."""
+    def allreduce_grads(self, groups=None, stream=None):
+        """Average the flat gradient arenas over ranks (NCCL over NVLink; the step's only gradient collective).
+        ``groups``: indices of the parameter groups to reduce (default all).  ``stream``: issue the collectives on this
+        side stream after it has waited for the current one — the caller joins it before the optimizer kernels
+        (train.GraphedTrainStep reduces the encoder / decoder arenas while the backbone's backward is still running)."""
         if dist_utils.get_world_size() < 2:
             return
-        for a in self._arenas:
-            if a is not None:
-                dist_utils.allreduce_mean_(a["g"])
+        idx = range(len(self._arenas)) if groups is None else groups
+        if stream is None:
+            for i in idx:
+                if self._arenas[i] is not None:
+                    dist_utils.allreduce_mean_(self._arenas[i]["g"])
+            return
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            for i in idx:
+                if self._arenas[i] is not None:
+                    dist_utils.allreduce_mean_(self._arenas[i]["g"])
+
+    def backbone_groups(self):
+        """(backbone group indices, other group indices) by the reference's grouping (dfine.py:87-124: groups 0 / 1 hold the
+        backbone's weights / norms, 2 / 3 the encoder's and decoder's)."""
+        n = len(self._arenas)
+        return [i for i in (0, 1) if i < n], [i for i in range(2, n)]
 
     # ---- step ----------------------------------------------------------------------------------
     def prepare(self, ema_momentum=None):

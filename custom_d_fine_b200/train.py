@@ -189,18 +189,65 @@ class TrainStep:
         if step_scheduler and self.scheduler is not None:
             self.scheduler.step()
 
+    # ---- data-parallel overlap: the backward pass in two halves --------------------------------------------------
+    # The optimizer's groups 2 / 3 (encoder + decoder) have their complete gradients once the backward pass reaches
+    # the backbone's outputs; groups 0 / 1 (backbone) only at the very end.  With more than one rank the graph is cut at
+    # the backbone outputs: half 1 = losses + decoder + encoder backward, then the all-reduce of arenas 2 / 3 is
+    # issued on a communication stream and overlaps half 2 = the backbone's backward; arenas 0 / 1 follow.
+    def _split(self):
+        from . import dist as dist_utils
+        import os
+        return self.fused and dist_utils.get_world_size() > 1 and not isinstance(self.model, DDP) \
+            and hasattr(self.model, "backbone") and os.environ.get("DFINE_SPLIT_BWD", "1") != "0"
+
+    def _forward(self, inputs, targets):
+        """(model output, cut): cut = None, or (backbone outputs, their detached leaves feeding the encoder)."""
+        if not self._split():
+            return self.model(inputs, targets=targets), None
+        m = self.model
+        feats = m.backbone(inputs.permute(0, 2, 3, 1))
+        leaves = [f.detach().requires_grad_(True) for f in feats]
+        return m.decoder(m.encoder(leaves), targets), (feats, leaves)
+
+    def _comm_stream(self, device):
+        if getattr(self, "_comm", None) is None:
+            self._comm = torch.cuda.Stream(device)
+        return self._comm
+
+    def _backward_half2(self, cut):
+        feats, leaves = cut
+        keep = [(f, l.grad) for f, l in zip(feats, leaves) if l.grad is not None]
+        torch.autograd.backward([f for f, _ in keep], [g for _, g in keep])
+
     def __call__(self, inputs, targets):
         """inputs float32 [B,3,H,W] on the device; targets list of dicts (labels int64 [T], boxes [T,4])."""
         _begin_step(inputs, self._counters if self.model.training else None)
-        output = self.model(inputs, targets=targets)
+        output, cut = self._forward(inputs, targets)
         _after_forward()
         loss_dict = self.loss_fn(output, targets)
         loss = sum(loss_dict.values()) / self.accum_steps
         loss.backward()
+        step_now = (self.batch_idx + 1) % self.accum_steps == 0
+        if cut is not None:
+            from . import cuda_ops
+            bb, rest = self.optimizer.backbone_groups()
+            cuda_ops.wgrad_stream.sync_main()           # encoder / decoder weight gradients are complete
+            if step_now:
+                self.optimizer.allreduce_grads(rest, self._comm_stream(inputs.device))
+            self._backward_half2(cut)
         _end_step()
         self.batch_idx += 1
-        if self.batch_idx % self.accum_steps == 0:
-            self.optimizer_step()
+        if step_now:
+            if cut is not None:
+                bb, rest = self.optimizer.backbone_groups()
+                self._host_prepare()
+                self.optimizer.allreduce_grads(bb, self._comm_stream(inputs.device))
+                torch.cuda.current_stream().wait_stream(self._comm)
+                self._apply_grads()
+                if self.scheduler is not None:
+                    self.scheduler.step()
+            else:
+                self.optimizer_step()
         return loss.detach(), loss_dict
 
 
@@ -299,7 +346,7 @@ class GraphedTrainStep(TrainStep):
         gA = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gA, stream=self._side):
             _begin_step(g["x"], self._counters)
-            out = self.model(g["x"], targets=g["targets"])
+            out, cut = self._forward(g["x"], g["targets"])
             raw, tg = crit.match(out, g["targets"])
             _after_forward()
         gB = torch.cuda.CUDAGraph()
@@ -307,9 +354,19 @@ class GraphedTrainStep(TrainStep):
             loss_dict = crit.compute(out, tg, g["table"], g["counts"], plan)
             loss = sum(loss_dict.values())
             loss.backward()
-            _end_step()
+            if cut is None:
+                _end_step()
+            else:
+                cuda_ops.wgrad_stream.sync_main()      # (a capture must end with its forked streams joined)
             g["loss"] = loss.detach()
             g["loss_dict"] = {k: v.detach() for k, v in loss_dict.items()}
+        g["gB2"] = None
+        if cut is not None:       # second half of the backward pass: the backbone, overlapped with the first all-reduce
+            gB2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gB2, pool=gA.pool(), stream=self._side):
+                self._backward_half2(cut)
+                _end_step()
+            g["gB2"] = gB2
         gC = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gC, pool=gA.pool(), stream=self._side):
             self._apply_grads()
@@ -325,13 +382,22 @@ class GraphedTrainStep(TrainStep):
         g["gA"].replay()
         ev = g.setdefault("gap_events", (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
         ev[0].record()
-        plan = self.loss_fn.plan(g["out"], g["targets"], g["raw"], g["plan"])     # syncs on the matcher D2H
+        plan = self.loss_fn.plan(g["out"], g["targets"], g["raw"], g["plan"], local_counts=True)   # syncs on the matcher D2H
         g["table"].copy_(plan.table, non_blocking=True)
         g["counts"].copy_(plan.counts, non_blocking=True)
+        self.loss_fn.finish_counts(g["counts"])          # 2-float all-reduce + clamp on the device: no host wait
         ev[1].record()                                   # ev[0] -> ev[1] = device idle time while the host plans
         self._last_gap = ev
         g["gB"].replay()
-        self.optimizer.allreduce_grads()
+        if g["gB2"] is None:
+            self.optimizer.allreduce_grads()
+        else:
+            bb, rest = self.optimizer.backbone_groups()
+            comm = self._comm_stream(inputs.device)
+            self.optimizer.allreduce_grads(rest, comm)   # encoder / decoder arenas: overlaps the backbone's backward
+            g["gB2"].replay()
+            self.optimizer.allreduce_grads(bb, comm)
+            torch.cuda.current_stream().wait_stream(comm)
         g["gC"].replay()
         if self.scheduler is not None:
             self.scheduler.step()

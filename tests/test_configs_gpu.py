@@ -82,8 +82,9 @@ def step_both(oracle_ops, size, hw, B, seg, mode, seed=11, T=(10, 7, 0, 3), pin_
 
 
 def check_selection(tag, picked):
-    """The CUDA path's own top-k against the oracle's: equal as sets except for candidates whose score is within 1e-4
-    (relative to the score range) of the rank-k score — near-ties that any fp32 re-association may order either way."""
+    """The CUDA path's own top-k against the oracle's: equal as sets except for candidates whose distance to the rank-k
+    score (relative to the score range) is within the encoder scores' own rounding error — near-ties that any
+    re-association of the fp32 sums may order either way."""
     a, b = picked["cpu"], picked["cuda"].cpu()
     sc, sg = picked["cpu_scores"], picked["cuda_scores"]
     worst, n_swapped = 0.0, 0
@@ -97,7 +98,7 @@ def check_selection(tag, picked):
     err = float((sg - sc).abs().max() / sc.abs().max())
     print(f"\n[{tag}] query selection: encoder scores max err {err:.2e}; candidates exchanged at the rank-k boundary (max per "
           f"image) {n_swapped}, their distance to the rank-k score {worst:.2e} of the score range")
-    assert worst <= 1e-4, (tag, worst)
+    assert worst <= max(1e-4, 2 * err), (tag, worst, err)      # exchanged candidates tie with rank k within the scores' own error
     assert n_swapped <= 0.05 * a.shape[1], (tag, n_swapped)
 
 

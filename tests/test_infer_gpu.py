@@ -16,8 +16,8 @@ pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).resolve().parent / "golden"
 
 
-@pytest.mark.parametrize("case", ["detect", "segment"])
-@pytest.mark.parametrize("deploy", [False, True])
+@pytest.mark.parametrize("case", [0, 1], ids=["detect", "segment"])
+@pytest.mark.parametrize("deploy", [False, True], ids=["eval", "deploy"])
 def test_eval_and_deploy_outputs_match_reference_fixture(cuda_ops, case, deploy):
     fix = torch.load(GOLD / "eval_s_320.pt", weights_only=False)[case]
     torch.manual_seed(0)
@@ -38,8 +38,10 @@ def test_eval_and_deploy_outputs_match_reference_fixture(cuda_ops, case, deploy)
     check_rows_up_to_order(f"{case}/deploy={deploy}: pred_logits|pred_boxes", both, both_ref, 1e-3, 1.0)
     if fix["seg"]:
         # masks of the first queries, paired through the row order of the logits
-        d = torch.cdist(both[0].double().cpu(), both_ref[0].double(), p=float("inf")).argmin(0)[:6]
-        check_close("pred_masks (sigmoid)", out["pred_masks"][0, d].cpu(), fix["pred_masks_q0_6"][0], 2e-3)
+        ref_m = fix["pred_masks_q0_6"]                                     # [B, 6, Hm, Wm]: the reference's first six queries
+        for b in range(ref_m.shape[0]):
+            d = torch.cdist(both[b].double().cpu(), both_ref[b].double(), p=float("inf")).argmin(0)[:6]
+            check_close("pred_masks (sigmoid)", out["pred_masks"][b, d].cpu(), ref_m[b], 2e-3)
 
 
 def test_postprocessor_matches_reference_arithmetic(cuda_ops, oracle_ops):
@@ -51,10 +53,17 @@ def test_postprocessor_matches_reference_arithmetic(cuda_ops, oracle_ops):
     with kernels.use(oracle_ops):
         want = DFINEPostProcessor(80)({"pred_logits": logits, "pred_boxes": boxes, "pred_masks": masks}, 640, 480)
     got = DFINEPostProcessor(80)({"pred_logits": logits.cuda(), "pred_boxes": boxes.cuda(), "pred_masks": masks.cuda()}, 640, 480)
-    assert torch.equal(got[0].cpu(), want[0]), "labels"
-    assert torch.equal(got[1].cpu(), want[1]), "boxes (integer-rounded pixels)"
+    # equal scores (distinct logits may share one fp32 sigmoid value) may come in either order: compare the sorted scores,
+    # and labels / boxes / masks position by position wherever the score is unique in its row
     check_close("scores", got[2].cpu(), want[2], 1e-6)
-    assert torch.equal(got[3].cpu(), want[3]), "masks"
+    s = want[2]
+    uniq = torch.ones_like(s, dtype=torch.bool)
+    uniq[:, 1:] &= s[:, 1:] != s[:, :-1]
+    uniq[:, :-1] &= s[:, :-1] != s[:, 1:]
+    assert float(uniq.float().mean()) > 0.9
+    assert torch.equal(got[0].cpu()[uniq], want[0][uniq]), "labels"
+    assert torch.equal(got[1].cpu()[uniq], want[1][uniq]), "boxes (integer-rounded pixels)"
+    assert torch.equal(got[3].cpu()[uniq], want[3][uniq]), "masks"
 
 
 @pytest.mark.parametrize("B,L,C,k", [(3, 8400, 80, 300), (2, 33600, 80, 300), (2, 1000, 1, 300), (1, 300, 5, 300)])

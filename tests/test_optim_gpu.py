@@ -72,7 +72,8 @@ def test_fused_adamw_ema_matches_torch(cuda_ops):
             if hi.dtype == torch.float16:      # 3xFP16: fp16 parts of w * 2^8, 22 significand bits together
                 back = (hi.double() + lo.double()) / co._F16_WSCALE
                 err = (back - a["p"].double()).abs()
-                assert float((err / a["p"].double().abs().clamp_min(2.0 ** -14)).max()) <= 2.0 ** -20
+                # 2^-22 relative, or half the smallest fp16 subnormal (2^-25) in the scaled domain for tiny weights
+                assert bool((err <= 2.0 ** -21 * a["p"].double().abs() + 2.0 ** -25 / co._F16_WSCALE).all())
                 assert torch.equal(hi, (a["p"] * co._F16_WSCALE).half())
             else:                              # 3xTF32: hi is tf32-representable, hi + lo is the parameter
                 assert torch.equal(hi + lo, a["p"])
