@@ -296,9 +296,10 @@ class GraphedTrainStep(TrainStep):
                 and next(self.model.parameters()).is_cuda)
 
     def __call__(self, inputs, targets):
-        if not self._can_graph() or any(t.get("masks") is not None for t in targets):
-            return super().__call__(inputs, targets)        # (segmentation batches run the eager step for now)
-        key = (tuple(inputs.shape), tuple(int(t["labels"].shape[0]) for t in targets))
+        if not self._can_graph():
+            return super().__call__(inputs, targets)
+        key = (tuple(inputs.shape), tuple(int(t["labels"].shape[0]) for t in targets),
+               tuple(tuple(t["masks"].shape) if t.get("masks") is not None else None for t in targets))
         g = self._graphs.get(key)
         if g is not None:
             self._graphs.move_to_end(key)
@@ -333,7 +334,7 @@ class GraphedTrainStep(TrainStep):
         g = {}
         dev = inputs.device
         g["x"] = inputs.clone()
-        g["targets"] = [{"labels": t["labels"].clone(), "boxes": t["boxes"].clone()} for t in targets]
+        g["targets"] = [{k: t[k].clone() for k in ("labels", "boxes", "masks") if t.get(k) is not None} for t in targets]
         crit = self.loss_fn
         # capture records launches without running them, so the index table used while capturing graph B is
         # the (same-shaped) plan of the last eager step of this key; replays refill it before graph B runs
@@ -376,8 +377,8 @@ class GraphedTrainStep(TrainStep):
     def _replay(self, g, inputs, targets):
         g["x"].copy_(inputs, non_blocking=True)
         for s, t in zip(g["targets"], targets):
-            s["labels"].copy_(t["labels"], non_blocking=True)
-            s["boxes"].copy_(t["boxes"], non_blocking=True)
+            for k, v in s.items():
+                v.copy_(t[k], non_blocking=True)
         self._host_prepare()
         g["gA"].replay()
         ev = g.setdefault("gap_events", (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))

@@ -70,3 +70,30 @@ def test_segmentation_step_matches_cpu_oracle(cuda_ops, oracle_ops):
     check_rows_up_to_order("seg: pred_logits|pred_boxes", both, both_ref, 1e-3, 1.0)
     d = (o1["dn_pred_masks"].cpu() - o0["dn_pred_masks"]).abs().max() / o0["dn_pred_masks"].abs().max()
     assert float(d) <= 1e-3, float(d)
+
+
+def test_segmentation_graph_replay_matches_eager(cuda_ops):
+    """Segmentation batches (mask matching cost, mask losses, MaskDecoder) replayed as CUDA graphs against the eager step:
+    same weights, batch and generator state -> the loss trajectories agree (atomics-order noise only)."""
+    from custom_d_fine_b200.model import build_optimizer
+    from custom_d_fine_b200.train import GraphedTrainStep, ModelEMA, TrainStep
+    x, targets = synthetic_batch(2, 320, 320, seed=5, T=(6, 3))
+    for t in targets:
+        t["masks"] = rect_masks(t["boxes"], 320, 320)
+    x = x.cuda()
+    targets = [{k: v.cuda() for k, v in t.items()} for t in targets]
+    traj = {}
+    for name, cls in (("eager", TrainStep), ("graph", GraphedTrainStep)):
+        torch.manual_seed(0)
+        model = build_model("s", 80, True, "cuda", img_size=(320, 320))
+        seeded_fill(model, 3)
+        model.train()
+        opt = build_optimizer(model, lr=1e-4, backbone_lr=1e-5, betas=(0.9, 0.999), weight_decay=1e-4, base_lr=1e-4)
+        step = cls(model, build_loss("s", 80, 0.0, True), opt, ema=ModelEMA(model, 0.9998), clip_max_norm=0.1)
+        torch.manual_seed(11)
+        torch.cuda.manual_seed(11)
+        traj[name] = [float(step(x, targets)[0]) for _ in range(7)]
+        if name == "graph":
+            assert step._graphs, "no CUDA graph was captured for the segmentation batch"
+    for a, b in zip(traj["eager"], traj["graph"]):
+        assert abs(a - b) <= 2e-2 * abs(a), traj
