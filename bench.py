@@ -218,13 +218,33 @@ def run_ours(args):
             for _ in range(self.n):
                 yield hx, to_targets(hl, hb, hm), None
 
+    e2e_walls = []
+
     def run_e2e(n):
         from custom_d_fine_b200.train import DevicePrefetcher
         last = None
+        t_prev = time.perf_counter()
         for x, tg, _ in DevicePrefetcher(HostBatches(n), device):
             loss, _ = step(x, tg)
             last = float(loss.item())          # D2H read of the step's result, every step
+            t_now = time.perf_counter()
+            e2e_walls.append((t_now - t_prev) * 1e3)
+            t_prev = t_now
         return last
+
+    def h2d_probe():
+        """Pinned host -> device bandwidth of this box for the step's image batch (context for the e2e number)."""
+        dst = torch.empty_like(dx)
+        torch.cuda.synchronize()
+        best = 0.0
+        for _ in range(3):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            dst.copy_(hx, non_blocking=True)
+            e.record()
+            torch.cuda.synchronize()
+            best = max(best, hx.numel() * 4 / (s.elapsed_time(e) * 1e-3) / 1e9)
+        return best
 
     graphed = hasattr(step, "_graphs")
     n_warm = max(args.warmup, 3) + (step.eager_steps + 1 if graphed else 0)   # + eager steps and the capture step
@@ -278,7 +298,9 @@ def run_ours(args):
             if split[name]["tensor_bound"]:
                 split[name]["tensor_bound"]["frac"] = round(split[name]["tensor_bound"]["TFLOP/s"] / tf32_peak, 4)
     run_e2e(2)
+    e2e_walls.clear()
     ms_e2e = timed(lambda: run_e2e(args.steps), 1)
+    h2d_gbs = h2d_probe()
     mode = "cuda-graph replay (3 graphs/step)" if graphed and step._graphs else "eager launches"
     clocks = sampler.stop() if rank == 0 else None
 
@@ -335,7 +357,8 @@ def run_ours(args):
                    "l2": "per-step working set (activations + grads > 10 GB) exceeds the 126 MB L2"},
         "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 2), "unit": "images/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": int(hx.numel() * 4 + hl.numel() * 8 + hb.numel() * 4 + (hm.numel() if SEG else 0)),
-                "d2h_bytes_per_step": 4},
+                "d2h_bytes_per_step": 4, "h2d_pinned_GB/s": round(h2d_gbs, 1),
+                "step_wall_ms": [round(v, 1) for v in e2e_walls]},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
     }
     if graphed and step.host_gap_ms() is not None:
