@@ -328,7 +328,7 @@ class DFINECriterion(nn.Module):
             losses["loss_ddf"] = torch.where(identical, pred_all.sum() * 0, ddf)
         return losses
 
-    def loss_masks(self, out, S, tg, num_boxes):
+    def loss_masks(self, out, S, tg, num_boxes, src=None):
         """Cropped BCE + cropped Dice of the matched mask logits against the GT masks resized to the prediction size
         (dfine_criterion.py:504-556 with 239-305, 335-386, 404-450): both are evaluated inside the GT box only, the BCE sum
         normalised by the box area, then averaged over the matched instances (NOT divided by num_boxes)."""
@@ -340,7 +340,12 @@ class DFINECriterion(nn.Module):
             zero = pm.sum() * 0
             return {"loss_mask_bce": zero, "loss_mask_dice": zero}
         assert S.v is None, "per-layer / denoising sets are never padded"
-        pred = pm.reshape(B * Q, Hm, Wm).index_select(0, S.b * Q + S.q)           # [M, Hm, Wm]
+        if src is not None and pm.is_cuda and hasattr(K, "mask_logits_at"):
+            # matched masks straight from the mask embeddings (src = (embed [B,Q,C], feat [B,Hm,Wm,C], pairs per image)): the
+            # [B,Q,Hm,Wm] logits of the unmatched queries stay out of the autograd graph
+            pred = K.mask_logits_at(src[0], src[1], S.b, S.q, src[2])
+        else:
+            pred = pm.reshape(B * Q, Hm, Wm).index_select(0, S.b * Q + S.q)       # [M, Hm, Wm]
         key = (Hm, Wm, tg[2].data_ptr())
         if getattr(self, "_mask_cache", (None,))[0] != key:          # every GT mask resized once per step
             g = tg[2].unsqueeze(1).float()
@@ -654,7 +659,15 @@ class DFINECriterion(nn.Module):
             return (_scalars(vfl_ * W["loss_vfl"]), _scalars(l1_ * W["loss_bbox"]), _scalars(gi_ * W["loss_giou"]),
                     _scalars(fgl_ * W["loss_fgl"]), _scalars(ddf_ * W["loss_ddf"]), ddf_)
 
-        def put(suffix, k, lay=None, with_ddf=False, mask_out=None, mask_set=None, mask_num=None):
+        msrc = outputs["_stacked"].get("mask_src") if with_masks else None
+
+        def src_of(group, i, per_image):
+            if msrc is None:
+                return None
+            embs = msrc["emb"] if group == "A" else msrc["dn_emb"]
+            return (embs[i], msrc["feat"], per_image) if i < len(embs) else None
+
+        def put(suffix, k, lay=None, with_ddf=False, mask_out=None, mask_set=None, mask_num=None, mask_src=None):
             losses["loss_vfl" + suffix] = fam[0][k]
             losses["loss_bbox" + suffix] = fam[1][k]
             losses["loss_giou" + suffix] = fam[2][k]
@@ -663,7 +676,7 @@ class DFINECriterion(nn.Module):
                 if with_ddf:
                     losses["loss_ddf" + suffix] = fam[4][lay] if lay < len(fam[4]) else fam[5].sum() * 0
             if with_masks and mask_out is not None and "pred_masks" in mask_out:
-                for kk, v in self.loss_masks(mask_out, mask_set, tg, mask_num).items():
+                for kk, v in self.loss_masks(mask_out, mask_set, tg, mask_num, mask_src).items():
                     if kk in W:
                         losses[kk + suffix] = torch.nan_to_num(v * W[kk], nan=0.0)
 
@@ -671,9 +684,10 @@ class DFINECriterion(nn.Module):
         sets = [_Set(table, *plan.set_slice(k), Q, False) for k in range(plan.n_sets)] if with_masks else [None] * plan.n_sets
         aux = outputs["aux_outputs"]
         fam = weighted(*A)
-        put("", 0, L - 1, mask_out=outputs, mask_set=sets[0], mask_num=nb)
+        put("", 0, L - 1, mask_out=outputs, mask_set=sets[0], mask_num=nb, mask_src=src_of("A", L - 1, plan.per_img))
         for i in range(L - 1):
-            put(f"_aux_{i}", 1 + i, i, True, mask_out=aux[i] if i < len(aux) else None, mask_set=sets[1 + i], mask_num=nb)
+            put(f"_aux_{i}", 1 + i, i, True, mask_out=aux[i] if i < len(aux) else None, mask_set=sets[1 + i], mask_num=nb,
+                mask_src=src_of("A", i, plan.per_img))
         put("_pre", L)
         put("_enc_0", L + 1)
         if DN is not None:
@@ -682,10 +696,12 @@ class DFINECriterion(nn.Module):
             s_dn = _Set(table, *plan.set_slice("dn"), Q, False) if with_masks else None
             dn_num = nb * meta["dn_num_group"]
             dn_out = outputs["dn_outputs"]
+            dn_per = [s * meta["dn_num_group"] for s in plan.sizes]
             for i in range(len(dn_out)):
-                put(f"_dn_{i}", i, i, True, mask_out=dn_out[i], mask_set=s_dn, mask_num=dn_num)
+                put(f"_dn_{i}", i, i, True, mask_out=dn_out[i], mask_set=s_dn, mask_num=dn_num, mask_src=src_of("DN", i, dn_per))
             if with_masks and "dn_pred_masks" in outputs:      # final denoising layer's masks (dfine_criterion.py:756-767)
-                for kk, v in self.loss_masks({"pred_masks": outputs["dn_pred_masks"]}, s_dn, tg, dn_num).items():
+                for kk, v in self.loss_masks({"pred_masks": outputs["dn_pred_masks"]}, s_dn, tg, dn_num,
+                                             src_of("DN", L - 1, dn_per)).items():
                     if kk in W:
                         losses[kk + "_dn_final"] = torch.nan_to_num(v * W[kk], nan=0.0)
             put("_dn_pre", L)

@@ -235,6 +235,8 @@ struct FwdParams {
     int wk2[MAX_TAPS];        // hybrid mode: first weight column of tap t in the tap-padded bf16 planes
     int half16;               // 16-bit plane modes (X3 = 2): 0 = bf16 planes (3xBF16), 1 = fp16 planes (3xFP16)
     float out_scale;          // accumulator scale applied first in the epilogue (3xFP16 weights are stored x 2^8)
+    int w_row_off, w_k_off;   // per-image weights ("grouped" launches: the mask product): image i reads weight rows
+                              // [n0 + i*w_row_off, ...) and weight columns [k + i*w_k_off, ...) of one stacked matrix
     int lab;                  // deploy-mode epilogue: y = lab_s * act(acc + bias) + lab_b (LearnableAffineBlock, hgnetv2.py:25-32)
     float lab_s, lab_b;
     const float* res;         // optional tensor added to the output in the epilogue (same pixel geometry as y,
@@ -528,6 +530,7 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                 const int mt = t / ts.n_tiles, n0 = (t % ts.n_tiles) * BN;
                 const int img = mt / tiles_per_img, tt = mt % tiles_per_img;
                 const int h0 = (tt / p.tiles_w) * p.TH, w0 = (tt % p.tiles_w) * p.TW;
+                const int wn_img = img * p.w_row_off, wk_img = img * p.w_k_off;
                 for (int kb = 0; kb < num_k; ++kb, ++g) {
                     const int s = g % STAGES, ph = (g / STAGES) & 1;
                     mbar_wait(&sm.empty[s], ph ^ 1);
@@ -546,13 +549,13 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                     tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 * p.in_stride + p.dw[tap],
                                 h0 * p.in_stride + p.dh[tap], img);
                     if (X3 == 3) {       // tf32 hi plane (fp32 map) + the two bf16 planes (one 3-D box, tap-padded K)
-                        tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
-                        tma_load_3d(sm.b[s] + Smem::B_PLANE, &map_wlo, &sm.full[s], p.wk2[tap] + c0, n0, 0);
+                        tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0 + wk_img, n0 + wn_img);
+                        tma_load_3d(sm.b[s] + Smem::B_PLANE, &map_wlo, &sm.full[s], p.wk2[tap] + c0 + wk_img, n0 + wn_img, 0);
                     } else if (X3 == 2 || (X3 && p.w_planes)) {   // hi and lo weight planes are adjacent in memory: one 3-D box
-                        tma_load_3d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0, n0, 0);
+                        tma_load_3d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0 + wk_img, n0 + wn_img, 0);
                     } else {
-                        tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
-                        if (X3) tma_load_2d(sm.b[s] + Smem::B_PLANE, &map_wlo, &sm.full[s], p.wk[tap] + c0, n0);
+                        tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0 + wk_img, n0 + wn_img);
+                        if (X3) tma_load_2d(sm.b[s] + Smem::B_PLANE, &map_wlo, &sm.full[s], p.wk[tap] + c0 + wk_img, n0 + wn_img);
                     }
                     }
                     sm.produced = g + 1;
@@ -1208,7 +1211,7 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
                  int YH, int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
                  const int* taps, long ldw, int act, void* stream, long ldw16 = 0, const float* res = nullptr,
                  long ldres = 0, int half16 = 0, float out_scale = 1.f, long plane_stride16 = 0, int lab = 0,
-                 float lab_s = 1.f, float lab_b = 0.f) {
+                 float lab_s = 1.f, float lab_b = 0.f, int w_rows = 0, int w_row_off = 0, int w_k_off = 0) {
     DFINE_REQUIRE(n_taps >= 1 && n_taps <= MAX_TAPS, "conv_tc: %d taps unsupported", n_taps);
     DFINE_REQUIRE(in_stride == 1 || in_stride == 2, "conv_tc: input stride %d unsupported", in_stride);
     DFINE_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldw % ((w_bf16 && !w) ? 8 : 4) == 0 &&
@@ -1234,6 +1237,8 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
     p.res = res; p.ldres = ldres;
     p.half16 = half16; p.out_scale = out_scale;
     p.lab = lab; p.lab_s = lab_s; p.lab_b = lab_b;
+    p.w_row_off = w_row_off; p.w_k_off = w_k_off;
+    const int WR = w_rows > 0 ? w_rows : Cout;        // rows of the weight matrix the maps cover (stacked per-image weights)
     p.in_stride = in_stride; p.Cin = Cin;
     p.OH = OH; p.OW = OW; p.N = Cout; p.ldy = ldy; p.act = act;
     p.YH = YH; p.YW = YW; p.osy = osy; p.osx = osx; p.ooy = ooy; p.oox = oox;
@@ -1267,9 +1272,9 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
             rc = make_map2(&mwlo, w, ldw, Cout, ldw, BK, bn, "conv_tc(w_hi)");     // placeholder var; swapped below
             if (rc) return rc;
         }
-        cuuint64_t dims[3] = {(cuuint64_t)ld16, (cuuint64_t)Cout, 2};
+        cuuint64_t dims[3] = {(cuuint64_t)ld16, (cuuint64_t)WR, 2};
         // (the two planes of a weight are adjacent, or sit in two arenas `plane_stride16` elements apart)
-        const cuuint64_t pstride = plane_stride16 > 0 ? (cuuint64_t)plane_stride16 * 2 : (cuuint64_t)ld16 * 2 * Cout;
+        const cuuint64_t pstride = plane_stride16 > 0 ? (cuuint64_t)plane_stride16 * 2 : (cuuint64_t)ld16 * 2 * WR;
         DFINE_REQUIRE(pstride % 16 == 0, "conv_tc: 16-bit plane stride %ld must be a multiple of 8 elements", plane_stride16);
         cuuint64_t strides[2] = {(cuuint64_t)ld16 * 2, pstride};
         cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)bn, 2};
@@ -1302,7 +1307,7 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
     // N tile: one tile covers Cout when it can (the A patch is then read exactly once); 256-wide tiles only on
     // the persistent plain-tf32 kernel (its smem ring has room for 48 KB stages)
     const int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : ((Cout <= 128 || w_lo || !persist_bn) ? 128 : 256));
-    rc = make_map2(&mw, w, ldw, Cout, ldw, BK, bn, "conv_tc(w)");
+    rc = make_map2(&mw, w, ldw, WR, ldw, BK, bn, "conv_tc(w)");
     if (rc) return rc;
     mwlo = mw;
     p.w_planes = 0;
@@ -1356,14 +1361,19 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
 }
 }  // namespace
 
+// Per-image weights ("grouped" launch, the segmentation head's mask product): `w` stacks the images' matrices — w_rows
+// total rows; image i uses rows [i*w_row_off, i*w_row_off + Cout) and columns [i*w_k_off, ...) — 0 / 0 / 0 = one shared weight.
 // `res` (optional, pixel stride ldres, same pixel geometry as y): y = act(conv + bias) + res — the data-gradient
 // launches use it to fold the gradient-accumulation add of a tensor with two consumers into the epilogue.
 DFINE_API int dfine_conv_tc(const float* x, const float* w, const float* w_lo, const float* bias, float* y,
                             double* stats, int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy,
                             int YH, int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
-                            const int* taps, long ldw, int act, const float* res, long ldres, void* stream) {
+                            const int* taps, long ldw, int act, const float* res, long ldres, int w_rows,
+                            int w_row_off, int w_k_off, void* stream) {
+    DFINE_REQUIRE(w_lo == nullptr || (w_row_off == 0 && w_k_off == 0), "conv_tc: per-image weights are not wired for 3xTF32");
     return conv_tc_impl(x, w, w_lo, nullptr, bias, y, stats, B, H, W, Cin, ldx, OH, OW, Cout, ldy, YH, YW, osy, osx, ooy,
-                        oox, in_stride, n_taps, taps, ldw, act, stream, 0, res, ldres);
+                        oox, in_stride, n_taps, taps, ldw, act, stream, 0, res, ldres, 0, 1.f, 0, 0, 1.f, 0.f, w_rows,
+                        w_row_off, w_k_off);
 }
 
 // The same contract with error-compensated 3xBF16 operands (see PersistSmem): `w_planes` = the two bf16 planes
@@ -1389,11 +1399,11 @@ DFINE_API int dfine_conv_tc_f16x3(const float* x, const void* w_planes, const fl
                                   int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy, int YH,
                                   int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
                                   const int* taps, long ldw, int act, float out_scale, long plane_stride,
-                                  int lab, float lab_scale, float lab_bias, void* stream) {
+                                  int lab, float lab_scale, float lab_bias, int w_rows, int w_row_off, void* stream) {
     DFINE_REQUIRE(w_planes != nullptr, "conv_tc_f16x3: null weight planes");
     return conv_tc_impl(x, nullptr, nullptr, w_planes, bias, y, stats, B, H, W, Cin, ldx, OH, OW, Cout, ldy, YH, YW, osy,
                         osx, ooy, oox, in_stride, n_taps, taps, ldw, act, stream, 0, nullptr, 0, 1, out_scale, plane_stride,
-                        lab, lab_scale, lab_bias);
+                        lab, lab_scale, lab_bias, w_rows, w_row_off, 0);
 }
 
 // Hybrid operands (see PersistSmem, X3 = 3): a_hi*w_hi on kind::tf32, the cross terms on bf16 copies.  `w_hi` = the

@@ -328,7 +328,8 @@ def _taps(key, make):
 
 
 def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, YH, YW, os_, oo, in_stride, taps, act,
-               stats, what, bf16_planes=None, res=None, ldres=0, plane_stride=0, lab=None):
+               stats, what, bf16_planes=None, res=None, ldres=0, plane_stride=0, lab=None, grouped=(0, 0, 0)):
+    """grouped = (total weight rows, per-image row offset, per-image column offset): per-image weights (the mask product)."""
     arr, n = taps
     # algorithmic bytes (SURVEY §8d): input pixels + output pixels + weights, each touched once, fp32
     nbytes = 4 * (B * min(H * W, OH * OW * in_stride * in_stride) * Cin + B * OH * OW * Cout + Cout * n * Cin)
@@ -344,7 +345,7 @@ def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, Y
                                              oo[1], in_stride, n, arr, c_long(bf16_planes.shape[-1]), act,
                                              c_float(1.0 / _F16_WSCALE), c_long(plane_stride), 0 if lab is None else 1,
                                              c_float(1.0 if lab is None else lab[0]), c_float(0.0 if lab is None else lab[1]),
-                                             _stream()), what)
+                                             grouped[0], grouped[1], _stream()), what)
         elif bf16_planes is not None:
             _check(lib().dfine_conv_tc_bf16x3(_p(x), _p(bf16_planes), _p(bias), _p(y), _p(stats), B, H, W, Cin,
                                               c_long(ldx), OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0],
@@ -353,7 +354,8 @@ def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, Y
         else:
             _check(lib().dfine_conv_tc(_p(x), _p(w), _p(w_lo), _p(bias), _p(y), _p(stats), B, H, W, Cin, c_long(ldx),
                                        OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0], oo[1], in_stride, n,
-                                       arr, c_long(ldw), act, _p(res), c_long(ldres), _stream()), what)
+                                       arr, c_long(ldw), act, _p(res), c_long(ldres), grouped[0], grouped[1], grouped[2],
+                                       _stream()), what)
 
 
 def _split_tf32(w2d):
@@ -1104,6 +1106,112 @@ class _Criterion(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+# segmentation head: GroupNorm(+ReLU), bilinear resize, mask product
+# ------------------------------------------------------------------------------------------------
+class _GroupNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, groups, eps, relu):
+        _req_cuda(x, w, b)
+        x = x.contiguous()
+        B, H, W, C = x.shape
+        y = torch.empty_like(x)
+        stats = zero_pool.take(2 * B * groups, x.device)
+        mean = torch.empty(B * groups, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(B * groups, device=x.device, dtype=torch.float32)
+        wc, bc = w.detach().contiguous(), b.detach().contiguous()
+        _check(lib().dfine_groupnorm_fwd(_p(x), _p(wc), _p(bc), _p(y), _p(stats), _p(mean), _p(rstd), B, c_long(H * W), C,
+                                         groups, c_float(eps), 1 if relu else 0, _stream()), "groupnorm_fwd")
+        ctx.save_for_backward(x, w, b, mean, rstd)
+        ctx.meta = (groups, relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, b, mean, rstd = ctx.saved_tensors
+        groups, relu = ctx.meta
+        B, H, W, C = x.shape
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        gw, gb = _grad_dst(w, "flat"), _grad_dst(b, "flat")
+        direct = gw is not None and gb is not None
+        if not direct:
+            gw, gb = torch.zeros(C, device=x.device), torch.zeros(C, device=x.device)
+        red = zero_pool.take(2 * B * groups, x.device)
+        _check(lib().dfine_groupnorm_bwd(_p(dy), _p(x), _p(w.detach().contiguous()), _p(b.detach().contiguous()), _p(mean),
+                                         _p(rstd), _p(dx), _p(gw), _p(gb), _p(red), B, c_long(H * W), C, groups,
+                                         1 if relu else 0, _stream()), "groupnorm_bwd")
+        return dx, None if direct else gw, None if direct else gb, None, None, None
+
+
+class _ResizeBilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size):
+        _req_cuda(x)
+        x = x.contiguous()
+        B, Hs, Ws, C = x.shape
+        H, W = size
+        y = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
+        _check(lib().dfine_resize_bilinear_f32(_p(x), _p(y), B, Hs, Ws, H, W, C, _stream()), "resize_bilinear_f32")
+        ctx.shape = (B, Hs, Ws, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, Hs, Ws, C, H, W = ctx.shape
+        dy = dy.contiguous()
+        dx = torch.empty((B, Hs, Ws, C), device=dy.device, dtype=torch.float32)
+        _check(lib().dfine_resize_bilinear_bwd(_p(dy), _p(dx), B, Hs, Ws, H, W, C, _stream()), "resize_bilinear_bwd")
+        return dx, None
+
+
+class _MaskDot(torch.autograd.Function):
+    """out[b, h, w, q] = sum_c feat[b, h, w, c] * embed[b, q, c]: one tcgen05 implicit-GEMM launch over all images with
+    per-image weights (the embeddings of image b are rows [b*Q, (b+1)*Q) of one stacked weight matrix)."""
+
+    @staticmethod
+    def forward(ctx, embed, feat):
+        _req_cuda(embed, feat)
+        embed, feat = embed.contiguous(), feat.contiguous()
+        B, Q, C = embed.shape
+        _, H, W, _ = feat.shape
+        assert Q % 4 == 0 and C % 8 == 0, "mask product: Q % 4 and C % 8"
+        out = torch.empty((B, H, W, Q), device=feat.device, dtype=torch.float32)
+        e2 = embed.reshape(B * Q, C)
+        taps = _taps(("f", 1, 0, 0, C), lambda: [(0, 0, 0)])
+        if _MODE == "hf3":
+            planes = _split_f16(e2, 1, C)
+            _tc_launch(feat, C, H, W, C, None, None, C, None, out, Q, B, H, W, Q, H, W, (1, 1), (0, 0), 1, taps, 0, None,
+                       "mask_dot", planes, grouped=(B * Q, Q, 0))
+        else:
+            _tc_launch(feat, C, H, W, C, e2, None, C, None, out, Q, B, H, W, Q, H, W, (1, 1), (0, 0), 1, taps, 0, None,
+                       "mask_dot", grouped=(B * Q, Q, 0))
+        ctx.save_for_backward(embed, feat)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        embed, feat = ctx.saved_tensors
+        B, Q, C = embed.shape
+        _, H, W, _ = feat.shape
+        dout = dout.contiguous()
+        dfeat = dembed = None
+        if ctx.needs_input_grad[1]:
+            # dfeat[b] = dout[b] [HW, Q] x embed[b] [Q, C]: the same kernel on dout with the stacked transposed embeddings
+            # [C, B*Q]; image b reads weight columns [b*Q, (b+1)*Q)
+            wd = embed.reshape(B * Q, C).t().contiguous()
+            dfeat = torch.empty_like(feat)
+            taps = _taps(("f", 1, 0, 0, Q), lambda: [(0, 0, 0)])
+            _tc_launch(dout, Q, H, W, Q, wd, None, B * Q, None, dfeat, C, B, H, W, C, H, W, (1, 1), (0, 0), 1, taps, 0, None,
+                       "mask_dot_dgrad", grouped=(C, 0, Q))
+        if ctx.needs_input_grad[0]:
+            dembed = torch.zeros((B, Q, 1, 1, C), device=feat.device, dtype=torch.float32)
+            for b in range(B):
+                _conv_wgrad(dout[b:b + 1], Q, feat[b:b + 1], C, (1, H, W, C, H, W, Q, 1, 1, (0, 0, 0, 0)), dembed[b])
+            dembed = dembed.reshape(B, Q, C)
+        return dembed, dfeat
+
+
+# ------------------------------------------------------------------------------------------------
 # decoder gate: sigmoid(g[:, :D]) * x1 + sigmoid(g[:, D:]) * x2
 # ------------------------------------------------------------------------------------------------
 class _GateMix(torch.autograd.Function):
@@ -1353,22 +1461,61 @@ class CudaOps:
         return _Conv.apply(x, w, int(stride), tuple(int(v) for v in pad))
 
     def group_norm(self, x, groups, w, b, eps=1e-5, act=None):
-        _req_cuda(x)
-        y = torch.nn.functional.group_norm(x.permute(0, 3, 1, 2), groups, w, b, eps).permute(0, 2, 3, 1)
-        if act == "relu":
-            y = torch.relu(y)
-        elif act is not None:
+        if act not in (None, "relu"):
             raise NotImplementedError(act)
-        return y.contiguous()
+        return _GroupNorm.apply(x, w, b, int(groups), float(eps), act == "relu")
 
     def resize_bilinear(self, x, size):
-        _req_cuda(x)
-        return torch.nn.functional.interpolate(x.permute(0, 3, 1, 2), size=tuple(size), mode="bilinear",
-                                               align_corners=False).permute(0, 2, 3, 1).contiguous()
+        return _ResizeBilinear.apply(x, (int(size[0]), int(size[1])))
 
     def mask_dot(self, embed, feat_nhwc):
-        _req_cuda(embed, feat_nhwc)
-        return torch.einsum("bqc,bhwc->bqhw", embed, feat_nhwc)
+        """[B,Q,C] x [B,Hm,Wm,C] -> mask logits [B,Q,Hm,Wm] — returned as a VIEW of a pixel-major [B,Hm,Wm,Q] buffer (the
+        layout the implicit-GEMM kernel writes and the mask-cost kernel reads)."""
+        if _MODE == "simt":          # strict-fp32 parity mode: no tensor-core product
+            return torch.einsum("bqc,bhwc->bqhw", embed, feat_nhwc)
+        return _MaskDot.apply(embed, feat_nhwc).permute(0, 3, 1, 2)
+
+    def mask_logits_at(self, embed, feat_nhwc, b_idx, q_idx, per_image):
+        """Mask logits of selected (image, query) pairs only — what the mask losses need (dfine_criterion.py:504-556 select
+        the matched masks out of [B,Q,Hm,Wm]; here the unmatched ones are never part of the autograd graph): embed [B,Q,C],
+        feat [B,Hm,Wm,C]; the pairs are sorted by image, `per_image` (host ints) of them per image.  -> [M,Hm,Wm]."""
+        B, Hm, Wm, C = feat_nhwc.shape
+        e = embed.reshape(-1, C).index_select(0, b_idx * embed.shape[1] + q_idx)          # [M, C]
+        outs, m0 = [], 0
+        for b, n in enumerate(per_image):
+            if n:
+                outs.append(e[m0:m0 + n] @ feat_nhwc[b].reshape(Hm * Wm, C).t())
+                m0 += n
+        return torch.cat(outs).reshape(-1, Hm, Wm)
+
+    @torch.no_grad()
+    def mask_cost_layer(self, pred_masks, gt, gsum, toff_dev, sizes, alpha, gamma, w_dice, w_mask):
+        """Mask term of the matching cost of one layer (matcher.py:175-237): pred_masks [B,Q,Hm,Wm] (a view of the
+        pixel-major buffer), gt [sumT, Hm*Wm] resized GT masks, gsum their sums -> [Q*sumT] cost blocks."""
+        B, Q, Hm, Wm = pred_masks.shape
+        pm = pred_masks.permute(0, 2, 3, 1)
+        if not pm.is_contiguous():
+            pm = pm.contiguous()
+        sumT, Tmax = sum(sizes), max(sizes)
+        extra = torch.zeros(Q * sumT, device=pm.device, dtype=torch.float32)
+        ws = torch.empty(2 * Q * (sumT + B), device=pm.device, dtype=torch.float32)
+        _check(lib().dfine_mask_cost(_p(pm), _p(gt), _p(gsum), _p(toff_dev), _p(extra), _p(ws), B, c_long(Hm * Wm), Q, sumT,
+                                     Tmax, c_float(alpha), c_float(gamma), c_float(w_dice), c_float(w_mask), _stream()),
+               "mask_cost")
+        return extra
+
+    def toff_device(self, sizes, device):
+        key = (tuple(sizes), device)
+        toff = self._toff_cache.get(key)
+        if toff is None:
+            offs = [0]
+            for sz in sizes:
+                offs.append(offs[-1] + sz)
+            toff = torch.tensor(offs, dtype=torch.int32).to(device)
+            if len(self._toff_cache) >= 256:
+                self._toff_cache.pop(next(iter(self._toff_cache)))
+            self._toff_cache[key] = toff
+        return toff
 
     # ---- input side / post-processing (SURVEY section 8f: the callers either side of the hot path) ----
     @torch.no_grad()

@@ -427,8 +427,10 @@ class DFINETransformer(nn.Module):
         return any(t.get("masks") is not None and hasattr(t["masks"], "numel") and t["masks"].numel() > 0
                    for t in targets)
 
-    def _mask_logits(self, h, mask_feat):
+    def _mask_logits(self, h, mask_feat, keep=None):
         e = self.mask_head(h) * (self.mask_dim ** -0.5)
+        if keep is not None:
+            keep.append(e)
         return K.mask_dot(e, mask_feat)   # [B,Q,C] x [B,Hm,Wm,C] -> [B,Q,Hm,Wm]
 
     def forward(self, feats, targets=None):
@@ -464,12 +466,13 @@ class DFINETransformer(nn.Module):
 
         if want_masks:
             mask_feat = self.mask_decoder(feats)
-            pred_masks = self._mask_logits(hs[-1], mask_feat)
-            aux_masks = [self._mask_logits(h, mask_feat) for h in hs[:-1]]
+            emb, dn_emb = [], []          # the per-layer mask embeddings: the criterion evaluates matched masks from them
+            aux_masks = [self._mask_logits(h, mask_feat, emb) for h in hs[:-1]]
+            pred_masks = self._mask_logits(hs[-1], mask_feat, emb)
             dn_pred_masks = dn_aux_masks = None
             if split_dn:
-                dn_pred_masks = self._mask_logits(dn_hs[-1], mask_feat)
-                dn_aux_masks = [self._mask_logits(h, mask_feat) for h in dn_hs[:-1]]
+                dn_aux_masks = [self._mask_logits(h, mask_feat, dn_emb) for h in dn_hs[:-1]]
+                dn_pred_masks = self._mask_logits(dn_hs[-1], mask_feat, dn_emb)
 
         if not self.training:
             out = {"pred_logits": logits[-1], "pred_boxes": boxes[-1]}
@@ -483,6 +486,8 @@ class DFINETransformer(nn.Module):
             out["pred_masks"] = pred_masks
         # layer-stacked views of the same tensors: the criterion evaluates every loss family once over all layers
         out["_stacked"] = {"logits": logits, "boxes": boxes, "corners": corners, "refs": refs, "full": full}
+        if want_masks:
+            out["_stacked"]["mask_src"] = {"feat": mask_feat, "emb": emb, "dn_emb": dn_emb}
         if split_dn:
             out["_stacked"].update(dn_logits=dn_logits, dn_boxes=dn_boxes, dn_corners=dn_corners, dn_refs=dn_refs)
         if self.aux_loss:

@@ -45,6 +45,9 @@ class HungarianMatcher(nn.Module):
         sizes = [len(t["boxes"]) for t in targets]
         Q = outputs_list[0]["pred_logits"].shape[1]
         dev = outputs_list[0]["pred_logits"].device
+        if dev.type == "cuda" and hasattr(K, "mask_cost_layer") and all(
+                t.get("masks") is not None and t["masks"].dim() == 3 for t in targets):
+            return self._mask_cost_kernel(outputs_list, targets, sizes, Q, dev)
         extra = torch.zeros((len(outputs_list), Q * sum(sizes)), device=dev, dtype=torch.float32)
         resized = {}
         for li, o in enumerate(outputs_list):
@@ -81,6 +84,30 @@ class HungarianMatcher(nn.Module):
                     cost = cost + self.cost_mask * ((pos @ gt.t() + neg @ (1 - gt).t()) / logit.shape[1])
                 extra[li, Q * off:Q * (off + n)] = cost.reshape(-1)
                 off += n
+        return extra
+
+    def _mask_cost_kernel(self, outputs_list, targets, sizes, Q, dev):
+        """CUDA path: one fused launch per layer (csrc/seg.cu: sigmoid / focal terms and the products with the GT masks in
+        one pass over the mask logits) instead of ~40 device ops and three fp32 GEMMs per (layer, image)."""
+        extra = torch.zeros((len(outputs_list), Q * sum(sizes)), device=dev, dtype=torch.float32)
+        toff = K.toff_device(sizes, dev)
+        gts = {}
+        for li, o in enumerate(outputs_list):
+            pm = o.get("pred_masks")
+            if pm is None:
+                continue
+            if pm.shape[1] != Q:
+                pm = pm[:, pm.shape[1] - Q:]
+            Hm, Wm = pm.shape[-2:]
+            if (Hm, Wm) not in gts:         # every GT mask resized once per step and prediction size
+                g = torch.cat([t["masks"] for t in targets]).float()
+                if g.shape[-2:] != (Hm, Wm):
+                    g = F.interpolate(g.unsqueeze(1), size=(Hm, Wm), mode="bilinear", align_corners=False).squeeze(1)
+                g = g.flatten(1).contiguous()
+                gts[(Hm, Wm)] = (g, g.sum(1).contiguous())
+            g, gsum = gts[(Hm, Wm)]
+            extra[li] = K.mask_cost_layer(pm, g, gsum, toff, sizes, self.alpha, self.gamma, float(self.cost_mask_dice),
+                                          float(self.cost_mask))
         return extra
 
     @torch.no_grad()

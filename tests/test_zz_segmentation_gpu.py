@@ -97,3 +97,45 @@ def test_segmentation_graph_replay_matches_eager(cuda_ops):
             assert step._graphs, "no CUDA graph was captured for the segmentation batch"
     for a, b in zip(traj["eager"], traj["graph"]):
         assert abs(a - b) <= 2e-2 * abs(a), traj
+
+
+def test_groupnorm_resize_maskdot_kernels_match_oracle(cuda_ops, oracle_ops):
+    """Segmentation-head kernels (csrc/seg.cu, io.cu, the grouped tcgen05 mask product) against the oracle's torch ops,
+    forward and backward."""
+    from tests.util import run_both
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 20, 24, 64, generator=g, requires_grad=True)
+    w = (torch.rand(64, generator=g) + 0.5).requires_grad_(True)
+    b = (torch.randn(64, generator=g) * 0.1).requires_grad_(True)
+    for act in (None, "relu"):
+        run_both(lambda K, x, w, b: K.group_norm(x, 32 if act is None else 8, w, b, 1e-5, act=act), cuda_ops, oracle_ops,
+                 [x, w, b], 2e-5, 2e-4)
+    for size in ((40, 48), (33, 31), (20, 24)):
+        run_both(lambda K, x: K.resize_bilinear(x, size), cuda_ops, oracle_ops, [x], 2e-6, 2e-5)
+    e = torch.randn(3, 300, 64, generator=g, requires_grad=True)
+    f = torch.randn(3, 20, 28, 64, generator=g, requires_grad=True)
+    run_both(lambda K, e, f: K.mask_dot(e, f), cuda_ops, oracle_ops, [e, f], 2e-5, 2e-3, grad_metric="l2")
+
+
+def test_mask_cost_kernel_matches_torch_formulation(cuda_ops):
+    """The fused mask-cost kernel against the reference formulation in torch ops (matcher.py:19-71, 175-237) on the same
+    device tensors: GT masks with ragged counts incl. an image without targets."""
+    from custom_d_fine_b200.matcher import HungarianMatcher
+    g = torch.Generator().manual_seed(2)
+    B, Q, Hm, Wm, sizes = 3, 300, 24, 20, [5, 0, 19]
+    outs = [{"pred_logits": torch.randn(B, Q, 80, generator=g).cuda(), "pred_boxes": torch.rand(B, Q, 4, generator=g).cuda(),
+             "pred_masks": (torch.randn(B, Hm, Wm, Q, generator=g) * 3).cuda().permute(0, 3, 1, 2)} for _ in range(2)]
+    targets = [{"labels": torch.zeros(n, dtype=torch.int64).cuda(), "boxes": torch.rand(n, 4, generator=g).cuda(),
+                "masks": (torch.rand(n, 2 * Hm, 2 * Wm, generator=g) > 0.6).to(torch.uint8).cuda()} for n in sizes]
+    m = HungarianMatcher({"cost_class": 2, "cost_bbox": 5, "cost_giou": 2, "cost_mask": 1, "cost_mask_dice": 1},
+                         use_focal_loss=True, alpha=0.25, gamma=2.0)
+    got = m.mask_cost(outs, targets)
+    saved = type(cuda_ops).mask_cost_layer
+    try:
+        del type(cuda_ops).mask_cost_layer          # force the torch formulation
+        want = m.mask_cost(outs, targets)
+    finally:
+        type(cuda_ops).mask_cost_layer = saved
+    assert got.shape == want.shape
+    err = float((got - want).abs().max() / want.abs().max())
+    assert err < 2e-5, err

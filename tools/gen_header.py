@@ -44,6 +44,8 @@ GROUPS = [
     ("io.cu", "Input preparation (uint8 -> float, resize) and detection post-processing",
      "Torch_model._prepare_inputs / _preds_postprocess infer/torch_model.py:153-292; DFINEPostProcessor dl/export.py:20-100;\n"
      " * multiscale collate dl/dataset.py:675-683."),
+    ("seg.cu", "Segmentation head: GroupNorm, bilinear-resize backward, mask matching cost",
+     "MaskDecoder.forward dfine_decoder.py:353-370; mask cost matcher.py:19-71,175-237."),
     ("matcher.cu", "Hungarian matcher (cost blocks + LSAP)",
      "HungarianMatcher.forward matcher.py:110-257 (scipy.optimize.linear_sum_assignment at 243)."),
     ("optim.cu", "Optimizer / EMA",
