@@ -286,3 +286,37 @@ def test_graph_replay_matches_eager(cuda_ops):
         assert abs(a - b) <= 2e-2 * abs(a), (traj["eager"][0], traj["graph"][0])
     k = "decoder.dec_score_head.0.weight"
     check_close("EMA weights", traj["graph"][1][k], traj["eager"][1][k], 1e-3)
+
+
+def test_loss_trajectory_default_mode_tracks_fp32(cuda_ops):
+    """What the reduced-precision GRADIENT products do to training (forward GEMMs are error-compensated, data / weight
+    gradients are single tf32 MMAs): 30 optimisation steps of D-FINE-s from the same weights, batches and generator
+    state in the default tensor-core mode against the strict-fp32 CUDA-core mode.  The loss trajectories must stay
+    together (measured drift is reported by the assertion message) — the per-step gradient error does not accumulate
+    into a different training run."""
+    from custom_d_fine_b200.model import build_optimizer
+    from custom_d_fine_b200.train import ModelEMA, TrainStep
+    batches = []
+    for i in range(3):
+        x, targets = synthetic_batch(2, 320, 320, seed=50 + i, T=(6, 4))
+        batches.append((x.cuda(), [{k: v.cuda() for k, v in t.items()} for t in targets]))
+    traj = {}
+    prev = co.get_gemm_mode()
+    try:
+        for mode in ("simt", "hf3"):
+            co.set_gemm_mode(mode)
+            torch.manual_seed(0)
+            model = build_model("s", 80, False, "cuda", img_size=(320, 320))
+            seeded_fill(model, 3)
+            model.train()
+            opt = build_optimizer(model, lr=2e-4, backbone_lr=2e-5, betas=(0.9, 0.999), weight_decay=1e-4, base_lr=2e-4)
+            step = TrainStep(model, build_loss("s", 80, 0.0, False), opt, ema=ModelEMA(model, 0.9998), clip_max_norm=0.1)
+            torch.manual_seed(11)
+            torch.cuda.manual_seed(11)
+            traj[mode] = [float(step(*batches[i % 3])[0]) for i in range(30)]
+    finally:
+        co.set_gemm_mode(prev)
+    a, b = traj["simt"], traj["hf3"]
+    assert a[-1] < a[0], "the fp32 run must actually train on this setup"
+    drift = max(abs(u - v) / abs(u) for u, v in zip(a, b))
+    assert drift <= 2e-2, (drift, a[::5], b[::5])
