@@ -40,46 +40,83 @@ class DevicePrefetcher:
     """Wraps a loader of host batches ``(images, targets, extra)`` (the reference's collate format,
     dataset.py:651-656) and yields device batches whose pinned host->device copies were issued on a side stream
     while the previous step was computing — what the reference gets from ``pin_memory`` + ``non_blocking`` copies
-    (train.py:558-565, dataset.py:570-580) only if the copy does not serialise with the step.  One batch ahead."""
+    (train.py:558-565, dataset.py:570-580) only if the copy does not serialise with the step.  One batch ahead.
 
-    def __init__(self, loader, device):
-        self.loader, self.device = loader, torch.device(device)
-        self.stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+    The copies land in TWO persistent staging slots per device (allocated once per tensor shape, shared by every
+    prefetcher of the process): no per-step device allocation, no allocator stalls on the first batch of an epoch.  A
+    slot is rewritten only after the step that consumed it has been enqueued AND has finished on the device (an event
+    recorded on the consumer's stream when it asks for the next batch).  Labels outside [0, num_classes) are rejected
+    here, where they are still host tensors (the device matcher clamps, it cannot raise)."""
+
+    _pool = {}      # device index -> {"stream", "slots": [ {key: tensor} x 2 ], "done": [event | None] x 2}
+
+    def __init__(self, loader, device, num_classes=None):
+        self.loader, self.device, self.num_classes = loader, torch.device(device), num_classes
+        self.state = None
+        if self.device.type == "cuda":
+            idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            st = DevicePrefetcher._pool.get(idx)
+            if st is None:
+                st = DevicePrefetcher._pool[idx] = {"stream": torch.cuda.Stream(self.device), "slots": [{}, {}],
+                                                    "done": [None, None]}
+            self.state = st
 
     def __len__(self):
         return len(self.loader)
 
-    def _stage(self, batch):
+    def _check(self, targets):
+        if self.num_classes is None:
+            return
+        for t in targets:
+            lab = t.get("labels")
+            if lab is not None and not lab.is_cuda and lab.numel() and (int(lab.min()) < 0 or int(lab.max()) >= self.num_classes):
+                raise IndexError(f"target label outside [0, {self.num_classes}) (the reference raises at matcher.py:150)")
+
+    def _into(self, slot, key, host):
+        buf = slot.get(key)
+        if buf is None or buf.shape != host.shape or buf.dtype != host.dtype:
+            buf = slot[key] = torch.empty(host.shape, dtype=host.dtype, device=self.device)
+        buf.copy_(host, non_blocking=True)
+        return buf
+
+    def _stage(self, batch, k):
         x, targets, extra = batch
-        if self.stream is None:
-            return x.to(self.device), [{k: v.to(self.device) for k, v in t.items() if torch.is_tensor(v)} for t in targets], extra, None
-        with torch.cuda.stream(self.stream):
-            x = x.to(self.device, non_blocking=True)
-            targets = [{k: v.to(self.device, non_blocking=True) for k, v in t.items() if torch.is_tensor(v)}
-                       for t in targets]
+        self._check(targets)
+        if self.state is None:
+            return x.to(self.device), [{n: v.to(self.device) for n, v in t.items() if torch.is_tensor(v)} for t in targets], extra, None
+        st = self.state
+        slot, stream = st["slots"][k % 2], st["stream"]
+        with torch.cuda.stream(stream):
+            if st["done"][k % 2] is not None:
+                stream.wait_event(st["done"][k % 2])          # the step that read this slot has finished
+            xd = self._into(slot, "x", x)
+            td = [{n: self._into(slot, (i, n), v) for n, v in t.items() if torch.is_tensor(v)} for i, t in enumerate(targets)]
             ev = torch.cuda.Event()
-            ev.record(self.stream)
-        return x, targets, extra, ev
+            ev.record(stream)
+        return xd, td, extra, ev
 
     def __iter__(self):
         it = iter(self.loader)
         try:
-            nxt = self._stage(next(it))
+            k = 0
+            nxt = self._stage(next(it), k)
         except StopIteration:
             return
         while nxt is not None:
             x, targets, extra, ev = nxt
+            cur = torch.cuda.current_stream(self.device) if ev is not None else None
             if ev is not None:
-                torch.cuda.current_stream(self.device).wait_event(ev)
-                x.record_stream(torch.cuda.current_stream(self.device))
-                for t in targets:
-                    for v in t.values():
-                        v.record_stream(torch.cuda.current_stream(self.device))
+                cur.wait_event(ev)
             try:
-                nxt = self._stage(next(it))      # next batch's copies overlap this batch's step
+                nxt = self._stage(next(it), k + 1)      # next batch's copies overlap this batch's step
             except StopIteration:
                 nxt = None
             yield x, targets, extra
+            if ev is not None:                          # the consumer has enqueued its step on `cur`: mark the slot's release
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream(self.device))
+                self.state["done"][k % 2] = done
+            k += 1
 
 
 class ModelEMA:

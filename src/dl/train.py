@@ -210,7 +210,7 @@ class Trainer:
             self.model.train()
             t0, n_img, losses = time.perf_counter(), 0, []
             # host->device copies of batch k+1 run on a side stream while batch k trains (train.py:558-565)
-            for inputs, targets, _ in DevicePrefetcher(self.train_loader, self.device):
+            for inputs, targets, _ in DevicePrefetcher(self.train_loader, self.device, self.num_labels):
                 loss, _ = self.step(inputs, targets)
                 losses.append(loss)
                 n_img += inputs.shape[0]
