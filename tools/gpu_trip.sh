@@ -28,7 +28,7 @@ for step in "$@"; do
               ncu -i /tmp/prof_$tag.ncu-rep --page raw --csv > gpurun_out/ncu_raw_$tag.csv 2>/dev/null
               python tools/ncu_summary.py full /tmp/prof_$tag.ncu-rep gpurun_out/ncu_full_$tag.csv ;;
     ncusrc)   # ncusrc:<kernel regex>:<python script and args, "," for spaces>  -> raw + source-page csv of ONE launch
-              tag=$(echo "$a$b" | tr -c 'A-Za-z0-9' '_' | cut -c1-80); run ncusrc_$tag ncu --set full --clock-control none --import-source on -k "regex:$a" -s 2 -c 1 -o /tmp/src_$tag -f python ${b//,/ }
+              tag=$(echo "$a$b" | tr -c 'A-Za-z0-9' '_' | cut -c1-120); run ncusrc_$tag ncu --set full --clock-control none --import-source on -k "regex:$a" -s 2 -c 1 -o /tmp/src_$tag -f python ${b//,/ }
               ncu -i /tmp/src_$tag.ncu-rep --page raw --csv > gpurun_out/ncusrc_raw_$tag.csv 2>/dev/null
               ncu -i /tmp/src_$tag.ncu-rep --page source --csv > gpurun_out/ncusrc_source_$tag.csv 2>/dev/null ;;
     py)       tag=$(echo "$a" | tr -c 'A-Za-z0-9' '_' | cut -c1-100); run py_$tag python ${a//,/ } ;;
