@@ -7,6 +7,8 @@ the state-dict keys equal the reference's.
 """
 from __future__ import annotations
 
+import os
+
 import torch.nn as nn
 
 from .blocks import ConvUnit
@@ -40,11 +42,11 @@ class LightConv(nn.Module):
         self.conv1 = ConvUnit(cin, cout, 1, act=None, lab=lab, frozen_norm=frozen)
         self.conv2 = ConvUnit(cout, cout, k, groups=cout, act="relu", lab=lab, frozen_norm=frozen)
 
-    def forward(self, x, tap=False):
+    def forward(self, x, tap=False, out=None):
         if tap:
             y, x_alias = self.conv1(x, tap=True)
-            return self.conv2(y), x_alias
-        return self.conv2(self.conv1(x))
+            return self.conv2(y, out=out), x_alias
+        return self.conv2(self.conv1(x), out=out)
 
 
 class HGBlock(nn.Module):
@@ -59,14 +61,26 @@ class HGBlock(nn.Module):
             else:
                 self.layers.append(ConvUnit(c, mid, k, act="relu", lab=lab, frozen_norm=frozen))
         total = cin + n_layers * mid
+        self.cin, self.mid, self.total, self.cout = cin, mid, total, cout
         self.aggregation = nn.Sequential(
             ConvUnit(total, cout // 2, 1, act="relu", lab=lab, frozen_norm=frozen),
             ConvUnit(cout // 2, cout, 1, act="relu", lab=lab, frozen_norm=frozen),
         )
 
-    def forward(self, x):
+    def forward(self, x, buf=None, out=None):
+        """buf: concatenation buffer [B,H,W,total] whose first `cin` channels ARE x (x is an alias of that slice): every
+        layer then writes its output into its own channel slice and the concat (hgnetv2.py:265-275) is the buffer
+        itself — no copy kernel.  out: where the block's result goes (the first slice of the next block's buffer)."""
+        if buf is not None:
+            feats, y, off = [x], x, self.cin
+            for layer in self.layers:
+                y = layer(y, out=buf[..., off:off + self.mid])
+                feats.append(y)
+                off += self.mid
+            y = self.aggregation[0](K.cat_alias(buf, feats))
+            return self.aggregation[1](y, post_add=x if self.residual else None, out=out)
         # every layer input is also a member of the concat: the concat reads the layer's `tap` alias of its input so
-        # that the concat's gradient slice is added inside that layer's data-gradient kernel (hgnetv2.py:265-275)
+        # that the concat's gradient slice is added inside that layer's data-gradient kernel
         feats = []
         y = x
         for layer in self.layers:
@@ -89,11 +103,29 @@ class HGStage(nn.Module):
             for i in range(n_blocks)
         ])
 
+    def _sliced(self, x):
+        blk = self.blocks[0]
+        return (hasattr(K, "concat_buffer") and os.environ.get("DFINE_CAT_ALIAS", "1") != "0" and x.is_cuda
+                and not hasattr(blk.aggregation[0], "conv_bn_fused") and blk.cin % 4 == 0 and blk.mid % 4 == 0)
+
     def forward(self, x):
+        if not self._sliced(x):
+            if self.downsample is not None:
+                x = self.downsample(x)
+            for blk in self.blocks:
+                x = blk(x)
+            return x
+        # concat by channel slice: every block input is produced straight into the first slice of that block's buffer
+        H, W = x.shape[1], x.shape[2]
         if self.downsample is not None:
-            x = self.downsample(x)
-        for blk in self.blocks:
-            x = blk(x)
+            H, W = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+        buf = K.concat_buffer(x, H, W, self.blocks[0].total)
+        first = buf[..., :self.blocks[0].cin]
+        x = self.downsample(x, out=first) if self.downsample is not None else K.copy_into(x, first)
+        for i, blk in enumerate(self.blocks):
+            nxt = K.concat_buffer(x, H, W, self.blocks[i + 1].total) if i + 1 < len(self.blocks) else None
+            x = blk(x, buf=buf, out=None if nxt is None else nxt[..., :blk.cout])
+            buf = nxt
         return x
 
 

@@ -89,8 +89,9 @@ class ConvUnit(nn.Module):
         del self.conv
         delattr(self, self._norm_name)
 
-    def forward(self, x, pre_add=None, post_add=None, tap=False):
+    def forward(self, x, pre_add=None, post_add=None, tap=False, out=None):
         if hasattr(self, "conv_bn_fused"):
+            assert out is None
             f = self.conv_bn_fused
             y = K.conv_bias_act(x, f.weight, f.bias, self.stride, self.pad, self.groups, self.act, self._lab, pre_add, post_add)
             return (y, x) if tap else y
@@ -104,7 +105,7 @@ class ConvUnit(nn.Module):
             training=self.training and not frozen, momentum=0.1, eps=bn.eps, act=self.act,
             lab_scale=None if lab is None else lab.scale,
             lab_bias=None if lab is None else lab.bias,
-            pre_add=pre_add, post_add=post_add, tap=tap)
+            pre_add=pre_add, post_add=post_add, tap=tap, **({} if out is None else {"out": out}))
 
 
 class MLP(nn.Module):

@@ -340,10 +340,8 @@ class DFINECriterion(nn.Module):
             zero = pm.sum() * 0
             return {"loss_mask_bce": zero, "loss_mask_dice": zero}
         assert S.v is None, "per-layer / denoising sets are never padded"
-        if src is not None and pm.is_cuda and hasattr(K, "mask_logits_at"):
-            # matched masks straight from the mask embeddings (src = (embed [B,Q,C], feat [B,Hm,Wm,C], pairs per image)): the
-            # [B,Q,Hm,Wm] logits of the unmatched queries stay out of the autograd graph
-            pred = K.mask_logits_at(src[0], src[1], S.b, S.q, src[2])
+        if src is not None and torch.is_tensor(src):
+            pred = src       # matched masks evaluated from the mask embeddings (see _matched_mask_logits)
         else:
             pred = pm.reshape(B * Q, Hm, Wm).index_select(0, S.b * Q + S.q)       # [M, Hm, Wm]
         key = (Hm, Wm, tg[2].data_ptr())
@@ -660,12 +658,10 @@ class DFINECriterion(nn.Module):
                     _scalars(fgl_ * W["loss_fgl"]), _scalars(ddf_ * W["loss_ddf"]), ddf_)
 
         msrc = outputs["_stacked"].get("mask_src") if with_masks else None
+        matched = {}
 
         def src_of(group, i, per_image):
-            if msrc is None:
-                return None
-            embs = msrc["emb"] if group == "A" else msrc["dn_emb"]
-            return (embs[i], msrc["feat"], per_image) if i < len(embs) else None
+            return matched.get((group, i))
 
         def put(suffix, k, lay=None, with_ddf=False, mask_out=None, mask_set=None, mask_num=None, mask_src=None):
             losses["loss_vfl" + suffix] = fam[0][k]
@@ -683,6 +679,18 @@ class DFINECriterion(nn.Module):
         nb = counts[1]
         sets = [_Set(table, *plan.set_slice(k), Q, False) for k in range(plan.n_sets)] if with_masks else [None] * plan.n_sets
         aux = outputs["aux_outputs"]
+        if msrc is not None and table.is_cuda and hasattr(K, "mask_logits_at_multi"):
+            # Matched mask logits of EVERY head that carries a mask loss, straight from the per-layer mask embeddings, in
+            # one call (one product per image, one gradient for the mask features): the [B,Q,Hm,Wm] logits of the
+            # unmatched queries stay out of the autograd graph.
+            req = [(("A", L - 1), msrc["emb"][L - 1], sets[0], plan.per_img)]
+            req += [(("A", i), msrc["emb"][i], sets[1 + i], plan.per_img) for i in range(min(L - 1, len(aux)))]
+            if DN is not None and msrc["dn_emb"]:
+                s_dn_ = _Set(table, *plan.set_slice("dn"), Q, False)
+                dn_per_ = [s_ * outputs["dn_meta"]["dn_num_group"] for s_ in plan.sizes]
+                req += [(("DN", i), msrc["dn_emb"][i], s_dn_, dn_per_) for i in range(len(msrc["dn_emb"]))]
+            preds = K.mask_logits_at_multi(msrc["feat"], [(e, S_.b, S_.q, per) for _, e, S_, per in req])
+            matched = {key: p_ for (key, _, _, _), p_ in zip(req, preds)}
         fam = weighted(*A)
         put("", 0, L - 1, mask_out=outputs, mask_set=sets[0], mask_num=nb, mask_src=src_of("A", L - 1, plan.per_img))
         for i in range(L - 1):

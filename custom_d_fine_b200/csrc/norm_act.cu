@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(NT) bn_apply_kernel(const float* __restrict__ 
                                                       const float* __restrict__ pre_add,
                                                       const float* __restrict__ post_add,
                                                       const float* __restrict__ lab, const float* __restrict__ lab_b,
-                                                      float* __restrict__ y, long n4, int VC, int act, long ldy) {
+                                                      float* __restrict__ y, long n4, int VC, int act, long ldy,
+                                                      long ld_post) {
     const float ls = lab ? __ldg(lab) : 1.f, lb = lab ? __ldg(lab_b) : 0.f;
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long)gridDim.x * NT) {
         const int c = (int)(i % VC) * 4;
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(NT) bn_apply_kernel(const float* __restrict__ 
         if (pre_add) { const float4 a = ld4(pre_add + i * 4); z.x += a.x; z.y += a.y; z.z += a.z; z.w += a.w; }
         float4 o = make_float4(act_fwd(z.x, act), act_fwd(z.y, act), act_fwd(z.z, act), act_fwd(z.w, act));
         if (lab) { o.x = ls * o.x + lb; o.y = ls * o.y + lb; o.z = ls * o.z + lb; o.w = ls * o.w + lb; }
-        if (post_add) { const float4 a = ld4(post_add + i * 4); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+        if (post_add) { const float4 a = ld4(post_add + (i / VC) * ld_post + c); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
         st4(y + (i / VC) * ldy + c, o);
     }
 }
@@ -407,13 +408,15 @@ DFINE_API int dfine_bn_fold(const float* weight, const float* bias, const float*
 // lab / lab_b: device pointers to the scalar LAB scale and bias (both or neither).  pre_add/post_add optional [M,C].
 DFINE_API int dfine_bn_apply(const float* x, const float* scale, const float* shift, const float* pre_add,
                              const float* post_add, const float* lab, const float* lab_b, float* y, long M, int C,
-                             int act, long ldy, void* stream) {
+                             int act, long ldy, long ld_post, void* stream) {
     DFINE_REQUIRE(C % 4 == 0, "bn_apply: C=%d must be a multiple of 4", C);
     DFINE_REQUIRE(ldy >= C && ldy % 4 == 0 && ((uintptr_t)y % 16) == 0, "bn_apply: output row stride %ld", ldy);
+    DFINE_REQUIRE(!post_add || (ld_post >= C && ld_post % 4 == 0 && ((uintptr_t)post_add % 16) == 0),
+                  "bn_apply: post_add row stride %ld", ld_post);
     const long n4 = M * C / 4;
     if (n4 == 0) return 0;
     bn_apply_kernel<<<ew_grid(n4), NT, 0, (cudaStream_t)stream>>>(x, scale, shift, pre_add, post_add, lab, lab_b, y,
-                                                                 n4, C / 4, act, ldy);
+                                                                 n4, C / 4, act, ldy, post_add ? ld_post : (long)C);
     DFINE_LAUNCH_CHECK("bn_apply");
     return 0;
 }

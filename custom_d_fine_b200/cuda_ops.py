@@ -611,7 +611,7 @@ def weights_changed():
 # ------------------------------------------------------------------------------------------------
 class _ConvBnAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bn_w, bn_b, lab_s, lab_b, pre_add, post_add, running_mean, running_var, cfg):
+    def forward(ctx, x, weight, bn_w, bn_b, lab_s, lab_b, pre_add, post_add, running_mean, running_var, cfg, out=None):
         stride, pad, groups, training, momentum, eps, act, frozen, tap = cfg
         _req_cuda(x, weight)
         x_in = x
@@ -654,9 +654,22 @@ class _ConvBnAct(torch.autograd.Function):
         mean = invstd = None
         if pre_add is not None:
             pre_add = pre_add.contiguous()
-        if post_add is not None:
-            post_add = post_add.contiguous()
-        y, ldy_out = _alloc_nhwc(B, OH, OW, Cout, dev)
+        ld_post = Cout
+        if post_add is not None:      # a channel slice of a concatenation buffer is read in place through its row stride
+            if (post_add.dim() == 4 and post_add.stride(3) == 1 and post_add.stride(2) % 4 == 0 and post_add.stride(2) >= Cout
+                    and post_add.stride(1) == OW * post_add.stride(2) and post_add.stride(0) == OH * OW * post_add.stride(2)
+                    and post_add.data_ptr() % 16 == 0):
+                ld_post = post_add.stride(2)
+            else:
+                post_add = post_add.contiguous()
+        if out is not None:
+            # the caller's channel slice of a concatenation buffer (concat by channel slice: no copy kernel later); written
+            # through the raw pointer and returned as an alias, so autograd sees no in-place operation
+            assert tuple(out.shape) == (B, OH, OW, Cout) and out.stride(3) == 1 and out.stride(2) % 4 == 0 and \
+                out.stride(1) == OW * out.stride(2) and out.stride(0) == OH * OW * out.stride(2) and out.data_ptr() % 16 == 0
+            y, ldy_out = out.as_strided(out.shape, out.stride(), out.storage_offset()), out.stride(2)
+        else:
+            y, ldy_out = _alloc_nhwc(B, OH, OW, Cout, dev)
         # (a fused finalize+apply launch was measured SLOWER: every CTA re-derives the scale / shift table in fp64 and
         #  synchronises before its first load — 20.5 us against 12.3 + 4.8 us per layer, profiles/README.md)
         if training:
@@ -669,7 +682,8 @@ class _ConvBnAct(torch.autograd.Function):
             _check(lib().dfine_bn_fold(_p(bn_w), _p(bn_b), _p(running_mean), _p(running_var), _p(scale), _p(shift),
                                        Cout, c_float(eps), _stream()), "bn_fold")
         _check(lib().dfine_bn_apply(_p(conv_out), _p(scale), _p(shift), _p(pre_add), _p(post_add), _p(lab_s),
-                                    _p(lab_b), _p(y), c_long(M), Cout, ACT[act], c_long(ldy_out), _stream()), "bn_apply")
+                                    _p(lab_b), _p(y), c_long(M), Cout, ACT[act], c_long(ldy_out), c_long(ld_post), _stream()),
+               "bn_apply")
         ctx.save_for_backward(x, weight, conv_out, scale, shift, mean, invstd, pre_add, lab_s, lab_b, bn_w)
         ctx.geom, ctx.ldx, ctx.cfg = geom, ldx, cfg
         ctx.has_post = post_add is not None
@@ -761,7 +775,39 @@ class _ConvBnAct(torch.autograd.Function):
                 g_x = torch.empty((B, H, W, Cin), device=dev, dtype=torch.float32)
                 _conv_dgrad(dconv, ld_dc, weight, _wcache.getter(weight), g_x, Cin, ctx.geom, dtap)
         g_post = (dy if dy.is_contiguous() else dy.contiguous()) if ctx.has_post else None
-        return g_x, g_w, g_bn_w, g_bn_b, g_lab_s, g_lab_b, dpre, g_post, None, None, None
+        return g_x, g_w, g_bn_w, g_bn_b, g_lab_s, g_lab_b, dpre, g_post, None, None, None, None
+
+
+class _CatAlias(torch.autograd.Function):
+    """The channel concatenation of tensors that were WRITTEN into consecutive channel slices of `buf` by their
+    producers: forward returns the buffer itself (no copy kernel), backward hands every producer its slice of the
+    gradient as a view."""
+
+    @staticmethod
+    def forward(ctx, buf, *parts):
+        ctx.splits = [p.shape[-1] for p in parts]
+        return buf.as_strided(buf.shape, buf.stride(), buf.storage_offset())
+
+    @staticmethod
+    def backward(ctx, g):
+        outs, o = [], 0
+        for n in ctx.splits:
+            outs.append(g[..., o:o + n])
+            o += n
+        return (None, *outs)
+
+
+class _CopyInto(torch.autograd.Function):
+    """x copied into a channel slice of a concatenation buffer (for a member whose producer could not write there)."""
+
+    @staticmethod
+    def forward(ctx, x, out):
+        out.data.copy_(x)
+        return out.as_strided(out.shape, out.stride(), out.storage_offset())
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -1211,6 +1257,43 @@ class _MaskDot(torch.autograd.Function):
         return dembed, dfeat
 
 
+class _RowsTimesFeat(torch.autograd.Function):
+    """out[m] = rows[m] . feat[b(m)] over the pixels, rows stacked image-major (`totals[b]` rows of image b): one product
+    per image forward, two backward, ONE d(feat) tensor."""
+
+    @staticmethod
+    def forward(ctx, rows, feat, totals):
+        B, Hm, Wm, C = feat.shape
+        f2 = feat.reshape(B, Hm * Wm, C)
+        out = torch.empty((rows.shape[0], Hm * Wm), device=feat.device, dtype=torch.float32)
+        o = 0
+        for b, n in enumerate(totals):
+            if n:
+                torch.matmul(rows[o:o + n], f2[b].t(), out=out[o:o + n])
+                o += n
+        ctx.save_for_backward(rows, feat)
+        ctx.totals = totals
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        rows, feat = ctx.saved_tensors
+        B, Hm, Wm, C = feat.shape
+        f2 = feat.reshape(B, Hm * Wm, C)
+        dout = dout.contiguous()
+        drows = torch.empty_like(rows)
+        dfeat = torch.empty_like(f2)
+        o = 0
+        for b, n in enumerate(ctx.totals):
+            if n:
+                torch.matmul(dout[o:o + n], f2[b], out=drows[o:o + n])
+                torch.matmul(dout[o:o + n].t(), rows[o:o + n], out=dfeat[b])
+                o += n
+            else:
+                dfeat[b].zero_()
+        return drows, dfeat.reshape(feat.shape), None
+
+
 # ------------------------------------------------------------------------------------------------
 # decoder gate: sigmoid(g[:, :D]) * x1 + sigmoid(g[:, D:]) * x2
 # ------------------------------------------------------------------------------------------------
@@ -1307,22 +1390,34 @@ class CudaOps:
     # ---- conv / norm ----
     def conv_bn_act(self, x, w, stride, pad, groups, bn_w, bn_b, running_mean, running_var, num_batches_tracked,
                     training, momentum=0.1, eps=1e-5, act=None, lab_scale=None, lab_bias=None, pre_add=None,
-                    post_add=None, tap=False):
+                    post_add=None, tap=False, out=None):
         frozen = num_batches_tracked is None
         if training and num_batches_tracked is not None and not (
                 wgrad_stream.in_step and num_batches_tracked.data_ptr() in _step_counters):
             num_batches_tracked.add_(1)      # (inside a train step the step bumps all registered counters at once)
         # (the 3-channel image convolution has its own direct kernels, csrc/stem.cu)
         if groups == 1 and ((x.shape[-1] % 4 and x.shape[-1] != 3) or w.shape[0] % 4):
+            assert out is None
             return self._conv_bn_act_padded(x, w, stride, pad, bn_w, bn_b, running_mean, running_var, training,
                                             momentum, eps, act, lab_scale, lab_bias, pre_add, post_add, frozen, tap)
         # tap: also return the input as a second output (see _ConvBnAct.forward); plain pass-through without autograd
         tap_ag = bool(tap) and _TAP and torch.is_grad_enabled() and x.requires_grad
         cfg = (stride, tuple(pad), groups, bool(training), float(momentum), float(eps), act, frozen, tap_ag)
-        out = _ConvBnAct.apply(x, w, bn_w, bn_b, lab_scale, lab_bias, pre_add, post_add, running_mean, running_var, cfg)
+        res = _ConvBnAct.apply(x, w, bn_w, bn_b, lab_scale, lab_bias, pre_add, post_add, running_mean, running_var, cfg, out)
         if tap and not tap_ag:
-            return out, x
-        return out
+            return res, x
+        return res
+
+    # ---- concat by channel slice ----
+    def concat_buffer(self, like, H, W, channels):
+        """An empty [B,H,W,channels] NHWC buffer whose channel slices are handed to producers as `out=`."""
+        return torch.empty((like.shape[0], H, W, channels), device=like.device, dtype=torch.float32)
+
+    def cat_alias(self, buf, parts):
+        return _CatAlias.apply(buf, *parts)
+
+    def copy_into(self, x, out):
+        return _CopyInto.apply(x, out)
 
     def _conv_bn_act_padded(self, x, w, stride, pad, bn_w, bn_b, running_mean, running_var, training, momentum, eps,
                             act, lab_scale, lab_bias, pre_add, post_add, frozen, tap):
@@ -1400,7 +1495,7 @@ class CudaOps:
         lb = None if lab is None else _as_dev_scalar(lab[1], x.device)
         _check(lib().dfine_bn_apply(_p(y), _p(one), _p(b), _p(None if pre_add is None else pre_add.contiguous()),
                                     _p(None if post_add is None else post_add.contiguous()), _p(ls), _p(lb), _p(out),
-                                    c_long(B * OH * OW), Cout, ACT[act], c_long(Cout), _stream()), "bn_apply")
+                                    c_long(B * OH * OW), Cout, ACT[act], c_long(Cout), c_long(Cout), _stream()), "bn_apply")
         return out
 
     def maxpool2x2_s1_padbr(self, x):
@@ -1475,18 +1570,35 @@ class CudaOps:
             return torch.einsum("bqc,bhwc->bqhw", embed, feat_nhwc)
         return _MaskDot.apply(embed, feat_nhwc).permute(0, 3, 1, 2)
 
-    def mask_logits_at(self, embed, feat_nhwc, b_idx, q_idx, per_image):
-        """Mask logits of selected (image, query) pairs only — what the mask losses need (dfine_criterion.py:504-556 select
-        the matched masks out of [B,Q,Hm,Wm]; here the unmatched ones are never part of the autograd graph): embed [B,Q,C],
-        feat [B,Hm,Wm,C]; the pairs are sorted by image, `per_image` (host ints) of them per image.  -> [M,Hm,Wm]."""
+    def mask_logits_at_multi(self, feat_nhwc, heads):
+        """Mask logits of selected (image, query) pairs only, for SEVERAL loss heads at once — what the mask losses need
+        (dfine_criterion.py:504-556 select the matched masks out of [B,Q,Hm,Wm]; here the unmatched ones never enter the
+        autograd graph).  heads: list of (embed [B,Q,C], b_idx, q_idx, per_image host counts; pairs sorted by image).
+        All heads' rows of one image go through ONE product with that image's features and ONE autograd node returns
+        ONE d(feat): 13 heads x 8 images of separate matmuls cost 104 full-size gradient fills + adds.  -> list of
+        [M_h,Hm,Wm]."""
         B, Hm, Wm, C = feat_nhwc.shape
-        e = embed.reshape(-1, C).index_select(0, b_idx * embed.shape[1] + q_idx)          # [M, C]
-        outs, m0 = [], 0
-        for b, n in enumerate(per_image):
-            if n:
-                outs.append(e[m0:m0 + n] @ feat_nhwc[b].reshape(Hm * Wm, C).t())
-                m0 += n
-        return torch.cat(outs).reshape(-1, Hm, Wm)
+        rows = [e.reshape(-1, C).index_select(0, bi * e.shape[1] + qi) for e, bi, qi, _ in heads]     # [M_h, C] each
+        # image-major stacking: image b's rows of every head are contiguous
+        pieces, spans, totals = [], [[] for _ in heads], []
+        for b in range(B):
+            n_b = 0
+            for h, (_, _, _, per) in enumerate(heads):
+                o = sum(per[:b])
+                if per[b]:
+                    pieces.append(rows[h][o:o + per[b]])
+                spans[h].append((sum(totals) + n_b, per[b]))
+                n_b += per[b]
+            totals.append(n_b)
+        if not pieces:
+            return [feat_nhwc.new_zeros((0, Hm, Wm)) for _ in heads]
+        out = _RowsTimesFeat.apply(torch.cat(pieces), feat_nhwc, tuple(totals))                         # [sumM, HW]
+        res = []
+        for h in range(len(heads)):
+            parts = [out[o:o + n] for o, n in spans[h] if n]
+            res.append((torch.cat(parts) if len(parts) > 1 else parts[0]).reshape(-1, Hm, Wm) if parts
+                       else feat_nhwc.new_zeros((0, Hm, Wm)))
+        return res
 
     @torch.no_grad()
     def mask_cost_layer(self, pred_masks, gt, gsum, toff_dev, sizes, alpha, gamma, w_dice, w_mask):

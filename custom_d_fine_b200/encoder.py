@@ -7,6 +7,8 @@ AIFI TransformerEncoderLayer 243-290 (post-norm, GELU FFN), sincos position embe
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -81,6 +83,15 @@ class ELANBlock(nn.Module):
         self.cv4 = _cn(c3 + 2 * c4, c2, 1, act=act)
 
     def forward(self, x):
+        if hasattr(K, "concat_buffer") and not hasattr(self.cv1, "conv_bn_fused") and os.environ.get("DFINE_CAT_ALIAS", "1") != "0":
+            # concat by channel slice: the three members are written straight into one buffer by their producers
+            c3, c4 = self.cv1.conv.out_channels, self.cv2[1].conv.out_channels
+            if c3 % 4 == 0 and c4 % 4 == 0:
+                buf = K.concat_buffer(x, x.shape[1], x.shape[2], c3 + 2 * c4)
+                y = self.cv1(x, out=buf[..., :c3])
+                y3 = self.cv2[1](self.cv2[0](y[..., self.c:]), out=buf[..., c3:c3 + c4])
+                y4 = self.cv3[1](self.cv3[0](y3), out=buf[..., c3 + c4:])
+                return self.cv4(K.cat_alias(buf, [y, y3, y4]))
         y = self.cv1(x)
         y2 = y[..., self.c:]
         y3 = self.cv2[1](self.cv2[0](y2))
