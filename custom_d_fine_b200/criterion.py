@@ -349,6 +349,10 @@ class DFINECriterion(nn.Module):
             g = tg[2].unsqueeze(1).float()
             g = F.interpolate(g, size=(Hm, Wm), mode="bilinear", align_corners=False).squeeze(1).clamp_(0, 1)
             self._mask_cache = (key, g)
+        if pred.is_cuda and hasattr(K, "mask_loss_rows") and os.environ.get("DFINE_MASK_LOSS", "kernel") != "torch":
+            # one kernel each way over the matched masks (csrc/seg.cu) instead of ~60 elementwise passes over [M,Hm,Wm]
+            bce_rows, dice_rows = K.mask_loss_rows(pred, self._mask_cache[1], S.t, tg[1])
+            return {"loss_mask_bce": bce_rows.mean(), "loss_mask_dice": dice_rows.mean()}
         tgt = self._mask_cache[1].index_select(0, S.t)
         cx, cy, w, h = tg[1].index_select(0, S.t).unbind(-1)
         x1 = ((cx - w / 2) * Wm).clamp(0, Wm - 1)[:, None, None]

@@ -879,6 +879,263 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
     }
 }
 
+// ------------------------------------------------------------------------------------------- CTA-pair forward
+// The plain-tf32 persistent kernel on a CTA PAIR (cluster of 2, tcgen05 cta_group::2): one UMMA covers 256 output
+// pixels x BN channels — CTA r of the pair owns pixel tile 2*mp + r (its A tile, its 128 TMEM lanes, its epilogue) and
+// loads only HALF of the weight tile (BN/2 rows); the tensor core reads A from both CTAs and the two weight halves from
+// the CTA that holds them.  Per CTA and k-block that is 16 KB of A + BN/8 KB of weights instead of 16 + BN/4: half the
+// weight bytes from L2 and from shared memory (the single-CTA kernel re-fetches the whole weight tile for every pixel
+// tile and reads 118 B/clk of shared memory per 128x128 MMA — at the port's limit), and stages of 32 KB (BN = 256)
+// allow a 6-deep ring.  Only the leader CTA (rank 0) issues MMAs; its tcgen05.commit multicasts the "stage free" /
+// "accumulator full" arrivals to both CTAs; every TMA load of either CTA signals the LEADER's full barrier
+// (.cta_group::2 form, peer bit of the mbarrier address cleared); the epilogue warps of both CTAs release the
+// accumulator on the leader's barrier.  Used for the data gradients (and the plain-tf32 forward mode).
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;     // shared::cluster address with the CTA-pair rank bit cleared = the leader's
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive::one on the barrier at the same shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((unsigned short)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                             int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+        "%6}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// instruction descriptor for the pair MMA: M = 256
+__host__ __device__ constexpr uint32_t make_idesc_m256(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+struct PairSmem {
+    alignas(1024) float a[STAGES][BM * BK];            // this CTA's 128 pixel rows
+    alignas(1024) float b[STAGES][(BN / 2) * BK];      // this CTA's half of the weight tile
+    alignas(16) float epi[4][32 * EPL];
+    typename StatT<BN>::type statw[4][2 * BN];
+    uint64_t full[STAGES], empty[STAGES], tfull[2], tempty[2];
+    uint32_t tmem_base;
+};
+constexpr int PAIR_THREADS = 32 * 6;
+
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
+    tc_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, float* __restrict__ y,
+                   const float* __restrict__ bias, double* __restrict__ stats, FwdParams p, TileSched ts) {
+    extern __shared__ uint8_t raw[];
+    using Smem = PairSmem<BN, STAGES>;
+    Smem& sm = *reinterpret_cast<Smem*>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x / 2, n_pairs = gridDim.x / 2;
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+    const int m_tiles = p.B * tiles_per_img;
+    const int pair_total = ((m_tiles + 1) / 2) * ts.n_tiles;        // (pixel-tile pair, N tile), N tiles of a pair adjacent
+    const int cblocks = (p.Cin + BK - 1) / BK;
+    const int num_k = p.n_taps * cblocks;
+    constexpr uint32_t TMEM_COLS = 2 * BN;
+    constexpr uint32_t STAGE_BYTES_CTA_B = (BN / 2) * BK * sizeof(float);
+
+    if (stats)
+        for (int i = threadIdx.x; i < 4 * 2 * BN; i += blockDim.x) (&sm.statw[0][0])[i] = 0;
+    if (warp == 0 && lane == 0) { prefetch_tmap(&map_x); prefetch_tmap(&map_w); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+            for (int a = 0; a < 2; ++a) { mbar_init(&sm.tfull[a], 1); mbar_init(&sm.tempty[a], 8); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc2(&sm.tmem_base, TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();          // both CTAs' barriers are initialised before any remote arrival / peer-signalling TMA load
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int t = pair; t < pair_total; t += n_pairs) {
+                const int mp = t / ts.n_tiles, n0 = (t % ts.n_tiles) * BN;
+                const int mt = 2 * mp + (int)rank;                 // may be == m_tiles (odd count): coordinates fall outside
+                const int img = mt / tiles_per_img, tt = mt % tiles_per_img;      // the batch dimension -> TMA zero fill
+                const int h0 = (tt / p.tiles_w) * p.TH, w0 = (tt % p.tiles_w) * p.TW;
+                const int wn_img = img * p.w_row_off, wk_img = img * p.w_k_off;
+                for (int kb = 0; kb < num_k; ++kb, ++g) {
+                    const int s = g % STAGES, ph = (g / STAGES) & 1;
+                    mbar_wait(&sm.empty[s], ph ^ 1);
+                    const int tap = kb / cblocks, c0 = (kb % cblocks) * BK;
+                    if (leader)      // the leader's barrier counts the bytes of BOTH CTAs' loads of this stage
+                        mbar_expect_tx(&sm.full[s], 2u * ((uint32_t)(p.TW * p.TH * BK * sizeof(float)) + STAGE_BYTES_CTA_B));
+                    tma2_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 * p.in_stride + p.dw[tap], h0 * p.in_stride + p.dh[tap],
+                                 img);
+                    tma2_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0 + wk_img, n0 + (int)rank * (BN / 2) + wn_img);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_m256(BN);
+            uint32_t g = 0, i = 0;
+            for (int t = pair; t < pair_total; t += n_pairs, ++i) {
+                const uint32_t acc = i & 1, aph = (i >> 1) & 1;
+                mbar_wait(&sm.tempty[acc], aph ^ 1);          // the epilogue warps of both CTAs have drained this accumulator
+                tc_fence_after();
+                const uint32_t d = tmem + acc * BN;
+                for (int kb = 0; kb < num_k; ++kb, ++g) {
+                    const int s = g % STAGES, ph = (g / STAGES) & 1;
+                    mbar_wait(&sm.full[s], ph);
+                    tc_fence_after();
+                    const uint64_t da = make_desc(smem_u32(sm.a[s]), 16, 1024);
+                    const uint64_t db = make_desc(smem_u32(sm.b[s]), 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) umma_tf32_2cta(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit_pair(&sm.empty[s]);
+                }
+                umma_commit_pair(&sm.tfull[acc]);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp % 4;  // TMEM lane quarter
+        const uint32_t wbase = smem_u32(sm.epi[q]);
+        const bool plain = (bias == nullptr) && p.act == 0;
+        const bool local_stats = stats != nullptr && ts.n_tiles == 1;
+        typename StatT<BN>::type* sw = sm.statw[q];
+        uint32_t i = 0;
+        for (int t = pair; t < pair_total; t += n_pairs, ++i) {
+            const uint32_t acc = i & 1, aph = (i >> 1) & 1;
+            const int mp = t / ts.n_tiles, n0 = (t % ts.n_tiles) * BN;
+            const int mt = 2 * mp + (int)rank;
+            const bool tile_ok = mt < m_tiles;
+            const int img = mt / tiles_per_img, tt = mt % tiles_per_img;
+            const int h0 = (tt / p.tiles_w) * p.TH, w0 = (tt % p.tiles_w) * p.TW;
+            long row_off[8];
+            bool row_ok[8];
+#pragma unroll
+            for (int r8 = 0; r8 < 8; ++r8) {
+                const int r = 32 * q + 4 * r8 + lane / 8;
+                const int th = r / p.TW, tw = r % p.TW;
+                const int oh = h0 + th, ow = w0 + tw;
+                row_ok[r8] = tile_ok && th < p.TH && oh < p.OH && ow < p.OW;
+                row_off[r8] = ((long)img * p.YH + (long)oh * p.osy + p.ooy) * p.YW + (long)ow * p.osx + p.oox;
+            }
+            mbar_wait(&sm.tfull[acc], aph);
+            tc_fence_after();
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (n0 + c0 >= p.N) break;
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + acc * BN + (uint32_t)c0, v);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4)
+                    sts128(wbase + (uint32_t)(lane * EPL + 4 * c4) * 4u, __uint_as_float(v[4 * c4]),
+                           __uint_as_float(v[4 * c4 + 1]), __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
+                __syncwarp();
+                const int col = n0 + c0 + 4 * (lane % 8);
+                const bool col_ok = col < p.N;
+                float4 bv = make_float4(0, 0, 0, 0);
+                if (bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+                float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int r8 = 0; r8 < 8; ++r8) {
+                    const int r = 4 * r8 + lane / 8;
+                    float4 o = lds128(wbase + (uint32_t)(r * EPL + 4 * (lane % 8)) * 4u);
+                    if (row_ok[r8] && col_ok) {
+                        if (stats) {
+                            s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
+                            s2[0] += o.x * o.x; s2[1] += o.y * o.y; s2[2] += o.z * o.z; s2[3] += o.w * o.w;
+                        }
+                        if (!plain) {
+                            o.x = act_fwd(o.x + bv.x, p.act); o.y = act_fwd(o.y + bv.y, p.act);
+                            o.z = act_fwd(o.z + bv.z, p.act); o.w = act_fwd(o.w + bv.w, p.act);
+                        }
+                        *reinterpret_cast<float4*>(y + row_off[r8] * p.ldy + col) = o;
+                    }
+                }
+                if (stats) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8); s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
+                        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+                    }
+                    if (lane < 8 && col_ok) {
+                        if (local_stats) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { sw[c0 + 4 * lane + j] += s1[j]; sw[BN + c0 + 4 * lane + j] += s2[j]; }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                atomicAdd(stats + col + j, (double)s1[j]);
+                                atomicAdd(stats + p.N + col + j, (double)s2[j]);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&sm.tempty[acc]);      // (the leader waits for all 8 epilogue warps of the pair)
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();          // neither CTA may leave (or free TMEM) while the peer's MMAs / arrivals can still touch it
+    if (warp == 1) tmem_dealloc2(tmem, TMEM_COLS);
+    if (stats && ts.n_tiles == 1) {
+        for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
+            const int c = i % BN, which = i / BN;
+            const double v = (double)sm.statw[0][i] + (double)sm.statw[1][i] + (double)sm.statw[2][i] + (double)sm.statw[3][i];
+            if (c < p.N && v != 0.0) atomicAdd(stats + (long)which * p.N + c, v);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------- wgrad
 constexpr int WG_THREADS = 192;
 constexpr int WG_STAGES = 3;
@@ -1167,6 +1424,34 @@ int launch_persist(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorM
     return 0;
 }
 
+template <int BN, int STAGES>
+int launch_pair(const CUtensorMap& mx, const CUtensorMap& mw, float* y, const float* bias, double* stats, const FwdParams& p,
+                int B, cudaStream_t st) {
+    const int smem = (int)sizeof(PairSmem<BN, STAGES>) + 1024;
+    DFINE_SET_SMEM_ONCE((tc_pair_kernel<BN, STAGES>), smem, "tc_pair");
+    TileSched ts;
+    ts.n_tiles = ceil_div(p.N, BN);
+    const int m_tiles = B * p.tiles_w * p.tiles_h;
+    ts.total = ((m_tiles + 1) / 2) * ts.n_tiles;
+    // as many CTA pairs as the device can keep resident at once (GPCs with an odd SM count leave an SM without a partner)
+    static const int max_pairs = [&] {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(sm_count(), 1, 1);
+        cfg.blockDim = dim3(PAIR_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, tc_pair_kernel<BN, STAGES>, &cfg) != cudaSuccess || n < 1) {
+            cudaGetLastError();
+            n = sm_count() / 2;
+        }
+        return n < sm_count() / 2 ? n : sm_count() / 2;
+    }();
+    int pairs = ts.total < max_pairs ? ts.total : max_pairs;
+    if (pairs < 1) pairs = 1;
+    tc_pair_kernel<BN, STAGES><<<2 * pairs, PAIR_THREADS, smem, st>>>(mx, mw, y, bias, stats, p, ts);
+    return 0;
+}
+
 template <int BN>
 int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, float* dwr, WgradParams p, cudaStream_t st) {
     const int smem = (int)sizeof(WgradSmem<BN>) + 1024;
@@ -1335,6 +1620,18 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
     cudaStream_t st = (cudaStream_t)stream;
     static const bool persist = [] { const char* e = getenv("DFINE_TC_PERSIST"); return !(e && e[0] == '0'); }();
     DFINE_REQUIRE((persist && !w_lo && !w_bf16) || !res, "conv_tc: the fused residual add needs the persistent plain-tf32 kernel");
+    // CTA-pair kernel (cta_group::2) for the plain-tf32 launches with at least a few pixel-tile pairs per SM pair and no
+    // fused residual: the weight map then delivers HALF an N tile per CTA.  DFINE_TC_PAIR=0 keeps the single-CTA kernel.
+    static const bool use_pair = [] { const char* e = getenv("DFINE_TC_PAIR"); return !(e && e[0] == '0'); }();
+    if (persist && use_pair && !w_lo && !res && bn >= 128 && (long)B * p.tiles_w * p.tiles_h >= 2) {
+        CUtensorMap mwh;
+        rc = make_map2(&mwh, w, ldw, WR, ldw, BK, bn / 2, "conv_tc(w half)");
+        if (rc) return rc;
+        rc = bn == 128 ? launch_pair<128, 8>(mx, mwh, y, bias, stats, p, B, st) : launch_pair<256, 6>(mx, mwh, y, bias, stats, p, B, st);
+        if (rc) return rc;
+        DFINE_LAUNCH_CHECK("conv_tc(pair)");
+        return 0;
+    }
     if (persist) {
         if (w_lo) {
             rc = bn == 32 ? launch_persist<32, 1, 4>(mx, mw, mwlo, y, bias, stats, p, B, st)

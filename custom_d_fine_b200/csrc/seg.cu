@@ -272,6 +272,90 @@ __global__ void mask_cost_final_kernel(const float* __restrict__ acc, const floa
     extra[(long)Q * t0 + (long)q * T + t] = c;
 }
 
+// ---- mask losses (dfine_criterion.py:335-386 cropped BCE, 404-450 cropped Dice, 504-556) ---------------------------
+// pred [M, HW] matched mask logits, gt [sumT, HW] resized GT masks in [0,1], t_idx [M] (int64) the target of every row,
+// tboxes [sumT,4] normalised cxcywh.  Both losses are evaluated INSIDE the GT box only:
+//   bce_row  = sum_inside BCE-with-logits(pred, gt) / max(box area in mask pixels, 1)
+//   dice_row = 1 - (2 sum p*t + 1e-6) / (sum p + sum t + 1e-6),  p = sigmoid(pred) inside the box, t = gt inside the box
+// One CTA per row; sums[m] = {sum p*t, sum p, sum t, area} is kept for the backward.
+struct BoxPx { float x1, y1, x2, y2; };
+__device__ __forceinline__ BoxPx box_px(const float* b, int Hm, int Wm) {
+    BoxPx r;
+    r.x1 = fminf(fmaxf((b[0] - b[2] / 2) * Wm, 0.f), (float)(Wm - 1));
+    r.y1 = fminf(fmaxf((b[1] - b[3] / 2) * Hm, 0.f), (float)(Hm - 1));
+    r.x2 = fminf(fmaxf((b[0] + b[2] / 2) * Wm, 1.f), (float)Wm);
+    r.y2 = fminf(fmaxf((b[1] + b[3] / 2) * Hm, 1.f), (float)Hm);
+    return r;
+}
+__device__ __forceinline__ float block_sum_f(float v, float* sh) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x / 32] = v;
+    __syncthreads();
+    float r = 0.f;
+    for (int i = 0; i < (int)(blockDim.x + 31) / 32; ++i) r += sh[i];
+    return r;
+}
+__global__ void __launch_bounds__(256) mask_loss_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                            const long* __restrict__ t_idx, const float* __restrict__ tboxes,
+                                                            float* __restrict__ bce_row, float* __restrict__ dice_row,
+                                                            float* __restrict__ sums, int Hm, int Wm) {
+    __shared__ float sh[8];
+    const int m = blockIdx.x;
+    const long t = t_idx[m];
+    const BoxPx bx = box_px(tboxes + t * 4, Hm, Wm);
+    const float* pr = pred + (long)m * Hm * Wm;
+    const float* g = gt + t * (long)Hm * Wm;
+    // only the rows / columns that can be inside the box are visited
+    const int ya = (int)ceilf(bx.y1), yb = (int)ceilf(bx.y2);     // y in [ya, yb): y >= y1 and y < y2
+    const int xa = (int)ceilf(bx.x1), xb = (int)ceilf(bx.x2);
+    const int bw = xb - xa, n = (yb - ya) * (bw > 0 ? bw : 0);
+    float bce = 0.f, spt = 0.f, sp = 0.f, st = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int y = ya + i / bw, x = xa + i % bw;
+        const float xv = __ldg(pr + (long)y * Wm + x), tv = __ldg(g + (long)y * Wm + x);
+        const float mv = fmaxf(-xv, 0.f);
+        bce += (1.f - tv) * xv + mv + logf(expf(-mv) + expf(-xv - mv));
+        const float pv = 1.f / (1.f + expf(-xv));
+        spt += pv * tv; sp += pv; st += tv;
+    }
+    bce = block_sum_f(bce, sh); spt = block_sum_f(spt, sh); sp = block_sum_f(sp, sh); st = block_sum_f(st, sh);
+    if (threadIdx.x == 0) {
+        const float area = fmaxf((bx.x2 - bx.x1) * (bx.y2 - bx.y1), 1.f);
+        bce_row[m] = bce / area;
+        dice_row[m] = 1.f - (2.f * spt + 1e-6f) / (sp + st + 1e-6f);
+        sums[4 * m] = spt; sums[4 * m + 1] = sp; sums[4 * m + 2] = st; sums[4 * m + 3] = area;
+    }
+}
+// dpred [M, HW] (written completely: zero outside the box)
+__global__ void __launch_bounds__(256) mask_loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                            const long* __restrict__ t_idx, const float* __restrict__ tboxes,
+                                                            const float* __restrict__ sums, const float* __restrict__ g_bce,
+                                                            const float* __restrict__ g_dice, float* __restrict__ dpred,
+                                                            int Hm, int Wm) {
+    const int m = blockIdx.x;
+    const long t = t_idx[m];
+    const BoxPx bx = box_px(tboxes + t * 4, Hm, Wm);
+    const float* pr = pred + (long)m * Hm * Wm;
+    const float* g = gt + t * (long)Hm * Wm;
+    float* d = dpred + (long)m * Hm * Wm;
+    const float spt = sums[4 * m], sp = sums[4 * m + 1], st = sums[4 * m + 2], area = sums[4 * m + 3];
+    const float N = 2.f * spt + 1e-6f, D = sp + st + 1e-6f;
+    const float cb = g_bce[m] / area, cd = g_dice[m];
+    const int HW = Hm * Wm;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+        const int y = i / Wm, x = i % Wm;
+        float o = 0.f;
+        if ((float)x >= bx.x1 && (float)x < bx.x2 && (float)y >= bx.y1 && (float)y < bx.y2) {
+            const float xv = __ldg(pr + i), tv = __ldg(g + i);
+            const float pv = 1.f / (1.f + expf(-xv));
+            // d dice / d p = -(2 t D - N) / D^2 ; d p / d x = p (1 - p)
+            o = cb * (pv - tv) + cd * (-(2.f * tv * D - N) / (D * D)) * pv * (1.f - pv);
+        }
+        d[i] = o;
+    }
+}
+
 int ew_grid(long n) {
     long g = (n + 255) / 256;
     return (int)(g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g));
@@ -334,6 +418,25 @@ DFINE_API int dfine_mask_cost(const float* logits, const float* gt, const float*
     dim3 g2(ceil_div((long)Q * Tmax, 128), B);
     mask_cost_final_kernel<<<g2, 128, 0, st>>>(workspace, gsum, toff, extra, B, Q, HW, w_dice, w_mask);
     DFINE_LAUNCH_CHECK("mask_cost");
+    return 0;
+}
+
+// Cropped BCE + cropped Dice of M matched mask logits (rows) against their GT masks: bce_row / dice_row [M] (the caller
+// averages them), sums [M,4] scratch kept for the backward.
+DFINE_API int dfine_mask_loss_fwd(const float* pred, const float* gt, const long* t_idx, const float* tboxes, float* bce_row,
+                                  float* dice_row, float* sums, int M, int Hm, int Wm, void* stream) {
+    DFINE_REQUIRE(M >= 0 && Hm > 0 && Wm > 0, "mask_loss: bad dims");
+    if (M == 0) return 0;
+    mask_loss_fwd_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(pred, gt, t_idx, tboxes, bce_row, dice_row, sums, Hm, Wm);
+    DFINE_LAUNCH_CHECK("mask_loss_fwd");
+    return 0;
+}
+DFINE_API int dfine_mask_loss_bwd(const float* pred, const float* gt, const long* t_idx, const float* tboxes, const float* sums,
+                                  const float* g_bce, const float* g_dice, float* dpred, int M, int Hm, int Wm, void* stream) {
+    DFINE_REQUIRE(M >= 0 && Hm > 0 && Wm > 0, "mask_loss_bwd: bad dims");
+    if (M == 0) return 0;
+    mask_loss_bwd_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(pred, gt, t_idx, tboxes, sums, g_bce, g_dice, dpred, Hm, Wm);
+    DFINE_LAUNCH_CHECK("mask_loss_bwd");
     return 0;
 }
 

@@ -1257,6 +1257,33 @@ class _MaskDot(torch.autograd.Function):
         return dembed, dfeat
 
 
+class _MaskLossRows(torch.autograd.Function):
+    """Cropped BCE + cropped Dice per matched mask (dfine_criterion.py:335-450): one kernel forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, pred, gt, t_idx, tboxes):
+        pred, gt = pred.contiguous(), gt.contiguous()
+        t_idx, tboxes = t_idx.contiguous(), tboxes.contiguous().float()
+        M, Hm, Wm = pred.shape
+        bce = torch.empty(M, device=pred.device, dtype=torch.float32)
+        dice = torch.empty(M, device=pred.device, dtype=torch.float32)
+        sums = torch.empty((M, 4), device=pred.device, dtype=torch.float32)
+        _check(lib().dfine_mask_loss_fwd(_p(pred), _p(gt), _p(t_idx), _p(tboxes), _p(bce), _p(dice), _p(sums), M, Hm, Wm,
+                                         _stream()), "mask_loss_fwd")
+        ctx.save_for_backward(pred, gt, t_idx, tboxes, sums)
+        return bce, dice
+
+    @staticmethod
+    def backward(ctx, g_bce, g_dice):
+        pred, gt, t_idx, tboxes, sums = ctx.saved_tensors
+        M, Hm, Wm = pred.shape
+        z = lambda g: torch.zeros(M, device=pred.device) if g is None else g.contiguous().float()   # noqa: E731
+        dpred = torch.empty_like(pred)
+        _check(lib().dfine_mask_loss_bwd(_p(pred), _p(gt), _p(t_idx), _p(tboxes), _p(sums), _p(z(g_bce)), _p(z(g_dice)),
+                                         _p(dpred), M, Hm, Wm, _stream()), "mask_loss_bwd")
+        return dpred, None, None, None
+
+
 class _RowsTimesFeat(torch.autograd.Function):
     """out[m] = rows[m] . feat[b(m)] over the pixels, rows stacked image-major (`totals[b]` rows of image b): one product
     per image forward, two backward, ONE d(feat) tensor."""
@@ -1599,6 +1626,10 @@ class CudaOps:
             res.append((torch.cat(parts) if len(parts) > 1 else parts[0]).reshape(-1, Hm, Wm) if parts
                        else feat_nhwc.new_zeros((0, Hm, Wm)))
         return res
+
+    def mask_loss_rows(self, pred, gt_resized, t_idx, tboxes):
+        """(bce_row [M], dice_row [M]) of matched mask logits pred [M,Hm,Wm] against gt_resized[t_idx] inside the GT boxes."""
+        return _MaskLossRows.apply(pred, gt_resized, t_idx, tboxes)
 
     @torch.no_grad()
     def mask_cost_layer(self, pred_masks, gt, gsum, toff_dev, sizes, alpha, gamma, w_dice, w_mask):

@@ -139,3 +139,31 @@ def test_mask_cost_kernel_matches_torch_formulation(cuda_ops):
     assert got.shape == want.shape
     err = float((got - want).abs().max() / want.abs().max())
     assert err < 2e-5, err
+
+
+def test_mask_loss_kernel_matches_torch_formulation(cuda_ops, monkeypatch):
+    """The fused cropped BCE + Dice kernels (csrc/seg.cu) against the torch formulation of dfine_criterion.py:335-450 in
+    DFINECriterion.loss_masks: values and the gradient of the matched mask logits, incl. boxes that touch the borders and
+    a degenerate (sub-pixel) box."""
+    from types import SimpleNamespace
+    from custom_d_fine_b200.criterion import DFINECriterion
+    g = torch.Generator().manual_seed(4)
+    B, Q, Hm, Wm, T, M = 2, 50, 40, 36, 9, 23
+    boxes = torch.rand(T, 4, generator=g) * 0.5 + 0.2
+    boxes[0] = torch.tensor([0.02, 0.5, 0.2, 0.9])          # clipped on the left
+    boxes[1] = torch.tensor([0.5, 0.99, 0.6, 0.3])          # clipped at the bottom
+    boxes[2] = torch.tensor([0.31, 0.47, 0.004, 0.003])     # smaller than a pixel
+    tg = (None, boxes.cuda(), (torch.rand(T, 2 * Hm, 2 * Wm, generator=g) > 0.5).to(torch.uint8).cuda())
+    S = SimpleNamespace(n=M, v=None, t=torch.randint(0, T, (M,), generator=g).cuda(), b=None, q=None)
+    out = {"pred_masks": torch.zeros(B, Q, Hm, Wm, device="cuda")}
+    crit = DFINECriterion.__new__(DFINECriterion)
+    res = {}
+    for mode in ("kernel", "torch"):
+        monkeypatch.setenv("DFINE_MASK_LOSS", mode)
+        src = (torch.randn(M, Hm, Wm, generator=torch.Generator().manual_seed(5)) * 3).cuda().requires_grad_(True)
+        d = crit.loss_masks(out, S, tg, 1.0, src=src)
+        (d["loss_mask_bce"] * 1.7 + d["loss_mask_dice"] * 0.6).backward()
+        res[mode] = (d["loss_mask_bce"].item(), d["loss_mask_dice"].item(), src.grad.clone())
+    k, t = res["kernel"], res["torch"]
+    assert abs(k[0] - t[0]) < 1e-5 * max(1.0, abs(t[0])) and abs(k[1] - t[1]) < 1e-5
+    assert float((k[2] - t[2]).abs().max()) < 1e-6 + 1e-5 * float(t[2].abs().max())
