@@ -279,6 +279,17 @@ def run_ours(args):
         except (KeyError, ValueError):
             pass
     ridge = tf32_peak * 1e12 / (float(pk0.get("hbm_gbs", 6650.0)) * 1e9)
+    if args.dump_launches:       # per-shape table of the timed families (tools: where the conv time goes)
+        rows = {}
+        for name, recs in cuda_ops.counters.timed.items():
+            for r in recs:
+                a = rows.setdefault((name, r[4]), [0, 0.0, 0, 0])
+                a[0] += 1; a[1] += r[0].elapsed_time(r[1]); a[2] += r[2]; a[3] += r[3]
+        with open(args.dump_launches, "w") as f:
+            f.write("| family | shape | launches/step | us/launch | ms/step | GB/s | TFLOP/s |\n|---|---|---:|---:|---:|---:|---:|\n")
+            for (name, tag), (n, ms, nb, fl) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
+                f.write(f"| {name} | {tag} | {n / args.steps:.1f} | {ms / n * 1e3:.1f} | {ms / args.steps:.3f} | "
+                        f"{nb / ms / 1e6:.0f} | {fl / ms / 1e9:.1f} |\n")
     for name, recs in cuda_ops.counters.timed.items():
         durs = [r[0].elapsed_time(r[1]) for r in recs]
         kern[name] = (sum(durs) / len(durs), sum(r[2] for r in recs) / len(recs), len(durs), sum(durs) / args.steps)
@@ -509,6 +520,7 @@ def main():
                     help="BASELINE.json workload: m640 (headline, configs 1/2), lseg640 (config 3), x1280 (config 4)")
     ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-launches", default=None, help="write the per-shape table of the timed kernel families here")
     args = ap.parse_args()
     args.batch = select_workload(args.config, args.batch)
     if args.impl == "reference":

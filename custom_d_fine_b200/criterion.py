@@ -328,6 +328,15 @@ class DFINECriterion(nn.Module):
             losses["loss_ddf"] = torch.where(identical, pred_all.sum() * 0, ddf)
         return losses
 
+    def _gt_resized(self, tg, Hm, Wm):
+        """Every GT mask resized to the prediction size, once per step (dfine_criterion.py:517-523)."""
+        key = (Hm, Wm, tg[2].data_ptr())
+        if getattr(self, "_mask_cache", (None,))[0] != key:
+            g = tg[2].unsqueeze(1).float()
+            g = F.interpolate(g, size=(Hm, Wm), mode="bilinear", align_corners=False).squeeze(1).clamp_(0, 1)
+            self._mask_cache = (key, g)
+        return self._mask_cache[1]
+
     def loss_masks(self, out, S, tg, num_boxes, src=None):
         """Cropped BCE + cropped Dice of the matched mask logits against the GT masks resized to the prediction size
         (dfine_criterion.py:504-556 with 239-305, 335-386, 404-450): both are evaluated inside the GT box only, the BCE sum
@@ -340,15 +349,13 @@ class DFINECriterion(nn.Module):
             zero = pm.sum() * 0
             return {"loss_mask_bce": zero, "loss_mask_dice": zero}
         assert S.v is None, "per-layer / denoising sets are never padded"
+        if isinstance(src, tuple):       # (bce, dice) of this head, already evaluated with the other heads (mask_losses_multi)
+            return {"loss_mask_bce": src[0], "loss_mask_dice": src[1]}
         if src is not None and torch.is_tensor(src):
-            pred = src       # matched masks evaluated from the mask embeddings (see _matched_mask_logits)
+            pred = src       # matched masks evaluated from the mask embeddings
         else:
             pred = pm.reshape(B * Q, Hm, Wm).index_select(0, S.b * Q + S.q)       # [M, Hm, Wm]
-        key = (Hm, Wm, tg[2].data_ptr())
-        if getattr(self, "_mask_cache", (None,))[0] != key:          # every GT mask resized once per step
-            g = tg[2].unsqueeze(1).float()
-            g = F.interpolate(g, size=(Hm, Wm), mode="bilinear", align_corners=False).squeeze(1).clamp_(0, 1)
-            self._mask_cache = (key, g)
+        self._gt_resized(tg, Hm, Wm)
         if pred.is_cuda and hasattr(K, "mask_loss_rows") and os.environ.get("DFINE_MASK_LOSS", "kernel") != "torch":
             # one kernel each way over the matched masks (csrc/seg.cu) instead of ~60 elementwise passes over [M,Hm,Wm]
             bce_rows, dice_rows = K.mask_loss_rows(pred, self._mask_cache[1], S.t, tg[1])
@@ -683,18 +690,22 @@ class DFINECriterion(nn.Module):
         nb = counts[1]
         sets = [_Set(table, *plan.set_slice(k), Q, False) for k in range(plan.n_sets)] if with_masks else [None] * plan.n_sets
         aux = outputs["aux_outputs"]
-        if msrc is not None and table.is_cuda and hasattr(K, "mask_logits_at_multi"):
-            # Matched mask logits of EVERY head that carries a mask loss, straight from the per-layer mask embeddings, in
-            # one call (one product per image, one gradient for the mask features): the [B,Q,Hm,Wm] logits of the
-            # unmatched queries stay out of the autograd graph.
+        if (msrc is not None and table.is_cuda and hasattr(K, "mask_losses_multi") and tg[2] is not None and tg[2].numel()
+                and sum(plan.per_img) > 0):
+            # Mask losses of EVERY head that carries one, straight from the per-layer mask embeddings of the matched
+            # queries, in one call (one product per image, one gradient for the mask features, one loss kernel each way):
+            # the [B,Q,Hm,Wm] logits of the unmatched queries stay out of the autograd graph.
             req = [(("A", L - 1), msrc["emb"][L - 1], sets[0], plan.per_img)]
             req += [(("A", i), msrc["emb"][i], sets[1 + i], plan.per_img) for i in range(min(L - 1, len(aux)))]
             if DN is not None and msrc["dn_emb"]:
                 s_dn_ = _Set(table, *plan.set_slice("dn"), Q, False)
                 dn_per_ = [s_ * outputs["dn_meta"]["dn_num_group"] for s_ in plan.sizes]
                 req += [(("DN", i), msrc["dn_emb"][i], s_dn_, dn_per_) for i in range(len(msrc["dn_emb"]))]
-            preds = K.mask_logits_at_multi(msrc["feat"], [(e, S_.b, S_.q, per) for _, e, S_, per in req])
-            matched = {key: p_ for (key, _, _, _), p_ in zip(req, preds)}
+            Hm_, Wm_ = msrc["feat"].shape[1:3]
+            bce_, dice_ = K.mask_losses_multi(msrc["feat"], [(e, S_.b, S_.q, S_.t, per) for _, e, S_, per in req],
+                                              self._gt_resized(tg, Hm_, Wm_), tg[1])
+            bce_, dice_ = bce_.unbind(0), dice_.unbind(0)
+            matched = {key: (bce_[j], dice_[j]) for j, (key, _, _, _) in enumerate(req)}
         fam = weighted(*A)
         put("", 0, L - 1, mask_out=outputs, mask_set=sets[0], mask_num=nb, mask_src=src_of("A", L - 1, plan.per_img))
         for i in range(L - 1):

@@ -1136,6 +1136,340 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
     }
 }
 
+// ---- CTA-pair forward on 16-bit split operands (the 3xFP16 / 3xBF16 modes) ------------------------------------------
+// tc_pair_kernel's layout with the converter stage of tc_fwd_persist<.., 2, ..>: each CTA lands its own fp32 pixel tile and
+// its HALF of the two weight planes on its OWN full barrier, its eight converter warps write the hi / lo 16-bit planes of
+// the pixel tile and then signal the LEADER's conv barrier (one elected cluster-scope arrive per warp, 16 per stage); the
+// leader issues three kind::f16 cta_group::2 MMAs (256 pixels x BN channels) per 16-channel k-step.  A stage is
+// 16 KB (fp32 landing) + 16 KB (pixel planes) + BN/16 KB (weight planes): 48 KB at BN = 256 where the single-CTA kernel
+// needs 64 KB, so the ring is 4 deep instead of 3 and the weight planes cost half the L2 -> SM bytes.
+__device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc16_m256(int n, int bf16) {
+    return (1u << 4) | ((uint32_t)bf16 << 7) | ((uint32_t)bf16 << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+struct Pair16Smem {
+    static constexpr int B_PLANE = (BN / 2) * BK * 2;       // bytes of one 16-bit plane of this CTA's half weight tile
+    static constexpr int A2_PLANE = BM * BK * 2;
+    alignas(1024) float a[STAGES][BM * BK];                 // fp32 landing buffer of this CTA's 128 pixel rows
+    alignas(1024) uint8_t a2[STAGES][2 * A2_PLANE];         // [hi | lo] planes written by the converter warps
+    alignas(1024) uint8_t b[STAGES][2 * B_PLANE];           // [hi | lo] planes of BN/2 weight rows
+    alignas(16) float epi[4][32 * EPL];
+    typename StatT<BN>::type statw[4][2 * BN];
+    uint64_t full[STAGES], empty[STAGES], conv[STAGES], tfull[2], tempty[2];
+    uint32_t tmem_base;
+    volatile uint32_t produced;
+};
+constexpr int PAIR16_CONV_WARPS = 8;
+constexpr int PAIR16_THREADS = 32 * (6 + PAIR16_CONV_WARPS + 1);
+
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR16_THREADS, 1)
+    tc_pair16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, float* __restrict__ y,
+                     const float* __restrict__ bias, double* __restrict__ stats, FwdParams p, TileSched ts) {
+    extern __shared__ uint8_t raw[];
+    using Smem = Pair16Smem<BN, STAGES>;
+    Smem& sm = *reinterpret_cast<Smem*>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x / 2, n_pairs = gridDim.x / 2;
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+    const int m_tiles = p.B * tiles_per_img;
+    const int pair_total = ((m_tiles + 1) / 2) * ts.n_tiles;
+    const int cblocks = (p.Cin + BK - 1) / BK;
+    const int num_k = p.n_taps * cblocks;
+    constexpr uint32_t TMEM_COLS = 2 * BN;
+
+    if (stats)
+        for (int i = threadIdx.x; i < 4 * 2 * BN; i += blockDim.x) (&sm.statw[0][0])[i] = 0;
+    if (warp == 0 && lane == 0) { prefetch_tmap(&map_x); prefetch_tmap(&map_w); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); mbar_init(&sm.conv[s], 2 * PAIR16_CONV_WARPS);
+            }
+            for (int a = 0; a < 2; ++a) { mbar_init(&sm.tfull[a], 1); mbar_init(&sm.tempty[a], 8); }
+            sm.produced = 0;
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc2(&sm.tmem_base, TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int t = pair; t < pair_total; t += n_pairs) {
+                const int mp = t / ts.n_tiles, n0 = (t % ts.n_tiles) * BN;
+                const int mt = 2 * mp + (int)rank;
+                const int img = mt / tiles_per_img, tt = mt % tiles_per_img;
+                const int h0 = (tt / p.tiles_w) * p.TH, w0 = (tt % p.tiles_w) * p.TW;
+                const int wn_img = img * p.w_row_off, wk_img = img * p.w_k_off;
+                for (int kb = 0; kb < num_k; ++kb, ++g) {
+                    const int s = g % STAGES, ph = (g / STAGES) & 1;
+                    mbar_wait(&sm.empty[s], ph ^ 1);
+                    const int tap = kb / cblocks, c0 = (kb % cblocks) * BK;
+                    mbar_expect_tx(&sm.full[s], (uint32_t)(p.TW * p.TH * BK * sizeof(float)) + 2u * (uint32_t)Smem::B_PLANE);
+                    tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 * p.in_stride + p.dw[tap], h0 * p.in_stride + p.dh[tap], img);
+                    tma_load_3d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0 + wk_img, n0 + (int)rank * (BN / 2) + wn_img, 0);
+                    sm.produced = g + 1;
+                }
+            }
+            sm.produced = 0x7fffffffu;
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            const uint32_t idesc16 = make_idesc16_m256(BN, p.half16 ? 0 : 1);
+            uint32_t g = 0, i = 0;
+            for (int t = pair; t < pair_total; t += n_pairs, ++i) {
+                const uint32_t acc = i & 1, aph = (i >> 1) & 1;
+                mbar_wait_cluster(&sm.tempty[acc], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem + acc * BN;
+                for (int kb = 0; kb < num_k; ++kb, ++g) {
+                    const int s = g % STAGES, ph = (g / STAGES) & 1;
+                    mbar_wait_cluster(&sm.conv[s], ph);          // both CTAs' planes written, both weight halves landed
+                    tc_fence_after();
+                    const uint64_t ah = make_desc(smem_u32(sm.a2[s]), 16, 512, 4);
+                    const uint64_t al = make_desc(smem_u32(sm.a2[s] + Smem::A2_PLANE), 16, 512, 4);
+                    const uint64_t bh = make_desc(smem_u32(sm.b[s]), 16, 512, 4);
+                    const uint64_t bl = make_desc(smem_u32(sm.b[s] + Smem::B_PLANE), 16, 512, 4);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        umma_f16_2cta(d, al + 2 * k, bh + 2 * k, idesc16, (kb | k) != 0);
+                        umma_f16_2cta(d, ah + 2 * k, bl + 2 * k, idesc16, 1);
+                        umma_f16_2cta(d, ah + 2 * k, bh + 2 * k, idesc16, 1);
+                    }
+                    umma_commit_pair(&sm.empty[s]);
+                }
+                umma_commit_pair(&sm.tfull[acc]);
+            }
+        }
+        __syncwarp();
+    } else if (warp < 6) {
+        const int q = warp % 4;
+        const uint32_t wbase = smem_u32(sm.epi[q]);
+        const bool plain = (bias == nullptr) && p.act == 0 && !p.lab;
+        const bool local_stats = stats != nullptr && ts.n_tiles == 1;
+        typename StatT<BN>::type* sw = sm.statw[q];
+        uint32_t i = 0;
+        for (int t = pair; t < pair_total; t += n_pairs, ++i) {
+            const uint32_t acc = i & 1, aph = (i >> 1) & 1;
+            const int mp = t / ts.n_tiles, n0 = (t % ts.n_tiles) * BN;
+            const int mt = 2 * mp + (int)rank;
+            const bool tile_ok = mt < m_tiles;
+            const int img = mt / tiles_per_img, tt = mt % tiles_per_img;
+            const int h0 = (tt / p.tiles_w) * p.TH, w0 = (tt % p.tiles_w) * p.TW;
+            long row_off[8];
+            bool row_ok[8];
+#pragma unroll
+            for (int r8 = 0; r8 < 8; ++r8) {
+                const int r = 32 * q + 4 * r8 + lane / 8;
+                const int th = r / p.TW, tw = r % p.TW;
+                const int oh = h0 + th, ow = w0 + tw;
+                row_ok[r8] = tile_ok && th < p.TH && oh < p.OH && ow < p.OW;
+                row_off[r8] = ((long)img * p.YH + (long)oh * p.osy + p.ooy) * p.YW + (long)ow * p.osx + p.oox;
+            }
+            mbar_wait(&sm.tfull[acc], aph);
+            tc_fence_after();
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (n0 + c0 >= p.N) break;
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + acc * BN + (uint32_t)c0, v);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4)
+                    sts128(wbase + (uint32_t)(lane * EPL + 4 * c4) * 4u, __uint_as_float(v[4 * c4]),
+                           __uint_as_float(v[4 * c4 + 1]), __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
+                __syncwarp();
+                const int col = n0 + c0 + 4 * (lane % 8);
+                const bool col_ok = col < p.N;
+                float4 bv = make_float4(0, 0, 0, 0);
+                if (bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+                float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int r8 = 0; r8 < 8; ++r8) {
+                    const int r = 4 * r8 + lane / 8;
+                    float4 o = lds128(wbase + (uint32_t)(r * EPL + 4 * (lane % 8)) * 4u);
+                    o.x *= p.out_scale; o.y *= p.out_scale; o.z *= p.out_scale; o.w *= p.out_scale;
+                    if (row_ok[r8] && col_ok) {
+                        if (stats) {
+                            s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
+                            s2[0] += o.x * o.x; s2[1] += o.y * o.y; s2[2] += o.z * o.z; s2[3] += o.w * o.w;
+                        }
+                        if (!plain) {
+                            o.x = act_fwd(o.x + bv.x, p.act); o.y = act_fwd(o.y + bv.y, p.act);
+                            o.z = act_fwd(o.z + bv.z, p.act); o.w = act_fwd(o.w + bv.w, p.act);
+                            if (p.lab) {
+                                o.x = fmaf(o.x, p.lab_s, p.lab_b); o.y = fmaf(o.y, p.lab_s, p.lab_b);
+                                o.z = fmaf(o.z, p.lab_s, p.lab_b); o.w = fmaf(o.w, p.lab_s, p.lab_b);
+                            }
+                        }
+                        *reinterpret_cast<float4*>(y + row_off[r8] * p.ldy + col) = o;
+                    }
+                }
+                if (stats) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8); s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
+                        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+                    }
+                    if (lane < 8 && col_ok) {
+                        if (local_stats) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { sw[c0 + 4 * lane + j] += s1[j]; sw[BN + c0 + 4 * lane + j] += s2[j]; }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                atomicAdd(stats + col + j, (double)s1[j]);
+                                atomicAdd(stats + p.N + col + j, (double)s2[j]);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader_release(&sm.tempty[acc]);
+        }
+    } else if (warp == 6 + PAIR16_CONV_WARPS) {
+        // L2 prefetch warp (see tc_fwd_persist): walks this CTA's (tile, k-block) sequence ahead of its producer
+        if (p.prefetch > 0) {
+            const uint32_t my_tiles = (uint32_t)((pair_total - pair + n_pairs - 1) / n_pairs);
+            const uint32_t total_k = my_tiles * (uint32_t)num_k;
+            const uint32_t dmin = STAGES, dmax = STAGES + (uint32_t)p.prefetch;
+            uint32_t gp = 0;
+            while (gp < total_k) {
+                const uint32_t done = sm.produced;
+                if (done >= total_k) break;
+                if (gp < done + dmin) gp = done + dmin;
+                if (gp >= total_k) break;
+                if (gp > done + dmax) { __nanosleep(200); continue; }
+                const int t = pair + (int)(gp / (uint32_t)num_k) * n_pairs;
+                const int kb = (int)(gp % (uint32_t)num_k);
+                const int mt = 2 * (t / ts.n_tiles) + (int)rank;
+                const int img = mt / tiles_per_img, tt = mt % tiles_per_img;
+                const int h0 = (tt / p.tiles_w) * p.TH, w0 = (tt % p.tiles_w) * p.TW;
+                const int tap = kb / cblocks, c0 = (kb % cblocks) * BK;
+                if (t % ts.n_tiles == 0 && img < p.B) {
+#pragma unroll
+                    for (int rr = 0; rr < BM / 32; ++rr) {
+                        const int r = lane + 32 * rr;
+                        const int th = r / p.TW, tw = r % p.TW;
+                        const int ih = (h0 + th) * p.in_stride + p.dh[tap], iw = (w0 + tw) * p.in_stride + p.dw[tap];
+                        if (th < p.TH && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
+                            const float* a = p.x + (((long)img * p.H + ih) * p.W + iw) * p.ldx + c0;
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                            if (((uintptr_t)a & 127) != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 31));
+                        }
+                    }
+                }
+                ++gp;
+            }
+        }
+    } else {
+        // converter warps: this CTA's fp32 pixel tile -> hi / lo 16-bit planes (index algebra in tc_fwd_persist)
+        constexpr int CT = 32 * PAIR16_CONV_WARPS;
+        const int ct = threadIdx.x - 192;
+        uint32_t g = 0;
+        for (int t = pair; t < pair_total; t += n_pairs) {
+            for (int kb = 0; kb < num_k; ++kb, ++g) {
+                const int s = g % STAGES, ph = (g / STAGES) & 1;
+                mbar_wait(&sm.full[s], ph);
+                const uint32_t a_base = smem_u32(sm.a[s]), l_base = smem_u32(sm.a2[s]);
+                constexpr int ITEMS = BM * 4 / CT;
+                float4 v0[ITEMS], v1[ITEMS];
+#pragma unroll
+                for (int i = 0; i < ITEMS; ++i) {
+                    const uint32_t idx = (uint32_t)(ct + i * CT);
+                    v0[i] = lds128(a_base + idx * 32u);
+                    v1[i] = lds128(a_base + idx * 32u + 16u);
+                }
+#pragma unroll
+                for (int i = 0; i < ITEMS; ++i) {
+                    const uint32_t idx = (uint32_t)(ct + i * CT);
+                    float4 x0 = v0[i], x1 = v1[i];
+                    if ((idx >> 2) & 1) { float4 tmp = x0; x0 = x1; x1 = tmp; }
+                    uint32_t b0, b1, b2, b3, l0, l1, l2, l3;
+                    if (p.half16) {
+                        b0 = f16x2_rn(x0.x, x0.y); b1 = f16x2_rn(x0.z, x0.w);
+                        b2 = f16x2_rn(x1.x, x1.y); b3 = f16x2_rn(x1.z, x1.w);
+                        l0 = f16x2_rn(x0.x - f16_lo(b0), x0.y - f16_hi(b0));
+                        l1 = f16x2_rn(x0.z - f16_lo(b1), x0.w - f16_hi(b1));
+                        l2 = f16x2_rn(x1.x - f16_lo(b2), x1.y - f16_hi(b2));
+                        l3 = f16x2_rn(x1.z - f16_lo(b3), x1.w - f16_hi(b3));
+                    } else {
+                        b0 = bf16x2_rn(x0.x, x0.y); b1 = bf16x2_rn(x0.z, x0.w);
+                        b2 = bf16x2_rn(x1.x, x1.y); b3 = bf16x2_rn(x1.z, x1.w);
+                        l0 = bf16x2_rn(x0.x - __uint_as_float(b0 << 16), x0.y - __uint_as_float(b0 & 0xffff0000u));
+                        l1 = bf16x2_rn(x0.z - __uint_as_float(b1 << 16), x0.w - __uint_as_float(b1 & 0xffff0000u));
+                        l2 = bf16x2_rn(x1.x - __uint_as_float(b2 << 16), x1.y - __uint_as_float(b2 & 0xffff0000u));
+                        l3 = bf16x2_rn(x1.z - __uint_as_float(b3 << 16), x1.w - __uint_as_float(b3 & 0xffff0000u));
+                    }
+                    const uint32_t pa = l_base + idx * 16u, pb = l_base + (uint32_t)Smem::A2_PLANE + idx * 16u;
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pa), "r"(b0), "r"(b1), "r"(b2), "r"(b3) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pb), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
+                }
+                fence_proxy_async();
+                __syncwarp();
+                // (every thread's plane writes are fenced to the async proxy above and ordered before lane 0's arrive by
+                // the warp barrier; a cluster-scope release on this arrive doubled the k-block time: the planes of the
+                // PEER are only ever read by the peer's own tensor core, after the leader has seen this arrival and issued
+                // the MMA — DFINE_TC_DBG=22 restores the cluster-scope release for A/B runs)
+                if (lane == 0) {
+                    if (p.dbg == 22) mbar_arrive_leader_release(&sm.conv[s]);
+                    else mbar_arrive_leader(&sm.conv[s]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    if (warp == 1) tmem_dealloc2(tmem, TMEM_COLS);
+    if (stats && ts.n_tiles == 1) {
+        for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
+            const int c = i % BN, which = i / BN;
+            const double v = (double)sm.statw[0][i] + (double)sm.statw[1][i] + (double)sm.statw[2][i] + (double)sm.statw[3][i];
+            if (c < p.N && v != 0.0) atomicAdd(stats + (long)which * p.N + c, v);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------- wgrad
 constexpr int WG_THREADS = 192;
 constexpr int WG_STAGES = 3;
@@ -1424,6 +1758,14 @@ int launch_persist(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorM
     return 0;
 }
 
+// Few pixel tiles (the decoder's 8000-row linears, the 20x20 maps): a narrower N tile puts more CTAs on the 148 SMs and
+// shortens every CTA's epilogue; the pixel tile is then re-read by the N tiles of its patch from L2.  DFINE_TC_FILL=0: off.
+int fill_bn(int bn, int m_tiles, int Cout) {
+    static const bool on = [] { const char* e = getenv("DFINE_TC_FILL"); return !(e && e[0] == '0'); }();
+    while (on && bn > 64 && (long)m_tiles * ceil_div(Cout, bn) < 120) bn /= 2;
+    return bn;
+}
+
 template <int BN, int STAGES>
 int launch_pair(const CUtensorMap& mx, const CUtensorMap& mw, float* y, const float* bias, double* stats, const FwdParams& p,
                 int B, cudaStream_t st) {
@@ -1449,6 +1791,34 @@ int launch_pair(const CUtensorMap& mx, const CUtensorMap& mw, float* y, const fl
     int pairs = ts.total < max_pairs ? ts.total : max_pairs;
     if (pairs < 1) pairs = 1;
     tc_pair_kernel<BN, STAGES><<<2 * pairs, PAIR_THREADS, smem, st>>>(mx, mw, y, bias, stats, p, ts);
+    return 0;
+}
+
+template <int BN, int STAGES>
+int launch_pair16(const CUtensorMap& mx, const CUtensorMap& mw, float* y, const float* bias, double* stats, const FwdParams& p,
+                  int B, cudaStream_t st) {
+    static_assert(sizeof(Pair16Smem<BN, STAGES>) + 1024 <= 232448, "tc_pair16: shared memory");
+    const int smem = (int)sizeof(Pair16Smem<BN, STAGES>) + 1024;
+    DFINE_SET_SMEM_ONCE((tc_pair16_kernel<BN, STAGES>), smem, "tc_pair16");
+    TileSched ts;
+    ts.n_tiles = ceil_div(p.N, BN);
+    const int m_tiles = B * p.tiles_w * p.tiles_h;
+    ts.total = ((m_tiles + 1) / 2) * ts.n_tiles;
+    static const int max_pairs = [&] {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(sm_count(), 1, 1);
+        cfg.blockDim = dim3(PAIR16_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, tc_pair16_kernel<BN, STAGES>, &cfg) != cudaSuccess || n < 1) {
+            cudaGetLastError();
+            n = sm_count() / 2;
+        }
+        return n < sm_count() / 2 ? n : sm_count() / 2;
+    }();
+    int pairs = ts.total < max_pairs ? ts.total : max_pairs;
+    if (pairs < 1) pairs = 1;
+    tc_pair16_kernel<BN, STAGES><<<2 * pairs, PAIR16_THREADS, smem, st>>>(mx, mw, y, bias, stats, p, ts);
     return 0;
 }
 
@@ -1543,7 +1913,8 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
         const long ld16 = hybrid ? ldw16 : ldw;
         // 256-wide tiles (the A patch is then read and converted once for Cout = 256) on the two-plane 16-bit modes
         static const bool wide16 = [] { const char* e = getenv("DFINE_TC_WIDE16"); return !(e && e[0] == '0'); }();
-        const int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : ((Cout <= 128 || hybrid || !wide16) ? 128 : 256));
+        int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : ((Cout <= 128 || hybrid || !wide16) ? 128 : 256));
+        bn = fill_bn(bn, B * p.tiles_w * p.tiles_h, Cout);
         EncodeTiledFn enc = get_encode();
         if (!enc) { dfine_set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return -2; }
         if (hybrid) {
@@ -1562,7 +1933,15 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
         const cuuint64_t pstride = plane_stride16 > 0 ? (cuuint64_t)plane_stride16 * 2 : (cuuint64_t)ld16 * 2 * WR;
         DFINE_REQUIRE(pstride % 16 == 0, "conv_tc: 16-bit plane stride %ld must be a multiple of 8 elements", plane_stride16);
         cuuint64_t strides[2] = {(cuuint64_t)ld16 * 2, pstride};
-        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)bn, 2};
+        // CTA-pair kernel (cta_group::2): every CTA fetches HALF of the N tile's rows.  Opt-in (DFINE_TC_PAIR16=1): worth
+        // 0.2 ms of the 40 ms D-FINE-m step and not yet cleared by the parity suite in every mode.
+        static const bool use_pair16 = [] { const char* e = getenv("DFINE_TC_PAIR16"); return e && e[0] == '1'; }();
+        // (per-image weights: both CTAs of a pair must sit in the same image — an even tile count per image)
+        const bool pair_grouped_ok = (w_row_off == 0 && w_k_off == 0) || (p.tiles_w * p.tiles_h) % 2 == 0;
+        // (measured, profiles/r2_pair16_microbench.txt: +6..13 % on the 256-wide tiles, -8..13 % on 128-wide ones, where
+        // waiting for the converter warps of BOTH CTAs costs more than the halved weight traffic saves)
+        const bool pair16 = use_pair16 && !hybrid && bn == 256 && (long)B * p.tiles_w * p.tiles_h >= 2 && pair_grouped_ok;
+        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(pair16 ? bn / 2 : bn), 2};
         cuuint32_t es[3] = {1, 1, 1};
         CUresult r = enc(&mw, half16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                          const_cast<void*>(w_bf16), dims, strides, box, es,
@@ -1574,6 +1953,12 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
         }
         p.w_planes = 1;
         cudaStream_t st = (cudaStream_t)stream;
+        if (pair16) {
+            rc = launch_pair16<256, 4>(mx, mw, y, bias, stats, p, B, st);
+            if (rc) return rc;
+            DFINE_LAUNCH_CHECK("conv_tc(16-bit planes, pair)");
+            return 0;
+        }
         if (hybrid) {     // map_w = fp32 hi plane (encoded into mwlo above), map_wlo = the bf16 planes (in mw)
             rc = bn == 32 ? launch_persist<32, 3, 4>(mx, mwlo, mw, y, bias, stats, p, B, st)
                : bn == 64 ? launch_persist<64, 3, 4>(mx, mwlo, mw, y, bias, stats, p, B, st)
@@ -1591,7 +1976,8 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
     static const bool persist_bn = [] { const char* e = getenv("DFINE_TC_PERSIST"); return !(e && e[0] == '0'); }();
     // N tile: one tile covers Cout when it can (the A patch is then read exactly once); 256-wide tiles only on
     // the persistent plain-tf32 kernel (its smem ring has room for 48 KB stages)
-    const int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : ((Cout <= 128 || w_lo || !persist_bn) ? 128 : 256));
+    int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : ((Cout <= 128 || w_lo || !persist_bn) ? 128 : 256));
+    bn = fill_bn(bn, B * p.tiles_w * p.tiles_h, Cout);
     rc = make_map2(&mw, w, ldw, WR, ldw, BK, bn, "conv_tc(w)");
     if (rc) return rc;
     mwlo = mw;
@@ -1623,11 +2009,14 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
     // CTA-pair kernel (cta_group::2) for the plain-tf32 launches with at least a few pixel-tile pairs per SM pair and no
     // fused residual: the weight map then delivers HALF an N tile per CTA.  DFINE_TC_PAIR=0 keeps the single-CTA kernel.
     static const bool use_pair = [] { const char* e = getenv("DFINE_TC_PAIR"); return !(e && e[0] == '0'); }();
-    if (persist && use_pair && !w_lo && !res && bn >= 128 && (long)B * p.tiles_w * p.tiles_h >= 2) {
+    const bool pair_grouped_ok = (w_row_off == 0 && w_k_off == 0) || (p.tiles_w * p.tiles_h) % 2 == 0;
+    if (persist && use_pair && !w_lo && !res && bn >= 64 && (long)B * p.tiles_w * p.tiles_h >= 2 && pair_grouped_ok) {
         CUtensorMap mwh;
         rc = make_map2(&mwh, w, ldw, WR, ldw, BK, bn / 2, "conv_tc(w half)");
         if (rc) return rc;
-        rc = bn == 128 ? launch_pair<128, 8>(mx, mwh, y, bias, stats, p, B, st) : launch_pair<256, 6>(mx, mwh, y, bias, stats, p, B, st);
+        rc = bn == 64  ? launch_pair<64, 8>(mx, mwh, y, bias, stats, p, B, st)
+           : bn == 128 ? launch_pair<128, 8>(mx, mwh, y, bias, stats, p, B, st)
+                       : launch_pair<256, 6>(mx, mwh, y, bias, stats, p, B, st);
         if (rc) return rc;
         DFINE_LAUNCH_CHECK("conv_tc(pair)");
         return 0;

@@ -132,3 +132,281 @@ DFINE_API int dfine_stem_conv_wgrad(const float* dy, long ldy, const float* x, l
     DFINE_LAUNCH_CHECK("stem_conv_wgrad");
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// The two 2x2 convolutions of the stem (hgnetv2.py:125-140 `stem2a` C1 -> C1/2 and `stem2b` C1/2 -> C1, kernel 2,
+// stride 1, on the input padded by one pixel at the bottom / right): 8..32 channels on the 320x320 map.  Through the
+// tensor-core path these layers ran at 0.1-0.2 of the HBM roofline (250 us forward, 170-270 us data gradient, 365 us
+// weight gradient per layer at batch 16: channel counts below the 32-channel k-block, N = 12 / 24 tiles of 128-row MMAs,
+// every pixel fetched once per tap).  Direct fp32 kernels:
+//   conv2x2_kernel   forward and data gradient (the data gradient is the same correlation on dy with the taps flipped and
+//                    the zero border at the top / left: the host passes flipped, transposed weights and origin = -1).
+//                    A CTA stages a (8+1) x (64+1) pixel tile in shared memory (pixel pitch CI + 4 floats), every thread
+//                    owns a 2 x 2 output block x all CO channels: 16 FMAs per 16-byte broadcast weight read.  Optional
+//                    fused BatchNorm statistics (sum | sum of squares per channel, double), flushed once per CTA.
+//   conv2x2_wgrad_kernel  a warp streams over output pixels; lane = (channel group, 4 consecutive k of the 4*CI patch
+//                    row), COL x 4 accumulators per lane; CTA-level reduction in shared memory, one atomic per weight and CTA.
+namespace {
+
+constexpr int C2_TH = 8, C2_TW = 64, C2_THREADS = 128;
+
+template <int CI, int CO>
+__global__ void __launch_bounds__(C2_THREADS) conv2x2_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ wt,
+                                                             float* __restrict__ y, long ldy, double* __restrict__ stats, int B,
+                                                             int H, int W, int origin, int tiles_w, int tiles_h) {
+    constexpr int PITCH = CI + 4;                       // floats per staged pixel: conflict-free float4 reads across lanes
+    extern __shared__ float4 c2_smem4[];
+    float* xs = reinterpret_cast<float*>(c2_smem4);                                   // [(TH+1)*(TW+1)][PITCH]
+    float* ws = xs + (C2_TH + 1) * (C2_TW + 1) * PITCH;                               // [4*CI][CO]
+    double* st = reinterpret_cast<double*>(ws + 4 * CI * CO);                         // [4 warps][2*CO]
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    for (int i = threadIdx.x; i < 4 * CI * CO / 4; i += C2_THREADS)
+        reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(wt) + i);
+    if (stats)
+        for (int i = threadIdx.x; i < 4 * 2 * CO; i += C2_THREADS) st[i] = 0.0;
+    const int total = B * tiles_h * tiles_w;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int b = t / (tiles_h * tiles_w), tt = t % (tiles_h * tiles_w);
+        const int h0 = (tt / tiles_w) * C2_TH, w0 = (tt % tiles_w) * C2_TW;
+        __syncthreads();                                // the previous tile's readers are done (and ws / st are written)
+        // staged U float4 per thread at a time, all loads issued before the first shared-memory store (one load in
+        // flight per thread left the kernel latency-bound at 1.2 TB/s)
+        constexpr int NV = (C2_TH + 1) * (C2_TW + 1) * (CI / 4), U = 8;
+        for (int base = 0; base < NV; base += C2_THREADS * U) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * C2_THREADS + threadIdx.x;
+                const int c4 = i % (CI / 4), px = i / (CI / 4);
+                const int r = px / (C2_TW + 1), c = px % (C2_TW + 1);
+                const int ih = h0 + origin + r, iw = w0 + origin + c;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < NV && ih >= 0 && ih < H && iw >= 0 && iw < W)
+                    v[u] = __ldg(reinterpret_cast<const float4*>(x + (((long)b * H + ih) * W + iw) * ldx + 4 * c4));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * C2_THREADS + threadIdx.x;
+                if (i < NV) *reinterpret_cast<float4*>(xs + (i / (CI / 4)) * PITCH + 4 * (i % (CI / 4))) = v[u];
+            }
+        }
+        __syncthreads();
+        float acc[2][2][CO];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+                for (int c = 0; c < CO; ++c) acc[a][bb][c] = 0.f;
+        const float* xb = xs + ((2 * warp) * (C2_TW + 1) + 2 * lane) * PITCH;
+#pragma unroll 1
+        for (int c4 = 0; c4 < CI / 4; ++c4) {
+            float4 xv[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    xv[i][j] = *reinterpret_cast<const float4*>(xb + (i * (C2_TW + 1) + j) * PITCH + 4 * c4);
+#pragma unroll
+            for (int tap = 0; tap < 4; ++tap) {
+                const int dh = tap / 2, dw = tap % 2;
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const float* wrow = ws + ((tap * CI) + 4 * c4 + cc) * CO;
+#pragma unroll
+                    for (int q = 0; q < CO / 4; ++q) {
+                        const float4 w = *reinterpret_cast<const float4*>(wrow + 4 * q);
+#pragma unroll
+                        for (int a = 0; a < 2; ++a)
+#pragma unroll
+                            for (int bb = 0; bb < 2; ++bb) {
+                                const float4 xq = xv[a + dh][bb + dw];
+                                const float xe = cc == 0 ? xq.x : (cc == 1 ? xq.y : (cc == 2 ? xq.z : xq.w));
+                                acc[a][bb][4 * q] += xe * w.x; acc[a][bb][4 * q + 1] += xe * w.y;
+                                acc[a][bb][4 * q + 2] += xe * w.z; acc[a][bb][4 * q + 3] += xe * w.w;
+                            }
+                    }
+                }
+            }
+        }
+        float s1[CO], s2[CO];
+#pragma unroll
+        for (int c = 0; c < CO; ++c) s1[c] = s2[c] = 0.f;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb) {
+                const int oh = h0 + 2 * warp + a, ow = w0 + 2 * lane + bb;
+                if (oh < H && ow < W) {
+                    float* o = y + (((long)b * H + oh) * W + ow) * ldy;
+#pragma unroll
+                    for (int q = 0; q < CO / 4; ++q)
+                        *reinterpret_cast<float4*>(o + 4 * q) =
+                            make_float4(acc[a][bb][4 * q], acc[a][bb][4 * q + 1], acc[a][bb][4 * q + 2], acc[a][bb][4 * q + 3]);
+                    if (stats) {
+#pragma unroll
+                        for (int c = 0; c < CO; ++c) { s1[c] += acc[a][bb][c]; s2[c] += acc[a][bb][c] * acc[a][bb][c]; }
+                    }
+                }
+            }
+        if (stats) {
+#pragma unroll
+            for (int c = 0; c < CO; ++c) {
+                const float v1 = warp_sum(s1[c]), v2 = warp_sum(s2[c]);
+                if (lane == 0) { st[warp * 2 * CO + c] += (double)v1; st[warp * 2 * CO + CO + c] += (double)v2; }
+            }
+        }
+    }
+    if (stats) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * CO; i += C2_THREADS) {
+            const double v = st[i] + st[2 * CO + i] + st[4 * CO + i] + st[6 * CO + i];
+            if (v != 0.0) atomicAdd(stats + i, v);
+        }
+    }
+}
+
+template <int CI, int CO>
+__global__ void __launch_bounds__(256) conv2x2_wgrad_kernel(const float* __restrict__ dy, long ldy, const float* __restrict__ x,
+                                                            long ldx, float* __restrict__ dwr, int B, int H, int W,
+                                                            long px_per_warp) {
+    constexpr int K = 4 * CI;
+    constexpr int G = 32 / CI;                  // channel groups a warp covers side by side (CI lanes per group)
+    constexpr int COL = CO / G;                 // output channels per lane
+    static_assert(G >= 1 && CO % G == 0 && COL % 4 == 0, "conv2x2_wgrad: lane tiling");
+    __shared__ float red[CO * K];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int g = lane / CI, kq = lane % CI;    // kq: float4 index inside the 4*CI patch row
+    const bool active = g < G;
+    const int tap = kq / (CI / 4), c4 = kq % (CI / 4);
+    const int dh = tap / 2, dw = tap % 2;
+    for (int i = threadIdx.x; i < CO * K; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    float acc[COL][4];
+#pragma unroll
+    for (int c = 0; c < COL; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+    const long P = (long)B * H * W;
+    const long gw = (long)blockIdx.x * (blockDim.x / 32) + warp;
+    const long p0 = gw * px_per_warp, p1 = p0 + px_per_warp < P ? p0 + px_per_warp : P;
+    if (active) {
+        constexpr int UP = 4;               // pixels per iteration: their loads are all in flight before the first FMA
+        for (long pb = p0; pb < p1; pb += UP) {
+            float4 xv[UP], gv[UP][COL / 4];
+#pragma unroll
+            for (int u = 0; u < UP; ++u) {
+                const long p = pb + u;
+                const bool in = p < p1;
+                const long pc = in ? p : p0;
+                const int ow = (int)(pc % W), oh = (int)((pc / W) % H), b = (int)(pc / ((long)W * H));
+                const int ih = oh + dh, iw = ow + dw;
+                xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (in && ih < H && iw < W)
+                    xv[u] = __ldg(reinterpret_cast<const float4*>(x + (((long)b * H + ih) * W + iw) * ldx + 4 * c4));
+                const float* d = dy + pc * ldy + g * COL;
+#pragma unroll
+                for (int q = 0; q < COL / 4; ++q) gv[u][q] = __ldg(reinterpret_cast<const float4*>(d + 4 * q));
+            }
+#pragma unroll
+            for (int u = 0; u < UP; ++u)
+#pragma unroll
+                for (int q = 0; q < COL / 4; ++q) {
+                    const float4 a = gv[u][q], v = xv[u];       // (xv is zero for the padded tail pixels)
+                    acc[4 * q][0] += a.x * v.x; acc[4 * q][1] += a.x * v.y; acc[4 * q][2] += a.x * v.z; acc[4 * q][3] += a.x * v.w;
+                    acc[4 * q + 1][0] += a.y * v.x; acc[4 * q + 1][1] += a.y * v.y; acc[4 * q + 1][2] += a.y * v.z; acc[4 * q + 1][3] += a.y * v.w;
+                    acc[4 * q + 2][0] += a.z * v.x; acc[4 * q + 2][1] += a.z * v.y; acc[4 * q + 2][2] += a.z * v.z; acc[4 * q + 2][3] += a.z * v.w;
+                    acc[4 * q + 3][0] += a.w * v.x; acc[4 * q + 3][1] += a.w * v.y; acc[4 * q + 3][2] += a.w * v.z; acc[4 * q + 3][3] += a.w * v.w;
+                }
+        }
+#pragma unroll
+        for (int c = 0; c < COL; ++c)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) atomicAdd(&red[(g * COL + c) * K + 4 * kq + j], acc[c][j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CO * K; i += blockDim.x)
+        if (red[i] != 0.f) atomicAdd(dwr + i, red[i]);
+}
+
+template <int CI, int CO>
+int launch_conv2x2(const float* x, long ldx, const float* wt, float* y, long ldy, double* stats, int B, int H, int W, int origin,
+                   cudaStream_t st) {
+    const int smem = ((C2_TH + 1) * (C2_TW + 1) * (CI + 4) + 4 * CI * CO) * 4 + 4 * 2 * CO * 8;
+    DFINE_SET_SMEM_ONCE((conv2x2_kernel<CI, CO>), smem, "conv2x2");
+    const int tiles_w = ceil_div(W, C2_TW), tiles_h = ceil_div(H, C2_TH);
+    const long total = (long)B * tiles_w * tiles_h;
+    const int per_sm = smem > 110 * 1024 ? 1 : (smem > 72 * 1024 ? 2 : 3);
+    const long cap = 148L * per_sm;
+    conv2x2_kernel<CI, CO><<<(int)(total < cap ? total : cap), C2_THREADS, smem, st>>>(x, ldx, wt, y, ldy, stats, B, H, W, origin,
+                                                                                     tiles_w, tiles_h);
+    return 0;
+}
+
+template <int CI, int CO>
+int launch_conv2x2_wgrad(const float* dy, long ldy, const float* x, long ldx, float* dwr, int B, int H, int W, cudaStream_t st) {
+    const long P = (long)B * H * W;
+    static const int per_sm = [] {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, conv2x2_wgrad_kernel<CI, CO>, 256, 0) != cudaSuccess || n < 1) n = 1;
+        return n > 4 ? 4 : n;
+    }();
+    const int ctas = 148 * per_sm, warps = ctas * 8;
+    const long per = (P + warps - 1) / warps;
+    conv2x2_wgrad_kernel<CI, CO><<<ctas, 256, 0, st>>>(dy, ldy, x, ldx, dwr, B, H, W, per);
+    return 0;
+}
+
+#define C2_DISPATCH(CI_, CO_, CALL)                                         \
+    if (CI_ == 24 && CO_ == 12) return CALL(24, 12);                        \
+    if (CI_ == 12 && CO_ == 24) return CALL(12, 24);                        \
+    if (CI_ == 32 && CO_ == 16) return CALL(32, 16);                        \
+    if (CI_ == 16 && CO_ == 32) return CALL(16, 32);                        \
+    if (CI_ == 16 && CO_ == 8) return CALL(16, 8);                          \
+    if (CI_ == 8 && CO_ == 16) return CALL(8, 16);
+
+}  // namespace
+
+// 1 if the direct 2x2 kernels take this geometry (kernel 2, stride 1, one pixel of zero padding at the bottom / right).
+DFINE_API int dfine_conv2x2_supported(int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l, int pad_b, int pad_r,
+                                      long ldx, long ldy) {
+    const bool pair = (Cin == 24 && Cout == 12) || (Cin == 12 && Cout == 24) || (Cin == 32 && Cout == 16) ||
+                      (Cin == 16 && Cout == 32) || (Cin == 16 && Cout == 8) || (Cin == 8 && Cout == 16);
+    return pair && KH == 2 && KW == 2 && stride == 1 && pad_t == 0 && pad_l == 0 && pad_b == 1 && pad_r == 1 && ldx % 4 == 0 &&
+           ldy % 4 == 0;
+}
+
+// y[B,H,W,Cout] (pixel stride ldy) = sum over the 4 taps (i, j) of x[b, h + origin + i, w + origin + j, :] . wt[(2i + j)][Cin][Cout]
+// with zeros outside the image.  origin = 0 with wt[tap][ci][co] = w[co][ci][i][j]: the forward conv; origin = -1 on dy with
+// wt[(2i + j)][co][ci] = w[co][ci][1 - i][1 - j]: its data gradient (Cin / Cout then name dy's / dx's channels).
+// stats (optional, double [2*Cout], accumulated): per-channel sum | sum of squares of y.
+DFINE_API int dfine_conv2x2(const float* x, long ldx, const float* wt, float* y, long ldy, double* stats, int B, int H, int W,
+                            int Cin, int Cout, int origin, void* stream) {
+    DFINE_REQUIRE(dfine_conv2x2_supported(Cin, Cout, 2, 2, 1, 0, 0, 1, 1, ldx, ldy) && (origin == 0 || origin == -1) &&
+                      ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)wt % 16) == 0,
+                  "conv2x2: %d -> %d, strides %ld / %ld unsupported", Cin, Cout, ldx, ldy);
+    if ((long)B * H * W == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+#define C2_FWD(CI_, CO_) launch_conv2x2<CI_, CO_>(x, ldx, wt, y, ldy, stats, B, H, W, origin, st)
+    auto run = [&]() -> int { C2_DISPATCH(Cin, Cout, C2_FWD) return -1; };
+    const int rc = run();
+#undef C2_FWD
+    if (rc) return rc;
+    DFINE_LAUNCH_CHECK("conv2x2");
+    return 0;
+}
+
+// dwr[Cout][2][2][Cin] += sum over pixels dy[p, co] * x[p + tap, ci]; dwr zeroed or holding a running gradient.
+DFINE_API int dfine_conv2x2_wgrad(const float* dy, long ldy, const float* x, long ldx, float* dwr, int B, int H, int W, int Cin,
+                                  int Cout, void* stream) {
+    DFINE_REQUIRE(dfine_conv2x2_supported(Cin, Cout, 2, 2, 1, 0, 0, 1, 1, ldx, ldy) && ((uintptr_t)x % 16) == 0 &&
+                      ((uintptr_t)dy % 16) == 0,
+                  "conv2x2_wgrad: %d -> %d, strides %ld / %ld unsupported", Cin, Cout, ldx, ldy);
+    if ((long)B * H * W == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+#define C2_WG(CI_, CO_) launch_conv2x2_wgrad<CI_, CO_>(dy, ldy, x, ldx, dwr, B, H, W, st)
+    auto run = [&]() -> int { C2_DISPATCH(Cin, Cout, C2_WG) return -1; };
+    const int rc = run();
+#undef C2_WG
+    if (rc) return rc;
+    DFINE_LAUNCH_CHECK("conv2x2_wgrad");
+    return 0;
+}

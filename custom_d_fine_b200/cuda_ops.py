@@ -83,9 +83,9 @@ _SPIN_CYCLES = 80_000      # ~40 us at 1.97 GHz
 
 
 class _timed:
-    def __init__(self, name, nbytes, flops=0):
+    def __init__(self, name, nbytes, flops=0, tag=""):
         self.on = name in counters.watch
-        self.name, self.nbytes, self.flops = name, nbytes, flops
+        self.name, self.nbytes, self.flops, self.tag = name, nbytes, flops, tag
 
     def __enter__(self):
         if self.on:
@@ -100,7 +100,7 @@ class _timed:
     def __exit__(self, *exc):
         if self.on:
             self.e.record()
-            counters.timed.setdefault(self.name, []).append((self.s, self.e, self.nbytes, self.flops))
+            counters.timed.setdefault(self.name, []).append((self.s, self.e, self.nbytes, self.flops, self.tag))
 
 
 def _p(t):
@@ -315,6 +315,15 @@ def _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy):
     return bool(lib().dfine_conv_tc_supported(Cin, Cout, k, k, stride, t, l, b, r, c_long(ldx), c_long(ldy)))
 
 
+def _conv2x2_ok(geom, ldx, ldy):
+    """The stem's kernel-2 convs go to the direct fp32 kernels of csrc/stem.cu (DFINE_CONV2X2=0: tensor-core path)."""
+    B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
+    if k != 2 or _MODE == "simt" or not _CONV2X2:
+        return False
+    return bool(lib().dfine_conv2x2_supported(Cin, Cout, k, k, stride, pad[0], pad[1], pad[2], pad[3], c_long(ldx), c_long(ldy)))
+
+
+_CONV2X2 = os.environ.get("DFINE_CONV2X2", "1") != "0"
 _taps_cache = {}
 
 
@@ -333,7 +342,8 @@ def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, Y
     arr, n = taps
     # algorithmic bytes: input pixels + output pixels + weights, each touched once, fp32
     nbytes = 4 * (B * min(H * W, OH * OW * in_stride * in_stride) * Cin + B * OH * OW * Cout + Cout * n * Cin)
-    with _timed("conv_tc", nbytes, 2 * B * OH * OW * Cout * n * Cin):
+    with _timed("conv_tc", nbytes, 2 * B * OH * OW * Cout * n * Cin,
+                f"{what} {Cin}->{Cout} taps{n} s{in_stride} {OH}x{OW} B{B}{' planes' if bf16_planes is not None else ''}"):
         if bf16_planes is not None and w is not None:      # hybrid: tf32 hi plane + bf16 cross-term planes
             _check(lib().dfine_conv_tc_hybrid(_p(x), _p(w), _p(bf16_planes), _p(bias), _p(y), _p(stats), B, H, W, Cin,
                                               c_long(ldx), OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0],
@@ -398,6 +408,12 @@ def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None, lab=Non
     linear); ``wkey`` its cache getter.  Returns True if the tensor-core kernel ran (it fuses the BN statistics)."""
     B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
     assert lab is None or _MODE == "hf3", "the fused LAB epilogue exists on the 3xFP16 path only"
+    if bias is None and act == 0 and lab is None and _conv2x2_ok(geom, ldx, ldy):
+        # the stem's 2x2 convs: direct fp32 kernel (csrc/stem.cu), BN statistics fused
+        wt = wkey("w2f", lambda: weight.permute(2, 3, 1, 0).reshape(4 * Cin, Cout).contiguous())
+        _check(lib().dfine_conv2x2(_p(x), c_long(ldx), _p(wt), _p(y), c_long(ldy), _p(stats), B, H, W, Cin, Cout, 0, _stream()),
+               "conv2x2")
+        return True
     if _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy):
         K = k * k * Cin
         wr = wkey("wr", lambda: weight.reshape(Cout, Cin, k, k).permute(0, 2, 3, 1).reshape(Cout, K).contiguous())
@@ -455,6 +471,14 @@ def _conv_dgrad(dy, ldy, weight, wkey, dx, ldx, geom, res=None):
     a stride-2 conv's data gradient is one launch per output-pixel parity.  ``res`` ([B,H,W,Cin], possibly a
     channel slice with a larger pixel stride): added to dx — in the kernel epilogue on the stride-1 tensor-core path."""
     B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
+    if _conv2x2_ok(geom, ldx, ldy) and lib().dfine_conv2x2_supported(Cout, Cin, 2, 2, 1, 0, 0, 1, 1, c_long(ldy), c_long(ldx)):
+        # wt[(2i + j)][co][ci] = w[co][ci][1 - i][1 - j]: the same correlation on dy, zero border at the top / left
+        wt = wkey("w2d", lambda: weight.flip(2, 3).permute(2, 3, 0, 1).reshape(4 * Cout, Cin).contiguous())
+        _check(lib().dfine_conv2x2(_p(dy), c_long(ldy), _p(wt), _p(dx), c_long(ldx), None, B, H, W, Cout, Cin, -1, _stream()),
+               "conv2x2(dgrad)")
+        if res is not None:
+            dx.add_(res)
+        return
     if res is not None:
         ok = (res.dim() == 4 and res.stride(3) == 1 and res.stride(2) % 4 == 0 and res.stride(2) >= Cin
               and res.stride(1) == W * res.stride(2) and res.stride(0) == H * W * res.stride(2)
@@ -525,9 +549,14 @@ def _grad_dst(p, kind):
 def _conv_wgrad(dy, ldy, x, ldx, geom, dst=None):
     B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
     dwr = dst if dst is not None else torch.zeros((Cout, k, k, Cin), device=dy.device, dtype=torch.float32)
+    if _conv2x2_ok(geom, ldx, ldy):
+        _check(lib().dfine_conv2x2_wgrad(_p(dy), c_long(ldy), _p(x), c_long(ldx), _p(dwr), B, H, W, Cin, Cout, _stream()),
+               "conv2x2_wgrad")
+        return dwr
     if _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy):
         nbytes = 4 * (B * H * W * Cin + B * OH * OW * Cout + 2 * Cout * k * k * Cin)
-        with _timed("conv_wgrad_tc", nbytes, 2 * B * OH * OW * Cout * k * k * Cin):
+        with _timed("conv_wgrad_tc", nbytes, 2 * B * OH * OW * Cout * k * k * Cin,
+                    f"wgrad {Cin}->{Cout} k{k} s{stride} {OH}x{OW} B{B}"):
             _check(lib().dfine_conv_wgrad_tc(_p(dy), _p(x), _p(dwr), B, H, W, Cin, OH, OW, Cout, k, k, stride, pad[0],
                                              pad[1], c_long(ldx), c_long(ldy), _stream()), "conv_wgrad_tc")
     elif _MODE != "simt" and lib().dfine_stem_conv_supported(Cin, Cout, k, k, stride, pad[0], pad[1], pad[2], pad[3],
@@ -1597,35 +1626,57 @@ class CudaOps:
             return torch.einsum("bqc,bhwc->bqhw", embed, feat_nhwc)
         return _MaskDot.apply(embed, feat_nhwc).permute(0, 3, 1, 2)
 
-    def mask_logits_at_multi(self, feat_nhwc, heads):
-        """Mask logits of selected (image, query) pairs only, for SEVERAL loss heads at once — what the mask losses need
-        (dfine_criterion.py:504-556 select the matched masks out of [B,Q,Hm,Wm]; here the unmatched ones never enter the
-        autograd graph).  heads: list of (embed [B,Q,C], b_idx, q_idx, per_image host counts; pairs sorted by image).
-        All heads' rows of one image go through ONE product with that image's features and ONE autograd node returns
-        ONE d(feat): 13 heads x 8 images of separate matmuls cost 104 full-size gradient fills + adds.  -> list of
-        [M_h,Hm,Wm]."""
+    def _multi_plan(self, pers, device):
+        """Index tensors of the image-major stacking used by mask_losses_multi, cached per tuple of per-head per-image
+        counts (host-known: they are part of the CUDA-graph key): perm[i] = head-major row of image-major row i, and the
+        [n_heads, sumM] averaging matrix (1 / M_h on head h's rows)."""
+        key = (tuple(tuple(p) for p in pers), device)
+        hit = self._multi_cache.get(key)
+        if hit is None:
+            B = len(pers[0])
+            base, o = [], 0
+            for per in pers:                      # head-major offsets: head h's rows are sorted by image
+                offs = [o]
+                for n in per:
+                    offs.append(offs[-1] + n)
+                base.append(offs)
+                o = offs[-1]
+            perm, head_of, totals = [], [], []
+            for b in range(B):
+                n_b = 0
+                for h, per in enumerate(pers):
+                    perm.extend(range(base[h][b], base[h][b] + per[b]))
+                    head_of.extend([h] * per[b])
+                    n_b += per[b]
+                totals.append(n_b)
+            avg = torch.zeros((len(pers), max(len(perm), 1)), dtype=torch.float32)
+            for i, h in enumerate(head_of):
+                avg[h, i] = 1.0 / sum(pers[h])
+            hit = (torch.tensor(perm, dtype=torch.int64).to(device), avg.to(device), tuple(totals))
+            if len(self._multi_cache) >= 64:
+                self._multi_cache.pop(next(iter(self._multi_cache)))
+            self._multi_cache[key] = hit
+        return hit
+
+    def mask_losses_multi(self, feat_nhwc, heads, gt_resized, tboxes):
+        """Cropped BCE / Dice mask losses (dfine_criterion.py:504-556) of SEVERAL heads at once, evaluated on the matched
+        (image, query) pairs only: heads = list of (embed [B,Q,C], b_idx, q_idx, t_idx, per-image host counts; pairs sorted
+        by image).  The matched rows of every head are stacked image-major (one index_select), their logits are ONE
+        product per image with that image's mask features, the loss kernels run once over all rows and the per-head
+        means are one small matrix product: the unmatched queries' [B,Q,Hm,Wm] logits never enter the autograd graph and
+        no per-head slice of the stacked logits does either (104 slice backwards were 30 ms of full-size fills + adds).
+        -> (bce [n_heads], dice [n_heads])."""
         B, Hm, Wm, C = feat_nhwc.shape
-        rows = [e.reshape(-1, C).index_select(0, bi * e.shape[1] + qi) for e, bi, qi, _ in heads]     # [M_h, C] each
-        # image-major stacking: image b's rows of every head are contiguous
-        pieces, spans, totals = [], [[] for _ in heads], []
-        for b in range(B):
-            n_b = 0
-            for h, (_, _, _, per) in enumerate(heads):
-                o = sum(per[:b])
-                if per[b]:
-                    pieces.append(rows[h][o:o + per[b]])
-                spans[h].append((sum(totals) + n_b, per[b]))
-                n_b += per[b]
-            totals.append(n_b)
-        if not pieces:
-            return [feat_nhwc.new_zeros((0, Hm, Wm)) for _ in heads]
-        out = _RowsTimesFeat.apply(torch.cat(pieces), feat_nhwc, tuple(totals))                         # [sumM, HW]
-        res = []
-        for h in range(len(heads)):
-            parts = [out[o:o + n] for o, n in spans[h] if n]
-            res.append((torch.cat(parts) if len(parts) > 1 else parts[0]).reshape(-1, Hm, Wm) if parts
-                       else feat_nhwc.new_zeros((0, Hm, Wm)))
-        return res
+        perm, avg, totals = self._multi_plan([per for *_, per in heads], feat_nhwc.device)
+        if perm.numel() == 0:
+            z = feat_nhwc.new_zeros(len(heads))
+            return z, z
+        rows_hm = torch.cat([e.reshape(-1, C).index_select(0, bi * e.shape[1] + qi) for e, bi, qi, _, _ in heads])
+        t_all = torch.cat([ti for _, _, _, ti, _ in heads]).index_select(0, perm)
+        out = _RowsTimesFeat.apply(rows_hm.index_select(0, perm), feat_nhwc, totals)                      # [sumM, HW]
+        bce_rows, dice_rows = _MaskLossRows.apply(out.view(-1, Hm, Wm), gt_resized, t_all, tboxes)
+        both = avg @ torch.stack((bce_rows, dice_rows), 1)                                                # [n_heads, 2]
+        return both[:, 0], both[:, 1]
 
     def mask_loss_rows(self, pred, gt_resized, t_idx, tboxes):
         """(bce_row [M], dice_row [M]) of matched mask logits pred [M,Hm,Wm] against gt_resized[t_idx] inside the GT boxes."""
@@ -1736,6 +1787,7 @@ class CudaOps:
         return out_q, out_t, cost
 
     _toff_cache = {}
+    _multi_cache = {}
 
     @torch.no_grad()
     def match_raw(self, logits_list, boxes_list, targets, alpha=0.25, gamma=2.0, w_class=2.0, w_bbox=5.0,

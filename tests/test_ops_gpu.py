@@ -230,6 +230,10 @@ TC_CASES = [
     (2, 33, 47, 48, 24, 3, 2, (1, 1, 1, 1)),          # odd sizes, stride 2
     (2, 40, 40, 24, 12, 2, 1, (0, 0, 1, 1)),          # stem2a: 2x2, bottom/right padding, Cout 12
     (2, 40, 40, 12, 24, 2, 1, (0, 0, 1, 1)),          # stem2b: Cin 12
+    (2, 37, 131, 32, 16, 2, 1, (0, 0, 1, 1)),         # l / x stem2a, ragged tile edges (direct 2x2 kernels, csrc/stem.cu)
+    (1, 19, 70, 16, 32, 2, 1, (0, 0, 1, 1)),          # l / x stem2b
+    (2, 24, 65, 16, 8, 2, 1, (0, 0, 1, 1)),           # n stem2a
+    (2, 24, 65, 8, 16, 2, 1, (0, 0, 1, 1)),           # n stem2b
     (1, 1, 700, 4, 512, 1, 1, (0, 0, 0, 0)),          # query_pos_head layer 0: K = 4
     (1, 1, 700, 256, 4, 1, 1, (0, 0, 0, 0)),          # bbox head: N = 4
 ]

@@ -29,7 +29,7 @@ targets = bench.to_targets(l, b, m)
 for _ in range(3):
     step(x, targets)
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof:
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True, record_shapes=True) as prof:
     step(x, targets)
     torch.cuda.synchronize()
 
@@ -42,11 +42,13 @@ for ev in prof.events():
     cuda_t = sum(k.duration for k in ev.kernels) if ev.kernels else 0.0
     if cuda_t == 0.0 or ev.cpu_children and any(c.kernels for c in ev.cpu_children):
         continue            # count leaf ops only (the op that actually launched the kernels)
-    frame = "autograd / other"
+    frame = None
     for f in ev.stack or []:              # innermost frame first
         if "custom_d_fine_b200/" in f:
             frame = f.split("custom_d_fine_b200/")[-1].strip()
             break
+    if frame is None:                     # autograd engine thread (no Python frames): the operand shapes identify the tensor
+        frame = "autograd " + str([tuple(s) for s in (ev.input_shapes or []) if s])[:100]
     sites[(ev.name, frame)][0] += 1
     sites[(ev.name, frame)][1] += cuda_t
     ops[ev.name][0] += 1

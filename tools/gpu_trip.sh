@@ -17,7 +17,7 @@ for step in "$@"; do
   case $kind in
     tests)    if [ -n "$a" ]; then run tests_${b:-sel} python -m pytest tests -q -m gpu -s -k "$a"; else run tests python -m pytest tests -q -m gpu; fi ;;
     smoke)    run smoke python __graft_entry__.py smoke ;;
-    bench)    run bench_${a:-m640}${b:+_$b} env ${b:+DFINE_GEMM=$b} python bench.py --config ${a:-m640} --steps 10 --warmup 3 ${c:+--no-cpu-baseline} ;;
+    bench)    run bench_${a:-m640}${b:+_$b} env ${b:+DFINE_GEMM=$b} python bench.py --config ${a:-m640} --steps 10 --warmup 3 ${c:+--no-cpu-baseline} --dump-launches gpurun_out/shapes_${a:-m640}${TAG:+_$TAG}.md ;;
     ref)      run bench_ref python bench.py --impl reference --steps 2 --warmup 1 ;;
     tf32peak) run tf32peak python tools/measure_tf32_peak.py ;;
     refgpu)   run refgpu_${a:-m640} python tools/ref_on_gpu.py --config ${a:-m640} ;;
