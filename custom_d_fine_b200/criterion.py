@@ -478,12 +478,8 @@ class DFINECriterion(nn.Module):
             plan = IndexPlan(sizes, Q, n_sets, meta["dn_positive_idx"] if meta else None,
                              meta["dn_num_group"] if meta else 0)
         out_q, out_t = self.matcher.raw_to_host(raw, plan)
-        plan.fill(out_q, out_t, want_lists=False)
-        go = self.go_indices_host(out_q, out_t, plan)
-        n_go = plan.fill_go(go)
-        counts = torch.tensor([float(n_go), float(sum(sizes))], dtype=torch.float32)
+        counts = self.plan_from_host(out_q, out_t, plan)
         if local_counts:
-            plan.counts.copy_(counts)
             return plan
         if dist_utils.is_dist_available_and_initialized():
             dev = outputs["pred_logits"].device
@@ -492,6 +488,17 @@ class DFINECriterion(nn.Module):
             counts = c.cpu()
         plan.counts.copy_(torch.clamp(counts / dist_utils.get_world_size(), min=1))
         return plan
+
+    def plan_from_host(self, out_q, out_t, plan):
+        """The host-only part of stage 2 (no device call, no stream dependency): fills ``plan.table`` and leaves this
+        rank's raw (n_go, n_targets) in ``plan.counts`` — both pinned, so a copy enqueued earlier behind a stream
+        wait picks the new contents up (train.GraphedTrainStep)."""
+        plan.fill(out_q, out_t, want_lists=False)
+        go = self.go_indices_host(out_q, out_t, plan)
+        n_go = plan.fill_go(go)
+        counts = torch.tensor([float(n_go), float(sum(plan.sizes))], dtype=torch.float32)
+        plan.counts.copy_(counts)
+        return counts
 
     @staticmethod
     def finish_counts(counts_dev):

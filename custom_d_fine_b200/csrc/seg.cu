@@ -356,6 +356,113 @@ __global__ void __launch_bounds__(256) mask_loss_bwd_kernel(const float* __restr
     }
 }
 
+// ---- the same losses on PIXEL-MAJOR logits ------------------------------------------------------------------------
+// pred [B, HW, R]: row r of image b is the column pred[(b*HW + px)*R + r] — the layout the tcgen05 mask product writes
+// (pixels = GEMM rows), so the matched logits never go through a transposing copy or a library sgemm.  Lane = row
+// (32 consecutive r: 128-byte coalesced accesses), a warp walks pixel rows y, y+8, ... of its CTA's slab; only the union
+// of the 32 lanes' boxes is visited.  sums [B*R, 4] = {bce sum, sum p*t, sum p, sum t}, zeroed by the caller.
+constexpr int PM_YROWS = 32;       // pixel rows per CTA slab
+__global__ void __launch_bounds__(256) mask_loss_pm_acc_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                               const long* __restrict__ t_idx, const float* __restrict__ tboxes,
+                                                               float* __restrict__ sums, int R, int Hm, int Wm) {
+    __shared__ float red[8][32][4];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int b = blockIdx.y, r = blockIdx.x * 32 + lane;
+    const int ybeg = blockIdx.z * PM_YROWS, yend = min(Hm, ybeg + PM_YROWS);
+    const long t = r < R ? t_idx[(long)b * R + r] : -1;
+    const bool valid = t >= 0;
+    int ya = Hm, yb = 0, xa = Wm, xb = 0;
+    if (valid) {
+        const BoxPx bx = box_px(tboxes + t * 4, Hm, Wm);
+        ya = (int)ceilf(bx.y1); yb = min((int)ceilf(bx.y2), Hm);
+        xa = (int)ceilf(bx.x1); xb = min((int)ceilf(bx.x2), Wm);
+    }
+    int uya = ya, uyb = yb, uxa = xa, uxb = xb;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        uya = min(uya, __shfl_xor_sync(0xffffffffu, uya, o)); uyb = max(uyb, __shfl_xor_sync(0xffffffffu, uyb, o));
+        uxa = min(uxa, __shfl_xor_sync(0xffffffffu, uxa, o)); uxb = max(uxb, __shfl_xor_sync(0xffffffffu, uxb, o));
+    }
+    float bce = 0.f, spt = 0.f, sp = 0.f, st = 0.f;
+    const float* g = gt + (valid ? t : 0) * (long)Hm * Wm;
+    for (int y = max(ybeg, uya) + warp; y < min(yend, uyb); y += 8) {
+        const bool yin = valid && y >= ya && y < yb;
+        const float* prow = pred + ((long)b * Hm * Wm + (long)y * Wm) * R + r;
+        const float* grow = g + (long)y * Wm;
+#pragma unroll 4
+        for (int x = uxa; x < uxb; ++x) {
+            if (yin && x >= xa && x < xb) {
+                const float xv = __ldg(prow + (long)x * R), tv = __ldg(grow + x);
+                const float mv = fmaxf(-xv, 0.f);
+                bce += (1.f - tv) * xv + mv + logf(expf(-mv) + expf(-xv - mv));
+                const float pv = 1.f / (1.f + expf(-xv));
+                spt += pv * tv; sp += pv; st += tv;
+            }
+        }
+    }
+    red[warp][lane][0] = bce; red[warp][lane][1] = spt; red[warp][lane][2] = sp; red[warp][lane][3] = st;
+    __syncthreads();
+    if (warp < 4) {        // warp j sums component j of the 8 partials of every lane's row
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][lane][warp];
+        if (valid && v != 0.f) atomicAdd(sums + ((long)b * R + r) * 4 + warp, v);
+    }
+}
+__global__ void mask_loss_pm_final_kernel(const float* __restrict__ sums, const long* __restrict__ t_idx,
+                                          const float* __restrict__ tboxes, float* __restrict__ bce_row,
+                                          float* __restrict__ dice_row, long n, int Hm, int Wm) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long t = t_idx[i];
+    if (t < 0) { bce_row[i] = 0.f; dice_row[i] = 0.f; return; }
+    const BoxPx bx = box_px(tboxes + t * 4, Hm, Wm);
+    const float area = fmaxf((bx.x2 - bx.x1) * (bx.y2 - bx.y1), 1.f);
+    bce_row[i] = sums[4 * i] / area;
+    dice_row[i] = 1.f - (2.f * sums[4 * i + 1] + 1e-6f) / (sums[4 * i + 2] + sums[4 * i + 3] + 1e-6f);
+}
+// dpred [B, HW, R], written completely (zero outside the boxes and on the padding rows)
+__global__ void __launch_bounds__(256) mask_loss_pm_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                               const long* __restrict__ t_idx, const float* __restrict__ tboxes,
+                                                               const float* __restrict__ sums, const float* __restrict__ g_bce,
+                                                               const float* __restrict__ g_dice, float* __restrict__ dpred,
+                                                               int R, int Hm, int Wm) {
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int b = blockIdx.y, r = blockIdx.x * 32 + lane;
+    if (r >= R) return;
+    const int ybeg = blockIdx.z * PM_YROWS, yend = min(Hm, ybeg + PM_YROWS);
+    const long row = (long)b * R + r;
+    const long t = t_idx[row];
+    const bool valid = t >= 0;
+    int ya = Hm, yb = 0, xa = Wm, xb = 0;
+    float cb = 0.f, cd = 0.f, N = 0.f, D = 1.f;
+    if (valid) {
+        const BoxPx bx = box_px(tboxes + t * 4, Hm, Wm);
+        ya = (int)ceilf(bx.y1); yb = min((int)ceilf(bx.y2), Hm);
+        xa = (int)ceilf(bx.x1); xb = min((int)ceilf(bx.x2), Wm);
+        const float area = fmaxf((bx.x2 - bx.x1) * (bx.y2 - bx.y1), 1.f);
+        cb = g_bce[row] / area; cd = g_dice[row];
+        N = 2.f * sums[4 * row + 1] + 1e-6f; D = sums[4 * row + 2] + sums[4 * row + 3] + 1e-6f;
+    }
+    const float* g = gt + (valid ? t : 0) * (long)Hm * Wm;
+    const float invD2 = 1.f / (D * D);
+    for (int y = ybeg + warp; y < yend; y += 8) {
+        const bool yin = valid && y >= ya && y < yb;
+        const long base = ((long)b * Hm * Wm + (long)y * Wm) * R + r;
+        const float* grow = g + (long)y * Wm;
+#pragma unroll 4
+        for (int x = 0; x < Wm; ++x) {
+            float o = 0.f;
+            if (yin && x >= xa && x < xb) {
+                const float xv = __ldg(pred + base + (long)x * R), tv = __ldg(grow + x);
+                const float pv = 1.f / (1.f + expf(-xv));
+                o = cb * (pv - tv) - cd * (2.f * tv * D - N) * invD2 * pv * (1.f - pv);
+            }
+            dpred[base + (long)x * R] = o;
+        }
+    }
+}
+
 int ew_grid(long n) {
     long g = (n + 255) / 256;
     return (int)(g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g));
@@ -437,6 +544,31 @@ DFINE_API int dfine_mask_loss_bwd(const float* pred, const float* gt, const long
     if (M == 0) return 0;
     mask_loss_bwd_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(pred, gt, t_idx, tboxes, sums, g_bce, g_dice, dpred, Hm, Wm);
     DFINE_LAUNCH_CHECK("mask_loss_bwd");
+    return 0;
+}
+
+// The same losses on pixel-major logits pred [B, Hm*Wm, R] (the layout of dfine_conv_tc's mask product): t_idx [B*R] int64,
+// negative = padding row (loss 0, zero gradient); sums [B*R, 4] scratch, ZEROED by the caller, kept for the backward.
+DFINE_API int dfine_mask_loss_pm_fwd(const float* pred, const float* gt, const long* t_idx, const float* tboxes, float* bce_row,
+                                     float* dice_row, float* sums, int B, int R, int Hm, int Wm, void* stream) {
+    DFINE_REQUIRE(B >= 0 && R >= 0 && Hm > 0 && Wm > 0, "mask_loss_pm: bad dims");
+    if ((long)B * R == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(ceil_div(R, 32), B, ceil_div(Hm, PM_YROWS));
+    mask_loss_pm_acc_kernel<<<grid, 256, 0, st>>>(pred, gt, t_idx, tboxes, sums, R, Hm, Wm);
+    DFINE_LAUNCH_CHECK("mask_loss_pm_acc");
+    mask_loss_pm_final_kernel<<<ceil_div((long)B * R, 256), 256, 0, st>>>(sums, t_idx, tboxes, bce_row, dice_row, (long)B * R, Hm, Wm);
+    DFINE_LAUNCH_CHECK("mask_loss_pm_final");
+    return 0;
+}
+DFINE_API int dfine_mask_loss_pm_bwd(const float* pred, const float* gt, const long* t_idx, const float* tboxes,
+                                     const float* sums, const float* g_bce, const float* g_dice, float* dpred, int B, int R, int Hm,
+                                     int Wm, void* stream) {
+    DFINE_REQUIRE(B >= 0 && R >= 0 && Hm > 0 && Wm > 0, "mask_loss_pm_bwd: bad dims");
+    if ((long)B * R == 0) return 0;
+    dim3 grid(ceil_div(R, 32), B, ceil_div(Hm, PM_YROWS));
+    mask_loss_pm_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, gt, t_idx, tboxes, sums, g_bce, g_dice, dpred, R, Hm, Wm);
+    DFINE_LAUNCH_CHECK("mask_loss_pm_bwd");
     return 0;
 }
 

@@ -79,6 +79,34 @@ def _check(rc, what):
     counters.launches += 1
 
 
+class HostFlag:
+    """A 32-bit word in mapped pinned memory that a stream can wait on (csrc/hostsync.cu)."""
+
+    def __init__(self):
+        h, d = ctypes.c_void_p(), ctypes.c_void_p()
+        _check(lib().dfine_flag_create(ctypes.byref(h), ctypes.byref(d)), "flag_create")
+        self.host, self.dev = h.value, d.value
+        self._word = ctypes.c_uint32.from_address(self.host)
+
+    def raise_to(self, value):
+        self._word.value = value & 0xffffffff
+
+    def __del__(self):
+        try:
+            lib().dfine_flag_destroy(ctypes.c_void_p(self.host))
+        except Exception:
+            pass
+
+
+def stream_wait_supported():
+    return bool(lib().dfine_stream_wait_supported())
+
+
+def stream_wait_flag(flag, value):
+    """Everything enqueued on the current stream after this call starts once ``flag`` has been raised to >= value."""
+    _check(lib().dfine_stream_wait_flag(ctypes.c_void_p(flag.dev), int(value), _stream()), "stream_wait_flag")
+
+
 _SPIN_CYCLES = 80_000      # ~40 us at 1.97 GHz
 
 
@@ -324,6 +352,7 @@ def _conv2x2_ok(geom, ldx, ldy):
 
 
 _CONV2X2 = os.environ.get("DFINE_CONV2X2", "1") != "0"
+_MASK_PM = os.environ.get("DFINE_MASK_PM", "1") != "0"      # matched-mask logits through the tcgen05 mask product
 _taps_cache = {}
 
 
@@ -549,10 +578,6 @@ def _grad_dst(p, kind):
 def _conv_wgrad(dy, ldy, x, ldx, geom, dst=None):
     B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
     dwr = dst if dst is not None else torch.zeros((Cout, k, k, Cin), device=dy.device, dtype=torch.float32)
-    if _conv2x2_ok(geom, ldx, ldy):
-        _check(lib().dfine_conv2x2_wgrad(_p(dy), c_long(ldy), _p(x), c_long(ldx), _p(dwr), B, H, W, Cin, Cout, _stream()),
-               "conv2x2_wgrad")
-        return dwr
     if _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy):
         nbytes = 4 * (B * H * W * Cin + B * OH * OW * Cout + 2 * Cout * k * k * Cin)
         with _timed("conv_wgrad_tc", nbytes, 2 * B * OH * OW * Cout * k * k * Cin,
@@ -1313,6 +1338,34 @@ class _MaskLossRows(torch.autograd.Function):
         return dpred, None, None, None
 
 
+class _MaskLossPM(torch.autograd.Function):
+    """The same two losses on PIXEL-MAJOR logits pred [B,Hm,Wm,R] (what the tcgen05 mask product writes); t_idx [B*R],
+    negative on padding rows.  -> (bce_row [B*R], dice_row [B*R])."""
+
+    @staticmethod
+    def forward(ctx, pred, gt, t_idx, tboxes):
+        pred, gt = pred.contiguous(), gt.contiguous()
+        t_idx, tboxes = t_idx.contiguous(), tboxes.contiguous().float()
+        B, Hm, Wm, R = pred.shape
+        bce = torch.empty(B * R, device=pred.device, dtype=torch.float32)
+        dice = torch.empty(B * R, device=pred.device, dtype=torch.float32)
+        sums = torch.zeros((B * R, 4), device=pred.device, dtype=torch.float32)
+        _check(lib().dfine_mask_loss_pm_fwd(_p(pred), _p(gt), _p(t_idx), _p(tboxes), _p(bce), _p(dice), _p(sums), B, R, Hm, Wm,
+                                            _stream()), "mask_loss_pm_fwd")
+        ctx.save_for_backward(pred, gt, t_idx, tboxes, sums)
+        return bce, dice
+
+    @staticmethod
+    def backward(ctx, g_bce, g_dice):
+        pred, gt, t_idx, tboxes, sums = ctx.saved_tensors
+        B, Hm, Wm, R = pred.shape
+        z = lambda g: torch.zeros(B * R, device=pred.device) if g is None else g.contiguous().float()   # noqa: E731
+        dpred = torch.empty_like(pred)
+        _check(lib().dfine_mask_loss_pm_bwd(_p(pred), _p(gt), _p(t_idx), _p(tboxes), _p(sums), _p(z(g_bce)), _p(z(g_dice)),
+                                            _p(dpred), B, R, Hm, Wm, _stream()), "mask_loss_pm_bwd")
+        return dpred, None, None, None
+
+
 class _RowsTimesFeat(torch.autograd.Function):
     """out[m] = rows[m] . feat[b(m)] over the pixels, rows stacked image-major (`totals[b]` rows of image b): one product
     per image forward, two backward, ONE d(feat) tensor."""
@@ -1652,7 +1705,17 @@ class CudaOps:
             avg = torch.zeros((len(pers), max(len(perm), 1)), dtype=torch.float32)
             for i, h in enumerate(head_of):
                 avg[h, i] = 1.0 / sum(pers[h])
-            hit = (torch.tensor(perm, dtype=torch.int64).to(device), avg.to(device), tuple(totals))
+            # padded image-major stacking for the pixel-major path: Rmax rows per image, the pads select an appended zero
+            # row / target -1 and carry weight 0 in the averaging matrix
+            n_all = len(perm)
+            rmax = (max(totals + [1]) + 3) // 4 * 4
+            perm_pad, avg_pad, o = [], torch.zeros((len(pers), B * rmax), dtype=torch.float32), 0
+            for b in range(B):
+                perm_pad += perm[o:o + totals[b]] + [n_all] * (rmax - totals[b])
+                avg_pad[:, b * rmax:b * rmax + totals[b]] = avg[:, o:o + totals[b]]
+                o += totals[b]
+            hit = (torch.tensor(perm, dtype=torch.int64).to(device), avg.to(device), tuple(totals),
+                   torch.tensor(perm_pad, dtype=torch.int64).to(device), avg_pad.to(device), rmax)
             if len(self._multi_cache) >= 64:
                 self._multi_cache.pop(next(iter(self._multi_cache)))
             self._multi_cache[key] = hit
@@ -1667,11 +1730,21 @@ class CudaOps:
         no per-head slice of the stacked logits does either (104 slice backwards were 30 ms of full-size fills + adds).
         -> (bce [n_heads], dice [n_heads])."""
         B, Hm, Wm, C = feat_nhwc.shape
-        perm, avg, totals = self._multi_plan([per for *_, per in heads], feat_nhwc.device)
+        perm, avg, totals, perm_pad, avg_pad, rmax = self._multi_plan([per for *_, per in heads], feat_nhwc.device)
         if perm.numel() == 0:
             z = feat_nhwc.new_zeros(len(heads))
             return z, z
         rows_hm = torch.cat([e.reshape(-1, C).index_select(0, bi * e.shape[1] + qi) for e, bi, qi, _, _ in heads])
+        if _MASK_PM and C % 8 == 0 and _MODE != "simt":
+            # pixel-major: the logits of the stacked rows are ONE grouped tcgen05 product over all images (per-image
+            # "weights" = that image's rows, padded to Rmax), its gradients the grouped data-gradient / per-image
+            # weight-gradient kernels of _MaskDot, and the loss kernels read that layout directly — no library sgemm
+            rows_pad = torch.cat([rows_hm, rows_hm.new_zeros((1, C))]).index_select(0, perm_pad).view(B, rmax, C)
+            t_pad = torch.cat([ti for _, _, _, ti, _ in heads] + [perm_pad.new_full((1,), -1)]).index_select(0, perm_pad)
+            pred = _MaskDot.apply(rows_pad, feat_nhwc)                                                   # [B,Hm,Wm,Rmax]
+            bce_rows, dice_rows = _MaskLossPM.apply(pred, gt_resized, t_pad, tboxes)
+            both = avg_pad @ torch.stack((bce_rows, dice_rows), 1)
+            return both[:, 0], both[:, 1]
         t_all = torch.cat([ti for _, _, _, ti, _ in heads]).index_select(0, perm)
         out = _RowsTimesFeat.apply(rows_hm.index_select(0, perm), feat_nhwc, totals)                      # [sumM, HW]
         bce_rows, dice_rows = _MaskLossRows.apply(out.view(-1, Hm, Wm), gt_resized, t_all, tboxes)

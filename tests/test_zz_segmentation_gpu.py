@@ -167,3 +167,31 @@ def test_mask_loss_kernel_matches_torch_formulation(cuda_ops, monkeypatch):
     k, t = res["kernel"], res["torch"]
     assert abs(k[0] - t[0]) < 1e-5 * max(1.0, abs(t[0])) and abs(k[1] - t[1]) < 1e-5
     assert float((k[2] - t[2]).abs().max()) < 1e-6 + 1e-5 * float(t[2].abs().max())
+
+
+def test_mask_loss_pixel_major_matches_row_major(cuda_ops):
+    """The pixel-major loss kernels (logits [B,Hm,Wm,R] as the tcgen05 mask product writes them, padding rows marked -1)
+    against the row-major kernels (which the previous test pins to the torch formulation): values and gradients."""
+    from custom_d_fine_b200 import cuda_ops as co
+    g = torch.Generator().manual_seed(7)
+    B, R, Hm, Wm, T = 3, 44, 40, 36, 9
+    boxes = (torch.rand(T, 4, generator=g) * 0.5 + 0.2).cuda()
+    boxes[0] = torch.tensor([0.02, 0.5, 0.2, 0.9])
+    boxes[1] = torch.tensor([0.31, 0.47, 0.004, 0.003])
+    gt = torch.rand(T, Hm, Wm, generator=g).cuda()
+    t_pad = torch.randint(-1, T, (B * R,), generator=g).cuda()
+    t_pad[:5] = -1
+    valid = t_pad >= 0
+    pred = (torch.randn(B, Hm, Wm, R, generator=g) * 3).cuda().requires_grad_(True)
+    w1, w2 = torch.rand(B * R, generator=g).cuda(), torch.rand(B * R, generator=g).cuda()
+    bce, dice = co._MaskLossPM.apply(pred, gt, t_pad, boxes)
+    ((bce * w1).sum() + (dice * w2).sum()).backward()
+    rows = pred.detach().permute(0, 3, 1, 2).reshape(B * R, Hm, Wm)[valid].clone().requires_grad_(True)
+    bce_r, dice_r = co._MaskLossRows.apply(rows, gt, t_pad[valid], boxes)
+    ((bce_r * w1[valid]).sum() + (dice_r * w2[valid]).sum()).backward()
+    assert float(bce[~valid].abs().max()) == 0.0 and float(dice[~valid].abs().max()) == 0.0
+    assert float((bce[valid] - bce_r).abs().max()) < 1e-5 * float(bce_r.abs().max())
+    assert float((dice[valid] - dice_r).abs().max()) < 1e-5
+    gp = pred.grad.permute(0, 3, 1, 2).reshape(B * R, Hm, Wm)
+    assert float(gp[~valid].abs().max()) == 0.0
+    assert float((gp[valid] - rows.grad).abs().max()) < 1e-6 + 1e-5 * float(rows.grad.abs().max())
