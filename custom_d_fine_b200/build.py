@@ -16,7 +16,7 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libdfine_sm100.so"
 SOURCES = ["lib.cu", "msda.cu", "matcher.cu", "norm_act.cu", "spatial.cu", "conv_simt.cu", "attention.cu", "attention_mma.cu",
-           "gemm_tc.cu", "fdr.cu", "stem.cu", "optim.cu", "loss.cu", "select.cu", "io.cu", "seg.cu", "hostsync.cu"]
+           "gemm_tc.cu", "fdr.cu", "stem.cu", "optim.cu", "loss.cu", "select.cu", "io.cu", "seg.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
 PER_FILE = {"matcher.cu": ["-fmad=false"]}

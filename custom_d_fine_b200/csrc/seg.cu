@@ -235,18 +235,30 @@ __global__ void __launch_bounds__(512) mask_cost_acc_kernel(const float* __restr
 #pragma unroll
             for (int t = 0; t < MC_T; ++t) { s1[t] = 0.f; s2[t] = 0.f; }
             const float* lp = logits + ((long)b * HW + p0) * Q + q;
-            for (int p = 0; p < np; ++p) {
-                const float x = __ldg(lp + (long)p * Q);
-                const float prob = 1.f / (1.f + expf(-x));
-                const float pg = gamma == 2.f ? prob * prob : powf(prob, gamma);
-                const float qg = gamma == 2.f ? (1.f - prob) * (1.f - prob) : powf(1.f - prob, gamma);
-                const float neg = (1.f - alpha) * pg * (-logf(1.f - prob + 1e-8f));
-                const float pos = alpha * qg * (-logf(prob + 1e-8f));
-                const float d = pos - neg;
-                P += prob; N += neg;
+            // eight pixels per iteration, their (row-strided) loads all issued before the first use: with one load in
+            // flight per thread the kernel ran at 0.4 TB/s (612 us per layer on the 160x160 masks of D-FINE-l-seg)
+            constexpr int U = 8;
+            for (int pb = 0; pb < np; pb += U) {
+                float xs[U];
 #pragma unroll
-                for (int t = 0; t < MC_T; ++t)
-                    if (t < nt) { const float g = gts[t * chunk + p]; s1[t] += prob * g; s2[t] += d * g; }
+                for (int u = 0; u < U; ++u) xs[u] = pb + u < np ? __ldg(lp + (long)(pb + u) * Q) : 0.f;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int p = pb + u;
+                    if (p < np) {
+                        const float x = xs[u];
+                        const float prob = 1.f / (1.f + expf(-x));
+                        const float pg = gamma == 2.f ? prob * prob : powf(prob, gamma);
+                        const float qg = gamma == 2.f ? (1.f - prob) * (1.f - prob) : powf(1.f - prob, gamma);
+                        const float neg = (1.f - alpha) * pg * (-logf(1.f - prob + 1e-8f));
+                        const float pos = alpha * qg * (-logf(prob + 1e-8f));
+                        const float d = pos - neg;
+                        P += prob; N += neg;
+#pragma unroll
+                        for (int t = 0; t < MC_T; ++t)
+                            if (t < nt) { const float g = gts[t * chunk + p]; s1[t] += prob * g; s2[t] += d * g; }
+                    }
+                }
             }
             float* o = out + (long)q * stride;
 #pragma unroll

@@ -79,34 +79,6 @@ def _check(rc, what):
     counters.launches += 1
 
 
-class HostFlag:
-    """A 32-bit word in mapped pinned memory that a stream can wait on (csrc/hostsync.cu)."""
-
-    def __init__(self):
-        h, d = ctypes.c_void_p(), ctypes.c_void_p()
-        _check(lib().dfine_flag_create(ctypes.byref(h), ctypes.byref(d)), "flag_create")
-        self.host, self.dev = h.value, d.value
-        self._word = ctypes.c_uint32.from_address(self.host)
-
-    def raise_to(self, value):
-        self._word.value = value & 0xffffffff
-
-    def __del__(self):
-        try:
-            lib().dfine_flag_destroy(ctypes.c_void_p(self.host))
-        except Exception:
-            pass
-
-
-def stream_wait_supported():
-    return bool(lib().dfine_stream_wait_supported())
-
-
-def stream_wait_flag(flag, value):
-    """Everything enqueued on the current stream after this call starts once ``flag`` has been raised to >= value."""
-    _check(lib().dfine_stream_wait_flag(ctypes.c_void_p(flag.dev), int(value), _stream()), "stream_wait_flag")
-
-
 _SPIN_CYCLES = 80_000      # ~40 us at 1.97 GHz
 
 

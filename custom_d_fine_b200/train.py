@@ -320,29 +320,6 @@ class GraphedTrainStep(TrainStep):
         # they were created on, and a node created on the legacy default stream cannot be used under capture.
         self._side = torch.cuda.Stream() if next(self.model.parameters()).is_cuda else None
 
-    def _prelaunch_ok(self, g):
-        """Set up (once per captured key) what the pre-launched replay needs; False keeps the plain order
-        (DFINE_PRELAUNCH=0, or a driver without stream memory operations)."""
-        if "raw_host" in g:
-            return True
-        if g.get("prelaunch") is False:
-            return False
-        from . import cuda_ops
-        import os
-        ok = os.environ.get("DFINE_PRELAUNCH", "1") != "0" and cuda_ops.stream_wait_supported()
-        raw = list(g["raw"]) if isinstance(g["raw"], (tuple, list)) else None
-        ok = ok and raw is not None and len(raw) == 2 and all(torch.is_tensor(r) and r.is_cuda for r in raw) \
-            and g["plan"].table.is_pinned()
-        if not ok:
-            g["prelaunch"] = False
-            return False
-        if getattr(self, "_flag", None) is None:
-            self._flag, self._flag_seq = cuda_ops.HostFlag(), 0
-        g["raw_dev"] = torch.stack(raw)
-        g["raw_host"] = torch.empty(g["raw_dev"].shape, dtype=g["raw_dev"].dtype).pin_memory()
-        g["d2h_event"] = torch.cuda.Event()
-        return True
-
     def host_gap_ms(self):
         """Device idle time between graph A and graph B of the last replayed step (host index planning)."""
         ev = getattr(self, "_last_gap", None)
@@ -443,22 +420,24 @@ class GraphedTrainStep(TrainStep):
         g["gA"].replay()
         ev = g.setdefault("gap_events", (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
         ev[0].record()
-        pre = self._prelaunch_ok(g)
-        if pre:
-            # Everything the device does after graph A is enqueued NOW, behind a stream wait on a host flag: the matcher
-            # result goes to pinned memory, the stream then blocks; the H2D copies of the (pinned, still to be filled)
-            # index table, graph B, the all-reduces and graph C queue up behind it.  The host plans below while those
-            # launches are already in the driver's queue and raises the flag the moment the table is complete, so the
-            # device idles for the planning time only — not for planning + the launch latency of a ~1500-node graph.
-            from . import cuda_ops
-            self._flag_seq = (self._flag_seq + 1) & 0x7fffffff
-            torch.stack(list(g["raw"]), out=g["raw_dev"])
-            g["raw_host"].copy_(g["raw_dev"], non_blocking=True)
-            g["d2h_event"].record()
-            cuda_ops.stream_wait_flag(self._flag, self._flag_seq)
-            plan = g["plan"]
-        else:
-            plan = self.loss_fn.plan(g["out"], g["targets"], g["raw"], g["plan"], local_counts=True)   # syncs on the matcher D2H
+        # (Enqueueing graph B behind a stream memory-wait while the host plans was tried: no gain where the planning
+        #  takes 0.6 ms, and a ~3800-node graph submitted to a stream that cannot drain blocks the submitting host
+        #  thread — which is the thread that would raise the flag.  The plain order stays.)
+        plan = self.loss_fn.plan(g["out"], g["targets"], g["raw"], g["plan"], local_counts=True)   # syncs on the matcher D2H
+        self._replay_tail(g, inputs, plan, ev)
+        if self.scheduler is not None:
+            self.scheduler.step()
+        from . import cuda_ops
+        cuda_ops.weights_changed()                       # graph C rewrote the parameters
+        cuda_ops.counters.launches += g["launches"]      # library kernels replayed by the graphs
+        self.batch_idx += 1
+        # the graph's output buffers are overwritten by every replay: hand out copies (one stacked clone), so that a
+        # caller may keep the losses of several steps (src/dl/train.Trainer averages them per epoch)
+        vals = torch.stack([g["loss"]] + list(g["loss_dict"].values())).clone()
+        return vals[0], dict(zip(g["loss_dict"].keys(), vals[1:].unbind(0)))
+
+    def _replay_tail(self, g, inputs, plan, ev):
+        """Everything the device runs after the index table: enqueued only (no host wait in here)."""
         g["table"].copy_(plan.table, non_blocking=True)
         g["counts"].copy_(plan.counts, non_blocking=True)
         self.loss_fn.finish_counts(g["counts"])          # 2-float all-reduce + clamp on the device: no host wait
@@ -475,20 +454,3 @@ class GraphedTrainStep(TrainStep):
             self.optimizer.allreduce_grads(bb, comm)
             torch.cuda.current_stream().wait_stream(comm)
         g["gC"].replay()
-        if pre:
-            try:
-                g["d2h_event"].synchronize()
-                both = g["raw_host"].numpy()
-                self.loss_fn.plan_from_host(both[0], both[1], g["plan"])
-            finally:
-                self._flag.raise_to(self._flag_seq)      # always: a stream left waiting would hang the device
-        if self.scheduler is not None:
-            self.scheduler.step()
-        from . import cuda_ops
-        cuda_ops.weights_changed()                       # graph C rewrote the parameters
-        cuda_ops.counters.launches += g["launches"]      # library kernels replayed by the graphs
-        self.batch_idx += 1
-        # the graph's output buffers are overwritten by every replay: hand out copies (one stacked clone), so that a
-        # caller may keep the losses of several steps (src/dl/train.Trainer averages them per epoch)
-        vals = torch.stack([g["loss"]] + list(g["loss_dict"].values())).clone()
-        return vals[0], dict(zip(g["loss_dict"].keys(), vals[1:].unbind(0)))

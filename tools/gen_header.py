@@ -50,9 +50,6 @@ GROUPS = [
      "HungarianMatcher.forward matcher.py:110-257 (scipy.optimize.linear_sum_assignment at 243)."),
     ("optim.cu", "Optimizer / EMA",
      "train.py:62-73,512-535; dfine.py:87-124."),
-    ("hostsync.cu", "Host -> stream hand-off (a stream blocks on a 4-byte flag in mapped pinned HOST memory)",
-     "train.py:395-470's host-side index planning between forward and loss (dfine_criterion.py:570-652), taken off the\n"
-     " * device's critical path: the launches that follow it are enqueued behind dfine_stream_wait_flag."),
 ]
 
 

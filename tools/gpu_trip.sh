@@ -11,7 +11,7 @@
 #   py:<script.py and args with , for spaces>
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
-run() { name=$1${TAG:+_$TAG}; shift; echo "== $name: $*" ; ( time timeout ${STEP_TIMEOUT:-900} "$@" ) > gpurun_out/$name.log 2>&1; echo "   rc=$? $(tail -n 1 gpurun_out/$name.log | cut -c1-200)"; }
+run() { name=$1${TAG:+_$TAG}; shift; echo "== $name: $*" ; ( time timeout -k 20 ${STEP_TIMEOUT:-900} "$@" ) > gpurun_out/$name.log 2>&1; echo "   rc=$? $(tail -n 1 gpurun_out/$name.log | cut -c1-200)"; }
 for step in "$@"; do
   IFS=: read -r kind a b c <<< "$step"
   case $kind in
