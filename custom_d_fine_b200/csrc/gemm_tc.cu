@@ -1136,6 +1136,298 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
     }
 }
 
+// ---- 16-bit split forward with the activation planes in TENSOR MEMORY (tcgen05.mma, A operand from TMEM) ---------------
+// tc_fwd_persist<.., 2, ..> is bound by shared-memory bandwidth, not by the tensor pipe: per 32-channel k-block and
+// 128 x 128 tile it moves 112 KB through shared memory (TMA writes the fp32 pixel tile and the weight planes, the converter
+// warps read the tile and write two 16-bit planes, the six MMAs read 4 KB of A and 4 KB of B each) = 875 clk at 128 B/clk
+// against 384 clk of kind::f16 tensor time.  Here the converter warps write the hi / lo planes straight into TMEM
+// (tcgen05.st, one pixel row per thread = one TMEM lane, 8 columns per 16-channel k-step and plane) and the MMAs take A from
+// there: 72 KB per k-block (562 clk), and a stage shrinks to the fp32 landing tile + the weight planes (32 KB at BN = 128:
+// a 6-deep ring).  TMEM: accumulators in columns [0, 2 BN), activation planes of stage s in [2 BN + 32 s, 2 BN + 32 s + 32)
+// as [plane][k-step][8 columns].  BN <= 128 (two accumulators of 256 columns would leave no room for the planes).
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int BN, int STAGES>
+struct TsSmem {
+    static constexpr int B_PLANE = BN * BK * 2;
+    alignas(1024) float a[STAGES][BM * BK];                 // fp32 landing buffer (128-byte swizzle)
+    alignas(1024) uint8_t b[STAGES][2 * B_PLANE];           // [hi | lo] weight planes (64-byte swizzle)
+    alignas(16) float epi[4][32 * EPL];
+    typename StatT<BN>::type statw[4][2 * BN];
+    uint64_t full[STAGES], empty[STAGES], conv[STAGES], tfull[2], tempty[2];
+    uint32_t tmem_base;
+    volatile uint32_t produced;
+};
+constexpr int TS_CONV_WARPS = 8;
+constexpr int TS_THREADS = 32 * (6 + TS_CONV_WARPS + 1);
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant__ CUtensorMap map_x,
+                                                           const __grid_constant__ CUtensorMap map_w, float* __restrict__ y,
+                                                           const float* __restrict__ bias, double* __restrict__ stats, FwdParams p,
+                                                           TileSched ts) {
+    static_assert(2 * BN + 32 * STAGES <= 512, "tc_fwd_ts: tensor memory columns");
+    extern __shared__ uint8_t raw[];
+    using Smem = TsSmem<BN, STAGES>;
+    Smem& sm = *reinterpret_cast<Smem*>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+    const int cblocks = (p.Cin + BK - 1) / BK;
+    const int num_k = p.n_taps * cblocks;
+    constexpr uint32_t TMEM_COLS = 512;
+    constexpr uint32_t A_COL0 = 2 * BN;
+
+    if (stats)
+        for (int i = threadIdx.x; i < 4 * 2 * BN; i += blockDim.x) (&sm.statw[0][0])[i] = 0;
+    if (warp == 0 && lane == 0) { prefetch_tmap(&map_x); prefetch_tmap(&map_w); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); mbar_init(&sm.conv[s], TS_CONV_WARPS); }
+            for (int a = 0; a < 2; ++a) { mbar_init(&sm.tfull[a], 1); mbar_init(&sm.tempty[a], 4); }
+            sm.produced = 0;
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(&sm.tmem_base, TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
+                const int mt = t / ts.n_tiles, n0 = (t % ts.n_tiles) * BN;
+                const int img = mt / tiles_per_img, tt = mt % tiles_per_img;
+                const int h0 = (tt / p.tiles_w) * p.TH, w0 = (tt % p.tiles_w) * p.TW;
+                const int wn_img = img * p.w_row_off, wk_img = img * p.w_k_off;
+                for (int kb = 0; kb < num_k; ++kb, ++g) {
+                    const int s = g % STAGES, ph = (g / STAGES) & 1;
+                    mbar_wait(&sm.empty[s], ph ^ 1);
+                    const int tap = kb / cblocks, c0 = (kb % cblocks) * BK;
+                    mbar_expect_tx(&sm.full[s], (uint32_t)(p.TW * p.TH * BK * sizeof(float)) + 2u * (uint32_t)Smem::B_PLANE);
+                    tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 * p.in_stride + p.dw[tap], h0 * p.in_stride + p.dh[tap], img);
+                    tma_load_3d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0 + wk_img, n0 + wn_img, 0);
+                    sm.produced = g + 1;
+                }
+            }
+            sm.produced = 0x7fffffffu;
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc16 = p.half16 ? make_idesc_f16(BN) : make_idesc_bf16(BN);
+            uint32_t g = 0, i = 0;
+            for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
+                const uint32_t acc = i & 1, aph = (i >> 1) & 1;
+                mbar_wait(&sm.tempty[acc], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem + acc * BN;
+                for (int kb = 0; kb < num_k; ++kb, ++g) {
+                    const int s = g % STAGES, ph = (g / STAGES) & 1;
+                    mbar_wait(&sm.conv[s], ph);          // planes of this stage are in TMEM (and, before that, the weights landed)
+                    tc_fence_after();
+                    const uint32_t ah = tmem + A_COL0 + (uint32_t)s * 32u, al = ah + 16u;
+                    const uint64_t bh = make_desc(smem_u32(sm.b[s]), 16, 512, 4);
+                    const uint64_t bl = make_desc(smem_u32(sm.b[s] + Smem::B_PLANE), 16, 512, 4);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        umma_f16_ts(d, al + 8 * k, bh + 2 * k, idesc16, (kb | k) != 0);
+                        umma_f16_ts(d, ah + 8 * k, bl + 2 * k, idesc16, 1);
+                        umma_f16_ts(d, ah + 8 * k, bh + 2 * k, idesc16, 1);
+                    }
+                    umma_commit(&sm.empty[s]);
+                }
+                umma_commit(&sm.tfull[acc]);
+            }
+        }
+        __syncwarp();
+    } else if (warp < 6) {
+        const int q = warp % 4;
+        const uint32_t wbase = smem_u32(sm.epi[q]);
+        const bool plain = (bias == nullptr) && p.act == 0 && !p.lab;
+        const bool local_stats = stats != nullptr && ts.n_tiles == 1;
+        typename StatT<BN>::type* sw = sm.statw[q];
+        uint32_t i = 0;
+        for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
+            const uint32_t acc = i & 1, aph = (i >> 1) & 1;
+            const int mt = t / ts.n_tiles, n0 = (t % ts.n_tiles) * BN;
+            const int img = mt / tiles_per_img, tt = mt % tiles_per_img;
+            const int h0 = (tt / p.tiles_w) * p.TH, w0 = (tt % p.tiles_w) * p.TW;
+            long row_off[8];
+            bool row_ok[8];
+#pragma unroll
+            for (int r8 = 0; r8 < 8; ++r8) {
+                const int r = 32 * q + 4 * r8 + lane / 8;
+                const int th = r / p.TW, tw = r % p.TW;
+                const int oh = h0 + th, ow = w0 + tw;
+                row_ok[r8] = th < p.TH && oh < p.OH && ow < p.OW;
+                row_off[r8] = ((long)img * p.YH + (long)oh * p.osy + p.ooy) * p.YW + (long)ow * p.osx + p.oox;
+            }
+            mbar_wait(&sm.tfull[acc], aph);
+            tc_fence_after();
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (n0 + c0 >= p.N) break;
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + acc * BN + (uint32_t)c0, v);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4)
+                    sts128(wbase + (uint32_t)(lane * EPL + 4 * c4) * 4u, __uint_as_float(v[4 * c4]),
+                           __uint_as_float(v[4 * c4 + 1]), __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
+                __syncwarp();
+                const int col = n0 + c0 + 4 * (lane % 8);
+                const bool col_ok = col < p.N;
+                float4 bv = make_float4(0, 0, 0, 0);
+                if (bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+                float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int r8 = 0; r8 < 8; ++r8) {
+                    const int r = 4 * r8 + lane / 8;
+                    float4 o = lds128(wbase + (uint32_t)(r * EPL + 4 * (lane % 8)) * 4u);
+                    o.x *= p.out_scale; o.y *= p.out_scale; o.z *= p.out_scale; o.w *= p.out_scale;
+                    if (row_ok[r8] && col_ok) {
+                        if (stats) {
+                            s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
+                            s2[0] += o.x * o.x; s2[1] += o.y * o.y; s2[2] += o.z * o.z; s2[3] += o.w * o.w;
+                        }
+                        if (!plain) {
+                            o.x = act_fwd(o.x + bv.x, p.act); o.y = act_fwd(o.y + bv.y, p.act);
+                            o.z = act_fwd(o.z + bv.z, p.act); o.w = act_fwd(o.w + bv.w, p.act);
+                            if (p.lab) {
+                                o.x = fmaf(o.x, p.lab_s, p.lab_b); o.y = fmaf(o.y, p.lab_s, p.lab_b);
+                                o.z = fmaf(o.z, p.lab_s, p.lab_b); o.w = fmaf(o.w, p.lab_s, p.lab_b);
+                            }
+                        }
+                        *reinterpret_cast<float4*>(y + row_off[r8] * p.ldy + col) = o;
+                    }
+                }
+                if (stats) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8); s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
+                        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+                    }
+                    if (lane < 8 && col_ok) {
+                        if (local_stats) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { sw[c0 + 4 * lane + j] += s1[j]; sw[BN + c0 + 4 * lane + j] += s2[j]; }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                atomicAdd(stats + col + j, (double)s1[j]);
+                                atomicAdd(stats + p.N + col + j, (double)s2[j]);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.tempty[acc]);
+        }
+    } else if (warp == 6 + TS_CONV_WARPS) {
+        if (p.prefetch > 0) {          // L2 prefetch warp (see tc_fwd_persist)
+            const uint32_t my_tiles = (uint32_t)((ts.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+            const uint32_t total_k = my_tiles * (uint32_t)num_k;
+            const uint32_t dmin = STAGES, dmax = STAGES + (uint32_t)p.prefetch;
+            uint32_t gp = 0;
+            while (gp < total_k) {
+                const uint32_t done = sm.produced;
+                if (done >= total_k) break;
+                if (gp < done + dmin) gp = done + dmin;
+                if (gp >= total_k) break;
+                if (gp > done + dmax) { __nanosleep(200); continue; }
+                const int t = (int)blockIdx.x + (int)(gp / (uint32_t)num_k) * (int)gridDim.x;
+                const int kb = (int)(gp % (uint32_t)num_k);
+                const int mt = t / ts.n_tiles;
+                const int img = mt / tiles_per_img, tt = mt % tiles_per_img;
+                const int h0 = (tt / p.tiles_w) * p.TH, w0 = (tt % p.tiles_w) * p.TW;
+                const int tap = kb / cblocks, c0 = (kb % cblocks) * BK;
+                if (t % ts.n_tiles == 0 && img < p.B) {
+#pragma unroll
+                    for (int rr = 0; rr < BM / 32; ++rr) {
+                        const int r = lane + 32 * rr;
+                        const int th = r / p.TW, tw = r % p.TW;
+                        const int ih = (h0 + th) * p.in_stride + p.dh[tap], iw = (w0 + tw) * p.in_stride + p.dw[tap];
+                        if (th < p.TH && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
+                            const float* a = p.x + (((long)img * p.H + ih) * p.W + iw) * p.ldx + c0;
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                            if (((uintptr_t)a & 127) != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 31));
+                        }
+                    }
+                }
+                ++gp;
+            }
+        }
+    } else {
+        // Converter warps (CTA warps 6..13): a warp can touch the TMEM lanes of quarter (warp % 4) only, so warp w converts
+        // pixel rows 32 (w % 4) .. +31 — one row per lane — and the two warps of a quarter split the k-block's two
+        // 16-channel k-steps.  Row r of the fp32 tile: 128 bytes, 16-byte chunk j at physical chunk j ^ (r & 7): the
+        // eight lanes of an LDS.128 phase read eight different chunks (no bank conflict).
+        const int q = warp % 4, ks = (warp - 6) / 4;
+        const int r = 32 * q + lane;
+        const uint32_t row_off = (uint32_t)r * 128u, sw7 = (uint32_t)(r & 7);
+        uint32_t g = 0;
+        for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
+            for (int kb = 0; kb < num_k; ++kb, ++g) {
+                const int s = g % STAGES, ph = (g / STAGES) & 1;
+                mbar_wait(&sm.full[s], ph);
+                const uint32_t a_row = smem_u32(sm.a[s]) + row_off;
+                float4 x[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) x[i] = lds128(a_row + ((((uint32_t)(4 * ks + i)) ^ sw7) << 4));
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (p.half16) {
+                        hi[2 * i] = f16x2_rn(x[i].x, x[i].y); hi[2 * i + 1] = f16x2_rn(x[i].z, x[i].w);
+                        lo[2 * i] = f16x2_rn(x[i].x - f16_lo(hi[2 * i]), x[i].y - f16_hi(hi[2 * i]));
+                        lo[2 * i + 1] = f16x2_rn(x[i].z - f16_lo(hi[2 * i + 1]), x[i].w - f16_hi(hi[2 * i + 1]));
+                    } else {
+                        hi[2 * i] = bf16x2_rn(x[i].x, x[i].y); hi[2 * i + 1] = bf16x2_rn(x[i].z, x[i].w);
+                        lo[2 * i] = bf16x2_rn(x[i].x - __uint_as_float(hi[2 * i] << 16), x[i].y - __uint_as_float(hi[2 * i] & 0xffff0000u));
+                        lo[2 * i + 1] = bf16x2_rn(x[i].z - __uint_as_float(hi[2 * i + 1] << 16),
+                                                  x[i].w - __uint_as_float(hi[2 * i + 1] & 0xffff0000u));
+                    }
+                }
+                const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + A_COL0 + (uint32_t)s * 32u + 8u * (uint32_t)ks;
+                tmem_st8(ta, hi);
+                tmem_st8(ta + 16u, lo);
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.conv[s]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+    if (stats && ts.n_tiles == 1) {
+        for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
+            const int c = i % BN, which = i / BN;
+            const double v = (double)sm.statw[0][i] + (double)sm.statw[1][i] + (double)sm.statw[2][i] + (double)sm.statw[3][i];
+            if (c < p.N && v != 0.0) atomicAdd(stats + (long)which * p.N + c, v);
+        }
+    }
+}
+
 // ---- CTA-pair forward on 16-bit split operands (the 3xFP16 / 3xBF16 modes) ------------------------------------------
 // tc_pair_kernel's layout with the converter stage of tc_fwd_persist<.., 2, ..>: each CTA lands its own fp32 pixel tile and
 // its HALF of the two weight planes on its OWN full barrier, its eight converter warps write the hi / lo 16-bit planes of
@@ -1795,6 +2087,20 @@ int launch_pair(const CUtensorMap& mx, const CUtensorMap& mw, float* y, const fl
 }
 
 template <int BN, int STAGES>
+int launch_ts(const CUtensorMap& mx, const CUtensorMap& mw, float* y, const float* bias, double* stats, const FwdParams& p, int B,
+              cudaStream_t st) {
+    static_assert(sizeof(TsSmem<BN, STAGES>) + 1024 <= 232448, "tc_fwd_ts: shared memory");
+    const int smem = (int)sizeof(TsSmem<BN, STAGES>) + 1024;
+    DFINE_SET_SMEM_ONCE((tc_fwd_ts<BN, STAGES>), smem, "tc_fwd_ts");
+    TileSched ts;
+    ts.n_tiles = ceil_div(p.N, BN);
+    ts.total = B * p.tiles_w * p.tiles_h * ts.n_tiles;
+    const int grid = ts.total < sm_count() ? ts.total : sm_count();
+    tc_fwd_ts<BN, STAGES><<<grid, TS_THREADS, smem, st>>>(mx, mw, y, bias, stats, p, ts);
+    return 0;
+}
+
+template <int BN, int STAGES>
 int launch_pair16(const CUtensorMap& mx, const CUtensorMap& mw, float* y, const float* bias, double* stats, const FwdParams& p,
                   int B, cudaStream_t st) {
     static_assert(sizeof(Pair16Smem<BN, STAGES>) + 1024 <= 232448, "tc_pair16: shared memory");
@@ -1915,6 +2221,10 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
         static const bool wide16 = [] { const char* e = getenv("DFINE_TC_WIDE16"); return !(e && e[0] == '0'); }();
         int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : ((Cout <= 128 || hybrid || !wide16) ? 128 : 256));
         bn = fill_bn(bn, B * p.tiles_w * p.tiles_h, Cout);
+        // activation planes in tensor memory (tc_fwd_ts): N tiles of at most 128.  DFINE_TC_TS=0: planes in shared memory.
+        static const bool use_ts = [] { const char* e = getenv("DFINE_TC_TS"); return !(e && e[0] == '0'); }();
+        const bool ts_path = use_ts && !hybrid;
+        if (ts_path && bn > 128) bn = 128;
         EncodeTiledFn enc = get_encode();
         if (!enc) { dfine_set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return -2; }
         if (hybrid) {
@@ -1953,6 +2263,14 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
         }
         p.w_planes = 1;
         cudaStream_t st = (cudaStream_t)stream;
+        if (ts_path) {
+            rc = bn == 32  ? launch_ts<32, 8>(mx, mw, y, bias, stats, p, B, st)
+               : bn == 64  ? launch_ts<64, 8>(mx, mw, y, bias, stats, p, B, st)
+                           : launch_ts<128, 6>(mx, mw, y, bias, stats, p, B, st);
+            if (rc) return rc;
+            DFINE_LAUNCH_CHECK("conv_tc(16-bit planes, A in TMEM)");
+            return 0;
+        }
         if (pair16) {
             rc = launch_pair16<256, 4>(mx, mw, y, bias, stats, p, B, st);
             if (rc) return rc;
