@@ -62,6 +62,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > (1u << 22)) __trap();  // a lost arrival must abort the launch, not hang the GPU
     }
 }
+// One lane of a converged warp.  The single-thread roles (TMA producer, MMA issuer) run their loops on the WHOLE warp and
+// only the issuing instructions sit under this predicate: inside an `if (lane == 0)` region the compiler must treat every
+// value as divergent, keeps descriptors / coordinates in vector registers and moves each one to the uniform datapath
+// through an ELECT + R2UR.BROADCAST waterfall loop — ncu's source view showed the producer thread spending 80 % of its
+// samples in that integer code (~1000 clk per k-block, the mainloop's actual bound), not waiting for a free stage.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -524,61 +535,65 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
     const uint32_t tmem = sm.tmem_base;
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t g = 0;
-            for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
-                const int mt = t / ts.n_tiles, n0 = (t % ts.n_tiles) * BN;
-                const int img = mt / tiles_per_img, tt = mt % tiles_per_img;
-                const int h0 = (tt / p.tiles_w) * p.TH, w0 = (tt % p.tiles_w) * p.TW;
-                const int wn_img = img * p.w_row_off, wk_img = img * p.w_k_off;
-                for (int kb = 0; kb < num_k; ++kb, ++g) {
-                    const int s = g % STAGES, ph = (g / STAGES) & 1;
+        // whole warp, warp-uniform values, one elected lane issues (see elect_one)
+        uint32_t g = 0, s = 0, ph = 0;
+        const uint32_t a_bytes = (uint32_t)(p.TW * p.TH * BK * sizeof(float));
+        for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
+            const int mt = t / ts.n_tiles, n0 = (t % ts.n_tiles) * BN;
+            const int img = mt / tiles_per_img, tt = mt % tiles_per_img;
+            const int h0 = (tt / p.tiles_w) * p.TH * p.in_stride, w0 = (tt % p.tiles_w) * p.TW * p.in_stride;
+            const int wn = n0 + img * p.w_row_off, wk_img = img * p.w_k_off;
+            for (int tap = 0; tap < p.n_taps; ++tap) {
+                const int xw = w0 + p.dw[tap], xh = h0 + p.dh[tap], wk = p.wk[tap] + wk_img, wk2 = p.wk2[tap] + wk_img;
+                for (int c0 = 0; c0 < p.Cin; c0 += BK) {
                     mbar_wait(&sm.empty[s], ph ^ 1);
-                    const int tap = kb / cblocks, c0 = (kb % cblocks) * BK;
-                    if (p.dbg == 11) {            // bring-up: no loads (the MMAs run on whatever smem holds)
-                        mbar_arrive(&sm.full[s]);
-                    } else if (p.dbg == 12) {     // bring-up: weights only
-                        mbar_expect_tx(&sm.full[s], (uint32_t)(BN * BK * sizeof(float)));
-                        tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0, n0);
-                    } else if (p.dbg == 13) {     // bring-up: activations only
-                        mbar_expect_tx(&sm.full[s], (uint32_t)(p.TW * p.TH * BK * sizeof(float)));
-                        tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 * p.in_stride + p.dw[tap],
-                                    h0 * p.in_stride + p.dh[tap], img);
+                    if (elect_one()) {
+                        if (p.dbg == 11) {            // bring-up: no loads (the MMAs run on whatever smem holds)
+                            mbar_arrive(&sm.full[s]);
+                        } else if (p.dbg == 12) {     // bring-up: weights only
+                            mbar_expect_tx(&sm.full[s], (uint32_t)(BN * BK * sizeof(float)));
+                            tma_load_2d(sm.b[s], &map_w, &sm.full[s], wk + c0, n0);
+                        } else if (p.dbg == 13) {     // bring-up: activations only
+                            mbar_expect_tx(&sm.full[s], a_bytes);
+                            tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, xw, xh, img);
+                        } else {
+                            mbar_expect_tx(&sm.full[s], a_bytes + (uint32_t)Smem::B_BYTES);
+                            tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, xw, xh, img);
+                            if (X3 == 3) {       // tf32 hi plane (fp32 map) + the two bf16 planes (one 3-D box, tap-padded K)
+                                tma_load_2d(sm.b[s], &map_w, &sm.full[s], wk + c0, wn);
+                                tma_load_3d(sm.b[s] + Smem::B_PLANE, &map_wlo, &sm.full[s], wk2 + c0, wn, 0);
+                            } else if (X3 == 2 || (X3 && p.w_planes)) {   // hi and lo weight planes are adjacent in memory: one 3-D box
+                                tma_load_3d(sm.b[s], &map_w, &sm.full[s], wk + c0, wn, 0);
+                            } else {
+                                tma_load_2d(sm.b[s], &map_w, &sm.full[s], wk + c0, wn);
+                                if (X3) tma_load_2d(sm.b[s] + Smem::B_PLANE, &map_wlo, &sm.full[s], wk + c0, wn);
+                            }
+                        }
+                        sm.produced = ++g;
                     } else {
-                    mbar_expect_tx(&sm.full[s], (uint32_t)(p.TW * p.TH * BK * sizeof(float)) + (uint32_t)Smem::B_BYTES);
-                    tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 * p.in_stride + p.dw[tap],
-                                h0 * p.in_stride + p.dh[tap], img);
-                    if (X3 == 3) {       // tf32 hi plane (fp32 map) + the two bf16 planes (one 3-D box, tap-padded K)
-                        tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0 + wk_img, n0 + wn_img);
-                        tma_load_3d(sm.b[s] + Smem::B_PLANE, &map_wlo, &sm.full[s], p.wk2[tap] + c0 + wk_img, n0 + wn_img, 0);
-                    } else if (X3 == 2 || (X3 && p.w_planes)) {   // hi and lo weight planes are adjacent in memory: one 3-D box
-                        tma_load_3d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0 + wk_img, n0 + wn_img, 0);
-                    } else {
-                        tma_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0 + wk_img, n0 + wn_img);
-                        if (X3) tma_load_2d(sm.b[s] + Smem::B_PLANE, &map_wlo, &sm.full[s], p.wk[tap] + c0 + wk_img, n0 + wn_img);
+                        ++g;
                     }
-                    }
-                    sm.produced = g + 1;
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
-            sm.produced = 0x7fffffffu;
         }
+        if (lane == 0) sm.produced = 0x7fffffffu;
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN, 0, 0);
-            uint32_t g = 0, i = 0;
-            for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
-                const uint32_t acc = i & 1, aph = (i >> 1) & 1;
-                mbar_wait(&sm.tempty[acc], aph ^ 1);          // epilogue has drained this accumulator
+        // whole warp, one elected lane issues the MMAs and commits (see elect_one)
+        constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+        uint32_t s = 0, ph = 0, i = 0;
+        for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
+            const uint32_t acc = i & 1, aph = (i >> 1) & 1;
+            mbar_wait(&sm.tempty[acc], aph ^ 1);          // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d = tmem + acc * BN;
+            for (int kb = 0; kb < num_k; ++kb) {
+                mbar_wait(X3 ? &sm.conv[s] : &sm.full[s], ph);
                 tc_fence_after();
-                const uint32_t d = tmem + acc * BN;
-                for (int kb = 0; kb < num_k; ++kb, ++g) {
-                    const int s = g % STAGES, ph = (g / STAGES) & 1;
-                    mbar_wait(X3 ? &sm.conv[s] : &sm.full[s], ph);
-                    tc_fence_after();
-                    const uint64_t da = make_desc(smem_u32(sm.a[s]), 16, 1024);
-                    const uint64_t db = make_desc(smem_u32(sm.b[s]), 16, 1024);
+                const uint64_t da = make_desc(smem_u32(sm.a[s]), 16, 1024);
+                const uint64_t db = make_desc(smem_u32(sm.b[s]), 16, 1024);
+                if (elect_one()) {
                     if constexpr (X3 == 2) {
                         // bf16 planes: 64-byte rows (32 channels), 64-byte swizzle (layout 4), 8-row atoms of 512 B;
                         // UMMA_K = 16 bf16 = 32 bytes -> +2 in 16-byte units per k-step
@@ -621,8 +636,9 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
                     }
                     umma_commit(&sm.empty[s]);
                 }
-                umma_commit(&sm.tfull[acc]);
+                if (++s == STAGES) { s = 0; ph ^= 1; }
             }
+            if (elect_one()) umma_commit(&sm.tfull[acc]);
         }
         __syncwarp();
     } else if (warp < 6) {
@@ -997,47 +1013,52 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
     const uint32_t tmem = sm.tmem_base;
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t g = 0;
-            for (int t = pair; t < pair_total; t += n_pairs) {
-                const int mp = t / ts.n_tiles, n0 = (t % ts.n_tiles) * BN;
-                const int mt = 2 * mp + (int)rank;                 // may be == m_tiles (odd count): coordinates fall outside
-                const int img = mt / tiles_per_img, tt = mt % tiles_per_img;      // the batch dimension -> TMA zero fill
-                const int h0 = (tt / p.tiles_w) * p.TH, w0 = (tt % p.tiles_w) * p.TW;
-                const int wn_img = img * p.w_row_off, wk_img = img * p.w_k_off;
-                for (int kb = 0; kb < num_k; ++kb, ++g) {
-                    const int s = g % STAGES, ph = (g / STAGES) & 1;
+        // whole warp, warp-uniform values, one elected lane issues (see elect_one)
+        uint32_t s = 0, ph = 0;
+        const uint32_t tx_bytes = 2u * ((uint32_t)(p.TW * p.TH * BK * sizeof(float)) + STAGE_BYTES_CTA_B);
+        for (int t = pair; t < pair_total; t += n_pairs) {
+            const int mp = t / ts.n_tiles, n0 = (t % ts.n_tiles) * BN;
+            const int mt = 2 * mp + (int)rank;                 // may be == m_tiles (odd count): coordinates fall outside
+            const int img = mt / tiles_per_img, tt = mt % tiles_per_img;      // the batch dimension -> TMA zero fill
+            const int h0 = (tt / p.tiles_w) * p.TH * p.in_stride, w0 = (tt % p.tiles_w) * p.TW * p.in_stride;
+            const int wn = n0 + (int)rank * (BN / 2) + img * p.w_row_off, wk_img = img * p.w_k_off;
+            for (int tap = 0; tap < p.n_taps; ++tap) {
+                const int xw = w0 + p.dw[tap], xh = h0 + p.dh[tap], wk = p.wk[tap] + wk_img;
+                for (int c0 = 0; c0 < p.Cin; c0 += BK) {
                     mbar_wait(&sm.empty[s], ph ^ 1);
-                    const int tap = kb / cblocks, c0 = (kb % cblocks) * BK;
-                    if (leader)      // the leader's barrier counts the bytes of BOTH CTAs' loads of this stage
-                        mbar_expect_tx(&sm.full[s], 2u * ((uint32_t)(p.TW * p.TH * BK * sizeof(float)) + STAGE_BYTES_CTA_B));
-                    tma2_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 * p.in_stride + p.dw[tap], h0 * p.in_stride + p.dh[tap],
-                                 img);
-                    tma2_load_2d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0 + wk_img, n0 + (int)rank * (BN / 2) + wn_img);
+                    if (elect_one()) {
+                        if (leader)      // the leader's barrier counts the bytes of BOTH CTAs' loads of this stage
+                            mbar_expect_tx(&sm.full[s], tx_bytes);
+                        tma2_load_4d(sm.a[s], &map_x, &sm.full[s], c0, xw, xh, img);
+                        tma2_load_2d(sm.b[s], &map_w, &sm.full[s], wk + c0, wn);
+                    }
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (leader && lane == 0) {
+        if (leader) {
             constexpr uint32_t idesc = make_idesc_m256(BN);
-            uint32_t g = 0, i = 0;
+            uint32_t s = 0, ph = 0, i = 0;
             for (int t = pair; t < pair_total; t += n_pairs, ++i) {
                 const uint32_t acc = i & 1, aph = (i >> 1) & 1;
                 mbar_wait(&sm.tempty[acc], aph ^ 1);          // the epilogue warps of both CTAs have drained this accumulator
                 tc_fence_after();
                 const uint32_t d = tmem + acc * BN;
-                for (int kb = 0; kb < num_k; ++kb, ++g) {
-                    const int s = g % STAGES, ph = (g / STAGES) & 1;
+                for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(&sm.full[s], ph);
                     tc_fence_after();
                     const uint64_t da = make_desc(smem_u32(sm.a[s]), 16, 1024);
                     const uint64_t db = make_desc(smem_u32(sm.b[s]), 16, 1024);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) umma_tf32_2cta(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit_pair(&sm.empty[s]);
+                        for (int k = 0; k < BK / 8; ++k) umma_tf32_2cta(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        umma_commit_pair(&sm.empty[s]);
+                    }
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
-                umma_commit_pair(&sm.tfull[acc]);
+                if (elect_one()) umma_commit_pair(&sm.tfull[acc]);
             }
         }
         __syncwarp();
@@ -1159,7 +1180,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                  : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 template <int BN, int STAGES>
 struct TsSmem {
     static constexpr int B_PLANE = BN * BK * 2;
@@ -1209,42 +1229,48 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
     const uint32_t tmem = sm.tmem_base;
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t g = 0;
-            for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
-                const int mt = t / ts.n_tiles, n0 = (t % ts.n_tiles) * BN;
-                const int img = mt / tiles_per_img, tt = mt % tiles_per_img;
-                const int h0 = (tt / p.tiles_w) * p.TH, w0 = (tt % p.tiles_w) * p.TW;
-                const int wn_img = img * p.w_row_off, wk_img = img * p.w_k_off;
-                for (int kb = 0; kb < num_k; ++kb, ++g) {
-                    const int s = g % STAGES, ph = (g / STAGES) & 1;
+        // TMA producer: the whole warp walks (tile, tap, channel block) with warp-uniform values, one elected lane issues
+        uint32_t g = 0, s = 0, ph = 0;
+        const uint32_t tx_bytes = (uint32_t)(p.TW * p.TH * BK * sizeof(float)) + 2u * (uint32_t)Smem::B_PLANE;
+        for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
+            const int mt = t / ts.n_tiles, n0 = (t % ts.n_tiles) * BN;
+            const int img = mt / tiles_per_img, tt = mt % tiles_per_img;
+            const int h0 = (tt / p.tiles_w) * p.TH * p.in_stride, w0 = (tt % p.tiles_w) * p.TW * p.in_stride;
+            const int wn = n0 + img * p.w_row_off, wk_img = img * p.w_k_off;
+            for (int tap = 0; tap < p.n_taps; ++tap) {
+                const int xw = w0 + p.dw[tap], xh = h0 + p.dh[tap], wk = p.wk[tap] + wk_img;
+                for (int c0 = 0; c0 < p.Cin; c0 += BK) {
                     mbar_wait(&sm.empty[s], ph ^ 1);
-                    const int tap = kb / cblocks, c0 = (kb % cblocks) * BK;
-                    mbar_expect_tx(&sm.full[s], (uint32_t)(p.TW * p.TH * BK * sizeof(float)) + 2u * (uint32_t)Smem::B_PLANE);
-                    tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, w0 * p.in_stride + p.dw[tap], h0 * p.in_stride + p.dh[tap], img);
-                    tma_load_3d(sm.b[s], &map_w, &sm.full[s], p.wk[tap] + c0 + wk_img, n0 + wn_img, 0);
-                    sm.produced = g + 1;
+                    if (elect_one()) {
+                        mbar_expect_tx(&sm.full[s], tx_bytes);
+                        tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, xw, xh, img);
+                        tma_load_3d(sm.b[s], &map_w, &sm.full[s], wk + c0, wn, 0);
+                        sm.produced = ++g;
+                    } else {
+                        ++g;
+                    }
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
-            sm.produced = 0x7fffffffu;
         }
+        if (lane == 0) sm.produced = 0x7fffffffu;
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc16 = p.half16 ? make_idesc_f16(BN) : make_idesc_bf16(BN);
-            uint32_t g = 0, i = 0;
-            for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
-                const uint32_t acc = i & 1, aph = (i >> 1) & 1;
-                mbar_wait(&sm.tempty[acc], aph ^ 1);
+        // MMA issuer: same scheme (tcgen05.mma / commit must come from ONE thread: elect.sync picks the same lane every time)
+        const uint32_t idesc16 = p.half16 ? make_idesc_f16(BN) : make_idesc_bf16(BN);
+        uint32_t s = 0, ph = 0, i = 0;
+        for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
+            const uint32_t acc = i & 1, aph = (i >> 1) & 1;
+            mbar_wait(&sm.tempty[acc], aph ^ 1);
+            tc_fence_after();
+            const uint32_t d = tmem + acc * BN;
+            for (int kb = 0; kb < num_k; ++kb) {
+                mbar_wait(&sm.conv[s], ph);          // planes of this stage are in TMEM (and, before that, the weights landed)
                 tc_fence_after();
-                const uint32_t d = tmem + acc * BN;
-                for (int kb = 0; kb < num_k; ++kb, ++g) {
-                    const int s = g % STAGES, ph = (g / STAGES) & 1;
-                    mbar_wait(&sm.conv[s], ph);          // planes of this stage are in TMEM (and, before that, the weights landed)
-                    tc_fence_after();
-                    const uint32_t ah = tmem + A_COL0 + (uint32_t)s * 32u, al = ah + 16u;
-                    const uint64_t bh = make_desc(smem_u32(sm.b[s]), 16, 512, 4);
-                    const uint64_t bl = make_desc(smem_u32(sm.b[s] + Smem::B_PLANE), 16, 512, 4);
+                const uint32_t ah = tmem + A_COL0 + s * 32u, al = ah + 16u;
+                const uint64_t bh = make_desc(smem_u32(sm.b[s]), 16, 512, 4);
+                const uint64_t bl = make_desc(smem_u32(sm.b[s] + Smem::B_PLANE), 16, 512, 4);
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         umma_f16_ts(d, al + 8 * k, bh + 2 * k, idesc16, (kb | k) != 0);
@@ -1253,15 +1279,18 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
                     }
                     umma_commit(&sm.empty[s]);
                 }
-                umma_commit(&sm.tfull[acc]);
+                if (++s == STAGES) { s = 0; ph ^= 1; }
             }
+            if (elect_one()) umma_commit(&sm.tfull[acc]);
         }
         __syncwarp();
     } else if (warp < 6) {
         const int q = warp % 4;
         const uint32_t wbase = smem_u32(sm.epi[q]);
         const bool plain = (bias == nullptr) && p.act == 0 && !p.lab;
-        const bool local_stats = stats != nullptr && ts.n_tiles == 1;
+        // warp-private shared slots whenever all tiles of this CTA cover the same channels (the host sizes the grid as a
+        // multiple of the N-tile count): global fp64 atomics per tile made the 256-wide layers 2x slower
+        const bool local_stats = stats != nullptr && (gridDim.x % ts.n_tiles) == 0;
         typename StatT<BN>::type* sw = sm.statw[q];
         uint32_t i = 0;
         for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++i) {
@@ -1383,7 +1412,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
         const int q = warp % 4, ks = (warp - 6) / 4;
         const int r = 32 * q + lane;
         const uint32_t row_off = (uint32_t)r * 128u, sw7 = (uint32_t)(r & 7);
+        // The TMEM stores of k-block g are waited for (tcgen05.wait::st) and signalled one iteration LATER, after the
+        // loads and the arithmetic of k-block g + 1: their latency is off the warp's per-k-block critical path.
         uint32_t g = 0;
+        int pending = -1;           // stage whose planes have been stored but not yet signalled
         for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
             for (int kb = 0; kb < num_k; ++kb, ++g) {
                 const int s = g % STAGES, ph = (g / STAGES) & 1;
@@ -1406,22 +1438,32 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
                                                   x[i].w - __uint_as_float(hi[2 * i + 1] & 0xffff0000u));
                     }
                 }
+                if (pending >= 0) {
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.conv[pending]);
+                }
                 const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + A_COL0 + (uint32_t)s * 32u + 8u * (uint32_t)ks;
                 tmem_st8(ta, hi);
                 tmem_st8(ta + 16u, lo);
-                tmem_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.conv[s]);
+                pending = s;
             }
+        }
+        if (pending >= 0) {
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.conv[pending]);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
-    if (stats && ts.n_tiles == 1) {
+    if (stats && (gridDim.x % ts.n_tiles) == 0) {
+        const int n0_cta = (int)(blockIdx.x % ts.n_tiles) * BN;       // the one N tile this CTA worked on
         for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
-            const int c = i % BN, which = i / BN;
+            const int c = n0_cta + i % BN, which = i / BN;
             const double v = (double)sm.statw[0][i] + (double)sm.statw[1][i] + (double)sm.statw[2][i] + (double)sm.statw[3][i];
             if (c < p.N && v != 0.0) atomicAdd(stats + (long)which * p.N + c, v);
         }
@@ -1818,17 +1860,20 @@ __global__ void __launch_bounds__(WG_THREADS) tc_wgrad_kernel(const __grid_const
     const uint32_t tmem = sm.tmem_base;
 
     if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < num_k; ++kb) {
-                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-                mbar_wait(&sm.empty[s], ph ^ 1);
-                long step = s_begin + kb;
-                const int wc = (int)(step % p.wchunks); step /= p.wchunks;
-                const int oh = (int)(step % p.OH);
-                const int b = (int)(step / p.OH);
+        // whole warp, warp-uniform values, one elected lane issues (see elect_one); the (image, row, 32-pixel chunk) of a
+        // step advances incrementally (two 64-bit divisions per step sat on the producer's critical path)
+        long step0 = s_begin;
+        int wc = (int)(step0 % p.wchunks); step0 /= p.wchunks;
+        int oh = (int)(step0 % p.OH);
+        int b = (int)(step0 / p.OH);
+        uint32_t s = 0, ph = 0;
+        const uint32_t tx_bytes = (uint32_t)(((p.dy5 ? BM / 32 : co_chunks) * 32 + BN) * BK * sizeof(float));
+        for (int kb = 0; kb < num_k; ++kb) {
+            mbar_wait(&sm.empty[s], ph ^ 1);
+            if (elect_one()) {
                 // one 5-D box {32 ch, 32 px, chunks, row, image} per operand where the channel count allows it
                 // (TMA instruction issue, not bytes, bounded the per-chunk version: 8 boxes of 4 KB per step)
-                mbar_expect_tx(&sm.full[s], (uint32_t)(((p.dy5 ? BM / 32 : co_chunks) * 32 + BN) * BK * sizeof(float)));
+                mbar_expect_tx(&sm.full[s], tx_bytes);
                 if (p.dy5) {
                     tma_load_5d(sm.a[s], &map_dy, &sm.full[s], 0, wc * 32, co0 / 32, oh, b);
                 } else {
@@ -1845,25 +1890,28 @@ __global__ void __launch_bounds__(WG_THREADS) tc_wgrad_kernel(const __grid_const
                                     wc * 32 * p.stride + kw - p.pad_l, oh * p.stride + kh - p.pad_t, b);
                 }
             }
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+            if (++wc == p.wchunks) { wc = 0; if (++oh == p.OH) { oh = 0; ++b; } }
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN, 1, 1);
-            for (int kb = 0; kb < num_k; ++kb) {
-                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-                mbar_wait(&sm.full[s], ph);
-                tc_fence_after();
-                // chunk (32 channels) stride = 32 pixels * 128 B = 4096 B (LBO); 4-pixel k-atom = 512 B (SBO)
-                const uint64_t da = make_desc(smem_u32(sm.a[s]), 32 * BK * 4, 512, 1);
-                const uint64_t db = make_desc(smem_u32(sm.b[s]), 32 * BK * 4, 512, 1);
+        constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+        uint32_t s = 0, ph = 0;
+        for (int kb = 0; kb < num_k; ++kb) {
+            mbar_wait(&sm.full[s], ph);
+            tc_fence_after();
+            // chunk (32 channels) stride = 32 pixels * 128 B = 4096 B (LBO); 4-pixel k-atom = 512 B (SBO)
+            const uint64_t da = make_desc(smem_u32(sm.a[s]), 32 * BK * 4, 512, 1);
+            const uint64_t db = make_desc(smem_u32(sm.b[s]), 32 * BK * 4, 512, 1);
+            if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 32 / 8; ++k)  // 8 pixels (two k-atoms) per UMMA -> +1024 B = +64 in 16-byte units
                     umma_tf32(tmem, da + 64 * k, db + 64 * k, idesc, (kb | k) != 0);
                 umma_commit(&sm.empty[s]);
             }
-            umma_commit(&sm.acc_full);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
         }
+        if (elect_one()) umma_commit(&sm.acc_full);
         __syncwarp();
     } else if (num_k > 0) {
         // Epilogue: TMEM -> registers (one Cout row per lane) -> shared transpose -> vector reductions.  A lane-per-row
@@ -2095,7 +2143,8 @@ int launch_ts(const CUtensorMap& mx, const CUtensorMap& mw, float* y, const floa
     TileSched ts;
     ts.n_tiles = ceil_div(p.N, BN);
     ts.total = B * p.tiles_w * p.tiles_h * ts.n_tiles;
-    const int grid = ts.total < sm_count() ? ts.total : sm_count();
+    int grid = ts.total < sm_count() ? ts.total : sm_count();
+    if (grid >= ts.n_tiles) grid -= grid % ts.n_tiles;      // every CTA then stays on ONE N tile (CTA-local BN statistics)
     tc_fwd_ts<BN, STAGES><<<grid, TS_THREADS, smem, st>>>(mx, mw, y, bias, stats, p, ts);
     return 0;
 }
