@@ -259,7 +259,7 @@ def run_ours(args):
     # single-kernel durations: the same K steps issued eagerly with CUDA events around the launches of the
     # kernel families that dominate the step (events on the launching stream; durations and algorithmic bytes
     # are summed per family: the conv kernel runs ~300 launches of 49 shapes per step)
-    cuda_ops.counters.watch = ("conv_tc", "conv_wgrad_tc", "msda_fwd", "msda_bwd")
+    cuda_ops.counters.watch = ("conv_tc", "conv_wgrad_tc", "msda_fwd", "msda_bwd", "bn_apply", "bn_bwd_reduce", "bn_bwd_apply")
     cuda_ops.counters.timed = {}
     cuda_ops.wgrad_stream.disabled = True      # one stream: a kernel's event pair must not time a concurrent kernel too
     timed(lambda: step.eager_twin(dx, dtargets), args.steps)

@@ -1414,11 +1414,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
         const uint32_t row_off = (uint32_t)r * 128u, sw7 = (uint32_t)(r & 7);
         // The TMEM stores of k-block g are waited for (tcgen05.wait::st) and signalled one iteration LATER, after the
         // loads and the arithmetic of k-block g + 1: their latency is off the warp's per-k-block critical path.
-        uint32_t g = 0;
+        uint32_t s = 0, ph = 0;
         int pending = -1;           // stage whose planes have been stored but not yet signalled
         for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
-            for (int kb = 0; kb < num_k; ++kb, ++g) {
-                const int s = g % STAGES, ph = (g / STAGES) & 1;
+            for (int kb = 0; kb < num_k; ++kb) {
                 mbar_wait(&sm.full[s], ph);
                 const uint32_t a_row = smem_u32(sm.a[s]) + row_off;
                 float4 x[4];
@@ -1444,10 +1443,11 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sm.conv[pending]);
                 }
-                const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + A_COL0 + (uint32_t)s * 32u + 8u * (uint32_t)ks;
+                const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + A_COL0 + s * 32u + 8u * (uint32_t)ks;
                 tmem_st8(ta, hi);
                 tmem_st8(ta + 16u, lo);
-                pending = s;
+                pending = (int)s;
+                if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
         if (pending >= 0) {

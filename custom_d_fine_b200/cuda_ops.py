@@ -707,9 +707,10 @@ class _ConvBnAct(torch.autograd.Function):
         else:
             _check(lib().dfine_bn_fold(_p(bn_w), _p(bn_b), _p(running_mean), _p(running_var), _p(scale), _p(shift),
                                        Cout, c_float(eps), _stream()), "bn_fold")
-        _check(lib().dfine_bn_apply(_p(conv_out), _p(scale), _p(shift), _p(pre_add), _p(post_add), _p(lab_s),
-                                    _p(lab_b), _p(y), c_long(M), Cout, ACT[act], c_long(ldy_out), c_long(ld_post), _stream()),
-               "bn_apply")
+        with _timed("bn_apply", 4 * M * Cout * (2 + (pre_add is not None) + (post_add is not None)), 0, f"bn_apply M{M} C{Cout}"):
+            _check(lib().dfine_bn_apply(_p(conv_out), _p(scale), _p(shift), _p(pre_add), _p(post_add), _p(lab_s),
+                                        _p(lab_b), _p(y), c_long(M), Cout, ACT[act], c_long(ldy_out), c_long(ld_post), _stream()),
+                   "bn_apply")
         ctx.save_for_backward(x, weight, conv_out, scale, shift, mean, invstd, pre_add, lab_s, lab_b, bn_w)
         ctx.geom, ctx.ldx, ctx.cfg = geom, ldx, cfg
         ctx.has_post = post_add is not None
@@ -741,9 +742,10 @@ class _ConvBnAct(torch.autograd.Function):
             # (eval-mode BN with LAB still needs the LAB scalar gradients; mean/invstd unused then)
             m_ = mean if mean is not None else shift
             i_ = invstd if invstd is not None else scale
-            _check(lib().dfine_bn_bwd_reduce(_p(dy), _p(conv_out), _p(scale), _p(shift), _p(m_), _p(i_), _p(pre_add),
-                                             _p(lab_s), _p(red), c_long(M), Cout, ACT[act], c_long(ld_dy), _stream()),
-                   "bn_bwd_reduce")
+            with _timed("bn_bwd_reduce", 4 * M * Cout * (2 + (pre_add is not None)), 0, f"bn_bwd_reduce M{M} C{Cout} ld{ld_dy}"):
+                _check(lib().dfine_bn_bwd_reduce(_p(dy), _p(conv_out), _p(scale), _p(shift), _p(m_), _p(i_), _p(pre_add),
+                                                 _p(lab_s), _p(red), c_long(M), Cout, ACT[act], c_long(ld_dy), _stream()),
+                       "bn_bwd_reduce")
         dconv, ld_dc = (torch.empty_like(conv_out), Cout) if groups > 1 else _alloc_nhwc(B, OH, OW, Cout, dev)
         dpre = torch.empty_like(conv_out) if (pre_add is not None and ctx.needs_input_grad[6]) else None
         # parameter gradients of BN / LAB: accumulated by the apply kernel straight into the .grad arenas
@@ -756,13 +758,15 @@ class _ConvBnAct(torch.autograd.Function):
             gs_, gl_ = _grad_dst(lab_s, "flat"), _grad_dst(lab_b, "flat")
             if gs_ is not None and gl_ is not None:
                 lab_direct = (gs_, gl_)
-        _check(lib().dfine_bn_bwd_apply(_p(dy), _p(conv_out), _p(scale), _p(shift), _p(mean), _p(invstd), _p(pre_add),
-                                        _p(lab_s), _p(red), _p(dconv), _p(dpre), c_long(M), Cout, ACT[act],
-                                        1 if bn_train else 0, _p(bn_direct[0]) if bn_direct else None,
-                                        _p(bn_direct[1]) if bn_direct else None,
-                                        _p(lab_direct[0]) if lab_direct else None,
-                                        _p(lab_direct[1]) if lab_direct else None, c_long(ld_dy), c_long(ld_dc),
-                                        _stream()), "bn_bwd_apply")
+        with _timed("bn_bwd_apply", 4 * M * Cout * (3 + (pre_add is not None) + (dpre is not None)), 0,
+                    f"bn_bwd_apply M{M} C{Cout} ld{ld_dy}"):
+            _check(lib().dfine_bn_bwd_apply(_p(dy), _p(conv_out), _p(scale), _p(shift), _p(mean), _p(invstd), _p(pre_add),
+                                            _p(lab_s), _p(red), _p(dconv), _p(dpre), c_long(M), Cout, ACT[act],
+                                            1 if bn_train else 0, _p(bn_direct[0]) if bn_direct else None,
+                                            _p(bn_direct[1]) if bn_direct else None,
+                                            _p(lab_direct[0]) if lab_direct else None,
+                                            _p(lab_direct[1]) if lab_direct else None, c_long(ld_dy), c_long(ld_dc),
+                                            _stream()), "bn_bwd_apply")
         g_bn_w = g_bn_b = g_lab_s = g_lab_b = None
         if red is not None:
             redf = None
