@@ -6,6 +6,7 @@
 #   tf32peak                  tools/measure_tf32_peak.py
 #   refgpu[:<config>]         tools/ref_on_gpu.py
 #   conv[:<mode>[:<dbg>]]     tools/bench_conv.py with DFINE_GEMM=<mode> DFINE_TC_DBG=<dbg>
+#   traffic[:<config>]        ncu DRAM bytes per kernel family of 1 eager step -> gpurun_out/traffic_<config>.json
 #   launches[:<config>]       ncu launch list of 1 eager step -> gpurun_out/launches_<config>.csv + .md summary
 #   ncu:<kernel regex>[:<config>]  ncu --set full on up to 3 launches -> summarised csv (the .ncu-rep stays on the box)
 #   py:<script.py and args with , for spaces>
@@ -24,6 +25,8 @@ for step in "$@"; do
     conv)     run conv_${a:-tc3}_${b:-0} env DFINE_GEMM=${a:-tc3} DFINE_TC_DBG=${b:-0} python tools/bench_conv.py ;;
     launches) run launches_${a:-m640} ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_${a:-m640}.csv python tools/profile_step.py --config ${a:-m640}
               python tools/ncu_summary.py launches gpurun_out/launches_${a:-m640}.csv gpurun_out/launches_${a:-m640}.md ;;
+    traffic)  run traffic_${a:-m640} ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/traffic_${a:-m640}.csv python tools/profile_step.py --config ${a:-m640}
+              python tools/ncu_summary.py traffic gpurun_out/traffic_${a:-m640}.csv gpurun_out/traffic_${a:-m640}.json ;;
     ncu)      tag=$(echo "$a" | tr -c 'A-Za-z0-9' '_'); run ncu_$tag ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:$a" -c ${c:-3} -o /tmp/prof_$tag -f python tools/profile_step.py --config ${b:-m640}
               ncu -i /tmp/prof_$tag.ncu-rep --page raw --csv > gpurun_out/ncu_raw_$tag.csv 2>/dev/null
               python tools/ncu_summary.py full /tmp/prof_$tag.ncu-rep gpurun_out/ncu_full_$tag.csv ;;

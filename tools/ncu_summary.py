@@ -21,6 +21,38 @@ KEYS = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
         "smsp__cycles_active.avg", "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu.sum"]
 
 
+FAMILIES = {"conv_tc": ("tc_fwd_persist", "tc_fwd_ts", "tc_pair_kernel", "tc_pair16_kernel", "tc_fwd_kernel"),
+            "conv_wgrad_tc": ("tc_wgrad_kernel",), "msda_fwd": ("msda_fwd_kernel",), "msda_bwd": ("msda_bwd_kernel",),
+            "bn": ("bn_apply_kernel", "bn_bwd_reduce_kernel", "bn_bwd_apply_kernel", "bn_stats_kernel", "bn_finalize_kernel"),
+            "attention": ("attn_mma::",)}
+
+
+def traffic(src, dst):
+    """DRAM bytes per kernel family of one eager step from an ncu pass with
+    --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum  ->  the json bench.py reads."""
+    import json
+    lines = open(src).read().splitlines()
+    start = next(i for i, l in enumerate(lines) if l.startswith('"ID"'))
+    per = collections.defaultdict(dict)
+    for row in csv.DictReader(lines[start:]):
+        v = float(row["Metric Value"].replace(",", ""))
+        unit = row["Metric Unit"]
+        scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+        per[row["ID"]][row["Metric Name"]] = v * scale
+        per[row["ID"]]["name"] = row["Kernel Name"]
+    out = {}
+    for fam, keys in FAMILIES.items():
+        rows = [r for r in per.values() if any(k in r["name"] for k in keys)]
+        if not rows:
+            continue
+        rd = sum(r.get("dram__bytes_read.sum", 0.0) for r in rows)
+        wr = sum(r.get("dram__bytes_write.sum", 0.0) for r in rows)
+        out[fam] = {"launches": len(rows), "us": sum(r.get("gpu__time_duration.sum", 0.0) for r in rows),
+                    "dram_read_bytes": rd, "dram_write_bytes": wr, "dram_bytes_per_launch": (rd + wr) / len(rows)}
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps({k: {"launches": v["launches"], "MB_per_launch": round(v["dram_bytes_per_launch"] / 1e6, 2)} for k, v in out.items()}))
+
+
 def launches(src, dst):
     lines = open(src).read().splitlines()
     start = next(i for i, l in enumerate(lines) if l.startswith('"ID"'))
@@ -59,34 +91,6 @@ def full(src, dst):
         for r in rows[2:]:
             w.writerow([re.sub(r"\(CUtensorMap.*|\(const float.*|\(float.*", "", r[i]) if k == "Kernel Name" else r[i]
                         for k, i in idx])
-
-
-def traffic(src, dst):
-    """Per kernel family: launches, summed duration, summed DRAM read / write bytes of one step (json)."""
-    import json
-    lines = open(src).read().splitlines()
-    start = next(i for i, l in enumerate(lines) if l.startswith('"ID"'))
-    fam = collections.defaultdict(lambda: {"launches": 0, "us": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0})
-    seen = set()
-    for row in csv.DictReader(lines[start:]):
-        name = row["Kernel Name"]
-        key = "conv_tc" if "tc_fwd_persist" in name else "conv_wgrad_tc" if "tc_wgrad" in name else \
-            "msda_fwd" if "msda_fwd" in name else "msda_bwd" if "msda_bwd" in name else None
-        if key is None:
-            continue
-        v = float(row["Metric Value"].replace(",", ""))
-        unit, metric = row["Metric Unit"], row["Metric Name"]
-        if metric == "gpu__time_duration.sum":
-            fam[key]["us"] += {"ns": v / 1e3, "us": v, "ms": v * 1e3}.get(unit, v)
-            if row["ID"] not in seen:
-                seen.add(row["ID"])
-                fam[key]["launches"] += 1
-        else:
-            b = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
-            fam[key]["dram_read_bytes" if "read" in metric else "dram_write_bytes"] += b
-    for k, d in fam.items():
-        d["dram_bytes_per_launch"] = (d["dram_read_bytes"] + d["dram_write_bytes"]) / max(d["launches"], 1)
-    json.dump(fam, open(dst, "w"), indent=1)
 
 
 if __name__ == "__main__":
