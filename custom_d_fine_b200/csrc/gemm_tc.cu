@@ -252,6 +252,8 @@ struct FwdParams {
     float lab_s, lab_b;
     const float* res;         // optional tensor added to the output in the epilogue (same pixel geometry as y,
     long ldres;               // pixel stride ldres): fuses the gradient-accumulation add of a multi-consumer tensor
+    const float* ch_scale;    // optional per-channel scale applied before the bias (tc_fwd_ts only): a frozen / eval-mode
+                              // BatchNorm folded into the epilogue, y = act(acc * scale[c] + bias[c])
 };
 
 // X3 = 0: one kind::tf32 MMA per k-step (operands truncated to tf32 by the tensor core).
@@ -1287,7 +1289,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
     } else if (warp < 6) {
         const int q = warp % 4;
         const uint32_t wbase = smem_u32(sm.epi[q]);
-        const bool plain = (bias == nullptr) && p.act == 0 && !p.lab;
+        const bool plain = (bias == nullptr) && p.act == 0 && !p.lab && p.ch_scale == nullptr;
         // warp-private shared slots whenever all tiles of this CTA cover the same channels (the host sizes the grid as a
         // multiple of the N-tile count): global fp64 atomics per tile made the 256-wide layers 2x slower
         const bool local_stats = stats != nullptr && (gridDim.x % ts.n_tiles) == 0;
@@ -1321,8 +1323,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
                 __syncwarp();
                 const int col = n0 + c0 + 4 * (lane % 8);
                 const bool col_ok = col < p.N;
-                float4 bv = make_float4(0, 0, 0, 0);
+                float4 bv = make_float4(0, 0, 0, 0), sv = make_float4(1.f, 1.f, 1.f, 1.f);
                 if (bias && col_ok) bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+                if (p.ch_scale && col_ok) sv = __ldg(reinterpret_cast<const float4*>(p.ch_scale + col));
                 float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
 #pragma unroll
                 for (int r8 = 0; r8 < 8; ++r8) {
@@ -1335,8 +1338,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
                             s2[0] += o.x * o.x; s2[1] += o.y * o.y; s2[2] += o.z * o.z; s2[3] += o.w * o.w;
                         }
                         if (!plain) {
-                            o.x = act_fwd(o.x + bv.x, p.act); o.y = act_fwd(o.y + bv.y, p.act);
-                            o.z = act_fwd(o.z + bv.z, p.act); o.w = act_fwd(o.w + bv.w, p.act);
+                            o.x = act_fwd(fmaf(o.x, sv.x, bv.x), p.act); o.y = act_fwd(fmaf(o.y, sv.y, bv.y), p.act);
+                            o.z = act_fwd(fmaf(o.z, sv.z, bv.z), p.act); o.w = act_fwd(fmaf(o.w, sv.w, bv.w), p.act);
                             if (p.lab) {
                                 o.x = fmaf(o.x, p.lab_s, p.lab_b); o.y = fmaf(o.y, p.lab_s, p.lab_b);
                                 o.z = fmaf(o.z, p.lab_s, p.lab_b); o.w = fmaf(o.w, p.lab_s, p.lab_b);
@@ -2221,7 +2224,8 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
                  int YH, int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
                  const int* taps, long ldw, int act, void* stream, long ldw16 = 0, const float* res = nullptr,
                  long ldres = 0, int half16 = 0, float out_scale = 1.f, long plane_stride16 = 0, int lab = 0,
-                 float lab_s = 1.f, float lab_b = 0.f, int w_rows = 0, int w_row_off = 0, int w_k_off = 0) {
+                 float lab_s = 1.f, float lab_b = 0.f, int w_rows = 0, int w_row_off = 0, int w_k_off = 0,
+                 const float* ch_scale = nullptr) {
     DFINE_REQUIRE(n_taps >= 1 && n_taps <= MAX_TAPS, "conv_tc: %d taps unsupported", n_taps);
     DFINE_REQUIRE(in_stride == 1 || in_stride == 2, "conv_tc: input stride %d unsupported", in_stride);
     DFINE_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldw % ((w_bf16 && !w) ? 8 : 4) == 0 &&
@@ -2248,6 +2252,7 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
     p.half16 = half16; p.out_scale = out_scale;
     p.lab = lab; p.lab_s = lab_s; p.lab_b = lab_b;
     p.w_row_off = w_row_off; p.w_k_off = w_k_off;
+    p.ch_scale = ch_scale;
     const int WR = w_rows > 0 ? w_rows : Cout;        // rows of the weight matrix the maps cover (stacked per-image weights)
     p.in_stride = in_stride; p.Cin = Cin;
     p.OH = OH; p.OW = OW; p.N = Cout; p.ldy = ldy; p.act = act;
@@ -2273,6 +2278,7 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
         // activation planes in tensor memory (tc_fwd_ts): N tiles of at most 128.  DFINE_TC_TS=0: planes in shared memory.
         static const bool use_ts = [] { const char* e = getenv("DFINE_TC_TS"); return !(e && e[0] == '0'); }();
         const bool ts_path = use_ts && !hybrid;
+        DFINE_REQUIRE(ts_path || !ch_scale, "conv_tc: the per-channel epilogue scale needs the tensor-memory kernel (DFINE_TC_TS)");
         if (ts_path && bn > 128) bn = 128;
         EncodeTiledFn enc = get_encode();
         if (!enc) { dfine_set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return -2; }
@@ -2340,6 +2346,7 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
         DFINE_LAUNCH_CHECK("conv_tc(bf16 planes)");
         return 0;
     }
+    DFINE_REQUIRE(!ch_scale, "conv_tc: the per-channel epilogue scale exists on the 16-bit-plane forward only");
     static const bool persist_bn = [] { const char* e = getenv("DFINE_TC_PERSIST"); return !(e && e[0] == '0'); }();
     // N tile: one tile covers Cout when it can (the A patch is then read exactly once); 256-wide tiles only on
     // the persistent plain-tf32 kernel (its smem ring has room for 48 KB stages)
@@ -2447,16 +2454,18 @@ DFINE_API int dfine_conv_tc_bf16x3(const float* x, const void* w_planes, const f
 // scale: `w_planes` = dfine_f16_split(w * w_scale) with w_scale a power of two that lifts the small weights' lo parts
 // out of the subnormal range; `out_scale` = 1 / w_scale is applied to the accumulator first thing in the epilogue
 // (exact).  lab != 0: the deploy-mode epilogue y = lab_scale * act(acc + bias) + lab_bias.  `plane_stride` = elements between the hi and the lo plane (0: adjacent, [2][Cout][ldw]).  Activations are split unscaled inside the kernel (post-normalisation values are O(1); |a| must stay below
-// 65504, lo parts below 2^-14 lose relative — not absolute (2^-25) — precision).
+// 65504, lo parts below 2^-14 lose relative — not absolute (2^-25) — precision).  ch_scale (optional, [Cout]): per-channel
+// scale applied before the bias — a frozen / eval-mode BatchNorm folded into the epilogue, y = act(acc * scale + bias).
 DFINE_API int dfine_conv_tc_f16x3(const float* x, const void* w_planes, const float* bias, float* y, double* stats,
                                   int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy, int YH,
                                   int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
                                   const int* taps, long ldw, int act, float out_scale, long plane_stride,
-                                  int lab, float lab_scale, float lab_bias, int w_rows, int w_row_off, void* stream) {
+                                  int lab, float lab_scale, float lab_bias, int w_rows, int w_row_off,
+                                  const float* ch_scale, void* stream) {
     DFINE_REQUIRE(w_planes != nullptr, "conv_tc_f16x3: null weight planes");
     return conv_tc_impl(x, nullptr, nullptr, w_planes, bias, y, stats, B, H, W, Cin, ldx, OH, OW, Cout, ldy, YH, YW, osy,
                         osx, ooy, oox, in_stride, n_taps, taps, ldw, act, stream, 0, nullptr, 0, 1, out_scale, plane_stride,
-                        lab, lab_scale, lab_bias, w_rows, w_row_off, 0);
+                        lab, lab_scale, lab_bias, w_rows, w_row_off, 0, ch_scale);
 }
 
 // Hybrid operands (see PersistSmem, X3 = 3): a_hi*w_hi on kind::tf32, the cross terms on bf16 copies.  `w_hi` = the

@@ -191,6 +191,24 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(
     }
 }
 
+// Backward of a frozen / eval-mode BatchNorm + ReLU that was folded into the conv epilogue (y = act(conv * scale + shift),
+// no pre-activation kept): dconv = dy * act'(y) * scale, with act' read off the OUTPUT (ReLU: y > 0; none: 1).
+__global__ void __launch_bounds__(NT) frozen_bn_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                           const float* __restrict__ scale, float* __restrict__ dx, long n4,
+                                                           int VC, int relu, long ld_dy, long ld_y, long ld_dx) {
+    for (long i = (long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long)gridDim.x * NT) {
+        const int c = (int)(i % VC) * 4;
+        const long r = i / VC;
+        const float4 g = ld4(dy + r * ld_dy + c), sc = ld4(scale + c);
+        float4 o = make_float4(g.x * sc.x, g.y * sc.y, g.z * sc.z, g.w * sc.w);
+        if (relu) {
+            const float4 v = ld4(y + r * ld_y + c);
+            o.x = v.x > 0.f ? o.x : 0.f; o.y = v.y > 0.f ? o.y : 0.f; o.z = v.z > 0.f ? o.z : 0.f; o.w = v.w > 0.f ? o.w : 0.f;
+        }
+        st4(dx + r * ld_dx + c, o);
+    }
+}
+
 // Backward pass 2.  training: dx = scale*(dz - sum_dz/M - xhat*sum_dzx/M) ; else dx = scale*dz.
 // Optionally also writes dz (= gradient of pre_add).
 __global__ void __launch_bounds__(NT) bn_bwd_apply_kernel(
@@ -456,6 +474,21 @@ DFINE_API int dfine_bn_bwd_apply(const float* dy, const float* x, const float* s
                                                                      red, dx, dpre, n4, C / 4, M, act, training, g_w,
                                                                      g_b, g_lab_s, g_lab_b, ld_dy, ld_dx);
     DFINE_LAUNCH_CHECK("bn_bwd_apply");
+    return 0;
+}
+
+// dx[M,C] (row stride ld_dx) = dy * act'(y) * scale[c] for a BatchNorm with fixed statistics folded into the producing conv's
+// epilogue (dfine_conv_tc_f16x3's ch_scale): act = DFINE_ACT_NONE or DFINE_ACT_RELU (the derivative is read off the output).
+DFINE_API int dfine_frozen_bn_bwd(const float* dy, const float* y, const float* scale, float* dx, long M, int C, int act,
+                                  long ld_dy, long ld_y, long ld_dx, void* stream) {
+    DFINE_REQUIRE(C % 4 == 0 && (act == 0 || act == 1), "frozen_bn_bwd: C=%d act=%d", C, act);
+    DFINE_REQUIRE(ld_dy >= C && ld_dy % 4 == 0 && ld_y >= C && ld_y % 4 == 0 && ld_dx >= C && ld_dx % 4 == 0 &&
+                      ((uintptr_t)dy % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)dx % 16) == 0,
+                  "frozen_bn_bwd: strides / alignment");
+    const long n4 = M * C / 4;
+    if (n4 == 0) return 0;
+    frozen_bn_bwd_kernel<<<ew_grid(n4), NT, 0, (cudaStream_t)stream>>>(dy, y, scale, dx, n4, C / 4, act == 1, ld_dy, ld_y, ld_dx);
+    DFINE_LAUNCH_CHECK("frozen_bn_bwd");
     return 0;
 }
 

@@ -324,6 +324,8 @@ def _conv2x2_ok(geom, ldx, ldy):
 
 
 _CONV2X2 = os.environ.get("DFINE_CONV2X2", "1") != "0"
+_TC_TS = os.environ.get("DFINE_TC_TS", "1") != "0"
+_FOLD_FROZEN = os.environ.get("DFINE_FOLD_FROZEN_BN", "1") != "0"   # frozen / eval BatchNorm + ReLU in the conv epilogue
 _MASK_PM = os.environ.get("DFINE_MASK_PM", "1") != "0"      # matched-mask logits through the tcgen05 mask product
 _taps_cache = {}
 
@@ -338,7 +340,7 @@ def _taps(key, make):
 
 
 def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, YH, YW, os_, oo, in_stride, taps, act,
-               stats, what, bf16_planes=None, res=None, ldres=0, plane_stride=0, lab=None, grouped=(0, 0, 0)):
+               stats, what, bf16_planes=None, res=None, ldres=0, plane_stride=0, lab=None, grouped=(0, 0, 0), ch_scale=None):
     """grouped = (total weight rows, per-image row offset, per-image column offset): per-image weights (the mask product)."""
     arr, n = taps
     # algorithmic bytes (SURVEY §8d): input pixels + output pixels + weights, each touched once, fp32
@@ -356,8 +358,9 @@ def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, Y
                                              oo[1], in_stride, n, arr, c_long(bf16_planes.shape[-1]), act,
                                              c_float(1.0 / _F16_WSCALE), c_long(plane_stride), 0 if lab is None else 1,
                                              c_float(1.0 if lab is None else lab[0]), c_float(0.0 if lab is None else lab[1]),
-                                             grouped[0], grouped[1], _stream()), what)
+                                             grouped[0], grouped[1], _p(ch_scale), _stream()), what)
         elif bf16_planes is not None:
+            assert ch_scale is None
             _check(lib().dfine_conv_tc_bf16x3(_p(x), _p(bf16_planes), _p(bias), _p(y), _p(stats), B, H, W, Cin,
                                               c_long(ldx), OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0],
                                               oo[1], in_stride, n, arr, c_long(bf16_planes.shape[-1]), act, _stream()),
@@ -404,12 +407,13 @@ def _split_bf16(w2d, taps, Cin, mode=0):
 # ------------------------------------------------------------------------------------------------
 # raw launchers (no autograd)
 # ------------------------------------------------------------------------------------------------
-def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None, lab=None):
+def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None, lab=None, ch_scale=None):
     """geom = (B,H,W,Cin,OH,OW,Cout,k,stride,pad4).  ``weight`` is the parameter ([Cout,Cin,k,k] conv or [N,K]
     linear); ``wkey`` its cache getter.  Returns True if the tensor-core kernel ran (it fuses the BN statistics)."""
     B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
     assert lab is None or _MODE == "hf3", "the fused LAB epilogue exists on the 3xFP16 path only"
-    if bias is None and act == 0 and lab is None and _conv2x2_ok(geom, ldx, ldy):
+    assert ch_scale is None or (_MODE == "hf3" and _TC_TS), "the per-channel epilogue scale exists on the tensor-memory kernel only"
+    if bias is None and act == 0 and lab is None and ch_scale is None and _conv2x2_ok(geom, ldx, ldy):
         # the stem's 2x2 convs: direct fp32 kernel (csrc/stem.cu), BN statistics fused
         wt = wkey("w2f", lambda: weight.permute(2, 3, 1, 0).reshape(4 * Cin, Cout).contiguous())
         _check(lib().dfine_conv2x2(_p(x), c_long(ldx), _p(wt), _p(y), c_long(ldy), _p(stats), B, H, W, Cin, Cout, 0, _stream()),
@@ -439,9 +443,9 @@ def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None, lab=Non
         taps = _taps(("f", k, pad[0], pad[1], cs),
                      lambda: [(kh - pad[0], kw - pad[1], (kh * k + kw) * cs) for kh in range(k) for kw in range(k)])
         _tc_launch(x, ldx, H, W, Cin, w_hi, w_lo, K, bias, y, ldy, B, OH, OW, Cout, OH, OW, (1, 1), (0, 0), stride,
-                   taps, act, stats, "conv_fwd_tc", planes, plane_stride=plane_stride, lab=lab)
+                   taps, act, stats, "conv_fwd_tc", planes, plane_stride=plane_stride, lab=lab, ch_scale=ch_scale)
         return True
-    assert lab is None, "fused LAB epilogue needs a tensor-core geometry"
+    assert lab is None and ch_scale is None, "fused LAB / scale epilogues need a tensor-core geometry"
     wr = wkey("wr", lambda: weight.reshape(Cout, Cin, k, k).permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous())
     if bias is None and act == 0 and _MODE != "simt" and \
             lib().dfine_stem_conv_supported(Cin, Cout, k, k, stride, pad[0], pad[1], pad[2], pad[3], c_long(ldy)):
@@ -655,8 +659,30 @@ class _ConvBnAct(torch.autograd.Function):
         OW = (W + pl + pr - k) // stride + 1
         geom = (B, H, W, Cin, OH, OW, Cout, k, stride, pad)
         dev = x.device
-        conv_out = torch.empty((B, OH, OW, Cout), device=dev, dtype=torch.float32)
         M = B * OH * OW
+        # BatchNorm with FIXED statistics (FrozenBatchNorm2d of the l / x backbones, eval mode) followed by ReLU / nothing:
+        # folded into the conv epilogue, y = act(conv * scale[c] + shift[c]) — no separate pass, no pre-activation tensor;
+        # the backward reads act' off the output (ReLU: y > 0).
+        ctx.folded = (_FOLD_FROZEN and not training and groups == 1 and pre_add is None and post_add is None
+                      and lab_s is None and act in (None, "relu") and _MODE == "hf3" and _TC_TS
+                      and not ctx.needs_input_grad[2] and not ctx.needs_input_grad[3]
+                      and _tc_ok(Cin, Cout, k, stride, pad, ldx, Cout) and not _conv2x2_ok(geom, ldx, Cout))
+        if ctx.folded:
+            scale, shift = _frozen_scale_shift(bn_w, bn_b, running_mean, running_var, eps)
+            if out is not None:
+                assert tuple(out.shape) == (B, OH, OW, Cout) and out.stride(3) == 1 and out.stride(2) % 4 == 0 and \
+                    out.stride(1) == OW * out.stride(2) and out.stride(0) == OH * OW * out.stride(2) and out.data_ptr() % 16 == 0
+                y, ldy_out = out.as_strided(out.shape, out.stride(), out.storage_offset()), out.stride(2)
+            else:
+                y, ldy_out = _alloc_nhwc(B, OH, OW, Cout, dev)
+            _conv_fwd(x, ldx, weight, _wcache.getter(weight), shift, y, ldy_out, geom, ACT[act], None, ch_scale=scale)
+            if ctx.needs_input_grad[0]:
+                _prefetch_dgrad_weight(weight, geom, ldx, Cout)
+            ctx.save_for_backward(x, weight, y, scale)
+            ctx.geom, ctx.ldx, ctx.cfg, ctx.ldy = geom, ldx, cfg, ldy_out
+            ctx.has_post = False
+            return (y, x_in) if tap else y
+        conv_out = torch.empty((B, OH, OW, Cout), device=dev, dtype=torch.float32)
         need_stats = training
         stats = zero_pool.take(2 * Cout, dev) if need_stats else None
         depthwise = groups > 1
@@ -724,6 +750,8 @@ class _ConvBnAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, dtap=None):
+        if ctx.folded:
+            return _ConvBnAct._backward_folded(ctx, dy, dtap)
         x, weight, conv_out, scale, shift, mean, invstd, pre_add, lab_s, lab_b, bn_w = ctx.saved_tensors
         stride, pad, groups, training, momentum, eps, act, frozen, tap = ctx.cfg
         B, H, W, Cin, OH, OW, Cout, k, _, _ = ctx.geom
@@ -806,6 +834,57 @@ class _ConvBnAct(torch.autograd.Function):
                 _conv_dgrad(dconv, ld_dc, weight, _wcache.getter(weight), g_x, Cin, ctx.geom, dtap)
         g_post = (dy if dy.is_contiguous() else dy.contiguous()) if ctx.has_post else None
         return g_x, g_w, g_bn_w, g_bn_b, g_lab_s, g_lab_b, dpre, g_post, None, None, None, None
+
+    @staticmethod
+    def _backward_folded(ctx, dy, dtap):
+        """Backward of the folded (fixed-statistics BatchNorm + ReLU in the conv epilogue) forward."""
+        x, weight, y, scale = ctx.saved_tensors
+        stride, pad, groups, training, momentum, eps, act, frozen, tap = ctx.cfg
+        B, H, W, Cin, OH, OW, Cout, k, _, _ = ctx.geom
+        ld_dy = dy.stride(2) if dy.dim() == 4 else 0
+        if not (dy.dim() == 4 and dy.stride(3) == 1 and ld_dy >= Cout and ld_dy % 4 == 0 and dy.stride(1) == OW * ld_dy
+                and dy.stride(0) == OH * OW * ld_dy and dy.data_ptr() % 16 == 0):
+            dy = dy.contiguous()
+            ld_dy = Cout
+        dev = dy.device
+        dconv, ld_dc = _alloc_nhwc(B, OH, OW, Cout, dev)
+        _check(lib().dfine_frozen_bn_bwd(_p(dy), _p(y), _p(scale), _p(dconv), c_long(B * OH * OW), Cout, ACT[act],
+                                         c_long(ld_dy), c_long(ctx.ldy), c_long(ld_dc), _stream()), "frozen_bn_bwd")
+        g_x = g_w = None
+        ldx = ctx.ldx
+        if ctx.needs_input_grad[1]:
+            dst = _grad_dst(weight, "conv")
+            if dst is not None:
+                geom_ = ctx.geom
+                wgrad_stream.run(lambda: _conv_wgrad(dconv, ld_dc, x, ldx, geom_, dst), dconv, x)
+            else:
+                g_w = _conv_wgrad(dconv, ld_dc, x, ldx, ctx.geom).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[0]:
+            g_x = torch.empty((B, H, W, Cin), device=dev, dtype=torch.float32)
+            _conv_dgrad(dconv, ld_dc, weight, _wcache.getter(weight), g_x, Cin, ctx.geom, dtap)
+        return g_x, g_w, None, None, None, None, None, None, None, None, None, None
+
+
+def _frozen_scale_shift(bn_w, bn_b, running_mean, running_var, eps):
+    """scale / shift of a BatchNorm evaluated with its running statistics, cached while none of the four tensors changes
+    (FrozenBatchNorm2d never does: the 130 per-step fold launches of the D-FINE-x backbone run once)."""
+    key = (id(bn_w), id(running_mean))
+    ver = (bn_w._version, bn_b._version, running_mean._version, running_var._version, _wcache.epoch if bn_w.requires_grad else -1)
+    hit = _fold_cache.get(key)
+    if hit is not None and hit[0] == ver and hit[3]() is bn_w:
+        return hit[1], hit[2]
+    C = bn_w.numel()
+    scale = torch.empty(C, device=bn_w.device, dtype=torch.float32)
+    shift = torch.empty(C, device=bn_w.device, dtype=torch.float32)
+    _check(lib().dfine_bn_fold(_p(bn_w), _p(bn_b), _p(running_mean), _p(running_var), _p(scale), _p(shift), C, c_float(eps),
+                               _stream()), "bn_fold")
+    if len(_fold_cache) > 4096:
+        _fold_cache.clear()
+    _fold_cache[key] = (ver, scale, shift, weakref.ref(bn_w))
+    return scale, shift
+
+
+_fold_cache = {}
 
 
 class _CatAlias(torch.autograd.Function):

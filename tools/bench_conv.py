@@ -22,6 +22,11 @@ SHAPES = [  # name, B, H, W, Cin, Cout, k, stride, pad
     ("stem2a 24->12 2x2 @320", 16, 320, 320, 24, 12, 2, 1, (0, 0, 1, 1)),
     ("enc_output 256->256 linear 134400 rows", 1, 1, 134400, 256, 256, 1, 1, (0, 0, 0, 0)),
 ]
+if len(sys.argv) > 1:        # extra geometries: BxHxWxCinxCoutxk (stride 1, "same" padding), e.g. 1x1x2000x256x1024x1
+    SHAPES = []
+    for a in sys.argv[1:]:
+        B_, H_, W_, ci_, co_, k_ = [int(v) for v in a.split("x")]
+        SHAPES.append((a, B_, H_, W_, ci_, co_, k_, 1, ((k_ - 1) // 2,) * 4))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 print({k: os.environ.get(k) for k in ("DFINE_GEMM", "DFINE_TC_PERSIST", "DFINE_TC_PREFETCH", "DFINE_TC_DBG", "DFINE_TMA_TF32")})
 for name, B, H, W, Cin, Cout, k, stride, pad in SHAPES:

@@ -82,12 +82,17 @@ def run(cls, split, steps=8):
     return losses, float(chk), dt
 
 
-ga, gb = grads_after_one_step(False), grads_after_one_step(True)
-for i, (u, v) in enumerate(zip(ga, gb)):
-    e = float((u - v).double().norm() / u.double().norm().clamp_min(1e-30))
-    assert e < 1e-4, f"gradient arena {i}: split vs plain all-reduce differ by {e:.2e}"
+# one-step gradients: plain twice (the run-to-run noise floor of this ill-conditioned seeded setup: float atomics in the
+# weight-gradient / BN reductions reorder between runs) and split once — the split must sit inside that floor
+ga, ga2, gb = grads_after_one_step(False), grads_after_one_step(False), grads_after_one_step(True)
+for i, (u, u2, v) in enumerate(zip(ga, ga2, gb)):
+    nrm = u.double().norm().clamp_min(1e-30)
+    floor = float((u - u2).double().norm() / nrm)
+    e = float((u - v).double().norm() / nrm)
     if rank == 0:
-        print(f"gradient arena {i}: split-backward vs plain all-reduce, relative L2 {e:.2e} ({u.numel()} elements)")
+        print(f"gradient arena {i}: split-backward vs plain all-reduce, relative L2 {e:.2e}; plain vs plain (noise floor) "
+              f"{floor:.2e} ({u.numel()} elements)")
+    assert e < max(1e-4, 5 * floor), f"gradient arena {i}: split vs plain all-reduce differ by {e:.2e} (noise floor {floor:.2e})"
 res = {}
 for cls in (TrainStep, GraphedTrainStep):
     for split in (False, True):
