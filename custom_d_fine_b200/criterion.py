@@ -343,10 +343,11 @@ class DFINECriterion(nn.Module):
         normalised by the box area, then averaged over the matched instances (NOT divided by num_boxes)."""
         if "pred_masks" not in out:
             return {}
-        pm = out["pred_masks"]                                   # [B, Q, Hm, Wm] logits
+        pm = out["pred_masks"]                                   # [B, Q, Hm, Wm] logits (possibly lazy: decoder.LazyMaskLogits)
         B, Q, Hm, Wm = pm.shape
+        lazy = not torch.is_tensor(pm)
         if S.n == 0 or tg[2] is None or tg[2].numel() == 0:
-            zero = pm.sum() * 0
+            zero = (pm.embed if lazy else pm).sum() * 0
             return {"loss_mask_bce": zero, "loss_mask_dice": zero}
         assert S.v is None, "per-layer / denoising sets are never padded"
         if isinstance(src, tuple):       # (bce, dice) of this head, already evaluated with the other heads (mask_losses_multi)
@@ -354,6 +355,8 @@ class DFINECriterion(nn.Module):
         if src is not None and torch.is_tensor(src):
             pred = src       # matched masks evaluated from the mask embeddings
         else:
+            if lazy:
+                pm = pm.dense()
             pred = pm.reshape(B * Q, Hm, Wm).index_select(0, S.b * Q + S.q)       # [M, Hm, Wm]
         self._gt_resized(tg, Hm, Wm)
         if pred.is_cuda and hasattr(K, "mask_loss_rows") and os.environ.get("DFINE_MASK_LOSS", "kernel") != "torch":

@@ -427,10 +427,12 @@ class DFINETransformer(nn.Module):
         return any(t.get("masks") is not None and hasattr(t["masks"], "numel") and t["masks"].numel() > 0
                    for t in targets)
 
-    def _mask_logits(self, h, mask_feat, keep=None):
+    def _mask_logits(self, h, mask_feat, keep=None, lazy=False):
         e = self.mask_head(h) * (self.mask_dim ** -0.5)
         if keep is not None:
             keep.append(e)
+        if lazy:
+            return LazyMaskLogits(e, mask_feat)
         return K.mask_dot(e, mask_feat)   # [B,Q,C] x [B,Hm,Wm,C] -> [B,Q,Hm,Wm]
 
     def forward(self, feats, targets=None):
@@ -471,8 +473,12 @@ class DFINETransformer(nn.Module):
             pred_masks = self._mask_logits(hs[-1], mask_feat, emb)
             dn_pred_masks = dn_aux_masks = None
             if split_dn:
-                dn_aux_masks = [self._mask_logits(h, mask_feat, dn_emb) for h in dn_hs[:-1]]
-                dn_pred_masks = self._mask_logits(dn_hs[-1], mask_feat, dn_emb)
+                # The denoising heads' dense [B,n_dn,Hm,Wm] logits have no consumer in a train step — no matching (the
+                # assignment is fixed), and the mask losses evaluate the matched rows from the embeddings — so they are
+                # handed out LAZILY (164 MB and one 124 us product per head at D-FINE-l-seg, batch 8): the object
+                # behaves like the tensor (shape, indexing, .cpu(), arithmetic) and materialises on first use.
+                dn_aux_masks = [self._mask_logits(h, mask_feat, dn_emb, lazy=True) for h in dn_hs[:-1]]
+                dn_pred_masks = self._mask_logits(dn_hs[-1], mask_feat, dn_emb, lazy=True)
 
         if not self.training:
             out = {"pred_logits": logits[-1], "pred_boxes": boxes[-1]}
@@ -506,6 +512,63 @@ class DFINETransformer(nn.Module):
                 out["dn_pre_outputs"] = {"pred_logits": dn_pre_logits, "pred_boxes": dn_pre_boxes}
                 out["dn_meta"] = dn_meta
         return out
+
+
+class LazyMaskLogits:
+    """Mask logits [B,Q,Hm,Wm] = embed [B,Q,C] . feat [B,Hm,Wm,C] that are computed on first use (dfine_decoder.py:353-370's
+    einsum for a head whose dense output nobody reads in training).  ``shape`` / ``dim()`` / ``device`` answer without
+    materialising; anything else (indexing, .cpu(), arithmetic, torch functions via ``dense()``) runs the product once."""
+
+    def __init__(self, embed, feat):
+        self.embed, self.feat, self._dense = embed, feat, None
+
+    @property
+    def shape(self):
+        B, Q, _ = self.embed.shape
+        return torch.Size((B, Q, self.feat.shape[1], self.feat.shape[2]))
+
+    def size(self, d=None):
+        return self.shape if d is None else self.shape[d]
+
+    def dim(self):
+        return 4
+
+    @property
+    def device(self):
+        return self.embed.device
+
+    @property
+    def dtype(self):
+        return self.embed.dtype
+
+    def dense(self):
+        if self._dense is None:
+            self._dense = K.mask_dot(self.embed, self.feat)
+        return self._dense
+
+    def __getitem__(self, idx):
+        return self.dense()[idx]
+
+    def __getattr__(self, name):          # everything else: the tensor's own attribute / method
+        if name.startswith("__") or name in ("embed", "feat", "_dense"):
+            raise AttributeError(name)
+        return getattr(self.dense(), name)
+
+    def __sub__(self, o):
+        return self.dense() - o
+
+    def __rsub__(self, o):
+        return o - self.dense()
+
+    def __add__(self, o):
+        return self.dense() + o
+
+    __radd__ = __add__
+
+    def __mul__(self, o):
+        return self.dense() * o
+
+    __rmul__ = __mul__
 
 
 def _layer_dicts(logits, boxes, corners, refs, teacher_corners, teacher_logits, masks=None):
