@@ -316,6 +316,7 @@ class GraphedTrainStep(TrainStep):
         self._seen = OrderedDict()
         self._graphs = OrderedDict()
         self._plans = {}
+        self._static, self._static_seen = OrderedDict(), {}      # backbone + encoder graphs per input shape (hybrid steps)
         # Warm-up steps and captures share ONE side stream: autograd's AccumulateGrad nodes remember the stream
         # they were created on, and a node created on the legacy default stream cannot be used under capture.
         self._side = torch.cuda.Stream() if next(self.model.parameters()).is_cuda else None
@@ -350,7 +351,7 @@ class GraphedTrainStep(TrainStep):
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
                 if n < self.eager_steps or key not in self._plans:     # (a plan evicted with its counter: one more eager step)
-                    res = super().__call__(inputs, targets)
+                    res = self._uncaptured_step(inputs, targets)
                     if n >= self.eager_steps - 1:          # the index plan of the LAST eager step is reused to capture
                         self._plans[key] = self.loss_fn.last_plan
                     eager = True
@@ -365,6 +366,83 @@ class GraphedTrainStep(TrainStep):
             if eager:
                 return res
         return self._replay(g, inputs, targets)
+
+    # ---- steps whose key is not captured: the target-independent half of the step still replays ---------------------
+    # With a real loader the per-image target counts (part of the graph key: the denoising groups, the matcher and the
+    # index table take their shapes from them) rarely repeat, and a fully eager step is host-bound (~2250 launches from
+    # Python: 134 ms against 35 ms replayed for D-FINE-m).  Backbone + encoder see only the images, so their forward and
+    # their backward are captured ONCE per input shape (the autograd graph is cut at the encoder's outputs, like the
+    # data-parallel split of TrainStep._forward); the decoder, the matcher, the criterion and their backward run eagerly
+    # between the two replays.  DFINE_HYBRID_GRAPH=0 keeps such steps fully eager.
+    def _uncaptured_step(self, inputs, targets):
+        import os
+        m = self.model
+        ok = (os.environ.get("DFINE_HYBRID_GRAPH", "1") != "0" and hasattr(m, "backbone") and hasattr(m, "encoder")
+              and hasattr(m, "decoder") and m.training)
+        if not ok:
+            return TrainStep.__call__(self, inputs, targets)
+        skey = tuple(inputs.shape)
+        st = self._static.get(skey)
+        if st is None:
+            n = self._static_seen.get(skey, 0)
+            self._static_seen[skey] = n + 1
+            if n < self.eager_steps:                   # eager steps double as the warm-up CUDA graphs need
+                return TrainStep.__call__(self, inputs, targets)
+            st = self._static[skey] = self._capture_static(inputs)
+            while len(self._static) > 2:               # (each owns the activations of a backbone + encoder pass)
+                self._static.pop(next(iter(self._static)))
+        return self._hybrid_step(st, inputs, targets)
+
+    def _capture_static(self, inputs):
+        from . import cuda_ops
+        m, dev = self.model, inputs.device
+        st = {"x": inputs.clone()}
+        pool, saved = cuda_ops._ZeroPool(), cuda_ops.zero_pool
+        cuda_ops.weights_changed()          # every cached weight re-layout is stale: the captures re-create them as graph nodes
+        torch.cuda.synchronize()
+        gF, gB = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        try:
+            cuda_ops.zero_pool = pool       # the captured half owns its fp64 scratch (zeroed by a captured memset)
+            with torch.cuda.graph(gF, stream=self._side):
+                pool.begin_step(dev)
+                cuda_ops.wgrad_stream.begin(dev)
+                feats = list(m.encoder(m.backbone(st["x"].permute(0, 2, 3, 1))))
+                cuda_ops.wgrad_stream.sync_main()
+            st["gbuf"] = [torch.zeros_like(f) for f in feats]
+            with torch.cuda.graph(gB, pool=gF.pool(), stream=self._side):
+                pool.active = True
+                torch.autograd.backward(feats, st["gbuf"])
+                cuda_ops.wgrad_stream.sync_main()
+        finally:
+            pool.end_step()
+            cuda_ops.zero_pool = saved
+            cuda_ops.wgrad_stream.join()
+        st.update(gF=gF, gB=gB, feats=feats)
+        return st
+
+    def _hybrid_step(self, st, inputs, targets):
+        from . import cuda_ops
+        st["x"].copy_(inputs, non_blocking=True)
+        _begin_step(inputs, self._counters)
+        st["gF"].replay()
+        leaves = [f.detach().requires_grad_(True) for f in st["feats"]]
+        output = self.model.decoder(leaves, targets)
+        _after_forward()
+        loss_dict = self.loss_fn(output, targets)
+        loss = sum(loss_dict.values())
+        loss.backward()
+        cuda_ops.wgrad_stream.sync_main()
+        for b, l in zip(st["gbuf"], leaves):
+            if l.grad is None:
+                b.zero_()
+            else:
+                b.copy_(l.grad)
+        st["gB"].replay()
+        _end_step()
+        self.batch_idx += 1
+        self.optimizer_step()
+        cuda_ops.weights_changed()
+        return loss.detach(), loss_dict
 
     def _capture(self, inputs, targets, plan):
         from . import cuda_ops

@@ -290,6 +290,40 @@ def test_graph_replay_matches_eager(cuda_ops):
     check_close("EMA weights", traj["graph"][1][k], traj["eager"][1][k], 1e-3)
 
 
+def test_hybrid_steps_with_changing_target_counts_match_eager(cuda_ops):
+    """Batches whose per-image target counts never repeat (no full-step graph key repeats): GraphedTrainStep replays the
+    backbone + encoder forward / backward as CUDA graphs and runs decoder, matcher and criterion eagerly.  Same weights,
+    same batches, same RNG state as the eager TrainStep -> the same loss trajectory and EMA weights (atomics-order noise)."""
+    from custom_d_fine_b200.model import build_optimizer
+    from custom_d_fine_b200.train import GraphedTrainStep, ModelEMA, TrainStep
+    batches = []
+    for i, T in enumerate([(5, 3), (2, 7), (4, 4), (1, 6), (3, 2), (6, 1), (2, 2), (7, 5)]):
+        x, targets = synthetic_batch(2, 320, 320, seed=70 + i, T=T)
+        batches.append((x.cuda(), [{k: v.cuda() for k, v in t.items()} for t in targets]))
+    traj = {}
+    for name, cls in (("eager", TrainStep), ("hybrid", GraphedTrainStep)):
+        torch.manual_seed(0)
+        model = build_model("s", 80, False, "cuda", img_size=(320, 320))
+        seeded_fill(model, 3)
+        model.train()
+        ema = ModelEMA(model, 0.9998)
+        opt = build_optimizer(model, lr=1e-4, backbone_lr=1e-5, betas=(0.9, 0.999), weight_decay=1e-4, base_lr=1e-4)
+        step = cls(model, build_loss("s", 80, 0.0, False), opt, ema=ema, clip_max_norm=0.1)
+        torch.manual_seed(11)
+        torch.cuda.manual_seed(11)
+        losses = [float(step(x, t)[0]) for x, t in batches]
+        traj[name] = (losses, {k: v.detach().clone() for k, v in ema.model.state_dict().items() if v.dtype.is_floating_point})
+        if name == "hybrid":
+            assert step._static and not step._graphs, "the static-part graphs were not used"
+    for a, b in zip(*[traj[k][0] for k in ("eager", "hybrid")]):
+        assert abs(a - b) <= 2e-2 * abs(a), (traj["eager"][0], traj["hybrid"][0])
+    k = "decoder.dec_score_head.0.weight"
+    check_close("EMA weights", traj["hybrid"][1][k], traj["eager"][1][k], 1e-3)
+    k = "backbone.stages.0.blocks.0.layers.0.conv.weight"
+    if k in traj["eager"][1]:
+        check_close("EMA backbone weights", traj["hybrid"][1][k], traj["eager"][1][k], 1e-3)
+
+
 def test_loss_trajectory_default_mode_tracks_fp32(cuda_ops):
     """What the reduced-precision GRADIENT products do to training (forward GEMMs are error-compensated, data / weight
     gradients are single tf32 MMAs): 30 optimisation steps of D-FINE-s from the same weights, batches and generator

@@ -1,5 +1,6 @@
-"""The step when the per-image target counts do NOT repeat (a real loader): GraphedTrainStep keys its CUDA graphs on
-(input shape, per-image counts), so such steps take the eager path (a correct, slower path; captured keys are LRU-bounded).
+"""The step when the per-image target counts do NOT repeat (a real loader): GraphedTrainStep keys its full-step CUDA graphs
+on (input shape, per-image counts), so such steps take the HYBRID path — backbone + encoder forward / backward replayed as
+graphs captured once per input shape, decoder / matcher / criterion eager (DFINE_HYBRID_GRAPH=0: fully eager).
 Times D-FINE-m, batch 16, 640x640 with counts drawn uniformly from 1..20 anew every step, next to the fixed-count
 (10 per image) graph-replay number that bench.py reports.
 
@@ -7,6 +8,7 @@ Times D-FINE-m, batch 16, 640x640 with counts drawn uniformly from 1..20 anew ev
 """
 import argparse
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -55,6 +57,7 @@ ms_fixed = run(args.steps, lambda: fixed)
 run(3, targets)
 ms_var = run(args.steps, targets)
 print(json.dumps({"workload": "D-FINE-m train step, batch 16, 640x640", "fixed_counts_graph_replay_ms": round(ms_fixed, 2),
-                  "fixed_counts_img_s": round(B / ms_fixed * 1e3, 1), "variable_counts_eager_ms": round(ms_var, 2),
+                  "fixed_counts_img_s": round(B / ms_fixed * 1e3, 1), "variable_counts_ms": round(ms_var, 2),
                   "variable_counts_img_s": round(B / ms_var * 1e3, 1), "steps": args.steps,
-                  "note": "counts ~ U{1..20} per image, new every step: no graph key repeats, every step runs eagerly"}))
+                  "hybrid": os.environ.get("DFINE_HYBRID_GRAPH", "1") != "0",
+                  "note": "counts ~ U{1..20} per image, new every step: no full-step graph key repeats"}))
