@@ -73,6 +73,31 @@ __device__ __forceinline__ float act_bwd(float z, int act) {
     }
 }
 
+// Train-mode BatchNorm finalize of ONE channel from its complete fp64 sums (sum x, sum x^2 over M pixels): mean / invstd,
+// the folded scale / shift, and the running-statistics update (momentum, unbiased variance) — torch.nn.BatchNorm2d's
+// arithmetic (hgnetv2.py:65 / hybrid_encoder.py:36).  Shared by bn_finalize_kernel and the conv kernel's last-CTA tail.
+__device__ __forceinline__ void bn_finalize_channel(double sum, double sumsq, int c, const float* __restrict__ weight,
+                                                    const float* __restrict__ bias, float* __restrict__ running_mean,
+                                                    float* __restrict__ running_var, float* __restrict__ mean_out,
+                                                    float* __restrict__ invstd_out, float* __restrict__ scale_out,
+                                                    float* __restrict__ shift_out, long M, float momentum, float eps) {
+    const double mean = sum / (double)M;
+    double var = sumsq / (double)M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float w = weight ? weight[c] : 1.f, b = bias ? bias[c] : 0.f;
+    mean_out[c] = (float)mean;
+    invstd_out[c] = invstd;
+    const float sc = w * invstd;
+    scale_out[c] = sc;
+    shift_out[c] = b - (float)mean * sc;
+    if (running_mean) {
+        const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -254,6 +254,20 @@ struct FwdParams {
     long ldres;               // pixel stride ldres): fuses the gradient-accumulation add of a multi-consumer tensor
     const float* ch_scale;    // optional per-channel scale applied before the bias (tc_fwd_ts only): a frozen / eval-mode
                               // BatchNorm folded into the epilogue, y = act(acc * scale[c] + bias[c])
+    // Train-mode BatchNorm finalize in the kernel's tail (tc_fwd_ts only; fin_counter != null): the CTA that retires last
+    // (ticket on fin_counter, zeroed by the caller with `stats`) turns the complete per-channel sums into mean / invstd /
+    // scale / shift and updates the running statistics — bn_finalize_kernel's arithmetic without its launch.
+    unsigned int* fin_counter;
+    const float* fin_w;       // BatchNorm weight / bias (null: 1 / 0)
+    const float* fin_b;
+    float* fin_rmean;         // running statistics (null: not tracked)
+    float* fin_rvar;
+    float* fin_mean;          // outputs, [N] each
+    float* fin_invstd;
+    float* fin_scale;
+    float* fin_shift;
+    long fin_M;               // pixels the statistics were taken over
+    float fin_momentum, fin_eps;
 };
 
 // X3 = 0: one kind::tf32 MMA per k-step (operands truncated to tf32 by the tensor core).
@@ -1192,6 +1206,7 @@ struct TsSmem {
     uint64_t full[STAGES], empty[STAGES], conv[STAGES], tfull[2], tempty[2];
     uint32_t tmem_base;
     volatile uint32_t produced;
+    uint32_t last_cta;
 };
 constexpr int TS_CONV_WARPS = 8;
 constexpr int TS_THREADS = 32 * (6 + TS_CONV_WARPS + 1);
@@ -1469,6 +1484,20 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
             const int c = n0_cta + i % BN, which = i / BN;
             const double v = (double)sm.statw[0][i] + (double)sm.statw[1][i] + (double)sm.statw[2][i] + (double)sm.statw[3][i];
             if (c < p.N && v != 0.0) atomicAdd(stats + (long)which * p.N + c, v);
+        }
+    }
+    if (stats && p.fin_counter) {
+        // last-CTA finalize: every thread's statistics atomics are ordered before the CTA's ticket (fence + barrier);
+        // the CTA drawing the last ticket sees all of them (fence after the ticket, L2 loads)
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) sm.last_cta = atomicAdd(p.fin_counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+        __syncthreads();
+        if (sm.last_cta) {
+            __threadfence();
+            for (int c = threadIdx.x; c < p.N; c += blockDim.x)
+                bn_finalize_channel(__ldcg(stats + c), __ldcg(stats + p.N + c), c, p.fin_w, p.fin_b, p.fin_rmean, p.fin_rvar,
+                                    p.fin_mean, p.fin_invstd, p.fin_scale, p.fin_shift, p.fin_M, p.fin_momentum, p.fin_eps);
         }
     }
 }
@@ -2219,13 +2248,19 @@ DFINE_API int dfine_conv_tc_supported(int Cin, int Cout, int KH, int KW, int str
 // w_lo == null: plain kind::tf32.  w_lo != null: 3xTF32 — `w` must then hold tf32-rounded weights and w_lo the
 // remainders (dfine_tf32_split); activations are split inside the kernel.  nn.Linear on [rows, K]: B=1, H=1, W=rows.
 namespace {
+struct BnFinArgs {      // the fused train-mode BatchNorm finalize (FwdParams::fin_*)
+    unsigned int* counter;
+    const float *w, *b;
+    float *rmean, *rvar, *mean, *invstd, *scale, *shift;
+    float momentum, eps;
+};
 int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* w_bf16, const float* bias, float* y,
                  double* stats, int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy,
                  int YH, int YW, int osy, int osx, int ooy, int oox, int in_stride, int n_taps,
                  const int* taps, long ldw, int act, void* stream, long ldw16 = 0, const float* res = nullptr,
                  long ldres = 0, int half16 = 0, float out_scale = 1.f, long plane_stride16 = 0, int lab = 0,
                  float lab_s = 1.f, float lab_b = 0.f, int w_rows = 0, int w_row_off = 0, int w_k_off = 0,
-                 const float* ch_scale = nullptr) {
+                 const float* ch_scale = nullptr, const BnFinArgs* fin = nullptr) {
     DFINE_REQUIRE(n_taps >= 1 && n_taps <= MAX_TAPS, "conv_tc: %d taps unsupported", n_taps);
     DFINE_REQUIRE(in_stride == 1 || in_stride == 2, "conv_tc: input stride %d unsupported", in_stride);
     DFINE_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldw % ((w_bf16 && !w) ? 8 : 4) == 0 &&
@@ -2253,6 +2288,14 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
     p.lab = lab; p.lab_s = lab_s; p.lab_b = lab_b;
     p.w_row_off = w_row_off; p.w_k_off = w_k_off;
     p.ch_scale = ch_scale;
+    p.fin_counter = nullptr;
+    if (fin) {
+        DFINE_REQUIRE(stats && fin->counter && fin->mean && fin->invstd && fin->scale && fin->shift && half16 && w_bf16 && !w,
+                      "conv_tc: the fused BatchNorm finalize needs statistics, its outputs and the 3xFP16 tensor-memory kernel");
+        p.fin_counter = fin->counter; p.fin_w = fin->w; p.fin_b = fin->b; p.fin_rmean = fin->rmean; p.fin_rvar = fin->rvar;
+        p.fin_mean = fin->mean; p.fin_invstd = fin->invstd; p.fin_scale = fin->scale; p.fin_shift = fin->shift;
+        p.fin_M = (long)B * OH * OW; p.fin_momentum = fin->momentum; p.fin_eps = fin->eps;
+    }
     const int WR = w_rows > 0 ? w_rows : Cout;        // rows of the weight matrix the maps cover (stacked per-image weights)
     p.in_stride = in_stride; p.Cin = Cin;
     p.OH = OH; p.OW = OW; p.N = Cout; p.ldy = ldy; p.act = act;
@@ -2279,6 +2322,7 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
         static const bool use_ts = [] { const char* e = getenv("DFINE_TC_TS"); return !(e && e[0] == '0'); }();
         const bool ts_path = use_ts && !hybrid;
         DFINE_REQUIRE(ts_path || !ch_scale, "conv_tc: the per-channel epilogue scale needs the tensor-memory kernel (DFINE_TC_TS)");
+        DFINE_REQUIRE(ts_path || !fin, "conv_tc: the fused BatchNorm finalize needs the tensor-memory kernel (DFINE_TC_TS)");
         if (ts_path && bn > 128) bn = 128;
         EncodeTiledFn enc = get_encode();
         if (!enc) { dfine_set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return -2; }
@@ -2466,6 +2510,23 @@ DFINE_API int dfine_conv_tc_f16x3(const float* x, const void* w_planes, const fl
     return conv_tc_impl(x, nullptr, nullptr, w_planes, bias, y, stats, B, H, W, Cin, ldx, OH, OW, Cout, ldy, YH, YW, osy,
                         osx, ooy, oox, in_stride, n_taps, taps, ldw, act, stream, 0, nullptr, 0, 1, out_scale, plane_stride,
                         lab, lab_scale, lab_bias, w_rows, w_row_off, 0, ch_scale);
+}
+
+// dfine_conv_tc_f16x3 for a conv followed by a TRAIN-mode BatchNorm: besides the per-channel statistics (`stats`,
+// double [2*Cout], zeroed by the caller) the kernel's last CTA runs dfine_bn_finalize's arithmetic in its tail — mean /
+// invstd / scale / shift [Cout] and the running-statistics update (hgnetv2.py:65, torch BatchNorm2d momentum rule) —
+// so the separate finalize launch disappears.  `counter`: one zeroed unsigned int (the retirement ticket).
+DFINE_API int dfine_conv_tc_f16x3_bn(const float* x, const void* w_planes, float* y, double* stats, unsigned int* counter,
+                                     const float* bn_weight, const float* bn_bias, float* running_mean,
+                                     float* running_var, float* mean, float* invstd, float* scale, float* shift,
+                                     float momentum, float eps, int B, int H, int W, int Cin, long ldx, int OH, int OW,
+                                     int Cout, long ldy, int in_stride, int n_taps, const int* taps, long ldw,
+                                     float out_scale, long plane_stride, void* stream) {
+    DFINE_REQUIRE(w_planes != nullptr, "conv_tc_f16x3_bn: null weight planes");
+    BnFinArgs fin{counter, bn_weight, bn_bias, running_mean, running_var, mean, invstd, scale, shift, momentum, eps};
+    return conv_tc_impl(x, nullptr, nullptr, w_planes, nullptr, y, stats, B, H, W, Cin, ldx, OH, OW, Cout, ldy, OH, OW, 1, 1,
+                        0, 0, in_stride, n_taps, taps, ldw, 0, stream, 0, nullptr, 0, 1, out_scale, plane_stride, 0, 1.f,
+                        0.f, 0, 0, 0, nullptr, &fin);
 }
 
 // Hybrid operands (see PersistSmem, X3 = 3): a_hi*w_hi on kind::tf32, the cross terms on bf16 copies.  `w_hi` = the

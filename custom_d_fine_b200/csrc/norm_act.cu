@@ -71,21 +71,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float
                                    float* __restrict__ shift_out, long M, int C, float momentum, float eps) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    const double mean = stats[c] / (double)M;
-    double var = stats[C + c] / (double)M - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float w = weight ? weight[c] : 1.f, b = bias ? bias[c] : 0.f;
-    mean_out[c] = (float)mean;
-    invstd_out[c] = invstd;
-    const float sc = w * invstd;
-    scale_out[c] = sc;
-    shift_out[c] = b - (float)mean * sc;
-    if (running_mean) {
-        const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
-    }
+    bn_finalize_channel(stats[c], stats[C + c], c, weight, bias, running_mean, running_var, mean_out, invstd_out, scale_out,
+                        shift_out, M, momentum, eps);
 }
 
 // scale/shift from running statistics (eval BatchNorm / FrozenBatchNorm2d, common.py:58-67)

@@ -340,8 +340,11 @@ def _taps(key, make):
 
 
 def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, YH, YW, os_, oo, in_stride, taps, act,
-               stats, what, bf16_planes=None, res=None, ldres=0, plane_stride=0, lab=None, grouped=(0, 0, 0), ch_scale=None):
-    """grouped = (total weight rows, per-image row offset, per-image column offset): per-image weights (the mask product)."""
+               stats, what, bf16_planes=None, res=None, ldres=0, plane_stride=0, lab=None, grouped=(0, 0, 0), ch_scale=None,
+               bn_fin=None):
+    """grouped = (total weight rows, per-image row offset, per-image column offset): per-image weights (the mask product).
+    bn_fin = (counter, bn_w, bn_b, running_mean, running_var, mean, invstd, scale, shift, momentum, eps): the train-mode
+    BatchNorm finalize runs in the kernel's tail (3xFP16 tensor-memory kernel only)."""
     arr, n = taps
     # algorithmic bytes (SURVEY §8d): input pixels + output pixels + weights, each touched once, fp32
     nbytes = 4 * (B * min(H * W, OH * OW * in_stride * in_stride) * Cin + B * OH * OW * Cout + Cout * n * Cin)
@@ -352,6 +355,15 @@ def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, Y
                                               c_long(ldx), OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0],
                                               oo[1], in_stride, n, arr, c_long(ldw), c_long(bf16_planes.shape[-1]),
                                               act, _stream()), what)
+        elif bn_fin is not None:
+            assert bf16_planes is not None and bf16_planes.dtype == torch.float16 and bias is None and act == 0 \
+                and lab is None and ch_scale is None and os_ == (1, 1) and oo == (0, 0) and (YH, YW) == (OH, OW)
+            cnt, bw, bb, rm, rv, mean, invstd, scale, shift, momentum, eps = bn_fin
+            _check(lib().dfine_conv_tc_f16x3_bn(_p(x), _p(bf16_planes), _p(y), _p(stats), _p(cnt), _p(bw), _p(bb), _p(rm),
+                                                _p(rv), _p(mean), _p(invstd), _p(scale), _p(shift), c_float(momentum),
+                                                c_float(eps), B, H, W, Cin, c_long(ldx), OH, OW, Cout, c_long(ldy),
+                                                in_stride, n, arr, c_long(bf16_planes.shape[-1]),
+                                                c_float(1.0 / _F16_WSCALE), c_long(plane_stride), _stream()), what)
         elif bf16_planes is not None and bf16_planes.dtype == torch.float16:
             _check(lib().dfine_conv_tc_f16x3(_p(x), _p(bf16_planes), _p(bias), _p(y), _p(stats), B, H, W, Cin,
                                              c_long(ldx), OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0],
@@ -407,9 +419,10 @@ def _split_bf16(w2d, taps, Cin, mode=0):
 # ------------------------------------------------------------------------------------------------
 # raw launchers (no autograd)
 # ------------------------------------------------------------------------------------------------
-def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None, lab=None, ch_scale=None):
+def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None, lab=None, ch_scale=None, bn_fin=None):
     """geom = (B,H,W,Cin,OH,OW,Cout,k,stride,pad4).  ``weight`` is the parameter ([Cout,Cin,k,k] conv or [N,K]
-    linear); ``wkey`` its cache getter.  Returns True if the tensor-core kernel ran (it fuses the BN statistics)."""
+    linear); ``wkey`` its cache getter.  Returns True if the tensor-core kernel ran (it fuses the BN statistics).
+    ``bn_fin`` (see _tc_launch) may only be passed when ``_bn_fin_ok`` holds for the layer."""
     B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
     assert lab is None or _MODE == "hf3", "the fused LAB epilogue exists on the 3xFP16 path only"
     assert ch_scale is None or (_MODE == "hf3" and _TC_TS), "the per-channel epilogue scale exists on the tensor-memory kernel only"
@@ -443,9 +456,10 @@ def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None, lab=Non
         taps = _taps(("f", k, pad[0], pad[1], cs),
                      lambda: [(kh - pad[0], kw - pad[1], (kh * k + kw) * cs) for kh in range(k) for kw in range(k)])
         _tc_launch(x, ldx, H, W, Cin, w_hi, w_lo, K, bias, y, ldy, B, OH, OW, Cout, OH, OW, (1, 1), (0, 0), stride,
-                   taps, act, stats, "conv_fwd_tc", planes, plane_stride=plane_stride, lab=lab, ch_scale=ch_scale)
+                   taps, act, stats, "conv_fwd_tc", planes, plane_stride=plane_stride, lab=lab, ch_scale=ch_scale,
+                   bn_fin=bn_fin)
         return True
-    assert lab is None and ch_scale is None, "fused LAB / scale epilogues need a tensor-core geometry"
+    assert lab is None and ch_scale is None and bn_fin is None, "fused LAB / scale / finalize epilogues need a tensor-core geometry"
     wr = wkey("wr", lambda: weight.reshape(Cout, Cin, k, k).permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous())
     if bias is None and act == 0 and _MODE != "simt" and \
             lib().dfine_stem_conv_supported(Cin, Cout, k, k, stride, pad[0], pad[1], pad[2], pad[3], c_long(ldy)):
@@ -455,6 +469,15 @@ def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None, lab=Non
     _check(lib().dfine_conv_fwd_simt(_p(x), _p(wr), _p(bias), _p(y), B, H, W, Cin, OH, OW, Cout, k, k, stride,
                                      pad[0], pad[1], c_long(ldx), c_long(ldy), act, _stream()), "conv_fwd_simt")
     return False
+
+
+_BN_FIN = os.environ.get("DFINE_BN_FIN", "1") != "0"     # train-mode BatchNorm finalize in the conv kernel's tail
+
+
+def _bn_fin_ok(geom, ldx, ldy):
+    """The layer's forward runs on tc_fwd_ts (3xFP16, activation planes in tensor memory), whose last CTA can finalize."""
+    B, H, W, Cin, OH, OW, Cout, k, stride, pad = geom
+    return _BN_FIN and _MODE == "hf3" and _TC_TS and not _conv2x2_ok(geom, ldx, ldy) and _tc_ok(Cin, Cout, k, stride, pad, ldx, ldy)
 
 
 def _prefetch_dgrad_weight(weight, geom, ldx, ldy):
@@ -684,8 +707,11 @@ class _ConvBnAct(torch.autograd.Function):
             return (y, x_in) if tap else y
         conv_out = torch.empty((B, OH, OW, Cout), device=dev, dtype=torch.float32)
         need_stats = training
-        stats = zero_pool.take(2 * Cout, dev) if need_stats else None
         depthwise = groups > 1
+        # train-mode finalize (mean / invstd / scale / shift / running statistics) in the conv kernel's last CTA: the
+        # statistics buffer carries one extra zeroed slot, the retirement ticket
+        fin = need_stats and not depthwise and _bn_fin_ok(geom, ldx, Cout)
+        stats = zero_pool.take(2 * Cout + (1 if fin else 0), dev) if need_stats else None
         if depthwise:
             assert groups == Cin == Cout and pt == pl == pb == pr, "only depthwise grouped convs are on the path"
             if ldx != Cin:
@@ -695,15 +721,23 @@ class _ConvBnAct(torch.autograd.Function):
             _check(lib().dfine_dwconv_fwd(_p(x), _p(wt), _p(conv_out), B, H, W, Cin, k, stride, pt, _stream()),
                    "dwconv_fwd")
             fused_stats = False
-        else:
+        scale = torch.empty(Cout, device=dev, dtype=torch.float32)
+        shift = torch.empty(Cout, device=dev, dtype=torch.float32)
+        mean = invstd = None
+        if fin:
+            mean = torch.empty(Cout, device=dev, dtype=torch.float32)
+            invstd = torch.empty(Cout, device=dev, dtype=torch.float32)
+            _conv_fwd(x, ldx, weight, _wcache.getter(weight), None, conv_out, Cout, geom, 0, stats,
+                      bn_fin=(stats[2 * Cout:], bn_w, bn_b, running_mean, running_var, mean, invstd, scale, shift, momentum, eps))
+            fused_stats = True
+            if ctx.needs_input_grad[0]:
+                _prefetch_dgrad_weight(weight, geom, ldx, Cout)
+        elif not depthwise:
             fused_stats = _conv_fwd(x, ldx, weight, _wcache.getter(weight), None, conv_out, Cout, geom, 0, stats)
             if ctx.needs_input_grad[0]:
                 _prefetch_dgrad_weight(weight, geom, ldx, Cout)
         if need_stats and not fused_stats:
             _check(lib().dfine_bn_stats(_p(conv_out), _p(stats), c_long(M), Cout, _stream()), "bn_stats")
-        scale = torch.empty(Cout, device=dev, dtype=torch.float32)
-        shift = torch.empty(Cout, device=dev, dtype=torch.float32)
-        mean = invstd = None
         if pre_add is not None:
             pre_add = pre_add.contiguous()
         ld_post = Cout
@@ -724,7 +758,9 @@ class _ConvBnAct(torch.autograd.Function):
             y, ldy_out = _alloc_nhwc(B, OH, OW, Cout, dev)
         # (a fused finalize+apply launch was measured SLOWER: every CTA re-derives the scale / shift table in fp64 and
         #  synchronises before its first load — 20.5 us against 12.3 + 4.8 us per layer, profiles/README.md)
-        if training:
+        if fin:
+            pass
+        elif training:
             mean = torch.empty(Cout, device=dev, dtype=torch.float32)
             invstd = torch.empty(Cout, device=dev, dtype=torch.float32)
             _check(lib().dfine_bn_finalize(_p(stats), _p(bn_w), _p(bn_b), _p(running_mean), _p(running_var), _p(mean),
