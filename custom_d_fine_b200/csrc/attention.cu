@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const float* __restrict__ 
                                                       long ldk, const float* __restrict__ v, long ldv,
                                                       const unsigned char* __restrict__ mask, float* __restrict__ o,
                                                       long ldo, float* __restrict__ lse, int S, int H, float scale) {
+    pdl_entry();
     extern __shared__ __align__(16) unsigned char raw[];
     Smem<HD>& sm = *reinterpret_cast<Smem<HD>*>(raw);
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ROWS;
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(NT) attn_bwd_dq_kernel(const float* __restrict
                                                          const float* __restrict__ dout, long ldd,
                                                          const float* __restrict__ lse, float* __restrict__ dsum,
                                                          float* __restrict__ dq, long lddq, int S, int H, float scale) {
+    pdl_entry();
     extern __shared__ __align__(16) unsigned char raw[];
     Smem<HD>& sm = *reinterpret_cast<Smem<HD>*>(raw);
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ROWS;
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(NT) attn_bwd_dkv_kernel(const float* __restric
                                                           const float* __restrict__ dsum, float* __restrict__ dk,
                                                           long lddk, float* __restrict__ dv, long lddv, int S, int H,
                                                           float scale) {
+    pdl_entry();
     extern __shared__ __align__(16) unsigned char raw[];
     Smem<HD>& sm = *reinterpret_cast<Smem<HD>*>(raw);
     const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * ROWS;
@@ -312,7 +315,7 @@ DFINE_API int dfine_attn_fwd(const float* q, long ldq, const float* k, long ldk,
     ATTN_DISPATCH(head_dim, {
         int rc = set_smem<HD, 0>((const void*)attn_fwd_kernel<HD>);
         if (rc) return rc;
-        attn_fwd_kernel<HD><<<grid, NT, sizeof(Smem<HD>), (cudaStream_t)stream>>>(q, ldq, k, ldk, v, ldv, mask, o, ldo,
+        launch_k(attn_fwd_kernel<HD>, grid, NT, sizeof(Smem<HD>), (cudaStream_t)stream, q, ldq, k, ldk, v, ldv, mask, o, ldo,
                                                                                   lse, S, H, scale);
     });
     DFINE_LAUNCH_CHECK("attn_fwd");
@@ -341,9 +344,9 @@ DFINE_API int dfine_attn_bwd(const float* q, long ldq, const float* k, long ldk,
         if (rc) return rc;
         rc = set_smem<HD, 2>((const void*)attn_bwd_dkv_kernel<HD>);
         if (rc) return rc;
-        attn_bwd_dq_kernel<HD><<<grid, NT, sizeof(Smem<HD>), (cudaStream_t)stream>>>(
+        launch_k(attn_bwd_dq_kernel<HD>, grid, NT, sizeof(Smem<HD>), (cudaStream_t)stream, 
             q, ldq, k, ldk, v, ldv, mask, o, ldo, dout, ldd, lse, dsum, dq, lddq, S, H, scale);
-        attn_bwd_dkv_kernel<HD><<<grid, NT, sizeof(Smem<HD>), (cudaStream_t)stream>>>(
+        launch_k(attn_bwd_dkv_kernel<HD>, grid, NT, sizeof(Smem<HD>), (cudaStream_t)stream, 
             q, ldq, k, ldk, v, ldv, mask, dout, ldd, lse, dsum, dk, lddk, dv, lddv, S, H, scale);
     });
     DFINE_LAUNCH_CHECK("attn_bwd");

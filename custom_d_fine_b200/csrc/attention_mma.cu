@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const float* __restrict__ q, lo
                                                  const float* __restrict__ v, long ldv,
                                                  const unsigned char* __restrict__ mask, float* __restrict__ o, long ldo,
                                                  float* __restrict__ lse, int S, int H, float scale) {
+    pdl_entry();
     extern __shared__ __align__(16) unsigned char raw[];
     FwdSmem<HD>& sm = *reinterpret_cast<FwdSmem<HD>*>(raw);
     const int b = blockIdx.z, h = blockIdx.y, warp = threadIdx.x / 32, lane = threadIdx.x % 32, g = lane / 4, t = lane % 4;
@@ -354,6 +355,7 @@ __global__ void __launch_bounds__(NT) dq_kernel(const float* __restrict__ q, lon
                                                 long ldo, const float* __restrict__ dout, long ldd,
                                                 const float* __restrict__ lse, float* __restrict__ dsum,
                                                 float* __restrict__ dq, long lddq, int S, int H, float scale) {
+    pdl_entry();
     extern __shared__ __align__(16) unsigned char raw[];
     DqSmem<HD>& sm = *reinterpret_cast<DqSmem<HD>*>(raw);
     const int b = blockIdx.z, h = blockIdx.y, warp = threadIdx.x / 32, lane = threadIdx.x % 32, g = lane / 4, t = lane % 4;
@@ -470,6 +472,7 @@ __global__ void __launch_bounds__(NT) dkv_kernel(const float* __restrict__ q, lo
                                                  const float* __restrict__ dout, long ldd, const float* __restrict__ lse,
                                                  const float* __restrict__ dsum, float* __restrict__ dk, long lddk,
                                                  float* __restrict__ dv, long lddv, int S, int H, float scale) {
+    pdl_entry();
     extern __shared__ __align__(16) unsigned char raw[];
     DkvSmem<HD>& sm = *reinterpret_cast<DkvSmem<HD>*>(raw);
     const int b = blockIdx.z, h = blockIdx.y, warp = threadIdx.x / 32, lane = threadIdx.x % 32, g = lane / 4, t = lane % 4;
@@ -570,7 +573,7 @@ int launch_fwd(const float* q, long ldq, const float* k, long ldk, const float* 
     static bool done = false;
     int rc = set_smem(fwd_kernel<HD>, (int)sizeof(FwdSmem<HD>), done);
     if (rc) return rc;
-    fwd_kernel<HD><<<dim3(ceil_div(S, Cfg<HD>::BQ), H, B), NT, sizeof(FwdSmem<HD>), st>>>(q, ldq, k, ldk, v, ldv, mask, o, ldo, lse,
+    launch_k(fwd_kernel<HD>, dim3(ceil_div(S, Cfg<HD>::BQ), H, B), NT, sizeof(FwdSmem<HD>), st, q, ldq, k, ldk, v, ldv, mask, o, ldo, lse,
                                                                                 S, H, scale);
     return 0;
 }
@@ -585,9 +588,9 @@ int launch_bwd(const float* q, long ldq, const float* k, long ldk, const float* 
     rc = set_smem(dkv_kernel<HD>, (int)sizeof(DkvSmem<HD>), d2);
     if (rc) return rc;
     const dim3 grid(ceil_div(S, Cfg<HD>::BQ), H, B);
-    dq_kernel<HD><<<grid, NT, sizeof(DqSmem<HD>), st>>>(q, ldq, k, ldk, v, ldv, mask, o, ldo, dout, ldd, lse, dsum, dq, lddq,
+    launch_k(dq_kernel<HD>, grid, NT, sizeof(DqSmem<HD>), st, q, ldq, k, ldk, v, ldv, mask, o, ldo, dout, ldd, lse, dsum, dq, lddq,
                                                        S, H, scale);
-    dkv_kernel<HD><<<grid, NT, sizeof(DkvSmem<HD>), st>>>(q, ldq, k, ldk, v, ldv, mask, dout, ldd, lse, dsum, dk, lddk, dv,
+    launch_k(dkv_kernel<HD>, grid, NT, sizeof(DkvSmem<HD>), st, q, ldq, k, ldk, v, ldv, mask, dout, ldd, lse, dsum, dk, lddk, dv,
                                                          lddv, S, H, scale);
     return 0;
 }

@@ -46,6 +46,38 @@ void dfine_set_error(const char* fmt, ...);
 
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch ---------------------------------------------------------------------------------
+// A train step is ~2000 short kernels in one stream order; between two dependent kernels the GPU idles for the launch
+// latency of the second one.  Every kernel of the library is launched with the programmatic-stream-serialization
+// attribute (also recorded by CUDA-graph capture as a programmatic edge) and starts with pdl_entry(): its CTAs may
+// become resident while the previous kernel drains, wait for that kernel's completion + memory flush
+// (griddepcontrol.wait) BEFORE touching global memory, then allow their own successor to be scheduled.  A kernel
+// launched without the attribute (or after a non-kernel stream item) executes both instructions as no-ops.
+// DFINE_PDL=0 launches without the attribute (plain stream serialization).
+__device__ __forceinline__ void pdl_entry() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+static inline bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("DFINE_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                   Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_GELU = 3 };
 
 __device__ __forceinline__ float act_fwd(float z, int act) {

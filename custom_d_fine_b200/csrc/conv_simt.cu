@@ -40,6 +40,7 @@ template <bool DGRAD>
 __global__ void __launch_bounds__(NT) conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ wr,
                                                        const float* __restrict__ bias, float* __restrict__ dst,
                                                        ConvGeom g, int act) {
+    pdl_entry();
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
     const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const float* __restrict__
 // ---- weight gradient: reduction over pixels, split across blockIdx.z ------------------------------
 __global__ void __launch_bounds__(NT) conv_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                         float* __restrict__ dwr, ConvGeom g, long pix_per_split) {
+    pdl_entry();
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
     const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
@@ -196,6 +198,7 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(const float* __restrict_
 // out[c] += sum_rows x[row*ld + c]   (bias gradients)
 __global__ void __launch_bounds__(NT) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long M,
                                                     int C, long ld, long rows_per_cta) {
+    pdl_entry();
     const long r0 = (long)blockIdx.x * rows_per_cta;
     const long r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
     for (int c = threadIdx.x; c < C; c += NT) {
@@ -230,7 +233,7 @@ DFINE_API int dfine_conv_fwd_simt(const float* x, const float* wr, const float* 
     const long M = (long)B * OH * OW;
     if (M == 0) return 0;
     dim3 grid(ceil_div(M, BM), ceil_div(Cout, BN));
-    conv_gemm_kernel<false><<<grid, NT, 0, (cudaStream_t)stream>>>(x, wr, bias, y, g, act);
+    launch_k(conv_gemm_kernel<false>, grid, NT, 0, (cudaStream_t)stream, x, wr, bias, y, g, act);
     DFINE_LAUNCH_CHECK("conv_fwd_simt");
     return 0;
 }
@@ -242,7 +245,7 @@ DFINE_API int dfine_conv_dgrad_simt(const float* dy, const float* wr, float* dx,
     const long M = (long)B * H * W;
     if (M == 0) return 0;
     dim3 grid(ceil_div(M, BM), ceil_div(Cin, BN));
-    conv_gemm_kernel<true><<<grid, NT, 0, (cudaStream_t)stream>>>(dy, wr, nullptr, dx, g, 0);
+    launch_k(conv_gemm_kernel<true>, grid, NT, 0, (cudaStream_t)stream, dy, wr, nullptr, dx, g, 0);
     DFINE_LAUNCH_CHECK("conv_dgrad_simt");
     return 0;
 }
@@ -260,7 +263,7 @@ DFINE_API int dfine_conv_wgrad_simt(const float* dy, const float* x, float* dwr,
     pps = (pps + BK - 1) / BK * BK;
     if (pps < 8 * BK) pps = 8 * BK;
     dim3 grid(gx, gy, ceil_div(P, pps));
-    conv_wgrad_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(dy, x, dwr, g, pps);
+    launch_k(conv_wgrad_kernel, grid, NT, 0, (cudaStream_t)stream, dy, x, dwr, g, pps);
     DFINE_LAUNCH_CHECK("conv_wgrad_simt");
     return 0;
 }
@@ -270,7 +273,7 @@ DFINE_API int dfine_colsum(const float* x, float* out, long M, int C, long ld, v
     if (M == 0 || C == 0) return 0;
     long rpc = (M + 148L * 2 - 1) / (148L * 2);
     if (rpc < 32) rpc = 32;
-    colsum_kernel<<<ceil_div(M, rpc), NT, 0, (cudaStream_t)stream>>>(x, out, M, C, ld, rpc);
+    launch_k(colsum_kernel, ceil_div(M, rpc), NT, 0, (cudaStream_t)stream, x, out, M, C, ld, rpc);
     DFINE_LAUNCH_CHECK("colsum");
     return 0;
 }

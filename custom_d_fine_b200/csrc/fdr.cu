@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(256) fdr_head_fwd_kernel(const float* __restri
                                                            const float* __restrict__ project,
                                                            const float* __restrict__ reg_scale, float* __restrict__ box,
                                                            float* __restrict__ stat, long rows, int NB, int k) {
+    pdl_entry();
     const long row = (long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     if (row >= rows) return;
     const int lane = threadIdx.x % 32, e = lane / 8, j = lane % 8;
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(256) fdr_head_bwd_kernel(const float* __restri
                                                            const float* __restrict__ reg_scale,
                                                            const float* __restrict__ dbox, const float* __restrict__ dstat,
                                                            float* __restrict__ dcorners, long rows, int NB, int k) {
+    pdl_entry();
     const long row = (long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     if (row >= rows) return;
     const int lane = threadIdx.x % 32, e = lane / 8, j = lane % 8;
@@ -175,7 +177,7 @@ DFINE_API int dfine_fdr_head_fwd(const float* corners, const float* ref, const f
     DFINE_REQUIRE(NB >= 1 && NB <= 8 * MAXB && k >= 0 && k <= MAXK && k <= NB, "fdr_head_fwd: NB=%d k=%d unsupported", NB, k);
     DFINE_REQUIRE(!box || (((uintptr_t)ref % 16) == 0 && ((uintptr_t)box % 16) == 0), "fdr_head_fwd: alignment");
     if (rows == 0) return 0;
-    fdr_head_fwd_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(corners, ref, project, reg_scale, box,
+    launch_k(fdr_head_fwd_kernel, ceil_div(rows, 8), 256, 0, (cudaStream_t)stream, corners, ref, project, reg_scale, box,
                                                                              stat, rows, NB, k);
     DFINE_LAUNCH_CHECK("fdr_head_fwd");
     return 0;
@@ -188,7 +190,7 @@ DFINE_API int dfine_fdr_head_bwd(const float* corners, const float* ref, const f
     DFINE_REQUIRE(NB >= 1 && NB <= 8 * MAXB && k >= 0 && k <= MAXK && k <= NB, "fdr_head_bwd: NB=%d k=%d unsupported", NB, k);
     DFINE_REQUIRE(!dbox || (((uintptr_t)ref % 16) == 0 && ((uintptr_t)dbox % 16) == 0), "fdr_head_bwd: alignment");
     if (rows == 0) return 0;
-    fdr_head_bwd_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(corners, ref, project, reg_scale, dbox,
+    launch_k(fdr_head_bwd_kernel, ceil_div(rows, 8), 256, 0, (cudaStream_t)stream, corners, ref, project, reg_scale, dbox,
                                                                              dstat, dcorners, rows, NB, k);
     DFINE_LAUNCH_CHECK("fdr_head_bwd");
     return 0;

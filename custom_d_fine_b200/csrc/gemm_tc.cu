@@ -268,6 +268,17 @@ struct FwdParams {
     float* fin_shift;
     long fin_M;               // pixels the statistics were taken over
     float fin_momentum, fin_eps;
+    // ... and the BatchNorm apply pass (fin_y != null): every CTA waits for the finalize (a release / acquire flag next to
+    // the ticket; the grid is at most one CTA per SM, so all CTAs are resident), then normalises the tiles IT wrote,
+    // y = lab_s * act(conv * scale[c] + shift[c]) + lab_b (+ post_add), re-reading its own accumulators from L2:
+    // bn_apply_kernel's arithmetic without its launch.  conv output `y` stays the saved pre-normalisation tensor.
+    float* fin_y;             // normalised output, pixel stride fin_ldy
+    long fin_ldy;
+    const float* fin_post;    // optional residual added last (pixel stride fin_ldpost)
+    long fin_ldpost;
+    const float* fin_lab_s;   // optional LAB scalars (device)
+    const float* fin_lab_b;
+    int fin_act;
 };
 
 // X3 = 0: one kind::tf32 MMA per k-step (operands truncated to tf32 by the tensor core).
@@ -323,6 +334,7 @@ __global__ void __launch_bounds__(fwd_threads(X3)) tc_fwd_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    pdl_entry();      // barriers / tensor memory / descriptor prefetch above overlap the previous kernel's tail
 
     if (warp == 0) {
         if (lane == 0) {
@@ -549,6 +561,7 @@ __global__ void __launch_bounds__(fwd_threads(X3), 1) tc_fwd_persist(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    pdl_entry();      // barriers / tensor memory / descriptor prefetch above overlap the previous kernel's tail
 
     if (warp == 0) {
         // whole warp, warp-uniform values, one elected lane issues (see elect_one)
@@ -1027,6 +1040,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
     cluster_sync();          // both CTAs' barriers are initialised before any remote arrival / peer-signalling TMA load
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    pdl_entry();      // barriers / tensor memory / descriptor prefetch above overlap the previous kernel's tail
 
     if (warp == 0) {
         // whole warp, warp-uniform values, one elected lane issues (see elect_one)
@@ -1244,6 +1258,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    pdl_entry();      // barriers / tensor memory / descriptor prefetch above overlap the previous kernel's tail
 
     if (warp == 0) {
         // TMA producer: the whole warp walks (tile, tap, channel block) with warp-uniform values, one elected lane issues
@@ -1499,6 +1514,59 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
                 bn_finalize_channel(__ldcg(stats + c), __ldcg(stats + p.N + c), c, p.fin_w, p.fin_b, p.fin_rmean, p.fin_rvar,
                                     p.fin_mean, p.fin_invstd, p.fin_scale, p.fin_shift, p.fin_M, p.fin_momentum, p.fin_eps);
         }
+        if (p.fin_y) {
+            unsigned int* flag = p.fin_counter + 1;
+            if (sm.last_cta) {
+                __threadfence();
+                __syncthreads();
+                if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory");
+            } else {
+                if (threadIdx.x == 0) {
+                    // bounded: the CTAs of this grid are co-resident by construction (<= one per SM); if that ever fails the
+                    // launch ends in a trap (a loud error) instead of a hang
+                    unsigned int v = 0, polls = 0;
+                    while (true) {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                        if (v) break;
+                        if (++polls > (1u << 23)) __trap();
+                        __nanosleep(64);
+                    }
+                }
+                __syncthreads();
+            }
+            // flat, grid-strided pass over the whole [M, N] tensor (every CTA's tiles are visible: each fenced before its
+            // ticket), eight 16-byte loads in flight per thread
+            const int VC = p.N / 4;
+            const long n4 = p.fin_M * VC, stride = (long)gridDim.x * blockDim.x;
+            const float ls = p.fin_lab_s ? __ldg(p.fin_lab_s) : 1.f, lb = p.fin_lab_s ? __ldg(p.fin_lab_b) : 0.f;
+            constexpr int U = 8;
+            for (long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += U * stride) {
+                float4 v[U];
+                long row[U];
+                int col[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const long i = i0 + u * stride;
+                    row[u] = i / VC;
+                    col[u] = (int)(i - row[u] * VC) * 4;
+                    if (i < n4) v[u] = __ldcg(reinterpret_cast<const float4*>(y + row[u] * p.ldy + col[u]));
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (i0 + u * stride >= n4) break;
+                    const float4 sc = __ldcg(reinterpret_cast<const float4*>(p.fin_scale + col[u]));
+                    const float4 sh = __ldcg(reinterpret_cast<const float4*>(p.fin_shift + col[u]));
+                    float4 o = make_float4(act_fwd(fmaf(v[u].x, sc.x, sh.x), p.fin_act), act_fwd(fmaf(v[u].y, sc.y, sh.y), p.fin_act),
+                                           act_fwd(fmaf(v[u].z, sc.z, sh.z), p.fin_act), act_fwd(fmaf(v[u].w, sc.w, sh.w), p.fin_act));
+                    if (p.fin_lab_s) { o.x = ls * o.x + lb; o.y = ls * o.y + lb; o.z = ls * o.z + lb; o.w = ls * o.w + lb; }
+                    if (p.fin_post) {
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(p.fin_post + row[u] * p.fin_ldpost + col[u]));
+                        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+                    }
+                    *reinterpret_cast<float4*>(p.fin_y + row[u] * p.fin_ldy + col[u]) = o;
+                }
+            }
+        }
     }
 }
 
@@ -1594,6 +1662,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR16_THREADS, 1)
     cluster_sync();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    pdl_entry();      // barriers / tensor memory / descriptor prefetch above overlap the previous kernel's tail
 
     if (warp == 0) {
         if (lane == 0) {
@@ -1890,6 +1959,7 @@ __global__ void __launch_bounds__(WG_THREADS) tc_wgrad_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    pdl_entry();      // barriers / tensor memory / descriptor prefetch above overlap the previous kernel's tail
 
     if (warp == 0) {
         // whole warp, warp-uniform values, one elected lane issues (see elect_one); the (image, row, 32-pixel chunk) of a
@@ -2103,7 +2173,7 @@ int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& 
     const int smem = (int)sizeof(FwdSmem<BN, X3, STAGES>) + 1024;
     DFINE_SET_SMEM_ONCE((tc_fwd_kernel<BN, X3, STAGES>), smem, "tc_fwd");
     dim3 grid(B * p.tiles_w * p.tiles_h, ceil_div(p.N, BN));
-    tc_fwd_kernel<BN, X3, STAGES><<<grid, fwd_threads(X3), smem, st>>>(mx, mw, mwlo, y, bias, stats, p);
+    launch_k(tc_fwd_kernel<BN, X3, STAGES>, grid, fwd_threads(X3), smem, st, mx, mw, mwlo, y, bias, stats, p);
     return 0;
 }
 
@@ -2126,7 +2196,7 @@ int launch_persist(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorM
     ts.n_tiles = ceil_div(p.N, BN);
     ts.total = B * p.tiles_w * p.tiles_h * ts.n_tiles;
     const int grid = ts.total < sm_count() ? ts.total : sm_count();
-    tc_fwd_persist<BN, X3, STAGES><<<grid, fwd_threads(X3), smem, st>>>(mx, mw, mwlo, y, bias, stats, p, ts);
+    launch_k(tc_fwd_persist<BN, X3, STAGES>, grid, fwd_threads(X3), smem, st, mx, mw, mwlo, y, bias, stats, p, ts);
     return 0;
 }
 
@@ -2162,7 +2232,7 @@ int launch_pair(const CUtensorMap& mx, const CUtensorMap& mw, float* y, const fl
     }();
     int pairs = ts.total < max_pairs ? ts.total : max_pairs;
     if (pairs < 1) pairs = 1;
-    tc_pair_kernel<BN, STAGES><<<2 * pairs, PAIR_THREADS, smem, st>>>(mx, mw, y, bias, stats, p, ts);
+    launch_k(tc_pair_kernel<BN, STAGES>, 2 * pairs, PAIR_THREADS, smem, st, mx, mw, y, bias, stats, p, ts);
     return 0;
 }
 
@@ -2177,7 +2247,7 @@ int launch_ts(const CUtensorMap& mx, const CUtensorMap& mw, float* y, const floa
     ts.total = B * p.tiles_w * p.tiles_h * ts.n_tiles;
     int grid = ts.total < sm_count() ? ts.total : sm_count();
     if (grid >= ts.n_tiles) grid -= grid % ts.n_tiles;      // every CTA then stays on ONE N tile (CTA-local BN statistics)
-    tc_fwd_ts<BN, STAGES><<<grid, TS_THREADS, smem, st>>>(mx, mw, y, bias, stats, p, ts);
+    launch_k(tc_fwd_ts<BN, STAGES>, grid, TS_THREADS, smem, st, mx, mw, y, bias, stats, p, ts);
     return 0;
 }
 
@@ -2205,7 +2275,7 @@ int launch_pair16(const CUtensorMap& mx, const CUtensorMap& mw, float* y, const 
     }();
     int pairs = ts.total < max_pairs ? ts.total : max_pairs;
     if (pairs < 1) pairs = 1;
-    tc_pair16_kernel<BN, STAGES><<<2 * pairs, PAIR16_THREADS, smem, st>>>(mx, mw, y, bias, stats, p, ts);
+    launch_k(tc_pair16_kernel<BN, STAGES>, 2 * pairs, PAIR16_THREADS, smem, st, mx, mw, y, bias, stats, p, ts);
     return 0;
 }
 
@@ -2221,7 +2291,7 @@ int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, float* dwr, Wgra
     if (sps < 8) sps = 8;
     p.steps_per_split = sps;
     dim3 grid(gx, gy, ceil_div(p.steps_total, sps));
-    tc_wgrad_kernel<BN><<<grid, WG_THREADS, smem, st>>>(mdy, mx, dwr, p);
+    launch_k(tc_wgrad_kernel<BN>, grid, WG_THREADS, smem, st, mdy, mx, dwr, p);
     return 0;
 }
 
@@ -2253,6 +2323,12 @@ struct BnFinArgs {      // the fused train-mode BatchNorm finalize (FwdParams::f
     const float *w, *b;
     float *rmean, *rvar, *mean, *invstd, *scale, *shift;
     float momentum, eps;
+    float* y_out;             // optional fused apply pass (FwdParams::fin_y ...)
+    long ld_out;
+    const float* post;
+    long ld_post;
+    const float *lab_s, *lab_b;
+    int act;
 };
 int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* w_bf16, const float* bias, float* y,
                  double* stats, int B, int H, int W, int Cin, long ldx, int OH, int OW, int Cout, long ldy,
@@ -2295,6 +2371,15 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
         p.fin_counter = fin->counter; p.fin_w = fin->w; p.fin_b = fin->b; p.fin_rmean = fin->rmean; p.fin_rvar = fin->rvar;
         p.fin_mean = fin->mean; p.fin_invstd = fin->invstd; p.fin_scale = fin->scale; p.fin_shift = fin->shift;
         p.fin_M = (long)B * OH * OW; p.fin_momentum = fin->momentum; p.fin_eps = fin->eps;
+        p.fin_y = fin->y_out; p.fin_ldy = fin->ld_out; p.fin_post = fin->post; p.fin_ldpost = fin->ld_post;
+        p.fin_lab_s = fin->lab_s; p.fin_lab_b = fin->lab_b; p.fin_act = fin->act;
+        if (fin->y_out) {
+            DFINE_REQUIRE(fin->ld_out % 4 == 0 && fin->ld_out >= Cout && ((uintptr_t)fin->y_out % 16) == 0 &&
+                              (!fin->post || (fin->ld_post % 4 == 0 && fin->ld_post >= Cout && ((uintptr_t)fin->post % 16) == 0)) &&
+                              (fin->lab_s == nullptr) == (fin->lab_b == nullptr) && YH == OH && YW == OW && osy == 1 && osx == 1 &&
+                              ooy == 0 && oox == 0,
+                          "conv_tc: fused BatchNorm apply geometry (ld_out=%ld ld_post=%ld)", fin->ld_out, fin->ld_post);
+        }
     }
     const int WR = w_rows > 0 ? w_rows : Cout;        // rows of the weight matrix the maps cover (stacked per-image weights)
     p.in_stride = in_stride; p.Cin = Cin;
@@ -2516,14 +2601,21 @@ DFINE_API int dfine_conv_tc_f16x3(const float* x, const void* w_planes, const fl
 // double [2*Cout], zeroed by the caller) the kernel's last CTA runs dfine_bn_finalize's arithmetic in its tail — mean /
 // invstd / scale / shift [Cout] and the running-statistics update (hgnetv2.py:65, torch BatchNorm2d momentum rule) —
 // so the separate finalize launch disappears.  `counter`: one zeroed unsigned int (the retirement ticket).
+// y_out != null: the kernel also runs dfine_bn_apply's pass on the tiles each CTA wrote (after a grid-wide wait for the
+// finalize; `counter` then points at TWO zeroed unsigned ints, ticket and flag):
+// y_out = lab_scale * act(y * scale[c] + shift[c]) + lab_bias (+ post_add), pixel strides ld_out / ld_post; `y` keeps the
+// raw conv output the backward pass needs.  lab_scale / lab_bias: device scalars or null.
 DFINE_API int dfine_conv_tc_f16x3_bn(const float* x, const void* w_planes, float* y, double* stats, unsigned int* counter,
                                      const float* bn_weight, const float* bn_bias, float* running_mean,
                                      float* running_var, float* mean, float* invstd, float* scale, float* shift,
                                      float momentum, float eps, int B, int H, int W, int Cin, long ldx, int OH, int OW,
                                      int Cout, long ldy, int in_stride, int n_taps, const int* taps, long ldw,
-                                     float out_scale, long plane_stride, void* stream) {
+                                     float out_scale, long plane_stride, float* y_out, long ld_out,
+                                     const float* post_add, long ld_post, const float* lab_scale, const float* lab_bias,
+                                     int act, void* stream) {
     DFINE_REQUIRE(w_planes != nullptr, "conv_tc_f16x3_bn: null weight planes");
-    BnFinArgs fin{counter, bn_weight, bn_bias, running_mean, running_var, mean, invstd, scale, shift, momentum, eps};
+    BnFinArgs fin{counter, bn_weight, bn_bias, running_mean, running_var, mean, invstd, scale, shift, momentum, eps,
+                  y_out, ld_out, post_add, ld_post, lab_scale, lab_bias, act};
     return conv_tc_impl(x, nullptr, nullptr, w_planes, nullptr, y, stats, B, H, W, Cin, ldx, OH, OW, Cout, ldy, OH, OW, 1, 1,
                         0, 0, in_stride, n_taps, taps, ldw, 0, stream, 0, nullptr, 0, 1, out_scale, plane_stride, 0, 1.f,
                         0.f, 0, 0, 0, nullptr, &fin);
@@ -2548,6 +2640,7 @@ DFINE_API int dfine_conv_tc_hybrid(const float* x, const float* w_hi, const void
 namespace {
 __global__ void bf16_split_kernel(const float* __restrict__ w, long ldw, unsigned short* __restrict__ planes,
                                   long rows, int taps, int Cin, int Cin_p, int mode) {
+    pdl_entry();
     const long ldp = (long)taps * Cin_p, n = rows * ldp;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         const long r = i / ldp;
@@ -2566,6 +2659,7 @@ __global__ void bf16_split_kernel(const float* __restrict__ w, long ldw, unsigne
 namespace {
 __global__ void f16_split_kernel(const float* __restrict__ w, long ldw, unsigned short* __restrict__ planes, long rows,
                                  int taps, int Cin, int Cin_p, float scale) {
+    pdl_entry();
     const long ldp = (long)taps * Cin_p, n = rows * ldp;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         const long r = i / ldp;
@@ -2592,7 +2686,7 @@ DFINE_API int dfine_f16_split(const float* w, long ldw, void* planes, long rows,
     if (n == 0) return 0;
     long g = (n + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
-    f16_split_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w, ldw, (unsigned short*)planes, rows, taps, Cin, Cin_p, scale);
+    launch_k(f16_split_kernel, (int)g, 256, 0, (cudaStream_t)stream, w, ldw, (unsigned short*)planes, rows, taps, Cin, Cin_p, scale);
     DFINE_LAUNCH_CHECK("f16_split");
     return 0;
 }
@@ -2606,7 +2700,7 @@ DFINE_API int dfine_bf16_split(const float* w, long ldw, void* planes, long rows
     if (n == 0) return 0;
     long g = (n + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
-    bf16_split_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w, ldw, (unsigned short*)planes, rows, taps, Cin, Cin_p,
+    launch_k(bf16_split_kernel, (int)g, 256, 0, (cudaStream_t)stream, w, ldw, (unsigned short*)planes, rows, taps, Cin, Cin_p,
                                                                mode);
     DFINE_LAUNCH_CHECK("bf16_split");
     return 0;
@@ -2616,6 +2710,7 @@ DFINE_API int dfine_bf16_split(const float* w, long ldw, void* planes, long rows
 // weight version over a flat arena.
 namespace {
 __global__ void tf32_split_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, long n) {
+    pdl_entry();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         const float v = w[i], h = tf32_rna(v);
         hi[i] = h;
@@ -2627,7 +2722,7 @@ DFINE_API int dfine_tf32_split(const float* w, float* hi, float* lo, long n, voi
     if (n == 0) return 0;
     long g = (n + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
-    tf32_split_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w, hi, lo, n);
+    launch_k(tf32_split_kernel, (int)g, 256, 0, (cudaStream_t)stream, w, hi, lo, n);
     DFINE_LAUNCH_CHECK("tf32_split");
     return 0;
 }

@@ -29,6 +29,7 @@ __device__ __forceinline__ void src_index(int d, float scale, int in_size, int* 
 template <typename T>
 __global__ void resize_kernel(const T* __restrict__ src, float* __restrict__ dst, int B, int Hs, int Ws, int H, int W, int C,
                               float mul, int swap_rb) {
+    pdl_entry();
     const long n = (long)B * H * W;
     const float sy = (float)Hs / (float)H, sx = (float)Ws / (float)W;
     const bool same = Hs == H && Ws == W;
@@ -56,6 +57,7 @@ __global__ void resize_kernel(const T* __restrict__ src, float* __restrict__ dst
 // float NHWC, C % 4 == 0: one thread = one destination pixel x 4 channels (coalesced float4 accesses)
 __global__ void __launch_bounds__(256) resize_f32x4_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int Hs,
                                                            int Ws, int H, int W, int C) {
+    pdl_entry();
     const int c4 = C / 4;
     const long n = (long)B * H * W * c4;
     const float sy = (float)Hs / (float)H, sx = (float)Ws / (float)W;
@@ -86,6 +88,7 @@ __global__ void __launch_bounds__(256) resize_f32x4_kernel(const float* __restri
 __global__ void postprocess_kernel(const float* __restrict__ logits, const float* __restrict__ boxes, const long* __restrict__ idx,
                                    long* __restrict__ labels, float* __restrict__ out_boxes, float* __restrict__ scores,
                                    long* __restrict__ qidx, int B, int Q, int C, int K, float height, float width, int to_round) {
+    pdl_entry();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * K) return;
     const int b = i / K;
@@ -120,7 +123,7 @@ DFINE_API int dfine_preprocess_u8(const void* src, float* dst, int B, int Hs, in
                                   int swap_rb, void* stream) {
     DFINE_REQUIRE(B >= 0 && Hs > 0 && Ws > 0 && H > 0 && W > 0 && C > 0 && C <= 4, "preprocess_u8: bad dims");
     if (B == 0) return 0;
-    resize_kernel<unsigned char><<<resize_grid((long)B * H * W), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(resize_kernel<unsigned char>, resize_grid((long)B * H * W), 256, 0, (cudaStream_t)stream, 
         (const unsigned char*)src, dst, B, Hs, Ws, H, W, C, mul, swap_rb);
     DFINE_LAUNCH_CHECK("preprocess_u8");
     return 0;
@@ -130,9 +133,9 @@ DFINE_API int dfine_resize_bilinear_f32(const float* src, float* dst, int B, int
     DFINE_REQUIRE(B >= 0 && Hs > 0 && Ws > 0 && H > 0 && W > 0 && C > 0, "resize_bilinear_f32: bad dims");
     if (B == 0) return 0;
     if (C % 4 == 0 && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0)
-        resize_f32x4_kernel<<<resize_grid((long)B * H * W * (C / 4)), 256, 0, (cudaStream_t)stream>>>(src, dst, B, Hs, Ws, H, W, C);
+        launch_k(resize_f32x4_kernel, resize_grid((long)B * H * W * (C / 4)), 256, 0, (cudaStream_t)stream, src, dst, B, Hs, Ws, H, W, C);
     else
-        resize_kernel<float><<<resize_grid((long)B * H * W), 256, 0, (cudaStream_t)stream>>>(src, dst, B, Hs, Ws, H, W, C, 1.f, 0);
+        launch_k(resize_kernel<float>, resize_grid((long)B * H * W), 256, 0, (cudaStream_t)stream, src, dst, B, Hs, Ws, H, W, C, 1.f, 0);
     DFINE_LAUNCH_CHECK("resize_bilinear_f32");
     return 0;
 }
@@ -145,7 +148,7 @@ DFINE_API int dfine_postprocess(const float* logits, const float* boxes, const l
                                 int to_round, void* stream) {
     DFINE_REQUIRE(B >= 0 && Q > 0 && C > 0 && K > 0 && ((uintptr_t)out_boxes % 16) == 0, "postprocess: bad dims / alignment");
     if (B == 0) return 0;
-    postprocess_kernel<<<ceil_div((long)B * K, 128), 128, 0, (cudaStream_t)stream>>>(logits, boxes, idx, labels, out_boxes,
+    launch_k(postprocess_kernel, ceil_div((long)B * K, 128), 128, 0, (cudaStream_t)stream, logits, boxes, idx, labels, out_boxes,
                                                                                      scores, qidx, B, Q, C, K, height, width,
                                                                                      to_round);
     DFINE_LAUNCH_CHECK("postprocess");

@@ -58,6 +58,7 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 
 // ---------------------------------------------------------------------------------------------- maps
 __global__ void loss_maps_kernel(LossDesc d) {
+    pdl_entry();
     const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= d.ncols) return;
     int map, b, q, t;
@@ -73,6 +74,7 @@ struct VflOut { float* logits; float* pre; float* enc; const float* gout; };
 
 template <bool BWD>
 __global__ void __launch_bounds__(256) loss_vfl_kernel(LossDesc d, double* acc, VflOut o) {
+    pdl_entry();
     __shared__ double sh[8];
     const int HA = d.L + 2;
     const int g = blockIdx.y < HA ? 0 : 1, h = blockIdx.y < HA ? blockIdx.y : blockIdx.y - HA;
@@ -122,6 +124,7 @@ struct BoxOut { float* boxes; float* pre; float* enc; const float* gout_l1; cons
 
 template <bool BWD>
 __global__ void __launch_bounds__(128) loss_box_kernel(LossDesc d, double* acc, BoxOut o) {
+    pdl_entry();
     __shared__ double sh[4];
     const int HA = d.L + 2;
     const int g = blockIdx.y < HA ? 0 : 1, h = blockIdx.y < HA ? blockIdx.y : blockIdx.y - HA;
@@ -161,6 +164,7 @@ __global__ void __launch_bounds__(128) loss_box_kernel(LossDesc d, double* acc, 
 template <bool BWD>
 __global__ void __launch_bounds__(128) loss_local_kernel(LossDesc d, double* acc, int* notsame, float* dcorners,
                                                          const float* coef, const float* gout_fgl, const float* gout_ddf) {
+    pdl_entry();
     __shared__ double sh[4];
     __shared__ int sh_ns;
     const int l = blockIdx.y, g = blockIdx.z;
@@ -208,6 +212,7 @@ __global__ void __launch_bounds__(128) loss_local_kernel(LossDesc d, double* acc
 }
 
 __global__ void loss_finalize_kernel(LossDesc d, const double* acc, const int* notsame, float* out) {
+    pdl_entry();
     if (blockIdx.x == 0 && threadIdx.x == 0) finalize(d, acc, notsame, out);
 }
 
@@ -255,7 +260,7 @@ DFINE_API int dfine_loss_prepare(const dfine_loss_desc* desc, void* workspace, v
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(workspace, 0, w.zero_bytes, st);
     cudaMemsetAsync(w.maps, 0xFF, w.maps_bytes, st);
-    if (d.ncols > 0) loss_maps_kernel<<<ceil_div(d.ncols, 256), 256, 0, st>>>(d);
+    if (d.ncols > 0) launch_k(loss_maps_kernel, ceil_div(d.ncols, 256), 256, 0, st, d);
     DFINE_LAUNCH_CHECK("loss_prepare");
     return 0;
 }
@@ -267,7 +272,7 @@ DFINE_API int dfine_loss_vfl_fwd(const dfine_loss_desc* desc, void* workspace, v
     const LossDesc d = with_ws(desc, workspace, &w);
     const int nq = d.Q > d.n_dn ? d.Q : d.n_dn;
     dim3 grid(ceil_div((long)d.B * nq, 8), heads_total(d));
-    loss_vfl_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(d, w.acc, VflOut{nullptr, nullptr, nullptr, nullptr});
+    launch_k(loss_vfl_kernel<false>, grid, 256, 0, (cudaStream_t)stream, d, w.acc, VflOut{nullptr, nullptr, nullptr, nullptr});
     DFINE_LAUNCH_CHECK("loss_vfl_fwd");
     return 0;
 }
@@ -278,7 +283,7 @@ DFINE_API int dfine_loss_box_fwd(const dfine_loss_desc* desc, void* workspace, v
     const long n = d.go_cap > d.n_dn_entries ? d.go_cap : d.n_dn_entries;
     if (n == 0) return 0;
     dim3 grid(ceil_div(n, 128), heads_total(d));
-    loss_box_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(d, w.acc, BoxOut{nullptr, nullptr, nullptr, nullptr, nullptr});
+    launch_k(loss_box_kernel<false>, grid, 128, 0, (cudaStream_t)stream, d, w.acc, BoxOut{nullptr, nullptr, nullptr, nullptr, nullptr});
     DFINE_LAUNCH_CHECK("loss_box_fwd");
     return 0;
 }
@@ -288,7 +293,7 @@ DFINE_API int dfine_loss_fgl_ddf_fwd(const dfine_loss_desc* desc, void* workspac
     const LossDesc d = with_ws(desc, workspace, &w);
     const int nq = d.Q > d.n_dn ? d.Q : d.n_dn;
     dim3 grid(ceil_div((long)d.B * nq * 4, 128), d.L, d.n_dn > 0 ? 2 : 1);
-    loss_local_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(d, w.acc, w.notsame, nullptr, nullptr, nullptr, nullptr);
+    launch_k(loss_local_kernel<false>, grid, 128, 0, (cudaStream_t)stream, d, w.acc, w.notsame, nullptr, nullptr, nullptr, nullptr);
     DFINE_LAUNCH_CHECK("loss_fgl_ddf_fwd");
     return 0;
 }
@@ -297,7 +302,7 @@ DFINE_API int dfine_loss_finalize(const dfine_loss_desc* desc, void* workspace, 
     if (int rc = check_desc(desc, workspace, "loss_finalize")) return rc;
     Ws w;
     const LossDesc d = with_ws(desc, workspace, &w);
-    loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d, w.acc, w.notsame, out);
+    launch_k(loss_finalize_kernel, 1, 32, 0, (cudaStream_t)stream, d, w.acc, w.notsame, out);
     DFINE_LAUNCH_CHECK("loss_finalize");
     return 0;
 }
@@ -312,7 +317,7 @@ DFINE_API int dfine_loss_vfl_bwd(const dfine_loss_desc* desc, void* workspace, c
     const LossDesc d = with_ws(desc, workspace, &w);
     const int nq = d.Q > d.n_dn ? d.Q : d.n_dn;
     dim3 grid(ceil_div((long)d.B * nq, 8), heads_total(d));
-    loss_vfl_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(d, w.acc, VflOut{dlogits, dpre_logits, denc_logits, gout});
+    launch_k(loss_vfl_kernel<true>, grid, 256, 0, (cudaStream_t)stream, d, w.acc, VflOut{dlogits, dpre_logits, denc_logits, gout});
     DFINE_LAUNCH_CHECK("loss_vfl_bwd");
     return 0;
 }
@@ -327,7 +332,7 @@ DFINE_API int dfine_loss_box_bwd(const dfine_loss_desc* desc, void* workspace, c
     if (n == 0) return 0;
     const int H = d.L + 2;
     dim3 grid(ceil_div(n, 128), heads_total(d));
-    loss_box_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(
+    launch_k(loss_box_kernel<true>, grid, 128, 0, (cudaStream_t)stream, 
         d, w.acc, BoxOut{dboxes, dpre_boxes, denc_boxes, gout + 2 * H, gout + 4 * H});
     DFINE_LAUNCH_CHECK("loss_box_bwd");
     return 0;
@@ -340,7 +345,7 @@ DFINE_API int dfine_loss_fgl_ddf_bwd(const dfine_loss_desc* desc, void* workspac
     const int nq = d.Q > d.n_dn ? d.Q : d.n_dn;
     const int H = d.L + 2;
     dim3 grid(ceil_div((long)d.B * nq * 4, 128), d.L, d.n_dn > 0 ? 2 : 1);
-    loss_local_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(d, w.acc, w.notsame, dcorners, out, gout + 6 * H,
+    launch_k(loss_local_kernel<true>, grid, 128, 0, (cudaStream_t)stream, d, w.acc, w.notsame, dcorners, out, gout + 6 * H,
                                                                    gout + 6 * H + 2 * d.L);
     DFINE_LAUNCH_CHECK("loss_fgl_ddf_bwd");
     return 0;

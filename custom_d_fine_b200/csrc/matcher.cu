@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(32) matcher_kernel(
     const float* __restrict__ extra,   // optional additive cost, same layout as cost_out (mask cost), or null
     int NL, int B, int Q, int C, int sumT, int Tmax, int cost_in_smem, float alpha, float gamma,
     float w_class, float w_bbox, float w_giou) {
+    pdl_entry();
     extern __shared__ __align__(16) unsigned char smem[];
     const int prob = blockIdx.x;
     const int layer = prob / B, b = prob % B;
@@ -247,7 +248,7 @@ int matcher_impl(const float* logits, const float* boxes, const long* labels, co
     DFINE_REQUIRE(in_smem || workspace != nullptr, "matcher: workspace required for Q=%d Tmax=%d", Q, Tmax);
     const long smem = fixed + (in_smem ? cost : 0);
     DFINE_SET_SMEM_ONCE(matcher_kernel, 220 * 1024, "matcher");
-    matcher_kernel<<<NL * B, 32, smem, (cudaStream_t)stream>>>(logits, boxes, labels, tboxes, toff, out_q, out_t,
+    launch_k(matcher_kernel, NL * B, 32, smem, (cudaStream_t)stream, logits, boxes, labels, tboxes, toff, out_q, out_t,
                                                               cost_out, workspace, extra, NL, B, Q, C, sumT, Tmax,
                                                               in_smem, alpha, gamma, w_class, w_bbox, w_giou);
     DFINE_LAUNCH_CHECK("matcher");

@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(
     const float* __restrict__ logits, long logit_ld, const float* __restrict__ ref,
     const float* __restrict__ pscale, float* __restrict__ out, MsdaGeom g, int B, int Q, int heads,
     int L, float offset_scale) {
+    pdl_entry();
     constexpr int D = TPG * 4;
     constexpr int GROUPS = 256 / TPG;
     __shared__ __align__(16) FwdSlot slots[GROUPS][MAX_POINTS];
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(256) msda_bwd_kernel(
     const float* __restrict__ pscale, const float* __restrict__ gout, float* __restrict__ gvalue,
     float* __restrict__ goff, long goff_ld, float* __restrict__ glogit, long glogit_ld, MsdaGeom g,
     int B, int Q, int heads, int L, float offset_scale) {
+    pdl_entry();
     constexpr int D = TPG * 4;
     constexpr int GROUPS = 256 / TPG;
     __shared__ PointSlot slots[GROUPS][MAX_POINTS];
@@ -299,10 +301,10 @@ DFINE_API int dfine_msda_fwd(const float* value, const float* offsets, long off_
     if (groups == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (head_dim == 32) {
-        msda_fwd_kernel<8><<<ceil_div(groups, 32), 256, 0, st>>>(value, offsets, off_ld, logits, logit_ld, ref,
+        launch_k(msda_fwd_kernel<8>, ceil_div(groups, 32), 256, 0, st, value, offsets, off_ld, logits, logit_ld, ref,
                                                                 pscale, out, g, B, Q, heads, L, offset_scale);
     } else {
-        msda_fwd_kernel<4><<<ceil_div(groups, 64), 256, 0, st>>>(value, offsets, off_ld, logits, logit_ld, ref,
+        launch_k(msda_fwd_kernel<4>, ceil_div(groups, 64), 256, 0, st, value, offsets, off_ld, logits, logit_ld, ref,
                                                                 pscale, out, g, B, Q, heads, L, offset_scale);
     }
     DFINE_LAUNCH_CHECK("msda_fwd");
@@ -327,11 +329,11 @@ DFINE_API int dfine_msda_bwd(const float* value, const float* offsets, long off_
     if (groups == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (head_dim == 32) {
-        msda_bwd_kernel<8><<<ceil_div(groups, 32), 256, 0, st>>>(value, offsets, off_ld, logits, logit_ld, ref,
+        launch_k(msda_bwd_kernel<8>, ceil_div(groups, 32), 256, 0, st, value, offsets, off_ld, logits, logit_ld, ref,
                                                                 pscale, gout, gvalue, goff, goff_ld, glogit,
                                                                 glogit_ld, g, B, Q, heads, L, offset_scale);
     } else {
-        msda_bwd_kernel<4><<<ceil_div(groups, 64), 256, 0, st>>>(value, offsets, off_ld, logits, logit_ld, ref,
+        launch_k(msda_bwd_kernel<4>, ceil_div(groups, 64), 256, 0, st, value, offsets, off_ld, logits, logit_ld, ref,
                                                                 pscale, gout, gvalue, goff, goff_ld, glogit,
                                                                 glogit_ld, g, B, Q, heads, L, offset_scale);
     }

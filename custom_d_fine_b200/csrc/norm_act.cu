@@ -37,6 +37,7 @@ __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<floa
 // cost more than the HBM pass itself.)
 __global__ void __launch_bounds__(NT) bn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats,
                                                       long M, int C, long rows_per_cta) {
+    pdl_entry();
     extern __shared__ float part[];  // [RPP][2*C]
     const RowMap m = make_rowmap(C);
     const long r0 = (long)blockIdx.x * rows_per_cta;
@@ -69,6 +70,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float
                                    float* __restrict__ running_var, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out, float* __restrict__ scale_out,
                                    float* __restrict__ shift_out, long M, int C, float momentum, float eps) {
+    pdl_entry();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     bn_finalize_channel(stats[c], stats[C + c], c, weight, bias, running_mean, running_var, mean_out, invstd_out, scale_out,
@@ -79,6 +81,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float
 __global__ void bn_fold_kernel(const float* __restrict__ weight, const float* __restrict__ bias,
                                const float* __restrict__ running_mean, const float* __restrict__ running_var,
                                float* __restrict__ scale_out, float* __restrict__ shift_out, int C, float eps) {
+    pdl_entry();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float sc = weight[c] * rsqrtf(running_var[c] + eps);
@@ -94,6 +97,7 @@ __global__ void __launch_bounds__(NT) bn_apply_kernel(const float* __restrict__ 
                                                       const float* __restrict__ lab, const float* __restrict__ lab_b,
                                                       float* __restrict__ y, long n4, int VC, int act, long ldy,
                                                       long ld_post) {
+    pdl_entry();
     const float ls = lab ? __ldg(lab) : 1.f, lb = lab ? __ldg(lab_b) : 0.f;
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long)gridDim.x * NT) {
         const int c = (int)(i % VC) * 4;
@@ -115,6 +119,7 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(
     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ pre_add, const float* __restrict__ lab, double* __restrict__ red, long M, int C,
     long rows_per_cta, int act, long ld_dy) {
+    pdl_entry();
     extern __shared__ float part[];  // [RPP][2*C] partial sums + [NT/32][2] LAB partials (see bn_stats_kernel)
     const float ls = lab ? __ldg(lab) : 1.f;
     const RowMap m = make_rowmap(C);
@@ -183,6 +188,7 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(
 __global__ void __launch_bounds__(NT) frozen_bn_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                                            const float* __restrict__ scale, float* __restrict__ dx, long n4,
                                                            int VC, int relu, long ld_dy, long ld_y, long ld_dx) {
+    pdl_entry();
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long)gridDim.x * NT) {
         const int c = (int)(i % VC) * 4;
         const long r = i / VC;
@@ -205,6 +211,7 @@ __global__ void __launch_bounds__(NT) bn_bwd_apply_kernel(
     float* __restrict__ dx, float* __restrict__ dpre, long n4, int VC, long M, int act, int training,
     float* __restrict__ g_w, float* __restrict__ g_b, float* __restrict__ g_lab_s, float* __restrict__ g_lab_b,
     long ld_dy, long ld_dx) {
+    pdl_entry();
     const float ls = lab ? __ldg(lab) : 1.f;
     const int C = VC * 4;
     const double invM = 1.0 / (double)M;
@@ -255,6 +262,7 @@ __global__ void __launch_bounds__(NT) layernorm_fwd_kernel(const float* __restri
                                                            const float* __restrict__ w, const float* __restrict__ b,
                                                            float* __restrict__ y, float* __restrict__ mean_out,
                                                            float* __restrict__ rstd_out, long rows, int D, float eps) {
+    pdl_entry();
     const long row = (long)blockIdx.x * (NT / 32) + threadIdx.x / 32;
     if (row >= rows) return;
     const int lane = threadIdx.x & 31, VD = D / 4;
@@ -305,6 +313,7 @@ __global__ void __launch_bounds__(NT) layernorm_bwd_kernel(const float* __restri
                                                            const float* __restrict__ rstd, float* __restrict__ dx,
                                                            float* __restrict__ dw, float* __restrict__ db, long rows,
                                                            int D) {
+    pdl_entry();
     extern __shared__ float shf[];  // [2*D]
     for (int i = threadIdx.x; i < 2 * D; i += NT) shf[i] = 0.f;
     __syncthreads();
@@ -390,7 +399,7 @@ DFINE_API int dfine_bn_stats(const float* x, double* stats, long M, int C, void*
     if (M == 0) return 0;
     const long rpc = pick_rows_per_cta(M, C);
     const RowMap rm = make_rowmap(C);
-    bn_stats_kernel<<<ceil_div(M, rpc), NT, (size_t)rm.RPP * 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, stats, M, C, rpc);
+    launch_k(bn_stats_kernel, ceil_div(M, rpc), NT, (size_t)rm.RPP * 2 * C * sizeof(float), (cudaStream_t)stream, x, stats, M, C, rpc);
     DFINE_LAUNCH_CHECK("bn_stats");
     return 0;
 }
@@ -398,7 +407,7 @@ DFINE_API int dfine_bn_stats(const float* x, double* stats, long M, int C, void*
 DFINE_API int dfine_bn_finalize(const double* stats, const float* weight, const float* bias, float* running_mean,
                                 float* running_var, float* mean, float* invstd, float* scale, float* shift, long M,
                                 int C, float momentum, float eps, void* stream) {
-    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(stats, weight, bias, running_mean,
+    launch_k(bn_finalize_kernel, ceil_div(C, 128), 128, 0, (cudaStream_t)stream, stats, weight, bias, running_mean,
                                                                           running_var, mean, invstd, scale, shift, M,
                                                                           C, momentum, eps);
     DFINE_LAUNCH_CHECK("bn_finalize");
@@ -407,7 +416,7 @@ DFINE_API int dfine_bn_finalize(const double* stats, const float* weight, const 
 
 DFINE_API int dfine_bn_fold(const float* weight, const float* bias, const float* running_mean,
                             const float* running_var, float* scale, float* shift, int C, float eps, void* stream) {
-    bn_fold_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(weight, bias, running_mean, running_var, scale,
+    launch_k(bn_fold_kernel, ceil_div(C, 128), 128, 0, (cudaStream_t)stream, weight, bias, running_mean, running_var, scale,
                                                                       shift, C, eps);
     DFINE_LAUNCH_CHECK("bn_fold");
     return 0;
@@ -423,7 +432,7 @@ DFINE_API int dfine_bn_apply(const float* x, const float* scale, const float* sh
                   "bn_apply: post_add row stride %ld", ld_post);
     const long n4 = M * C / 4;
     if (n4 == 0) return 0;
-    bn_apply_kernel<<<ew_grid(n4), NT, 0, (cudaStream_t)stream>>>(x, scale, shift, pre_add, post_add, lab, lab_b, y,
+    launch_k(bn_apply_kernel, ew_grid(n4), NT, 0, (cudaStream_t)stream, x, scale, shift, pre_add, post_add, lab, lab_b, y,
                                                                  n4, C / 4, act, ldy, post_add ? ld_post : (long)C);
     DFINE_LAUNCH_CHECK("bn_apply");
     return 0;
@@ -439,7 +448,7 @@ DFINE_API int dfine_bn_bwd_reduce(const float* dy, const float* x, const float* 
     const long rpc = pick_rows_per_cta(M, C);
     const RowMap rm = make_rowmap(C);
     const size_t smem = ((size_t)rm.RPP * 2 * C + 2 * (NT / 32)) * sizeof(float);
-    bn_bwd_reduce_kernel<<<ceil_div(M, rpc), NT, smem, (cudaStream_t)stream>>>(
+    launch_k(bn_bwd_reduce_kernel, ceil_div(M, rpc), NT, smem, (cudaStream_t)stream, 
         dy, x, scale, shift, mean, invstd, pre_add, lab, red, M, C, rpc, act, ld_dy);
     DFINE_LAUNCH_CHECK("bn_bwd_reduce");
     return 0;
@@ -457,7 +466,7 @@ DFINE_API int dfine_bn_bwd_apply(const float* dy, const float* x, const float* s
                   "bn_bwd_apply: gradient outputs come in pairs");
     const long n4 = M * C / 4;
     if (n4 == 0) return 0;
-    bn_bwd_apply_kernel<<<ew_grid(n4), NT, 2 * C * sizeof(float), (cudaStream_t)stream>>>(dy, x, scale, shift, mean, invstd, pre_add, lab,
+    launch_k(bn_bwd_apply_kernel, ew_grid(n4), NT, 2 * C * sizeof(float), (cudaStream_t)stream, dy, x, scale, shift, mean, invstd, pre_add, lab,
                                                                      red, dx, dpre, n4, C / 4, M, act, training, g_w,
                                                                      g_b, g_lab_s, g_lab_b, ld_dy, ld_dx);
     DFINE_LAUNCH_CHECK("bn_bwd_apply");
@@ -474,7 +483,7 @@ DFINE_API int dfine_frozen_bn_bwd(const float* dy, const float* y, const float* 
                   "frozen_bn_bwd: strides / alignment");
     const long n4 = M * C / 4;
     if (n4 == 0) return 0;
-    frozen_bn_bwd_kernel<<<ew_grid(n4), NT, 0, (cudaStream_t)stream>>>(dy, y, scale, dx, n4, C / 4, act == 1, ld_dy, ld_y, ld_dx);
+    launch_k(frozen_bn_bwd_kernel, ew_grid(n4), NT, 0, (cudaStream_t)stream, dy, y, scale, dx, n4, C / 4, act == 1, ld_dy, ld_y, ld_dx);
     DFINE_LAUNCH_CHECK("frozen_bn_bwd");
     return 0;
 }
@@ -484,7 +493,7 @@ DFINE_API int dfine_layernorm_fwd(const float* x, const float* res, const float*
                                   float* mean, float* rstd, long rows, int D, float eps, void* stream) {
     DFINE_REQUIRE(D % 4 == 0 && D <= 1024, "layernorm: D=%d must be a multiple of 4 and <= 1024", D);
     if (rows == 0) return 0;
-    layernorm_fwd_kernel<<<ceil_div(rows, NT / 32), NT, 0, (cudaStream_t)stream>>>(x, res, w, b, y, mean, rstd, rows,
+    launch_k(layernorm_fwd_kernel, ceil_div(rows, NT / 32), NT, 0, (cudaStream_t)stream, x, res, w, b, y, mean, rstd, rows,
                                                                                   D, eps);
     DFINE_LAUNCH_CHECK("layernorm_fwd");
     return 0;
@@ -502,10 +511,10 @@ DFINE_API int dfine_layernorm_bwd(const float* dy, const float* x, const float* 
     // four times as many rows are in flight per SM (the 134 400-row encoder LayerNorm ran at 1.6 TB/s)
     const int grid = (int)(slabs < 148L * 8 ? slabs : 148L * 8);
     if (D <= 256)
-        layernorm_bwd_kernel<2><<<grid, NT, 2 * D * sizeof(float), (cudaStream_t)stream>>>(dy, x, res, w, mean, rstd, dx,
+        launch_k(layernorm_bwd_kernel<2>, grid, NT, 2 * D * sizeof(float), (cudaStream_t)stream, dy, x, res, w, mean, rstd, dx,
                                                                                           dw, db, rows, D);
     else
-        layernorm_bwd_kernel<LN_MAXV><<<grid, NT, 2 * D * sizeof(float), (cudaStream_t)stream>>>(dy, x, res, w, mean, rstd,
+        launch_k(layernorm_bwd_kernel<LN_MAXV>, grid, NT, 2 * D * sizeof(float), (cudaStream_t)stream, dy, x, res, w, mean, rstd,
                                                                                                 dx, dw, db, rows, D);
     DFINE_LAUNCH_CHECK("layernorm_bwd");
     return 0;
@@ -516,6 +525,7 @@ DFINE_API int dfine_layernorm_bwd(const float* dy, const float* x, const float* 
 // ---------------------------------------------------------------------------------------------
 namespace {
 __global__ void __launch_bounds__(NT) act_fwd_kernel(const float* __restrict__ z, float* __restrict__ y, long n4, int act) {
+    pdl_entry();
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long)gridDim.x * NT) {
         const float4 v = ld4(z + i * 4);
         st4(y + i * 4, make_float4(act_fwd(v.x, act), act_fwd(v.y, act), act_fwd(v.z, act), act_fwd(v.w, act)));
@@ -524,6 +534,7 @@ __global__ void __launch_bounds__(NT) act_fwd_kernel(const float* __restrict__ z
 // dz = dy * act'(z).  For ReLU `z` may be the activation output (same sign test).
 __global__ void __launch_bounds__(NT) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                                      float* __restrict__ dz, long n4, int act) {
+    pdl_entry();
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long)gridDim.x * NT) {
         const float4 g = ld4(dy + i * 4), v = ld4(z + i * 4);
         st4(dz + i * 4, make_float4(g.x * act_bwd(v.x, act), g.y * act_bwd(v.y, act), g.z * act_bwd(v.z, act),
@@ -535,14 +546,14 @@ __global__ void __launch_bounds__(NT) act_bwd_kernel(const float* __restrict__ d
 DFINE_API int dfine_act_fwd(const float* z, float* y, long n, int act, void* stream) {
     DFINE_REQUIRE(n % 4 == 0, "act_fwd: n=%ld must be a multiple of 4", n);
     if (n == 0) return 0;
-    act_fwd_kernel<<<ew_grid(n / 4), NT, 0, (cudaStream_t)stream>>>(z, y, n / 4, act);
+    launch_k(act_fwd_kernel, ew_grid(n / 4), NT, 0, (cudaStream_t)stream, z, y, n / 4, act);
     DFINE_LAUNCH_CHECK("act_fwd");
     return 0;
 }
 DFINE_API int dfine_act_bwd(const float* dy, const float* z, float* dz, long n, int act, void* stream) {
     DFINE_REQUIRE(n % 4 == 0, "act_bwd: n=%ld must be a multiple of 4", n);
     if (n == 0) return 0;
-    act_bwd_kernel<<<ew_grid(n / 4), NT, 0, (cudaStream_t)stream>>>(dy, z, dz, n / 4, act);
+    launch_k(act_bwd_kernel, ew_grid(n / 4), NT, 0, (cudaStream_t)stream, dy, z, dz, n / 4, act);
     DFINE_LAUNCH_CHECK("act_bwd");
     return 0;
 }

@@ -17,6 +17,7 @@ namespace {
 constexpr int NT = 256;
 
 __global__ void __launch_bounds__(NT) sumsq_kernel(const float4* __restrict__ g, long n4, double* __restrict__ out) {
+    pdl_entry();
     float s = 0.f;
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long)gridDim.x * NT) {
         const float4 v = __ldg(g + i);
@@ -55,6 +56,7 @@ __device__ __forceinline__ void split_f16x4(const float4& w, float scale, uint2&
 
 __global__ void __launch_bounds__(NT) f16_split_flat_kernel(const float4* __restrict__ w, uint2* __restrict__ hi,
                                                             uint2* __restrict__ lo, long n4, float scale) {
+    pdl_entry();
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long)gridDim.x * NT) {
         uint2 h, l;
         split_f16x4(__ldg(w + i), scale, h, l);
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(NT) adamw_ema_kernel(float4* __restrict__ p, f
                                                        float beta1, float beta2, float eps, int zero_grad,
                                                        float4* __restrict__ hi, float4* __restrict__ lo, int plane_mode,
                                                        float plane_scale) {
+    pdl_entry();
     const float lr = __ldg(hyper + 0), wd = __ldg(hyper + 1), step = __ldg(hyper + 2), em = __ldg(hyper + 3);
     // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
     float coef = 1.f;
@@ -124,6 +127,7 @@ __global__ void __launch_bounds__(NT) adamw_ema_kernel(float4* __restrict__ p, f
 // ema = m * ema + (1 - m) * src   (floating-point buffers: BatchNorm running statistics etc., train.py:70-73)
 __global__ void __launch_bounds__(NT) ema_blend_kernel(float4* __restrict__ ema, const float4* __restrict__ src, long n4,
                                                        const float* __restrict__ momentum) {
+    pdl_entry();
     const float em = __ldg(momentum);
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long)gridDim.x * NT) {
         float4 e = ema[i];
@@ -146,7 +150,7 @@ int grid_for(long n4) {
 DFINE_API int dfine_sumsq(const float* g, long n, double* out, void* stream) {
     DFINE_REQUIRE(n % 4 == 0 && ((uintptr_t)g % 16) == 0, "sumsq: arena must be 16-byte aligned and padded to 4 floats");
     if (n == 0) return 0;
-    sumsq_kernel<<<grid_for(n / 4), NT, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(g), n / 4, out);
+    launch_k(sumsq_kernel, grid_for(n / 4), NT, 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(g), n / 4, out);
     DFINE_LAUNCH_CHECK("sumsq");
     return 0;
 }
@@ -168,7 +172,7 @@ DFINE_API int dfine_adamw_ema(float* p, float* g, float* m, float* v, float* ema
                       ((uintptr_t)lo % 16) == 0 && ((hi == nullptr) == (lo == nullptr)),
                   "adamw_ema: arenas must be 16-byte aligned");
     if (n == 0) return 0;
-    adamw_ema_kernel<<<grid_for(n / 4), NT, 0, (cudaStream_t)stream>>>(
+    launch_k(adamw_ema_kernel, grid_for(n / 4), NT, 0, (cudaStream_t)stream, 
         reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g), reinterpret_cast<float4*>(m),
         reinterpret_cast<float4*>(v), reinterpret_cast<float4*>(ema), n / 4, hyper, gnorm_sq, max_norm, beta1, beta2,
         eps, zero_grad, reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo), plane_mode, plane_scale);
@@ -181,7 +185,7 @@ DFINE_API int dfine_f16_split_flat(const float* w, void* hi16, void* lo16, long 
     DFINE_REQUIRE(n % 4 == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)hi16 % 8) == 0 && ((uintptr_t)lo16 % 8) == 0 && scale > 0.f,
                   "f16_split_flat: alignment / n %% 4");
     if (n == 0) return 0;
-    f16_split_flat_kernel<<<grid_for(n / 4), NT, 0, (cudaStream_t)stream>>>(
+    launch_k(f16_split_flat_kernel, grid_for(n / 4), NT, 0, (cudaStream_t)stream, 
         reinterpret_cast<const float4*>(w), reinterpret_cast<uint2*>(hi16), reinterpret_cast<uint2*>(lo16), n / 4, scale);
     DFINE_LAUNCH_CHECK("f16_split_flat");
     return 0;
@@ -190,7 +194,7 @@ DFINE_API int dfine_f16_split_flat(const float* w, void* hi16, void* lo16, long 
 DFINE_API int dfine_ema_blend(float* ema, const float* src, long n, const float* momentum, void* stream) {
     DFINE_REQUIRE(n % 4 == 0 && ((uintptr_t)ema % 16) == 0 && ((uintptr_t)src % 16) == 0, "ema_blend: alignment");
     if (n == 0) return 0;
-    ema_blend_kernel<<<grid_for(n / 4), NT, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(ema),
+    launch_k(ema_blend_kernel, grid_for(n / 4), NT, 0, (cudaStream_t)stream, reinterpret_cast<float4*>(ema),
                                                                        reinterpret_cast<const float4*>(src), n / 4,
                                                                        momentum);
     DFINE_LAUNCH_CHECK("ema_blend");

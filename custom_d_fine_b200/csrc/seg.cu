@@ -15,6 +15,7 @@ namespace {
 // channels are contiguous (cpg = C / G, cpg % 4 == 0), so a float4 belongs to one group.  grid = (chunks, B).
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, long HW,
                                                        int C, int G) {
+    pdl_entry();
     extern __shared__ double sh[];        // [2 * G]
     const int b = blockIdx.y, c4 = C / 4, cpg4 = C / G / 4;
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.0;
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
 
 __global__ void gn_finalize_kernel(const double* __restrict__ stats, float* __restrict__ mean, float* __restrict__ rstd,
                                    int BG, double n, float eps) {
+    pdl_entry();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= BG) return;
     const double m = stats[2 * i] / n;
@@ -54,6 +56,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
                                                        const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, float* __restrict__ y, long HW,
                                                        int C, int G, int B, int relu) {
+    pdl_entry();
     const int c4 = C / 4, cpg4 = C / G / 4;
     const long n = (long)B * HW * c4;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -79,6 +82,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const float* __restr
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             double* __restrict__ red, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, long HW, int C, int G, int relu) {
+    pdl_entry();
     extern __shared__ double sh[];        // [2 * G]
     const int b = blockIdx.y, c4 = C / 4, cpg4 = C / G / 4;
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.0;
@@ -126,6 +130,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const float* __restri
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const double* __restrict__ red, float* __restrict__ dx, long HW,
                                                            int C, int G, int B, int relu, double inv_n) {
+    pdl_entry();
     const int c4 = C / 4, cpg4 = C / G / 4;
     const long n = (long)B * HW * c4;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -173,6 +178,7 @@ __device__ __forceinline__ float tap_weight(int d, int s, float scale, int in_si
 // dx[b, ys, xs, :] = sum over destination pixels of dy * weight; x: [B,Hs,Ws,C] source grid, dy: [B,H,W,C]
 __global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int Hs,
                                                          int Ws, int H, int W, int C) {
+    pdl_entry();
     const int c4 = C / 4;
     const long n = (long)B * Hs * Ws * c4;
     const float sy = (float)Hs / (float)H, sx = (float)Ws / (float)W;
@@ -215,6 +221,7 @@ constexpr int MC_T = 16;         // targets per register pass
 __global__ void __launch_bounds__(512) mask_cost_acc_kernel(const float* __restrict__ logits, const float* __restrict__ gt,
                                                             const int* __restrict__ toff, float* __restrict__ acc, long HW,
                                                             int Q, float alpha, float gamma, int chunk) {
+    pdl_entry();
     extern __shared__ float gts[];              // [MC_T][chunk]
     const int b = blockIdx.y;
     const int t0 = toff[b], T = toff[b + 1] - t0;
@@ -271,6 +278,7 @@ __global__ void __launch_bounds__(512) mask_cost_acc_kernel(const float* __restr
 // extra[Q*toff[b] + q*T_b + t] (+)= w_dice * (1 - (2 S1 + 1e-6) / (P + G_t + 1e-6)) + w_mask * (S2 + N) / HW
 __global__ void mask_cost_final_kernel(const float* __restrict__ acc, const float* __restrict__ gsum, const int* __restrict__ toff,
                                        float* __restrict__ extra, int B, int Q, long HW, float w_dice, float w_mask) {
+    pdl_entry();
     const int b = blockIdx.y;
     const int t0 = toff[b], T = toff[b + 1] - t0;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -312,6 +320,7 @@ __global__ void __launch_bounds__(256) mask_loss_fwd_kernel(const float* __restr
                                                             const long* __restrict__ t_idx, const float* __restrict__ tboxes,
                                                             float* __restrict__ bce_row, float* __restrict__ dice_row,
                                                             float* __restrict__ sums, int Hm, int Wm) {
+    pdl_entry();
     __shared__ float sh[8];
     const int m = blockIdx.x;
     const long t = t_idx[m];
@@ -345,6 +354,7 @@ __global__ void __launch_bounds__(256) mask_loss_bwd_kernel(const float* __restr
                                                             const float* __restrict__ sums, const float* __restrict__ g_bce,
                                                             const float* __restrict__ g_dice, float* __restrict__ dpred,
                                                             int Hm, int Wm) {
+    pdl_entry();
     const int m = blockIdx.x;
     const long t = t_idx[m];
     const BoxPx bx = box_px(tboxes + t * 4, Hm, Wm);
@@ -377,6 +387,7 @@ constexpr int PM_YROWS = 32;       // pixel rows per CTA slab
 __global__ void __launch_bounds__(256) mask_loss_pm_acc_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
                                                                const long* __restrict__ t_idx, const float* __restrict__ tboxes,
                                                                float* __restrict__ sums, int R, int Hm, int Wm) {
+    pdl_entry();
     __shared__ float red[8][32][4];
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int b = blockIdx.y, r = blockIdx.x * 32 + lane;
@@ -424,6 +435,7 @@ __global__ void __launch_bounds__(256) mask_loss_pm_acc_kernel(const float* __re
 __global__ void mask_loss_pm_final_kernel(const float* __restrict__ sums, const long* __restrict__ t_idx,
                                           const float* __restrict__ tboxes, float* __restrict__ bce_row,
                                           float* __restrict__ dice_row, long n, int Hm, int Wm) {
+    pdl_entry();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const long t = t_idx[i];
@@ -439,6 +451,7 @@ __global__ void __launch_bounds__(256) mask_loss_pm_bwd_kernel(const float* __re
                                                                const float* __restrict__ sums, const float* __restrict__ g_bce,
                                                                const float* __restrict__ g_dice, float* __restrict__ dpred,
                                                                int R, int Hm, int Wm) {
+    pdl_entry();
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int b = blockIdx.y, r = blockIdx.x * 32 + lane;
     if (r >= R) return;
@@ -494,9 +507,9 @@ DFINE_API int dfine_groupnorm_fwd(const float* x, const float* gamma, const floa
     cudaStream_t st = (cudaStream_t)stream;
     int chunks = (int)((HW + 255) / 256);
     if (chunks > 148 * 4 / (B > 0 ? B : 1) + 1) chunks = 148 * 4 / B + 1;
-    gn_stats_kernel<<<dim3(chunks, B), 256, 2 * G * sizeof(double), st>>>(x, stats, HW, C, G);
-    gn_finalize_kernel<<<ceil_div((long)B * G, 128), 128, 0, st>>>(stats, mean, rstd, B * G, (double)HW * (C / G), eps);
-    gn_apply_kernel<<<ew_grid((long)B * HW * (C / 4)), 256, 0, st>>>(x, mean, rstd, gamma, beta, y, HW, C, G, B, relu);
+    launch_k(gn_stats_kernel, dim3(chunks, B), 256, 2 * G * sizeof(double), st, x, stats, HW, C, G);
+    launch_k(gn_finalize_kernel, ceil_div((long)B * G, 128), 128, 0, st, stats, mean, rstd, B * G, (double)HW * (C / G), eps);
+    launch_k(gn_apply_kernel, ew_grid((long)B * HW * (C / 4)), 256, 0, st, x, mean, rstd, gamma, beta, y, HW, C, G, B, relu);
     DFINE_LAUNCH_CHECK("groupnorm_fwd");
     return 0;
 }
@@ -511,9 +524,9 @@ DFINE_API int dfine_groupnorm_bwd(const float* dy, const float* x, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     int chunks = (int)((HW + 255) / 256);
     if (chunks > 148 * 4 / (B > 0 ? B : 1) + 1) chunks = 148 * 4 / B + 1;
-    gn_bwd_reduce_kernel<<<dim3(chunks, B), 256, 2 * G * sizeof(double), st>>>(dy, x, mean, rstd, gamma, beta, red, dgamma,
+    launch_k(gn_bwd_reduce_kernel, dim3(chunks, B), 256, 2 * G * sizeof(double), st, dy, x, mean, rstd, gamma, beta, red, dgamma,
                                                                                dbeta, HW, C, G, relu);
-    gn_bwd_apply_kernel<<<ew_grid((long)B * HW * (C / 4)), 256, 0, st>>>(dy, x, mean, rstd, gamma, beta, red, dx, HW, C, G, B,
+    launch_k(gn_bwd_apply_kernel, ew_grid((long)B * HW * (C / 4)), 256, 0, st, dy, x, mean, rstd, gamma, beta, red, dx, HW, C, G, B,
                                                                          relu, 1.0 / ((double)HW * (C / G)));
     DFINE_LAUNCH_CHECK("groupnorm_bwd");
     return 0;
@@ -533,9 +546,9 @@ DFINE_API int dfine_mask_cost(const float* logits, const float* gt, const float*
     const int chunk = 512;                                   // pixels per CTA: 16 x 512 floats of GT in shared memory
     dim3 grid(ceil_div(HW, chunk), B);
     const int threads = Q >= 512 ? 512 : (Q + 31) / 32 * 32;      // one thread per query where they fit
-    mask_cost_acc_kernel<<<grid, threads, MC_T * chunk * sizeof(float), st>>>(logits, gt, toff, workspace, HW, Q, alpha, gamma, chunk);
+    launch_k(mask_cost_acc_kernel, grid, threads, MC_T * chunk * sizeof(float), st, logits, gt, toff, workspace, HW, Q, alpha, gamma, chunk);
     dim3 g2(ceil_div((long)Q * Tmax, 128), B);
-    mask_cost_final_kernel<<<g2, 128, 0, st>>>(workspace, gsum, toff, extra, B, Q, HW, w_dice, w_mask);
+    launch_k(mask_cost_final_kernel, g2, 128, 0, st, workspace, gsum, toff, extra, B, Q, HW, w_dice, w_mask);
     DFINE_LAUNCH_CHECK("mask_cost");
     return 0;
 }
@@ -546,7 +559,7 @@ DFINE_API int dfine_mask_loss_fwd(const float* pred, const float* gt, const long
                                   float* dice_row, float* sums, int M, int Hm, int Wm, void* stream) {
     DFINE_REQUIRE(M >= 0 && Hm > 0 && Wm > 0, "mask_loss: bad dims");
     if (M == 0) return 0;
-    mask_loss_fwd_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(pred, gt, t_idx, tboxes, bce_row, dice_row, sums, Hm, Wm);
+    launch_k(mask_loss_fwd_kernel, M, 256, 0, (cudaStream_t)stream, pred, gt, t_idx, tboxes, bce_row, dice_row, sums, Hm, Wm);
     DFINE_LAUNCH_CHECK("mask_loss_fwd");
     return 0;
 }
@@ -554,7 +567,7 @@ DFINE_API int dfine_mask_loss_bwd(const float* pred, const float* gt, const long
                                   const float* g_bce, const float* g_dice, float* dpred, int M, int Hm, int Wm, void* stream) {
     DFINE_REQUIRE(M >= 0 && Hm > 0 && Wm > 0, "mask_loss_bwd: bad dims");
     if (M == 0) return 0;
-    mask_loss_bwd_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(pred, gt, t_idx, tboxes, sums, g_bce, g_dice, dpred, Hm, Wm);
+    launch_k(mask_loss_bwd_kernel, M, 256, 0, (cudaStream_t)stream, pred, gt, t_idx, tboxes, sums, g_bce, g_dice, dpred, Hm, Wm);
     DFINE_LAUNCH_CHECK("mask_loss_bwd");
     return 0;
 }
@@ -567,9 +580,9 @@ DFINE_API int dfine_mask_loss_pm_fwd(const float* pred, const float* gt, const l
     if ((long)B * R == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(ceil_div(R, 32), B, ceil_div(Hm, PM_YROWS));
-    mask_loss_pm_acc_kernel<<<grid, 256, 0, st>>>(pred, gt, t_idx, tboxes, sums, R, Hm, Wm);
+    launch_k(mask_loss_pm_acc_kernel, grid, 256, 0, st, pred, gt, t_idx, tboxes, sums, R, Hm, Wm);
     DFINE_LAUNCH_CHECK("mask_loss_pm_acc");
-    mask_loss_pm_final_kernel<<<ceil_div((long)B * R, 256), 256, 0, st>>>(sums, t_idx, tboxes, bce_row, dice_row, (long)B * R, Hm, Wm);
+    launch_k(mask_loss_pm_final_kernel, ceil_div((long)B * R, 256), 256, 0, st, sums, t_idx, tboxes, bce_row, dice_row, (long)B * R, Hm, Wm);
     DFINE_LAUNCH_CHECK("mask_loss_pm_final");
     return 0;
 }
@@ -579,7 +592,7 @@ DFINE_API int dfine_mask_loss_pm_bwd(const float* pred, const float* gt, const l
     DFINE_REQUIRE(B >= 0 && R >= 0 && Hm > 0 && Wm > 0, "mask_loss_pm_bwd: bad dims");
     if ((long)B * R == 0) return 0;
     dim3 grid(ceil_div(R, 32), B, ceil_div(Hm, PM_YROWS));
-    mask_loss_pm_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, gt, t_idx, tboxes, sums, g_bce, g_dice, dpred, R, Hm, Wm);
+    launch_k(mask_loss_pm_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, pred, gt, t_idx, tboxes, sums, g_bce, g_dice, dpred, R, Hm, Wm);
     DFINE_LAUNCH_CHECK("mask_loss_pm_bwd");
     return 0;
 }
@@ -588,7 +601,7 @@ DFINE_API int dfine_mask_loss_pm_bwd(const float* pred, const float* gt, const l
 DFINE_API int dfine_resize_bilinear_bwd(const float* dy, float* dx, int B, int Hs, int Ws, int H, int W, int C, void* stream) {
     DFINE_REQUIRE(B >= 0 && Hs > 0 && Ws > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "resize_bilinear_bwd: bad dims (C %% 4)");
     if (B == 0) return 0;
-    resize_bwd_kernel<<<ew_grid((long)B * Hs * Ws * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dy, dx, B, Hs, Ws, H, W, C);
+    launch_k(resize_bwd_kernel, ew_grid((long)B * Hs * Ws * (C / 4)), 256, 0, (cudaStream_t)stream, dy, dx, B, Hs, Ws, H, W, C);
     DFINE_LAUNCH_CHECK("resize_bilinear_bwd");
     return 0;
 }

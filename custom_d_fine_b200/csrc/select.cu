@@ -27,6 +27,7 @@ constexpr int TK_THREADS = 1024;
 // scores[b, t] = max_c logits[b, t, c] (NaN if any class is NaN): one warp per token over the whole grid
 __global__ void __launch_bounds__(256) rowmax_kernel(const float* __restrict__ logits, float* __restrict__ scores, long rows,
                                                      int C) {
+    pdl_entry();
     const long t = (long)blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (t >= rows) return;
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(256) rowmax_kernel(const float* __restrict__ l
 template <int KP>
 __global__ void __launch_bounds__(TK_THREADS) topk_rowmax_kernel(const float* __restrict__ scores, long* __restrict__ out,
                                                                  int L, int k) {
+    pdl_entry();
     extern __shared__ uint32_t keys[];
     __shared__ uint32_t hist[256];
     __shared__ uint32_t sel_prefix, sel_remaining, n_above, n_equal_taken;
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(TK_THREADS) topk_rowmax_kernel(const float* __
 
 __global__ void gate_mix_fwd_kernel(const float* __restrict__ g, const float* __restrict__ x1, const float* __restrict__ x2,
                                     float* __restrict__ out, long rows, int D) {
+    pdl_entry();
     const long n4 = rows * (D / 4);
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         const long r = i / (D / 4);
@@ -165,6 +168,7 @@ __device__ __forceinline__ void gate_bwd1(float go, float g, float x, float& dg,
 __global__ void gate_mix_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ g, const float* __restrict__ x1,
                                     const float* __restrict__ x2, float* __restrict__ dg, float* __restrict__ dx1,
                                     float* __restrict__ dx2, long rows, int D) {
+    pdl_entry();
     const long n4 = rows * (D / 4);
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         const long r = i / (D / 4);
@@ -197,13 +201,13 @@ DFINE_API int dfine_topk_rowmax(const float* logits, float* scores, long* idx, i
     if (B == 0) return 0;
     const int smem = L * 4;
     cudaStream_t st = (cudaStream_t)stream;
-    rowmax_kernel<<<ceil_div((long)B * L, 8), 256, 0, st>>>(logits, scores, (long)B * L, C);
+    launch_k(rowmax_kernel, ceil_div((long)B * L, 8), 256, 0, st, logits, scores, (long)B * L, C);
     if (k <= 512) {
         DFINE_SET_SMEM_ONCE((topk_rowmax_kernel<512>), 200 * 1024, "topk_rowmax");
-        topk_rowmax_kernel<512><<<B, TK_THREADS, smem, st>>>(scores, idx, L, k);
+        launch_k(topk_rowmax_kernel<512>, B, TK_THREADS, smem, st, scores, idx, L, k);
     } else {
         DFINE_SET_SMEM_ONCE((topk_rowmax_kernel<1024>), 200 * 1024, "topk_rowmax");
-        topk_rowmax_kernel<1024><<<B, TK_THREADS, smem, st>>>(scores, idx, L, k);
+        launch_k(topk_rowmax_kernel<1024>, B, TK_THREADS, smem, st, scores, idx, L, k);
     }
     DFINE_LAUNCH_CHECK("topk_rowmax");
     return 0;
@@ -217,7 +221,7 @@ DFINE_API int dfine_gate_mix_fwd(const float* g, const float* x1, const float* x
     if (rows == 0) return 0;
     long blocks = (rows * (D / 4) + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    gate_mix_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, x1, x2, out, rows, D);
+    launch_k(gate_mix_fwd_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, g, x1, x2, out, rows, D);
     DFINE_LAUNCH_CHECK("gate_mix_fwd");
     return 0;
 }
@@ -227,7 +231,7 @@ DFINE_API int dfine_gate_mix_bwd(const float* dout, const float* g, const float*
     if (rows == 0) return 0;
     long blocks = (rows * (D / 4) + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    gate_mix_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(dout, g, x1, x2, dg, dx1, dx2, rows, D);
+    launch_k(gate_mix_bwd_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, dout, g, x1, x2, dg, dx1, dx2, rows, D);
     DFINE_LAUNCH_CHECK("gate_mix_bwd");
     return 0;
 }

@@ -20,6 +20,7 @@ __device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& w
 __global__ void __launch_bounds__(NT) dwconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         float* __restrict__ y, int B, int H, int W, int C, int OH,
                                                         int OW, int k, int stride, int pad) {
+    pdl_entry();
     const int VC = C / 4;
     const long total = (long)B * OH * OW * VC;
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(NT) dwconv_fwd_kernel(const float* __restrict_
 __global__ void __launch_bounds__(NT) dwconv_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                              float* __restrict__ dx, int B, int H, int W, int C,
                                                              int OH, int OW, int k, int stride, int pad) {
+    pdl_entry();
     const int VC = C / 4;
     const long total = (long)B * H * W * VC;
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
@@ -82,6 +84,7 @@ template <int K, int S>
 __global__ void __launch_bounds__(NT) dwconv_fwd_blocked(const float* __restrict__ x, const float* __restrict__ w,
                                                          float* __restrict__ y, int B, int H, int W, int C, int OH,
                                                          int OW, int pad) {
+    pdl_entry();
     constexpr int SPAN = (PX - 1) * S + K;
     const int VC = C / 4, WB = (OW + PX - 1) / PX;
     const long total = (long)B * OH * WB * VC;
@@ -123,6 +126,7 @@ template <int K>
 __global__ void __launch_bounds__(NT) dwconv_bwd_data_blocked(const float* __restrict__ dy, const float* __restrict__ w,
                                                               float* __restrict__ dx, int B, int H, int W, int C,
                                                               int OH, int OW, int pad) {
+    pdl_entry();
     constexpr int SPAN = PX - 1 + K;
     const int VC = C / 4, WB = (W + PX - 1) / PX;
     const long total = (long)B * H * WB * VC;
@@ -166,6 +170,7 @@ __global__ void __launch_bounds__(NT) dwconv_bwd_data_blocked(const float* __res
 __global__ void __launch_bounds__(NT) dwconv3x3s2_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                                   float* __restrict__ dx, int B, int H, int W, int C,
                                                                   int OH, int OW) {
+    pdl_entry();
     const int VC = C / 4, HB = (H + 1) / 2, WB = (W + 1) / 2;
     const long total = (long)B * HB * WB * VC;
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
@@ -210,6 +215,7 @@ template <int K, int S>
 __global__ void __launch_bounds__(NT) dwconv_bwd_weight_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                float* __restrict__ dw, int B, int H, int W, int C,
                                                                int OH, int OW, int pad, long pix_per_cta) {
+    pdl_entry();
     constexpr int stride = S;
     extern __shared__ float shw[];  // [K*K*C]
     for (int i = threadIdx.x; i < K * K * C; i += NT) shw[i] = 0.f;
@@ -284,6 +290,7 @@ __device__ __forceinline__ int window_argmax(const float* __restrict__ x, int b,
 }
 __global__ void __launch_bounds__(NT) maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
                                                          int H, int W, int C) {
+    pdl_entry();
     const long total = (long)B * H * W * C;
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
         const int c = (int)(i % C);
@@ -299,6 +306,7 @@ __global__ void __launch_bounds__(NT) maxpool_fwd_kernel(const float* __restrict
 // gather form of the backward: input (h,w) receives dy of each of its <=4 windows whose argmax it is.
 __global__ void __launch_bounds__(NT) maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                          float* __restrict__ dx, int B, int H, int W, int C) {
+    pdl_entry();
     const long total = (long)B * H * W * C;
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
         const int c = (int)(i % C);
@@ -344,6 +352,7 @@ __device__ __forceinline__ int window_argmax4(const float* __restrict__ x, int b
 }
 __global__ void __launch_bounds__(NT) maxpool_fwd4_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
                                                           int H, int W, int VC, long ldx) {
+    pdl_entry();
     const long total = (long)B * H * W * VC;
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
         const int cv = (int)(i % VC);
@@ -358,6 +367,7 @@ __global__ void __launch_bounds__(NT) maxpool_fwd4_kernel(const float* __restric
 }
 __global__ void __launch_bounds__(NT) maxpool_bwd4_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                           float* __restrict__ dx, int B, int H, int W, int VC, long ldx) {
+    pdl_entry();
     const long total = (long)B * H * W * VC;
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
         const int cv = (int)(i % VC);
@@ -386,6 +396,7 @@ __global__ void __launch_bounds__(NT) maxpool_bwd4_kernel(const float* __restric
 
 __global__ void __launch_bounds__(NT) upsample2x_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
                                                             int H, int W, int VC) {
+    pdl_entry();
     const long total = (long)B * (2 * H) * (2 * W) * VC;
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
         const int cv = (int)(i % VC);
@@ -398,6 +409,7 @@ __global__ void __launch_bounds__(NT) upsample2x_fwd_kernel(const float* __restr
 }
 __global__ void __launch_bounds__(NT) upsample2x_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx,
                                                             int B, int H, int W, int VC) {
+    pdl_entry();
     const long total = (long)B * H * W * VC;
     for (long i = (long)blockIdx.x * NT + threadIdx.x; i < total; i += (long)gridDim.x * NT) {
         const int cv = (int)(i % VC);
@@ -431,13 +443,13 @@ DFINE_API int dfine_dwconv_fwd(const float* x, const float* w, float* y, int B, 
     const long blocked = (long)B * OH * ((OW + PX - 1) / PX) * (C / 4);
     cudaStream_t st = (cudaStream_t)stream;
     if (k == 5 && stride == 1)
-        dwconv_fwd_blocked<5, 1><<<ew_grid(blocked), NT, 0, st>>>(x, w, y, B, H, W, C, OH, OW, pad);
+        launch_k(dwconv_fwd_blocked<5, 1>, ew_grid(blocked), NT, 0, st, x, w, y, B, H, W, C, OH, OW, pad);
     else if (k == 3 && stride == 2)
-        dwconv_fwd_blocked<3, 2><<<ew_grid(blocked), NT, 0, st>>>(x, w, y, B, H, W, C, OH, OW, pad);
+        launch_k(dwconv_fwd_blocked<3, 2>, ew_grid(blocked), NT, 0, st, x, w, y, B, H, W, C, OH, OW, pad);
     else if (k == 3 && stride == 1)
-        dwconv_fwd_blocked<3, 1><<<ew_grid(blocked), NT, 0, st>>>(x, w, y, B, H, W, C, OH, OW, pad);
+        launch_k(dwconv_fwd_blocked<3, 1>, ew_grid(blocked), NT, 0, st, x, w, y, B, H, W, C, OH, OW, pad);
     else
-        dwconv_fwd_kernel<<<ew_grid(total), NT, 0, st>>>(x, w, y, B, H, W, C, OH, OW, k, stride, pad);
+        launch_k(dwconv_fwd_kernel, ew_grid(total), NT, 0, st, x, w, y, B, H, W, C, OH, OW, k, stride, pad);
     DFINE_LAUNCH_CHECK("dwconv_fwd");
     return 0;
 }
@@ -451,14 +463,14 @@ DFINE_API int dfine_dwconv_bwd_data(const float* dy, const float* w, float* dx, 
     const long blocked = (long)B * H * ((W + PX - 1) / PX) * (C / 4);
     cudaStream_t st = (cudaStream_t)stream;
     if (k == 5 && stride == 1)
-        dwconv_bwd_data_blocked<5><<<ew_grid(blocked), NT, 0, st>>>(dy, w, dx, B, H, W, C, OH, OW, pad);
+        launch_k(dwconv_bwd_data_blocked<5>, ew_grid(blocked), NT, 0, st, dy, w, dx, B, H, W, C, OH, OW, pad);
     else if (k == 3 && stride == 1)
-        dwconv_bwd_data_blocked<3><<<ew_grid(blocked), NT, 0, st>>>(dy, w, dx, B, H, W, C, OH, OW, pad);
+        launch_k(dwconv_bwd_data_blocked<3>, ew_grid(blocked), NT, 0, st, dy, w, dx, B, H, W, C, OH, OW, pad);
     else if (k == 3 && stride == 2 && pad == 1)
-        dwconv3x3s2_bwd_data_kernel<<<ew_grid((long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4)), NT, 0, st>>>(
+        launch_k(dwconv3x3s2_bwd_data_kernel, ew_grid((long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4)), NT, 0, st, 
             dy, w, dx, B, H, W, C, OH, OW);
     else
-        dwconv_bwd_data_kernel<<<ew_grid(total), NT, 0, st>>>(dy, w, dx, B, H, W, C, OH, OW, k, stride, pad);
+        launch_k(dwconv_bwd_data_kernel, ew_grid(total), NT, 0, st, dy, w, dx, B, H, W, C, OH, OW, k, stride, pad);
     DFINE_LAUNCH_CHECK("dwconv_bwd_data");
     return 0;
 }
@@ -485,7 +497,7 @@ DFINE_API int dfine_dwconv_bwd_weight(const float* dy, const float* x, float* dw
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) { dfine_set_error("dwconv_bwd_weight: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
         }
-        kern<<<grid, NT, smem, st>>>(dy, x, dw, B, H, W, C, OH, OW, pad, ppc);
+        launch_k(kern, grid, NT, smem, st, dy, x, dw, B, H, W, C, OH, OW, pad, ppc);
         return 0;
     };
     int rc;
@@ -504,9 +516,9 @@ DFINE_API int dfine_maxpool2x2_fwd(const float* x, long ldx, float* y, int B, in
     if (total == 0) return 0;
     DFINE_REQUIRE(ldx == C || (C % 4 == 0 && ldx % 4 == 0 && ldx > C), "maxpool_fwd: pixel stride %ld", ldx);
     if (C % 4 == 0)
-        maxpool_fwd4_kernel<<<ew_grid(total / 4), NT, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C / 4, ldx);
+        launch_k(maxpool_fwd4_kernel, ew_grid(total / 4), NT, 0, (cudaStream_t)stream, x, y, B, H, W, C / 4, ldx);
     else
-        maxpool_fwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C);
+        launch_k(maxpool_fwd_kernel, ew_grid(total), NT, 0, (cudaStream_t)stream, x, y, B, H, W, C);
     DFINE_LAUNCH_CHECK("maxpool_fwd");
     return 0;
 }
@@ -516,9 +528,9 @@ DFINE_API int dfine_maxpool2x2_bwd(const float* x, long ldx, const float* dy, fl
     if (total == 0) return 0;
     DFINE_REQUIRE(ldx == C || (C % 4 == 0 && ldx % 4 == 0 && ldx > C), "maxpool_bwd: pixel stride %ld", ldx);
     if (C % 4 == 0)
-        maxpool_bwd4_kernel<<<ew_grid(total / 4), NT, 0, (cudaStream_t)stream>>>(x, dy, dx, B, H, W, C / 4, ldx);
+        launch_k(maxpool_bwd4_kernel, ew_grid(total / 4), NT, 0, (cudaStream_t)stream, x, dy, dx, B, H, W, C / 4, ldx);
     else
-        maxpool_bwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x, dy, dx, B, H, W, C);
+        launch_k(maxpool_bwd_kernel, ew_grid(total), NT, 0, (cudaStream_t)stream, x, dy, dx, B, H, W, C);
     DFINE_LAUNCH_CHECK("maxpool_bwd");
     return 0;
 }
@@ -526,7 +538,7 @@ DFINE_API int dfine_upsample2x_fwd(const float* x, float* y, int B, int H, int W
     DFINE_REQUIRE(C % 4 == 0, "upsample2x: C=%d", C);
     const long total = (long)B * 4 * H * W * (C / 4);
     if (total == 0) return 0;
-    upsample2x_fwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C / 4);
+    launch_k(upsample2x_fwd_kernel, ew_grid(total), NT, 0, (cudaStream_t)stream, x, y, B, H, W, C / 4);
     DFINE_LAUNCH_CHECK("upsample2x_fwd");
     return 0;
 }
@@ -534,7 +546,7 @@ DFINE_API int dfine_upsample2x_bwd(const float* dy, float* dx, int B, int H, int
     DFINE_REQUIRE(C % 4 == 0, "upsample2x: C=%d", C);
     const long total = (long)B * H * W * (C / 4);
     if (total == 0) return 0;
-    upsample2x_bwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(dy, dx, B, H, W, C / 4);
+    launch_k(upsample2x_bwd_kernel, ew_grid(total), NT, 0, (cudaStream_t)stream, dy, dx, B, H, W, C / 4);
     DFINE_LAUNCH_CHECK("upsample2x_bwd");
     return 0;
 }

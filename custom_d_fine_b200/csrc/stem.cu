@@ -31,6 +31,7 @@ template <int CO4>
 __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ wr,
                                                        float* __restrict__ y, long ldy, int B, int H, int W, int OH,
                                                        int OW) {
+    pdl_entry();
     __shared__ float4 ws[27][CO4];
     for (int i = threadIdx.x; i < 27 * CO4; i += blockDim.x) {
         const int k = i / CO4, c4 = i % CO4;
@@ -62,6 +63,7 @@ template <int CO4>
 __global__ void __launch_bounds__(32 * CO4) stem_wgrad_kernel(const float* __restrict__ dy, long ldy,
                                                               const float* __restrict__ x, long ldx,
                                                               float* __restrict__ dwr, int B, int H, int W, int OH, int OW) {
+    pdl_entry();
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const long P = (long)B * OH * OW;
     float acc[4][27];
@@ -107,9 +109,9 @@ DFINE_API int dfine_stem_conv_fwd(const float* x, long ldx, const float* wr, flo
     if (P == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = ceil_div(P, 256);
-    if (Cout == 16) stem_fwd_kernel<4><<<grid, 256, 0, st>>>(x, ldx, wr, y, ldy, B, H, W, OH, OW);
-    else if (Cout == 24) stem_fwd_kernel<6><<<grid, 256, 0, st>>>(x, ldx, wr, y, ldy, B, H, W, OH, OW);
-    else stem_fwd_kernel<8><<<grid, 256, 0, st>>>(x, ldx, wr, y, ldy, B, H, W, OH, OW);
+    if (Cout == 16) launch_k(stem_fwd_kernel<4>, grid, 256, 0, st, x, ldx, wr, y, ldy, B, H, W, OH, OW);
+    else if (Cout == 24) launch_k(stem_fwd_kernel<6>, grid, 256, 0, st, x, ldx, wr, y, ldy, B, H, W, OH, OW);
+    else launch_k(stem_fwd_kernel<8>, grid, 256, 0, st, x, ldx, wr, y, ldy, B, H, W, OH, OW);
     DFINE_LAUNCH_CHECK("stem_conv_fwd");
     return 0;
 }
@@ -126,9 +128,9 @@ DFINE_API int dfine_stem_conv_wgrad(const float* dy, long ldy, const float* x, l
     long g = (P + 31) / 32;
     if (g > 148 * 4) g = 148 * 4;
     const int grid = (int)g;
-    if (Cout == 16) stem_wgrad_kernel<4><<<grid, 128, 0, st>>>(dy, ldy, x, ldx, dwr, B, H, W, OH, OW);
-    else if (Cout == 24) stem_wgrad_kernel<6><<<grid, 192, 0, st>>>(dy, ldy, x, ldx, dwr, B, H, W, OH, OW);
-    else stem_wgrad_kernel<8><<<grid, 256, 0, st>>>(dy, ldy, x, ldx, dwr, B, H, W, OH, OW);
+    if (Cout == 16) launch_k(stem_wgrad_kernel<4>, grid, 128, 0, st, dy, ldy, x, ldx, dwr, B, H, W, OH, OW);
+    else if (Cout == 24) launch_k(stem_wgrad_kernel<6>, grid, 192, 0, st, dy, ldy, x, ldx, dwr, B, H, W, OH, OW);
+    else launch_k(stem_wgrad_kernel<8>, grid, 256, 0, st, dy, ldy, x, ldx, dwr, B, H, W, OH, OW);
     DFINE_LAUNCH_CHECK("stem_conv_wgrad");
     return 0;
 }
@@ -153,6 +155,7 @@ template <int CI, int CO>
 __global__ void __launch_bounds__(C2_THREADS) conv2x2_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ wt,
                                                              float* __restrict__ y, long ldy, double* __restrict__ stats, int B,
                                                              int H, int W, int origin, int tiles_w, int tiles_h) {
+    pdl_entry();
     constexpr int PITCH = CI + 4;                       // floats per staged pixel: conflict-free float4 reads across lanes
     extern __shared__ float4 c2_smem4[];
     float* xs = reinterpret_cast<float*>(c2_smem4);                                   // [(TH+1)*(TW+1)][PITCH]
@@ -274,7 +277,7 @@ int launch_conv2x2(const float* x, long ldx, const float* wt, float* y, long ldy
     const long total = (long)B * tiles_w * tiles_h;
     const int per_sm = smem > 110 * 1024 ? 1 : (smem > 72 * 1024 ? 2 : 3);
     const long cap = 148L * per_sm;
-    conv2x2_kernel<CI, CO><<<(int)(total < cap ? total : cap), C2_THREADS, smem, st>>>(x, ldx, wt, y, ldy, stats, B, H, W, origin,
+    launch_k(conv2x2_kernel<CI, CO>, (int)(total < cap ? total : cap), C2_THREADS, smem, st, x, ldx, wt, y, ldy, stats, B, H, W, origin,
                                                                                      tiles_w, tiles_h);
     return 0;
 }

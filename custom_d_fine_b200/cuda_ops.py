@@ -348,6 +348,8 @@ def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, Y
     arr, n = taps
     # algorithmic bytes: input pixels + output pixels + weights, each touched once, fp32
     nbytes = 4 * (B * min(H * W, OH * OW * in_stride * in_stride) * Cin + B * OH * OW * Cout + Cout * n * Cin)
+    if bn_fin is not None and len(bn_fin) > 11:      # the fused normalise pass: conv output read again, y (+ residual) moved
+        nbytes += 4 * B * OH * OW * Cout * (2 + (bn_fin[13] is not None))
     with _timed("conv_tc", nbytes, 2 * B * OH * OW * Cout * n * Cin,
                 f"{what} {Cin}->{Cout} taps{n} s{in_stride} {OH}x{OW} B{B}{' planes' if bf16_planes is not None else ''}"):
         if bf16_planes is not None and w is not None:      # hybrid: tf32 hi plane + bf16 cross-term planes
@@ -358,12 +360,14 @@ def _tc_launch(x, ldx, H, W, Cin, w, w_lo, ldw, bias, y, ldy, B, OH, OW, Cout, Y
         elif bn_fin is not None:
             assert bf16_planes is not None and bf16_planes.dtype == torch.float16 and bias is None and act == 0 \
                 and lab is None and ch_scale is None and os_ == (1, 1) and oo == (0, 0) and (YH, YW) == (OH, OW)
-            cnt, bw, bb, rm, rv, mean, invstd, scale, shift, momentum, eps = bn_fin
+            cnt, bw, bb, rm, rv, mean, invstd, scale, shift, momentum, eps = bn_fin[:11]
+            y_out, ld_out, post, ld_post, lab_s, lab_b, bn_act = bn_fin[11:] if len(bn_fin) > 11 else (None, 0, None, 0, None, None, 0)
             _check(lib().dfine_conv_tc_f16x3_bn(_p(x), _p(bf16_planes), _p(y), _p(stats), _p(cnt), _p(bw), _p(bb), _p(rm),
                                                 _p(rv), _p(mean), _p(invstd), _p(scale), _p(shift), c_float(momentum),
                                                 c_float(eps), B, H, W, Cin, c_long(ldx), OH, OW, Cout, c_long(ldy),
                                                 in_stride, n, arr, c_long(bf16_planes.shape[-1]),
-                                                c_float(1.0 / _F16_WSCALE), c_long(plane_stride), _stream()), what)
+                                                c_float(1.0 / _F16_WSCALE), c_long(plane_stride), _p(y_out), c_long(ld_out),
+                                                _p(post), c_long(ld_post), _p(lab_s), _p(lab_b), bn_act, _stream()), what)
         elif bf16_planes is not None and bf16_planes.dtype == torch.float16:
             _check(lib().dfine_conv_tc_f16x3(_p(x), _p(bf16_planes), _p(bias), _p(y), _p(stats), B, H, W, Cin,
                                              c_long(ldx), OH, OW, Cout, c_long(ldy), YH, YW, os_[0], os_[1], oo[0],
@@ -472,6 +476,11 @@ def _conv_fwd(x, ldx, weight, wkey, bias, y, ldy, geom, act, stats=None, lab=Non
 
 
 _BN_FIN = os.environ.get("DFINE_BN_FIN", "1") != "0"     # train-mode BatchNorm finalize in the conv kernel's tail
+# ... and (opt-in, DFINE_BN_APPLY=1) the normalise / activation pass after a grid-wide wait.  Measured on B200 (profiles/
+# README.md): 148 CTAs cannot match the bandwidth of the standalone full-occupancy bn_apply kernel — the D-FINE-m step is
+# 2.3 ms slower with it on every layer and 0.1 ms slower restricted to conv outputs <= 32 MB — so it stays off.
+_BN_APPLY = os.environ.get("DFINE_BN_APPLY", "0") == "1"
+_BN_APPLY_MAX = int(float(os.environ.get("DFINE_BN_APPLY_MAX_MB", "1e9")) * (1 << 20))   # ... for conv outputs up to this size
 
 
 def _bn_fin_ok(geom, ldx, ldy):
@@ -711,7 +720,7 @@ class _ConvBnAct(torch.autograd.Function):
         # train-mode finalize (mean / invstd / scale / shift / running statistics) in the conv kernel's last CTA: the
         # statistics buffer carries one extra zeroed slot, the retirement ticket
         fin = need_stats and not depthwise and _bn_fin_ok(geom, ldx, Cout)
-        stats = zero_pool.take(2 * Cout + (1 if fin else 0), dev) if need_stats else None
+        stats = zero_pool.take(2 * Cout + (1 if fin else 0), dev) if need_stats else None   # (+1: ticket and flag, 2 x u32)
         if depthwise:
             assert groups == Cin == Cout and pt == pl == pb == pr, "only depthwise grouped convs are on the path"
             if ldx != Cin:
@@ -724,20 +733,6 @@ class _ConvBnAct(torch.autograd.Function):
         scale = torch.empty(Cout, device=dev, dtype=torch.float32)
         shift = torch.empty(Cout, device=dev, dtype=torch.float32)
         mean = invstd = None
-        if fin:
-            mean = torch.empty(Cout, device=dev, dtype=torch.float32)
-            invstd = torch.empty(Cout, device=dev, dtype=torch.float32)
-            _conv_fwd(x, ldx, weight, _wcache.getter(weight), None, conv_out, Cout, geom, 0, stats,
-                      bn_fin=(stats[2 * Cout:], bn_w, bn_b, running_mean, running_var, mean, invstd, scale, shift, momentum, eps))
-            fused_stats = True
-            if ctx.needs_input_grad[0]:
-                _prefetch_dgrad_weight(weight, geom, ldx, Cout)
-        elif not depthwise:
-            fused_stats = _conv_fwd(x, ldx, weight, _wcache.getter(weight), None, conv_out, Cout, geom, 0, stats)
-            if ctx.needs_input_grad[0]:
-                _prefetch_dgrad_weight(weight, geom, ldx, Cout)
-        if need_stats and not fused_stats:
-            _check(lib().dfine_bn_stats(_p(conv_out), _p(stats), c_long(M), Cout, _stream()), "bn_stats")
         if pre_add is not None:
             pre_add = pre_add.contiguous()
         ld_post = Cout
@@ -756,6 +751,24 @@ class _ConvBnAct(torch.autograd.Function):
             y, ldy_out = out.as_strided(out.shape, out.stride(), out.storage_offset()), out.stride(2)
         else:
             y, ldy_out = _alloc_nhwc(B, OH, OW, Cout, dev)
+        # ... and the normalise / activation / LAB / residual pass too: after a grid-wide wait for the finalize every CTA
+        # of the conv kernel normalises the tiles it wrote (no bn_apply launch; its reads are L2 hits)
+        fin_apply = fin and _BN_APPLY and pre_add is None and 4 * M * Cout <= _BN_APPLY_MAX
+        if fin:
+            mean = torch.empty(Cout, device=dev, dtype=torch.float32)
+            invstd = torch.empty(Cout, device=dev, dtype=torch.float32)
+            _conv_fwd(x, ldx, weight, _wcache.getter(weight), None, conv_out, Cout, geom, 0, stats,
+                      bn_fin=(stats[2 * Cout:], bn_w, bn_b, running_mean, running_var, mean, invstd, scale, shift, momentum, eps)
+                      + ((y, ldy_out, post_add, ld_post, lab_s, lab_b, ACT[act]) if fin_apply else ()))
+            fused_stats = True
+            if ctx.needs_input_grad[0]:
+                _prefetch_dgrad_weight(weight, geom, ldx, Cout)
+        elif not depthwise:
+            fused_stats = _conv_fwd(x, ldx, weight, _wcache.getter(weight), None, conv_out, Cout, geom, 0, stats)
+            if ctx.needs_input_grad[0]:
+                _prefetch_dgrad_weight(weight, geom, ldx, Cout)
+        if need_stats and not fused_stats:
+            _check(lib().dfine_bn_stats(_p(conv_out), _p(stats), c_long(M), Cout, _stream()), "bn_stats")
         # (a fused finalize+apply launch was measured SLOWER: every CTA re-derives the scale / shift table in fp64 and
         #  synchronises before its first load — 20.5 us against 12.3 + 4.8 us per layer, profiles/README.md)
         if fin:
@@ -769,10 +782,11 @@ class _ConvBnAct(torch.autograd.Function):
         else:
             _check(lib().dfine_bn_fold(_p(bn_w), _p(bn_b), _p(running_mean), _p(running_var), _p(scale), _p(shift),
                                        Cout, c_float(eps), _stream()), "bn_fold")
-        with _timed("bn_apply", 4 * M * Cout * (2 + (pre_add is not None) + (post_add is not None)), 0, f"bn_apply M{M} C{Cout}"):
-            _check(lib().dfine_bn_apply(_p(conv_out), _p(scale), _p(shift), _p(pre_add), _p(post_add), _p(lab_s),
-                                        _p(lab_b), _p(y), c_long(M), Cout, ACT[act], c_long(ldy_out), c_long(ld_post), _stream()),
-                   "bn_apply")
+        if not fin_apply:
+            with _timed("bn_apply", 4 * M * Cout * (2 + (pre_add is not None) + (post_add is not None)), 0, f"bn_apply M{M} C{Cout}"):
+                _check(lib().dfine_bn_apply(_p(conv_out), _p(scale), _p(shift), _p(pre_add), _p(post_add), _p(lab_s),
+                                            _p(lab_b), _p(y), c_long(M), Cout, ACT[act], c_long(ldy_out), c_long(ld_post), _stream()),
+                       "bn_apply")
         ctx.save_for_backward(x, weight, conv_out, scale, shift, mean, invstd, pre_add, lab_s, lab_b, bn_w)
         ctx.geom, ctx.ldx, ctx.cfg = geom, ldx, cfg
         ctx.has_post = post_add is not None
