@@ -7,6 +7,7 @@ reference's ``Trainer`` / ``main`` names.
 from __future__ import annotations
 
 import math
+import os
 from copy import deepcopy
 
 import torch
@@ -248,7 +249,9 @@ class TrainStep:
 
     def _comm_stream(self, device):
         if getattr(self, "_comm", None) is None:
-            self._comm = torch.cuda.Stream(device)
+            # (same priority as the step's stream, above the weight-gradient stream: the all-reduce must not queue behind
+            #  weight-gradient CTAs)
+            self._comm = torch.cuda.Stream(device, priority=-1 if os.environ.get("DFINE_STREAM_PRIO", "1") != "0" else 0)
         return self._comm
 
     def _backward_half2(self, cut):
@@ -319,7 +322,11 @@ class GraphedTrainStep(TrainStep):
         self._static, self._static_seen = OrderedDict(), {}      # backbone + encoder graphs per input shape (hybrid steps)
         # Warm-up steps and captures share ONE side stream: autograd's AccumulateGrad nodes remember the stream
         # they were created on, and a node created on the legacy default stream cannot be used under capture.
-        self._side = torch.cuda.Stream() if next(self.model.parameters()).is_cuda else None
+        # ... at a HIGHER priority than the weight-gradient stream (kernel nodes keep their capture stream's priority):
+        # when SMs free up, the critical chain of data gradients is scheduled ahead of the queued weight-gradient CTAs
+        # instead of waiting behind them.  DFINE_STREAM_PRIO=0: equal priorities.
+        prio = -1 if os.environ.get("DFINE_STREAM_PRIO", "1") != "0" else 0
+        self._side = torch.cuda.Stream(priority=prio) if next(self.model.parameters()).is_cuda else None
 
     def host_gap_ms(self):
         """Device idle time between graph A and graph B of the last replayed step (host index planning)."""
