@@ -254,6 +254,7 @@ struct FwdParams {
     long ldres;               // pixel stride ldres): fuses the gradient-accumulation add of a multi-consumer tensor
     const float* ch_scale;    // optional per-channel scale applied before the bias (tc_fwd_ts only): a frozen / eval-mode
                               // BatchNorm folded into the epilogue, y = act(acc * scale[c] + bias[c])
+    unsigned long long* trace;   // bring-up: per-CTA phase timestamps (globaltimer ns), 16 slots per CTA (dfine_tc_trace)
     // Train-mode BatchNorm finalize in the kernel's tail (tc_fwd_ts only; fin_counter != null): the CTA that retires last
     // (ticket on fin_counter, zeroed by the caller with `stats`) turns the complete per-channel sums into mean / invstd /
     // scale / shift and updates the running statistics — bn_finalize_kernel's arithmetic without its launch.
@@ -1210,6 +1211,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                  : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void trace_mark(unsigned long long* trace, int slot) {
+    if (trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        trace[(size_t)blockIdx.x * 16 + slot] = t;
+    }
+}
 template <int BN, int STAGES>
 struct TsSmem {
     static constexpr int B_PLANE = BN * BK * 2;
@@ -1240,6 +1248,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
     const int num_k = p.n_taps * cblocks;
     constexpr uint32_t TMEM_COLS = 512;
     constexpr uint32_t A_COL0 = 2 * BN;
+    if (threadIdx.x == 0) trace_mark(p.trace, 0);
 
     if (stats)
         for (int i = threadIdx.x; i < 4 * 2 * BN; i += blockDim.x) (&sm.statw[0][0])[i] = 0;
@@ -1258,7 +1267,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    if (threadIdx.x == 0) trace_mark(p.trace, 1);
     pdl_entry();      // barriers / tensor memory / descriptor prefetch above overlap the previous kernel's tail
+    if (threadIdx.x == 0) trace_mark(p.trace, 2);
 
     if (warp == 0) {
         // TMA producer: the whole warp walks (tile, tap, channel block) with warp-uniform values, one elected lane issues
@@ -1277,6 +1288,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
                         mbar_expect_tx(&sm.full[s], tx_bytes);
                         tma_load_4d(sm.a[s], &map_x, &sm.full[s], c0, xw, xh, img);
                         tma_load_3d(sm.b[s], &map_w, &sm.full[s], wk + c0, wn, 0);
+                        if (g == 0) trace_mark(p.trace, 3);
                         sm.produced = ++g;
                     } else {
                         ++g;
@@ -1298,6 +1310,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
             const uint32_t d = tmem + acc * BN;
             for (int kb = 0; kb < num_k; ++kb) {
                 mbar_wait(&sm.conv[s], ph);          // planes of this stage are in TMEM (and, before that, the weights landed)
+                if (i == 0 && kb == 0 && lane == 0) trace_mark(p.trace, 5);
                 tc_fence_after();
                 const uint32_t ah = tmem + A_COL0 + s * 32u, al = ah + 16u;
                 const uint64_t bh = make_desc(smem_u32(sm.b[s]), 16, 512, 4);
@@ -1341,16 +1354,20 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
                 row_off[r8] = ((long)img * p.YH + (long)oh * p.osy + p.ooy) * p.YW + (long)ow * p.osx + p.oox;
             }
             mbar_wait(&sm.tfull[acc], aph);
+            if (i == 0 && warp == 2 && lane == 0) trace_mark(p.trace, 6);
             tc_fence_after();
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 if (n0 + c0 >= p.N) break;
                 uint32_t v[32];
                 tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + acc * BN + (uint32_t)c0, v);
+                const bool tr = p.trace && i == 0 && c0 == 0 && warp == 2 && lane == 0;
+                if (tr) trace_mark(p.trace, 12);
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4)
                     sts128(wbase + (uint32_t)(lane * EPL + 4 * c4) * 4u, __uint_as_float(v[4 * c4]),
                            __uint_as_float(v[4 * c4 + 1]), __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
                 __syncwarp();
+                if (tr) trace_mark(p.trace, 13);
                 const int col = n0 + c0 + 4 * (lane % 8);
                 const bool col_ok = col < p.N;
                 float4 bv = make_float4(0, 0, 0, 0), sv = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -1378,6 +1395,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
                         *reinterpret_cast<float4*>(y + row_off[r8] * p.ldy + col) = o;
                     }
                 }
+                if (tr) trace_mark(p.trace, 14);
                 if (stats) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -1398,10 +1416,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
                     }
                 }
                 __syncwarp();
+                if (tr) trace_mark(p.trace, 15);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.tempty[acc]);
+            if (warp == 2 && lane == 0) trace_mark(p.trace, i == 0 ? 7 : 8);
         }
     } else if (warp == 6 + TS_CONV_WARPS) {
         if (p.prefetch > 0) {          // L2 prefetch warp (see tc_fwd_persist)
@@ -1452,6 +1472,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
         for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
             for (int kb = 0; kb < num_k; ++kb) {
                 mbar_wait(&sm.full[s], ph);
+                if (pending < 0 && warp == 6 && lane == 0) trace_mark(p.trace, 4);
                 const uint32_t a_row = smem_u32(sm.a[s]) + row_off;
                 float4 x[4];
 #pragma unroll
@@ -1492,6 +1513,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) trace_mark(p.trace, 9);
     if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
     if (stats && (gridDim.x % ts.n_tiles) == 0) {
         const int n0_cta = (int)(blockIdx.x % ts.n_tiles) * BN;       // the one N tile this CTA worked on
@@ -1501,6 +1523,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
             if (c < p.N && v != 0.0) atomicAdd(stats + (long)which * p.N + c, v);
         }
     }
+    if (threadIdx.x == 0) trace_mark(p.trace, 10);
     if (stats && p.fin_counter) {
         // last-CTA finalize: every thread's statistics atomics are ordered before the CTA's ticket (fence + barrier);
         // the CTA drawing the last ticket sees all of them (fence after the ticket, L2 loads)
@@ -1514,6 +1537,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_fwd_ts(const __grid_constant
                 bn_finalize_channel(__ldcg(stats + c), __ldcg(stats + p.N + c), c, p.fin_w, p.fin_b, p.fin_rmean, p.fin_rvar,
                                     p.fin_mean, p.fin_invstd, p.fin_scale, p.fin_shift, p.fin_M, p.fin_momentum, p.fin_eps);
         }
+        if (threadIdx.x == 0) trace_mark(p.trace, 11);
         if (p.fin_y) {
             unsigned int* flag = p.fin_counter + 1;
             if (sm.last_cta) {
@@ -2317,6 +2341,17 @@ DFINE_API int dfine_conv_tc_supported(int Cin, int Cout, int KH, int KW, int str
 // zeroed by the caller) receives per-channel sum / sum of squares of the raw accumulator (train-mode BatchNorm).
 // w_lo == null: plain kind::tf32.  w_lo != null: 3xTF32 — `w` must then hold tf32-rounded weights and w_lo the
 // remainders (dfine_tf32_split); activations are split inside the kernel.  nn.Linear on [rows, K]: B=1, H=1, W=rows.
+// Bring-up / profiling: when `buf` is non-null every tc_fwd_ts launch (the 3xFP16 forward kernel) writes per-CTA phase
+// timestamps (globaltimer, ns) to buf[cta * 16 + slot]; slots: 0 entry, 1 prologue done, 2 dependency wait done,
+// 3 first TMA issued, 4 first tile landed (converter), 5 first planes converted (MMA issuer), 6 first accumulator ready,
+// 7 first tile stored, 8 last tile stored, 9 all roles done, 10 statistics flushed, 11 finalize done.  buf must hold
+// 16 * grid unsigned 64-bit words; null switches the trace off.  (tools/trace_conv.py)
+static unsigned long long* g_tc_trace = nullptr;
+DFINE_API int dfine_tc_trace(unsigned long long* buf) {
+    g_tc_trace = buf;
+    return 0;
+}
+
 namespace {
 struct BnFinArgs {      // the fused train-mode BatchNorm finalize (FwdParams::fin_*)
     unsigned int* counter;
@@ -2364,6 +2399,7 @@ int conv_tc_impl(const float* x, const float* w, const float* w_lo, const void* 
     p.lab = lab; p.lab_s = lab_s; p.lab_b = lab_b;
     p.w_row_off = w_row_off; p.w_k_off = w_k_off;
     p.ch_scale = ch_scale;
+    p.trace = g_tc_trace;
     p.fin_counter = nullptr;
     if (fin) {
         DFINE_REQUIRE(stats && fin->counter && fin->mean && fin->invstd && fin->scale && fin->shift && half16 && w_bf16 && !w,
