@@ -249,9 +249,11 @@ class TrainStep:
 
     def _comm_stream(self, device):
         if getattr(self, "_comm", None) is None:
-            # (same priority as the step's stream, above the weight-gradient stream: the all-reduce must not queue behind
-            #  weight-gradient CTAs)
-            self._comm = torch.cuda.Stream(device, priority=-1 if os.environ.get("DFINE_STREAM_PRIO", "1") != "0" else 0)
+            # (above the step's stream, which is above the weight-gradient stream: the all-reduce kernels get their few SMs
+            #  as soon as they are launched instead of queueing behind compute CTAs — 2 GPUs, same box: 36.24 ms per step
+            #  against 36.56 at the step stream's priority and 36.48 at the weight-gradient stream's)
+            prio = -2 if os.environ.get("DFINE_STREAM_PRIO", "1") != "0" else 0
+            self._comm = torch.cuda.Stream(device, priority=int(os.environ.get("DFINE_COMM_PRIO", prio)))
         return self._comm
 
     def _backward_half2(self, cut):
