@@ -132,6 +132,24 @@ def test_go_union_fast_paths_equal_the_reference_formulation():
         plan = IndexPlan([T], Q, S, None, 0)
         (hq, ht), = DFINECriterion.go_indices_host(oq, ot, plan)
         assert want[0] == hq.tolist() and want[1] == ht.tolist()
+    # whole-batch pass (ragged sizes, an image without targets, an image with more targets than queries) == image by image
+    for _ in range(100):
+        Q, S = int(rng.integers(4, 24)), int(rng.integers(1, 7))
+        sizes = [int(rng.integers(0, 30)) for _ in range(int(rng.integers(1, 7)))] + [0]
+        rng.shuffle(sizes)
+        plan = IndexPlan(sizes, Q, S, None, 0)
+        oq, ot = np.zeros((S, sum(sizes)), np.int64), np.zeros((S, sum(sizes)), np.int64)
+        for b, (T, n) in enumerate(zip(sizes, plan.per_img)):
+            o = int(plan.offs[b])
+            for k in range(S):
+                oq[k, o:o + n] = np.sort(rng.choice(Q, n, replace=False))
+                ot[k, o:o + n] = rng.permutation(T)[:n]
+        got = DFINECriterion.go_indices_host(oq, ot, plan)
+        for b, n in enumerate(plan.per_img):
+            o = int(plan.offs[b])
+            q, t = torch.from_numpy(oq[:, o:o + n].reshape(-1)), torch.from_numpy(ot[:, o:o + n].reshape(-1))
+            want = DFINECriterion._go_union(q, t) if n else (torch.zeros(0), torch.zeros(0))
+            assert want[0].tolist() == got[b][0].tolist() and want[1].tolist() == got[b][1].tolist()
     # table filling: vectorised path == per-image path
     B, S, T, Q = 5, 6, 7, 300
     oq = np.stack([np.concatenate([np.sort(rng.choice(Q, T, replace=False)) for _ in range(B)]) for _ in range(S)])
