@@ -62,6 +62,24 @@ static inline bool pdl_enabled() {
     static const bool on = [] { const char* e = getenv("DFINE_PDL"); return !(e && e[0] == '0'); }();
     return on;
 }
+// Grid of a grid-strided elementwise kernel: enough CTAs for n work items, capped at TWO FULL WAVES of what is resident
+// with this kernel's registers / shared memory (occupancy x SM count).  Every CTA of a capped grid does the same amount of
+// work, so a cap that is not a multiple of the resident count leaves the last round partly empty: the old fixed cap of
+// 148 x 16 CTAs cost the 46-register BatchNorm-backward kernel (5 CTAs per SM) a fourth round for 3.2 rounds of work.
+template <typename K>
+static inline int ew_grid_k(K kernel, long n, int block, size_t smem) {
+    int occ = 0, dev = 0, sms = 148;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem) != cudaSuccess || occ < 1) occ = 1;
+    static int sm_cache[64] = {0};
+    cudaGetDevice(&dev);
+    if (sm_cache[dev & 63] == 0 &&
+        (cudaDeviceGetAttribute(&sm_cache[dev & 63], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_cache[dev & 63] <= 0))
+        sm_cache[dev & 63] = 148;
+    sms = sm_cache[dev & 63];
+    const long g = (n + block - 1) / block, cap = 2L * occ * sms;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                    Args&&... args) {

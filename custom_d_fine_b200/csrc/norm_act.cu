@@ -111,10 +111,19 @@ __global__ void __launch_bounds__(NT) bn_apply_kernel(const float* __restrict__ 
     }
 }
 
+// Register budget of the reduce kernel: four rows in flight per thread cost 97 registers = 2 CTAs per SM, and the
+// 4-CTAs-per-SM grid of pick_rows_per_cta then ran in TWO half-occupied waves (ncu: 12-25 % warps active).  Two rows per
+// thread fit 64 registers: four resident CTAs per SM, the grid is one wave.
+#ifndef BN_RED_UNROLL
+#define BN_RED_UNROLL 2
+#endif
+#ifndef BN_RED_CTAS
+#define BN_RED_CTAS 4
+#endif
 // Backward pass 1: per-channel sums of dz and dz*xhat (double), LAB scalar grads.
 //   dz = dy * lab_s * act'(z),  z = x*scale+shift (+pre_add),  xhat = (x-mean)*invstd
 // red[0:C] += sum dz ; red[C:2C] += sum dz*xhat ; red[2C] += sum dy*act(z) ; red[2C+1] += sum dy
-__global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(
+__global__ void __launch_bounds__(NT, BN_RED_CTAS) bn_bwd_reduce_kernel(
     const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ scale,
     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ pre_add, const float* __restrict__ lab, double* __restrict__ red, long M, int C,
@@ -150,15 +159,16 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(
                 q.z += dz.z * (v.z - mu.z) * is.z; q.w += dz.w * (v.w - mu.w) * is.w;
             };
             long r = r0 + lane_r;
-            for (; r + 3L * m.RPP < r1; r += 4L * m.RPP) {
-                float4 g[4], v[4];
+            constexpr int U = BN_RED_UNROLL;
+            for (; r + (long)(U - 1) * m.RPP < r1; r += (long)U * m.RPP) {
+                float4 g[U], v[U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < U; ++u) {
                     g[u] = ld4(dy + (r + (long)u * m.RPP) * ld_dy + c);
                     v[u] = ld4(x + (r + (long)u * m.RPP) * C + c);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) body(g[u], v[u], (r + (long)u * m.RPP) * C + c);
+                for (int u = 0; u < U; ++u) body(g[u], v[u], (r + (long)u * m.RPP) * C + c);
             }
             for (; r < r1; r += m.RPP) body(ld4(dy + r * ld_dy + c), ld4(x + r * C + c), r * C + c);
             st4(mine + c, s);
@@ -204,7 +214,7 @@ __global__ void __launch_bounds__(NT) frozen_bn_bwd_kernel(const float* __restri
 
 // Backward pass 2.  training: dx = scale*(dz - sum_dz/M - xhat*sum_dzx/M) ; else dx = scale*dz.
 // Optionally also writes dz (= gradient of pre_add).
-__global__ void __launch_bounds__(NT) bn_bwd_apply_kernel(
+__global__ void __launch_bounds__(NT, 8) bn_bwd_apply_kernel(
     const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ scale,
     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ pre_add, const float* __restrict__ lab, const double* __restrict__ red,
@@ -385,12 +395,6 @@ inline long pick_rows_per_cta(long M, int C) {
     if (rpc < m.RPP * 8) rpc = m.RPP * 8;
     return rpc;
 }
-inline int ew_grid(long n4) {
-    long g = (n4 + NT - 1) / NT;
-    const long cap = 148L * 16;
-    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
-}
-
 }  // namespace
 
 // stats: double [2*C], zero-initialised by the caller.
@@ -432,7 +436,7 @@ DFINE_API int dfine_bn_apply(const float* x, const float* scale, const float* sh
                   "bn_apply: post_add row stride %ld", ld_post);
     const long n4 = M * C / 4;
     if (n4 == 0) return 0;
-    launch_k(bn_apply_kernel, ew_grid(n4), NT, 0, (cudaStream_t)stream, x, scale, shift, pre_add, post_add, lab, lab_b, y,
+    launch_k(bn_apply_kernel, ew_grid_k(bn_apply_kernel, n4, NT, 0), NT, 0, (cudaStream_t)stream, x, scale, shift, pre_add, post_add, lab, lab_b, y,
                                                                  n4, C / 4, act, ldy, post_add ? ld_post : (long)C);
     DFINE_LAUNCH_CHECK("bn_apply");
     return 0;
@@ -466,7 +470,7 @@ DFINE_API int dfine_bn_bwd_apply(const float* dy, const float* x, const float* s
                   "bn_bwd_apply: gradient outputs come in pairs");
     const long n4 = M * C / 4;
     if (n4 == 0) return 0;
-    launch_k(bn_bwd_apply_kernel, ew_grid(n4), NT, 2 * C * sizeof(float), (cudaStream_t)stream, dy, x, scale, shift, mean, invstd, pre_add, lab,
+    launch_k(bn_bwd_apply_kernel, ew_grid_k(bn_bwd_apply_kernel, n4, NT, 2 * C * sizeof(float)), NT, 2 * C * sizeof(float), (cudaStream_t)stream, dy, x, scale, shift, mean, invstd, pre_add, lab,
                                                                      red, dx, dpre, n4, C / 4, M, act, training, g_w,
                                                                      g_b, g_lab_s, g_lab_b, ld_dy, ld_dx);
     DFINE_LAUNCH_CHECK("bn_bwd_apply");
@@ -483,7 +487,7 @@ DFINE_API int dfine_frozen_bn_bwd(const float* dy, const float* y, const float* 
                   "frozen_bn_bwd: strides / alignment");
     const long n4 = M * C / 4;
     if (n4 == 0) return 0;
-    launch_k(frozen_bn_bwd_kernel, ew_grid(n4), NT, 0, (cudaStream_t)stream, dy, y, scale, dx, n4, C / 4, act == 1, ld_dy, ld_y, ld_dx);
+    launch_k(frozen_bn_bwd_kernel, ew_grid_k(frozen_bn_bwd_kernel, n4, NT, 0), NT, 0, (cudaStream_t)stream, dy, y, scale, dx, n4, C / 4, act == 1, ld_dy, ld_y, ld_dx);
     DFINE_LAUNCH_CHECK("frozen_bn_bwd");
     return 0;
 }
@@ -546,14 +550,14 @@ __global__ void __launch_bounds__(NT) act_bwd_kernel(const float* __restrict__ d
 DFINE_API int dfine_act_fwd(const float* z, float* y, long n, int act, void* stream) {
     DFINE_REQUIRE(n % 4 == 0, "act_fwd: n=%ld must be a multiple of 4", n);
     if (n == 0) return 0;
-    launch_k(act_fwd_kernel, ew_grid(n / 4), NT, 0, (cudaStream_t)stream, z, y, n / 4, act);
+    launch_k(act_fwd_kernel, ew_grid_k(act_fwd_kernel, n / 4, NT, 0), NT, 0, (cudaStream_t)stream, z, y, n / 4, act);
     DFINE_LAUNCH_CHECK("act_fwd");
     return 0;
 }
 DFINE_API int dfine_act_bwd(const float* dy, const float* z, float* dz, long n, int act, void* stream) {
     DFINE_REQUIRE(n % 4 == 0, "act_bwd: n=%ld must be a multiple of 4", n);
     if (n == 0) return 0;
-    launch_k(act_bwd_kernel, ew_grid(n / 4), NT, 0, (cudaStream_t)stream, dy, z, dz, n / 4, act);
+    launch_k(act_bwd_kernel, ew_grid_k(act_bwd_kernel, n / 4, NT, 0), NT, 0, (cudaStream_t)stream, dy, z, dz, n / 4, act);
     DFINE_LAUNCH_CHECK("act_bwd");
     return 0;
 }

@@ -488,11 +488,6 @@ __global__ void __launch_bounds__(256) mask_loss_pm_bwd_kernel(const float* __re
     }
 }
 
-int ew_grid(long n) {
-    long g = (n + 255) / 256;
-    return (int)(g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g));
-}
-
 }  // namespace
 
 // GroupNorm forward over an NHWC tensor x [B,HW,C]: y = (x - mean_g) * rstd_g * gamma + beta (+ReLU).  stats: caller-zeroed
@@ -509,7 +504,7 @@ DFINE_API int dfine_groupnorm_fwd(const float* x, const float* gamma, const floa
     if (chunks > 148 * 4 / (B > 0 ? B : 1) + 1) chunks = 148 * 4 / B + 1;
     launch_k(gn_stats_kernel, dim3(chunks, B), 256, 2 * G * sizeof(double), st, x, stats, HW, C, G);
     launch_k(gn_finalize_kernel, ceil_div((long)B * G, 128), 128, 0, st, stats, mean, rstd, B * G, (double)HW * (C / G), eps);
-    launch_k(gn_apply_kernel, ew_grid((long)B * HW * (C / 4)), 256, 0, st, x, mean, rstd, gamma, beta, y, HW, C, G, B, relu);
+    launch_k(gn_apply_kernel, ew_grid_k(gn_apply_kernel, (long)B * HW * (C / 4), 256, 0), 256, 0, st, x, mean, rstd, gamma, beta, y, HW, C, G, B, relu);
     DFINE_LAUNCH_CHECK("groupnorm_fwd");
     return 0;
 }
@@ -526,7 +521,7 @@ DFINE_API int dfine_groupnorm_bwd(const float* dy, const float* x, const float* 
     if (chunks > 148 * 4 / (B > 0 ? B : 1) + 1) chunks = 148 * 4 / B + 1;
     launch_k(gn_bwd_reduce_kernel, dim3(chunks, B), 256, 2 * G * sizeof(double), st, dy, x, mean, rstd, gamma, beta, red, dgamma,
                                                                                dbeta, HW, C, G, relu);
-    launch_k(gn_bwd_apply_kernel, ew_grid((long)B * HW * (C / 4)), 256, 0, st, dy, x, mean, rstd, gamma, beta, red, dx, HW, C, G, B,
+    launch_k(gn_bwd_apply_kernel, ew_grid_k(gn_bwd_apply_kernel, (long)B * HW * (C / 4), 256, 0), 256, 0, st, dy, x, mean, rstd, gamma, beta, red, dx, HW, C, G, B,
                                                                          relu, 1.0 / ((double)HW * (C / G)));
     DFINE_LAUNCH_CHECK("groupnorm_bwd");
     return 0;
@@ -601,7 +596,7 @@ DFINE_API int dfine_mask_loss_pm_bwd(const float* pred, const float* gt, const l
 DFINE_API int dfine_resize_bilinear_bwd(const float* dy, float* dx, int B, int Hs, int Ws, int H, int W, int C, void* stream) {
     DFINE_REQUIRE(B >= 0 && Hs > 0 && Ws > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "resize_bilinear_bwd: bad dims (C %% 4)");
     if (B == 0) return 0;
-    launch_k(resize_bwd_kernel, ew_grid((long)B * Hs * Ws * (C / 4)), 256, 0, (cudaStream_t)stream, dy, dx, B, Hs, Ws, H, W, C);
+    launch_k(resize_bwd_kernel, ew_grid_k(resize_bwd_kernel, (long)B * Hs * Ws * (C / 4), 256, 0), 256, 0, (cudaStream_t)stream, dy, dx, B, Hs, Ws, H, W, C);
     DFINE_LAUNCH_CHECK("resize_bilinear_bwd");
     return 0;
 }

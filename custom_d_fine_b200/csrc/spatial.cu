@@ -425,12 +425,6 @@ __global__ void __launch_bounds__(NT) upsample2x_bwd_kernel(const float* __restr
     }
 }
 
-inline int ew_grid(long n) {
-    long g = (n + NT - 1) / NT;
-    const long cap = 148L * 16;
-    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
-}
-
 }  // namespace
 
 // x [B,H,W,C], w [k*k,C] tap-major, y [B,OH,OW,C]; symmetric padding `pad`.
@@ -443,13 +437,13 @@ DFINE_API int dfine_dwconv_fwd(const float* x, const float* w, float* y, int B, 
     const long blocked = (long)B * OH * ((OW + PX - 1) / PX) * (C / 4);
     cudaStream_t st = (cudaStream_t)stream;
     if (k == 5 && stride == 1)
-        launch_k(dwconv_fwd_blocked<5, 1>, ew_grid(blocked), NT, 0, st, x, w, y, B, H, W, C, OH, OW, pad);
+        launch_k(dwconv_fwd_blocked<5, 1>, ew_grid_k(dwconv_fwd_blocked<5, 1>, blocked, NT, 0), NT, 0, st, x, w, y, B, H, W, C, OH, OW, pad);
     else if (k == 3 && stride == 2)
-        launch_k(dwconv_fwd_blocked<3, 2>, ew_grid(blocked), NT, 0, st, x, w, y, B, H, W, C, OH, OW, pad);
+        launch_k(dwconv_fwd_blocked<3, 2>, ew_grid_k(dwconv_fwd_blocked<3, 2>, blocked, NT, 0), NT, 0, st, x, w, y, B, H, W, C, OH, OW, pad);
     else if (k == 3 && stride == 1)
-        launch_k(dwconv_fwd_blocked<3, 1>, ew_grid(blocked), NT, 0, st, x, w, y, B, H, W, C, OH, OW, pad);
+        launch_k(dwconv_fwd_blocked<3, 1>, ew_grid_k(dwconv_fwd_blocked<3, 1>, blocked, NT, 0), NT, 0, st, x, w, y, B, H, W, C, OH, OW, pad);
     else
-        launch_k(dwconv_fwd_kernel, ew_grid(total), NT, 0, st, x, w, y, B, H, W, C, OH, OW, k, stride, pad);
+        launch_k(dwconv_fwd_kernel, ew_grid_k(dwconv_fwd_kernel, total, NT, 0), NT, 0, st, x, w, y, B, H, W, C, OH, OW, k, stride, pad);
     DFINE_LAUNCH_CHECK("dwconv_fwd");
     return 0;
 }
@@ -463,14 +457,14 @@ DFINE_API int dfine_dwconv_bwd_data(const float* dy, const float* w, float* dx, 
     const long blocked = (long)B * H * ((W + PX - 1) / PX) * (C / 4);
     cudaStream_t st = (cudaStream_t)stream;
     if (k == 5 && stride == 1)
-        launch_k(dwconv_bwd_data_blocked<5>, ew_grid(blocked), NT, 0, st, dy, w, dx, B, H, W, C, OH, OW, pad);
+        launch_k(dwconv_bwd_data_blocked<5>, ew_grid_k(dwconv_bwd_data_blocked<5>, blocked, NT, 0), NT, 0, st, dy, w, dx, B, H, W, C, OH, OW, pad);
     else if (k == 3 && stride == 1)
-        launch_k(dwconv_bwd_data_blocked<3>, ew_grid(blocked), NT, 0, st, dy, w, dx, B, H, W, C, OH, OW, pad);
+        launch_k(dwconv_bwd_data_blocked<3>, ew_grid_k(dwconv_bwd_data_blocked<3>, blocked, NT, 0), NT, 0, st, dy, w, dx, B, H, W, C, OH, OW, pad);
     else if (k == 3 && stride == 2 && pad == 1)
-        launch_k(dwconv3x3s2_bwd_data_kernel, ew_grid((long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4)), NT, 0, st, 
+        launch_k(dwconv3x3s2_bwd_data_kernel, ew_grid_k(dwconv3x3s2_bwd_data_kernel, (long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4), NT, 0), NT, 0, st, 
             dy, w, dx, B, H, W, C, OH, OW);
     else
-        launch_k(dwconv_bwd_data_kernel, ew_grid(total), NT, 0, st, dy, w, dx, B, H, W, C, OH, OW, k, stride, pad);
+        launch_k(dwconv_bwd_data_kernel, ew_grid_k(dwconv_bwd_data_kernel, total, NT, 0), NT, 0, st, dy, w, dx, B, H, W, C, OH, OW, k, stride, pad);
     DFINE_LAUNCH_CHECK("dwconv_bwd_data");
     return 0;
 }
@@ -516,9 +510,9 @@ DFINE_API int dfine_maxpool2x2_fwd(const float* x, long ldx, float* y, int B, in
     if (total == 0) return 0;
     DFINE_REQUIRE(ldx == C || (C % 4 == 0 && ldx % 4 == 0 && ldx > C), "maxpool_fwd: pixel stride %ld", ldx);
     if (C % 4 == 0)
-        launch_k(maxpool_fwd4_kernel, ew_grid(total / 4), NT, 0, (cudaStream_t)stream, x, y, B, H, W, C / 4, ldx);
+        launch_k(maxpool_fwd4_kernel, ew_grid_k(maxpool_fwd4_kernel, total / 4, NT, 0), NT, 0, (cudaStream_t)stream, x, y, B, H, W, C / 4, ldx);
     else
-        launch_k(maxpool_fwd_kernel, ew_grid(total), NT, 0, (cudaStream_t)stream, x, y, B, H, W, C);
+        launch_k(maxpool_fwd_kernel, ew_grid_k(maxpool_fwd_kernel, total, NT, 0), NT, 0, (cudaStream_t)stream, x, y, B, H, W, C);
     DFINE_LAUNCH_CHECK("maxpool_fwd");
     return 0;
 }
@@ -528,9 +522,9 @@ DFINE_API int dfine_maxpool2x2_bwd(const float* x, long ldx, const float* dy, fl
     if (total == 0) return 0;
     DFINE_REQUIRE(ldx == C || (C % 4 == 0 && ldx % 4 == 0 && ldx > C), "maxpool_bwd: pixel stride %ld", ldx);
     if (C % 4 == 0)
-        launch_k(maxpool_bwd4_kernel, ew_grid(total / 4), NT, 0, (cudaStream_t)stream, x, dy, dx, B, H, W, C / 4, ldx);
+        launch_k(maxpool_bwd4_kernel, ew_grid_k(maxpool_bwd4_kernel, total / 4, NT, 0), NT, 0, (cudaStream_t)stream, x, dy, dx, B, H, W, C / 4, ldx);
     else
-        launch_k(maxpool_bwd_kernel, ew_grid(total), NT, 0, (cudaStream_t)stream, x, dy, dx, B, H, W, C);
+        launch_k(maxpool_bwd_kernel, ew_grid_k(maxpool_bwd_kernel, total, NT, 0), NT, 0, (cudaStream_t)stream, x, dy, dx, B, H, W, C);
     DFINE_LAUNCH_CHECK("maxpool_bwd");
     return 0;
 }
@@ -538,7 +532,7 @@ DFINE_API int dfine_upsample2x_fwd(const float* x, float* y, int B, int H, int W
     DFINE_REQUIRE(C % 4 == 0, "upsample2x: C=%d", C);
     const long total = (long)B * 4 * H * W * (C / 4);
     if (total == 0) return 0;
-    launch_k(upsample2x_fwd_kernel, ew_grid(total), NT, 0, (cudaStream_t)stream, x, y, B, H, W, C / 4);
+    launch_k(upsample2x_fwd_kernel, ew_grid_k(upsample2x_fwd_kernel, total, NT, 0), NT, 0, (cudaStream_t)stream, x, y, B, H, W, C / 4);
     DFINE_LAUNCH_CHECK("upsample2x_fwd");
     return 0;
 }
@@ -546,7 +540,7 @@ DFINE_API int dfine_upsample2x_bwd(const float* dy, float* dx, int B, int H, int
     DFINE_REQUIRE(C % 4 == 0, "upsample2x: C=%d", C);
     const long total = (long)B * H * W * (C / 4);
     if (total == 0) return 0;
-    launch_k(upsample2x_bwd_kernel, ew_grid(total), NT, 0, (cudaStream_t)stream, dy, dx, B, H, W, C / 4);
+    launch_k(upsample2x_bwd_kernel, ew_grid_k(upsample2x_bwd_kernel, total, NT, 0), NT, 0, (cudaStream_t)stream, dy, dx, B, H, W, C / 4);
     DFINE_LAUNCH_CHECK("upsample2x_bwd");
     return 0;
 }
