@@ -283,3 +283,79 @@ def test_tc_matches_simt(cuda_ops, case):
         check_close(f"{mode} fused stats sumsq", stats[Cout:].float(), (y0.reshape(M, Cout) ** 2).sum(0), max(tol, 1e-4))
         check_close(f"{mode} dgrad {case}", dx, dx0, TF32)
         check_close(f"{mode} wgrad {case}", dw, dw0, TF32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 40, 40, 160, 48, 1, "relu", True, True), (2, 20, 20, 128, 128, 3, "silu", False, False),
+                                   (1, 23, 37, 128, 256, 1, None, False, True)],
+                         ids=["pw1x1_lab_post", "c3x3_silu", "odd_256"])
+def test_bn_finalize_in_conv_tail_equals_separate_launches(cuda_ops, shape):
+    """Train-mode conv + BatchNorm: the finalize in the conv kernel's last CTA (default), the opt-in in-kernel apply pass
+    behind a grid-wide wait and the separate bn_finalize / bn_apply launches are the SAME arithmetic on the same
+    statistics — outputs, saved statistics (through the backward pass) and running statistics must agree to rounding."""
+    from custom_d_fine_b200 import cuda_ops as co
+    B, H, W, Cin, Cout, k, act, lab, post = shape
+    g = _g(11)
+    dev = torch.device("cuda", 0)
+    x = torch.randn(B, H, W, Cin, generator=g).to(dev)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(k * k * Cin)).to(dev)
+    bw, bb = (torch.rand(Cout, generator=g) + 0.5).to(dev), (torch.randn(Cout, generator=g) * 0.1).to(dev)
+    ls = torch.tensor([1.3], device=dev) if lab else None
+    lb = torch.tensor([-0.2], device=dev) if lab else None
+    p2 = torch.randn(B, H, W, Cout, generator=g).to(dev) if post else None
+    dy = torch.randn(B, H, W, Cout, generator=g).to(dev)
+    pad = ((k - 1) // 2,) * 4
+
+    def run(fin, apply_):
+        old = co._BN_FIN, co._BN_APPLY
+        co._BN_FIN, co._BN_APPLY = fin, apply_
+        try:
+            xs, ws = x.clone().requires_grad_(), w.clone().requires_grad_()
+            bws, bbs = bw.clone().requires_grad_(), bb.clone().requires_grad_()
+            rm, rv = torch.zeros(Cout, device=dev), torch.ones(Cout, device=dev)
+            nbt = torch.zeros((), dtype=torch.int64, device=dev)
+            y = cuda_ops.conv_bn_act(xs, ws, 1, pad, 1, bws, bbs, rm, rv, nbt, training=True, momentum=0.1, eps=1e-5,
+                                     act=act, lab_scale=ls, lab_bias=lb, pre_add=None, post_add=p2)
+            y.backward(dy)
+            torch.cuda.synchronize()
+            return [t.detach().clone() for t in (y, rm, rv, xs.grad, ws.grad, bws.grad, bbs.grad)]
+        finally:
+            co._BN_FIN, co._BN_APPLY = old
+
+    base = run(False, False)
+    for mode in ((True, False), (True, True)):
+        got = run(*mode)
+        for name, a, b in zip(("y", "running_mean", "running_var", "dx", "dw", "dgamma", "dbeta"), got, base):
+            scale = float(b.abs().max()) + 1e-12
+            # (the gradient kernels accumulate split-K partial sums with fp32 atomics: run-to-run noise of ~1e-6)
+            tol = 2e-6 if name in ("y", "running_mean", "running_var") else 3e-5
+            assert float((a - b).abs().max()) <= tol * scale, (mode, name, float((a - b).abs().max()), scale)
+
+
+@pytest.mark.gpu
+def test_tc_trace_stamps_every_cta(cuda_ops):
+    """dfine_tc_trace: every CTA of the forward kernel writes ordered phase timestamps; a null buffer switches it off."""
+    import ctypes
+    from custom_d_fine_b200 import cuda_ops as co
+    dev = torch.device("cuda", 0)
+    B, H, W, Cin, Cout = 4, 40, 40, 128, 128
+    x, w = torch.randn(B, H, W, Cin, device=dev), torch.randn(Cout, Cin, 1, 1, device=dev) * 0.05
+    y = torch.empty(B, H, W, Cout, device=dev)
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device=dev)
+    buf = torch.zeros(256 * 16, dtype=torch.int64, device=dev)
+    cache = co._WCache()
+    co.lib().dfine_tc_trace(ctypes.c_void_p(buf.data_ptr()))
+    try:
+        co._conv_fwd(x, Cin, w, cache.getter(w), None, y, Cout, (B, H, W, Cin, H, W, Cout, 1, 1, (0, 0, 0, 0)), 0, stats)
+    finally:
+        co.lib().dfine_tc_trace(ctypes.c_void_p(0))
+    torch.cuda.synchronize()
+    t = buf.cpu().view(256, 16)
+    live = t[:, 0] > 0
+    assert int(live.sum()) >= 1
+    for a, b in ((0, 1), (1, 2), (2, 3), (3, 6), (6, 7), (7, 9), (9, 10)):
+        assert bool((t[live, a] <= t[live, b]).all()), (a, b)
+    before = buf.clone()
+    co._conv_fwd(x, Cin, w, cache.getter(w), None, y, Cout, (B, H, W, Cin, H, W, Cout, 1, 1, (0, 0, 0, 0)), 0, stats)
+    torch.cuda.synchronize()
+    assert torch.equal(before, buf)
