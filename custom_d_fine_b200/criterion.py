@@ -130,7 +130,7 @@ class IndexPlan:
     worst case with valid = 0).  Static shapes are what lets the loss + backward segment of the step be
     replayed as a CUDA graph (custom_d_fine_b200/train.py)."""
 
-    def __init__(self, sizes, num_queries, n_sets, dn_positive_idx=None, dn_groups=0):
+    def __init__(self, sizes, num_queries, n_sets, dn_positive_idx=None, dn_groups=0, dn_max_gt=None):
         self.sizes = [int(s) for s in sizes]
         self.Q = int(num_queries)
         self.n_sets = n_sets
@@ -150,8 +150,15 @@ class IndexPlan:
         if self.n_dn:
             # the denoising set depends on the targets' sizes only (dfine_criterion.py:809-831)
             b = np.concatenate([np.full(s * dn_groups, i) for i, s in enumerate(self.sizes)]) if self.n_dn else []
-            q = np.concatenate([np.asarray(p.cpu() if hasattr(p, "cpu") else p).reshape(-1)[: s * dn_groups]
-                                for p, s in zip(dn_positive_idx, self.sizes) if s > 0] or [np.zeros(0)])
+            if dn_max_gt is not None:
+                # the positive denoising queries of image i are g * 2 * max_gt + j (g < groups, j < T_i) by construction
+                # (decoder.make_denoising_group): written down on the host instead of reading the device tensors back
+                # (one D2H synchronisation per image whenever a step needs a new plan)
+                q = np.concatenate([(np.arange(dn_groups)[:, None] * (2 * int(dn_max_gt)) + np.arange(s)[None]).reshape(-1)
+                                    for s in self.sizes if s > 0] or [np.zeros(0)])
+            else:
+                q = np.concatenate([np.asarray(p.cpu() if hasattr(p, "cpu") else p).reshape(-1)[: s * dn_groups]
+                                    for p, s in zip(dn_positive_idx, self.sizes) if s > 0] or [np.zeros(0)])
             t = np.concatenate([np.tile(np.arange(s), dn_groups) + self.offs[i] for i, s in enumerate(self.sizes)])
             self._dn_static = np.stack([b, q, t, np.ones_like(b)]).astype(np.int64)
 
@@ -508,7 +515,7 @@ class DFINECriterion(nn.Module):
         meta = outputs.get("dn_meta") if "dn_outputs" in outputs else None
         if plan is None:
             plan = IndexPlan(sizes, Q, n_sets, meta["dn_positive_idx"] if meta else None,
-                             meta["dn_num_group"] if meta else 0)
+                             meta["dn_num_group"] if meta else 0, meta.get("dn_max_gt") if meta else None)
         out_q, out_t = self.matcher.raw_to_host(raw, plan)
         counts = self.plan_from_host(out_q, out_t, plan)
         if local_counts:

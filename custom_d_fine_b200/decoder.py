@@ -224,14 +224,19 @@ def make_denoising_group(targets, num_classes, num_queries, class_embed, num_den
         return None, None, None, {"dn_positive_idx": None, "dn_num_group": 0, "dn_num_split": [0, num_queries]}
     groups = max(num_denoising // max_gt, 1)
     bs = len(num_gts)
-    cls = torch.full([bs, max_gt], num_classes, dtype=torch.int32, device=device)
-    box = torch.zeros([bs, max_gt, 4], device=device)
-    valid = torch.zeros([bs, max_gt], dtype=torch.bool, device=device)
-    for i, n in enumerate(num_gts):
-        if n > 0:
-            cls[i, :n] = targets[i]["labels"]
-            box[i, :n] = targets[i]["boxes"]
-            valid[i, :n] = True
+    # padded [bs, max_gt] tables: one pad_sequence per field (a C++ loop of slice copies; the per-image Python slice
+    # assignments it replaces were ~100 small host-side calls per step on the uncaptured path)
+    pad = torch.nn.utils.rnn.pad_sequence
+    cls = pad([t["labels"] for t in targets], batch_first=True, padding_value=num_classes).to(torch.int32)
+    box = pad([t["boxes"].to(torch.float32) for t in targets], batch_first=True, padding_value=0.0)
+    if device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+        # (no host -> device copy inside a capture: the table is filled by per-image device writes)
+        valid = torch.zeros([bs, max_gt], dtype=torch.bool, device=device)
+        for i, n in enumerate(num_gts):
+            if n > 0:
+                valid[i, :n] = True
+    else:
+        valid = (torch.arange(max_gt)[None] < torch.tensor(num_gts)[:, None]).to(device)
     cls = cls.tile([1, 2 * groups])
     box = box.tile([1, 2 * groups, 1])
     valid = valid.tile([1, 2 * groups])
@@ -239,7 +244,8 @@ def make_denoising_group(targets, num_classes, num_queries, class_embed, num_den
     pos_in_group = torch.arange(n_dn, device=device) % (2 * max_gt)
     neg = (pos_in_group >= max_gt).to(box.dtype).reshape(1, n_dn, 1)  # second half of each group
     g_idx = torch.arange(groups, device=device)[:, None] * (2 * max_gt)
-    dn_positive_idx = tuple((g_idx + torch.arange(n, device=device)[None]).flatten() for n in num_gts)
+    base = g_idx + torch.arange(max_gt, device=device)[None]
+    dn_positive_idx = tuple(base[:, :n].reshape(-1) for n in num_gts)
 
     if label_noise_ratio > 0:
         flip = torch.rand_like(cls, dtype=torch.float) < (label_noise_ratio * 0.5)
@@ -264,7 +270,8 @@ def make_denoising_group(targets, num_classes, num_queries, class_embed, num_den
     # True = blocked: matching queries never see dn queries; a dn query only sees its own group
     # (and all matching queries).
     mask = is_dn[None, :] & (~is_dn[:, None] | (grp[:, None] != grp[None, :]))
-    meta = {"dn_positive_idx": dn_positive_idx, "dn_num_group": groups, "dn_num_split": [n_dn, num_queries]}
+    meta = {"dn_positive_idx": dn_positive_idx, "dn_num_group": groups, "dn_num_split": [n_dn, num_queries],
+            "dn_max_gt": max_gt}
     return content, box_unact, mask, meta
 
 
