@@ -62,3 +62,31 @@ def test_loss_descriptor_layout_matches_the_library(built_lib):
     assert L.dfine_loss_desc_size() == ctypes.sizeof(loss_desc.LossDesc)
     L.dfine_loss_out_count.restype = ctypes.c_int
     assert L.dfine_loss_out_count(4) == loss_desc.out_count(4)
+
+
+def test_every_kernel_waits_for_its_stream_predecessor(built_lib):
+    """Programmatic dependent launch: every launch of the library carries the stream-serialization attribute (launch_k), so
+    EVERY kernel must execute griddepcontrol.wait (SASS: ACQBULK) before it touches global memory — a kernel without it could
+    start on its predecessor's unfinished output.  Checked on the shipped binary; no launch may bypass launch_k."""
+    import shutil
+    import subprocess
+    csrc = ROOT / "custom_d_fine_b200" / "csrc"
+    for src in csrc.glob("*.cu"):
+        assert "<<<" not in src.read_text(), f"{src.name}: raw <<< >>> launch (use launch_k)"
+    n_kernels = sum(len(re.findall(r"__global__", s.read_text())) for s in csrc.glob("*.cu"))
+    n_entries = sum(len(re.findall(r"^\s*pdl_entry\(\);", s.read_text(), flags=re.M)) for s in csrc.glob("*.cu"))
+    assert n_kernels == n_entries > 50, (n_kernels, n_entries)
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", str(built_lib)], capture_output=True, text=True, check=True).stdout
+    cur, waits = None, {}
+    for line in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            waits[cur] = 0
+        elif cur and re.search(r"\bACQBULK\b", line):
+            waits[cur] += 1
+    assert len(waits) > 100
+    missing = [k for k, v in waits.items() if v == 0]
+    assert not missing, missing[:5]
