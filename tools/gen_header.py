@@ -15,7 +15,8 @@ GROUPS = [
     ("lib.cu", "Library", "Error convention: every entry point returns 0 on success, a positive cudaError_t from the\n"
      " * launch, or a negative value for an argument / shape / alignment violation; dfine_last_error() returns a\n"
      " * thread-local description.  The library never allocates or frees device memory, never synchronises the\n"
-     " * device and keeps no mutable global state besides immutable per-process caches; all entry points are\n"
+     " * device and keeps no mutable global state besides immutable per-process caches (and the bring-up trace\n"
+     " * pointer of dfine_tc_trace, null unless a profiling tool sets it); all entry points are\n"
      " * re-entrant (autograd calls backward kernels from another host thread).  `stream` is a cudaStream_t."),
     ("gemm_tc.cu", "tcgen05 implicit-GEMM convolution / linear (tensor cores, TMA, TMEM)",
      "Replaces cuDNN/cuBLAS behind nn.Conv2d (hgnetv2.py:53-64, hybrid_encoder.py:25-27,86-88) and nn.Linear\n"
