@@ -76,6 +76,15 @@ def test_every_kernel_waits_for_its_stream_predecessor(built_lib):
     n_kernels = sum(len(re.findall(r"__global__", s.read_text())) for s in csrc.glob("*.cu"))
     n_entries = sum(len(re.findall(r"^\s*pdl_entry\(\);", s.read_text(), flags=re.M)) for s in csrc.glob("*.cu"))
     assert n_kernels == n_entries > 50, (n_kernels, n_entries)
+    # ... as the FIRST statement of the kernel (the tcgen05 kernels run their shared-memory / tensor-memory prologue first)
+    for src in csrc.glob("*.cu"):
+        text = src.read_text()
+        for m in re.finditer(r"__global__", text):
+            head = text[m.start():m.start() + 1500]
+            body = head[head.index("{", head.index(")" + " {") if ")" + " {" in head else 0) + 1:]
+            name = re.search(r"(\w+)\s*\(", re.sub(r"__launch_bounds__\([^)]*\)(, \d+\))?|__cluster_dims__\([^)]*\)", "", head)).group(1)
+            if not name.startswith("tc_"):
+                assert body.lstrip().startswith("pdl_entry();"), (src.name, name)
     if shutil.which("cuobjdump") is None:
         pytest.skip("cuobjdump not on PATH")
     sass = subprocess.run(["cuobjdump", "-sass", str(built_lib)], capture_output=True, text=True, check=True).stdout
